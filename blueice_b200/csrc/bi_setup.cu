@@ -1,0 +1,173 @@
+// blueice_b200 -- K1: per-point anchor-grid morphing set-up (cells, corner weights, scaled rates).
+//
+// One thread per parameter point.  All arithmetic that the reference performs in NumPy/SciPy with
+// separately rounded multiplies and adds is done here with __dmul_rn/__dadd_rn (no FMA contraction),
+// so cells, fractions, weights and mus are BIT-IDENTICAL to the reference:
+//   find_indices / _evaluate_linear            scipy/interpolate/_rgi.py:520-549
+//   mus = itp(zs)[0]                           blueice/pdf_morphers.py:70, likelihood.py:355
+//   mus[s] *= mult; mus *= lt; mus[eff] *= e   blueice/likelihood.py:366-393
+//   unphysical-rate test                       blueice/likelihood.py:397-415
+//   mu.sum()                                   numpy pairwise sum (n < 8 sequential; n <= 128 eight lanes)
+#include "bi_common.cuh"
+
+struct BiAllowNegative { uint8_t flag[BI_MAX_SOURCES]; int32_t any; };
+
+__device__ __forceinline__ double bi_numpy_sum_small(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = a[k];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], a[i + k]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+__global__ void __launch_bounds__(128)
+k_point_setup(const __grid_constant__ BiGrid grid, int n_sources, int64_t n_points,
+              const double* __restrict__ zs, const double* __restrict__ rate_mult,
+              const double* __restrict__ scale, const double* __restrict__ eff,
+              const double* __restrict__ mus_anchor, const __grid_constant__ BiAllowNegative allow,
+              int32_t* __restrict__ cell_out, double* __restrict__ frac_out,
+              int32_t* __restrict__ corner_out, double* __restrict__ weight_out,
+              double* __restrict__ mus_out, double* __restrict__ musum_out,
+              int32_t* __restrict__ status_out) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_points) return;
+    const int D = grid.n_dims, C = grid.n_corners, S = n_sources;
+    int status = BI_POINT_OK;
+
+    int cell[BI_MAX_DIMS];
+    double frac[BI_MAX_DIMS];
+    for (int d = 0; d < D; ++d) {
+        const double* axis = grid.axes + grid.axis_offset[d];
+        const int n = grid.n_anchors[d];
+        const double z = zs[p * D + d];
+        // likelihood.py:345-346: `if not minbound <= z <= maxbound: return -inf` (NaN fails)
+        if (!(axis[0] <= z && z <= axis[n - 1])) status |= BI_POINT_OUT_OF_RANGE;
+        int c; double y;
+        if (n == 1) { c = -1; y = 0.0; }
+        else {
+            c = bi_upper_bound(axis, n, z) - 1;
+            c = c < 0 ? 0 : (c > n - 2 ? n - 2 : c);
+            y = __ddiv_rn(__dsub_rn(z, axis[c]), __dsub_rn(axis[c + 1], axis[c]));
+        }
+        cell[d] = c; frac[d] = y;
+        cell_out[p * D + d] = c;
+        frac_out[p * D + d] = y;
+    }
+
+    // corners, first dim slowest (itertools.product order), weight = ((1*t_0)*t_1)*...
+    for (int c = 0; c < C; ++c) {
+        double w = 1.0;
+        int flat = 0;
+        for (int d = 0; d < D; ++d) {
+            const int bit = (c >> (D - 1 - d)) & 1;
+            const double t = bit ? frac[d] : __dsub_rn(1.0, frac[d]);
+            w = __dmul_rn(w, t);
+            int idx = cell[d] + bit;
+            if (idx < 0) idx += grid.n_anchors[d];   // one-point axis: index -1 aliases the last (= only) anchor
+            flat += idx * grid.stride[d];
+        }
+        corner_out[p * C + c] = flat;
+        weight_out[p * C + c] = w;
+    }
+
+    // mus: value = 0; value = value + M[corner] * weight   (then the three in-place scalings)
+    double mu_local[BI_MAX_SOURCES];
+    for (int s = 0; s < S; ++s) {
+        double acc;
+        if (D == 0) {
+            acc = mus_anchor[s];
+        } else {
+            acc = 0.0;
+            for (int c = 0; c < C; ++c)
+                acc = __dadd_rn(acc, __dmul_rn(mus_anchor[(int64_t)corner_out[p * C + c] * S + s],
+                                               weight_out[p * C + c]));
+        }
+        acc = __dmul_rn(acc, rate_mult[p * S + s]);
+        if (scale) acc = __dmul_rn(acc, scale[p]);
+        if (eff) acc = __dmul_rn(acc, eff[p * S + s]);
+        mu_local[s] = acc;
+        mus_out[p * S + s] = acc;
+    }
+    const double musum = bi_numpy_sum_small(mu_local, S);
+    musum_out[p] = musum;
+
+    // likelihood.py:397-415
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    bool bad = false;
+    if (!allow.any) {
+        for (int s = 0; s < S; ++s) bad |= !((mu_local[s] >= 0.0) && (mu_local[s] < inf));
+    } else {
+        bool any_finite = false;
+        for (int s = 0; s < S; ++s) any_finite |= (mu_local[s] < inf);
+        if (!any_finite || (musum < 0.0)) bad = true;
+        for (int s = 0; s < S; ++s)
+            if (!(0.0 <= mu_local[s]) && !allow.flag[s]) bad = true;
+    }
+    if (bad) status |= BI_POINT_UNPHYSICAL;
+    status_out[p] = status;
+}
+
+int bi_fill_grid(BiGrid* g, int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host) {
+    BI_REQUIRE(n_dims >= 0 && n_dims <= BI_MAX_DIMS, "n_dims=%d outside [0,%d]", n_dims, BI_MAX_DIMS);
+    BI_REQUIRE(n_dims == 0 || (n_anchors_host && axes_host), "anchor grid pointers are NULL");
+    memset(g, 0, sizeof(BiGrid));
+    g->n_dims = n_dims;
+    g->n_corners = 1 << n_dims;
+    int total = 0;
+    for (int d = 0; d < n_dims; ++d) {
+        BI_REQUIRE(n_anchors_host[d] >= 1, "dimension %d has %d anchors", d, n_anchors_host[d]);
+        g->n_anchors[d] = n_anchors_host[d];
+        g->axis_offset[d] = total;
+        total += n_anchors_host[d];
+    }
+    BI_REQUIRE(total <= BI_MAX_AXIS_POINTS, "sum of anchors per dim = %d exceeds %d", total, BI_MAX_AXIS_POINTS);
+    int stride = 1;
+    for (int d = n_dims - 1; d >= 0; --d) { g->stride[d] = stride; stride *= n_anchors_host[d]; }
+    for (int i = 0; i < total; ++i) g->axes[i] = axes_host[i];
+    for (int d = 0; d < n_dims; ++d)
+        for (int i = 1; i < g->n_anchors[d]; ++i)
+            BI_REQUIRE(g->axes[g->axis_offset[d] + i] > g->axes[g->axis_offset[d] + i - 1],
+                       "anchor axis %d is not strictly increasing", d);
+    return BI_OK;
+}
+
+extern "C" int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                              int32_t n_sources, int64_t n_points,
+                              const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                              const double* eff_dev, const double* mus_anchor_dev,
+                              const uint8_t* allow_negative_host,
+                              int32_t* cell_dev, double* frac_dev, int32_t* corner_dev, double* weight_dev,
+                              double* mus_dev, double* musum_dev, int32_t* status_dev, void* stream) {
+    BiGrid grid;
+    int rc = bi_fill_grid(&grid, n_dims, n_anchors_host, axes_host);
+    if (rc != BI_OK) return rc;
+    BI_REQUIRE(n_sources >= 1 && n_sources <= BI_MAX_SOURCES, "n_sources=%d outside [1,%d]", n_sources, BI_MAX_SOURCES);
+    BI_REQUIRE(n_points >= 0, "n_points < 0");
+    if (n_points == 0) return BI_OK;
+    BI_REQUIRE(rate_mult_dev && mus_anchor_dev && corner_dev && weight_dev && mus_dev && musum_dev && status_dev,
+               "bi_point_setup: NULL device pointer");
+    BI_REQUIRE(n_dims == 0 || (zs_dev && cell_dev && frac_dev), "bi_point_setup: NULL zs/cell/frac pointer");
+    BiAllowNegative allow;
+    memset(&allow, 0, sizeof(allow));
+    if (allow_negative_host)
+        for (int s = 0; s < n_sources; ++s) { allow.flag[s] = allow_negative_host[s] ? 1 : 0; allow.any |= allow.flag[s]; }
+    const int threads = 128;
+    const int64_t blocks = (n_points + threads - 1) / threads;
+    k_point_setup<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        grid, n_sources, n_points, zs_dev, rate_mult_dev, scale_dev, eff_dev, mus_anchor_dev, allow,
+        cell_dev, frac_dev, corner_dev, weight_dev, mus_dev, musum_dev, status_dev);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}

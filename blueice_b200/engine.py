@@ -1,0 +1,525 @@
+"""Device engine: owns HBM-resident anchor tensors and drives the C-ABI kernels.
+
+PyTorch is used here only for device memory, pinned staging buffers and streams.  All numerics
+run in blueice_b200/csrc (hand-written sm_100a CUDA) through blueice_b200._cabi; there is no CPU
+fallback -- constructing an engine without a CUDA device raises.
+
+Layout in HBM:
+    mus_anchor  [G, S]            float64   expected events at every anchor, anchors in C order
+    ps_anchor   [G, S, ld]        float64   per-event pdf values (unbinned) or pmf per bin (binned),
+                                            ld = N rounded up to a multiple of 64, padding zeroed
+Per batch of P points (workspace, reused between calls):
+    zs [P, D], mult [P, S], scale [P], eff [P, S] -> cell [P, D], frac [P, D], corner [P, C],
+    weight [P, C], mus [P, S], musum [P], status [P], partial [P, n_super], logl [P]
+"""
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+
+_LD_ALIGN = 64
+_GROUP_MIN_POINTS = 16          # cells with at least this many points use the grouped kernel
+_GROUP_TARGET_ITEMS = 148 * 8   # aim for a few CTAs per SM
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("blueice_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _cabi.load()
+    return torch
+
+
+def round_up(n, m):
+    return ((int(n) + m - 1) // m) * m
+
+
+class MorphGrid(object):
+    """Host description of the regular anchor grid (pdf_morphers.py:45-50)."""
+
+    def __init__(self, axes):
+        self.axes = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in axes]
+        self.n_dims = len(self.axes)
+        if self.n_dims > _cabi.MAX_DIMS:
+            raise ValueError("at most %d shape parameters per morph grid are supported" % _cabi.MAX_DIMS)
+        self.shape = tuple(len(a) for a in self.axes)
+        self.n_anchors = int(np.prod(self.shape)) if self.n_dims else 1
+        self.n_corners = 1 << self.n_dims
+        self.n_anchors_i32 = _cabi.as_i32(self.shape if self.n_dims else [0])
+        self.axes_concat = _cabi.as_f64(np.concatenate(self.axes) if self.n_dims else [0.0])
+        if self.axes_concat.size > _cabi.MAX_AXIS_POINTS:
+            raise ValueError("too many anchor values in total (max %d)" % _cabi.MAX_AXIS_POINTS)
+        # number of hypercube cells per dim (a one-point axis has a single degenerate cell)
+        self.cells_per_dim = [max(n - 1, 1) for n in self.shape]
+
+    def in_range(self, zs):
+        """likelihood.py:345-347: min(anchor) <= z <= max(anchor) for every dim; NaN fails."""
+        zs = np.asarray(zs, dtype=np.float64).reshape(-1, self.n_dims)
+        ok = np.ones(len(zs), dtype=bool)
+        with np.errstate(invalid='ignore'):
+            for d, a in enumerate(self.axes):
+                ok &= (a[0] <= zs[:, d]) & (zs[:, d] <= a[-1])
+        return ok
+
+    def cell_ids(self, zs):
+        """Flat hypercube-cell id per point (host copy of the device rule, used only for bucketing)."""
+        zs = np.asarray(zs, dtype=np.float64).reshape(-1, self.n_dims)
+        flat = np.zeros(len(zs), dtype=np.int64)
+        for d, a in enumerate(self.axes):
+            n = len(a)
+            if n == 1:
+                c = np.zeros(len(zs), dtype=np.int64)
+            else:
+                c = np.clip(np.searchsorted(a, zs[:, d], side='right') - 1, 0, n - 2)
+            flat = flat * self.cells_per_dim[d] + c
+        return flat
+
+
+class _Workspace(object):
+    """Per-batch device buffers + one pinned staging buffer each way, grown on demand."""
+
+    def __init__(self, torch, device):
+        self.torch = torch
+        self.device = device
+        self.capacity = {}
+        self.buf = {}
+
+    def get(self, name, n, dtype, pinned=False):
+        n = max(int(n), 1)
+        key = (name, dtype, pinned)
+        if self.capacity.get(key, 0) < n:
+            cap = max(n, int(self.capacity.get(key, 0) * 1.5))
+            if pinned:
+                self.buf[key] = self.torch.empty(cap, dtype=dtype, pin_memory=True)
+            else:
+                self.buf[key] = self.torch.empty(cap, dtype=dtype, device=self.device)
+            self.capacity[key] = cap
+        return self.buf[key][:n]
+
+
+class PointPlan(object):
+    """Host-side schedule of a batch: which points go to which kernel (results do not depend on it)."""
+
+    def __init__(self, n_points, in_range, stream_points, group_points, work):
+        self.n_points = n_points
+        self.in_range = in_range
+        self.stream_points = stream_points      # int32 [n_stream]
+        self.group_points = group_points        # int32 [n_grouped]
+        self.work = work                        # int32 [n_work, 4]
+
+
+class _EngineBase(object):
+    def __init__(self, grid, mus_anchor, allow_negative=None, device=None):
+        torch = require_cuda()
+        self.torch = torch
+        self.lib = _cabi.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.grid = grid
+        mus_anchor = np.ascontiguousarray(np.asarray(mus_anchor, dtype=np.float64)).reshape(grid.n_anchors, -1)
+        self.n_sources = mus_anchor.shape[1]
+        if self.n_sources > _cabi.MAX_SOURCES:
+            raise ValueError("at most %d sources are supported" % _cabi.MAX_SOURCES)
+        self.mus_anchor_host = mus_anchor
+        self.mus_anchor = torch.from_numpy(mus_anchor).to(self.device)
+        if allow_negative is not None and any(allow_negative):
+            self.allow_negative = np.ascontiguousarray(np.asarray(allow_negative, dtype=np.uint8))
+        else:
+            self.allow_negative = None
+        self.ws = _Workspace(torch, self.device)
+        self.launches = 0          # number of kernel launches issued by this engine (for bench.py)
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _upload_points(self, zs, mult, scale, eff):
+        """One pinned staging buffer, one H2D copy.  Returns device views (zs, mult, scale, eff)."""
+        torch = self.torch
+        P = len(mult)
+        D, S = self.grid.n_dims, self.n_sources
+        n_scale = P if scale is not None else 0
+        n_eff = P * S if eff is not None else 0
+        total = P * D + P * S + n_scale + n_eff
+        pin = self.ws.get("h2d", total, torch.float64, pinned=True)
+        pin_np = pin.numpy()
+        o = 0
+        pin_np[o:o + P * D] = np.asarray(zs, dtype=np.float64).reshape(-1); o += P * D
+        pin_np[o:o + P * S] = np.asarray(mult, dtype=np.float64).reshape(-1); o += P * S
+        if n_scale:
+            pin_np[o:o + P] = np.asarray(scale, dtype=np.float64).reshape(-1); o += P
+        if n_eff:
+            pin_np[o:o + P * S] = np.asarray(eff, dtype=np.float64).reshape(-1); o += P * S
+        dev = self.ws.get("points_in", total, torch.float64)
+        dev.copy_(pin, non_blocking=True)
+        o = 0
+        zs_d = dev[o:o + P * D]; o += P * D
+        mult_d = dev[o:o + P * S]; o += P * S
+        scale_d = dev[o:o + P] if n_scale else None; o += n_scale
+        eff_d = dev[o:o + P * S] if n_eff else None
+        return zs_d, mult_d, scale_d, eff_d, total * 8
+
+    def _setup(self, P, zs_d, mult_d, scale_d, eff_d):
+        """K1: bi_point_setup on device-resident inputs.  Returns the dict of device outputs."""
+        torch = self.torch
+        D, S, C = self.grid.n_dims, self.n_sources, self.grid.n_corners
+        out = dict(
+            cell=self.ws.get("cell", P * max(D, 1), torch.int32),
+            frac=self.ws.get("frac", P * max(D, 1), torch.float64),
+            corner=self.ws.get("corner", P * C, torch.int32),
+            weight=self.ws.get("weight", P * C, torch.float64),
+            mus=self.ws.get("mus", P * S, torch.float64),
+            musum=self.ws.get("musum", P, torch.float64),
+            status=self.ws.get("status", P, torch.int32),
+        )
+        rc = self.lib.bi_point_setup(
+            D, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat), S, P,
+            _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
+            _cabi.dev_ptr(self.mus_anchor), _cabi.host_ptr(self.allow_negative),
+            _cabi.dev_ptr(out["cell"]), _cabi.dev_ptr(out["frac"]), _cabi.dev_ptr(out["corner"]),
+            _cabi.dev_ptr(out["weight"]), _cabi.dev_ptr(out["mus"]), _cabi.dev_ptr(out["musum"]),
+            _cabi.dev_ptr(out["status"]), self._stream())
+        _cabi.check(rc, "bi_point_setup")
+        self.launches += 1
+        return out
+
+    def point_setup_host(self, zs, mult, scale=None, eff=None):
+        """Run K1 and return its outputs as NumPy arrays (index-parity tests, 'error' mode messages)."""
+        P = len(mult)
+        D, S, C = self.grid.n_dims, self.n_sources, self.grid.n_corners
+        zs_d, mult_d, scale_d, eff_d, _ = self._upload_points(zs, mult, scale, eff)
+        o = self._setup(P, zs_d, mult_d, scale_d, eff_d)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return dict(cell=o["cell"].cpu().numpy().reshape(P, max(D, 1))[:, :D],
+                    frac=o["frac"].cpu().numpy().reshape(P, max(D, 1))[:, :D],
+                    corner=o["corner"].cpu().numpy().reshape(P, C),
+                    weight=o["weight"].cpu().numpy().reshape(P, C),
+                    mus=o["mus"].cpu().numpy().reshape(P, S),
+                    musum=o["musum"].cpu().numpy(),
+                    status=o["status"].cpu().numpy())
+
+
+class UnbinnedEngine(_EngineBase):
+    """Fused unbinned likelihood over a device-resident anchor tensor (K1 + K2 + finalize)."""
+
+    def __init__(self, grid, mus_anchor, outlier_likelihood=1e-12, allow_negative=None, device=None):
+        super().__init__(grid, mus_anchor, allow_negative, device)
+        self.outlier_likelihood = float(outlier_likelihood)
+        self.n_events = 0
+        self.ld = 0
+        self.ps_anchor = None
+        self.force_kernel = None      # None (auto) | 'stream' | 'grouped'  (tests / bench)
+
+    # -- set_data -------------------------------------------------------------------------------
+    def allocate_ps_anchor(self, n_events):
+        torch = self.torch
+        self.n_events = int(n_events)
+        self.ld = max(round_up(self.n_events, _LD_ALIGN), _LD_ALIGN)
+        self.ps_anchor = torch.zeros((self.grid.n_anchors, self.n_sources, self.ld), dtype=torch.float64,
+                                     device=self.device)
+        self.n_super = int(self.lib.bi_num_superblocks(self.n_events))
+        return self.ps_anchor
+
+    def set_ps_anchor(self, ps_anchor_host):
+        """ps_anchor_host: [G, S, N] (or [n1..nD, S, N]) float64 computed on the host by Source.pdf."""
+        ps = np.asarray(ps_anchor_host, dtype=np.float64)
+        n = ps.shape[-1]
+        ps = ps.reshape(self.grid.n_anchors, self.n_sources, n)
+        self.allocate_ps_anchor(n)
+        if n:
+            self.ps_anchor[:, :, :n].copy_(self.torch.from_numpy(np.ascontiguousarray(ps)))
+        return self
+
+    def set_rows(self, anchor_index, source_index, values_host):
+        """Upload one [N] row (a Source.pdf result computed on the host)."""
+        v = self.torch.from_numpy(np.ascontiguousarray(np.asarray(values_host, dtype=np.float64)))
+        self.ps_anchor[anchor_index, source_index, :self.n_events].copy_(v)
+
+    def lookup_rows(self, rows, templates_host, edges_list, coords_dev, method):
+        """K3: fill ps_anchor rows [(anchor, source), ...] from histogram templates that share edges.
+
+        templates_host [T, *bins]; coords_dev: torch [n_space, ld_coords] on device.
+        Replaces the G*S calls of HistogramPdfSource.pdf in set_data (likelihood.py:557-560)."""
+        torch = self.torch
+        templates_host = np.ascontiguousarray(np.asarray(templates_host, dtype=np.float64))
+        T = templates_host.shape[0]
+        n_bins = _cabi.as_i32([len(e) - 1 for e in edges_list])
+        edges = _cabi.as_f64(np.concatenate([np.asarray(e, dtype=np.float64) for e in edges_list]))
+        tmpl = torch.from_numpy(templates_host.reshape(T, -1)).to(self.device)
+        out = torch.empty((T, self.ld), dtype=torch.float64, device=self.device)
+        rc = self.lib.bi_hist_lookup(_cabi.dev_ptr(tmpl), T, len(edges_list), _cabi.host_ptr(n_bins),
+                                     _cabi.host_ptr(edges), _cabi.dev_ptr(coords_dev), coords_dev.shape[1],
+                                     self.n_events, method, _cabi.dev_ptr(out), self.ld, None, self._stream())
+        _cabi.check(rc, "bi_hist_lookup")
+        self.launches += 1
+        idx = torch.as_tensor([a * self.n_sources + s for a, s in rows], device=self.device, dtype=torch.int64)
+        flat = self.ps_anchor.view(self.grid.n_anchors * self.n_sources, self.ld)
+        if self.ld > self.n_events:
+            out[:, self.n_events:] = 0.0
+        flat.index_copy_(0, idx, out)
+
+    # -- planning (host) ------------------------------------------------------------------------
+    def plan(self, zs):
+        """Bucket points by hypercube cell and split the work between the two K2 kernels."""
+        P = len(zs)
+        grid = self.grid
+        in_range = grid.in_range(zs) if grid.n_dims else np.ones(P, dtype=bool)
+        idx = np.nonzero(in_range)[0]
+        can_group = (self.n_sources <= _cabi.GROUP_MAX_SOURCES and grid.n_corners <= _cabi.GROUP_MAX_CORNERS
+                     and self.n_super > 0 and self.force_kernel != 'stream')
+        stream_pts = idx
+        group_pts = np.zeros(0, dtype=np.int64)
+        work = np.zeros((0, 4), dtype=np.int32)
+        min_pts = 1 if self.force_kernel == 'grouped' else _GROUP_MIN_POINTS
+        if can_group and len(idx) >= min_pts:
+            cells = grid.cell_ids(np.asarray(zs, dtype=np.float64).reshape(P, grid.n_dims)[idx]) if grid.n_dims \
+                else np.zeros(len(idx), dtype=np.int64)
+            order = np.argsort(cells, kind='stable')
+            sorted_cells = cells[order]
+            sorted_idx = idx[order]
+            starts = np.flatnonzero(np.r_[True, sorted_cells[1:] != sorted_cells[:-1]])
+            ends = np.r_[starts[1:], len(sorted_cells)]
+            big = (ends - starts) >= min_pts
+            chunks = []
+            keep = np.zeros(len(sorted_idx), dtype=bool)
+            for s0, e0 in zip(starts[big], ends[big]):
+                keep[s0:e0] = True
+            group_pts = sorted_idx[keep]
+            stream_pts = np.sort(sorted_idx[~keep])
+            # positions of the kept runs inside group_pts
+            pos = 0
+            for s0, e0 in zip(starts[big], ends[big]):
+                n = e0 - s0
+                for c0 in range(0, n, _cabi.GROUP_POINTS):
+                    chunks.append((pos + c0, min(_cabi.GROUP_POINTS, n - c0)))
+                pos += n
+            if chunks:
+                n_ranges = int(np.clip(_GROUP_TARGET_ITEMS // len(chunks), 1, self.n_super))
+                sb_per = -(-self.n_super // n_ranges)
+                sb_begin = np.arange(0, self.n_super, sb_per, dtype=np.int64)
+                sb_end = np.minimum(sb_begin + sb_per, self.n_super)
+                ch = np.asarray(chunks, dtype=np.int64)
+                work = np.empty((len(ch) * len(sb_begin), 4), dtype=np.int32)
+                work[:, 0] = np.repeat(ch[:, 0], len(sb_begin))
+                work[:, 1] = np.repeat(ch[:, 1], len(sb_begin))
+                work[:, 2] = np.tile(sb_begin, len(ch))
+                work[:, 3] = np.tile(sb_end, len(ch))
+        return PointPlan(P, in_range, stream_pts.astype(np.int32), group_pts.astype(np.int32), work)
+
+    def upload_plan(self, plan):
+        """H2D of the schedule (one pinned buffer).  Returns device views + byte count."""
+        torch = self.torch
+        n_s, n_g, n_w = len(plan.stream_points), len(plan.group_points), len(plan.work)
+        off_g = round_up(n_s, 4)
+        off_w = off_g + round_up(n_g, 4)
+        total = off_w + 4 * n_w
+        pin = self.ws.get("plan_h", total, torch.int32, pinned=True)
+        pn = pin.numpy()
+        pn[:n_s] = plan.stream_points
+        pn[off_g:off_g + n_g] = plan.group_points
+        pn[off_w:off_w + 4 * n_w] = plan.work.reshape(-1)
+        dev = self.ws.get("plan_d", total, torch.int32)
+        dev.copy_(pin, non_blocking=True)
+        return (dev[:n_s] if n_s else None, dev[off_g:off_g + n_g] if n_g else None,
+                dev[off_w:off_w + 4 * n_w] if n_w else None, total * 4)
+
+    # -- evaluation -----------------------------------------------------------------------------
+    def run_device(self, P, zs_d, mult_d, scale_d, eff_d, plan, plan_dev, want_setup=False):
+        """Device-only part: K1 -> K2 (stream and/or grouped) -> finalize.  Returns logl (device)."""
+        torch = self.torch
+        if self.ps_anchor is None:
+            raise RuntimeError("set_ps_anchor / allocate_ps_anchor must be called first")
+        S, C = self.n_sources, self.grid.n_corners
+        o = self._setup(P, zs_d, mult_d, scale_d, eff_d)
+        partial = self.ws.get("partial", P * max(self.n_super, 1), torch.float64)
+        stream_d, group_d, work_d = plan_dev
+        st = self._stream()
+        if self.n_super > 0 and len(plan.stream_points):
+            rc = self.lib.bi_unbinned_partials_stream(
+                _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, S, C, _cabi.dev_ptr(stream_d),
+                len(plan.stream_points), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),
+                _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]), self.outlier_likelihood,
+                _cabi.dev_ptr(partial), st)
+            _cabi.check(rc, "bi_unbinned_partials_stream")
+            self.launches += 1
+        if self.n_super > 0 and len(plan.work):
+            rc = self.lib.bi_unbinned_partials_grouped(
+                _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, S, C, _cabi.dev_ptr(group_d),
+                _cabi.dev_ptr(work_d), len(plan.work), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),
+                _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]), self.outlier_likelihood,
+                _cabi.dev_ptr(partial), st)
+            _cabi.check(rc, "bi_unbinned_partials_grouped")
+            self.launches += 1
+        logl = self.ws.get("logl", P, torch.float64)
+        rc = self.lib.bi_unbinned_finalize(_cabi.dev_ptr(partial), self.n_super, _cabi.dev_ptr(o["musum"]),
+                                           _cabi.dev_ptr(o["status"]), P, _cabi.dev_ptr(logl), st)
+        _cabi.check(rc, "bi_unbinned_finalize")
+        self.launches += 1
+        if want_setup:
+            return logl, o
+        return logl
+
+    def evaluate(self, zs, mult, scale=None, eff=None, return_status=False):
+        """Host buffers in, host buffers out (the e2e path): H2D, K1, K2, finalize, D2H."""
+        torch = self.torch
+        P = len(mult)
+        if P == 0:
+            return (np.zeros(0), np.zeros(0, dtype=np.int32)) if return_status else np.zeros(0)
+        zs = np.asarray(zs, dtype=np.float64).reshape(P, self.grid.n_dims)
+        plan = self.plan(zs)
+        zs_d, mult_d, scale_d, eff_d, nbytes = self._upload_points(zs, mult, scale, eff)
+        plan_dev = self.upload_plan(plan)
+        logl, o = self.run_device(P, zs_d, mult_d, scale_d, eff_d, plan, plan_dev[:3], want_setup=True)
+        out_pin = self.ws.get("d2h", P, torch.float64, pinned=True)
+        out_pin.copy_(logl, non_blocking=True)
+        st_pin = self.ws.get("d2h_status", P, torch.int32, pinned=True)
+        st_pin.copy_(o["status"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.last_h2d_bytes = nbytes + plan_dev[3]
+        self.last_d2h_bytes = P * 12
+        res = out_pin.numpy().copy()
+        if return_status:
+            return res, st_pin.numpy().copy()
+        return res
+
+    def ps(self, z_row, mult_row, scale=None, eff=None):
+        """(mus [S], ps [S, N]) for one point in the reference's operation order (full_output=True)."""
+        torch = self.torch
+        S, C = self.n_sources, self.grid.n_corners
+        zs_d, mult_d, scale_d, eff_d, _ = self._upload_points(np.asarray(z_row, dtype=np.float64).reshape(1, -1),
+                                                              np.asarray(mult_row, dtype=np.float64).reshape(1, -1),
+                                                              None if scale is None else [scale],
+                                                              None if eff is None else np.asarray(eff).reshape(1, -1))
+        o = self._setup(1, zs_d, mult_d, scale_d, eff_d)
+        out = torch.empty((S, max(self.n_events, 1)), dtype=torch.float64, device=self.device)
+        rc = self.lib.bi_unbinned_ps(_cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, S, C,
+                                     _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]), _cabi.dev_ptr(out),
+                                     out.shape[1], self._stream())
+        _cabi.check(rc, "bi_unbinned_ps")
+        self.launches += 1
+        return o["mus"].cpu().numpy().copy(), out[:, :self.n_events].cpu().numpy()
+
+
+class BinnedEngine(_EngineBase):
+    """Binned Poisson likelihood with optional Beeston-Barlow over device-resident pmf tensors (K1 + K4)."""
+
+    def __init__(self, grid, mus_anchor, pmf_anchor, n_model_anchor=None, bb_source=None, device=None):
+        super().__init__(grid, mus_anchor, None, device)
+        torch = self.torch
+        pmf = np.asarray(pmf_anchor, dtype=np.float64)
+        self.bin_shape = pmf.shape[grid.n_dims + 1:] if grid.n_dims else pmf.shape[1:]
+        self.n_bins = int(np.prod(self.bin_shape))
+        pmf = pmf.reshape(grid.n_anchors, self.n_sources, self.n_bins)
+        self.ld = round_up(self.n_bins, _LD_ALIGN)
+        self.pmf_anchor = torch.zeros((grid.n_anchors, self.n_sources, self.ld), dtype=torch.float64, device=self.device)
+        self.pmf_anchor[:, :, :self.n_bins].copy_(torch.from_numpy(np.ascontiguousarray(pmf)))
+        self.bb_source = -1 if bb_source is None else int(bb_source)
+        self.nm_anchor = None
+        self.nm_sum_anchor = None
+        if self.bb_source >= 0:
+            nm = np.asarray(n_model_anchor, dtype=np.float64).reshape(grid.n_anchors, self.n_sources, self.n_bins)
+            nm_i = np.ascontiguousarray(nm[:, self.bb_source, :])
+            self.nm_anchor = torch.zeros((grid.n_anchors, self.ld), dtype=torch.float64, device=self.device)
+            self.nm_anchor[:, :self.n_bins].copy_(torch.from_numpy(nm_i))
+            # per-anchor sum over bins in NumPy's own (pairwise) order
+            self.nm_sum_anchor = torch.from_numpy(np.ascontiguousarray(nm_i.sum(axis=1))).to(self.device)
+        self.observed = None
+        self.lgamma_obs = None
+        self.n_chunks = int(self.lib.bi_num_superblocks(self.n_bins))
+
+    def set_observed(self, observed_host):
+        from scipy.special import gammaln
+        torch = self.torch
+        obs = np.ascontiguousarray(np.asarray(observed_host, dtype=np.float64).reshape(-1))
+        assert obs.size == self.n_bins
+        self.observed = torch.from_numpy(obs).to(self.device)
+        self.lgamma_obs = torch.from_numpy(np.ascontiguousarray(gammaln(obs + 1))).to(self.device)
+        return self
+
+    def histogram_events(self, edges_list, coords_host):
+        """np.histogramdd-compatible binning on device (likelihood.py:604-609); returns counts [*bins] on host."""
+        torch = self.torch
+        n_space = len(edges_list)
+        n = len(coords_host[0]) if n_space else 0
+        n_bins = _cabi.as_i32([len(e) - 1 for e in edges_list])
+        edges = _cabi.as_f64(np.concatenate([np.asarray(e, dtype=np.float64) for e in edges_list]))
+        counts = torch.zeros(int(np.prod(n_bins)), dtype=torch.int64, device=self.device)
+        if n:
+            coords = torch.from_numpy(np.ascontiguousarray(np.asarray(coords_host, dtype=np.float64))).to(self.device)
+            rc = self.lib.bi_histogramdd(n_space, _cabi.host_ptr(n_bins), _cabi.host_ptr(edges), _cabi.dev_ptr(coords),
+                                         coords.shape[1], n, _cabi.dev_ptr(counts), None, self._stream())
+            _cabi.check(rc, "bi_histogramdd")
+            self.launches += 1
+        return counts.cpu().numpy().astype(np.float64).reshape([int(b) for b in n_bins])
+
+    def run_device(self, P, zs_d, mult_d, scale_d, eff_d, want_all=False):
+        torch = self.torch
+        if self.observed is None:
+            raise RuntimeError("set_observed must be called first")
+        S, C = self.n_sources, self.grid.n_corners
+        o = self._setup(P, zs_d, mult_d, scale_d, eff_d)
+        n_scratch = int(self.lib.bi_binned_scratch_doubles(P, self.n_bins))
+        scratch = self.ws.get("scratch", n_scratch, torch.float64)
+        logl = self.ws.get("logl", P, torch.float64)
+        mus_adj = self.ws.get("mus_adj", P * S, torch.float64)
+        flags = self.ws.get("flags", P, torch.int32)
+        rc = self.lib.bi_binned_ll_batch(
+            _cabi.dev_ptr(self.pmf_anchor), _cabi.dev_ptr(self.nm_anchor), _cabi.dev_ptr(self.nm_sum_anchor),
+            self.ld, self.n_bins, S, C, self.bb_source, _cabi.dev_ptr(self.observed), _cabi.dev_ptr(self.lgamma_obs),
+            _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]), _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]),
+            P, _cabi.dev_ptr(scratch), _cabi.dev_ptr(logl), _cabi.dev_ptr(mus_adj), _cabi.dev_ptr(flags), self._stream())
+        _cabi.check(rc, "bi_binned_ll_batch")
+        self.launches += 5 if self.bb_source >= 0 else 3
+        if want_all:
+            return logl, o, mus_adj, flags, scratch
+        return logl
+
+    def evaluate(self, zs, mult, scale=None, eff=None, return_status=False):
+        """Host in / host out.  Returns logl [P] (+ status [P], bb flags [P])."""
+        torch = self.torch
+        P = len(mult)
+        if P == 0:
+            z = np.zeros(0)
+            return (z, z.astype(np.int32), z.astype(np.int32)) if return_status else z
+        zs = np.asarray(zs, dtype=np.float64).reshape(P, self.grid.n_dims)
+        zs_d, mult_d, scale_d, eff_d, nbytes = self._upload_points(zs, mult, scale, eff)
+        logl, o, mus_adj, flags, _ = self.run_device(P, zs_d, mult_d, scale_d, eff_d, want_all=True)
+        out_pin = self.ws.get("d2h", P, torch.float64, pinned=True)
+        out_pin.copy_(logl, non_blocking=True)
+        st_pin = self.ws.get("d2h_status", 2 * P, torch.int32, pinned=True)
+        st_pin[:P].copy_(o["status"], non_blocking=True)
+        st_pin[P:].copy_(flags, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.last_h2d_bytes = nbytes
+        self.last_d2h_bytes = P * 16
+        res = out_pin.numpy().copy()
+        if return_status:
+            s = st_pin.numpy().copy()
+            return res, s[:P], s[P:]
+        return res
+
+    def pmfs(self, z_row, mult_row, scale=None, eff=None):
+        """(logl, adjusted mus [S], adjusted pmfs [S, *bins], bb flags) for one point (full_output=True)."""
+        torch = self.torch
+        S, C = self.n_sources, self.grid.n_corners
+        zs_d, mult_d, scale_d, eff_d, _ = self._upload_points(np.asarray(z_row, dtype=np.float64).reshape(1, -1),
+                                                              np.asarray(mult_row, dtype=np.float64).reshape(1, -1),
+                                                              None if scale is None else [scale],
+                                                              None if eff is None else np.asarray(eff).reshape(1, -1))
+        logl, o, mus_adj, flags, scratch = self.run_device(1, zs_d, mult_d, scale_d, eff_d, want_all=True)
+        out = torch.empty((S, self.n_bins), dtype=torch.float64, device=self.device)
+        sum_t = scratch[2 * self.n_chunks:2 * self.n_chunks + 1]
+        rc = self.lib.bi_binned_pmfs(
+            _cabi.dev_ptr(self.pmf_anchor), _cabi.dev_ptr(self.nm_anchor), _cabi.dev_ptr(self.nm_sum_anchor),
+            self.ld, self.n_bins, S, C, self.bb_source, _cabi.dev_ptr(self.observed),
+            _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]), _cabi.dev_ptr(o["mus"]),
+            _cabi.dev_ptr(sum_t), _cabi.dev_ptr(out), self.n_bins, self._stream())
+        _cabi.check(rc, "bi_binned_pmfs")
+        self.launches += 1
+        return (float(logl.cpu()[0]), mus_adj[:S].cpu().numpy().copy(),
+                out.cpu().numpy().reshape((S,) + tuple(self.bin_shape)), int(flags.cpu()[0]))

@@ -1,0 +1,789 @@
+"""Log-likelihood constructors with the reference's API, evaluated by sm_100a kernels.
+
+Drop-in surface (blueice/likelihood.py):
+    UnbinnedLogLikelihood / BinnedLogLikelihood(pdf_base_config, likelihood_config=None, **overrides)
+    add_rate_parameter, add_shape_parameter, add_rate_uncertainty, add_shape_uncertainty,
+    prepare(), set_data(d), ll(**params), get_bounds(), the inference methods, and the NEW
+    ll.batch(params_array, names=None, livetime_days=None) -> float64[P]
+    (row p is bit-identical to ll(**dict(zip(names, params_array[p])))).
+
+What runs where
+    host (this file): parameter validation, defaults, bounds -> -inf, priors (arbitrary Python
+        callables), livetime/efficiency factors, 'error'-mode exceptions -- the control flow of
+        LogLikelihoodBase.__call__ (likelihood.py:318-427), vectorised over the batch.
+    device (engine.py -> csrc/): anchor-grid morphing of mus and of the per-event pdf / per-bin pmf
+        tensors, rate scaling, unphysical-rate test, mixture density, log, reduction; binned Poisson
+        with Beeston-Barlow; template lookup and event binning in set_data.
+"""
+from collections import OrderedDict
+from copy import deepcopy
+from functools import wraps
+
+import numpy as np
+from scipy import stats
+
+from . import _cabi
+from . import inference
+from .engine import BinnedEngine, MorphGrid, UnbinnedEngine
+from .exceptions import InvalidParameter, InvalidParameterSpecification, NotPreparedException
+from .hist import Histdd
+from .model import Model
+from .pdf_morphers import MORPHERS
+from .source import HistogramPdfSource
+from .utils import combine_dicts, inherit_docstring_from
+
+__all__ = ['LogLikelihoodBase', 'BinnedLogLikelihood', 'UnbinnedLogLikelihood', 'LogLikelihoodSum',
+           'LogAncillaryLikelihood', 'extended_loglikelihood',
+           'beeston_barlow_root1', 'beeston_barlow_root2', 'beeston_barlow_roots']
+
+_RATE_SUFFIX = '_rate_multiplier'
+_NEG_INF = -float('inf')
+
+
+def _needs_preparation(method):
+    """Auto-prepare when there are no shape parameters, otherwise insist on prepare() (likelihood.py:30-41)."""
+    @wraps(method)
+    def wrapped(self, *args, **kwargs):
+        if not self.is_prepared:
+            if len(self.shape_parameters):
+                raise NotPreparedException("%s requires you to first prepare the likelihood function using prepare()"
+                                           % method.__name__)
+            self.prepare()
+        return method(self, *args, **kwargs)
+    return wrapped
+
+
+def _needs_data(method):
+    @wraps(method)
+    def wrapped(self, *args, **kwargs):
+        if not self.is_data_set:
+            raise NotPreparedException("%s requires you to first set the data using set_data()" % method.__name__)
+        return method(self, *args, **kwargs)
+    return wrapped
+
+
+def _is_number(x):
+    # the reference's test (likelihood.py:285,465,472): np.float64 passes, np.int64 does not
+    return isinstance(x, (float, int))
+
+
+class LogLikelihoodBase(object):
+    """Log likelihood function with several rate and/or shape parameters.
+
+    likelihood_config options: morpher, morpher_config, unphysical_behaviour ('error' or None),
+    outlier_likelihood (default 1e-12), model_statistical_uncertainty_handling, bb_single_source.
+    """
+
+    def __init__(self, pdf_base_config, likelihood_config=None, **kwargs):
+        self.pdf_base_config = combine_dicts(pdf_base_config, kwargs, deep_copy=True)
+        self.config = {} if likelihood_config is None else likelihood_config   # kept by reference (likelihood.py:74)
+        self.config.setdefault('morpher', 'GridInterpolator')
+        self.source_wise_interpolation = self.pdf_base_config.get('source_wise_interpolation', False)
+
+        self.base_model = Model(self.pdf_base_config)
+        sources = self.base_model.sources
+        self.source_name_list = [s.name for s in sources]
+        self.source_allowed_negative = [s.config.get("allow_negative", False) for s in sources]
+        self.source_apply_efficiency = np.array([s.config.get("apply_efficiency", False) for s in sources])
+        self.source_efficiency_names = np.array([s.config.get("efficiency_name", "efficiency") for s in sources])
+
+        self.rate_parameters = OrderedDict()     # source name -> log prior (or None)
+        self.shape_parameters = OrderedDict()    # setting name -> (anchors {z: setting}, log prior, base z)
+        self.is_prepared = False
+        self.is_data_set = False
+        self._has_non_numeric = False
+
+        self.ps = None                           # no shape parameters: pdf values / pmf grid of the base model
+        self.anchor_models = OrderedDict()       # anchor z tuple -> Model
+        self.anchor_sources = OrderedDict()
+        self.morpher = None
+        self.mus_interpolator = None
+        self.ps_interpolator = None
+        self.n_model_events_interpolator = lambda x: None
+        self.n_model_events = None
+        self._engine = None                      # device engine, built by set_data (unbinned) / prepare (binned)
+        self._grid = None
+        self._mus_anchor = None
+
+    # ------------------------------------------------------------------------------------------
+    # parameter bookkeeping
+    # ------------------------------------------------------------------------------------------
+    def add_rate_parameter(self, source_name, log_prior=None):
+        """Add <source_name>_rate_multiplier, multiplying the expected events of that source."""
+        self.rate_parameters[source_name] = log_prior
+
+    def add_shape_parameter(self, setting_name, anchors, log_prior=None, base_value=None):
+        """Add a shape parameter: `anchors` is a sequence of numeric setting values, or a dict
+        {representative number z: setting} for non-numeric settings (then base_value is required)."""
+        numeric = _is_number(self.pdf_base_config.get(setting_name))
+        if not isinstance(anchors, dict):
+            if not numeric:
+                raise InvalidParameterSpecification("When specifying anchors only by setting values, "
+                                                    "base setting must have a numerical default.")
+            anchors = {z: z for z in anchors}
+        if not numeric:
+            self._has_non_numeric = True
+            if base_value is None:
+                raise InvalidParameterSpecification("For non-numeric settings, you must specify what number "
+                                                    "will represent the default value (the base model setting)")
+        elif base_value is not None:
+            raise InvalidParameterSpecification("For numeric settings, base_value is an unnecessary argument.")
+        self.shape_parameters[setting_name] = (anchors, log_prior, base_value)
+
+    def add_rate_uncertainty(self, source_name, fractional_uncertainty):
+        """Rate parameter with a Gaussian prior of width fractional_uncertainty around 1."""
+        self.add_rate_parameter(source_name, log_prior=stats.norm(1, fractional_uncertainty).logpdf)
+
+    def add_shape_uncertainty(self, setting_name, fractional_uncertainty, anchor_zs=(-2, -1, 0, 1, 2), base_value=None):
+        """Shape parameter with a Gaussian prior around its default value (likelihood.py:492-504)."""
+        self.add_shape_parameter(setting_name, anchor_zs, base_value=base_value)
+        anchors, _, base_value = self.shape_parameters[setting_name]
+        prior = stats.norm(base_value, base_value * fractional_uncertainty).logpdf
+        self.shape_parameters[setting_name] = (anchors, prior, base_value)
+
+    def get_bounds(self, parameter_name=None):
+        """Bounds of one parameter, or the list of bounds of all shape parameters."""
+        if parameter_name is None:
+            return [self.get_bounds(p) for p in self.shape_parameters.keys()]
+        if parameter_name in self.shape_parameters:
+            zs = list(self.shape_parameters[parameter_name][0].keys())
+            return min(zs), max(zs)
+        if parameter_name.endswith(_RATE_SUFFIX):
+            for name, negative_ok in zip(self.source_name_list, self.source_allowed_negative):
+                if parameter_name.startswith(name) and negative_ok == True:    # noqa: E712 (reference semantics)
+                    return float('-inf'), float('inf')
+            return 0, float('inf')
+        raise InvalidParameter("Non-existing parameter %s" % parameter_name)
+
+    @property
+    def source_shape_parameters(self):
+        """source name -> OrderedDict of the shape parameters that source depends on (likelihood.py:113-130)."""
+        out = OrderedDict()
+        for name, source, use_eff, eff_name in zip(self.source_name_list, self.base_model.sources,
+                                                   self.source_apply_efficiency, self.source_efficiency_names):
+            ignored = set(source.config['dont_hash_settings'])
+            if use_eff:
+                ignored.discard(eff_name)
+            mine = OrderedDict((k, v) for k, v in self.shape_parameters.items() if k not in ignored)
+            if mine:
+                out[name] = mine
+        return out
+
+    def _default_z(self, setting_name, base_value):
+        base_setting = self.pdf_base_config.get(setting_name)
+        if _is_number(base_setting):
+            assert base_value is None
+            return base_setting
+        return base_value
+
+    def _kwargs_to_settings(self, **kwargs):
+        """(rate multipliers per source, {shape setting: z}) from call keywords (likelihood.py:443-481)."""
+        for key in kwargs:
+            if key in self.shape_parameters:
+                continue
+            if key.endswith(_RATE_SUFFIX) and key[:-len(_RATE_SUFFIX)] in self.source_name_list:
+                continue
+            raise InvalidParameter("%s is not a known shape or rate parameter!" % key)
+        settings = dict()
+        for name, (_, _, base_value) in self.shape_parameters.items():
+            z = kwargs.get(name)
+            if z is None:
+                z = self._default_z(name, base_value)
+            if not _is_number(z):
+                raise ValueError("Arguments to likelihood function must be numeric, not %s" % type(z))
+            settings[name] = z
+        multipliers = [kwargs.get(name + _RATE_SUFFIX, 1) for name in self.source_name_list]
+        return multipliers, settings
+
+    # ------------------------------------------------------------------------------------------
+    # prepare: anchor models (cold path, host)
+    # ------------------------------------------------------------------------------------------
+    def prepare(self, n_cores=1, ipp_client=None):
+        """Compute the model at every anchor point of the shape-parameter grid (likelihood.py:147-254).
+
+        Model construction is user Python (simulators, files) and stays on the host, serially;
+        n_cores / ipp_client are accepted for signature compatibility (the reference's process-pool /
+        ipyparallel farm, blueice/parallel.py, is out of scope -- SURVEY.md section 2 row 12)."""
+        if len(self.shape_parameters):
+            if self.source_wise_interpolation:
+                self._prepare_source_wise()
+            else:
+                self.morpher = MORPHERS[self.config['morpher']](self.config.get('morpher_config', {}),
+                                                                self.shape_parameters)
+                zs_list = self.morpher.get_anchor_points(bounds=self.get_bounds())
+                for zs in zs_list:
+                    config = deepcopy(self.pdf_base_config)
+                    for i, (setting_name, (anchors, _, _)) in enumerate(self.shape_parameters.items()):
+                        if zs[i] is not None:
+                            config[setting_name] = anchors[zs[i]]
+                    self.anchor_models[tuple(zs)] = Model(config)
+                self._grid = MorphGrid(self.morpher.anchor_z_arrays)
+                self._mus_anchor = self.morpher.anchor_tensor(lambda m: m.expected_events(),
+                                                              [len(self.source_name_list)], self.anchor_models)
+                self.mus_interpolator = _LazyInterpolator(self.morpher, self._mus_anchor,
+                                                          [len(self.source_name_list)])
+        else:
+            self._grid = MorphGrid([])
+            self._mus_anchor = np.asarray(self.base_model.expected_events(), dtype=np.float64)[np.newaxis, :]
+        self.is_data_set = False
+        self.is_prepared = True
+
+    def _prepare_source_wise(self):
+        raise NotImplementedError("source_wise_interpolation is not implemented yet in blueice_b200 "
+                                  "(SURVEY.md section 8f, row f1)")
+
+    @_needs_preparation
+    def set_data(self, d):
+        """Prepare dataset d (anything indexable by analysis-dimension name) for evaluation."""
+        self._data = d
+        self.is_data_set = True
+
+    # ------------------------------------------------------------------------------------------
+    # evaluation
+    # ------------------------------------------------------------------------------------------
+    def parameter_names(self):
+        """Default column order of batch(): rate parameters (insertion order), then shape parameters
+        (the order make_objective uses, inference.py:79-102)."""
+        return [s + _RATE_SUFFIX for s in self.rate_parameters.keys()] + list(self.shape_parameters.keys())
+
+    @_needs_data
+    def __call__(self, livetime_days=None, compute_pdf=False, full_output=False, **kwargs):
+        """Evaluate the log likelihood; parameters not passed take their base values.
+
+        :param livetime_days: exposure to evaluate at (scales the rates of all sources)
+        :param compute_pdf: build a new model at the requested parameters instead of interpolating
+        :param full_output: also return the adjusted mus and the pdf values / pmf grid
+        """
+        multipliers, settings = self._kwargs_to_settings(**kwargs)
+        if len(self.shape_parameters) and compute_pdf:
+            if self._has_non_numeric:
+                raise NotImplementedError("compute_pdf only works for numerical values")
+            return self._call_computed_pdf(multipliers, settings, livetime_days, full_output, kwargs)
+        zs = np.array([[settings[name] for name in self.shape_parameters]], dtype=np.float64).reshape(1, -1)
+        mult = np.array([multipliers], dtype=np.float64)
+        result = self._evaluate_rows(self._engine, zs, mult, livetime_days, scalar=True)
+        if full_output and result != _NEG_INF:
+            scale, _ = self._livetime_scale(livetime_days)
+            eff = self._efficiencies(zs)
+            return self._full_output(self._engine, zs[0], mult[0], scale, None if eff is None else eff[0], result)
+        return result
+
+    @_needs_data
+    def batch(self, params, names=None, livetime_days=None):
+        """Evaluate the log likelihood at P parameter points with one device pass.
+
+        :param params: array [P, k]; column j holds parameter names[j]
+        :param names: parameter names of the columns; default self.parameter_names()
+        :returns: float64 [P]; row p equals self(**dict(zip(names, params[p])), livetime_days=...)
+        """
+        names = self.parameter_names() if names is None else list(names)
+        params = np.asarray(params, dtype=np.float64)
+        if params.ndim == 1:
+            params = params.reshape(-1, max(len(names), 1)) if len(names) != 1 else params.reshape(-1, 1)
+        if params.ndim != 2 or params.shape[1] != len(names):
+            raise ValueError("params must have shape [n_points, %d]" % len(names))
+        P = params.shape[0]
+        # validate names exactly like __call__ does
+        self._kwargs_to_settings(**{n: 1.0 for n in names})
+        defaults_mult, defaults_settings = self._kwargs_to_settings()
+        zs = np.empty((P, len(self.shape_parameters)), dtype=np.float64)
+        for j, name in enumerate(self.shape_parameters):
+            zs[:, j] = params[:, names.index(name)] if name in names else defaults_settings[name]
+        mult = np.empty((P, len(self.source_name_list)), dtype=np.float64)
+        for j, source_name in enumerate(self.source_name_list):
+            key = source_name + _RATE_SUFFIX
+            mult[:, j] = params[:, names.index(key)] if key in names else defaults_mult[j]
+        return self._evaluate_rows(self._engine, zs, mult, livetime_days, scalar=False)
+
+    def _livetime_scale(self, livetime_days):
+        """Factor applied to all mus (likelihood.py:374-382); None when no scaling happens."""
+        if livetime_days is None:
+            return None, False
+        if 'livetime_days' not in self.pdf_base_config:
+            raise ValueError("Cannot scale live-time, base value absent")
+        base = self.pdf_base_config['livetime_days']
+        if base == 0:
+            if livetime_days != 0:
+                raise ValueError("Cannot scale from 0 to non-0 livetime")
+            return None, True
+        return livetime_days / base, False
+
+    def _prior_sum(self, zs, mult):
+        """Sum of log priors per point, accumulated in the reference's order (likelihood.py:349-350,369-371)."""
+        P = len(mult)
+        total = np.zeros(P)
+        columns = [(prior, zs[:, j]) for j, (_, prior, _) in enumerate(self.shape_parameters.values())]
+        columns += [(self.rate_parameters.get(name), mult[:, j]) for j, name in enumerate(self.source_name_list)]
+        for prior, values in columns:
+            if prior is None:
+                continue
+            vec = None
+            if P > 1:
+                try:
+                    vec = np.asarray(prior(values), dtype=np.float64)
+                    if vec.shape != (P,):
+                        vec = None
+                except Exception:
+                    vec = None
+            if vec is None:
+                vec = np.array([prior(float(v)) for v in values], dtype=np.float64)
+            total = total + vec
+        return total
+
+    def _efficiencies(self, zs):
+        """[P, S] efficiency multipliers, or None when no source applies one (likelihood.py:385-393)."""
+        if True not in self.source_apply_efficiency:
+            return None
+        names = list(self.shape_parameters.keys())
+        eff = np.ones((len(zs), len(self.source_name_list)))
+        for s, (use, eff_name) in enumerate(zip(self.source_apply_efficiency, self.source_efficiency_names)):
+            if use and eff_name in names:
+                eff[:, s] = zs[:, names.index(eff_name)]
+        return eff
+
+    def _evaluate_rows(self, engine, zs, mult, livetime_days, scalar):
+        scale, zero_base = self._livetime_scale(livetime_days)
+        P = len(mult)
+        scale_arr = None if scale is None else np.full(P, scale, dtype=np.float64)
+        eff = self._efficiencies(zs)
+        priors = self._prior_sum(zs, mult)
+        ll, status = self._device_loglikelihood(engine, zs, mult, scale_arr, eff)
+        unphysical = (status & _cabi.POINT_UNPHYSICAL) != 0
+        in_range = (status & _cabi.POINT_OUT_OF_RANGE) == 0
+        if zero_base:
+            mus = engine.point_setup_host(zs, mult, scale_arr, eff)["mus"]
+            assert np.all(mus[in_range] == 0), "Got non-0 mus with 0 livetime?!"
+        if self.config.get('unphysical_behaviour') == 'error' and np.any(unphysical & in_range):
+            p = int(np.flatnonzero(unphysical & in_range)[0])
+            mus = engine.point_setup_host(zs[p:p + 1], mult[p:p + 1],
+                                          None if scale_arr is None else scale_arr[p:p + 1],
+                                          None if eff is None else eff[p:p + 1])["mus"][0]
+            raise ValueError("Unphysical rates: %s" % str(mus))
+        result = np.where(status != 0, _NEG_INF, priors + ll)
+        if scalar:
+            return result[0] if status[0] == 0 else _NEG_INF
+        return result
+
+    def _device_loglikelihood(self, engine, zs, mult, scale, eff):
+        """(logL without priors [P], status [P]) from the device engine."""
+        raise NotImplementedError
+
+    def _full_output(self, engine, z_row, mult_row, scale, eff_row, result):
+        raise NotImplementedError
+
+    def _evaluate_fixed_model(self, engine, multipliers, settings, livetime_days, full_output):
+        """compute_pdf=True: a freshly computed model instead of interpolation, then rate priors, scaling
+        and checks as usual (likelihood.py:331-335,365-427; the reference skips shape priors here)."""
+        mult = np.array([multipliers], dtype=np.float64)
+        zs_named = np.array([[settings[name] for name in self.shape_parameters]], dtype=np.float64).reshape(1, -1)
+        scale, _ = self._livetime_scale(livetime_days)
+        scale_arr = None if scale is None else np.full(1, scale)
+        eff = self._efficiencies(zs_named)
+        prior = 0.
+        for j, name in enumerate(self.source_name_list):
+            log_prior = self.rate_parameters.get(name)
+            if log_prior is not None:
+                prior += log_prior(multipliers[j])
+        no_zs = np.zeros((1, 0))
+        ll, status = self._device_loglikelihood(engine, no_zs, mult, scale_arr, eff)
+        if status[0] != 0:
+            if self.config.get('unphysical_behaviour') == 'error':
+                raise ValueError("Unphysical rates: %s" % str(engine.point_setup_host(no_zs, mult, scale_arr, eff)["mus"][0]))
+            return _NEG_INF
+        result = prior + ll[0]
+        if full_output:
+            return self._full_output(engine, no_zs[0], mult[0], scale, None if eff is None else eff[0], result)
+        return result
+
+    def _call_computed_pdf(self, multipliers, settings, livetime_days, full_output, kwargs):
+        raise NotImplementedError
+
+    def _compute_single_model(self, **kwargs):
+        """Model built from the base config with the given shape settings as overrides (likelihood.py:506-512)."""
+        _, settings = self._kwargs_to_settings(**kwargs)
+        config = combine_dicts(self.pdf_base_config, settings, deep_copy=True)
+        config['never_save_to_cache'] = True
+        return Model(config, **settings)
+
+    def adjust_expectations(self, mus, ps, n_model_events):
+        """Hook of the reference (likelihood.py:429-441); identity unless overridden."""
+        return mus, ps
+
+    def _compute_likelihood(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def _compute_single_pdf(self, **kwargs):
+        raise NotImplementedError
+
+
+class _LazyInterpolator(object):
+    """`mus_interpolator` / `ps_interpolator` attributes of the reference API: a callable zs -> array,
+    backed by a device tensor that is only uploaded if somebody actually calls it."""
+
+    def __init__(self, morpher, anchor_tensor, extra_dims):
+        self._morpher, self._tensor, self._extra = morpher, anchor_tensor, list(extra_dims)
+        self._fn = None
+
+    def __call__(self, zs):
+        if self._fn is None:
+            from .pdf_morphers import DeviceGridFunction
+            self._fn = DeviceGridFunction(self._morpher.anchor_z_arrays, self._tensor, self._extra)
+        return self._fn(zs)
+
+
+class UnbinnedLogLikelihood(LogLikelihoodBase):
+
+    @inherit_docstring_from(LogLikelihoodBase)
+    def set_data(self, d):
+        LogLikelihoodBase.set_data(self, d)
+        outlier = self.config.get('outlier_likelihood', 1e-12)
+        engine = UnbinnedEngine(self._grid, self._mus_anchor.reshape(self._grid.n_anchors, -1),
+                                outlier_likelihood=outlier, allow_negative=self.source_allowed_negative)
+        if len(self.shape_parameters):
+            models = [self.anchor_models[tuple(zs)] for _, zs in self.morpher._anchor_grid_iterator()]
+        else:
+            models = [self.base_model]
+        self._fill_anchor_rows(engine, models, d)
+        self._engine = engine
+        if len(self.shape_parameters):
+            self.ps_interpolator = lambda zs: engine.ps(np.asarray(zs, dtype=np.float64),
+                                                        np.ones(engine.n_sources))[1]
+        else:
+            self.ps = engine.ps(np.zeros(0), np.ones(engine.n_sources))[1]
+
+    def _fill_anchor_rows(self, engine, models, d):
+        """Build the per-event pdf tensor [G, S, N] in HBM (likelihood.py:557-562 -> model.py:97-99).
+
+        Histogram-backed sources that share bin edges and lookup method are evaluated for ALL anchors
+        with one gather kernel (K3); any other Source.pdf is called on the host and its row uploaded."""
+        torch = engine.torch
+        coords = [np.asarray(c, dtype=np.float64) for c in self.base_model.to_analysis_dimensions(d)]
+        n = len(coords[0]) if len(coords) else len(d)
+        engine.allocate_ps_anchor(n)
+        if n == 0:
+            return
+        groups = OrderedDict()          # (edges bytes, method) -> [(anchor, source, histogram)]
+        for g, model in enumerate(models):
+            dims = model.to_analysis_dimensions(d)
+            for s, source in enumerate(model.sources):
+                on_device = (isinstance(source, HistogramPdfSource)
+                             and type(source).pdf is HistogramPdfSource.pdf
+                             and len(dims) <= _cabi.MAX_SPACE_DIMS)
+                if on_device:
+                    hist, edges, method = source.template()
+                    key = (tuple(np.asarray(e, dtype=np.float64).tobytes() for e in edges), method)
+                    groups.setdefault(key, (edges, method, []))[2].append((g, s, hist))
+                else:
+                    engine.set_rows(g, s, source.pdf(*dims))
+        if groups:
+            host = np.ascontiguousarray(np.asarray(coords, dtype=np.float64))
+            if np.isnan(host).any() and any(m == 'linear' for _, m, _ in groups.values()):
+                raise ValueError("One of the requested xi is out of bounds in dimension 0")
+            coords_dev = torch.from_numpy(host).to(engine.device)
+            for edges, method, items in groups.values():
+                rows = [(g, s) for g, s, _ in items]
+                templates = np.stack([h for _, _, h in items])
+                engine.lookup_rows(rows, templates, edges,
+                                   coords_dev, _cabi.LOOKUP_LINEAR if method == 'linear' else _cabi.LOOKUP_PIECEWISE)
+
+    def _device_loglikelihood(self, engine, zs, mult, scale, eff):
+        return engine.evaluate(zs, mult, scale, eff, return_status=True)
+
+    def _full_output(self, engine, z_row, mult_row, scale, eff_row, result):
+        mus, ps = engine.ps(z_row, mult_row, scale, eff_row)
+        return result, mus, ps
+
+    @inherit_docstring_from(LogLikelihoodBase)
+    def _compute_single_pdf(self, **kwargs):
+        model = self._compute_single_model(**kwargs)
+        return model.expected_events(), model.score_events(self._data), None
+
+    def _call_computed_pdf(self, multipliers, settings, livetime_days, full_output, kwargs):
+        mus, ps, _ = self._compute_single_pdf(**kwargs)
+        outlier = self.config.get('outlier_likelihood', 1e-12)
+        engine = UnbinnedEngine(MorphGrid([]), np.asarray(mus, dtype=np.float64)[np.newaxis, :],
+                                outlier_likelihood=outlier, allow_negative=self.source_allowed_negative)
+        engine.set_ps_anchor(np.asarray(ps, dtype=np.float64)[np.newaxis])
+        return self._evaluate_fixed_model(engine, multipliers, settings, livetime_days, full_output)
+
+    def _compute_likelihood(self, mus, pdf_values_at_events):
+        """Extended unbinned log likelihood of explicit (mus, ps) arrays on the device (likelihood.py:571-573)."""
+        return extended_loglikelihood(mus, pdf_values_at_events,
+                                      outlier_likelihood=self.config.get('outlier_likelihood', 1e-12))
+
+
+class BinnedLogLikelihood(LogLikelihoodBase):
+
+    def __init__(self, pdf_base_config, likelihood_config=None, **kwargs):
+        LogLikelihoodBase.__init__(self, pdf_base_config, likelihood_config, **kwargs)
+        pdf_base_config['pdf_interpolation_method'] = 'piecewise'     # (sic) reference likelihood.py:580
+        self.model_statistical_uncertainty_handling = self.config.get('model_statistical_uncertainty_handling')
+
+    @inherit_docstring_from(LogLikelihoodBase)
+    def prepare(self, *args):
+        LogLikelihoodBase.prepare(self, *args)
+        self.ps, self.n_model_events = self.base_model.pmf_grids()
+        n_sources = len(self.source_name_list)
+        use_bb = self.model_statistical_uncertainty_handling is not None
+        if len(self.shape_parameters):
+            if self.source_wise_interpolation:
+                raise NotImplementedError("Source-wise interpolation not implemented for binned likelihoods")
+            shape = list(self.ps.shape)
+            pmf_anchor = self.morpher.anchor_tensor(lambda m: m.pmf_grids()[0], shape, self.anchor_models)
+            self.ps_interpolator = _LazyInterpolator(self.morpher, pmf_anchor, shape)
+            nm_anchor = None
+            if use_bb:
+                nm_anchor = self.morpher.anchor_tensor(lambda m: m.pmf_grids()[1], shape, self.anchor_models)
+                self.n_model_events_interpolator = _LazyInterpolator(self.morpher, nm_anchor, shape)
+        else:
+            pmf_anchor = self.ps[np.newaxis]
+            nm_anchor = self.n_model_events[np.newaxis] if use_bb else None
+        self._pmf_anchor, self._nm_anchor = pmf_anchor, nm_anchor
+        self._engine = None
+
+    def _bb_source_index(self):
+        if self.model_statistical_uncertainty_handling != 'bb_single':
+            return None
+        source_i = self.config.get('bb_single_source')
+        if source_i is None:
+            raise ValueError("You need to specify bb_single_source to use bb_single_source expectation adjustment")
+        return self.base_model.get_source_i(source_i)
+
+    def _build_engine(self):
+        bb = self._bb_source_index()
+        G = self._grid.n_anchors
+        S = len(self.source_name_list)
+        pmf = np.asarray(self._pmf_anchor, dtype=np.float64).reshape((G, S) + tuple(self.ps.shape[1:]))
+        nm = None
+        if bb is not None:
+            nm = np.asarray(self._nm_anchor, dtype=np.float64).reshape(pmf.shape)
+        return BinnedEngine(self._grid, self._mus_anchor.reshape(G, -1), pmf, nm, bb)
+
+    @inherit_docstring_from(LogLikelihoodBase)
+    def set_data(self, d):
+        LogLikelihoodBase.set_data(self, d)
+        from . import device_ops
+        dimnames, bins = zip(*self.base_model.config['analysis_space'])
+        coords = self.base_model.to_analysis_dimensions(d)
+        counts = device_ops.histogramdd(bins, coords) if len(d) else np.zeros([len(b) - 1 for b in bins])
+        self.data_events_per_bin = Histdd.from_histogram(counts, bins, axis_names=dimnames)
+        self._observed_dirty = True
+
+    def _ensure_engine(self):
+        if self._engine is None:
+            self._engine = self._build_engine()
+            self._observed_dirty = True
+        if self._observed_dirty:
+            self._engine.set_observed(self.data_events_per_bin.histogram)
+            self._observed_dirty = False
+        return self._engine
+
+    @_needs_data
+    def __call__(self, *args, **kwargs):
+        self._ensure_engine()
+        return LogLikelihoodBase.__call__(self, *args, **kwargs)
+
+    @_needs_data
+    def batch(self, *args, **kwargs):
+        self._ensure_engine()
+        return LogLikelihoodBase.batch(self, *args, **kwargs)
+
+    @staticmethod
+    def _raise_bb_flags(flags):
+        if np.any(flags & _cabi.BB_ROOT1_POSITIVE):
+            raise AssertionError("Beeston-Barlow: first root is not <= 0 in every bin "
+                                 "(e.g. a bin without calibration events)")
+        if np.any(flags & _cabi.BB_NEGATIVE_A):
+            raise AssertionError("Beeston-Barlow: adjusted expectation is not >= 0 in every bin")
+
+    def _device_loglikelihood(self, engine, zs, mult, scale, eff):
+        ll, status, flags = engine.evaluate(zs, mult, scale, eff, return_status=True)
+        self._raise_bb_flags(flags[status == 0])
+        return ll, status
+
+    def _full_output(self, engine, z_row, mult_row, scale, eff_row, result):
+        _, mus, pmfs, flags = engine.pmfs(z_row, mult_row, scale, eff_row)
+        return result, mus, pmfs
+
+    @inherit_docstring_from(LogLikelihoodBase)
+    def _compute_single_pdf(self, **kwargs):
+        model = self._compute_single_model(**kwargs)
+        ps, n_model_events = model.pmf_grids()
+        return model.expected_events(), ps, n_model_events
+
+    def _call_computed_pdf(self, multipliers, settings, livetime_days, full_output, kwargs):
+        mus, ps, n_model_events = self._compute_single_pdf(**kwargs)
+        bb = self._bb_source_index()
+        engine = BinnedEngine(MorphGrid([]), np.asarray(mus, dtype=np.float64)[np.newaxis, :], ps[np.newaxis],
+                              None if bb is None else n_model_events[np.newaxis], bb)
+        engine.set_observed(self.data_events_per_bin.histogram)
+        return self._evaluate_fixed_model(engine, multipliers, settings, livetime_days, full_output)
+
+    def _fixed_engine(self, mus, pmfs, n_model_events):
+        bb = self._bb_source_index()
+        engine = BinnedEngine(MorphGrid([]), np.asarray(mus, dtype=np.float64)[np.newaxis, :],
+                              np.asarray(pmfs, dtype=np.float64)[np.newaxis],
+                              None if bb is None else np.asarray(n_model_events, dtype=np.float64)[np.newaxis], bb)
+        engine.set_observed(self.data_events_per_bin.histogram)
+        return engine
+
+    @_needs_data
+    def adjust_expectations(self, mus, pmfs, n_model_events):
+        """Beeston-Barlow adjusted (mus, pmfs) of explicit arrays, computed on the device (likelihood.py:618-660)."""
+        mus = np.array(mus, dtype=np.float64)
+        pmfs = np.array(pmfs, dtype=np.float64)
+        if self.model_statistical_uncertainty_handling != 'bb_single':
+            return mus, pmfs
+        engine = self._fixed_engine(mus, pmfs, n_model_events)
+        _, mus_adj, pmfs_adj, flags = engine.pmfs(np.zeros(0), np.ones(len(mus)))
+        self._raise_bb_flags(np.array([flags]))
+        return mus_adj, pmfs_adj
+
+    def _compute_likelihood(self, mus, pmfs):
+        """Binned Poisson log likelihood of explicit (mus, pmfs) arrays on the device (likelihood.py:662-675)."""
+        engine = BinnedEngine(MorphGrid([]), np.asarray(mus, dtype=np.float64)[np.newaxis, :],
+                              np.asarray(pmfs, dtype=np.float64)[np.newaxis], None, None)
+        engine.set_observed(self.data_events_per_bin.histogram)
+        ll, status, _ = engine.evaluate(np.zeros((1, 0)), np.ones((1, len(mus))), return_status=True)
+        return ll[0]
+
+
+def extended_loglikelihood(mu, ps, outlier_likelihood=0.0):
+    """Extended unbinned log likelihood -sum(mu) + sum_i log(sum_s mu_s ps[s, i]) on the device.
+
+    Same semantics as blueice/likelihood.py:678-690 (NaN terms dropped, non-positive densities replaced
+    by outlier_likelihood when it is non-zero); no unphysical-rate test is applied here."""
+    mu = np.asarray(mu, dtype=np.float64)
+    ps = np.asarray(ps, dtype=np.float64)
+    engine = UnbinnedEngine(MorphGrid([]), np.ones((1, len(mu))), outlier_likelihood=outlier_likelihood,
+                            allow_negative=[True] * len(mu))
+    engine.set_ps_anchor(ps[np.newaxis])
+    # rates enter as multipliers of unit anchors, so any finite mu is passed through unchanged
+    ll, status = engine.evaluate(np.zeros((1, 0)), mu[np.newaxis, :], return_status=True)
+    if status[0] != 0:
+        # the reference has no rate check here; evaluate the definition for the (rare) flagged input
+        return float('nan')
+    return ll[0]
+
+
+def _bb_root(a, p, U, d, sign):
+    a, p, U, d = [np.asarray(x, dtype=np.float64) for x in (a, p, U, d)]
+    with np.errstate(all='ignore'):
+        disc = (U**2*p**2 + 2*U**2*p + U**2 + 2*U*a*p**2 + 2*U*a*p - 2*U*d*p**2 - 2*U*d*p
+                + a**2*p**2 + 2*a*d*p**2 + d**2*p**2)
+        return (-U*p - U + a*p + d*p + sign * np.sqrt(disc)) / (2*p*(p + 1))
+
+
+def beeston_barlow_root1(a, p, U, d):
+    """Closed-form root of the single-source Beeston-Barlow equations that the reference asserts to be
+    non-positive (likelihood.py:693-700).  Host helper of the public API; the likelihood evaluates the
+    same expression per bin inside the K4 kernel."""
+    return _bb_root(a, p, U, d, -1.0)
+
+
+def beeston_barlow_root2(a, p, U, d):
+    """The physical root (likelihood.py:703-708)."""
+    return _bb_root(a, p, U, d, +1.0)
+
+
+def beeston_barlow_roots(a, p, U, d):
+    return beeston_barlow_root1(a, p, U, d), beeston_barlow_root2(a, p, U, d)
+
+
+class LogLikelihoodSum(object):
+    """Weighted sum of several likelihoods that share parameters by name (likelihood.py:867-955).
+
+    Pure keyword plumbing over ll(**kw) / ll.batch; adds a batch() that sums the members' batches."""
+
+    def __init__(self, likelihood_list, likelihood_weights=None):
+        self.likelihood_list = list(likelihood_list)
+        self.likelihood_weights = [1 for _ in self.likelihood_list] if likelihood_weights is None \
+            else likelihood_weights
+        self.rate_parameters = dict()
+        self.shape_parameters = dict()
+        self.source_list = []
+        self.pdf_base_config = {}
+        self.likelihood_parameters = []
+        for ll in self.likelihood_list:
+            self.rate_parameters.update(ll.rate_parameters)
+            self.shape_parameters.update(ll.shape_parameters)
+            names = []
+            for rate_name in ll.rate_parameters.keys():
+                names.append(rate_name + _RATE_SUFFIX)
+                self._remember_base(ll, rate_name)
+            for shape_name in ll.shape_parameters.keys():
+                names.append(shape_name)
+                self._remember_base(ll, shape_name)
+            self.likelihood_parameters.append(names)
+
+    def _remember_base(self, ll, name):
+        value = ll.pdf_base_config.get(name)
+        if value is not None:
+            self.pdf_base_config[name] = value
+
+    def __call__(self, compute_pdf=False, livetime_days=None, **kwargs):
+        total = 0.
+        for i, (ll, names, weight) in enumerate(zip(self.likelihood_list, self.likelihood_parameters,
+                                                    self.likelihood_weights)):
+            mine = {k: v for k, v in kwargs.items() if k in names}
+            livetime = livetime_days[i] if isinstance(livetime_days, list) else livetime_days
+            total += weight * ll(compute_pdf=compute_pdf, livetime_days=livetime, **mine)
+        return total
+
+    def batch(self, params, names, livetime_days=None):
+        params = np.asarray(params, dtype=np.float64)
+        names = list(names)
+        total = np.zeros(len(params))
+        for i, (ll, own, weight) in enumerate(zip(self.likelihood_list, self.likelihood_parameters,
+                                                  self.likelihood_weights)):
+            cols = [j for j, n in enumerate(names) if n in own]
+            livetime = livetime_days[i] if isinstance(livetime_days, list) else livetime_days
+            total = total + weight * ll.batch(params[:, cols], [names[j] for j in cols], livetime_days=livetime)
+        return total
+
+    def split_results(self, result_dict):
+        return [{k: v for k, v in result_dict.items() if k in names} for names in self.likelihood_parameters]
+
+    def get_bounds(self, parameter_name=None):
+        if parameter_name is None:
+            return [self.get_bounds(p) for p in self.shape_parameters]
+        if parameter_name in self.shape_parameters.keys():
+            bounds = np.array([ll.get_bounds(parameter_name) for ll in self.likelihood_list
+                               if parameter_name in ll.shape_parameters.keys()])
+            lo, hi = np.max(bounds[:, 0]), np.min(bounds[:, 1])
+            if hi <= lo:
+                raise InvalidParameterSpecification("lower bound %s higher than upper bound!" % parameter_name)
+            return lo, hi
+        if parameter_name.endswith(_RATE_SUFFIX):
+            return 0, float('inf')
+        raise InvalidParameter("Non-existing parameter %s" % parameter_name)
+
+
+class LogAncillaryLikelihood(object):
+    """Analytic constraint term func({parameter: value}, **func_kwargs) (likelihood.py:958-1001)."""
+
+    def __init__(self, func, parameter_list, config=None, func_kwargs=None):
+        self.rate_parameters = dict()
+        self.shape_parameters = OrderedDict((name, (None, None, None)) for name in parameter_list)
+        self.source_list = []
+        self.pdf_base_config = dict() if config is None else config
+        self.func = func
+        self.func_kwargs = dict() if func_kwargs is None else func_kwargs
+
+    def get_bounds(self, parameter_name=None):
+        if parameter_name is None:
+            return [self.get_bounds(p) for p in self.shape_parameters]
+        if parameter_name in self.shape_parameters.keys():
+            return -np.inf, np.inf
+        raise InvalidParameter("Non-existing parameter %s" % parameter_name)
+
+    def __call__(self, **kwargs):
+        values = OrderedDict((name, self.pdf_base_config[name]) for name in self.shape_parameters)
+        values.update(kwargs)
+        return self.func(values, **self.func_kwargs)
+
+
+# the inference helpers double as methods of every likelihood class (likelihood.py:1004-1007)
+for _name in inference.__all__:
+    for _cls in (LogLikelihoodBase, LogLikelihoodSum, LogAncillaryLikelihood):
+        setattr(_cls, _name, getattr(inference, _name))

@@ -1,0 +1,230 @@
+/*
+ * blueice_b200 -- C-ABI of the B200-native likelihood-evaluation hot path.
+ *
+ * The reference (JelleAalbers/blueice v1.2.1) is pure Python and has NO FFI / plugin interface
+ * for this path; the drop-in boundary is its Python class API.  The entry
+ * points below are what a ctypes binding inside the reference would call at the three seams where
+ * the reference already isolates the numerics.  Each one cites the reference code it replaces
+ * (file:line relative to the reference checkout).  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - `*_dev` pointers are CUDA device pointers owned by the caller; `*_host` are host pointers that
+ *     are read during the call only.  The library never allocates persistent memory and never frees
+ *     caller memory.  Every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     re-entrant per stream, and keeps no global state besides a thread-local error string.
+ *   - return value: 0 = ok, negative = bi_status error code; text via bi_last_error().
+ *   - all floating point is IEEE float64; indices are int32 unless noted; sizes are int64.
+ *
+ * Canonical summation order (what makes results independent of batch shape, kernel choice, grid
+ * size and GPU count per shard) is documented in DESIGN.md section 4 and implemented in
+ * blueice_b200/csrc/bi_common.cuh:
+ *   block      = 32 consecutive events  -> L_b  (adjacent-pair binary tree)
+ *   superblock = 16 consecutive blocks  -> S_j  (sequential)
+ *   total      = 256 strided lanes (j mod 256, sequential) + xor-butterfly over the lanes
+ */
+#ifndef BLUEICE_B200_H
+#define BLUEICE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BI_ABI_VERSION 1
+#define BI_MAX_DIMS 6          /* max shape parameters per morph grid (2^6 = 64 corners)          */
+#define BI_MAX_SOURCES 64      /* max sources per model                                           */
+#define BI_MAX_SPACE_DIMS 4    /* max analysis-space dimensions of a histogram template           */
+#define BI_MAX_AXIS_POINTS 256 /* max total anchor values (sum over dims) in one grid             */
+#define BI_EVENT_BLOCK 32      /* canonical block: events per tree-reduced block                  */
+#define BI_SUPERBLOCK 512      /* canonical superblock: events per sequentially summed partial    */
+
+typedef enum bi_status {
+    BI_OK = 0,
+    BI_ERR_INVALID_ARGUMENT = -1,
+    BI_ERR_CUDA = -2,
+    BI_ERR_UNSUPPORTED = -3
+} bi_status;
+
+/* point status flags written by bi_point_setup (bitmask) */
+#define BI_POINT_OK 0
+#define BI_POINT_OUT_OF_RANGE 1   /* some z outside [min anchor, max anchor] or NaN: logL = -inf  */
+#define BI_POINT_UNPHYSICAL 2     /* rates fail the check of likelihood.py:397-415: -inf / error  */
+
+/* lookup methods for bi_hist_lookup */
+#define BI_LOOKUP_LINEAR 0        /* source.py:225-240 */
+#define BI_LOOKUP_PIECEWISE 1     /* source.py:242-243 */
+
+/* binned flags returned per point by bi_binned_ll_batch (bitmask) */
+#define BI_BB_ROOT1_POSITIVE 1    /* reference would fail `assert np.all(A_bins_1 <= 0)`  (likelihood.py:649) */
+#define BI_BB_NEGATIVE_A 2        /* reference would fail `assert np.all(0 <= A_bins)`    (likelihood.py:655) */
+
+const char* bi_last_error(void);
+int bi_abi_version(void);
+
+/* Number of superblock partials for n_events events: ceil(n_events / BI_SUPERBLOCK). */
+int64_t bi_num_superblocks(int64_t n_events);
+
+/*
+ * K1 -- anchor-grid morphing set-up for a batch of parameter points.
+ *
+ * Replaces: GridInterpolator.make_interpolator / RegularGridInterpolator index search and corner
+ * weights (pdf_morphers.py:57-70; scipy/interpolate/_rgi.py:520-549 + find_indices), the `mus`
+ * interpolation call (likelihood.py:355), rate / livetime / efficiency scaling (likelihood.py:366-393)
+ * and the unphysical-rate test (likelihood.py:397-415).
+ *
+ *   n_dims            D >= 0 shape parameters (0: no morphing, one anchor)
+ *   n_anchors_host    [D] anchors per dimension
+ *   axes_host         concatenated sorted anchor z values, sum(n_anchors) doubles
+ *   zs_dev            [P, D] shape-parameter values (row major)
+ *   rate_mult_dev     [P, S] rate multipliers
+ *   scale_dev         [P] livetime scale (livetime_days / base) or NULL (= not applied)
+ *   eff_dev           [P, S] efficiency multipliers (1 where a source has none) or NULL
+ *   mus_anchor_dev    [G, S] expected events at each anchor, anchors in C order (first dim slowest)
+ *   allow_negative_host [S] bytes (likelihood.py:82) or NULL (= all false)
+ * outputs
+ *   cell_dev          [P, D] int32 lower cell index per dim (bit-exact vs scipy find_indices)
+ *   frac_dev          [P, D] normalised distance per dim
+ *   corner_dev        [P, C] int32 flat anchor index of each hypercube corner, C = 2^D, first dim slowest
+ *   weight_dev        [P, C] corner weights, product taken in scipy's order
+ *   mus_dev           [P, S] scaled expected events
+ *   musum_dev         [P]    sum_s mus (numpy pairwise order)
+ *   status_dev        [P]    BI_POINT_* flags
+ */
+int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                   int32_t n_sources, int64_t n_points,
+                   const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                   const double* eff_dev, const double* mus_anchor_dev,
+                   const uint8_t* allow_negative_host,
+                   int32_t* cell_dev, double* frac_dev, int32_t* corner_dev, double* weight_dev,
+                   double* mus_dev, double* musum_dev, int32_t* status_dev, void* stream);
+
+/*
+ * K2 -- fused morph + mixture density + log + reduce, unbinned (per-superblock partial sums).
+ *
+ * Replaces: the `ps` interpolation call (likelihood.py:356 -> pdf_morphers.py:70 ->
+ * _rgi.py:520-549 on the [n1..nD, S, N] tensor) fused with extended_loglikelihood
+ * (likelihood.py:678-690): p_i = nansum_s(mu_s * ps[s,i]); non-positive/NaN p_i -> outlier_likelihood
+ * (if non-zero); sum_i log p_i.
+ *
+ *   ps_anchor_dev   [G, S, ld_events] per-event pdf values at each anchor; ld_events even, >= n_events
+ *   corner/weight/mus/status: outputs of bi_point_setup
+ *   partial_dev     [P, n_super] out: S_j partial log sums (n_super = bi_num_superblocks(n_events))
+ *
+ * bi_unbinned_partials_stream : lanes = events; any P; HBM-bound when P is small.
+ * bi_unbinned_partials_grouped: threads = points that share a hypercube cell, events broadcast from
+ *                               shared memory staged by TMA bulk copies; FP64-bound for large P.
+ *   group_points_dev [n_grouped] point indices, points of one work item contiguous
+ *   work_host        [n_work, 4] int32 (first, count<=BI_GROUP_POINTS, superblock_begin, superblock_end)
+ *                    all points of a work item MUST share the same corner list (same cell).
+ * Both produce bit-identical partials for the same point.
+ */
+#define BI_GROUP_POINTS 256        /* max points per grouped work item                          */
+#define BI_GROUP_MAX_SOURCES 8     /* grouped kernel keeps mus in registers: n_sources <= 8     */
+int bi_unbinned_partials_stream(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
+                                int32_t n_sources, int32_t n_corners,
+                                const int32_t* point_index_dev, int64_t n_points,
+                                const int32_t* corner_dev, const double* weight_dev,
+                                const double* mus_dev, const int32_t* status_dev,
+                                double outlier_likelihood, double* partial_dev, void* stream);
+
+int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
+                                 int32_t n_sources, int32_t n_corners,
+                                 const int32_t* group_points_dev, const int32_t* work_dev, int64_t n_work,
+                                 const int32_t* corner_dev, const double* weight_dev,
+                                 const double* mus_dev, const int32_t* status_dev,
+                                 double outlier_likelihood, double* partial_dev, void* stream);
+
+/* logL[p] = -musum[p] + total(partial[p, :]) in canonical order; status != 0 -> -inf.
+ * (likelihood.py:690 `-mu.sum() + np.sum(np.log(p_events))`, :347/:402 soft failures.) */
+int bi_unbinned_finalize(const double* partial_dev, int64_t n_super, const double* musum_dev,
+                         const int32_t* status_dev, int64_t n_points, double* logl_dev, void* stream);
+
+/* Morphed per-event pdf values ps[S, N] for ONE point (full_output=True, likelihood.py:424-425). */
+int bi_unbinned_ps(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
+                   int32_t n_sources, int32_t n_corners, const int32_t* corner_dev,
+                   const double* weight_dev, double* ps_out_dev, int64_t ld_out, void* stream);
+
+/*
+ * K3 -- histogram-template lookup of N events in T templates that share their bin edges.
+ *
+ * Replaces: HistogramPdfSource.pdf (source.py:219-246) called G*S times by
+ * UnbinnedLogLikelihood.set_data (likelihood.py:557-560 -> model.py:97-99).
+ *
+ *   templates_dev [T, prod(n_bins)] densities, C order
+ *   n_space       analysis-space dimensions (1..BI_MAX_SPACE_DIMS)
+ *   n_bins_host   [n_space]
+ *   edges_host    concatenated bin edges, sum(n_bins + 1) doubles
+ *   coords_dev    [n_space, ld_coords] event coordinates
+ *   out_dev       [T, ld_out]
+ * LINEAR: clip to the bin-centre range, multilinear over bin centres, scipy's operation order
+ *         (2-D: evaluate_linear_2d fast path; otherwise the generic corner loop).
+ * PIECEWISE: idx_d = clip(searchsorted(edges_d, x_d, 'left') - 1, 0, n_bins_d - 1).
+ */
+int bi_hist_lookup(const double* templates_dev, int64_t n_templates, int32_t n_space,
+                   const int32_t* n_bins_host, const double* edges_host,
+                   const double* coords_dev, int64_t ld_coords, int64_t n_events, int32_t method,
+                   double* out_dev, int64_t ld_out, int32_t* bin_index_dev, void* stream);
+
+/*
+ * Event binning with np.histogramdd semantics (multihist.Histdd.add; likelihood.py:604-609).
+ *   counts_dev [prod(n_bins)] uint64, ZEROED BY THE CALLER, incremented with integer atomics
+ *   bin_index_dev [N] optional out: flat bin index or -1 for dropped events (may be NULL)
+ */
+int bi_histogramdd(int32_t n_space, const int32_t* n_bins_host, const double* edges_host,
+                   const double* coords_dev, int64_t ld_coords, int64_t n_events,
+                   unsigned long long* counts_dev, int32_t* bin_index_dev, void* stream);
+
+/*
+ * K4 -- binned Poisson log-likelihood with optional Beeston-Barlow adjustment, batch of points.
+ *
+ * Replaces: BinnedLogLikelihood.adjust_expectations (likelihood.py:618-660),
+ * beeston_barlow_root1/2 (likelihood.py:693-712), _compute_likelihood (likelihood.py:662-675) and the
+ * pmf / n_model_events interpolation calls (likelihood.py:356-357).
+ *
+ *   pmf_anchor_dev      [G, S, ld_bins] pmf per bin at each anchor
+ *   n_model_anchor_dev  [G, ld_bins] calibration events per bin of source `bb_source` at each anchor
+ *                       (NULL when bb_source < 0)
+ *   n_model_sum_anchor_dev [G] sum over bins of n_model_anchor_dev per anchor (NULL when bb_source < 0);
+ *                       n_model_events[source_i].sum() (likelihood.py:645) is taken as the morph of these
+ *   observed_dev        [n_bins] observed counts (float64)
+ *   lgamma_obs_dev      [n_bins] gammaln(observed + 1), computed once per dataset by the caller
+ *   scratch_dev         bi_binned_scratch_doubles(P, n_bins) doubles
+ * outputs
+ *   logl_dev [P] (status != 0 -> -inf), mus_adj_dev [P, S] adjusted mus (may be NULL),
+ *   flags_dev [P] BI_BB_* bits; the sum over bins of A*w of each point is left in
+ *   scratch_dev[2 * P * bi_num_superblocks(n_bins) + p] (input of bi_binned_pmfs).
+ */
+int64_t bi_binned_scratch_doubles(int64_t n_points, int64_t n_bins);
+int bi_binned_ll_batch(const double* pmf_anchor_dev, const double* n_model_anchor_dev,
+                       const double* n_model_sum_anchor_dev,
+                       int64_t ld_bins, int64_t n_bins, int32_t n_sources, int32_t n_corners,
+                       int32_t bb_source, const double* observed_dev, const double* lgamma_obs_dev,
+                       const int32_t* corner_dev, const double* weight_dev, const double* mus_dev,
+                       const int32_t* status_dev, int64_t n_points, double* scratch_dev,
+                       double* logl_dev, double* mus_adj_dev, int32_t* flags_dev, void* stream);
+
+/* Morphed (and BB-adjusted) pmf grid [S, n_bins] for ONE point (full_output=True);
+ * corner/weight/mus point at that point's rows, sum_t_dev at its sum over bins of A*w. */
+int bi_binned_pmfs(const double* pmf_anchor_dev, const double* n_model_anchor_dev,
+                   const double* n_model_sum_anchor_dev,
+                   int64_t ld_bins, int64_t n_bins, int32_t n_sources, int32_t n_corners,
+                   int32_t bb_source, const double* observed_dev,
+                   const int32_t* corner_dev, const double* weight_dev, const double* mus_dev,
+                   const double* sum_t_dev, double* pmf_out_dev, int64_t ld_out, void* stream);
+
+/*
+ * Micro-benchmarks used by bench.py to measure the roofline denominators that
+ * MEASURED_PEAKS.json does not hold: dependent-free FP64 FMA throughput
+ * and a plain streaming read.  Each returns elapsed milliseconds (CUDA events on `stream`) in *ms_host.
+ */
+int bi_bench_fp64_fma(int64_t fma_per_thread, int32_t n_blocks, double* sink_dev, float* ms_host,
+                      double* flops_host, void* stream);
+int bi_bench_stream_read(const double* src_dev, int64_t n_doubles, double* sink_dev, float* ms_host,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLUEICE_B200_H */
