@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""Benchmark of the likelihood-evaluation hot path (BASELINE.json metric: logL evals/s = points x events / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--points P] [--events N]
+
+Workload at N=1 = BASELINE.json configs[1]: 2 sources, 2-D 100x100 histogram templates, 2 shape
+nuisances x 5 anchors (G = 25), ~100k events, 4096-point profile scan.  One "step" = one pass of the
+hot path over the whole scan.
+
+  value     device-resident: parameter points and schedule already in HBM; timed region (CUDA events on
+            the launching stream) = K1 point set-up + K2 fused morph/mixture/log/reduce + finalize.
+  e2e       ll.batch(host ndarray) -> host ndarray through the public API: planning, H2D of points and
+            schedule from pinned memory, the same kernels, D2H of logL + status, stream sync.
+  roofline  dominant kernel (grouped K2) timed alone; FP64-pipe bound for a shared-dataset scan
+            (SURVEY.md section 8d), peak = FP64 FMA micro-benchmark measured in this run; the same
+            kernel's algorithmic HBM bytes and the streaming (P=1, HBM-bound) regime are reported too.
+  cpu_baseline  the oracle pipeline (same SciPy calls as the reference) on a bounded sample, 1 core.
+
+The L2 (126 MB) is flushed between timed steps by writing a 512 MB buffer (the 40 MB anchor tensor
+would otherwise stay L2-resident); the flush is outside the timed intervals.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import bench_workloads as wl   # noqa: E402
+
+METRIC = "logL evals/sec (points x events / s)"
+UNIT = "point-events/s"
+N_SOURCES, N_SHAPE, ANCHORS, BINS = 2, 2, wl.ANCHORS_5, (100, 100)
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle pipeline on the host cores
+# ------------------------------------------------------------------------------------------------
+_ORACLE = None
+
+
+def build_oracle(n_events, seed=1):
+    from oracle.pipeline import UnbinnedOracle
+    axes, edges, templates, mus = wl.c2_arrays(N_SOURCES, N_SHAPE, ANCHORS, BINS)
+    x, y = wl.c2_events(templates, mus, edges, n_events, seed)
+    t0 = time.perf_counter()
+    orc = UnbinnedOracle(axes, mus).set_data_from_templates(templates, edges, [x, y])
+    return orc, len(x), time.perf_counter() - t0
+
+
+def _oracle_chunk(args):
+    zs, mult = args
+    return _ORACLE.batch(zs, mult)
+
+
+def cpu_baseline_single_core(n_events, budget_s=12.0):
+    """Oracle (kind 'port') on ONE core (the reference evaluation path is single-threaded)."""
+    orc, n, set_data_s = build_oracle(n_events)
+    zs, mult = wl.scan_points(4096, N_SHAPE, N_SOURCES, seed=2)
+    orc(zs[0], mult[0])                                     # warm-up
+    done, t0 = 0, time.perf_counter()
+    while done < len(zs) and time.perf_counter() - t0 < budget_s:
+        orc(zs[done], mult[done])
+        done += 1
+    dt = time.perf_counter() - t0
+    return {"value": done * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d of the 4096 scan points x %d events, %.1f s; oracle.pipeline.UnbinnedOracle "
+                      "(scipy RegularGridInterpolator + NumPy, as the reference); set_data %.2f s"
+                      % (done, n, dt, set_data_s),
+            "ms_per_point": 1e3 * dt / done, "set_data_s": set_data_s}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    global _ORACLE
+    n_events = args.events
+    _ORACLE, n, set_data_s = build_oracle(n_events)
+    cores = os.cpu_count() or 1
+    per_worker = max(2, args.ref_points_per_core)
+    zs, mult = wl.scan_points(cores * per_worker, N_SHAPE, N_SOURCES, seed=2)
+    chunks = [(zs[i::cores], mult[i::cores]) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_oracle_chunk, chunks)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_oracle_chunk, chunks)
+        dt = time.perf_counter() - t0
+    value = args.steps * len(zs) * n / dt
+    sample = ("%d points x %d events per step over %d worker processes (disjoint point chunks); "
+              "oracle.pipeline.UnbinnedOracle; set_data %.2f s" % (len(zs), n, cores, set_data_s))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(n, len(zs)),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n_events, n_points):
+    return {"workload": "config 2: 2-source 2D (cs1,cs2) HistogramPdfSource templates 100x100 bins, "
+                        "2 shape nuisances x 5 anchors, ~100k events, 4096-point profile scan",
+            "n_events": int(n_events), "n_points_per_gpu": int(n_points), "n_sources": N_SOURCES,
+            "n_anchors": len(ANCHORS) ** N_SHAPE, "lookup": "linear",
+            "l2": "flushed between timed steps (512 MB write, outside the timed intervals)",
+            "parallelism": "points sharded over GPUs, dataset replicated, all_gather of results"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="bi_clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for row in open(self.path):
+                parts = [p.strip() for p in row.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    smax.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for name, flag in zip(names, parts[3:7]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+def run_own_arm(args):
+    import torch
+    import torch.distributed as dist
+    from blueice_b200 import _cabi
+    from blueice_b200.engine import MorphGrid, UnbinnedEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    os.chdir(tempfile.mkdtemp(prefix="bi_bench_"))
+
+    sampler = ClockSampler(local_rank)
+    # ---- build the workload through the public API (prepare + set_data are not part of a step) ----
+    t0 = time.perf_counter()
+    ll, d, names = wl.c2_api(N_SOURCES, N_SHAPE, ANCHORS, BINS, n_events=args.events, seed=1)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ll.set_data(d)
+    torch.cuda.synchronize()
+    set_data_s = time.perf_counter() - t0
+    eng = ll._engine
+    n_events = len(d)
+    P = args.points
+    # weak scaling: every rank evaluates its own P points of a (world * P)-point scan
+    zs_all, mult_all = wl.scan_points(P * world, N_SHAPE, N_SOURCES, seed=2)
+    zs, mult = zs_all[rank * P:(rank + 1) * P], mult_all[rank * P:(rank + 1) * P]
+    table = np.ascontiguousarray(np.column_stack([mult, zs]))
+
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=device)
+
+    def flush_l2():
+        flush.fill_(1.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -----------------------------------------------------------------------
+    plan = eng.plan(zs)
+    zs_d, mult_d, _, _, _ = eng._upload_points(zs, mult, None, None)
+    zs_d, mult_d = zs_d.clone(), mult_d.clone()
+    plan_dev = tuple(None if t is None else t.clone() for t in eng.upload_plan(plan)[:3])
+    gathered = [torch.empty(P, dtype=torch.float64, device=device) for _ in range(world)] if world > 1 else None
+
+    def device_step():
+        logl = eng.run_device(P, zs_d, mult_d, None, None, plan, plan_dev)
+        if world > 1:
+            dist.all_gather(gathered, logl)
+        return logl
+
+    for _ in range(max(args.warmup, 3)):
+        flush_l2()
+        device_step()
+    barrier()
+    sampler.start()
+    launches0 = eng.launches
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush_l2()
+        starts[k].record()
+        logl = device_step()
+        ends[k].record()
+    barrier()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(np.sum(step_ms))
+    launches_timed = eng.launches - launches0
+    result_dev = logl.cpu().numpy().copy()
+
+    # ---- end-to-end arm (public API, host buffers) ---------------------------------------------------
+    for _ in range(3):
+        flush_l2()
+        torch.cuda.synchronize()
+        ll.batch(table, names)
+    e2e_s = []
+    for k in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = ll.batch(table, names)
+        if world > 1:
+            dist.all_gather(gathered, torch.from_numpy(res).to(device))
+            torch.cuda.synchronize()
+        e2e_s.append(time.perf_counter() - t0)
+    assert np.array_equal(res, result_dev), "device-resident and e2e arms disagree"
+    e2e_total = float(np.sum(e2e_s))
+    h2d, d2h = int(eng.last_h2d_bytes), int(eng.last_d2h_bytes)
+
+    # ---- dominant kernel alone (grouped K2), for the roofline --------------------------------------
+    S, C = eng.n_sources, eng.grid.n_corners
+    o = eng._setup(P, zs_d, mult_d, None, None)
+    partial = eng.ws.get("partial", P * eng.n_super, torch.float64)
+    stream = eng._stream()
+
+    def grouped_only():
+        rc = eng.lib.bi_unbinned_partials_grouped(
+            _cabi.dev_ptr(eng.ps_anchor), eng.ld, eng.n_events, S, C, _cabi.dev_ptr(plan_dev[1]),
+            _cabi.dev_ptr(plan_dev[2]), len(plan.work), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),
+            _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]), eng.outlier_likelihood, _cabi.dev_ptr(partial), stream)
+        _cabi.check(rc, "bi_unbinned_partials_grouped")
+
+    k2_ms = []
+    n_grouped = len(plan.group_points)
+    if len(plan.work):
+        for _ in range(3):
+            grouped_only()
+        for _ in range(max(args.steps, 10)):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            grouped_only()
+            b.record()
+            torch.cuda.synchronize()
+            k2_ms.append(a.elapsed_time(b))
+    clocks = sampler.stop()
+
+    # ---- roofline denominators measured in this run ---------------------------------------------------
+    peaks, peak_src = measured_peaks()
+    sink = torch.zeros(8, dtype=torch.float64, device=device)
+    ms = np.zeros(1, dtype=np.float32)
+    flops = np.zeros(1, dtype=np.float64)
+    fp64_tflops = []
+    for _ in range(3):
+        _cabi.check(eng.lib.bi_bench_fp64_fma(1 << 17, 148 * 16, _cabi.dev_ptr(sink), _cabi.host_ptr(ms),
+                                              _cabi.host_ptr(flops), stream), "bi_bench_fp64_fma")
+        fp64_tflops.append(flops[0] / (ms[0] * 1e-3) / 1e12)
+    fp64_peak = max(fp64_tflops)
+
+    # streaming regime: P = 1 over a tensor much larger than L2 (HBM-bound), same G/S/C
+    stream_info = None
+    if rank == 0 and not args.skip_stream:
+        n_big = args.stream_events
+        big = UnbinnedEngine(MorphGrid(eng.grid.axes), eng.mus_anchor_host, device=device)
+        big.allocate_ps_anchor(n_big)
+        reps = -(-n_big // n_events)
+        src = eng.ps_anchor[:, :, :n_events]
+        for r in range(reps):
+            lo = r * n_events
+            hi = min(lo + n_events, n_big)
+            big.ps_anchor[:, :, lo:hi].copy_(src[:, :, :hi - lo])
+        big.force_kernel = 'stream'
+        z1, m1 = zs[:1], mult[:1]
+        plan1 = big.plan(z1)
+        z1_d, m1_d, _, _, _ = big._upload_points(z1, m1, None, None)
+        plan1_dev = big.upload_plan(plan1)[:3]
+        o1 = big._setup(1, z1_d, m1_d, None, None)
+        part1 = big.ws.get("partial", big.n_super, torch.float64)
+
+        def stream_only():
+            rc = big.lib.bi_unbinned_partials_stream(
+                _cabi.dev_ptr(big.ps_anchor), big.ld, big.n_events, S, C, _cabi.dev_ptr(plan1_dev[0]), 1,
+                _cabi.dev_ptr(o1["corner"]), _cabi.dev_ptr(o1["weight"]), _cabi.dev_ptr(o1["mus"]),
+                _cabi.dev_ptr(o1["status"]), big.outlier_likelihood, _cabi.dev_ptr(part1), big._stream())
+            _cabi.check(rc, "bi_unbinned_partials_stream")
+
+        for _ in range(3):
+            stream_only()
+        sms = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            stream_only()
+            b.record()
+            torch.cuda.synchronize()
+            sms.append(a.elapsed_time(b))
+        bytes_alg = 8.0 * C * S * n_big
+        gbs = bytes_alg / (np.mean(sms) * 1e-3) / 1e9
+        # plain streaming read of the same number of bytes with this library's own reader
+        n_read = int(min(bytes_alg // 8, big.ps_anchor.numel()))
+        rd = []
+        for _ in range(5):
+            _cabi.check(big.lib.bi_bench_stream_read(_cabi.dev_ptr(big.ps_anchor), n_read, _cabi.dev_ptr(sink),
+                                                     _cabi.host_ptr(ms), big._stream()), "bi_bench_stream_read")
+            rd.append(n_read * 8 / (ms[0] * 1e-3) / 1e9)
+        stream_info = {"kernel": "k_unbinned_stream<4> (P=1, lanes=events)", "bound": "hbm",
+                       "n_events": int(n_big), "bytes_per_point_event": 8 * C * S,
+                       "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                       "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peak_src == "measured"
+                       else "fallback 6.65 TB/s", "ms": float(np.mean(sms)),
+                       "point_events_per_s": n_big / (np.mean(sms) * 1e-3),
+                       "plain_read_gbs_this_run": float(max(rd))}
+        del big
+
+    # ---- reduce over ranks -------------------------------------------------------------------------
+    total_ms_max, e2e_total_max = total_ms, e2e_total
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms_max, e2e_total_max = float(t[0]), float(t[1])
+
+    if rank == 0:
+        units = float(world) * P * n_events * args.steps
+        value = units / (total_ms_max * 1e-3)
+        e2e_value = units / e2e_total_max
+        G = eng.grid.n_anchors
+        roofline = None
+        if k2_ms:
+            k2 = float(np.mean(k2_ms)) * 1e-3
+            flops_alg = float(n_grouped) * n_events * (2.0 * C * S + 2.0 * S)
+            bytes_alg = 8.0 * S * n_events * G
+            roofline = {"kernel": "k_unbinned_grouped<%d> (threads=points, TMA-staged event tiles)" % C,
+                        "bound": "fp64", "achieved": flops_alg / k2 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                        "frac": flops_alg / k2 / 1e12 / fp64_peak, "traffic": None,
+                        "peak_source": "bi_bench_fp64_fma measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
+                        "flops_alg_per_point_event": 2 * C * S + 2 * S, "ms": k2 * 1e3,
+                        "share_of_step": k2 * 1e3 / (total_ms / args.steps),
+                        "points_in_kernel": int(n_grouped),
+                        "hbm": {"bytes_alg": bytes_alg, "achieved_gbs": bytes_alg / k2 / 1e9,
+                                "peak_gbs": peaks["hbm_gbs"], "frac": bytes_alg / k2 / 1e9 / peaks["hbm_gbs"],
+                                "note": "shared-dataset scan: the anchor tensor is read once per launch, "
+                                        "so this kernel is FP64-pipe bound, not HBM bound (SURVEY.md 8d)"}}
+        cpu = cpu_baseline_single_core(args.events) if not args.skip_cpu else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config(n_events, P),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1e3 * e2e_total_max / args.steps},
+                "gpu_launches": int(launches_timed),
+                "launches_per_step": launches_timed / args.steps,
+                "roofline": roofline, "roofline_stream": stream_info, "cpu_baseline": cpu,
+                "clocks": clocks, "fp64_fma_peak_tflops": fp64_peak,
+                "set_data_s": set_data_s, "model_build_s": build_s,
+                "plan": {"grouped_points": int(n_grouped), "stream_points": int(len(plan.stream_points)),
+                         "work_items": int(len(plan.work))},
+                "step_ms_min_max": [float(np.min(step_ms)), float(np.max(step_ms))]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--points", type=int, default=4096)
+    ap.add_argument("--events", type=int, default=None, help="fix the number of events (default: Poisson ~100k)")
+    ap.add_argument("--stream-events", type=int, default=8 * 1024 * 1024)
+    ap.add_argument("--skip-stream", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--ref-points-per-core", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

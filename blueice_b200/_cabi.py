@@ -31,7 +31,8 @@ SIGNATURES = {
     "bi_unbinned_partials_grouped": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p,
                                                     _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
                                                     _c_void_p, _c_void_p]),
-    "bi_unbinned_finalize": (ctypes.c_int, [_c_void_p, _i64, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p]),
+    "bi_unbinned_finalize": (ctypes.c_int, [_c_void_p, _i64, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
+                                            _c_void_p]),
     "bi_unbinned_ps": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p, _c_void_p,
                                       _i64, _c_void_p]),
     "bi_hist_lookup": (ctypes.c_int, [_c_void_p, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _i64, _i64,

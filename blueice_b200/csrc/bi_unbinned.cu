@@ -161,18 +161,27 @@ __device__ __forceinline__ void bi_mbar_expect_tx(uint64_t* bar, unsigned bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bi_smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void bi_mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ bool bi_mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bi_smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bi_smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// Bounded wait: a byte-count bug would otherwise hang the GPU; after ~2 s of polling the kernel traps
+// (a reported CUDA error) instead of spinning forever.
+__device__ __forceinline__ void bi_mbar_wait(uint64_t* bar, unsigned parity) {
+    if (bi_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!bi_mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bi_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
@@ -418,12 +427,15 @@ k_unbinned_grouped(const double* __restrict__ A, int64_t ld, int64_t N, int S, i
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 k_unbinned_finalize(const double* __restrict__ partial, int64_t n_super, const double* __restrict__ musum,
-                    const int32_t* __restrict__ status, double* __restrict__ logl) {
+                    const int32_t* __restrict__ status, double* __restrict__ logl, double* __restrict__ logsum) {
     __shared__ double warp_tot[8];
     const int64_t p = blockIdx.x;
     const int t = threadIdx.x;
     if (status[p] != 0) {                                     // block-uniform
-        if (t == 0) logl[p] = -__longlong_as_double(0x7ff0000000000000LL);
+        if (t == 0) {
+            logl[p] = -__longlong_as_double(0x7ff0000000000000LL);
+            if (logsum) logsum[p] = 0.0;
+        }
         return;
     }
     double u = 0.0;
@@ -436,6 +448,7 @@ k_unbinned_finalize(const double* __restrict__ partial, int64_t n_super, const d
         const double total = __dadd_rn(__dadd_rn(__dadd_rn(warp_tot[0], warp_tot[1]), __dadd_rn(warp_tot[2], warp_tot[3])),
                                        __dadd_rn(__dadd_rn(warp_tot[4], warp_tot[5]), __dadd_rn(warp_tot[6], warp_tot[7])));
         logl[p] = __dadd_rn(-musum[p], total);               // likelihood.py:690
+        if (logsum) logsum[p] = total;                       // sum_i log p_i alone (event-sharded evaluation)
     }
 }
 
@@ -588,12 +601,13 @@ extern "C" int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t
 }
 
 extern "C" int bi_unbinned_finalize(const double* partial_dev, int64_t n_super, const double* musum_dev,
-                                    const int32_t* status_dev, int64_t n_points, double* logl_dev, void* stream) {
+                                    const int32_t* status_dev, int64_t n_points, double* logl_dev,
+                                    double* logsum_dev, void* stream) {
     BI_REQUIRE(n_points >= 0 && n_super >= 0, "negative size");
     if (n_points == 0) return BI_OK;
     BI_REQUIRE(musum_dev && status_dev && logl_dev && (n_super == 0 || partial_dev), "bi_unbinned_finalize: NULL pointer");
     k_unbinned_finalize<<<(unsigned)n_points, 256, 0, (cudaStream_t)stream>>>(partial_dev, n_super, musum_dev,
-                                                                              status_dev, logl_dev);
+                                                                              status_dev, logl_dev, logsum_dev);
     BI_LAUNCH_CHECK();
     return BI_OK;
 }

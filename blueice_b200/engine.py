@@ -114,6 +114,57 @@ class PointPlan(object):
         self.work = work                        # int32 [n_work, 4]
 
 
+def plan_points(grid, zs, n_sources, n_super, force_kernel=None):
+    """Host-side schedule of a batch (pure function; results never depend on it).
+
+    Points whose hypercube cell is shared by at least _GROUP_MIN_POINTS points of the batch go to the
+    grouped kernel in chunks of <= GROUP_POINTS points x ranges of superblocks; all other in-range
+    points go to the streaming kernel; out-of-range points get no work (their result is -inf)."""
+    P = len(zs)
+    in_range = grid.in_range(zs) if grid.n_dims else np.ones(P, dtype=bool)
+    idx = np.nonzero(in_range)[0]
+    can_group = (n_sources <= _cabi.GROUP_MAX_SOURCES and grid.n_corners <= _cabi.GROUP_MAX_CORNERS
+                 and n_super > 0 and force_kernel != 'stream')
+    stream_pts = idx
+    group_pts = np.zeros(0, dtype=np.int64)
+    work = np.zeros((0, 4), dtype=np.int32)
+    min_pts = 1 if force_kernel == 'grouped' else _GROUP_MIN_POINTS
+    if can_group and len(idx) >= min_pts:
+        if grid.n_dims:
+            cells = grid.cell_ids(np.asarray(zs, dtype=np.float64).reshape(P, grid.n_dims)[idx])
+        else:
+            cells = np.zeros(len(idx), dtype=np.int64)
+        order = np.argsort(cells, kind='stable')
+        sorted_cells = cells[order]
+        sorted_idx = idx[order]
+        starts = np.flatnonzero(np.r_[True, sorted_cells[1:] != sorted_cells[:-1]])
+        ends = np.r_[starts[1:], len(sorted_cells)]
+        big = (ends - starts) >= min_pts
+        keep = np.zeros(len(sorted_idx), dtype=bool)
+        chunks = []
+        pos = 0
+        for s0, e0 in zip(starts[big], ends[big]):
+            keep[s0:e0] = True
+            n = e0 - s0
+            for c0 in range(0, n, _cabi.GROUP_POINTS):
+                chunks.append((pos + c0, min(_cabi.GROUP_POINTS, n - c0)))
+            pos += n
+        group_pts = sorted_idx[keep]
+        stream_pts = np.sort(sorted_idx[~keep])
+        if chunks:
+            n_ranges = int(np.clip(_GROUP_TARGET_ITEMS // len(chunks), 1, n_super))
+            sb_per = -(-n_super // n_ranges)
+            sb_begin = np.arange(0, n_super, sb_per, dtype=np.int64)
+            sb_end = np.minimum(sb_begin + sb_per, n_super)
+            ch = np.asarray(chunks, dtype=np.int64)
+            work = np.empty((len(ch) * len(sb_begin), 4), dtype=np.int32)
+            work[:, 0] = np.repeat(ch[:, 0], len(sb_begin))
+            work[:, 1] = np.repeat(ch[:, 1], len(sb_begin))
+            work[:, 2] = np.tile(sb_begin, len(ch))
+            work[:, 3] = np.tile(sb_end, len(ch))
+    return PointPlan(P, in_range, stream_pts.astype(np.int32), group_pts.astype(np.int32), work)
+
+
 class _EngineBase(object):
     def __init__(self, grid, mus_anchor, allow_negative=None, device=None):
         torch = require_cuda()
@@ -266,50 +317,7 @@ class UnbinnedEngine(_EngineBase):
     # -- planning (host) ------------------------------------------------------------------------
     def plan(self, zs):
         """Bucket points by hypercube cell and split the work between the two K2 kernels."""
-        P = len(zs)
-        grid = self.grid
-        in_range = grid.in_range(zs) if grid.n_dims else np.ones(P, dtype=bool)
-        idx = np.nonzero(in_range)[0]
-        can_group = (self.n_sources <= _cabi.GROUP_MAX_SOURCES and grid.n_corners <= _cabi.GROUP_MAX_CORNERS
-                     and self.n_super > 0 and self.force_kernel != 'stream')
-        stream_pts = idx
-        group_pts = np.zeros(0, dtype=np.int64)
-        work = np.zeros((0, 4), dtype=np.int32)
-        min_pts = 1 if self.force_kernel == 'grouped' else _GROUP_MIN_POINTS
-        if can_group and len(idx) >= min_pts:
-            cells = grid.cell_ids(np.asarray(zs, dtype=np.float64).reshape(P, grid.n_dims)[idx]) if grid.n_dims \
-                else np.zeros(len(idx), dtype=np.int64)
-            order = np.argsort(cells, kind='stable')
-            sorted_cells = cells[order]
-            sorted_idx = idx[order]
-            starts = np.flatnonzero(np.r_[True, sorted_cells[1:] != sorted_cells[:-1]])
-            ends = np.r_[starts[1:], len(sorted_cells)]
-            big = (ends - starts) >= min_pts
-            chunks = []
-            keep = np.zeros(len(sorted_idx), dtype=bool)
-            for s0, e0 in zip(starts[big], ends[big]):
-                keep[s0:e0] = True
-            group_pts = sorted_idx[keep]
-            stream_pts = np.sort(sorted_idx[~keep])
-            # positions of the kept runs inside group_pts
-            pos = 0
-            for s0, e0 in zip(starts[big], ends[big]):
-                n = e0 - s0
-                for c0 in range(0, n, _cabi.GROUP_POINTS):
-                    chunks.append((pos + c0, min(_cabi.GROUP_POINTS, n - c0)))
-                pos += n
-            if chunks:
-                n_ranges = int(np.clip(_GROUP_TARGET_ITEMS // len(chunks), 1, self.n_super))
-                sb_per = -(-self.n_super // n_ranges)
-                sb_begin = np.arange(0, self.n_super, sb_per, dtype=np.int64)
-                sb_end = np.minimum(sb_begin + sb_per, self.n_super)
-                ch = np.asarray(chunks, dtype=np.int64)
-                work = np.empty((len(ch) * len(sb_begin), 4), dtype=np.int32)
-                work[:, 0] = np.repeat(ch[:, 0], len(sb_begin))
-                work[:, 1] = np.repeat(ch[:, 1], len(sb_begin))
-                work[:, 2] = np.tile(sb_begin, len(ch))
-                work[:, 3] = np.tile(sb_end, len(ch))
-        return PointPlan(P, in_range, stream_pts.astype(np.int32), group_pts.astype(np.int32), work)
+        return plan_points(self.grid, zs, self.n_sources, self.n_super, self.force_kernel)
 
     def upload_plan(self, plan):
         """H2D of the schedule (one pinned buffer).  Returns device views + byte count."""
@@ -356,36 +364,49 @@ class UnbinnedEngine(_EngineBase):
             _cabi.check(rc, "bi_unbinned_partials_grouped")
             self.launches += 1
         logl = self.ws.get("logl", P, torch.float64)
+        logsum = self.ws.get("logsum", P, torch.float64)
+        o["logsum"] = logsum
         rc = self.lib.bi_unbinned_finalize(_cabi.dev_ptr(partial), self.n_super, _cabi.dev_ptr(o["musum"]),
-                                           _cabi.dev_ptr(o["status"]), P, _cabi.dev_ptr(logl), st)
+                                           _cabi.dev_ptr(o["status"]), P, _cabi.dev_ptr(logl),
+                                           _cabi.dev_ptr(logsum), st)
         _cabi.check(rc, "bi_unbinned_finalize")
         self.launches += 1
         if want_setup:
             return logl, o
         return logl
 
-    def evaluate(self, zs, mult, scale=None, eff=None, return_status=False):
-        """Host buffers in, host buffers out (the e2e path): H2D, K1, K2, finalize, D2H."""
+    def evaluate(self, zs, mult, scale=None, eff=None, return_status=False, return_parts=False):
+        """Host buffers in, host buffers out (the e2e path): H2D, K1, K2, finalize, D2H.
+
+        return_parts=True returns (sum_i log p_i [P], sum_s mu_s [P], status [P]) instead: the terms an
+        event-sharded evaluation combines across ranks."""
         torch = self.torch
         P = len(mult)
         if P == 0:
+            if return_parts:
+                return np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int32)
             return (np.zeros(0), np.zeros(0, dtype=np.int32)) if return_status else np.zeros(0)
         zs = np.asarray(zs, dtype=np.float64).reshape(P, self.grid.n_dims)
         plan = self.plan(zs)
         zs_d, mult_d, scale_d, eff_d, nbytes = self._upload_points(zs, mult, scale, eff)
         plan_dev = self.upload_plan(plan)
         logl, o = self.run_device(P, zs_d, mult_d, scale_d, eff_d, plan, plan_dev[:3], want_setup=True)
-        out_pin = self.ws.get("d2h", P, torch.float64, pinned=True)
-        out_pin.copy_(logl, non_blocking=True)
+        out_pin = self.ws.get("d2h", 3 * P, torch.float64, pinned=True)
+        out_pin[:P].copy_(logl, non_blocking=True)
+        if return_parts:
+            out_pin[P:2 * P].copy_(o["logsum"], non_blocking=True)
+            out_pin[2 * P:].copy_(o["musum"], non_blocking=True)
         st_pin = self.ws.get("d2h_status", P, torch.int32, pinned=True)
         st_pin.copy_(o["status"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         self.last_h2d_bytes = nbytes + plan_dev[3]
-        self.last_d2h_bytes = P * 12
+        self.last_d2h_bytes = P * (28 if return_parts else 12)
         res = out_pin.numpy().copy()
+        if return_parts:
+            return res[P:2 * P], res[2 * P:], st_pin.numpy().copy()
         if return_status:
-            return res, st_pin.numpy().copy()
-        return res
+            return res[:P], st_pin.numpy().copy()
+        return res[:P]
 
     def ps(self, z_row, mult_row, scale=None, eff=None):
         """(mus [S], ps [S, N]) for one point in the reference's operation order (full_output=True)."""

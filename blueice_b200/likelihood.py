@@ -276,15 +276,19 @@ class LogLikelihoodBase(object):
         :param names: parameter names of the columns; default self.parameter_names()
         :returns: float64 [P]; row p equals self(**dict(zip(names, params[p])), livetime_days=...)
         """
+        zs, mult = self._rows_from_params(params, names)
+        return self._evaluate_rows(self._engine, zs, mult, livetime_days, scalar=False)
+
+    def _rows_from_params(self, params, names):
+        """(zs [P, D], rate multipliers [P, S]) from a parameter table, defaults filled in like __call__."""
         names = self.parameter_names() if names is None else list(names)
         params = np.asarray(params, dtype=np.float64)
         if params.ndim == 1:
-            params = params.reshape(-1, max(len(names), 1)) if len(names) != 1 else params.reshape(-1, 1)
+            params = params.reshape(-1, max(len(names), 1))
         if params.ndim != 2 or params.shape[1] != len(names):
             raise ValueError("params must have shape [n_points, %d]" % len(names))
         P = params.shape[0]
-        # validate names exactly like __call__ does
-        self._kwargs_to_settings(**{n: 1.0 for n in names})
+        self._kwargs_to_settings(**{n: 1.0 for n in names})          # same name validation as __call__
         defaults_mult, defaults_settings = self._kwargs_to_settings()
         zs = np.empty((P, len(self.shape_parameters)), dtype=np.float64)
         for j, name in enumerate(self.shape_parameters):
@@ -293,7 +297,7 @@ class LogLikelihoodBase(object):
         for j, source_name in enumerate(self.source_name_list):
             key = source_name + _RATE_SUFFIX
             mult[:, j] = params[:, names.index(key)] if key in names else defaults_mult[j]
-        return self._evaluate_rows(self._engine, zs, mult, livetime_days, scalar=False)
+        return zs, mult
 
     def _livetime_scale(self, livetime_days):
         """Factor applied to all mus (likelihood.py:374-382); None when no scaling happens."""
@@ -488,6 +492,17 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
 
     def _device_loglikelihood(self, engine, zs, mult, scale, eff):
         return engine.evaluate(zs, mult, scale, eff, return_status=True)
+
+    @_needs_data
+    def batch_parts(self, params, names=None, livetime_days=None):
+        """(sum_i log f_i [P], sum_s mu_s [P], status [P], prior sum [P]) of this likelihood's events:
+        the terms combined across ranks when events are sharded over GPUs (blueice_b200.distributed)."""
+        zs, mult = self._rows_from_params(params, names)
+        scale, _ = self._livetime_scale(livetime_days)
+        scale_arr = None if scale is None else np.full(len(mult), scale, dtype=np.float64)
+        logsum, musum, status = self._engine.evaluate(zs, mult, scale_arr, self._efficiencies(zs),
+                                                      return_parts=True)
+        return logsum, musum, status, self._prior_sum(zs, mult)
 
     def _full_output(self, engine, z_row, mult_row, scale, eff_row, result):
         mus, ps = engine.ps(z_row, mult_row, scale, eff_row)

@@ -221,6 +221,8 @@ class MonteCarloSource(DensityEstimatingSource):
 
     def get_events_for_density_estimate(self):
         wanted = self.config['n_events_for_pdf'] * self.config['pdf_sampling_multiplier']
-        batch = min(self.config['pdf_sampling_batch_size'], wanted)
+        batch = self.config['pdf_sampling_batch_size']
+        if wanted <= batch:
+            batch = wanted
         for _ in range(int(wanted // batch)):
             yield self.simulate(n_events=batch), batch

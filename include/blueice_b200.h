@@ -137,9 +137,12 @@ int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t ld_events,
                                  double outlier_likelihood, double* partial_dev, void* stream);
 
 /* logL[p] = -musum[p] + total(partial[p, :]) in canonical order; status != 0 -> -inf.
- * (likelihood.py:690 `-mu.sum() + np.sum(np.log(p_events))`, :347/:402 soft failures.) */
+ * (likelihood.py:690 `-mu.sum() + np.sum(np.log(p_events))`, :347/:402 soft failures.)
+ * logsum_dev (may be NULL) receives total(partial[p, :]) alone: the per-shard term that is summed over
+ * ranks when the events are sharded across GPUs. */
 int bi_unbinned_finalize(const double* partial_dev, int64_t n_super, const double* musum_dev,
-                         const int32_t* status_dev, int64_t n_points, double* logl_dev, void* stream);
+                         const int32_t* status_dev, int64_t n_points, double* logl_dev,
+                         double* logsum_dev, void* stream);
 
 /* Morphed per-event pdf values ps[S, N] for ONE point (full_output=True, likelihood.py:424-425). */
 int bi_unbinned_ps(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,

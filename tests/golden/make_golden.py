@@ -1,0 +1,187 @@
+"""Generate golden vectors by running the UNMODIFIED reference (JelleAalbers/blueice v1.2.1).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    cd /tmp/somewhere && python /root/repo/tests/golden/make_golden.py
+
+The reference needs `multihist` and `atomicwrites`, which are not installable here; the two
+test-only stand-ins under tests/golden/_shims are put on sys.path for this script alone
+(the reference's own 30 tests pass with them).  Outputs: tests/golden/*.npz,
+small enough to commit; tests/test_golden_*.py replay them through blueice_b200 and the oracle.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, '_shims'))
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, REPO)
+
+os.chdir(tempfile.mkdtemp(prefix='blueice_golden_'))     # the reference writes ./pdf_cache
+
+import blueice                                            # noqa: E402  (the reference)
+from blueice.likelihood import BinnedLogLikelihood, UnbinnedLogLikelihood   # noqa: E402
+from blueice.source import HistogramPdfSource             # noqa: E402
+from blueice.test_helpers import conf_for_test            # noqa: E402
+from multihist import Histdd                              # noqa: E402  (shim)
+
+import bench_workloads as wl                              # noqa: E402
+
+assert blueice.__version__ == '1.2.1'
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print('wrote', path, {k: np.asarray(v).shape for k, v in arrays.items()})
+
+
+def special_points(zs, mult, axes):
+    """Append points on anchors, on the grid boundary, out of range, and with odd rate multipliers."""
+    zs, mult = zs.copy(), mult.copy()
+    k = 0
+    for d, a in enumerate(axes):
+        for v in (a[0], a[len(a) // 2], a[-1]):
+            zs[k, d] = v
+            k += 1
+    zs[k, 0] = axes[0][-1] + 0.5; k += 1          # out of range -> -inf
+    zs[k, 0] = np.nan; k += 1                     # NaN -> -inf
+    mult[k, 0] = 0.0; k += 1                      # zero rate
+    mult[k, 0] = -1.0; k += 1                     # unphysical -> -inf
+    mult[k, -1] = np.inf; k += 1                  # unphysical -> -inf
+    return zs, mult
+
+
+# ---------------------------------------------------------------------------------------------
+# G1: config 1 (Gaussian source, analytic pdf, mu with 3 anchors)
+# ---------------------------------------------------------------------------------------------
+def golden_c1():
+    lf = UnbinnedLogLikelihood(conf_for_test(n_sources=1))
+    lf.add_rate_parameter('s0')
+    lf.add_shape_parameter('mu', {-2: -2, 0: 0, 2: 2})
+    lf.prepare()
+    np.random.seed(0)
+    d = lf.base_model.simulate()
+    lf.set_data(d)
+    zs, mult = wl.scan_points(64, 1, 1, seed=1, mult_range=(0.5, 2.0))
+    zs, mult = special_points(zs, mult, [np.array([-2., 0., 2.])])
+    logl = np.array([lf(mu=float(z[0]), s0_rate_multiplier=float(m[0])) for z, m in zip(zs, mult)])
+    full = [lf(mu=float(zs[i, 0]), s0_rate_multiplier=float(mult[i, 0]), full_output=True) for i in (20, 21)]
+    save('c1_gaussian', x=d['x'], zs=zs, mult=mult, logl=logl,
+         full_index=np.array([20, 21]), full_mus=np.array([f[1] for f in full]),
+         full_ps=np.array([f[2] for f in full]))
+
+
+# ---------------------------------------------------------------------------------------------
+# G2: config-2-shaped (histogram templates, 2 shape parameters), linear and piecewise lookup
+# ---------------------------------------------------------------------------------------------
+def golden_c2(method):
+    n_sources, n_shape, anchors, bins = 2, 2, (-1., 0., 1.), (20, 16)
+    axes, edges, templates, mus = wl.c2_arrays(n_sources, n_shape, anchors, bins)
+    names = ['cs1', 'cs2']
+    params = ['shift1', 'shift2']
+    cls = wl.array_source_class(HistogramPdfSource, Histdd, axes, edges, names, mus, templates, None, params)
+    lf = UnbinnedLogLikelihood(wl.array_model_config(cls, edges, names, n_sources, params, method))
+    for s in range(n_sources):
+        lf.add_rate_parameter('src%d' % s)
+    for p in params:
+        lf.add_shape_parameter(p, anchors)
+    lf.prepare()
+    x, y = wl.c2_events(templates, mus * 4e-3, edges, seed=7)          # ~400 events
+    # put some events exactly on bin edges / bin centres / the space boundary
+    x[:4] = [0., 100., 50., 52.5]
+    y[:4] = [0., 4., 2., 2.125]
+    d = np.zeros(len(x), dtype=[('cs1', float), ('cs2', float), ('source', int)])
+    d['cs1'], d['cs2'] = x, y
+    lf.set_data(d)
+    zs, mult = wl.scan_points(48, n_shape, n_sources, seed=2, z_range=(-1., 1.))
+    zs, mult = special_points(zs, mult, axes)
+    logl = np.array([lf(shift1=float(z[0]), shift2=float(z[1]), src0_rate_multiplier=float(m[0]),
+                        src1_rate_multiplier=float(m[1])) for z, m in zip(zs, mult)])
+    full = [lf(shift1=float(zs[i, 0]), shift2=float(zs[i, 1]), src0_rate_multiplier=float(mult[i, 0]),
+               src1_rate_multiplier=float(mult[i, 1]), full_output=True) for i in (30, 31)]
+    # the dense anchor tensor of the reference itself (pdf_morphers.py:59-65)
+    ps_anchor = np.array([[lf.anchor_models[(a, b)].score_events(d) for b in anchors] for a in anchors])
+    save('c2_templates_' + method, x=x, y=y, zs=zs, mult=mult, logl=logl, ps_anchor=ps_anchor,
+         full_index=np.array([30, 31]), full_mus=np.array([f[1] for f in full]),
+         full_ps=np.array([f[2] for f in full]))
+
+
+# ---------------------------------------------------------------------------------------------
+# G3: binned likelihood, with and without Beeston-Barlow, 3-D bins, 3 sources, 2 shape parameters
+# ---------------------------------------------------------------------------------------------
+def golden_binned(bb):
+    bins, n_sources, n_shape, anchors = (6, 5, 4), 3, 2, (-1., 0., 1.)
+    axes, edges, mus, pmf, n_model, observed = wl.c3_arrays(bins, n_sources, n_shape, anchors, seed=3,
+                                                            total_events=600.)
+    vol = np.ones(1)
+    for e in edges:
+        vol = np.multiply.outer(vol, np.diff(e))
+    density = pmf / vol.reshape(bins)
+    names = ['x', 'y', 'z']
+    params = ['za', 'zb']
+    cls = wl.array_source_class(HistogramPdfSource, Histdd, axes, edges, names, mus, density, n_model, params)
+    likelihood_config = ({'model_statistical_uncertainty_handling': 'bb_single', 'bb_single_source': 0}
+                         if bb else None)
+    lf = BinnedLogLikelihood(wl.array_model_config(cls, edges, names, n_sources, params), likelihood_config)
+    for s in range(n_sources):
+        lf.add_rate_parameter('src%d' % s)
+    for p in params:
+        lf.add_shape_parameter(p, anchors)
+    lf.prepare()
+    cols = wl.events_from_counts(edges, observed, seed=5)
+    d = np.zeros(len(cols[0]), dtype=[('x', float), ('y', float), ('z', float), ('source', int)])
+    d['x'], d['y'], d['z'] = cols
+    lf.set_data(d)
+    assert np.array_equal(lf.data_events_per_bin.histogram, observed)
+    zs, mult = wl.scan_points(40, n_shape, n_sources, seed=4, z_range=(-1., 1.), mult_range=(0.6, 1.4))
+    zs, mult = special_points(zs, mult, axes)
+    logl, raises = [], []
+    for z, m in zip(zs, mult):
+        try:
+            logl.append(lf(za=float(z[0]), zb=float(z[1]), **{'src%d_rate_multiplier' % s: float(m[s])
+                                                            for s in range(n_sources)}))
+            raises.append(False)
+        except AssertionError:        # Beeston-Barlow asserts (likelihood.py:649,655), e.g. zero rate -> 0/0
+            logl.append(np.nan)
+            raises.append(True)
+    full = [lf(za=float(zs[i, 0]), zb=float(zs[i, 1]), full_output=True,
+               **{'src%d_rate_multiplier' % s: float(mult[i, s]) for s in range(n_sources)}) for i in (30, 31)]
+    save('binned_bb' if bb else 'binned_plain', x=d['x'], y=d['y'], z=d['z'], observed=observed,
+         zs=zs, mult=mult, logl=np.array(logl), raises=np.array(raises), full_index=np.array([30, 31]),
+         full_mus=np.array([f[1] for f in full]), full_pmfs=np.array([f[2] for f in full]))
+
+
+# ---------------------------------------------------------------------------------------------
+# G4: values of the reference's own test scenarios on seeded data (tests/test_likelihood.py:124-148)
+# ---------------------------------------------------------------------------------------------
+def golden_multisource():
+    lf = UnbinnedLogLikelihood(conf_for_test(n_sources=2))
+    lf.add_shape_parameter('some_multiplier', (0.5, 1, 2, 4))
+    lf.add_rate_parameter('s0')
+    lf.add_rate_parameter('s1')
+    lf.prepare()
+    np.random.seed(42)
+    d = lf.base_model.simulate()
+    lf.set_data(d)
+    calls = [dict(), dict(s0_rate_multiplier=2.), dict(s1_rate_multiplier=2.), dict(s0_rate_multiplier=4.),
+             dict(s0_rate_multiplier=2.5, s1_rate_multiplier=2.5), dict(s0_rate_multiplier=2., s1_rate_multiplier=2.),
+             dict(some_multiplier=2.), dict(some_multiplier=3.3, s0_rate_multiplier=0.7), dict(some_multiplier=0.5),
+             dict(some_multiplier=4.), dict(some_multiplier=0.75, s1_rate_multiplier=1.2)]
+    names = ['s0_rate_multiplier', 's1_rate_multiplier', 'some_multiplier']
+    table = np.array([[c.get(n, 1.) for n in names] for c in calls])
+    logl = np.array([lf(**c) for c in calls])
+    save('multisource', x=d['x'], params=table, logl=logl)
+
+
+if __name__ == '__main__':
+    golden_c1()
+    golden_c2('linear')
+    golden_c2('piecewise')
+    golden_binned(False)
+    golden_binned(True)
+    golden_multisource()

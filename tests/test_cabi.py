@@ -1,0 +1,84 @@
+"""The C-ABI library loads on a CPU-only box and exports exactly what include/blueice_b200.h declares.
+No compute calls: argument validation happens before any CUDA call, so error paths are testable here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+from blueice_b200 import _build, _cabi
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "blueice_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bi_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    path = _build.build()
+    assert os.path.dirname(path) == os.path.dirname(_build.__file__)
+    assert os.path.exists(path)
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _cabi.load()
+    names = declared_functions()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), "symbol %s declared in the header is not exported" % name
+        assert name in _cabi.SIGNATURES, "symbol %s has no ctypes signature" % name
+    for name in _cabi.SIGNATURES:
+        assert name in names, "ctypes signature %s is not declared in the header" % name
+
+
+def test_header_constants_match_python_mirror():
+    text = open(HEADER).read()
+    consts = dict(re.findall(r"#define\s+BI_([A-Z0-9_]+)\s+(-?\d+)", text))
+    assert int(consts["MAX_DIMS"]) == _cabi.MAX_DIMS
+    assert int(consts["MAX_SOURCES"]) == _cabi.MAX_SOURCES
+    assert int(consts["EVENT_BLOCK"]) == _cabi.EVENT_BLOCK
+    assert int(consts["SUPERBLOCK"]) == _cabi.SUPERBLOCK
+    assert int(consts["GROUP_POINTS"]) == _cabi.GROUP_POINTS
+    assert int(consts["GROUP_MAX_SOURCES"]) == _cabi.GROUP_MAX_SOURCES
+    assert int(consts["MAX_AXIS_POINTS"]) == _cabi.MAX_AXIS_POINTS
+    assert int(consts["ABI_VERSION"]) == _cabi.load().bi_abi_version()
+
+
+def test_superblock_count():
+    lib = _cabi.load()
+    assert lib.bi_num_superblocks(0) == 0
+    assert lib.bi_num_superblocks(1) == 1
+    assert lib.bi_num_superblocks(512) == 1
+    assert lib.bi_num_superblocks(513) == 2
+    assert lib.bi_num_superblocks(100000) == 196
+    assert lib.bi_binned_scratch_doubles(3, 1000) == 3 * (2 * 2 + 1)
+
+
+def test_argument_validation_reports_errors_without_a_gpu():
+    lib = _cabi.load()
+    n_anchors = _cabi.as_i32([3] * 7)
+    axes = _cabi.as_f64(np.zeros(21))
+    rc = lib.bi_point_setup(7, _cabi.host_ptr(n_anchors), _cabi.host_ptr(axes), 1, 1, None, None, None, None, None,
+                            None, None, None, None, None, None, None, None, None)
+    assert rc == -1 and b"n_dims" in lib.bi_last_error()
+    # non-increasing anchor axis
+    n_anchors = _cabi.as_i32([3])
+    axes = _cabi.as_f64([0., 2., 1.])
+    rc = lib.bi_point_setup(1, _cabi.host_ptr(n_anchors), _cabi.host_ptr(axes), 1, 1, None, None, None, None, None,
+                            None, None, None, None, None, None, None, None, None)
+    assert rc == -1 and b"increasing" in lib.bi_last_error()
+    # odd leading dimension of the anchor tensor
+    rc = lib.bi_unbinned_partials_stream(ctypes.c_void_p(16), 7, 7, 1, 1, None, 1, None, None, None, None, 1e-12,
+                                         None, None)
+    assert rc == -1 and b"ld_events" in lib.bi_last_error()
+    # unknown lookup method
+    rc = lib.bi_hist_lookup(None, 1, 1, _cabi.host_ptr(_cabi.as_i32([4])), _cabi.host_ptr(_cabi.as_f64(np.arange(5.))),
+                            None, 0, 0, 9, None, 0, None, None)
+    assert rc == -1 and b"method" in lib.bi_last_error()
+    # grouped kernel limits
+    rc = lib.bi_unbinned_partials_grouped(ctypes.c_void_p(16), 64, 64, 9, 4, None, None, 1, None, None, None, None,
+                                          1e-12, None, None)
+    assert rc == -1 and b"sources" in lib.bi_last_error()

@@ -1,0 +1,216 @@
+"""Host-side logic of the API mirror that needs no device: parameter bookkeeping and errors, config
+handling of Model/Source, histogram semantics, anchor-grid ordering, batch planning, objectives."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+import blueice_b200 as bi
+from blueice_b200 import engine, pdf_morphers
+from blueice_b200.exceptions import (InvalidParameter, InvalidParameterSpecification, NoOpimizationNecessary,
+                                     NoShapeParameters, NotPreparedException)
+from blueice_b200.hist import Histdd
+from blueice_b200.model import Model
+from blueice_b200.test_helpers import FixedSampleSource, conf_for_test, make_data
+from blueice_b200.utils import arrays_to_grid, combine_dicts, deterministic_hash, InterpolateAndExtrapolate1D
+from oracle import hist as ohist
+from oracle import morph as omorph
+
+
+def test_package_exposes_reference_names():
+    for name in ['Model', 'Source', 'HistogramPdfSource', 'DensityEstimatingSource', 'MonteCarloSource',
+                 'UnbinnedLogLikelihood', 'BinnedLogLikelihood', 'LogLikelihoodSum', 'InvalidParameter',
+                 'NotPreparedException', 'OptimizationFailed', 'PDFNotComputedException']:
+        assert hasattr(bi, name)
+    for method in ['bestfit_scipy', 'one_parameter_interval', 'make_objective', 'best_anchor', 'batch']:
+        assert hasattr(bi.UnbinnedLogLikelihood, method)
+
+
+def test_model_rates_and_source_lookup():
+    # mirrors tests/test_model.py of the reference
+    m = Model(conf_for_test(n_sources=1))
+    np.testing.assert_array_equal(m.expected_events(), np.array([1000]))
+    m.sources[0].fraction_in_range = 0.5
+    np.testing.assert_array_equal(m.expected_events(), np.array([500]))
+    conf = conf_for_test(n_sources=2)
+    conf['some_multiplier'] = 2
+    m = Model(conf)
+    np.testing.assert_array_equal(m.expected_events(), np.array([2000, 2000]))
+    assert m.get_source(1) == m.sources[1]
+    assert m.get_source_i('s1') == 1 and m.get_source_i(1) == 1
+    with pytest.raises(ValueError):
+        m.get_source_i('nope')
+    conf = conf_for_test(n_sources=1)
+    conf['strlen_multiplier'] = 'hi'
+    np.testing.assert_array_equal(Model(conf).expected_events(), np.array([2000]))
+    with pytest.raises(ValueError):
+        Model(conf_for_test(rate_multiplier=3))
+    assert Model(conf_for_test(events_per_day=1)).expected_events().dtype == np.float64
+
+
+def test_per_source_rate_multiplier_setting():
+    conf = conf_for_test(n_sources=2, s1_rate_multiplier=3)
+    m = Model(conf)
+    np.testing.assert_array_equal(m.expected_events(), np.array([1000., 3000.]))
+    assert all('s1_rate_multiplier' not in s.config for s in m.sources)
+
+
+def test_range_cut_is_closed_interval():
+    m = Model(conf_for_test())
+    d = np.zeros(4, dtype=[('x', float), ('source', int)])
+    d['x'] = [-10, 10, -10.0001, 3]
+    assert len(m.range_cut(d)) == 3
+
+
+def test_density_estimating_source_histogram():
+    data, n = make_data([dict(n_events=24, x=0.5), dict(n_events=56, x=1.5), dict(n_events=20, x=7.)])
+    conf = conf_for_test(events_per_day=42, analysis_space=[['x', [0, 1, 5]]],
+                         default_source_class=FixedSampleSource, data=data)
+    s = Model(conf).sources[0]
+    assert s.fraction_in_range == 0.8
+    pmf, n_ev = s.get_pmf_grid()
+    np.testing.assert_allclose(pmf, [0.3, 0.7])
+    np.testing.assert_array_equal(n_ev, [24, 56])
+    assert s.expected_events == 42 * 0.8
+
+
+def test_histdd_matches_oracle_rules():
+    rng = np.random.default_rng(3)
+    edges = [np.linspace(0, 1, 6), np.array([0., 0.5, 2., 3.])]
+    x = np.r_[edges[0], rng.uniform(-0.2, 1.2, 500)]
+    y = np.r_[edges[1], 1.0, 1.0, rng.uniform(-0.5, 3.5, 500)]
+    h = Histdd(x, y, bins=edges)
+    np.testing.assert_array_equal(h.histogram, ohist.histogramdd(edges, [x, y]))
+    h.histogram = rng.random(h.histogram.shape)
+    np.testing.assert_array_equal(h.lookup(x, y), ohist.lookup_piecewise(h.histogram, edges, [x, y]))
+    np.testing.assert_array_equal(h.bin_centers(0), ohist.bin_centers(edges[0]))
+    assert (h * 2.0).histogram[1, 1] == 2 * h.histogram[1, 1]
+    np.random.seed(0)
+    r = h.get_random(1000)
+    assert r.shape == (1000, 2) and r[:, 0].min() >= 0 and r[:, 1].max() <= 3
+
+
+def test_utils():
+    np.testing.assert_array_equal(arrays_to_grid([np.array([1, 2]), np.array([3, 4])]),
+                                  np.array([[[1, 3], [1, 4]], [[2, 3], [2, 4]]]))
+    assert combine_dicts(dict(a=1, b=2), dict(b=3, c=4), exclude=['c']) == dict(a=1, b=3)
+    assert deterministic_hash(dict(a=[1, 2], b=np.arange(3))) == deterministic_hash(dict(b=np.arange(3), a=[1, 2]))
+    itp = InterpolateAndExtrapolate1D([0, 1], [0, 42])
+    assert itp(3) == 42 and itp(0.5) == 21 and itp([3]) == [42]
+    assert InterpolateAndExtrapolate1D(0, 42)(3) == 42
+
+
+def test_morpher_contract_and_anchor_order():
+    with pytest.raises(NoShapeParameters):
+        pdf_morphers.GridInterpolator(config={}, shape_parameters=OrderedDict())
+    pars = OrderedDict([('a', ({2: 2, -2: -2, 0: 0}, None, None)), ('b', ({1: 'x', 0: 'y'}, None, 0))])
+    mr = pdf_morphers.MORPHERS['GridInterpolator']({}, pars)
+    pts = mr.get_anchor_points(bounds=None)
+    assert isinstance(pts, list) and isinstance(pts[0], tuple)
+    assert pts == omorph.anchor_points(omorph.anchor_axes([[2, -2, 0], [1, 0]]))
+    tensor = mr.anchor_tensor(lambda z: np.array([z[0] * 10 + z[1]]), [1], {p: p for p in pts})
+    assert tensor.shape == (3, 2, 1) and tensor[2, 1, 0] == 21 and tensor[0, 0, 0] == -20
+
+
+def test_parameter_bookkeeping_and_errors():
+    lf = bi.UnbinnedLogLikelihood(conf_for_test(n_sources=2))
+    lf.add_rate_parameter('s0')
+    with pytest.raises(InvalidParameterSpecification):
+        lf.add_shape_parameter('strlen_multiplier', {1: 'x', 2: 'hi', 3: 'wha'})
+    with pytest.raises(InvalidParameterSpecification):
+        lf.add_shape_parameter('strlen_multiplier', ['x', 'hi'])
+    with pytest.raises(InvalidParameterSpecification):
+        lf.add_shape_parameter('some_multiplier', (0.5, 1, 2), base_value=1)
+    lf.add_shape_parameter('strlen_multiplier', {1: 'q', 2: 'hi', 3: 'wha'}, base_value=1)
+    lf.add_shape_parameter('some_multiplier', (0.5, 1, 2, 4))
+    assert lf.get_bounds('some_multiplier') == (0.5, 4)
+    assert lf.get_bounds('strlen_multiplier') == (1, 3)
+    assert lf.get_bounds() == [(1, 3), (0.5, 4)]
+    assert lf.get_bounds('s0_rate_multiplier') == (0, float('inf'))
+    with pytest.raises(InvalidParameter):
+        lf.get_bounds('blargh')
+    mult, settings = lf._kwargs_to_settings(s1_rate_multiplier=2.5, some_multiplier=2)
+    assert mult == [1, 2.5] and settings == dict(strlen_multiplier=1, some_multiplier=2)
+    with pytest.raises(InvalidParameter):
+        lf._kwargs_to_settings(blargh=41)
+    with pytest.raises(ValueError):
+        lf._kwargs_to_settings(strlen_multiplier='hi')
+    with pytest.raises(ValueError):
+        lf._kwargs_to_settings(some_multiplier=np.int64(2))      # reference quirk: np.int64 is not accepted
+    assert lf.parameter_names() == ['s0_rate_multiplier', 'strlen_multiplier', 'some_multiplier']
+    d = np.zeros(3, dtype=[('x', float), ('source', int)])
+    with pytest.raises(NotPreparedException):
+        lf.set_data(d)
+    with pytest.raises(NotPreparedException):
+        lf()
+
+
+def test_allow_negative_bounds():
+    conf = conf_for_test(n_sources=2)
+    conf['sources'][1]['allow_negative'] = True
+    lf = bi.UnbinnedLogLikelihood(conf)
+    assert lf.get_bounds('s1_rate_multiplier') == (float('-inf'), float('inf'))
+    assert lf.get_bounds('s0_rate_multiplier') == (0, float('inf'))
+    assert lf.source_allowed_negative == [False, True]
+
+
+def test_make_objective_names_bounds_guesses():
+    lf = bi.UnbinnedLogLikelihood(conf_for_test(n_sources=2))
+    lf.add_rate_parameter('s0')
+    lf.add_rate_parameter('s1')
+    lf.add_shape_parameter('some_multiplier', (0.5, 1, 2, 4))
+    f, names, guess, bounds = lf.make_objective(s1_rate_multiplier=2.)
+    assert names == ['s0_rate_multiplier', 'some_multiplier']
+    np.testing.assert_array_equal(guess, [1, 1])
+    assert bounds == [(0, None), (0.5, 4)]
+    f, names, guess, bounds = lf.make_objective(rates_in_log_space=True, guess=dict(s0_rate_multiplier=10.))
+    assert guess[0] == 1.0 and bounds[0] == (None, None)
+    with pytest.raises(NoOpimizationNecessary):
+        lf.make_objective(s0_rate_multiplier=1, s1_rate_multiplier=1, some_multiplier=1)
+
+
+def test_grid_cell_ids_follow_the_oracle_rule():
+    rng = np.random.default_rng(0)
+    axes = [np.array([-2., -1., 0., 1., 2.]), np.array([0.5, 1., 4.]), np.array([3.])]
+    grid = engine.MorphGrid(axes)
+    zs = np.column_stack([rng.uniform(-2, 2, 500), rng.uniform(0.5, 4, 500), np.full(500, 3.)])
+    zs[:5, 0] = axes[0]
+    zs[:3, 1] = axes[1]
+    ids = grid.cell_ids(zs)
+    for row, cid in zip(zs, ids):
+        c0 = omorph.find_cell(axes[0], row[0])[0]
+        c1 = omorph.find_cell(axes[1], row[1])[0]
+        assert cid == (c0 * 2 + c1) * 1 + 0
+    ok = grid.in_range(np.array([[0., 1., 3.], [2.5, 1., 3.], [np.nan, 1., 3.], [0., 1., 3.1]]))
+    assert ok.tolist() == [True, False, False, False]
+    assert grid.n_anchors == 15 and grid.n_corners == 8
+
+
+def test_plan_points_covers_every_in_range_point_exactly_once():
+    rng = np.random.default_rng(1)
+    grid = engine.MorphGrid([np.array([-2., -1., 0., 1., 2.])] * 2)
+    zs = rng.uniform(-2.3, 2.0, (3000, 2))
+    zs[7] = np.nan
+    n_super = 37
+    plan = engine.plan_points(grid, zs, 2, n_super)
+    covered = np.zeros(len(zs), dtype=int)
+    covered[plan.stream_points] += 1
+    cells = grid.cell_ids(np.nan_to_num(zs))
+    seen = {}
+    for first, count, sb0, sb1 in plan.work:
+        assert 0 < count <= 256 and 0 <= sb0 < sb1 <= n_super
+        pts = plan.group_points[first:first + count]
+        assert len(set(cells[pts])) == 1                    # one hypercube cell per work item
+        seen.setdefault((first, count), []).append((sb0, sb1))
+    for (first, count), ranges in seen.items():
+        ranges.sort()
+        assert ranges[0][0] == 0 and ranges[-1][1] == n_super
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))   # superblock ranges tile [0, n_super)
+        covered[plan.group_points[first:first + count]] += 1
+    assert np.array_equal(covered == 1, plan.in_range)
+    assert not plan.in_range[7]
+    # forcing a kernel only moves points between the two lists
+    assert len(engine.plan_points(grid, zs, 2, n_super, 'stream').work) == 0
+    assert len(engine.plan_points(grid, zs, 2, n_super, 'grouped').stream_points) == 0
+    # too many sources for the grouped kernel -> everything streams
+    assert len(engine.plan_points(grid, zs, 9, n_super).work) == 0
