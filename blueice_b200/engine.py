@@ -429,11 +429,13 @@ class UnbinnedEngine(_EngineBase):
 class BinnedEngine(_EngineBase):
     """Binned Poisson likelihood with optional Beeston-Barlow over device-resident pmf tensors (K1 + K4)."""
 
-    def __init__(self, grid, mus_anchor, pmf_anchor, n_model_anchor=None, bb_source=None, device=None):
+    def __init__(self, grid, mus_anchor, pmf_anchor, n_model_anchor=None, bb_source=None, device=None,
+                 bin_shape=None):
+        """pmf_anchor / n_model_anchor: [n1..nD, S, *bins] (or [G, S, *bins] with bin_shape given)."""
         super().__init__(grid, mus_anchor, None, device)
         torch = self.torch
         pmf = np.asarray(pmf_anchor, dtype=np.float64)
-        self.bin_shape = pmf.shape[grid.n_dims + 1:] if grid.n_dims else pmf.shape[1:]
+        self.bin_shape = tuple(bin_shape) if bin_shape is not None else tuple(pmf.shape[grid.n_dims + 1:])
         self.n_bins = int(np.prod(self.bin_shape))
         pmf = pmf.reshape(grid.n_anchors, self.n_sources, self.n_bins)
         self.ld = round_up(self.n_bins, _LD_ALIGN)

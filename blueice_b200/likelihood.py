@@ -572,7 +572,7 @@ class BinnedLogLikelihood(LogLikelihoodBase):
         nm = None
         if bb is not None:
             nm = np.asarray(self._nm_anchor, dtype=np.float64).reshape(pmf.shape)
-        return BinnedEngine(self._grid, self._mus_anchor.reshape(G, -1), pmf, nm, bb)
+        return BinnedEngine(self._grid, self._mus_anchor.reshape(G, -1), pmf, nm, bb, bin_shape=self.ps.shape[1:])
 
     @inherit_docstring_from(LogLikelihoodBase)
     def set_data(self, d):
@@ -629,16 +629,16 @@ class BinnedLogLikelihood(LogLikelihoodBase):
     def _call_computed_pdf(self, multipliers, settings, livetime_days, full_output, kwargs):
         mus, ps, n_model_events = self._compute_single_pdf(**kwargs)
         bb = self._bb_source_index()
-        engine = BinnedEngine(MorphGrid([]), np.asarray(mus, dtype=np.float64)[np.newaxis, :], ps[np.newaxis],
-                              None if bb is None else n_model_events[np.newaxis], bb)
+        engine = BinnedEngine(MorphGrid([]), np.asarray(mus, dtype=np.float64)[np.newaxis, :], ps,
+                              None if bb is None else n_model_events, bb)
         engine.set_observed(self.data_events_per_bin.histogram)
         return self._evaluate_fixed_model(engine, multipliers, settings, livetime_days, full_output)
 
     def _fixed_engine(self, mus, pmfs, n_model_events):
         bb = self._bb_source_index()
         engine = BinnedEngine(MorphGrid([]), np.asarray(mus, dtype=np.float64)[np.newaxis, :],
-                              np.asarray(pmfs, dtype=np.float64)[np.newaxis],
-                              None if bb is None else np.asarray(n_model_events, dtype=np.float64)[np.newaxis], bb)
+                              np.asarray(pmfs, dtype=np.float64),
+                              None if bb is None else np.asarray(n_model_events, dtype=np.float64), bb)
         engine.set_observed(self.data_events_per_bin.histogram)
         return engine
 
@@ -657,7 +657,7 @@ class BinnedLogLikelihood(LogLikelihoodBase):
     def _compute_likelihood(self, mus, pmfs):
         """Binned Poisson log likelihood of explicit (mus, pmfs) arrays on the device (likelihood.py:662-675)."""
         engine = BinnedEngine(MorphGrid([]), np.asarray(mus, dtype=np.float64)[np.newaxis, :],
-                              np.asarray(pmfs, dtype=np.float64)[np.newaxis], None, None)
+                              np.asarray(pmfs, dtype=np.float64), None, None)
         engine.set_observed(self.data_events_per_bin.histogram)
         ll, status, _ = engine.evaluate(np.zeros((1, 0)), np.ones((1, len(mus))), return_status=True)
         return ll[0]
