@@ -133,51 +133,60 @@ def workload_config(n_events, n_points):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons with NVML every 20 ms in a thread during the timed region."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(prefix="bi_clocks_", suffix=".csv")
-        self.proc = None
         self.gpu_index = gpu_index
+        self.samples, self.reasons, self.power = [], set(), []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.sm_max = None
+        self.error = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES-style remapping by matching the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(self.gpu_index).pci_bus_id
+            handle = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                    handle = h
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                try:
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0)
+                except Exception:
+                    pass
+                time.sleep(0.02)
+        except Exception as exc:                                   # pragma: no cover
+            self.error = repr(exc)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for row in open(self.path):
-                parts = [p.strip() for p in row.split(",")]
-                if len(parts) < 7:
-                    continue
-                try:
-                    sm.append(float(parts[0]))
-                    smax.append(float(parts[1]))
-                except ValueError:
-                    continue
-                for name, flag in zip(names, parts[3:7]):
-                    if flag.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
+               "samples": len(self.samples), "reasons": sorted(self.reasons),
+               "power_w_max": max(self.power) if self.power else None}
+        if self.error:
+            out["error"] = self.error
+        return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libblueice_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["bi_util.cu", "bi_setup.cu", "bi_unbinned.cu", "bi_lookup.cu", "bi_binned.cu"]
+SOURCES = ["bi_util.cu", "bi_setup.cu", "bi_unbinned.cu", "bi_lookup.cu", "bi_binned.cu",
+           "bi_grouped_c1.cu", "bi_grouped_c2.cu", "bi_grouped_c4.cu", "bi_grouped_c8.cu", "bi_grouped_c16.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
@@ -46,16 +47,22 @@ def build(force=False, verbose=False):
     nvcc = find_nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    objects = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or res.returncode != 0:
-            sys.stderr.write(res.stdout + res.stderr)
-        if res.returncode != 0:
-            raise RuntimeError("nvcc failed on %s" % src)
-        objects.append(obj)
+        return src, obj, res
+
+    objects = []
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        for src, obj, res in pool.map(compile_one, SOURCES):
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed on %s" % src)
+            objects.append(obj)
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objects
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -106,10 +106,26 @@ __device__ __forceinline__ void bi_split(double p, double* m, int* e) {
     *m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
 }
 
-// L_b = log(M * 2^E) for a block product M in [1, 2^32), exact-integer E
+// L_b = log(M * 2^E) for a block product M in [1, 2^8), exact-integer E
 __device__ __forceinline__ double bi_block_log(double M, int E) {
     double e = (double)E;
     return fma(e, BI_LN2_LO, fma(e, BI_LN2_HI, log(M)));
+}
+
+// Canonical QUAD of four normal positive densities p0..p3:
+//     value = fl( fl(p0*p1) * fl(p2*p3) )   evaluated as if the exponent range were unbounded,
+// returned normalised as (m in [1,2), e).  Fast path: the two pair products and the quad product are
+// formed directly and the quad product is split once (3 DMUL + ~6 integer ops per 4 events).  If a pair
+// or the quad product leaves the normal range, the same value is formed from the four mantissas
+// (scaling by powers of two is exact, so both routes give identical bits).
+__device__ __forceinline__ void bi_quad_from_mantissas(double p0, double p1, double p2, double p3, double* m, int* e) {
+    double m0, m1, m2, m3;
+    int e0, e1, e2, e3;
+    bi_split(p0, &m0, &e0); bi_split(p1, &m1, &e1); bi_split(p2, &m2, &e2); bi_split(p3, &m3, &e3);
+    const double c = __dmul_rn(__dmul_rn(m0, m1), __dmul_rn(m2, m3));       // in [1, 16)
+    int ec;
+    bi_split(c, m, &ec);
+    *e = ((e0 + e1) + (e2 + e3)) + ec;
 }
 
 // Per-event density with the reference's semantics (likelihood.py:686-689):
