@@ -15,11 +15,13 @@
 //                        FP64-pipe-bound for profile scans / toy batches.
 //
 // Canonical arithmetic.  For each block of 32 consecutive events:
-//   fast:  quad k (4 events) = fl(fl(p0*p1)*fl(p2*p3)) = m_k * 2^e_k (unbounded-exponent semantics);
-//          M = binary-tree product of the 8 quad mantissas;  E = sum e_k;
-//          L_b = fma(E, LN2_LO, fma(E, LN2_HI, log(M)))          -> ONE log per 32 events
-//   slow (some p_i not a normal positive double): L_b = same tree shape over log(p_i)
-// superblock S_j = sequential sum of its 16 L_b; events >= N count as p = 1.
+//   quad k (4 events) = fl(fl(p0*p1)*fl(p2*p3)) = m_k * 2^e_k (unbounded-exponent semantics);
+//   block (8 quads)   = binary-tree product M_b of the quad mantissas, E_b = sum e_k;
+//   a block with a density that is not a normal positive double contributes M_b = 1, E_b = 0 and
+//   instead adds the same tree over log(p_i) to slow_j (sequentially, in block order);
+//   superblock (16 blocks) = binary-tree product M_j of the M_b, E_j = sum E_b;
+//   S_j = fma(E_j, LN2_LO, fma(E_j, LN2_HI, log(M_j))) + slow_j        -> ONE log per 512 events
+// events >= N count as p = 1 (exact identity).
 #include "bi_common.cuh"
 
 
@@ -42,7 +44,7 @@ __device__ __noinline__ double bi_slow_density_global(const double* __restrict__
 }
 
 // =============================================================================================
-// Streaming kernel: one warp per (point, superblock) task, lane = 2 consecutive events
+// Streaming kernel: one warp per (point, superblock) task, lane = 2 consecutive events per iteration
 // =============================================================================================
 template <int C>
 __global__ void __launch_bounds__(256, (C <= 8) ? 2 : 1)
@@ -55,6 +57,8 @@ k_unbinned_stream(const double* __restrict__ A, int64_t ld, int64_t N, int S,
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_tasks = n_points * n_super;
+    constexpr int CH = (C < 8) ? C : 8;                       // corners per load batch
+    constexpr int SG = (C >= 8) ? 1 : (8 / C);                // sources per load batch (SG * CH <= 8 loads in flight)
 
     for (int64_t task = warp_global; task < n_tasks; task += n_warps) {
         const int64_t k = task / n_super;
@@ -62,52 +66,51 @@ k_unbinned_stream(const double* __restrict__ A, int64_t ld, int64_t N, int S,
         const int64_t p = point_index ? (int64_t)point_index[k] : k;
         if (status[p] != 0) continue;                         // warp-uniform
 
+        const int64_t ev0 = j * BI_SUPERBLOCK;
         double w[C];
-        const double* base[C];
+        const double* ptr[C];                                 // this lane's first event, source 0
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             w[c] = weight[p * C + c];
-            base[c] = A + (int64_t)corner[p * C + c] * S * ld;
+            ptr[c] = A + (int64_t)corner[p * C + c] * S * ld + ev0 + 2 * lane;
         }
         const double* mu = mus + p * S;
 
-        double s_sum = 0.0;
-        double acc_ps0[(C >= 8) ? 1 : (8 / C)], acc_ps1[(C >= 8) ? 1 : (8 / C)];
-        const int64_t ev0 = j * BI_SUPERBLOCK;
+        double l1 = 1.0, l2 = 1.0, l3 = 1.0, m_super = 1.0, slow_sum = 0.0;
+        int e_super = 0;
+        int64_t left = N - ev0;
+        if (left > BI_SUPERBLOCK) left = BI_SUPERBLOCK;
+        const int n_iter = (int)((left + 63) >> 6);
 #pragma unroll 1
-        for (int it = 0; it < BI_SUPERBLOCK / 64; ++it) {
-            const int64_t chunk = ev0 + (int64_t)it * 64;
-            if (chunk >= N) break;                            // warp-uniform
-            const int64_t e = chunk + 2 * lane;
+        for (int it = 0; it < n_iter; ++it) {
+            const int64_t e = ev0 + (int64_t)it * 64 + 2 * lane;
             const bool in_ld = e < ld;                        // ld even -> e + 1 < ld as well
             double p0 = 0.0, p1 = 0.0;
-            // SG sources x C corners = up to 16 independent 16-byte loads in flight per lane
-            constexpr int SG = (C >= 8) ? 1 : (8 / C);
             for (int s0 = 0; s0 < S; s0 += SG) {
-                double2 v[SG][(C < 8) ? C : 8];
-                constexpr int CH = (C < 8) ? C : 8;
+                double acc0[SG], acc1[SG];
 #pragma unroll
                 for (int c0 = 0; c0 < C; c0 += CH) {
+                    double2 v[SG][CH];
 #pragma unroll
                     for (int g = 0; g < SG; ++g) {
                         if (s0 + g < S) {                     // warp-uniform
+                            const int64_t off = (int64_t)(s0 + g) * ld + it * 64;
 #pragma unroll
                             for (int c = 0; c < CH; ++c)
-                                v[g][c] = in_ld ? __ldg(reinterpret_cast<const double2*>(
-                                                      base[c0 + c] + (int64_t)(s0 + g) * ld + e))
+                                v[g][c] = in_ld ? __ldg(reinterpret_cast<const double2*>(ptr[c0 + c] + off))
                                                 : make_double2(0.0, 0.0);
                         }
                     }
 #pragma unroll
                     for (int g = 0; g < SG; ++g) {
                         if (s0 + g < S) {
-                            double ps0 = (c0 == 0) ? 0.0 : acc_ps0[g], ps1 = (c0 == 0) ? 0.0 : acc_ps1[g];
+                            double ps0 = (c0 == 0) ? 0.0 : acc0[g], ps1 = (c0 == 0) ? 0.0 : acc1[g];
 #pragma unroll
                             for (int c = 0; c < CH; ++c) {
                                 ps0 = fma(v[g][c].x, w[c0 + c], ps0);
                                 ps1 = fma(v[g][c].y, w[c0 + c], ps1);
                             }
-                            acc_ps0[g] = ps0; acc_ps1[g] = ps1;
+                            acc0[g] = ps0; acc1[g] = ps1;
                         }
                     }
                 }
@@ -115,8 +118,8 @@ k_unbinned_stream(const double* __restrict__ A, int64_t ld, int64_t N, int S,
                 for (int g = 0; g < SG; ++g) {
                     if (s0 + g < S) {
                         const double m = mu[s0 + g];
-                        p0 = fma(m, acc_ps0[g], p0);
-                        p1 = fma(m, acc_ps1[g], p1);
+                        p0 = fma(m, acc0[g], p0);
+                        p1 = fma(m, acc1[g], p1);
                     }
                 }
             }
@@ -127,42 +130,56 @@ k_unbinned_stream(const double* __restrict__ A, int64_t ld, int64_t N, int S,
             bool ok1 = bi_is_normal_positive(p1);
             if (!ok1) { p1 = bi_slow_density_global(A, ld, S, C, corner + p * C, weight + p * C, mu, e + 1, outlier); ok1 = bi_is_normal_positive(p1); }
             const unsigned bad = __ballot_sync(BI_FULL_MASK, !(ok0 && ok1));
+            // a block (half warp) with an abnormal density contributes 1 to the product and its log tree to slow_sum
+            const bool half_bad = ((lane < 16) ? (bad & 0xffffu) : (bad >> 16)) != 0;
 
             // canonical quad = the two events of this lane and of lane ^ 1
-            const double f0 = ok0 ? p0 : 1.0, f1 = ok1 ? p1 : 1.0;
+            const double f0 = half_bad ? 1.0 : p0, f1 = half_bad ? 1.0 : p1;
             const double q2 = __dmul_rn(f0, f1);
             const double q2o = __shfl_xor_sync(BI_FULL_MASK, q2, 1);
             const double q4 = __dmul_rn(q2, q2o);
             const bool direct_ok = bi_is_normal_positive(q2) && bi_is_normal_positive(q2o) && bi_is_normal_positive(q4);
-            double qm; int qe;
+            double q; int E;
             if (__ballot_sync(BI_FULL_MASK, !direct_ok) == 0) {
-                bi_split(q4, &qm, &qe);
+                bi_split(q4, &q, &E);
             } else {                                          // warp-uniform, rare: go through the mantissas
                 const double g0 = __shfl_xor_sync(BI_FULL_MASK, f0, 1), g1 = __shfl_xor_sync(BI_FULL_MASK, f1, 1);
-                if (lane & 1) bi_quad_from_mantissas(g0, g1, f0, f1, &qm, &qe);
-                else bi_quad_from_mantissas(f0, f1, g0, g1, &qm, &qe);
+                if (lane & 1) bi_quad_from_mantissas(g0, g1, f0, f1, &q, &E);
+                else bi_quad_from_mantissas(f0, f1, g0, g1, &q, &E);
             }
-            double q = qm;
-            int E = qe;
+            // binary tree over the 8 quads of each block (xor 2, 4, 8) and over the two blocks (xor 16)
 #pragma unroll
-            for (int x = 2; x < 16; x <<= 1) {
+            for (int x = 2; x < 32; x <<= 1) {
                 q = __dmul_rn(q, __shfl_xor_sync(BI_FULL_MASK, q, x));
                 E += __shfl_xor_sync(BI_FULL_MASK, E, x);
             }
-            double L = bi_block_log(q, E);
+            e_super += E;
             if (bad) {                                        // warp-uniform, rare
                 double l = __dadd_rn(log(p0), log(p1));
 #pragma unroll
                 for (int x = 1; x < 16; x <<= 1) l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, x));
-                const unsigned half_bad = (lane < 16) ? (bad & 0xffffu) : (bad >> 16);
-                if (half_bad) L = l;
+                const double la = __shfl_sync(BI_FULL_MASK, l, 0), lb = __shfl_sync(BI_FULL_MASK, l, 16);
+                if (bad & 0xffffu) slow_sum = __dadd_rn(slow_sum, la);
+                if (bad >> 16) slow_sum = __dadd_rn(slow_sum, lb);
             }
-            const double la = __shfl_sync(BI_FULL_MASK, L, 0);
-            const double lb = __shfl_sync(BI_FULL_MASK, L, 16);
-            s_sum = __dadd_rn(s_sum, la);
-            s_sum = __dadd_rn(s_sum, lb);
+            // binary counter over the 8 iterations = upper levels of the superblock product tree
+            double v = q;
+            if (it & 1) {
+                v = __dmul_rn(l1, v);
+                if (it & 2) {
+                    v = __dmul_rn(l2, v);
+                    if (it & 4) m_super = __dmul_rn(l3, v); else l3 = v;
+                } else l2 = v;
+            } else l1 = v;
         }
-        if (lane == 0) partial[p * n_super + j] = s_sum;
+        if (n_iter < BI_SUPERBLOCK / 64) {                    // superblock ends early: missing blocks count as 1
+            double v = 1.0;
+            if (n_iter & 1) v = __dmul_rn(l1, v);
+            if (n_iter & 2) v = __dmul_rn(l2, v);
+            if (n_iter & 4) v = __dmul_rn(l3, v);
+            m_super = v;
+        }
+        if (lane == 0) partial[p * n_super + j] = __dadd_rn(bi_block_log(m_super, e_super), slow_sum);
     }
 }
 

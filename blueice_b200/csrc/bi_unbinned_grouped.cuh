@@ -1,21 +1,24 @@
 // blueice_b200 -- K2 grouped kernel (threads = points of one hypercube cell), templated on <C, S>.
 //
 // One CTA = one work item: up to 256 points that share a hypercube cell x a range of 512-event
-// superblocks.  4 consumer warps (64 points each: lane l owns points l and l + 32 of its warp) and
-// 1 producer warp.  The producer stages the cell's C*S slab tiles of T events into shared memory with
-// TMA bulk copies (cp.async.bulk, SASS UBLKCP) through a STAGES-deep ring guarded by full/empty
-// mbarriers -- there is no CTA-wide barrier in the main loop, warps drift up to STAGES tiles apart.
+// superblocks.  4 warps, 64 points each (lane l owns points l and l + 32 of its warp).  The cell's
+// C*S slab tiles of T events are staged in shared memory by TMA bulk copies (cp.async.bulk, SASS
+// UBLKCP) through a STAGES-deep ring.  "full" mbarriers signal arrival of the bytes; a stage is
+// released with a shared-memory counter and THE LAST WARP TO RELEASE IT ISSUES THE NEXT TILE into it,
+// so nobody ever waits for a free stage and there is no CTA-wide barrier and no idle producer warp.
 // Consumers read the tile with broadcast LDS.128 (all lanes read the same two events of one slab) at
 // compile-time offsets, so the inner loop is DFMA + LDS only:
 //     ps_s[k] = fma(A[c,s,e+k], w_c, ps_s[k])   (C*S*4 per quad and point)
 //     p[k]    = fma(mu_s, ps_s[k], p[k])
 // followed by the canonical quad product (bi_common.cuh): 3 DMUL + one mantissa/exponent split per
-// 4 events, one combined normality predicate, one log per 32 events.
+// 4 events, one combined normality predicate, and ONE log per 512-event superblock (the product tree
+// of the 16 block products lives in shared memory).
 #pragma once
 #include "bi_common.cuh"
 
-#define BI_GROUP_CONSUMER_WARPS 4
-#define BI_GROUP_THREADS ((BI_GROUP_CONSUMER_WARPS + 1) * 32)
+#define BI_GROUP_WARPS 4
+#define BI_GROUP_THREADS (BI_GROUP_WARPS * 32)
+#define BI_SUPER_LEVELS 4          /* 16 blocks per superblock = 2^4 */
 
 template <int C, int S>
 struct BiGroupCfg {
@@ -23,8 +26,10 @@ struct BiGroupCfg {
     static constexpr int T = CS <= 16 ? 128 : (CS <= 32 ? 64 : 32);          // events per tile
     static constexpr int STAGES = (CS * T * 8 <= 16384) ? 4 : 3;
     static constexpr int TILE_DOUBLES = CS * T;
-    static constexpr int SMEM_BYTES = 256 + STAGES * TILE_DOUBLES * 8;
-    static constexpr int MIN_BLOCKS = C <= 4 ? 3 : 2;        // 160 threads: 3 CTAs -> 128 regs, 2 -> 200
+    // ring of tiles + per-thread superblock product tree (BI_SUPER_LEVELS x 2 points x 128 threads doubles)
+    static constexpr int LEVEL_DOUBLES = BI_SUPER_LEVELS * 2 * BI_GROUP_THREADS;
+    static constexpr int SMEM_BYTES = 256 + (STAGES * TILE_DOUBLES + LEVEL_DOUBLES) * 8;
+    static constexpr int MIN_BLOCKS = C <= 4 ? 4 : (C == 8 ? 3 : 2);   // 128 threads: 4 CTAs -> 128 regs
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -187,14 +192,17 @@ __device__ __forceinline__ void bi_quad_density(const double* __restrict__ row0,
     }
 }
 
-// One canonical block (32 events at tile offset e0) for the Q points of this thread.
+// One canonical block (32 events at tile offset e0) for the Q points of this thread:
+// fast result (M in [1, 2^8), E) or, if some density of the block is abnormal, M = 1, E = 0 and the
+// block's tree sum of logs in `Lslow` (0 otherwise).
 template <int C, int S, int Q, bool TAIL>
 __device__ __forceinline__ void bi_group_block(const double* __restrict__ tile, int e0, int n_valid,
                                                const BiGroupRegs<C, S, Q>& g, const double* const (&wp)[Q],
-                                               const double* const (&mp)[Q], double outlier, double (&L)[Q]) {
+                                               const double* const (&mp)[Q], double outlier,
+                                               double (&M)[Q], int (&E)[Q], double (&Lslow)[Q]) {
     constexpr int T = BiGroupCfg<C, S>::T;
-    double l4[Q], l5[Q], M[Q];
-    int E[Q], slow[Q];
+    double l4[Q], l5[Q];
+    int slow[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) { E[q] = 0; slow[q] = 0; l4[q] = l5[q] = M[q] = 1.0; }
 
@@ -245,20 +253,87 @@ __device__ __forceinline__ void bi_group_block(const double* __restrict__ tile, 
     }
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        L[q] = bi_block_log(M[q], E[q]);
-        if (slow[q]) L[q] = bi_block_slow(tile, T, S, C, e0, n_valid, wp[q], mp[q], outlier);
+        Lslow[q] = 0.0;
+        if (slow[q]) {
+            Lslow[q] = bi_block_slow(tile, T, S, C, e0, n_valid, wp[q], mp[q], outlier);
+            M[q] = 1.0;
+            E[q] = 0;
+        }
+    }
+}
+
+// Superblock product tree over the 16 block products of a 512-event superblock, kept in shared memory
+// ([level][point slot][thread], conflict-free): binary counter on the block index.
+template <int Q>
+__device__ __forceinline__ void bi_super_merge(double* lv, int blk, const double (&Mb)[Q], double (&out)[Q]) {
+    // lv: this thread's base in the level array; element (level, q) at lv[(level * 2 + q) * BI_GROUP_THREADS]
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        double v = Mb[q];
+        bool done = false;
+#pragma unroll
+        for (int b = 0; b < BI_SUPER_LEVELS; ++b) {
+            if (!done) {
+                double* slot = lv + (b * 2 + q) * BI_GROUP_THREADS;
+                if (blk & (1 << b)) v = __dmul_rn(*slot, v);
+                else { *slot = v; done = true; }
+            }
+        }
+        out[q] = v;       // complete product iff blk == 15
+    }
+}
+
+// product of the pending levels when the superblock ends early (missing blocks count as 1.0, exactly)
+template <int Q>
+__device__ __forceinline__ void bi_super_flush(const double* lv, int n_blocks_done, double (&out)[Q]) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        double v = 1.0;
+#pragma unroll
+        for (int b = 0; b < BI_SUPER_LEVELS; ++b)
+            if (n_blocks_done & (1 << b)) v = __dmul_rn(lv[(b * 2 + q) * BI_GROUP_THREADS], v);
+        out[q] = v;
+    }
+}
+
+// producer step, executed by one whole warp: arm the full barrier and issue the C*S bulk copies of tile t
+template <int C, int S>
+__device__ __forceinline__ void bi_group_issue(const double* __restrict__ A, int64_t ld, int64_t ev_begin, int t,
+                                               const int32_t* __restrict__ corner_lead, double* smem_tiles,
+                                               uint64_t* full_bar) {
+    using Cfg = BiGroupCfg<C, S>;
+    constexpr int T = Cfg::T;
+    const int lane = threadIdx.x & 31;
+    const int st = t % Cfg::STAGES;
+    const int64_t ev = ev_begin + (int64_t)t * T;
+    int64_t n_ld = ld - ev;
+    if (n_ld > T) n_ld = T;
+    const unsigned bytes = (unsigned)(n_ld * sizeof(double));
+    if (lane == 0) {
+        // order the generic-proxy reads of this stage (all warps are done with it) before the async-proxy writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bi_mbar_expect_tx(&full_bar[st], bytes * (unsigned)Cfg::CS);
+    }
+    __syncwarp();
+    double* dst = smem_tiles + (size_t)st * Cfg::TILE_DOUBLES;
+    for (int k = lane; k < Cfg::CS; k += 32) {
+        const int c = k / S, s = k - c * S;
+        const double* src = A + ((int64_t)corner_lead[c] * S + s) * ld + ev;
+        bi_bulk_g2s(dst + (size_t)k * T, src, bytes, &full_bar[st]);
     }
 }
 
 template <int C, int S, int Q>
-__device__ __forceinline__ void bi_group_consume(int64_t N, const int32_t* __restrict__ group_points, int first,
-                                                 int count, int64_t sb_begin, int64_t ev_begin, int n_tiles,
-                                                 int64_t n_super, const double* __restrict__ weight,
-                                                 const double* __restrict__ mus, double outlier,
-                                                 double* __restrict__ partial, const double* smem_tiles,
-                                                 uint64_t* full_bar, uint64_t* empty_bar) {
+__device__ __forceinline__ void bi_group_consume(const double* __restrict__ A, int64_t ld, int64_t N,
+                                                 const int32_t* __restrict__ group_points, int first, int count,
+                                                 int n_cwarps, int64_t sb_begin, int64_t ev_begin, int n_tiles,
+                                                 int64_t n_super, const int32_t* __restrict__ corner,
+                                                 const double* __restrict__ weight, const double* __restrict__ mus,
+                                                 double outlier, double* __restrict__ partial, double* smem_tiles,
+                                                 double* smem_levels, uint64_t* full_bar, int* release_cnt) {
     using Cfg = BiGroupCfg<C, S>;
     constexpr int T = Cfg::T;
+    constexpr int BLOCKS_PER_TILE = T / BI_EVENT_BLOCK;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     BiGroupRegs<C, S, Q> g;
@@ -278,48 +353,60 @@ __device__ __forceinline__ void bi_group_consume(int64_t N, const int32_t* __res
 #pragma unroll
         for (int s = 0; s < S; ++s) g.mu[q][s] = mp[q][s];
     }
+    const int32_t* corner_lead = corner + (int64_t)group_points[first] * C;
+    double* lv = smem_levels + threadIdx.x;
 
-    double s_sum[Q];
+    int e_super[Q];
+    double slow_sum[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) s_sum[q] = 0.0;
-    constexpr int TILES_PER_SUPER = BI_SUPERBLOCK / T;
+    for (int q = 0; q < Q; ++q) { e_super[q] = 0; slow_sum[q] = 0.0; }
     int64_t sb = sb_begin;
-    int in_super = 0, st = 0;
+    int blk = 0, st = 0;                                    // block index inside the current superblock
     unsigned parity = 0;
 
     for (int t = 0; t < n_tiles; ++t) {
         bi_mbar_wait(&full_bar[st], parity);
         const double* tile = smem_tiles + (size_t)st * Cfg::TILE_DOUBLES;
         const int64_t remaining = N - (ev_begin + (int64_t)t * T);
-        if (remaining >= T) {
+        const bool full_tile = remaining >= T;
+        const int n_valid = full_tile ? T : (int)remaining;
+        const int n_blocks = full_tile ? BLOCKS_PER_TILE : (n_valid + BI_EVENT_BLOCK - 1) / BI_EVENT_BLOCK;
+        double Msuper[Q];
 #pragma unroll 1
-            for (int b = 0; b < T / BI_EVENT_BLOCK; ++b) {
-                double L[Q];
-                bi_group_block<C, S, Q, false>(tile, b * BI_EVENT_BLOCK, T, g, wp, mp, outlier, L);
-#pragma unroll
-                for (int q = 0; q < Q; ++q) s_sum[q] = __dadd_rn(s_sum[q], L[q]);
-            }
-        } else {
-            const int n_valid = (int)remaining;
-            const int n_blocks = (n_valid + BI_EVENT_BLOCK - 1) / BI_EVENT_BLOCK;
-#pragma unroll 1
-            for (int b = 0; b < n_blocks; ++b) {
-                double L[Q];
-                bi_group_block<C, S, Q, true>(tile, b * BI_EVENT_BLOCK, n_valid, g, wp, mp, outlier, L);
-#pragma unroll
-                for (int q = 0; q < Q; ++q) s_sum[q] = __dadd_rn(s_sum[q], L[q]);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) bi_mbar_arrive(&empty_bar[st]);       // this warp is done reading stage `st`
-        if (++in_super == TILES_PER_SUPER || t == n_tiles - 1) {
+        for (int b = 0; b < n_blocks; ++b) {
+            double Mb[Q], Ls[Q];
+            int Eb[Q];
+            if (full_tile) bi_group_block<C, S, Q, false>(tile, b * BI_EVENT_BLOCK, T, g, wp, mp, outlier, Mb, Eb, Ls);
+            else bi_group_block<C, S, Q, true>(tile, b * BI_EVENT_BLOCK, n_valid, g, wp, mp, outlier, Mb, Eb, Ls);
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                if (active[q]) partial[pidx[q] * n_super + sb] = s_sum[q];
-                s_sum[q] = 0.0;
+                e_super[q] += Eb[q];
+                slow_sum[q] = __dadd_rn(slow_sum[q], Ls[q]);
+            }
+            bi_super_merge<Q>(lv, blk, Mb, Msuper);
+            ++blk;
+        }
+        // release the stage; the last warp to do so refills it with tile t + STAGES
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) last = (atomicAdd(&release_cnt[st], 1) == n_cwarps - 1);
+        last = __shfl_sync(BI_FULL_MASK, last, 0);
+        if (last) {
+            if (lane == 0) release_cnt[st] = 0;
+            if (t + Cfg::STAGES < n_tiles)
+                bi_group_issue<C, S>(A, ld, ev_begin, t + Cfg::STAGES, corner_lead, smem_tiles, full_bar);
+        }
+        if (blk == BI_SUPERBLOCK / BI_EVENT_BLOCK || t == n_tiles - 1) {
+            if (blk != BI_SUPERBLOCK / BI_EVENT_BLOCK) bi_super_flush<Q>(lv, blk, Msuper);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double sj = __dadd_rn(bi_block_log(Msuper[q], e_super[q]), slow_sum[q]);
+                if (active[q]) partial[pidx[q] * n_super + sb] = sj;
+                e_super[q] = 0;
+                slow_sum[q] = 0.0;
             }
             ++sb;
-            in_super = 0;
+            blk = 0;
         }
         if (++st == Cfg::STAGES) { st = 0; parity ^= 1u; }
     }
@@ -335,8 +422,9 @@ k_unbinned_grouped(const double* __restrict__ A, int64_t ld, int64_t N,
     constexpr int T = Cfg::T;
     extern __shared__ __align__(128) unsigned char bi_smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bi_smem);                   // [STAGES]
-    uint64_t* empty_bar = full_bar + Cfg::STAGES;                                // [STAGES]
+    int* release_cnt = reinterpret_cast<int*>(bi_smem + 64);                     // [STAGES]
     double* smem_tiles = reinterpret_cast<double*>(bi_smem + 256);
+    double* smem_levels = smem_tiles + Cfg::STAGES * Cfg::TILE_DOUBLES;
 
     const int4 wk = work[blockIdx.x];
     const int first = wk.x, count = wk.y;
@@ -345,48 +433,31 @@ k_unbinned_grouped(const double* __restrict__ A, int64_t ld, int64_t N,
     int64_t ev_end = sb_end * BI_SUPERBLOCK;
     if (ev_end > N) ev_end = N;
     const int n_tiles = (int)((ev_end - ev_begin + T - 1) / T);
-    const int n_cwarps = min(BI_GROUP_CONSUMER_WARPS, (count + 63) / 64);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_cwarps = min(BI_GROUP_WARPS, (count + 63) / 64);
+    const int warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) {
             bi_mbar_init(&full_bar[i], 1);
-            bi_mbar_init(&empty_bar[i], n_cwarps);
+            release_cnt[i] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (warp >= n_cwarps) return;                           // warps without points
 
-    if (warp == BI_GROUP_CONSUMER_WARPS) {
-        // ===== producer warp: TMA bulk copies of the C*S slab tiles of each event tile =====
-        const int64_t lead = group_points[first];
-        int st = 0;
-        unsigned parity = 0;
-        for (int t = 0; t < n_tiles; ++t) {
-            if (t >= Cfg::STAGES) bi_mbar_wait(&empty_bar[st], parity ^ 1u);     // consumers released tile t - STAGES
-            const int64_t ev = ev_begin + (int64_t)t * T;
-            int64_t n_ld = ld - ev;
-            if (n_ld > T) n_ld = T;
-            const unsigned bytes = (unsigned)(n_ld * sizeof(double));
-            if (lane == 0) bi_mbar_expect_tx(&full_bar[st], bytes * (unsigned)Cfg::CS);
-            __syncwarp();
-            double* dst = smem_tiles + (size_t)st * Cfg::TILE_DOUBLES;
-            for (int k = lane; k < Cfg::CS; k += 32) {
-                const int c = k / S, s = k - c * S;
-                const double* src = A + ((int64_t)corner[lead * C + c] * S + s) * ld + ev;
-                bi_bulk_g2s(dst + (size_t)k * T, src, bytes, &full_bar[st]);
-            }
-            if (++st == Cfg::STAGES) { st = 0; parity ^= 1u; }
-        }
-    } else if (warp < n_cwarps) {
-        // ===== consumer warps: 64 points each; the last warp may hold 32 or fewer =====
-        if (count - warp * 64 > 32)
-            bi_group_consume<C, S, 2>(N, group_points, first, count, sb_begin, ev_begin, n_tiles, n_super, weight,
-                                      mus, outlier, partial, smem_tiles, full_bar, empty_bar);
-        else
-            bi_group_consume<C, S, 1>(N, group_points, first, count, sb_begin, ev_begin, n_tiles, n_super, weight,
-                                      mus, outlier, partial, smem_tiles, full_bar, empty_bar);
+    if (warp == 0) {                                        // prologue: fill the ring
+        const int32_t* corner_lead = corner + (int64_t)group_points[first] * C;
+        for (int t = 0; t < Cfg::STAGES && t < n_tiles; ++t)
+            bi_group_issue<C, S>(A, ld, ev_begin, t, corner_lead, smem_tiles, full_bar);
     }
+    // 64 points per warp; the last warp may hold 32 or fewer
+    if (count - warp * 64 > 32)
+        bi_group_consume<C, S, 2>(A, ld, N, group_points, first, count, n_cwarps, sb_begin, ev_begin, n_tiles, n_super,
+                                  corner, weight, mus, outlier, partial, smem_tiles, smem_levels, full_bar, release_cnt);
+    else
+        bi_group_consume<C, S, 1>(A, ld, N, group_points, first, count, n_cwarps, sb_begin, ev_begin, n_tiles, n_super,
+                                  corner, weight, mus, outlier, partial, smem_tiles, smem_levels, full_bar, release_cnt);
 }
 
 template <int C, int S>

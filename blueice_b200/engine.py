@@ -157,11 +157,18 @@ def plan_points(grid, zs, n_sources, n_super, force_kernel=None):
             sb_begin = np.arange(0, n_super, sb_per, dtype=np.int64)
             sb_end = np.minimum(sb_begin + sb_per, n_super)
             ch = np.asarray(chunks, dtype=np.int64)
+            # heaviest chunks first (the block scheduler hands out CTAs in order, so the light ones fill
+            # the tail); within equal weight, event-range-major so co-resident CTAs share tiles in L2
+            weight_class = -np.minimum((ch[:, 1] + 63) // 64, 4)
+            order = np.lexsort((np.tile(np.arange(len(ch)), len(sb_begin)),
+                                np.repeat(np.arange(len(sb_begin)), len(ch)),
+                                np.tile(weight_class, len(sb_begin))))
             work = np.empty((len(ch) * len(sb_begin), 4), dtype=np.int32)
-            work[:, 0] = np.repeat(ch[:, 0], len(sb_begin))
-            work[:, 1] = np.repeat(ch[:, 1], len(sb_begin))
-            work[:, 2] = np.tile(sb_begin, len(ch))
-            work[:, 3] = np.tile(sb_end, len(ch))
+            work[:, 0] = np.tile(ch[:, 0], len(sb_begin))
+            work[:, 1] = np.tile(ch[:, 1], len(sb_begin))
+            work[:, 2] = np.repeat(sb_begin, len(ch))
+            work[:, 3] = np.repeat(sb_end, len(ch))
+            work = np.ascontiguousarray(work[order])
     return PointPlan(P, in_range, stream_pts.astype(np.int32), group_pts.astype(np.int32), work)
 
 
