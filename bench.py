@@ -218,6 +218,7 @@ def run_own_arm(args):
     torch.cuda.synchronize()
     set_data_s = time.perf_counter() - t0
     eng = ll._engine
+    eng.force_kernel = args.kernel
     n_events = len(d)
     P = args.points
     # weak scaling: every rank evaluates its own P points of a (world * P)-point scan
@@ -292,12 +293,26 @@ def run_own_arm(args):
     partial = eng.ws.get("partial", P * eng.n_super, torch.float64)
     stream = eng._stream()
 
+    def launch_k2(e, pl, pl_dev, setup, part):
+        """The K2 launch(es) the plan names, alone (what run_device issues between K1 and finalize)."""
+        common = (_cabi.dev_ptr(setup["corner"]), _cabi.dev_ptr(setup["weight"]), _cabi.dev_ptr(setup["mus"]),
+                  _cabi.dev_ptr(setup["status"]), e.outlier_likelihood, _cabi.dev_ptr(part), e._stream())
+        if pl.kernel == 'mma':
+            _cabi.check(e.lib.bi_unbinned_partials_mma(
+                _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(pl_dev[1]),
+                _cabi.dev_ptr(pl_dev[2]), len(pl.work), *common), "bi_unbinned_partials_mma")
+            return
+        if len(pl.stream_points):
+            _cabi.check(e.lib.bi_unbinned_partials_stream(
+                _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(pl_dev[0]),
+                len(pl.stream_points), *common), "bi_unbinned_partials_stream")
+        if len(pl.work):
+            _cabi.check(e.lib.bi_unbinned_partials_grouped(
+                _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(pl_dev[1]),
+                _cabi.dev_ptr(pl_dev[2]), len(pl.work), *common), "bi_unbinned_partials_grouped")
+
     def grouped_only():
-        rc = eng.lib.bi_unbinned_partials_grouped(
-            _cabi.dev_ptr(eng.ps_anchor), eng.ld, eng.n_events, S, C, _cabi.dev_ptr(plan_dev[1]),
-            _cabi.dev_ptr(plan_dev[2]), len(plan.work), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),
-            _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]), eng.outlier_likelihood, _cabi.dev_ptr(partial), stream)
-        _cabi.check(rc, "bi_unbinned_partials_grouped")
+        launch_k2(eng, plan, plan_dev, o, partial)
 
     k2_ms = []
     n_grouped = len(plan.group_points)
@@ -324,6 +339,10 @@ def run_own_arm(args):
         _cabi.check(eng.lib.bi_bench_fp64_fma(1 << 17, 148 * 16, _cabi.dev_ptr(sink), _cabi.host_ptr(ms),
                                               _cabi.host_ptr(flops), stream), "bi_bench_fp64_fma")
         fp64_tflops.append(flops[0] / (ms[0] * 1e-3) / 1e12)
+    for _ in range(3):
+        _cabi.check(eng.lib.bi_bench_fp64_mma(1 << 15, 148 * 4, _cabi.dev_ptr(sink), _cabi.host_ptr(ms),
+                                              _cabi.host_ptr(flops), stream), "bi_bench_fp64_mma")
+        fp64_tflops.append(flops[0] / (ms[0] * 1e-3) / 1e12)
     fp64_peak = max(fp64_tflops)
 
     # streaming regime: P = 1 over a tensor much larger than L2 (HBM-bound), same G/S/C
@@ -338,7 +357,7 @@ def run_own_arm(args):
             lo = r * n_events
             hi = min(lo + n_events, n_big)
             big.ps_anchor[:, :, lo:hi].copy_(src[:, :, :hi - lo])
-        big.force_kernel = 'stream'
+        big.force_kernel = args.stream_kernel
         z1, m1 = zs[:1], mult[:1]
         plan1 = big.plan(z1)
         z1_d, m1_d, _, _, _ = big._upload_points(z1, m1, None, None)
@@ -347,11 +366,7 @@ def run_own_arm(args):
         part1 = big.ws.get("partial", big.n_super, torch.float64)
 
         def stream_only():
-            rc = big.lib.bi_unbinned_partials_stream(
-                _cabi.dev_ptr(big.ps_anchor), big.ld, big.n_events, S, C, _cabi.dev_ptr(plan1_dev[0]), 1,
-                _cabi.dev_ptr(o1["corner"]), _cabi.dev_ptr(o1["weight"]), _cabi.dev_ptr(o1["mus"]),
-                _cabi.dev_ptr(o1["status"]), big.outlier_likelihood, _cabi.dev_ptr(part1), big._stream())
-            _cabi.check(rc, "bi_unbinned_partials_stream")
+            launch_k2(big, plan1, plan1_dev, o1, part1)
 
         for _ in range(3):
             stream_only()
@@ -372,7 +387,8 @@ def run_own_arm(args):
             _cabi.check(big.lib.bi_bench_stream_read(_cabi.dev_ptr(big.ps_anchor), n_read, _cabi.dev_ptr(sink),
                                                      _cabi.host_ptr(ms), big._stream()), "bi_bench_stream_read")
             rd.append(n_read * 8 / (ms[0] * 1e-3) / 1e9)
-        stream_info = {"kernel": "k_unbinned_stream<4> (P=1, lanes=events)", "bound": "hbm",
+        stream_info = {"kernel": "k_unbinned_mma (P=1: one 8-point m-tile per warp, TMA ring)" if plan1.kernel == 'mma'
+                       else "k_unbinned_stream (P=1, lanes=events)", "bound": "hbm",
                        "n_events": int(n_big), "bytes_per_point_event": 8 * C * S,
                        "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peak_src == "measured"
@@ -396,13 +412,19 @@ def run_own_arm(args):
         roofline = None
         if k2_ms:
             k2 = float(np.mean(k2_ms)) * 1e-3
-            flops_alg = float(n_grouped) * n_events * (2.0 * C * S + 2.0 * S)
+            flops_alg = float(n_grouped) * n_events * 2.0 * C * S
             bytes_alg = 8.0 * S * n_events * G
-            roofline = {"kernel": "k_unbinned_grouped<%d> (threads=points, TMA-staged event tiles)" % C,
-                        "bound": "fp64", "achieved": flops_alg / k2 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+            kname = ("k_unbinned_mma<K4=%d> (DMMA.8x8x4 contraction over K=C*S=%d, per-warp TMA ring)"
+                     % ((C * S + 3) // 4, C * S) if plan.kernel == 'mma'
+                     else "k_unbinned_grouped<%d> (threads=points, TMA-staged event tiles)" % C)
+            roofline = {"kernel": kname, "bound": "fp64", "achieved": flops_alg / k2 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": flops_alg / k2 / 1e12 / fp64_peak, "traffic": None,
-                        "peak_source": "bi_bench_fp64_fma measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
-                        "flops_alg_per_point_event": 2 * C * S + 2 * S, "ms": k2 * 1e3,
+                        "peak_source": "max(bi_bench_fp64_fma, bi_bench_fp64_mma) measured in this run: DFMA and DMMA "
+                                       "share one pipe on sm_100a (MEASURED_PEAKS.json holds no FP64 figure)",
+                        "flops_alg_per_point_event": 2 * C * S,
+                        "flops_alg_note": "SURVEY.md 8d: 2*C*S flop + 1 log per point-event; the log is replaced by "
+                                          "one FP64 multiply per point-event (product tree, one log per 512 events) "
+                                          "which is NOT counted, so frac <= 2CS/(2CS+2) = %.3f" % (C * S / (C * S + 1.0)), "ms": k2 * 1e3,
                         "share_of_step": k2 * 1e3 / (total_ms / args.steps),
                         "points_in_kernel": int(n_grouped),
                         "hbm": {"bytes_alg": bytes_alg, "achieved_gbs": bytes_alg / k2 / 1e9,
@@ -440,6 +462,10 @@ def main():
     ap.add_argument("--events", type=int, default=None, help="fix the number of events (default: Poisson ~100k)")
     ap.add_argument("--stream-events", type=int, default=8 * 1024 * 1024)
     ap.add_argument("--skip-stream", action="store_true")
+    ap.add_argument("--stream-kernel", default=None, choices=[None, "mma", "stream"],
+                    help="kernel for the P=1 HBM-bound measurement (default: the engine's own choice)")
+    ap.add_argument("--kernel", default=None, choices=[None, "mma", "grouped", "stream"],
+                    help="force a K2 kernel for the scan (default: the engine's own choice)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--ref-points-per-core", type=int, default=8)
     args = ap.parse_args()

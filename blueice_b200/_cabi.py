@@ -31,6 +31,10 @@ SIGNATURES = {
     "bi_unbinned_partials_grouped": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p,
                                                     _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
                                                     _c_void_p, _c_void_p]),
+    "bi_unbinned_partials_mma": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p,
+                                                _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
+                                                _c_void_p, _c_void_p]),
+    "bi_mma_unit_points": (_i32, [_i32, _i32]),
     "bi_unbinned_finalize": (ctypes.c_int, [_c_void_p, _i64, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
                                             _c_void_p]),
     "bi_unbinned_ps": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p, _c_void_p,
@@ -47,6 +51,7 @@ SIGNATURES = {
                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                       _i64, _c_void_p]),
     "bi_bench_fp64_fma": (ctypes.c_int, [_i64, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "bi_bench_fp64_mma": (ctypes.c_int, [_i64, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_bench_stream_read": (ctypes.c_int, [_c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p]),
 }
 
@@ -61,6 +66,7 @@ GROUP_POINTS = 256
 GROUP_MAX_SOURCES = 8
 GROUP_MAX_CORNERS = 16
 STREAM_MAX_CORNERS = 32
+MMA_MAX_TERMS = 32
 POINT_OUT_OF_RANGE = 1
 POINT_UNPHYSICAL = 2
 LOOKUP_LINEAR = 0
@@ -77,7 +83,7 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB_PATH
+    return os.environ.get("BLUEICE_B200_LIB") or _build.LIB_PATH     # override: kernel-variant experiments
 
 
 def load():

@@ -1,0 +1,470 @@
+// blueice_b200 -- K2: fused anchor-morph + mixture density + log + reduce on the FP64 tensor path (DMMA).
+//
+// Replaces, for a batch of P parameter points over N events (blueice/likelihood.py:355-356,678-690 and
+// scipy/interpolate/_rgi.py:520-549):
+//     f(theta_p, x_i) = sum_{c,s} (w_{p,c} * mu_{p,s}) * A[corner_c, s, i]       (morph x mixture as ONE contraction)
+//     partial[p, j]   = sum_{i in superblock j} log f(theta_p, x_i)
+//
+// The contraction over k = c*S + s (K = C*S terms) of 8 points x 8 events is one chain of
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): A operand = the points' coefficients (registers, loaded once
+// per work unit), B operand = the event tile (shared memory, staged by TMA bulk copies through a
+// per-warp mbarrier ring), D = densities, 2 consecutive events of one point per thread.  DMMA and DFMA
+// share one pipe on sm_100a (37.1 TFLOP/s either way, profiles/microbench), but one DMMA replaces 8 warp
+// DFMAs, needs no broadcast LDS and keeps the coefficients of 8 points in ONE register pair per k-step,
+// so the kernel is bound by that pipe instead of by instruction issue.  DMMA accumulates as a
+// sequential fma chain in k order (bit-exact, profiles/microbench/dmma_probe_b200.log).
+//
+// Work unit (one warp): up to 8*MT points that share one hypercube cell x a range of superblocks.
+// Four units per CTA; every warp owns its ring, its barriers and its TMA issue -- no CTA-wide sync.
+//
+// Canonical arithmetic -- what every result is defined by, independent of how the
+// batch is cut into units:
+//   p_i        = fma chain over k = 0..K-1 of A[k,i] * coef_k starting from 0, coef_k = fl(w_c * mu_s)
+//   group      = 32 consecutive events (4 octets); class t = 0..3 owns events 8n + 2t, 8n + 2t + 1 of octet n
+//   (t, group) : pair_n = fl(p * p'), quad = fl(pair_0 * pair_1), fl(pair_2 * pair_3), oct = fl(quad * quad')
+//                -> (m, e) = mantissa / exponent of oct.          [needs every p in [2^-126, 2^127)]
+//                otherwise (m, e) = (1, 0) and l = the same tree over log(p_i) with p_i re-evaluated
+//                with the reference's nansum / outlier semantics (likelihood.py:686-689)
+//   superblock = 16 groups: M_t = (((1 * m_0) * m_1) ...), E_t = sum e, L_t = ((0 + l_0) + l_1) ...
+//                M = (M_0 * M_1) * (M_2 * M_3), E = sum E_t, L = (L_0 + L_1) + (L_2 + L_3)
+//                partial = fma(E, LN2_LO, fma(E, LN2_HI, log(M))) + L           -> ONE log per 512 events
+//   events >= N count as p = 1 (exact identity).
+#pragma once
+#include "bi_common.cuh"
+
+#define BI_MMA_WARPS 4
+#define BI_MMA_THREADS (BI_MMA_WARPS * 32)
+#define BI_GROUP_EVENTS 32
+#define BI_GROUPS_PER_SUPER (BI_SUPERBLOCK / BI_GROUP_EVENTS)
+// p in [2^-126, 2^127)  <=>  (unsigned)(hi32(p) - BI_RANGE_LO) < BI_RANGE_SPAN
+#define BI_RANGE_LO ((1023 - 126) << 20)
+#define BI_RANGE_SPAN (253u << 20)
+
+template <int K4>
+struct BiMmaCfg {
+#ifndef BI_MT_SMALL
+#define BI_MT_SMALL 8
+#endif
+#ifndef BI_CTAS_SMALL
+#define BI_CTAS_SMALL 3
+#endif
+    static constexpr int MT = K4 <= 2 ? BI_MT_SMALL : (K4 <= 4 ? 4 : 2);     // 8-point m-tiles per unit
+    static constexpr int KP = 4 * K4;                              // rows incl. zero padding
+    static constexpr int T = K4 <= 2 ? 128 : (K4 <= 4 ? 64 : 32);  // events per tile (row copies of T*8 bytes)
+    static constexpr int RS = T + 4;                               // row stride: B-fragment loads hit 16 distinct banks
+    static constexpr int STAGES = K4 <= 4 ? 2 : 3;
+    static constexpr int STAGE_DOUBLES = KP * RS;
+    static constexpr int RING_DOUBLES = STAGES * STAGE_DOUBLES;
+    static constexpr int BREG = K4 <= 4;                           // B fragments of a whole group live in registers
+    static constexpr int HEADER_BYTES = 256;                       // mbarriers [WARPS][STAGES]
+    static constexpr int SLOW_DOUBLES = MT * BI_MMA_THREADS;       // L_t accumulators (touched on the slow path only)
+    static constexpr int SMEM_BYTES = HEADER_BYTES + (BI_MMA_WARPS * RING_DOUBLES + SLOW_DOUBLES) * 8;
+    static constexpr int MIN_CTAS = K4 <= 2 ? BI_CTAS_SMALL : (K4 <= 4 ? 3 : 2);
+};
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / TMA / DMMA helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bi_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bi_mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bi_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bi_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bi_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool bi_mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bi_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a byte-count bug would otherwise hang the GPU; after ~2 s of polling the kernel traps
+// (a reported CUDA error) instead of spinning forever.
+__device__ __forceinline__ void bi_mbar_wait(uint64_t* bar, unsigned parity) {
+    if (bi_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!bi_mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bi_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     bi_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(bi_smem_u32(bar))
+                 : "memory");
+}
+// D(8x8) += A(8x4, row) * B(4x8, col); thread (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void bi_dmma(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------
+// slow path (rare; noinline keeps it out of the hot loop's register allocation)
+// ---------------------------------------------------------------------------------------------
+// density of one event with the reference's semantics; `col` points at row 0 of that event, rows `rs` apart
+static __device__ __noinline__ double bi_slow_density_rows(const double* col, int rs, int S, int C,
+                                                           const double* __restrict__ weight_p,
+                                                           const double* __restrict__ mu, double outlier) {
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        double ps = 0.0;
+        for (int c = 0; c < C; ++c) ps = fma(col[(c * S + s) * rs], weight_p[c], ps);
+        const double term = __dmul_rn(mu[s], ps);
+        if (term == term) acc = __dadd_rn(acc, term);       // nansum: NaN terms count as 0
+    }
+    return bi_fix_density(acc, outlier);
+}
+
+// (t, group) fallback: the canonical tree over log(p_i) of the class's 8 events; grp points at row 0 of
+// the group's first event, n_valid = events of the group that exist (others count as p = 1)
+static __device__ __noinline__ double bi_slow_group(const double* grp, int rs, int S, int C, int t, int n_valid,
+                                                    const double* __restrict__ weight_p,
+                                                    const double* __restrict__ mu, double outlier) {
+    double quad[2];
+    for (int h = 0; h < 2; ++h) {
+        double pr[2];
+        for (int n = 0; n < 2; ++n) {
+            const int e = 8 * (2 * h + n) + 2 * t;
+            const double p0 = (e < n_valid) ? bi_slow_density_rows(grp + e, rs, S, C, weight_p, mu, outlier) : 1.0;
+            const double p1 = (e + 1 < n_valid) ? bi_slow_density_rows(grp + e + 1, rs, S, C, weight_p, mu, outlier) : 1.0;
+            pr[n] = __dadd_rn(log(p0), log(p1));
+        }
+        quad[h] = __dadd_rn(pr[0], pr[1]);
+    }
+    return __dadd_rn(quad[0], quad[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// producer step (whole warp): arm the stage's barrier and issue the K row copies of tile `tile_idx`.
+// src_row: this lane's row (k = lane) of the cell at event 0 (lanes >= K idle); K <= 32.
+// ---------------------------------------------------------------------------------------------
+template <int K4>
+__device__ __forceinline__ void bi_mma_issue(const double* __restrict__ src_row, int64_t ld, int64_t ev_begin,
+                                             int tile_idx, int st, int K, double* ring, uint64_t* full_bar, int lane) {
+    using Cfg = BiMmaCfg<K4>;
+    const int64_t ev = ev_begin + (int64_t)tile_idx * Cfg::T;
+    const int64_t left = ld - ev;
+    const unsigned bytes = (unsigned)(left < Cfg::T ? left : Cfg::T) * (unsigned)sizeof(double);
+    if (lane == 0) {
+        // order this warp's generic-proxy reads of the stage before the async-proxy writes that refill it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bi_mbar_expect_tx(&full_bar[st], bytes * (unsigned)K);
+    }
+    __syncwarp();
+    if (lane < K)
+        bi_bulk_g2s(ring + (size_t)st * Cfg::STAGE_DOUBLES + (size_t)lane * Cfg::RS, src_row + ev, bytes, &full_bar[st]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one canonical group (32 events at tile offset e0) for the NMT m-tiles of this warp
+// ---------------------------------------------------------------------------------------------
+// densities of the 32 events x 8 points of (group, m-tile): 4 octets x K4 chained DMMA.8x8x4
+template <int K4>
+__device__ __forceinline__ void bi_mma_tile(const double* __restrict__ bcol, const double (&b)[4][K4], const double (&a)[K4],
+                                            double (&d)[4][2]) {
+    using Cfg = BiMmaCfg<K4>;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) d[n][0] = d[n][1] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < K4; ++kk)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+            bi_dmma(d[n][0], d[n][1], a[kk], Cfg::BREG ? b[n][kk] : bcol[4 * kk * Cfg::RS + 8 * n]);
+}
+
+// NMT (compile time) m-tiles in use: the body is ONE branch-free basic block, so ptxas interleaves the DMMAs
+// of the next m-tile with the product-tree epilogue of the previous one.
+// TAIL: the group holds events >= N (they count as p = 1).
+template <int K4, int NMT, bool TAIL>
+__device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, int e0, int n_valid, int S, int C,
+                                             unsigned active_mask, const double (&a)[NMT][K4],
+                                             const int32_t* __restrict__ slot_point, const double* __restrict__ weight,
+                                             const double* __restrict__ mus, double outlier, double* slow_acc,
+                                             bool& slow_any, double (&M)[NMT], int (&E)[NMT], int lane) {
+    using Cfg = BiMmaCfg<K4>;
+    const int g = lane >> 2, t = lane & 3;
+    // B fragment of octet n, k-step kk: tile[(4 kk + t) * RS + e0 + 8 n + g] (rows >= K are zero)
+    const double* bcol = tile + t * Cfg::RS + e0 + g;
+    double b[4][K4];
+    if (Cfg::BREG) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int kk = 0; kk < K4; ++kk) b[n][kk] = bcol[4 * kk * Cfg::RS + 8 * n];
+    }
+    unsigned bad = 0;
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) {
+        double d[4][2];
+        bi_mma_tile<K4>(bcol, b, a[mt], d);
+        if (TAIL) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const int e = e0 + 8 * n + 2 * t;
+                if (e >= n_valid) d[n][0] = 1.0;
+                if (e + 1 >= n_valid) d[n][1] = 1.0;
+            }
+        }
+        unsigned tmax = (unsigned)(__double2hiint(d[0][0]) - BI_RANGE_LO);
+        tmax = max(tmax, (unsigned)(__double2hiint(d[0][1]) - BI_RANGE_LO));
+#pragma unroll
+        for (int n = 1; n < 4; ++n) {
+            tmax = max(tmax, (unsigned)(__double2hiint(d[n][0]) - BI_RANGE_LO));
+            tmax = max(tmax, (unsigned)(__double2hiint(d[n][1]) - BI_RANGE_LO));
+        }
+        const double q0 = __dmul_rn(__dmul_rn(d[0][0], d[0][1]), __dmul_rn(d[1][0], d[1][1]));
+        const double q1 = __dmul_rn(__dmul_rn(d[2][0], d[2][1]), __dmul_rn(d[3][0], d[3][1]));
+        const double oct = __dmul_rn(q0, q1);
+        // branch-free: split unconditionally, neutralise (m, e) = (1, 0) when the class leaves the fast range
+        double m;
+        int e;
+        bi_split(oct, &m, &e);
+        if (tmax >= BI_RANGE_SPAN) {
+            m = 1.0;
+            e = 0;
+            bad |= 1u << mt;
+        }
+        M[mt] = __dmul_rn(M[mt], m);
+        E[mt] += e;
+    }
+    bad &= active_mask;
+    if (bad) {                                                    // rare: reference-semantics fallback per (t, group)
+        for (int mt = 0; mt < NMT; ++mt) {
+            if ((bad >> mt) & 1u) {
+                const int64_t p = slot_point[mt * 8 + g];
+                const int nv = TAIL ? (n_valid - e0 < BI_GROUP_EVENTS ? n_valid - e0 : BI_GROUP_EVENTS) : BI_GROUP_EVENTS;
+                const double l = bi_slow_group(tile + e0, Cfg::RS, S, C, t, nv, weight + p * C, mus + p * S, outlier);
+                double* acc = slow_acc + mt * BI_MMA_THREADS;
+                *acc = __dadd_rn(*acc, l);
+                slow_any = true;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one work unit with NMT m-tiles: coefficients -> registers, then the tile loop
+// ---------------------------------------------------------------------------------------------
+template <int K4, int NMT>
+__device__ __forceinline__ void bi_mma_unit(const double* __restrict__ src_row, int64_t ld, int64_t N, int S, int C,
+                                            const int32_t* __restrict__ slot_point, unsigned active_mask, int64_t healthy,
+                                            int64_t sb_begin, int64_t sb_end, int64_t ev_begin, int n_tiles, int64_t n_super,
+                                            const double* __restrict__ weight,
+                                            const double* __restrict__ mus, double outlier, double* __restrict__ partial,
+                                            double* ring, uint64_t* full_bar, double* slow_acc, int lane) {
+    using Cfg = BiMmaCfg<K4>;
+    constexpr int T = Cfg::T;
+    const int g = lane >> 2, t = lane & 3;
+    const int K = C * S;
+
+    double a[NMT][K4];
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) {
+        const int64_t p = ((active_mask >> mt) & 1u) ? (int64_t)slot_point[mt * 8 + g] : healthy;
+#pragma unroll
+        for (int kk = 0; kk < K4; ++kk) {
+            const int k = 4 * kk + t;
+            const int c = k / S, s = k - c * S;
+            a[mt][kk] = (k < K) ? __dmul_rn(weight[p * C + c], mus[p * S + s]) : 0.0;
+        }
+    }
+
+    double M[NMT];
+    int E[NMT];
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) { M[mt] = 1.0; E[mt] = 0; }
+    bool slow_any = false;
+    int st = 0, tile_idx = 0;
+    unsigned parity = 0;
+    constexpr int TILES_PER_SUPER = BI_SUPERBLOCK / T, GROUPS_PER_TILE = T / BI_GROUP_EVENTS;
+
+    for (int64_t sb = sb_begin; sb < sb_end; ++sb) {
+        const int64_t left = N - sb * BI_SUPERBLOCK;
+        const int n_ev = left < BI_SUPERBLOCK ? (int)left : BI_SUPERBLOCK;      // events of this superblock that exist
+#pragma unroll 1
+        for (int ti = 0; ti < TILES_PER_SUPER && ti * T < n_ev; ++ti, ++tile_idx) {
+            bi_mbar_wait(&full_bar[st], parity);
+            const double* tile = ring + (size_t)st * Cfg::STAGE_DOUBLES;
+            const int n_valid = n_ev - ti * T;                                   // may exceed T
+            if (n_valid >= T) {
+#pragma unroll 1
+                for (int gi = 0; gi < GROUPS_PER_TILE; ++gi)
+                    bi_mma_group<K4, NMT, false>(tile, gi * BI_GROUP_EVENTS, T, S, C, active_mask, a, slot_point, weight,
+                                                 mus, outlier, slow_acc, slow_any, M, E, lane);
+            } else {
+#pragma unroll 1
+                for (int e0 = 0; e0 < n_valid; e0 += BI_GROUP_EVENTS) {
+                    if (e0 + BI_GROUP_EVENTS <= n_valid)
+                        bi_mma_group<K4, NMT, false>(tile, e0, n_valid, S, C, active_mask, a, slot_point, weight, mus,
+                                                     outlier, slow_acc, slow_any, M, E, lane);
+                    else
+                        bi_mma_group<K4, NMT, true>(tile, e0, n_valid, S, C, active_mask, a, slot_point, weight, mus,
+                                                    outlier, slow_acc, slow_any, M, E, lane);
+                }
+            }
+            // this warp is done with the stage: refill it with tile + STAGES
+            __syncwarp();
+            if (tile_idx + Cfg::STAGES < n_tiles)
+                bi_mma_issue<K4>(src_row, ld, ev_begin, tile_idx + Cfg::STAGES, st, K, ring, full_bar, lane);
+            if (++st == Cfg::STAGES) { st = 0; parity ^= 1u; }
+        }
+        // ---- close the superblock: combine the four classes, one log per point
+        const bool any_slow = __any_sync(BI_FULL_MASK, slow_any);
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) {
+            double m = M[mt];
+            m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 1));
+            m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 2));
+            int e = E[mt];
+            e += __shfl_xor_sync(BI_FULL_MASK, e, 1);
+            e += __shfl_xor_sync(BI_FULL_MASK, e, 2);
+            M[mt] = m;
+            E[mt] = e;
+        }
+        // lane t evaluates the log of m-tiles t, t + 4 (the four lanes of a row hold identical values)
+#pragma unroll
+        for (int r = 0; r < (NMT + 3) / 4; ++r) {
+            double m = 1.0;
+            int e = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * r + q < NMT && t == q) { m = M[4 * r + q]; e = E[4 * r + q]; }
+            double L = bi_block_log(m, e);
+            const int mt_mine = 4 * r + t;
+            if (any_slow) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (4 * r + q < NMT) {
+                        double l = slow_acc[(4 * r + q) * BI_MMA_THREADS];
+                        l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
+                        l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 2));
+                        if (t == q) L = __dadd_rn(L, l);
+                        slow_acc[(4 * r + q) * BI_MMA_THREADS] = 0.0;
+                    }
+                }
+            }
+            if (mt_mine < NMT && ((active_mask >> mt_mine) & 1u)) {
+                const int64_t p = slot_point[mt_mine * 8 + g];
+                partial[p * n_super + sb] = L;
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) { M[mt] = 1.0; E[mt] = 0; }
+        slow_any = false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel: one warp per work unit (first, n_points, superblock_begin, superblock_end)
+// ---------------------------------------------------------------------------------------------
+template <int K4>
+__global__ void __launch_bounds__(BI_MMA_THREADS, BiMmaCfg<K4>::MIN_CTAS)
+k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int S, int C,
+               const int32_t* __restrict__ group_points, const int4* __restrict__ work, int64_t n_work,
+               int64_t n_super, const int32_t* __restrict__ corner, const double* __restrict__ weight,
+               const double* __restrict__ mus, const int32_t* __restrict__ status, double outlier,
+               double* __restrict__ partial) {
+    using Cfg = BiMmaCfg<K4>;
+    constexpr int MT = Cfg::MT, T = Cfg::T;
+    extern __shared__ __align__(128) unsigned char bi_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bi_smem) + warp * Cfg::STAGES;
+    double* ring = reinterpret_cast<double*>(bi_smem + Cfg::HEADER_BYTES) + (size_t)warp * Cfg::RING_DOUBLES;
+    double* slow_acc = reinterpret_cast<double*>(bi_smem + Cfg::HEADER_BYTES) + (size_t)BI_MMA_WARPS * Cfg::RING_DOUBLES +
+                       threadIdx.x;
+
+    const int64_t unit = (int64_t)blockIdx.x * BI_MMA_WARPS + warp;
+    if (unit >= n_work) return;
+    const int4 wk = work[unit];
+    const int first = wk.x, n_pts = wk.y;
+    const int64_t sb_begin = wk.z, sb_end = wk.w;
+    const int K = C * S;
+    const int n_mt = (n_pts + 7) >> 3;
+
+    // ---- slots: point of (m-tile mt, row g); slots beyond n_pts or with a failed status replay a healthy point
+    const int32_t* slot_point = group_points + first;              // slot -> point index (slots < n_pts)
+    unsigned active_mask = 0;                                      // bit mt: this lane's slot of m-tile mt is live
+    int64_t healthy = -1;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int slot = mt * 8 + g;
+        bool ok = false;
+        int64_t p = 0;
+        if (slot < n_pts) {
+            p = slot_point[slot];
+            ok = status[p] == 0;
+        }
+        if (ok) active_mask |= 1u << mt;
+        const unsigned vote = __ballot_sync(BI_FULL_MASK, ok);
+        if (healthy < 0 && vote) healthy = __shfl_sync(BI_FULL_MASK, p, __ffs(vote) - 1);
+    }
+    if (healthy < 0) return;                                       // warp-uniform: nothing to evaluate
+    const int32_t* corner_lead = corner + healthy * C;
+
+    if (lane == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) bi_mbar_init(&full_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) slow_acc[mt * BI_MMA_THREADS] = 0.0;
+    // rows K..KP-1 of every stage are never written by the TMA copies: zero them once (0 * coef 0 adds nothing)
+    for (int i = lane; i < (Cfg::KP - K) * Cfg::RS * Cfg::STAGES; i += 32) {
+        const int st_i = i / ((Cfg::KP - K) * Cfg::RS), r = i - st_i * (Cfg::KP - K) * Cfg::RS;
+        ring[(size_t)st_i * Cfg::STAGE_DOUBLES + K * Cfg::RS + r] = 0.0;
+    }
+    __syncwarp();
+
+    // the first tiles are in flight while the coefficients are gathered
+    const int64_t ev_begin = sb_begin * BI_SUPERBLOCK;
+    int64_t ev_end = sb_end * BI_SUPERBLOCK;
+    if (ev_end > N) ev_end = N;
+    const int n_tiles = (int)((ev_end - ev_begin + T - 1) / T);
+    const double* src_row = A;
+    if (lane < K) {
+        const int c = lane / S, s = lane - c * S;
+        src_row = A + ((int64_t)corner_lead[c] * S + s) * ld;
+    }
+    for (int i = 0; i < Cfg::STAGES && i < n_tiles; ++i)
+        bi_mma_issue<K4>(src_row, ld, ev_begin, i, i, K, ring, full_bar, lane);
+
+#define BI_MMA_UNIT(NN)                                                                                              \
+    case NN:                                                                                                         \
+        if (NN <= MT)                                                                                                \
+            bi_mma_unit<K4, (NN <= MT ? NN : 1)>(src_row, ld, N, S, C, slot_point, active_mask, healthy, sb_begin,  \
+                                                 sb_end, ev_begin, n_tiles, n_super, weight, mus, outlier, partial,  \
+                                                 ring, full_bar, slow_acc, lane);                                    \
+        break;
+    switch (n_mt) {
+        BI_MMA_UNIT(1) BI_MMA_UNIT(2) BI_MMA_UNIT(3) BI_MMA_UNIT(4)
+        BI_MMA_UNIT(5) BI_MMA_UNIT(6) BI_MMA_UNIT(7) BI_MMA_UNIT(8)
+    }
+#undef BI_MMA_UNIT
+}
+
+template <int K4>
+static int bi_launch_mma(const double* A, int64_t ld, int64_t N, int S, int C, const int32_t* group_points,
+                         const int32_t* work, int64_t n_work, int64_t n_super, const int32_t* corner,
+                         const double* weight, const double* mus, const int32_t* status, double outlier,
+                         double* partial, cudaStream_t st) {
+    using Cfg = BiMmaCfg<K4>;
+    static bool configured = false;
+    if (!configured) {
+        BI_CUDA_CHECK(cudaFuncSetAttribute(k_unbinned_mma<K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int64_t blocks = (n_work + BI_MMA_WARPS - 1) / BI_MMA_WARPS;
+    k_unbinned_mma<K4><<<(unsigned)blocks, BI_MMA_THREADS, Cfg::SMEM_BYTES, st>>>(
+        A, ld, N, S, C, group_points, reinterpret_cast<const int4*>(work), n_work, n_super, corner, weight, mus, status,
+        outlier, partial);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}

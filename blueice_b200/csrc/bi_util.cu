@@ -57,6 +57,47 @@ extern "C" int bi_bench_fp64_fma(int64_t fma_per_thread, int32_t n_blocks, doubl
     return BI_OK;
 }
 
+// FP64 tensor-pipe peak: 8 independent DMMA.8x8x4 accumulation chains per warp, nothing else in the loop.
+// (On sm_100a DMMA and DFMA share one pipe; this is the denominator of the DMMA K2 kernel's roofline.)
+__global__ void __launch_bounds__(128) k_fp64_mma(int64_t iters, double* sink) {
+    double d[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i][0] = d[i][1] = 0.0;
+    const double a = 1e-3 * (threadIdx.x + 1), b = 1.0000000001;
+    for (int64_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(d[i][0]), "+d"(d[i][1]) : "d"(a), "d"(b));
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += d[i][0] + d[i][1];
+    if (r == 123.456) sink[0] = r;
+}
+
+extern "C" int bi_bench_fp64_mma(int64_t mma_per_warp, int32_t n_blocks, double* sink_dev,
+                                 float* ms_host, double* flops_host, void* stream) {
+    BI_REQUIRE(mma_per_warp > 0 && n_blocks > 0 && sink_dev && ms_host && flops_host,
+               "bi_bench_fp64_mma: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t iters = mma_per_warp / 8;
+    cudaEvent_t e0, e1;
+    BI_CUDA_CHECK(cudaEventCreate(&e0));
+    BI_CUDA_CHECK(cudaEventCreate(&e1));
+    k_fp64_mma<<<n_blocks, 128, 0, st>>>(iters / 8 + 1, sink_dev);  // warm-up
+    BI_CUDA_CHECK(cudaEventRecord(e0, st));
+    k_fp64_mma<<<n_blocks, 128, 0, st>>>(iters, sink_dev);
+    BI_CUDA_CHECK(cudaEventRecord(e1, st));
+    BI_LAUNCH_CHECK();
+    BI_CUDA_CHECK(cudaEventSynchronize(e1));
+    BI_CUDA_CHECK(cudaEventElapsedTime(ms_host, e0, e1));
+    *flops_host = 2.0 * 256.0 * 8.0 * (double)iters * 4.0 * (double)n_blocks;   // 8x8x4 FMAs per DMMA, 4 warps per CTA
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return BI_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Streaming read (sum of all doubles, 16-byte loads, grid-stride): the read-only HBM ceiling the
 // streaming likelihood kernel is compared with next to MEASURED_PEAKS.json's copy figure.

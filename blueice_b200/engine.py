@@ -13,6 +13,7 @@ Per batch of P points (workspace, reused between calls):
     weight [P, C], mus [P, S], musum [P], status [P], partial [P, n_super], logl [P]
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -106,7 +107,8 @@ class _Workspace(object):
 class PointPlan(object):
     """Host-side schedule of a batch: which points go to which kernel (results do not depend on it)."""
 
-    def __init__(self, n_points, in_range, stream_points, group_points, work):
+    def __init__(self, n_points, in_range, stream_points, group_points, work, kernel='vector'):
+        self.kernel = kernel                    # 'mma': work units of the DMMA kernel; 'vector': stream + grouped
         self.n_points = n_points
         self.in_range = in_range
         self.stream_points = stream_points      # int32 [n_stream]
@@ -170,6 +172,65 @@ def plan_points(grid, zs, n_sources, n_super, force_kernel=None):
             work[:, 3] = np.repeat(sb_end, len(ch))
             work = np.ascontiguousarray(work[order])
     return PointPlan(P, in_range, stream_pts.astype(np.int32), group_pts.astype(np.int32), work)
+
+
+_MMA_TARGET_UNITS = int(os.environ.get('BI_MMA_TARGET_UNITS', 148 * 12 * 3))   # ~3 units per resident warp
+
+
+def plan_points_mma(grid, zs, n_sources, n_super, unit_points):
+    """Schedule of the DMMA K2 kernel (pure function; results never depend on it).
+
+    In-range points are bucketed by hypercube cell; each cell's points are cut into work units of at most
+    `unit_points` points (full units plus one remainder unit per cell); every unit is paired
+    with each of n_ranges superblock ranges.  Heaviest units first."""
+    P = len(zs)
+    in_range = grid.in_range(zs) if grid.n_dims else np.ones(P, dtype=bool)
+    idx = np.nonzero(in_range)[0]
+    empty = np.zeros(0, dtype=np.int32)
+    if len(idx) == 0 or n_super == 0:
+        return PointPlan(P, in_range, empty, empty, np.zeros((0, 4), dtype=np.int32))
+    if grid.n_dims:
+        cells = grid.cell_ids(np.asarray(zs, dtype=np.float64).reshape(P, grid.n_dims)[idx])
+        order = np.argsort(cells, kind='stable')
+        sorted_cells = cells[order]
+        sorted_idx = idx[order]
+        starts = np.flatnonzero(np.r_[True, sorted_cells[1:] != sorted_cells[:-1]])
+        ends = np.r_[starts[1:], len(sorted_cells)]
+    else:
+        sorted_idx = idx
+        starts = np.array([0])
+        ends = np.array([len(idx)])
+    firsts, counts = [], []
+    tiles_per_unit = unit_points // 8
+    for s0, e0 in zip(starts, ends):
+        n = int(e0 - s0)
+        n_mt = -(-n // 8)
+        # full units first, one remainder unit (the kernel is specialised per m-tile count; full units are
+        # the dense code path and the light remainder units fill the tail of the grid)
+        pos = int(s0)
+        while pos < e0:
+            c = min(unit_points, int(e0) - pos)
+            firsts.append(pos)
+            counts.append(c)
+            pos += c
+    firsts = np.asarray(firsts, dtype=np.int64)
+    counts = np.asarray(counts, dtype=np.int64)
+    n_ranges = int(np.clip(_MMA_TARGET_UNITS // len(firsts), 1, n_super))
+    sb_per = -(-n_super // n_ranges)
+    sb_begin = np.arange(0, n_super, sb_per, dtype=np.int64)
+    sb_end = np.minimum(sb_begin + sb_per, n_super)
+    # heaviest units first; within equal weight event-range-major so co-resident warps share tiles in L2
+    weight_class = -((counts + 7) // 8)
+    order = np.lexsort((np.tile(np.arange(len(firsts)), len(sb_begin)),
+                        np.repeat(np.arange(len(sb_begin)), len(firsts)),
+                        np.tile(weight_class, len(sb_begin))))
+    work = np.empty((len(firsts) * len(sb_begin), 4), dtype=np.int32)
+    work[:, 0] = np.tile(firsts, len(sb_begin))
+    work[:, 1] = np.tile(counts, len(sb_begin))
+    work[:, 2] = np.repeat(sb_begin, len(firsts))
+    work[:, 3] = np.repeat(sb_end, len(firsts))
+    work = np.ascontiguousarray(work[order])
+    return PointPlan(P, in_range, empty, sorted_idx.astype(np.int32), work, kernel='mma')
 
 
 class _EngineBase(object):
@@ -324,7 +385,11 @@ class UnbinnedEngine(_EngineBase):
     # -- planning (host) ------------------------------------------------------------------------
     def plan(self, zs):
         """Bucket points by hypercube cell and split the work between the two K2 kernels."""
-        return plan_points(self.grid, zs, self.n_sources, self.n_super, self.force_kernel)
+        if self.force_kernel in (None, 'mma') and self.n_sources * self.grid.n_corners <= _cabi.MMA_MAX_TERMS:
+            unit_points = int(self.lib.bi_mma_unit_points(self.n_sources, self.grid.n_corners))
+            return plan_points_mma(self.grid, zs, self.n_sources, self.n_super, unit_points)
+        return plan_points(self.grid, zs, self.n_sources, self.n_super,
+                           None if self.force_kernel == 'mma' else self.force_kernel)
 
     def upload_plan(self, plan):
         """H2D of the schedule (one pinned buffer).  Returns device views + byte count."""
@@ -362,7 +427,15 @@ class UnbinnedEngine(_EngineBase):
                 _cabi.dev_ptr(partial), st)
             _cabi.check(rc, "bi_unbinned_partials_stream")
             self.launches += 1
-        if self.n_super > 0 and len(plan.work):
+        if self.n_super > 0 and len(plan.work) and plan.kernel == 'mma':
+            rc = self.lib.bi_unbinned_partials_mma(
+                _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, S, C, _cabi.dev_ptr(group_d),
+                _cabi.dev_ptr(work_d), len(plan.work), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),
+                _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]), self.outlier_likelihood,
+                _cabi.dev_ptr(partial), st)
+            _cabi.check(rc, "bi_unbinned_partials_mma")
+            self.launches += 1
+        elif self.n_super > 0 and len(plan.work):
             rc = self.lib.bi_unbinned_partials_grouped(
                 _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, S, C, _cabi.dev_ptr(group_d),
                 _cabi.dev_ptr(work_d), len(plan.work), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),

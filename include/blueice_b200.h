@@ -136,6 +136,22 @@ int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t ld_events,
                                  const double* mus_dev, const int32_t* status_dev,
                                  double outlier_likelihood, double* partial_dev, void* stream);
 
+/*
+ * bi_unbinned_partials_mma: the FP64 tensor-pipe (DMMA) form of K2.  Work unit = one warp =
+ * up to bi_mma_unit_points(S, C) points that share a hypercube cell x a range of superblocks;
+ * work_dev [n_work, 4] int32 (first, count, superblock_begin, superblock_end) as above.
+ * Points whose status is non-zero are skipped (their partials are not written).
+ * Requires n_corners * n_sources <= BI_MMA_MAX_TERMS.
+ */
+#define BI_MMA_MAX_TERMS 32
+int bi_unbinned_partials_mma(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
+                             int32_t n_sources, int32_t n_corners,
+                             const int32_t* group_points_dev, const int32_t* work_dev, int64_t n_work,
+                             const int32_t* corner_dev, const double* weight_dev,
+                             const double* mus_dev, const int32_t* status_dev,
+                             double outlier_likelihood, double* partial_dev, void* stream);
+int32_t bi_mma_unit_points(int32_t n_sources, int32_t n_corners);
+
 /* logL[p] = -musum[p] + total(partial[p, :]) in canonical order; status != 0 -> -inf.
  * (likelihood.py:690 `-mu.sum() + np.sum(np.log(p_events))`, :347/:402 soft failures.)
  * logsum_dev (may be NULL) receives total(partial[p, :]) alone: the per-shard term that is summed over
@@ -223,6 +239,8 @@ int bi_binned_pmfs(const double* pmf_anchor_dev, const double* n_model_anchor_de
  * and a plain streaming read.  Each returns elapsed milliseconds (CUDA events on `stream`) in *ms_host.
  */
 int bi_bench_fp64_fma(int64_t fma_per_thread, int32_t n_blocks, double* sink_dev, float* ms_host,
+                      double* flops_host, void* stream);
+int bi_bench_fp64_mma(int64_t mma_per_warp, int32_t n_blocks, double* sink_dev, float* ms_host,
                       double* flops_host, void* stream);
 int bi_bench_stream_read(const double* src_dev, int64_t n_doubles, double* sink_dev, float* ms_host,
                          void* stream);

@@ -150,17 +150,18 @@ def test_unbinned_stream_matches_oracle(d, s, n):
     rng = np.random.default_rng(100 * d + s + n)
     axes, mus_anchor, ps_anchor = make_case(rng, d, s, n)
     eng = build_engine(axes, mus_anchor, ps_anchor)
-    eng.force_kernel = 'stream'
     p = 9
     zs = random_points(rng, axes, p)
     mult = rng.uniform(0.5, 2, (p, s))
     if d:
         zs[8, 0] = axes[0][-1] + 0.1
     mult[7, 0] = -1
-    got = eng.evaluate(zs, mult)
     orc = UnbinnedOracle(axes, mus_anchor).set_ps(ps_anchor)
     ref = orc.batch(zs, mult)
-    assert_logl_close(got, ref, n, "stream d=%d s=%d n=%d" % (d, s, n))
+    for mode in (None, 'stream'):                     # None: the engine's own choice (DMMA kernel when C*S <= 32)
+        eng.force_kernel = mode
+        got = eng.evaluate(zs, mult)
+        assert_logl_close(got, ref, n, "%s d=%d s=%d n=%d" % (mode, d, s, n))
 
 
 @pytest.mark.parametrize("d,s,n", [(0, 1, 1000), (1, 1, 1), (1, 2, 33), (2, 2, 5000), (2, 2, 511), (2, 2, 512),
@@ -181,10 +182,12 @@ def test_grouped_is_bitwise_identical_to_stream_and_matches_oracle(d, s, n):
         eng.force_kernel = mode
         res[mode] = eng.evaluate(zs, mult)
     assert np.array_equal(res['stream'], res['grouped'], equal_nan=True)
-    assert np.array_equal(res['stream'], res[None], equal_nan=True)
     plan = eng.plan(zs)
-    if d <= 2:
-        assert len(plan.work) > 0                     # auto mode really exercised the grouped kernel
+    if (2 ** d) * s <= 32:
+        assert plan.kernel == 'mma' and len(plan.work) > 0   # auto mode really exercised the DMMA kernel
+        assert_logl_close(res[None], res['stream'], n, "mma vs vector kernels")
+    else:
+        assert np.array_equal(res['stream'], res[None], equal_nan=True)
     orc = UnbinnedOracle(axes, mus_anchor).set_ps(ps_anchor)
     check = rng.choice(p, size=12 if n > 20000 else 40, replace=False)
     ref = orc.batch(zs[check], mult[check])
@@ -239,7 +242,7 @@ def test_nan_inf_zero_and_negative_densities(outlier):
     mult = rng.uniform(0.5, 2, (p, 2))
     mult[5, 0] = 0.0                                  # 0 * inf = NaN term, dropped
     mult[6, :] = 0.0                                  # all-zero rates: every event is an outlier
-    for mode in ('stream', 'grouped'):
+    for mode in (None, 'stream', 'grouped'):
         eng.force_kernel = mode
         got = eng.evaluate(zs, mult)
         ref = orc.batch(zs, mult)
