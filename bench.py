@@ -289,19 +289,33 @@ def run_own_arm(args):
 
     # ---- dominant kernel alone (grouped K2), for the roofline --------------------------------------
     S, C = eng.n_sources, eng.grid.n_corners
-    o = eng._setup(P, zs_d, mult_d, None, None)
-    partial = eng.ws.get("partial", P * eng.n_super, torch.float64)
     stream = eng._stream()
 
-    def launch_k2(e, pl, pl_dev, setup, part):
-        """The K2 launch(es) the plan names, alone (what run_device issues between K1 and finalize)."""
+    def mma_stage_fns(e, n_pts, z_dev, m_dev):
+        """(plan, k2) launchers of the fused path's middle stages, on the workspace a fused call has filled."""
+        outs = e.run_fused(n_pts, z_dev, m_dev, None, None)            # K1 outputs + status now live in the workspace
+        _, v = e.mma_workspace(n_pts)
+        unit_points = int(e.lib.bi_mma_unit_points(S, C))
+        from blueice_b200.engine import _MMA_TARGET_UNITS
+
+        def plan_fn():
+            _cabi.check(e.lib.bi_unbinned_plan(
+                e.grid.n_dims, _cabi.host_ptr(e.grid.n_anchors_i32), n_pts, _cabi.dev_ptr(v["cell"]),
+                _cabi.dev_ptr(outs["status"]), unit_points, e.n_events, _MMA_TARGET_UNITS,
+                _cabi.dev_ptr(v["group_points"]), _cabi.dev_ptr(v["groups"]), _cabi.dev_ptr(v["header"]),
+                e._stream()), "bi_unbinned_plan")
+
+        def k2_fn():
+            _cabi.check(e.lib.bi_unbinned_partials_mma(
+                _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(v["group_points"]),
+                _cabi.dev_ptr(v["groups"]), _cabi.dev_ptr(v["header"]), _cabi.dev_ptr(v["corner"]),
+                _cabi.dev_ptr(v["weight"]), _cabi.dev_ptr(v["mus"]), e.outlier_likelihood,
+                _cabi.dev_ptr(v["partial"]), e._stream()), "bi_unbinned_partials_mma")
+        return plan_fn, k2_fn, v
+
+    def legacy_k2(e, pl, pl_dev, setup, part):
         common = (_cabi.dev_ptr(setup["corner"]), _cabi.dev_ptr(setup["weight"]), _cabi.dev_ptr(setup["mus"]),
                   _cabi.dev_ptr(setup["status"]), e.outlier_likelihood, _cabi.dev_ptr(part), e._stream())
-        if pl.kernel == 'mma':
-            _cabi.check(e.lib.bi_unbinned_partials_mma(
-                _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(pl_dev[1]),
-                _cabi.dev_ptr(pl_dev[2]), len(pl.work), *common), "bi_unbinned_partials_mma")
-            return
         if len(pl.stream_points):
             _cabi.check(e.lib.bi_unbinned_partials_stream(
                 _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(pl_dev[0]),
@@ -311,16 +325,34 @@ def run_own_arm(args):
                 _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(pl_dev[1]),
                 _cabi.dev_ptr(pl_dev[2]), len(pl.work), *common), "bi_unbinned_partials_grouped")
 
-    def grouped_only():
-        launch_k2(eng, plan, plan_dev, o, partial)
+    if plan.kernel == 'mma':
+        plan_fn, grouped_only, views = mma_stage_fns(eng, P, zs_d, mult_d)
+    else:
+        o = eng._setup(P, zs_d, mult_d, None, None)
+        partial = eng.ws.get("partial", P * eng.n_super, torch.float64)
+
+        def plan_fn():
+            pass
+
+        def grouped_only():
+            legacy_k2(eng, plan, plan_dev, o, partial)
 
     k2_ms = []
-    n_grouped = len(plan.group_points)
-    if len(plan.work):
+    n_grouped = len(plan.group_points) if plan.kernel != 'mma' else P
+    sched = None
+    if len(plan.work) or plan.kernel == 'mma':
         for _ in range(3):
+            plan_fn()
             grouped_only()
+        if plan.kernel == 'mma':
+            torch.cuda.synchronize()
+            hdr = views["header"][:8].cpu().numpy()
+            sched = {"point_groups": int(hdr[0]), "superblock_ranges": int(hdr[1]), "superblocks_per_range": int(hdr[2]),
+                     "work_units": int(hdr[3]), "evaluable_points": int(hdr[5])}
+            n_grouped = int(hdr[5])
         for _ in range(max(args.steps, 10)):
             flush_l2()
+            plan_fn()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             grouped_only()
@@ -361,17 +393,29 @@ def run_own_arm(args):
         z1, m1 = zs[:1], mult[:1]
         plan1 = big.plan(z1)
         z1_d, m1_d, _, _, _ = big._upload_points(z1, m1, None, None)
-        plan1_dev = big.upload_plan(plan1)[:3]
-        o1 = big._setup(1, z1_d, m1_d, None, None)
-        part1 = big.ws.get("partial", big.n_super, torch.float64)
+        z1_d, m1_d = z1_d.clone(), m1_d.clone()
+        if plan1.kernel == 'mma':
+            plan1_fn, k2_1, _ = mma_stage_fns(big, 1, z1_d, m1_d)
+        else:
+            plan1_dev = big.upload_plan(plan1)[:3]
+            o1 = big._setup(1, z1_d, m1_d, None, None)
+            part1 = big.ws.get("partial", big.n_super, torch.float64)
+
+            def plan1_fn():
+                pass
+
+            def k2_1():
+                legacy_k2(big, plan1, plan1_dev, o1, part1)
 
         def stream_only():
-            launch_k2(big, plan1, plan1_dev, o1, part1)
+            k2_1()
 
         for _ in range(3):
+            plan1_fn()
             stream_only()
         sms = []
         for _ in range(10):
+            plan1_fn()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             stream_only()
@@ -443,8 +487,9 @@ def run_own_arm(args):
                 "roofline": roofline, "roofline_stream": stream_info, "cpu_baseline": cpu,
                 "clocks": clocks, "fp64_fma_peak_tflops": fp64_peak,
                 "set_data_s": set_data_s, "model_build_s": build_s,
-                "plan": {"grouped_points": int(n_grouped), "stream_points": int(len(plan.stream_points)),
-                         "work_items": int(len(plan.work))},
+                "plan": sched if sched is not None else
+                {"grouped_points": int(n_grouped), "stream_points": int(len(plan.stream_points)),
+                 "work_items": int(len(plan.work))},
                 "step_ms_min_max": [float(np.min(step_ms)), float(np.max(step_ms))]}
         print(json.dumps(line))
     if world > 1:

@@ -31,10 +31,19 @@ SIGNATURES = {
     "bi_unbinned_partials_grouped": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p,
                                                     _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
                                                     _c_void_p, _c_void_p]),
+    "bi_plan_max_cells": (_i64, []),
+    "bi_unbinned_plan": (ctypes.c_int, [_i32, _c_void_p, _i64, _c_void_p, _c_void_p, _i32, _i64, _i32,
+                                        _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_unbinned_partials_mma": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p,
-                                                _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
+                                                _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
                                                 _c_void_p, _c_void_p]),
     "bi_mma_unit_points": (_i32, [_i32, _i32]),
+    "bi_unbinned_workspace_bytes": (_i64, [_i32, _i32, _i64, _i64]),
+    "bi_unbinned_workspace_layout": (ctypes.c_int, [_i32, _i32, _i64, _i64, _c_void_p]),
+    "bi_unbinned_ll_batch": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _i64,
+                                            _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                            _c_void_p, _i64, _i64, _f64, _i32, _c_void_p, _i64,
+                                            _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_unbinned_finalize": (ctypes.c_int, [_c_void_p, _i64, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
                                             _c_void_p]),
     "bi_unbinned_ps": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p, _c_void_p,
@@ -67,6 +76,7 @@ GROUP_MAX_SOURCES = 8
 GROUP_MAX_CORNERS = 16
 STREAM_MAX_CORNERS = 32
 MMA_MAX_TERMS = 32
+PLAN_MAX_CELLS = 16384
 POINT_OUT_OF_RANGE = 1
 POINT_UNPHYSICAL = 2
 LOOKUP_LINEAR = 0

@@ -259,7 +259,8 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ src_row, 
                                             int64_t sb_begin, int64_t sb_end, int64_t ev_begin, int n_tiles, int64_t n_super,
                                             const double* __restrict__ weight,
                                             const double* __restrict__ mus, double outlier, double* __restrict__ partial,
-                                            double* ring, uint64_t* full_bar, double* slow_acc, int lane) {
+                                            double* ring, uint64_t* full_bar, double* slow_acc, unsigned tiles_done,
+                                            int lane) {
     using Cfg = BiMmaCfg<K4>;
     constexpr int T = Cfg::T;
     const int g = lane >> 2, t = lane & 3;
@@ -282,8 +283,8 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ src_row, 
 #pragma unroll
     for (int mt = 0; mt < NMT; ++mt) { M[mt] = 1.0; E[mt] = 0; }
     bool slow_any = false;
-    int st = 0, tile_idx = 0;
-    unsigned parity = 0;
+    int st = (int)(tiles_done % Cfg::STAGES), tile_idx = 0;
+    unsigned parity = (tiles_done / Cfg::STAGES) & 1u;
     constexpr int TILES_PER_SUPER = BI_SUPERBLOCK / T, GROUPS_PER_TILE = T / BI_GROUP_EVENTS;
 
     for (int64_t sb = sb_begin; sb < sb_end; ++sb) {
@@ -363,15 +364,15 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ src_row, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel: one warp per work unit (first, n_points, superblock_begin, superblock_end)
+// kernel (persistent): every warp fetches work units u = (point group u % n_groups, superblock range
+// u / n_groups) from the schedule header until all n_units are taken
 // ---------------------------------------------------------------------------------------------
 template <int K4>
 __global__ void __launch_bounds__(BI_MMA_THREADS, BiMmaCfg<K4>::MIN_CTAS)
 k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int S, int C,
-               const int32_t* __restrict__ group_points, const int4* __restrict__ work, int64_t n_work,
+               const int32_t* __restrict__ group_points, const int2* __restrict__ groups, int32_t* header,
                int64_t n_super, const int32_t* __restrict__ corner, const double* __restrict__ weight,
-               const double* __restrict__ mus, const int32_t* __restrict__ status, double outlier,
-               double* __restrict__ partial) {
+               const double* __restrict__ mus, double outlier, double* __restrict__ partial) {
     using Cfg = BiMmaCfg<K4>;
     constexpr int MT = Cfg::MT, T = Cfg::T;
     extern __shared__ __align__(128) unsigned char bi_smem[];
@@ -381,34 +382,8 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int S, int C
     double* ring = reinterpret_cast<double*>(bi_smem + Cfg::HEADER_BYTES) + (size_t)warp * Cfg::RING_DOUBLES;
     double* slow_acc = reinterpret_cast<double*>(bi_smem + Cfg::HEADER_BYTES) + (size_t)BI_MMA_WARPS * Cfg::RING_DOUBLES +
                        threadIdx.x;
-
-    const int64_t unit = (int64_t)blockIdx.x * BI_MMA_WARPS + warp;
-    if (unit >= n_work) return;
-    const int4 wk = work[unit];
-    const int first = wk.x, n_pts = wk.y;
-    const int64_t sb_begin = wk.z, sb_end = wk.w;
     const int K = C * S;
-    const int n_mt = (n_pts + 7) >> 3;
-
-    // ---- slots: point of (m-tile mt, row g); slots beyond n_pts or with a failed status replay a healthy point
-    const int32_t* slot_point = group_points + first;              // slot -> point index (slots < n_pts)
-    unsigned active_mask = 0;                                      // bit mt: this lane's slot of m-tile mt is live
-    int64_t healthy = -1;
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-        const int slot = mt * 8 + g;
-        bool ok = false;
-        int64_t p = 0;
-        if (slot < n_pts) {
-            p = slot_point[slot];
-            ok = status[p] == 0;
-        }
-        if (ok) active_mask |= 1u << mt;
-        const unsigned vote = __ballot_sync(BI_FULL_MASK, ok);
-        if (healthy < 0 && vote) healthy = __shfl_sync(BI_FULL_MASK, p, __ffs(vote) - 1);
-    }
-    if (healthy < 0) return;                                       // warp-uniform: nothing to evaluate
-    const int32_t* corner_lead = corner + healthy * C;
+    const int n_groups = header[0], sb_per = header[2], n_units = header[3];
 
     if (lane == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) bi_mbar_init(&full_bar[i], 1);
@@ -422,48 +397,88 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int S, int C
         ring[(size_t)st_i * Cfg::STAGE_DOUBLES + K * Cfg::RS + r] = 0.0;
     }
     __syncwarp();
+    unsigned tiles_done = 0;                                       // ring position carries over from unit to unit
 
-    // the first tiles are in flight while the coefficients are gathered
-    const int64_t ev_begin = sb_begin * BI_SUPERBLOCK;
-    int64_t ev_end = sb_end * BI_SUPERBLOCK;
-    if (ev_end > N) ev_end = N;
-    const int n_tiles = (int)((ev_end - ev_begin + T - 1) / T);
-    const double* src_row = A;
-    if (lane < K) {
-        const int c = lane / S, s = lane - c * S;
-        src_row = A + ((int64_t)corner_lead[c] * S + s) * ld;
-    }
-    for (int i = 0; i < Cfg::STAGES && i < n_tiles; ++i)
-        bi_mma_issue<K4>(src_row, ld, ev_begin, i, i, K, ring, full_bar, lane);
+    for (;;) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(&header[4], 1);
+        unit = __shfl_sync(BI_FULL_MASK, unit, 0);
+        if (unit >= n_units) break;
+        const int range = unit / n_groups, grp = unit - range * n_groups;
+        const int2 gp = groups[grp];
+        const int n_pts = gp.y;
+        const int64_t sb_begin = (int64_t)range * sb_per;
+        int64_t sb_end = sb_begin + sb_per;
+        if (sb_end > n_super) sb_end = n_super;
+        const int n_mt = (n_pts + 7) >> 3;
+
+        // slots: point of (m-tile mt, row g); slots beyond n_pts replay the group's first point
+        const int32_t* slot_point = group_points + gp.x;
+        unsigned active_mask = 0;                                  // bit mt: this lane's slot of m-tile mt is live
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+            if (mt * 8 + g < n_pts) active_mask |= 1u << mt;
+        const int64_t lead = slot_point[0];
+        const int32_t* corner_lead = corner + lead * C;
+
+        // the first tiles are in flight while the coefficients are gathered
+        const int64_t ev_begin = sb_begin * BI_SUPERBLOCK;
+        int64_t ev_end = sb_end * BI_SUPERBLOCK;
+        if (ev_end > N) ev_end = N;
+        const int n_tiles = (int)((ev_end - ev_begin + T - 1) / T);
+        const double* src_row = A;
+        if (lane < K) {
+            const int c = lane / S, s = lane - c * S;
+            src_row = A + ((int64_t)corner_lead[c] * S + s) * ld;
+        }
+        for (int i = 0; i < Cfg::STAGES && i < n_tiles; ++i)
+            bi_mma_issue<K4>(src_row, ld, ev_begin, i, (tiles_done + i) % Cfg::STAGES, K, ring, full_bar, lane);
 
 #define BI_MMA_UNIT(NN)                                                                                              \
     case NN:                                                                                                         \
         if (NN <= MT)                                                                                                \
-            bi_mma_unit<K4, (NN <= MT ? NN : 1)>(src_row, ld, N, S, C, slot_point, active_mask, healthy, sb_begin,  \
+            bi_mma_unit<K4, (NN <= MT ? NN : 1)>(src_row, ld, N, S, C, slot_point, active_mask, lead, sb_begin,     \
                                                  sb_end, ev_begin, n_tiles, n_super, weight, mus, outlier, partial,  \
-                                                 ring, full_bar, slow_acc, lane);                                    \
+                                                 ring, full_bar, slow_acc, tiles_done, lane);                        \
         break;
-    switch (n_mt) {
-        BI_MMA_UNIT(1) BI_MMA_UNIT(2) BI_MMA_UNIT(3) BI_MMA_UNIT(4)
-        BI_MMA_UNIT(5) BI_MMA_UNIT(6) BI_MMA_UNIT(7) BI_MMA_UNIT(8)
-    }
+        switch (n_mt) {
+            BI_MMA_UNIT(1) BI_MMA_UNIT(2) BI_MMA_UNIT(3) BI_MMA_UNIT(4)
+            BI_MMA_UNIT(5) BI_MMA_UNIT(6) BI_MMA_UNIT(7) BI_MMA_UNIT(8)
+        }
 #undef BI_MMA_UNIT
+        tiles_done += (unsigned)n_tiles;
+    }
+}
+
+// resident CTAs of the persistent kernel on the current device
+template <int K4>
+static int bi_mma_grid(int* blocks) {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0, sms = 0, per_sm = 0;
+        BI_CUDA_CHECK(cudaGetDevice(&dev));
+        BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        BI_CUDA_CHECK(cudaFuncSetAttribute(k_unbinned_mma<K4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           BiMmaCfg<K4>::SMEM_BYTES));
+        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unbinned_mma<K4>, BI_MMA_THREADS,
+                                                                    BiMmaCfg<K4>::SMEM_BYTES));
+        BI_REQUIRE(per_sm >= 1, "k_unbinned_mma<%d> does not fit on this device", K4);
+        cached = sms * per_sm;
+    }
+    *blocks = cached;
+    return BI_OK;
 }
 
 template <int K4>
 static int bi_launch_mma(const double* A, int64_t ld, int64_t N, int S, int C, const int32_t* group_points,
-                         const int32_t* work, int64_t n_work, int64_t n_super, const int32_t* corner,
-                         const double* weight, const double* mus, const int32_t* status, double outlier,
-                         double* partial, cudaStream_t st) {
+                         const int32_t* groups, int32_t* header, int64_t n_super, const int32_t* corner,
+                         const double* weight, const double* mus, double outlier, double* partial, cudaStream_t st) {
     using Cfg = BiMmaCfg<K4>;
-    static bool configured = false;
-    if (!configured) {
-        BI_CUDA_CHECK(cudaFuncSetAttribute(k_unbinned_mma<K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
-    const int64_t blocks = (n_work + BI_MMA_WARPS - 1) / BI_MMA_WARPS;
+    int blocks = 0;
+    int rc = bi_mma_grid<K4>(&blocks);
+    if (rc != BI_OK) return rc;
     k_unbinned_mma<K4><<<(unsigned)blocks, BI_MMA_THREADS, Cfg::SMEM_BYTES, st>>>(
-        A, ld, N, S, C, group_points, reinterpret_cast<const int4*>(work), n_work, n_super, corner, weight, mus, status,
+        A, ld, N, S, C, group_points, reinterpret_cast<const int2*>(groups), header, n_super, corner, weight, mus,
         outlier, partial);
     BI_LAUNCH_CHECK();
     return BI_OK;

@@ -174,63 +174,8 @@ def plan_points(grid, zs, n_sources, n_super, force_kernel=None):
     return PointPlan(P, in_range, stream_pts.astype(np.int32), group_pts.astype(np.int32), work)
 
 
-_MMA_TARGET_UNITS = int(os.environ.get('BI_MMA_TARGET_UNITS', 148 * 12 * 3))   # ~3 units per resident warp
-
-
-def plan_points_mma(grid, zs, n_sources, n_super, unit_points):
-    """Schedule of the DMMA K2 kernel (pure function; results never depend on it).
-
-    In-range points are bucketed by hypercube cell; each cell's points are cut into work units of at most
-    `unit_points` points (full units plus one remainder unit per cell); every unit is paired
-    with each of n_ranges superblock ranges.  Heaviest units first."""
-    P = len(zs)
-    in_range = grid.in_range(zs) if grid.n_dims else np.ones(P, dtype=bool)
-    idx = np.nonzero(in_range)[0]
-    empty = np.zeros(0, dtype=np.int32)
-    if len(idx) == 0 or n_super == 0:
-        return PointPlan(P, in_range, empty, empty, np.zeros((0, 4), dtype=np.int32))
-    if grid.n_dims:
-        cells = grid.cell_ids(np.asarray(zs, dtype=np.float64).reshape(P, grid.n_dims)[idx])
-        order = np.argsort(cells, kind='stable')
-        sorted_cells = cells[order]
-        sorted_idx = idx[order]
-        starts = np.flatnonzero(np.r_[True, sorted_cells[1:] != sorted_cells[:-1]])
-        ends = np.r_[starts[1:], len(sorted_cells)]
-    else:
-        sorted_idx = idx
-        starts = np.array([0])
-        ends = np.array([len(idx)])
-    firsts, counts = [], []
-    tiles_per_unit = unit_points // 8
-    for s0, e0 in zip(starts, ends):
-        n = int(e0 - s0)
-        n_mt = -(-n // 8)
-        # full units first, one remainder unit (the kernel is specialised per m-tile count; full units are
-        # the dense code path and the light remainder units fill the tail of the grid)
-        pos = int(s0)
-        while pos < e0:
-            c = min(unit_points, int(e0) - pos)
-            firsts.append(pos)
-            counts.append(c)
-            pos += c
-    firsts = np.asarray(firsts, dtype=np.int64)
-    counts = np.asarray(counts, dtype=np.int64)
-    n_ranges = int(np.clip(_MMA_TARGET_UNITS // len(firsts), 1, n_super))
-    sb_per = -(-n_super // n_ranges)
-    sb_begin = np.arange(0, n_super, sb_per, dtype=np.int64)
-    sb_end = np.minimum(sb_begin + sb_per, n_super)
-    # heaviest units first; within equal weight event-range-major so co-resident warps share tiles in L2
-    weight_class = -((counts + 7) // 8)
-    order = np.lexsort((np.tile(np.arange(len(firsts)), len(sb_begin)),
-                        np.repeat(np.arange(len(sb_begin)), len(firsts)),
-                        np.tile(weight_class, len(sb_begin))))
-    work = np.empty((len(firsts) * len(sb_begin), 4), dtype=np.int32)
-    work[:, 0] = np.tile(firsts, len(sb_begin))
-    work[:, 1] = np.tile(counts, len(sb_begin))
-    work[:, 2] = np.repeat(sb_begin, len(firsts))
-    work[:, 3] = np.repeat(sb_end, len(firsts))
-    work = np.ascontiguousarray(work[order])
-    return PointPlan(P, in_range, empty, sorted_idx.astype(np.int32), work, kernel='mma')
+_MMA_TARGET_UNITS = int(os.environ.get('BI_MMA_TARGET_UNITS', 148 * 12 * 2))   # ~2 units per resident warp (measured optimum)
+_EMPTY_I32 = np.zeros(0, dtype=np.int32)
 
 
 class _EngineBase(object):
@@ -385,15 +330,55 @@ class UnbinnedEngine(_EngineBase):
     # -- planning (host) ------------------------------------------------------------------------
     def plan(self, zs):
         """Bucket points by hypercube cell and split the work between the two K2 kernels."""
-        if self.force_kernel in (None, 'mma') and self.n_sources * self.grid.n_corners <= _cabi.MMA_MAX_TERMS:
-            unit_points = int(self.lib.bi_mma_unit_points(self.n_sources, self.grid.n_corners))
-            return plan_points_mma(self.grid, zs, self.n_sources, self.n_super, unit_points)
+        if self.uses_mma():
+            return PointPlan(len(zs), None, _EMPTY_I32, _EMPTY_I32, np.zeros((0, 4), dtype=np.int32), kernel='mma')
         return plan_points(self.grid, zs, self.n_sources, self.n_super,
                            None if self.force_kernel == 'mma' else self.force_kernel)
+
+    def uses_mma(self):
+        """True when the batch runs through the fused device path (K1 -> device schedule -> DMMA K2 -> finalize)."""
+        n_cells = int(np.prod([max(n - 1, 1) for n in self.grid.n_anchors_i32])) if self.grid.n_dims else 1
+        return (self.force_kernel in (None, 'mma') and self.n_sources * self.grid.n_corners <= _cabi.MMA_MAX_TERMS
+                and n_cells <= _cabi.PLAN_MAX_CELLS)
+
+    def mma_workspace(self, P):
+        """(workspace tensor, dict of typed device views) for a P-point batch of the fused path."""
+        torch = self.torch
+        D, S = self.grid.n_dims, self.n_sources
+        off = np.zeros(10, dtype=np.int64)
+        _cabi.check(self.lib.bi_unbinned_workspace_layout(D, S, P, self.n_events, _cabi.host_ptr(off)),
+                    "bi_unbinned_workspace_layout")
+        ws = self.ws.get("mma_ws", int(off[9]), torch.uint8)
+        names = ["cell", "frac", "corner", "weight", "mus", "partial", "group_points", "groups", "header"]
+        dtypes = [torch.int32, torch.float64, torch.int32, torch.float64, torch.float64, torch.float64,
+                  torch.int32, torch.int32, torch.int32]
+        views = {}
+        for i, (name, dt) in enumerate(zip(names, dtypes)):
+            views[name] = ws[int(off[i]):int(off[i + 1])].view(dt)
+        return ws, views
+
+    def run_fused(self, P, zs_d, mult_d, scale_d, eff_d):
+        """ONE C-ABI call: K1 -> device schedule -> K2 (DMMA) -> finalize.  Returns dict of device outputs."""
+        torch = self.torch
+        ws, _ = self.mma_workspace(P)
+        out = dict(logl=self.ws.get("logl", P, torch.float64), logsum=self.ws.get("logsum", P, torch.float64),
+                   musum=self.ws.get("musum", P, torch.float64), status=self.ws.get("status", P, torch.int32))
+        rc = self.lib.bi_unbinned_ll_batch(
+            self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat),
+            self.n_sources, P, _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
+            _cabi.dev_ptr(self.mus_anchor), _cabi.host_ptr(self.allow_negative),
+            _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, self.outlier_likelihood, _MMA_TARGET_UNITS,
+            _cabi.dev_ptr(ws), ws.numel(), _cabi.dev_ptr(out["logl"]), _cabi.dev_ptr(out["logsum"]),
+            _cabi.dev_ptr(out["musum"]), _cabi.dev_ptr(out["status"]), self._stream())
+        _cabi.check(rc, "bi_unbinned_ll_batch")
+        self.launches += 4 if self.n_super > 0 else 2
+        return out
 
     def upload_plan(self, plan):
         """H2D of the schedule (one pinned buffer).  Returns device views + byte count."""
         torch = self.torch
+        if plan.kernel == 'mma':
+            return None, None, None, 0
         n_s, n_g, n_w = len(plan.stream_points), len(plan.group_points), len(plan.work)
         off_g = round_up(n_s, 4)
         off_w = off_g + round_up(n_g, 4)
@@ -414,6 +399,9 @@ class UnbinnedEngine(_EngineBase):
         torch = self.torch
         if self.ps_anchor is None:
             raise RuntimeError("set_ps_anchor / allocate_ps_anchor must be called first")
+        if plan.kernel == 'mma':
+            o = self.run_fused(P, zs_d, mult_d, scale_d, eff_d)
+            return (o["logl"], o) if want_setup else o["logl"]
         S, C = self.n_sources, self.grid.n_corners
         o = self._setup(P, zs_d, mult_d, scale_d, eff_d)
         partial = self.ws.get("partial", P * max(self.n_super, 1), torch.float64)
@@ -427,15 +415,7 @@ class UnbinnedEngine(_EngineBase):
                 _cabi.dev_ptr(partial), st)
             _cabi.check(rc, "bi_unbinned_partials_stream")
             self.launches += 1
-        if self.n_super > 0 and len(plan.work) and plan.kernel == 'mma':
-            rc = self.lib.bi_unbinned_partials_mma(
-                _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, S, C, _cabi.dev_ptr(group_d),
-                _cabi.dev_ptr(work_d), len(plan.work), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),
-                _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]), self.outlier_likelihood,
-                _cabi.dev_ptr(partial), st)
-            _cabi.check(rc, "bi_unbinned_partials_mma")
-            self.launches += 1
-        elif self.n_super > 0 and len(plan.work):
+        if self.n_super > 0 and len(plan.work):
             rc = self.lib.bi_unbinned_partials_grouped(
                 _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, S, C, _cabi.dev_ptr(group_d),
                 _cabi.dev_ptr(work_d), len(plan.work), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),

@@ -137,20 +137,59 @@ int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t ld_events,
                                  double outlier_likelihood, double* partial_dev, void* stream);
 
 /*
- * bi_unbinned_partials_mma: the FP64 tensor-pipe (DMMA) form of K2.  Work unit = one warp =
- * up to bi_mma_unit_points(S, C) points that share a hypercube cell x a range of superblocks;
- * work_dev [n_work, 4] int32 (first, count, superblock_begin, superblock_end) as above.
- * Points whose status is non-zero are skipped (their partials are not written).
- * Requires n_corners * n_sources <= BI_MMA_MAX_TERMS.
+ * Device-side schedule for bi_unbinned_partials_mma (no host round trip per batch).  Buckets the
+ * evaluable points (status == 0) by hypercube cell and cuts them into point groups of at most
+ * `unit_points` = bi_mma_unit_points(S, C) points.
+ *   cell_dev / status_dev   outputs of bi_point_setup ([P, max(D, 1)] and [P])
+ *   group_points_dev [P]    out: point indices, cell-major
+ *   groups_dev [(P + 1) * 2] out: (first, count) per point group
+ *   header_dev [8]          out: n_groups, n_ranges, superblocks_per_range, n_units, 0 (fetch counter),
+ *                           n_evaluable, 0, 0.  Work unit u = (group u % n_groups, range u / n_groups).
+ *   target_units            aimed-at number of work units (a few per resident warp)
+ * Grids with more than BI_PLAN_MAX_CELLS hypercube cells are rejected (BI_ERR_INVALID_ARGUMENT).
+ */
+#define BI_PLAN_MAX_CELLS 16384
+int64_t bi_plan_max_cells(void);
+int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_points,
+                     const int32_t* cell_dev, const int32_t* status_dev, int32_t unit_points,
+                     int64_t n_events, int32_t target_units,
+                     int32_t* group_points_dev, int32_t* groups_dev, int32_t* header_dev, void* stream);
+
+/*
+ * bi_unbinned_partials_mma: K2 on the FP64 tensor pipe (DMMA.8x8x4), persistent: every warp fetches
+ * work units (point group x superblock range) from header_dev[4] until header_dev[3] units are done.
+ * group_points_dev / groups_dev / header_dev as written by bi_unbinned_plan (or by the caller: all
+ * points of a group MUST share their corner list, have status 0, and count <= bi_mma_unit_points;
+ * header_dev[4] must be 0 on entry).  Requires n_corners * n_sources <= BI_MMA_MAX_TERMS.
  */
 #define BI_MMA_MAX_TERMS 32
 int bi_unbinned_partials_mma(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
                              int32_t n_sources, int32_t n_corners,
-                             const int32_t* group_points_dev, const int32_t* work_dev, int64_t n_work,
-                             const int32_t* corner_dev, const double* weight_dev,
-                             const double* mus_dev, const int32_t* status_dev,
+                             const int32_t* group_points_dev, const int32_t* groups_dev, int32_t* header_dev,
+                             const int32_t* corner_dev, const double* weight_dev, const double* mus_dev,
                              double outlier_likelihood, double* partial_dev, void* stream);
 int32_t bi_mma_unit_points(int32_t n_sources, int32_t n_corners);
+
+/*
+ * The whole unbinned hot path in ONE call: K1 point set-up -> device-side schedule -> K2 (DMMA) ->
+ * finalize.  Replaces LogLikelihoodBase.__call__'s numerics for a batch of P points
+ * (likelihood.py:318-427 with UnbinnedLogLikelihood._compute_likelihood, :571-573).
+ *   workspace_dev   bi_unbinned_workspace_bytes(n_dims, n_sources, n_points, n_events) bytes, 256-byte aligned
+ *   logl_dev [P], logsum_dev [P] (may be NULL), musum_dev [P], status_dev [P]: outputs
+ */
+int64_t bi_unbinned_workspace_bytes(int32_t n_dims, int32_t n_sources, int64_t n_points, int64_t n_events);
+/* byte offsets of the workspace regions: cell, frac, corner, weight, mus, partial, group_points, groups,
+ * header, total (10 int64) -- lets a caller run / inspect the stages separately */
+int bi_unbinned_workspace_layout(int32_t n_dims, int32_t n_sources, int64_t n_points, int64_t n_events,
+                                 int64_t* offsets_host);
+int bi_unbinned_ll_batch(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                         int32_t n_sources, int64_t n_points,
+                         const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                         const double* eff_dev, const double* mus_anchor_dev, const uint8_t* allow_negative_host,
+                         const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
+                         double outlier_likelihood, int32_t target_units,
+                         void* workspace_dev, int64_t workspace_bytes,
+                         double* logl_dev, double* logsum_dev, double* musum_dev, int32_t* status_dev, void* stream);
 
 /* logL[p] = -musum[p] + total(partial[p, :]) in canonical order; status != 0 -> -inf.
  * (likelihood.py:690 `-mu.sum() + np.sum(np.log(p_events))`, :347/:402 soft failures.)

@@ -1,0 +1,69 @@
+"""Steady-state efficiency of the DMMA K2 kernel: full units only, exactly `waves` units per resident warp.
+    BI_MMA_TARGET_UNITS=<units> python profiles/steady_state.py [points] [superblocks_per_unit] [waves]
+Prints the kernel time against the FP64-pipe ideal (8 DMMA-equivalent + 1 DMUL per point-event)."""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+points = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+sb_per_unit = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+waves = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+groups = -(-points // 64)
+units = 148 * 12 * waves
+os.environ['BI_MMA_TARGET_UNITS'] = str(units)
+import torch                                     # noqa: E402
+from blueice_b200 import _cabi                   # noqa: E402
+from blueice_b200.engine import MorphGrid, UnbinnedEngine, _MMA_TARGET_UNITS   # noqa: E402
+
+n_events = (units // groups) * sb_per_unit * 512
+axes = [np.linspace(-2, 2, 5), np.linspace(-2, 2, 5)]
+rng = np.random.default_rng(0)
+eng = UnbinnedEngine(MorphGrid(axes), rng.uniform(50, 100, (25, 2)))
+eng.allocate_ps_anchor(n_events)
+eng.ps_anchor.uniform_(1e-4, 1e-2)
+zs = np.column_stack([rng.uniform(-0.9, -0.1, points), rng.uniform(0.1, 0.9, points)])     # one cell
+mult = rng.uniform(0.5, 1.5, (points, 2))
+zs_d, mult_d, _, _, _ = eng._upload_points(zs, mult, None, None)
+zs_d, mult_d = zs_d.clone(), mult_d.clone()
+outs = eng.run_fused(points, zs_d, mult_d, None, None)
+_, v = eng.mma_workspace(points)
+S, C = 2, 4
+up = int(eng.lib.bi_mma_unit_points(S, C))
+
+
+def plan_fn():
+    _cabi.check(eng.lib.bi_unbinned_plan(2, _cabi.host_ptr(eng.grid.n_anchors_i32), points, _cabi.dev_ptr(v["cell"]),
+                                         _cabi.dev_ptr(outs["status"]), up, n_events, _MMA_TARGET_UNITS,
+                                         _cabi.dev_ptr(v["group_points"]), _cabi.dev_ptr(v["groups"]),
+                                         _cabi.dev_ptr(v["header"]), eng._stream()), "plan")
+
+
+def k2_fn():
+    _cabi.check(eng.lib.bi_unbinned_partials_mma(_cabi.dev_ptr(eng.ps_anchor), eng.ld, n_events, S, C,
+                                                 _cabi.dev_ptr(v["group_points"]), _cabi.dev_ptr(v["groups"]),
+                                                 _cabi.dev_ptr(v["header"]), _cabi.dev_ptr(v["corner"]),
+                                                 _cabi.dev_ptr(v["weight"]), _cabi.dev_ptr(v["mus"]), 1e-12,
+                                                 _cabi.dev_ptr(v["partial"]), eng._stream()), "k2")
+
+
+ms = []
+for i in range(8):
+    plan_fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    k2_fn()
+    b.record()
+    torch.cuda.synchronize()
+    if i >= 3:
+        ms.append(a.elapsed_time(b))
+hdr = v["header"][:8].cpu().numpy()
+t = float(np.mean(ms))
+pe = float(points) * n_events
+ideal_cycles = pe * (8 / 256 * 16 + 1 / 32 * 2) / (148 * 4)
+print("points %d events %d units %d (groups %d x ranges %d, %d sb each): %.4f ms; pipe-ideal %.4f ms @1.92GHz -> %.1f%%; "
+      "%.3e point-events/s; %.2f TFLOP/s (2CS flops)" % (points, n_events, hdr[3], hdr[0], hdr[1], hdr[2], t,
+                                                          ideal_cycles / 1.92e6, 100 * ideal_cycles / 1.92e6 / t,
+                                                          pe / t * 1e3, pe * 16 / t * 1e-9))
