@@ -295,22 +295,12 @@ def run_own_arm(args):
         """(plan, k2) launchers of the fused path's middle stages, on the workspace a fused call has filled."""
         outs = e.run_fused(n_pts, z_dev, m_dev, None, None)            # K1 outputs + status now live in the workspace
         _, v = e.mma_workspace(n_pts)
-        unit_points = int(e.lib.bi_mma_unit_points(S, C))
-        from blueice_b200.engine import _MMA_TARGET_UNITS
 
         def plan_fn():
-            _cabi.check(e.lib.bi_unbinned_plan(
-                e.grid.n_dims, _cabi.host_ptr(e.grid.n_anchors_i32), n_pts, _cabi.dev_ptr(v["cell"]),
-                _cabi.dev_ptr(outs["status"]), unit_points, e.n_events, _MMA_TARGET_UNITS,
-                _cabi.dev_ptr(v["group_points"]), _cabi.dev_ptr(v["groups"]), _cabi.dev_ptr(v["header"]),
-                e._stream()), "bi_unbinned_plan")
+            e.mma_plan(n_pts, v, outs["status"])
 
         def k2_fn():
-            _cabi.check(e.lib.bi_unbinned_partials_mma(
-                _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(v["group_points"]),
-                _cabi.dev_ptr(v["groups"]), _cabi.dev_ptr(v["header"]), _cabi.dev_ptr(v["corner"]),
-                _cabi.dev_ptr(v["weight"]), _cabi.dev_ptr(v["mus"]), e.outlier_likelihood,
-                _cabi.dev_ptr(v["partial"]), e._stream()), "bi_unbinned_partials_mma")
+            e.mma_k2(v)
         return plan_fn, k2_fn, v
 
     def legacy_k2(e, pl, pl_dev, setup, part):

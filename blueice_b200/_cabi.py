@@ -24,7 +24,7 @@ SIGNATURES = {
     "bi_point_setup": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _i64,
                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                                      _c_void_p, _c_void_p]),
+                                      _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_unbinned_partials_stream": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _i64,
                                                    _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
                                                    _c_void_p, _c_void_p]),
@@ -35,11 +35,11 @@ SIGNATURES = {
     "bi_unbinned_plan": (ctypes.c_int, [_i32, _c_void_p, _i64, _c_void_p, _c_void_p, _i32, _i64, _i32,
                                         _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_unbinned_partials_mma": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p,
-                                                _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
-                                                _c_void_p, _c_void_p]),
-    "bi_mma_unit_points": (_i32, [_i32, _i32]),
-    "bi_unbinned_workspace_bytes": (_i64, [_i32, _i32, _i64, _i64]),
-    "bi_unbinned_workspace_layout": (ctypes.c_int, [_i32, _i32, _i64, _i64, _c_void_p]),
+                                                _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                                _f64, _c_void_p, _c_void_p]),
+    "bi_mma_unit_points": (_i32, [_i32]),
+    "bi_unbinned_workspace_bytes": (_i64, [_i32, _i32, _i32, _i64, _i64]),
+    "bi_unbinned_workspace_layout": (ctypes.c_int, [_i32, _i32, _i32, _i64, _i64, _c_void_p]),
     "bi_unbinned_ll_batch": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _i64,
                                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                             _c_void_p, _i64, _i64, _f64, _i32, _c_void_p, _i64,
@@ -75,7 +75,7 @@ GROUP_POINTS = 256
 GROUP_MAX_SOURCES = 8
 GROUP_MAX_CORNERS = 16
 STREAM_MAX_CORNERS = 32
-MMA_MAX_TERMS = 32
+MMA_MAX_TERMS = 128
 PLAN_MAX_CELLS = 16384
 POINT_OUT_OF_RANGE = 1
 POINT_UNPHYSICAL = 2

@@ -40,8 +40,11 @@ k_point_setup(const __grid_constant__ BiGrid grid, int n_sources, int64_t n_poin
               int32_t* __restrict__ cell_out, double* __restrict__ frac_out,
               int32_t* __restrict__ corner_out, double* __restrict__ weight_out,
               double* __restrict__ mus_out, double* __restrict__ musum_out,
-              int32_t* __restrict__ status_out) {
+              int32_t* __restrict__ status_out, int32_t* __restrict__ row_out, double* __restrict__ coef_out,
+              double* __restrict__ wterm_out, int32_t* __restrict__ term_source_out) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0 && term_source_out)
+        for (int k = 0; k < grid.n_corners * n_sources; ++k) term_source_out[k] = k % n_sources;
     if (p >= n_points) return;
     const int D = grid.n_dims, C = grid.n_corners, S = n_sources;
     int status = BI_POINT_OK;
@@ -103,6 +106,20 @@ k_point_setup(const __grid_constant__ BiGrid grid, int n_sources, int64_t n_poin
     const double musum = bi_numpy_sum_small(mu_local, S);
     musum_out[p] = musum;
 
+    // contraction terms of K2 (DMMA form): k = c * S + s -> row of the [G * S, ld] anchor tensor, weight, coefficient
+    if (row_out) {
+        const int64_t K = (int64_t)C * S;
+        for (int c = 0; c < C; ++c) {
+            const int flat = corner_out[p * C + c];
+            const double w = weight_out[p * C + c];
+            for (int s = 0; s < S; ++s) {
+                row_out[p * K + c * S + s] = flat * S + s;
+                wterm_out[p * K + c * S + s] = w;
+                coef_out[p * K + c * S + s] = __dmul_rn(w, mu_local[s]);
+            }
+        }
+    }
+
     // likelihood.py:397-415
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     bool bad = false;
@@ -149,7 +166,9 @@ extern "C" int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, con
                               const double* eff_dev, const double* mus_anchor_dev,
                               const uint8_t* allow_negative_host,
                               int32_t* cell_dev, double* frac_dev, int32_t* corner_dev, double* weight_dev,
-                              double* mus_dev, double* musum_dev, int32_t* status_dev, void* stream) {
+                              double* mus_dev, double* musum_dev, int32_t* status_dev,
+                              int32_t* row_dev, double* coef_dev, double* wterm_dev, int32_t* term_source_dev,
+                              void* stream) {
     BiGrid grid;
     int rc = bi_fill_grid(&grid, n_dims, n_anchors_host, axes_host);
     if (rc != BI_OK) return rc;
@@ -159,6 +178,8 @@ extern "C" int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, con
     BI_REQUIRE(rate_mult_dev && mus_anchor_dev && corner_dev && weight_dev && mus_dev && musum_dev && status_dev,
                "bi_point_setup: NULL device pointer");
     BI_REQUIRE(n_dims == 0 || (zs_dev && cell_dev && frac_dev), "bi_point_setup: NULL zs/cell/frac pointer");
+    BI_REQUIRE(!row_dev || (coef_dev && wterm_dev && term_source_dev),
+               "bi_point_setup: row_dev needs coef_dev, wterm_dev and term_source_dev");
     BiAllowNegative allow;
     memset(&allow, 0, sizeof(allow));
     if (allow_negative_host)
@@ -167,7 +188,8 @@ extern "C" int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, con
     const int64_t blocks = (n_points + threads - 1) / threads;
     k_point_setup<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
         grid, n_sources, n_points, zs_dev, rate_mult_dev, scale_dev, eff_dev, mus_anchor_dev, allow,
-        cell_dev, frac_dev, corner_dev, weight_dev, mus_dev, musum_dev, status_dev);
+        cell_dev, frac_dev, corner_dev, weight_dev, mus_dev, musum_dev, status_dev, row_dev, coef_dev, wterm_dev,
+        term_source_dev);
     BI_LAUNCH_CHECK();
     return BI_OK;
 }

@@ -2,10 +2,12 @@
 //
 // Replaces, for a batch of P parameter points over N events (blueice/likelihood.py:355-356,678-690 and
 // scipy/interpolate/_rgi.py:520-549):
-//     f(theta_p, x_i) = sum_{c,s} (w_{p,c} * mu_{p,s}) * A[corner_c, s, i]       (morph x mixture as ONE contraction)
+//     f(theta_p, x_i) = sum_k coef_{p,k} * A[row_{p,k}, i],  coef = fl(w * mu)      (morph x mixture as ONE contraction;
+//                       term k = (corner c, source s) of the full anchor grid, or (source s, corner c_s of
+//                       that source's own sub-grid) with source-wise interpolation, likelihood.py:210-240)
 //     partial[p, j]   = sum_{i in superblock j} log f(theta_p, x_i)
 //
-// The contraction over k = c*S + s (K = C*S terms) of 8 points x 8 events is one chain of
+// The contraction over the K terms of 8 points x 8 events is one chain of
 // mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): A operand = the points' coefficients (registers, loaded once
 // per work unit), B operand = the event tile (shared memory, staged by TMA bulk copies through a
 // per-warp mbarrier ring), D = densities, 2 consecutive events of one point per thread.  DMMA and DFMA
@@ -32,34 +34,30 @@
 #pragma once
 #include "bi_common.cuh"
 
-#define BI_MMA_WARPS 4
-#define BI_MMA_THREADS (BI_MMA_WARPS * 32)
 #define BI_GROUP_EVENTS 32
 #define BI_GROUPS_PER_SUPER (BI_SUPERBLOCK / BI_GROUP_EVENTS)
 // p in [2^-126, 2^127)  <=>  (unsigned)(hi32(p) - BI_RANGE_LO) < BI_RANGE_SPAN
 #define BI_RANGE_LO ((1023 - 126) << 20)
 #define BI_RANGE_SPAN (253u << 20)
 
+// K4 = k-steps of 4 terms (instantiated: 1..8, 12, 16, 24, 32 -> up to 128 terms, rows zero-padded to 4 * K4)
 template <int K4>
 struct BiMmaCfg {
-#ifndef BI_MT_SMALL
-#define BI_MT_SMALL 8
-#endif
-#ifndef BI_CTAS_SMALL
-#define BI_CTAS_SMALL 3
-#endif
-    static constexpr int MT = K4 <= 2 ? BI_MT_SMALL : (K4 <= 4 ? 4 : 2);     // 8-point m-tiles per unit
+    static constexpr int MT = K4 <= 2 ? 8 : (K4 <= 4 ? 4 : (K4 <= 16 ? 2 : 1));   // 8-point m-tiles per unit
     static constexpr int KP = 4 * K4;                              // rows incl. zero padding
     static constexpr int T = K4 <= 2 ? 128 : (K4 <= 4 ? 64 : 32);  // events per tile (row copies of T*8 bytes)
     static constexpr int RS = T + 4;                               // row stride: B-fragment loads hit 16 distinct banks
-    static constexpr int STAGES = K4 <= 4 ? 2 : 3;
+    static constexpr int STAGES = K4 <= 4 ? 2 : (K4 <= 8 ? 3 : 2);
+    static constexpr int WARPS = K4 <= 8 ? 4 : (K4 <= 16 ? 2 : 1); // work units (warps) per CTA
+    static constexpr int THREADS = WARPS * 32;
     static constexpr int STAGE_DOUBLES = KP * RS;
     static constexpr int RING_DOUBLES = STAGES * STAGE_DOUBLES;
     static constexpr int BREG = K4 <= 4;                           // B fragments of a whole group live in registers
+    static constexpr int ROWREG = K4 <= 8;                         // K <= 32: lane k keeps the source pointer of row k
     static constexpr int HEADER_BYTES = 256;                       // mbarriers [WARPS][STAGES]
-    static constexpr int SLOW_DOUBLES = MT * BI_MMA_THREADS;       // L_t accumulators (touched on the slow path only)
-    static constexpr int SMEM_BYTES = HEADER_BYTES + (BI_MMA_WARPS * RING_DOUBLES + SLOW_DOUBLES) * 8;
-    static constexpr int MIN_CTAS = K4 <= 2 ? BI_CTAS_SMALL : (K4 <= 4 ? 3 : 2);
+    static constexpr int SLOW_DOUBLES = MT * THREADS;              // L_t accumulators (touched on the slow path only)
+    static constexpr int SMEM_BYTES = HEADER_BYTES + (WARPS * RING_DOUBLES + SLOW_DOUBLES) * 8;
+    static constexpr int MIN_CTAS = K4 <= 4 ? 3 : (K4 <= 8 ? 2 : (K4 <= 16 ? 3 : (K4 <= 24 ? 4 : 3)));
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -109,14 +107,17 @@ __device__ __forceinline__ void bi_dmma(double& d0, double& d1, double a, double
 // ---------------------------------------------------------------------------------------------
 // slow path (rare; noinline keeps it out of the hot loop's register allocation)
 // ---------------------------------------------------------------------------------------------
-// density of one event with the reference's semantics; `col` points at row 0 of that event, rows `rs` apart
-static __device__ __noinline__ double bi_slow_density_rows(const double* col, int rs, int S, int C,
-                                                           const double* __restrict__ weight_p,
+// density of one event with the reference's semantics (likelihood.py:686-689); `col` points at term row 0 of that
+// event, rows `rs` apart; term k belongs to source term_source[k] and carries the morph weight wterm[k]
+static __device__ __noinline__ double bi_slow_density_rows(const double* col, int rs, int K, int S,
+                                                           const int32_t* __restrict__ term_source,
+                                                           const double* __restrict__ wterm,
                                                            const double* __restrict__ mu, double outlier) {
     double acc = 0.0;
     for (int s = 0; s < S; ++s) {
         double ps = 0.0;
-        for (int c = 0; c < C; ++c) ps = fma(col[(c * S + s) * rs], weight_p[c], ps);
+        for (int k = 0; k < K; ++k)
+            if (term_source[k] == s) ps = fma(col[k * rs], wterm[k], ps);
         const double term = __dmul_rn(mu[s], ps);
         if (term == term) acc = __dadd_rn(acc, term);       // nansum: NaN terms count as 0
     }
@@ -125,16 +126,17 @@ static __device__ __noinline__ double bi_slow_density_rows(const double* col, in
 
 // (t, group) fallback: the canonical tree over log(p_i) of the class's 8 events; grp points at row 0 of
 // the group's first event, n_valid = events of the group that exist (others count as p = 1)
-static __device__ __noinline__ double bi_slow_group(const double* grp, int rs, int S, int C, int t, int n_valid,
-                                                    const double* __restrict__ weight_p,
+static __device__ __noinline__ double bi_slow_group(const double* grp, int rs, int K, int S, int t, int n_valid,
+                                                    const int32_t* __restrict__ term_source,
+                                                    const double* __restrict__ wterm,
                                                     const double* __restrict__ mu, double outlier) {
     double quad[2];
     for (int h = 0; h < 2; ++h) {
         double pr[2];
         for (int n = 0; n < 2; ++n) {
             const int e = 8 * (2 * h + n) + 2 * t;
-            const double p0 = (e < n_valid) ? bi_slow_density_rows(grp + e, rs, S, C, weight_p, mu, outlier) : 1.0;
-            const double p1 = (e + 1 < n_valid) ? bi_slow_density_rows(grp + e + 1, rs, S, C, weight_p, mu, outlier) : 1.0;
+            const double p0 = (e < n_valid) ? bi_slow_density_rows(grp + e, rs, K, S, term_source, wterm, mu, outlier) : 1.0;
+            const double p1 = (e + 1 < n_valid) ? bi_slow_density_rows(grp + e + 1, rs, K, S, term_source, wterm, mu, outlier) : 1.0;
             pr[n] = __dadd_rn(log(p0), log(p1));
         }
         quad[h] = __dadd_rn(pr[0], pr[1]);
@@ -144,10 +146,11 @@ static __device__ __noinline__ double bi_slow_group(const double* grp, int rs, i
 
 // ---------------------------------------------------------------------------------------------
 // producer step (whole warp): arm the stage's barrier and issue the K row copies of tile `tile_idx`.
-// src_row: this lane's row (k = lane) of the cell at event 0 (lanes >= K idle); K <= 32.
+// K <= 32: src_row = this lane's row (k = lane) at event 0; otherwise rows are looked up in row_lead[K].
 // ---------------------------------------------------------------------------------------------
 template <int K4>
-__device__ __forceinline__ void bi_mma_issue(const double* __restrict__ src_row, int64_t ld, int64_t ev_begin,
+__device__ __forceinline__ void bi_mma_issue(const double* __restrict__ A, const double* __restrict__ src_row,
+                                             const int32_t* __restrict__ row_lead, int64_t ld, int64_t ev_begin,
                                              int tile_idx, int st, int K, double* ring, uint64_t* full_bar, int lane) {
     using Cfg = BiMmaCfg<K4>;
     const int64_t ev = ev_begin + (int64_t)tile_idx * Cfg::T;
@@ -159,8 +162,13 @@ __device__ __forceinline__ void bi_mma_issue(const double* __restrict__ src_row,
         bi_mbar_expect_tx(&full_bar[st], bytes * (unsigned)K);
     }
     __syncwarp();
-    if (lane < K)
-        bi_bulk_g2s(ring + (size_t)st * Cfg::STAGE_DOUBLES + (size_t)lane * Cfg::RS, src_row + ev, bytes, &full_bar[st]);
+    double* dst = ring + (size_t)st * Cfg::STAGE_DOUBLES;
+    if (Cfg::ROWREG) {
+        if (lane < K) bi_bulk_g2s(dst + (size_t)lane * Cfg::RS, src_row + ev, bytes, &full_bar[st]);
+    } else {
+        for (int k = lane; k < K; k += 32)
+            bi_bulk_g2s(dst + (size_t)k * Cfg::RS, A + (int64_t)row_lead[k] * ld + ev, bytes, &full_bar[st]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -184,9 +192,10 @@ __device__ __forceinline__ void bi_mma_tile(const double* __restrict__ bcol, con
 // of the next m-tile with the product-tree epilogue of the previous one.
 // TAIL: the group holds events >= N (they count as p = 1).
 template <int K4, int NMT, bool TAIL>
-__device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, int e0, int n_valid, int S, int C,
+__device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, int e0, int n_valid, int K, int S,
                                              unsigned active_mask, const double (&a)[NMT][K4],
-                                             const int32_t* __restrict__ slot_point, const double* __restrict__ weight,
+                                             const int32_t* __restrict__ slot_point,
+                                             const int32_t* __restrict__ term_source, const double* __restrict__ wterm,
                                              const double* __restrict__ mus, double outlier, double* slow_acc,
                                              bool& slow_any, double (&M)[NMT], int (&E)[NMT], int lane) {
     using Cfg = BiMmaCfg<K4>;
@@ -241,8 +250,8 @@ __device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, in
             if ((bad >> mt) & 1u) {
                 const int64_t p = slot_point[mt * 8 + g];
                 const int nv = TAIL ? (n_valid - e0 < BI_GROUP_EVENTS ? n_valid - e0 : BI_GROUP_EVENTS) : BI_GROUP_EVENTS;
-                const double l = bi_slow_group(tile + e0, Cfg::RS, S, C, t, nv, weight + p * C, mus + p * S, outlier);
-                double* acc = slow_acc + mt * BI_MMA_THREADS;
+                const double l = bi_slow_group(tile + e0, Cfg::RS, K, S, t, nv, term_source, wterm + p * K, mus + p * S, outlier);
+                double* acc = slow_acc + mt * Cfg::THREADS;
                 *acc = __dadd_rn(*acc, l);
                 slow_any = true;
             }
@@ -254,27 +263,27 @@ __device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, in
 // one work unit with NMT m-tiles: coefficients -> registers, then the tile loop
 // ---------------------------------------------------------------------------------------------
 template <int K4, int NMT>
-__device__ __forceinline__ void bi_mma_unit(const double* __restrict__ src_row, int64_t ld, int64_t N, int S, int C,
-                                            const int32_t* __restrict__ slot_point, unsigned active_mask, int64_t healthy,
+__device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const double* __restrict__ src_row,
+                                            const int32_t* __restrict__ row_lead, int64_t ld, int64_t N, int K, int S,
+                                            const int32_t* __restrict__ slot_point, unsigned active_mask, int64_t lead,
                                             int64_t sb_begin, int64_t sb_end, int64_t ev_begin, int n_tiles, int64_t n_super,
-                                            const double* __restrict__ weight,
-                                            const double* __restrict__ mus, double outlier, double* __restrict__ partial,
+                                            const double* __restrict__ coef, const int32_t* __restrict__ term_source,
+                                            const double* __restrict__ wterm, const double* __restrict__ mus,
+                                            double outlier, double* __restrict__ partial,
                                             double* ring, uint64_t* full_bar, double* slow_acc, unsigned tiles_done,
                                             int lane) {
     using Cfg = BiMmaCfg<K4>;
     constexpr int T = Cfg::T;
     const int g = lane >> 2, t = lane & 3;
-    const int K = C * S;
 
     double a[NMT][K4];
 #pragma unroll
     for (int mt = 0; mt < NMT; ++mt) {
-        const int64_t p = ((active_mask >> mt) & 1u) ? (int64_t)slot_point[mt * 8 + g] : healthy;
+        const int64_t p = ((active_mask >> mt) & 1u) ? (int64_t)slot_point[mt * 8 + g] : lead;
 #pragma unroll
         for (int kk = 0; kk < K4; ++kk) {
             const int k = 4 * kk + t;
-            const int c = k / S, s = k - c * S;
-            a[mt][kk] = (k < K) ? __dmul_rn(weight[p * C + c], mus[p * S + s]) : 0.0;
+            a[mt][kk] = (k < K) ? coef[p * K + k] : 0.0;
         }
     }
 
@@ -298,23 +307,23 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ src_row, 
             if (n_valid >= T) {
 #pragma unroll 1
                 for (int gi = 0; gi < GROUPS_PER_TILE; ++gi)
-                    bi_mma_group<K4, NMT, false>(tile, gi * BI_GROUP_EVENTS, T, S, C, active_mask, a, slot_point, weight,
-                                                 mus, outlier, slow_acc, slow_any, M, E, lane);
+                    bi_mma_group<K4, NMT, false>(tile, gi * BI_GROUP_EVENTS, T, K, S, active_mask, a, slot_point, term_source,
+                                                 wterm, mus, outlier, slow_acc, slow_any, M, E, lane);
             } else {
 #pragma unroll 1
                 for (int e0 = 0; e0 < n_valid; e0 += BI_GROUP_EVENTS) {
                     if (e0 + BI_GROUP_EVENTS <= n_valid)
-                        bi_mma_group<K4, NMT, false>(tile, e0, n_valid, S, C, active_mask, a, slot_point, weight, mus,
-                                                     outlier, slow_acc, slow_any, M, E, lane);
+                        bi_mma_group<K4, NMT, false>(tile, e0, n_valid, K, S, active_mask, a, slot_point, term_source, wterm,
+                                                     mus, outlier, slow_acc, slow_any, M, E, lane);
                     else
-                        bi_mma_group<K4, NMT, true>(tile, e0, n_valid, S, C, active_mask, a, slot_point, weight, mus,
-                                                    outlier, slow_acc, slow_any, M, E, lane);
+                        bi_mma_group<K4, NMT, true>(tile, e0, n_valid, K, S, active_mask, a, slot_point, term_source, wterm,
+                                                    mus, outlier, slow_acc, slow_any, M, E, lane);
                 }
             }
             // this warp is done with the stage: refill it with tile + STAGES
             __syncwarp();
             if (tile_idx + Cfg::STAGES < n_tiles)
-                bi_mma_issue<K4>(src_row, ld, ev_begin, tile_idx + Cfg::STAGES, st, K, ring, full_bar, lane);
+                bi_mma_issue<K4>(A, src_row, row_lead, ld, ev_begin, tile_idx + Cfg::STAGES, st, K, ring, full_bar, lane);
             if (++st == Cfg::STAGES) { st = 0; parity ^= 1u; }
         }
         // ---- close the superblock: combine the four classes, one log per point
@@ -344,11 +353,11 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ src_row, 
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (4 * r + q < NMT) {
-                        double l = slow_acc[(4 * r + q) * BI_MMA_THREADS];
+                        double l = slow_acc[(4 * r + q) * Cfg::THREADS];
                         l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
                         l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 2));
                         if (t == q) L = __dadd_rn(L, l);
-                        slow_acc[(4 * r + q) * BI_MMA_THREADS] = 0.0;
+                        slow_acc[(4 * r + q) * Cfg::THREADS] = 0.0;
                     }
                 }
             }
@@ -368,10 +377,11 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ src_row, 
 // u / n_groups) from the schedule header until all n_units are taken
 // ---------------------------------------------------------------------------------------------
 template <int K4>
-__global__ void __launch_bounds__(BI_MMA_THREADS, BiMmaCfg<K4>::MIN_CTAS)
-k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int S, int C,
+__global__ void __launch_bounds__(BiMmaCfg<K4>::THREADS, BiMmaCfg<K4>::MIN_CTAS)
+k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S,
                const int32_t* __restrict__ group_points, const int2* __restrict__ groups, int32_t* header,
-               int64_t n_super, const int32_t* __restrict__ corner, const double* __restrict__ weight,
+               int64_t n_super, const int32_t* __restrict__ row, const double* __restrict__ coef,
+               const double* __restrict__ wterm, const int32_t* __restrict__ term_source,
                const double* __restrict__ mus, double outlier, double* __restrict__ partial) {
     using Cfg = BiMmaCfg<K4>;
     constexpr int MT = Cfg::MT, T = Cfg::T;
@@ -380,9 +390,8 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int S, int C
     const int g = lane >> 2;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bi_smem) + warp * Cfg::STAGES;
     double* ring = reinterpret_cast<double*>(bi_smem + Cfg::HEADER_BYTES) + (size_t)warp * Cfg::RING_DOUBLES;
-    double* slow_acc = reinterpret_cast<double*>(bi_smem + Cfg::HEADER_BYTES) + (size_t)BI_MMA_WARPS * Cfg::RING_DOUBLES +
+    double* slow_acc = reinterpret_cast<double*>(bi_smem + Cfg::HEADER_BYTES) + (size_t)Cfg::WARPS * Cfg::RING_DOUBLES +
                        threadIdx.x;
-    const int K = C * S;
     const int n_groups = header[0], sb_per = header[2], n_units = header[3];
 
     if (lane == 0) {
@@ -390,7 +399,7 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int S, int C
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) slow_acc[mt * BI_MMA_THREADS] = 0.0;
+    for (int mt = 0; mt < MT; ++mt) slow_acc[mt * Cfg::THREADS] = 0.0;
     // rows K..KP-1 of every stage are never written by the TMA copies: zero them once (0 * coef 0 adds nothing)
     for (int i = lane; i < (Cfg::KP - K) * Cfg::RS * Cfg::STAGES; i += 32) {
         const int st_i = i / ((Cfg::KP - K) * Cfg::RS), r = i - st_i * (Cfg::KP - K) * Cfg::RS;
@@ -419,7 +428,7 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int S, int C
         for (int mt = 0; mt < MT; ++mt)
             if (mt * 8 + g < n_pts) active_mask |= 1u << mt;
         const int64_t lead = slot_point[0];
-        const int32_t* corner_lead = corner + lead * C;
+        const int32_t* row_lead = row + lead * K;                  // every point of the group has these rows
 
         // the first tiles are in flight while the coefficients are gathered
         const int64_t ev_begin = sb_begin * BI_SUPERBLOCK;
@@ -427,19 +436,17 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int S, int C
         if (ev_end > N) ev_end = N;
         const int n_tiles = (int)((ev_end - ev_begin + T - 1) / T);
         const double* src_row = A;
-        if (lane < K) {
-            const int c = lane / S, s = lane - c * S;
-            src_row = A + ((int64_t)corner_lead[c] * S + s) * ld;
-        }
+        if (Cfg::ROWREG && lane < K) src_row = A + (int64_t)row_lead[lane] * ld;
         for (int i = 0; i < Cfg::STAGES && i < n_tiles; ++i)
-            bi_mma_issue<K4>(src_row, ld, ev_begin, i, (tiles_done + i) % Cfg::STAGES, K, ring, full_bar, lane);
+            bi_mma_issue<K4>(A, src_row, row_lead, ld, ev_begin, i, (tiles_done + i) % Cfg::STAGES, K, ring, full_bar, lane);
 
 #define BI_MMA_UNIT(NN)                                                                                              \
     case NN:                                                                                                         \
         if (NN <= MT)                                                                                                \
-            bi_mma_unit<K4, (NN <= MT ? NN : 1)>(src_row, ld, N, S, C, slot_point, active_mask, lead, sb_begin,     \
-                                                 sb_end, ev_begin, n_tiles, n_super, weight, mus, outlier, partial,  \
-                                                 ring, full_bar, slow_acc, tiles_done, lane);                        \
+            bi_mma_unit<K4, (NN <= MT ? NN : 1)>(A, src_row, row_lead, ld, N, K, S, slot_point, active_mask, lead,   \
+                                                 sb_begin, sb_end, ev_begin, n_tiles, n_super, coef, term_source,   \
+                                                 wterm, mus, outlier, partial, ring, full_bar, slow_acc, tiles_done, \
+                                                 lane);                                                              \
         break;
         switch (n_mt) {
             BI_MMA_UNIT(1) BI_MMA_UNIT(2) BI_MMA_UNIT(3) BI_MMA_UNIT(4)
@@ -460,7 +467,7 @@ static int bi_mma_grid(int* blocks) {
         BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         BI_CUDA_CHECK(cudaFuncSetAttribute(k_unbinned_mma<K4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            BiMmaCfg<K4>::SMEM_BYTES));
-        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unbinned_mma<K4>, BI_MMA_THREADS,
+        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unbinned_mma<K4>, BiMmaCfg<K4>::THREADS,
                                                                     BiMmaCfg<K4>::SMEM_BYTES));
         BI_REQUIRE(per_sm >= 1, "k_unbinned_mma<%d> does not fit on this device", K4);
         cached = sms * per_sm;
@@ -470,16 +477,17 @@ static int bi_mma_grid(int* blocks) {
 }
 
 template <int K4>
-static int bi_launch_mma(const double* A, int64_t ld, int64_t N, int S, int C, const int32_t* group_points,
-                         const int32_t* groups, int32_t* header, int64_t n_super, const int32_t* corner,
-                         const double* weight, const double* mus, double outlier, double* partial, cudaStream_t st) {
+static int bi_launch_mma(const double* A, int64_t ld, int64_t N, int K, int S, const int32_t* group_points,
+                         const int32_t* groups, int32_t* header, int64_t n_super, const int32_t* row, const double* coef,
+                         const double* wterm, const int32_t* term_source, const double* mus, double outlier,
+                         double* partial, cudaStream_t st) {
     using Cfg = BiMmaCfg<K4>;
     int blocks = 0;
     int rc = bi_mma_grid<K4>(&blocks);
     if (rc != BI_OK) return rc;
-    k_unbinned_mma<K4><<<(unsigned)blocks, BI_MMA_THREADS, Cfg::SMEM_BYTES, st>>>(
-        A, ld, N, S, C, group_points, reinterpret_cast<const int2*>(groups), header, n_super, corner, weight, mus,
-        outlier, partial);
+    k_unbinned_mma<K4><<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
+        A, ld, N, K, S, group_points, reinterpret_cast<const int2*>(groups), header, n_super, row, coef, wterm,
+        term_source, mus, outlier, partial);
     BI_LAUNCH_CHECK();
     return BI_OK;
 }

@@ -247,7 +247,7 @@ class _EngineBase(object):
             _cabi.dev_ptr(self.mus_anchor), _cabi.host_ptr(self.allow_negative),
             _cabi.dev_ptr(out["cell"]), _cabi.dev_ptr(out["frac"]), _cabi.dev_ptr(out["corner"]),
             _cabi.dev_ptr(out["weight"]), _cabi.dev_ptr(out["mus"]), _cabi.dev_ptr(out["musum"]),
-            _cabi.dev_ptr(out["status"]), self._stream())
+            _cabi.dev_ptr(out["status"]), None, None, None, None, self._stream())
         _cabi.check(rc, "bi_point_setup")
         self.launches += 1
         return out
@@ -338,24 +338,51 @@ class UnbinnedEngine(_EngineBase):
     def uses_mma(self):
         """True when the batch runs through the fused device path (K1 -> device schedule -> DMMA K2 -> finalize)."""
         n_cells = int(np.prod([max(n - 1, 1) for n in self.grid.n_anchors_i32])) if self.grid.n_dims else 1
-        return (self.force_kernel in (None, 'mma') and self.n_sources * self.grid.n_corners <= _cabi.MMA_MAX_TERMS
+        return (self.force_kernel in (None, 'mma') and self.n_terms <= _cabi.MMA_MAX_TERMS
                 and n_cells <= _cabi.PLAN_MAX_CELLS)
+
+    @property
+    def n_terms(self):
+        """Contraction terms per point-event of K2: corners x sources of the full anchor grid."""
+        return self.n_sources * self.grid.n_corners
 
     def mma_workspace(self, P):
         """(workspace tensor, dict of typed device views) for a P-point batch of the fused path."""
         torch = self.torch
         D, S = self.grid.n_dims, self.n_sources
-        off = np.zeros(10, dtype=np.int64)
-        _cabi.check(self.lib.bi_unbinned_workspace_layout(D, S, P, self.n_events, _cabi.host_ptr(off)),
+        off = np.zeros(14, dtype=np.int64)
+        _cabi.check(self.lib.bi_unbinned_workspace_layout(D, S, self.n_terms, P, self.n_events, _cabi.host_ptr(off)),
                     "bi_unbinned_workspace_layout")
-        ws = self.ws.get("mma_ws", int(off[9]), torch.uint8)
-        names = ["cell", "frac", "corner", "weight", "mus", "partial", "group_points", "groups", "header"]
+        ws = self.ws.get("mma_ws", int(off[13]), torch.uint8)
+        names = ["cell", "frac", "corner", "weight", "mus", "partial", "group_points", "groups", "header",
+                 "row", "coef", "wterm", "term_source"]
         dtypes = [torch.int32, torch.float64, torch.int32, torch.float64, torch.float64, torch.float64,
-                  torch.int32, torch.int32, torch.int32]
+                  torch.int32, torch.int32, torch.int32, torch.int32, torch.float64, torch.float64, torch.int32]
         views = {}
         for i, (name, dt) in enumerate(zip(names, dtypes)):
             views[name] = ws[int(off[i]):int(off[i + 1])].view(dt)
         return ws, views
+
+    def mma_plan(self, P, views, status_d):
+        """Stage 2 of the fused path alone (bench / profiling): device-side schedule into the workspace views."""
+        _cabi.check(self.lib.bi_unbinned_plan(
+            self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), P, _cabi.dev_ptr(views["cell"]),
+            _cabi.dev_ptr(status_d), int(self.lib.bi_mma_unit_points(self.n_terms)), self.n_events, _MMA_TARGET_UNITS,
+            _cabi.dev_ptr(views["group_points"]), _cabi.dev_ptr(views["groups"]), _cabi.dev_ptr(views["header"]),
+            self._stream()), "bi_unbinned_plan")
+
+    def mma_k2(self, views):
+        """Stage 3 of the fused path alone (bench / profiling): the persistent DMMA kernel on a planned workspace."""
+        _cabi.check(self.lib.bi_unbinned_partials_mma(
+            _cabi.dev_ptr(self.rows_tensor()), self.ld, self.n_events, self.n_terms, self.n_sources,
+            _cabi.dev_ptr(views["group_points"]), _cabi.dev_ptr(views["groups"]), _cabi.dev_ptr(views["header"]),
+            _cabi.dev_ptr(views["row"]), _cabi.dev_ptr(views["coef"]), _cabi.dev_ptr(views["wterm"]),
+            _cabi.dev_ptr(views["term_source"]), _cabi.dev_ptr(views["mus"]), self.outlier_likelihood,
+            _cabi.dev_ptr(views["partial"]), self._stream()), "bi_unbinned_partials_mma")
+
+    def rows_tensor(self):
+        """The [n_rows, ld] per-event pdf matrix K2 contracts (the anchor tensor viewed as rows)."""
+        return self.ps_anchor
 
     def run_fused(self, P, zs_d, mult_d, scale_d, eff_d):
         """ONE C-ABI call: K1 -> device schedule -> K2 (DMMA) -> finalize.  Returns dict of device outputs."""

@@ -91,6 +91,12 @@ int64_t bi_num_superblocks(int64_t n_events);
  *   mus_dev           [P, S] scaled expected events
  *   musum_dev         [P]    sum_s mus (numpy pairwise order)
  *   status_dev        [P]    BI_POINT_* flags
+ * optional outputs (all four or none; NULL = skip) -- the contraction terms bi_unbinned_partials_mma consumes,
+ * K = C * S terms per point, term k = c * S + s:
+ *   row_dev           [P, K] int32 row of the [G * S, ld] anchor tensor (= corner_c * S + s)
+ *   coef_dev          [P, K] fl(weight_c * mus_s)
+ *   wterm_dev         [P, K] weight_c
+ *   term_source_dev   [K]    int32 source index of term k (= k % S)
  */
 int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
                    int32_t n_sources, int64_t n_points,
@@ -98,7 +104,8 @@ int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, const double* 
                    const double* eff_dev, const double* mus_anchor_dev,
                    const uint8_t* allow_negative_host,
                    int32_t* cell_dev, double* frac_dev, int32_t* corner_dev, double* weight_dev,
-                   double* mus_dev, double* musum_dev, int32_t* status_dev, void* stream);
+                   double* mus_dev, double* musum_dev, int32_t* status_dev,
+                   int32_t* row_dev, double* coef_dev, double* wterm_dev, int32_t* term_source_dev, void* stream);
 
 /*
  * K2 -- fused morph + mixture density + log + reduce, unbinned (per-superblock partial sums).
@@ -139,7 +146,7 @@ int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t ld_events,
 /*
  * Device-side schedule for bi_unbinned_partials_mma (no host round trip per batch).  Buckets the
  * evaluable points (status == 0) by hypercube cell and cuts them into point groups of at most
- * `unit_points` = bi_mma_unit_points(S, C) points.
+ * `unit_points` = bi_mma_unit_points(n_terms) points.
  *   cell_dev / status_dev   outputs of bi_point_setup ([P, max(D, 1)] and [P])
  *   group_points_dev [P]    out: point indices, cell-major
  *   groups_dev [(P + 1) * 2] out: (first, count) per point group
@@ -158,30 +165,38 @@ int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_po
 /*
  * bi_unbinned_partials_mma: K2 on the FP64 tensor pipe (DMMA.8x8x4), persistent: every warp fetches
  * work units (point group x superblock range) from header_dev[4] until header_dev[3] units are done.
- * group_points_dev / groups_dev / header_dev as written by bi_unbinned_plan (or by the caller: all
- * points of a group MUST share their corner list, have status 0, and count <= bi_mma_unit_points;
- * header_dev[4] must be 0 on entry).  Requires n_corners * n_sources <= BI_MMA_MAX_TERMS.
+ * The density is the contraction f_i = sum_k coef[p, k] * rows[row[p, k], i] over n_terms terms
+ * (bi_point_setup / bi_point_setup_sourcewise write row / coef / wterm / term_source).
+ *   rows_dev   [n_rows, ld_events] per-event pdf values, one row per (anchor, source); ld_events even
+ *   group_points_dev / groups_dev / header_dev as written by bi_unbinned_plan (or by the caller: all
+ *   points of a group MUST share their row list, have status 0, and count <= bi_mma_unit_points(n_terms);
+ *   header_dev[4] must be 0 on entry).  Requires n_terms <= BI_MMA_MAX_TERMS.
+ * Densities that leave [2^-126, 2^127) (zero, negative, NaN, inf ...) are re-evaluated with the
+ * reference's nansum / outlier semantics from wterm / term_source / mus (likelihood.py:686-689).
  */
-#define BI_MMA_MAX_TERMS 32
-int bi_unbinned_partials_mma(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
-                             int32_t n_sources, int32_t n_corners,
+#define BI_MMA_MAX_TERMS 128
+int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t n_events,
+                             int32_t n_terms, int32_t n_sources,
                              const int32_t* group_points_dev, const int32_t* groups_dev, int32_t* header_dev,
-                             const int32_t* corner_dev, const double* weight_dev, const double* mus_dev,
+                             const int32_t* row_dev, const double* coef_dev, const double* wterm_dev,
+                             const int32_t* term_source_dev, const double* mus_dev,
                              double outlier_likelihood, double* partial_dev, void* stream);
-int32_t bi_mma_unit_points(int32_t n_sources, int32_t n_corners);
+int32_t bi_mma_unit_points(int32_t n_terms);
 
 /*
  * The whole unbinned hot path in ONE call: K1 point set-up -> device-side schedule -> K2 (DMMA) ->
  * finalize.  Replaces LogLikelihoodBase.__call__'s numerics for a batch of P points
  * (likelihood.py:318-427 with UnbinnedLogLikelihood._compute_likelihood, :571-573).
- *   workspace_dev   bi_unbinned_workspace_bytes(n_dims, n_sources, n_points, n_events) bytes, 256-byte aligned
+ *   workspace_dev   bi_unbinned_workspace_bytes(n_dims, n_sources, n_terms, n_points, n_events) bytes,
+ *                   256-byte aligned; n_terms = 2^n_dims * n_sources for bi_unbinned_ll_batch
  *   logl_dev [P], logsum_dev [P] (may be NULL), musum_dev [P], status_dev [P]: outputs
  */
-int64_t bi_unbinned_workspace_bytes(int32_t n_dims, int32_t n_sources, int64_t n_points, int64_t n_events);
+int64_t bi_unbinned_workspace_bytes(int32_t n_dims, int32_t n_sources, int32_t n_terms, int64_t n_points,
+                                    int64_t n_events);
 /* byte offsets of the workspace regions: cell, frac, corner, weight, mus, partial, group_points, groups,
- * header, total (10 int64) -- lets a caller run / inspect the stages separately */
-int bi_unbinned_workspace_layout(int32_t n_dims, int32_t n_sources, int64_t n_points, int64_t n_events,
-                                 int64_t* offsets_host);
+ * header, row, coef, wterm, term_source, total (14 int64) -- lets a caller run / inspect the stages separately */
+int bi_unbinned_workspace_layout(int32_t n_dims, int32_t n_sources, int32_t n_terms, int64_t n_points,
+                                 int64_t n_events, int64_t* offsets_host);
 int bi_unbinned_ll_batch(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
                          int32_t n_sources, int64_t n_points,
                          const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,

@@ -15,8 +15,7 @@ groups = -(-points // 64)
 units = 148 * 12 * waves
 os.environ['BI_MMA_TARGET_UNITS'] = str(units)
 import torch                                     # noqa: E402
-from blueice_b200 import _cabi                   # noqa: E402
-from blueice_b200.engine import MorphGrid, UnbinnedEngine, _MMA_TARGET_UNITS   # noqa: E402
+from blueice_b200.engine import MorphGrid, UnbinnedEngine   # noqa: E402
 
 n_events = (units // groups) * sb_per_unit * 512
 axes = [np.linspace(-2, 2, 5), np.linspace(-2, 2, 5)]
@@ -30,23 +29,14 @@ zs_d, mult_d, _, _, _ = eng._upload_points(zs, mult, None, None)
 zs_d, mult_d = zs_d.clone(), mult_d.clone()
 outs = eng.run_fused(points, zs_d, mult_d, None, None)
 _, v = eng.mma_workspace(points)
-S, C = 2, 4
-up = int(eng.lib.bi_mma_unit_points(S, C))
 
 
 def plan_fn():
-    _cabi.check(eng.lib.bi_unbinned_plan(2, _cabi.host_ptr(eng.grid.n_anchors_i32), points, _cabi.dev_ptr(v["cell"]),
-                                         _cabi.dev_ptr(outs["status"]), up, n_events, _MMA_TARGET_UNITS,
-                                         _cabi.dev_ptr(v["group_points"]), _cabi.dev_ptr(v["groups"]),
-                                         _cabi.dev_ptr(v["header"]), eng._stream()), "plan")
+    eng.mma_plan(points, v, outs["status"])
 
 
 def k2_fn():
-    _cabi.check(eng.lib.bi_unbinned_partials_mma(_cabi.dev_ptr(eng.ps_anchor), eng.ld, n_events, S, C,
-                                                 _cabi.dev_ptr(v["group_points"]), _cabi.dev_ptr(v["groups"]),
-                                                 _cabi.dev_ptr(v["header"]), _cabi.dev_ptr(v["corner"]),
-                                                 _cabi.dev_ptr(v["weight"]), _cabi.dev_ptr(v["mus"]), 1e-12,
-                                                 _cabi.dev_ptr(v["partial"]), eng._stream()), "k2")
+    eng.mma_k2(v)
 
 
 ms = []

@@ -62,13 +62,13 @@ def test_argument_validation_reports_errors_without_a_gpu():
     n_anchors = _cabi.as_i32([3] * 7)
     axes = _cabi.as_f64(np.zeros(21))
     rc = lib.bi_point_setup(7, _cabi.host_ptr(n_anchors), _cabi.host_ptr(axes), 1, 1, None, None, None, None, None,
-                            None, None, None, None, None, None, None, None, None)
+                            None, None, None, None, None, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"n_dims" in lib.bi_last_error()
     # non-increasing anchor axis
     n_anchors = _cabi.as_i32([3])
     axes = _cabi.as_f64([0., 2., 1.])
     rc = lib.bi_point_setup(1, _cabi.host_ptr(n_anchors), _cabi.host_ptr(axes), 1, 1, None, None, None, None, None,
-                            None, None, None, None, None, None, None, None, None)
+                            None, None, None, None, None, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"increasing" in lib.bi_last_error()
     # odd leading dimension of the anchor tensor
     rc = lib.bi_unbinned_partials_stream(ctypes.c_void_p(16), 7, 7, 1, 1, None, 1, None, None, None, None, 1e-12,

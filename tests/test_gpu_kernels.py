@@ -183,7 +183,7 @@ def test_grouped_is_bitwise_identical_to_stream_and_matches_oracle(d, s, n):
         res[mode] = eng.evaluate(zs, mult)
     assert np.array_equal(res['stream'], res['grouped'], equal_nan=True)
     plan = eng.plan(zs)
-    if (2 ** d) * s <= 32:
+    if (2 ** d) * s <= 128:
         assert plan.kernel == 'mma'                   # auto mode really exercised the DMMA kernel
         assert_logl_close(res[None], res['stream'], n, "mma vs vector kernels")
     else:
