@@ -1,8 +1,1 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -6
-python bench.py --steps 10 --warmup 3 --skip-cpu 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('value %.3e ms/step %.3f e2e %.3f k2 %.4f frac %.3f stream %.0f GB/s'%(d['value'],d['ms_per_step'],d['e2e']['ms_per_step'],d['roofline']['ms'],d['roofline']['frac'],d['roofline_stream']['achieved']), d['plan'])
-    elif 'rror' in l or 'Trace' in l: print(l[:300])
-"
+python -m pytest tests -x -q -m gpu -k "sourcewise or source_wise" 2>&1 | tail -30

@@ -44,6 +44,17 @@ SIGNATURES = {
                                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                             _c_void_p, _i64, _i64, _f64, _i32, _c_void_p, _i64,
                                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "bi_sourcewise_terms": (_i32, [_i32, _c_void_p]),
+    "bi_point_setup_sourcewise": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _c_void_p, _c_void_p, _i64,
+                                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "bi_unbinned_ll_batch_sourcewise": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _c_void_p, _c_void_p, _i64,
+                                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                                       _c_void_p, _c_void_p, _i64, _i64, _f64, _i32, _c_void_p, _i64,
+                                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "bi_unbinned_ps_terms": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p, _c_void_p,
+                                            _c_void_p, _c_void_p, _i64, _c_void_p]),
     "bi_unbinned_finalize": (ctypes.c_int, [_c_void_p, _i64, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
                                             _c_void_p]),
     "bi_unbinned_ps": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p, _c_void_p,

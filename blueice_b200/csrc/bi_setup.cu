@@ -193,3 +193,144 @@ extern "C" int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, con
     BI_LAUNCH_CHECK();
     return BI_OK;
 }
+
+// =============================================================================================
+// Source-wise interpolation (likelihood.py:113-145,152-169,210-240,534-555): every source is morphed
+// over its own sub-grid -- the shape parameters it does not ignore -- by its own RegularGridInterpolator.
+// The contraction terms of a point are (source s, corner c_s of that source's sub-grid), s-major.
+// =============================================================================================
+struct BiSourcewise {
+    uint32_t mask[BI_MAX_SOURCES];        // bit d: source uses shape parameter d
+    int32_t row_base[BI_MAX_SOURCES];     // first row (sub-anchor 0) of the source in the row matrix / mus_rows
+    int32_t term_base[BI_MAX_SOURCES + 1];
+};
+
+__global__ void __launch_bounds__(128)
+k_point_setup_sw(const __grid_constant__ BiGrid grid, const __grid_constant__ BiSourcewise sw, int n_sources,
+                 int64_t n_points, const double* __restrict__ zs, const double* __restrict__ rate_mult,
+                 const double* __restrict__ scale, const double* __restrict__ eff,
+                 const double* __restrict__ mus_rows, const __grid_constant__ BiAllowNegative allow,
+                 int32_t* __restrict__ cell_out, double* __restrict__ frac_out, double* __restrict__ mus_out,
+                 double* __restrict__ musum_out, int32_t* __restrict__ status_out, int32_t* __restrict__ row_out,
+                 double* __restrict__ coef_out, double* __restrict__ wterm_out, int32_t* __restrict__ term_source_out) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int D = grid.n_dims, S = n_sources;
+    const int K = sw.term_base[S];
+    if (p == 0)
+        for (int s = 0; s < S; ++s)
+            for (int k = sw.term_base[s]; k < sw.term_base[s + 1]; ++k) term_source_out[k] = s;
+    if (p >= n_points) return;
+    int status = BI_POINT_OK;
+    int cell[BI_MAX_DIMS];
+    double frac[BI_MAX_DIMS];
+    for (int d = 0; d < D; ++d) {
+        const double* axis = grid.axes + grid.axis_offset[d];
+        const int n = grid.n_anchors[d];
+        const double z = zs[p * D + d];
+        if (!(axis[0] <= z && z <= axis[n - 1])) status |= BI_POINT_OUT_OF_RANGE;     // likelihood.py:345-346
+        bi_find_cell(axis, n, z, &cell[d], &frac[d]);
+        cell_out[p * D + d] = cell[d];
+        frac_out[p * D + d] = frac[d];
+    }
+    double mu_local[BI_MAX_SOURCES];
+    for (int s = 0; s < S; ++s) {
+        const uint32_t mask = sw.mask[s];
+        int dims[BI_MAX_DIMS], stride[BI_MAX_DIMS], nd = 0;
+        for (int d = 0; d < D; ++d)
+            if ((mask >> d) & 1u) dims[nd++] = d;
+        int st = 1;
+        for (int j = nd - 1; j >= 0; --j) { stride[j] = st; st *= grid.n_anchors[dims[j]]; }   // C order over the sub-grid
+        const int Cs = 1 << nd;
+        double acc = 0.0;
+        for (int c = 0; c < Cs; ++c) {
+            double w = 1.0;
+            int flat = 0;
+            for (int j = 0; j < nd; ++j) {
+                const int d = dims[j];
+                const int bit = (c >> (nd - 1 - j)) & 1;
+                const double t = bit ? frac[d] : __dsub_rn(1.0, frac[d]);
+                w = __dmul_rn(w, t);
+                int idx = cell[d] + bit;
+                if (idx < 0) idx += grid.n_anchors[d];
+                flat += idx * stride[j];
+            }
+            const int r = sw.row_base[s] + flat;
+            const int64_t k = p * K + sw.term_base[s] + c;
+            row_out[k] = r;
+            wterm_out[k] = w;
+            // mus: RegularGridInterpolator value = value + M * w  (a source without shape parameters keeps its base value)
+            acc = nd ? __dadd_rn(acc, __dmul_rn(mus_rows[r], w)) : mus_rows[r];
+        }
+        acc = __dmul_rn(acc, rate_mult[p * S + s]);
+        if (scale) acc = __dmul_rn(acc, scale[p]);
+        if (eff) acc = __dmul_rn(acc, eff[p * S + s]);
+        mu_local[s] = acc;
+        mus_out[p * S + s] = acc;
+        for (int c = 0; c < Cs; ++c) {
+            const int64_t k = p * K + sw.term_base[s] + c;
+            coef_out[k] = __dmul_rn(wterm_out[k], acc);
+        }
+    }
+    const double musum = bi_numpy_sum_small(mu_local, S);
+    musum_out[p] = musum;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    bool bad = false;
+    if (!allow.any) {
+        for (int s = 0; s < S; ++s) bad |= !((mu_local[s] >= 0.0) && (mu_local[s] < inf));
+    } else {
+        bool any_finite = false;
+        for (int s = 0; s < S; ++s) any_finite |= (mu_local[s] < inf);
+        if (!any_finite || (musum < 0.0)) bad = true;
+        for (int s = 0; s < S; ++s)
+            if (!(0.0 <= mu_local[s]) && !allow.flag[s]) bad = true;
+    }
+    if (bad) status |= BI_POINT_UNPHYSICAL;
+    status_out[p] = status;
+}
+
+extern "C" int32_t bi_sourcewise_terms(int32_t n_sources, const uint32_t* dim_mask_host) {
+    if (n_sources < 1 || n_sources > BI_MAX_SOURCES || !dim_mask_host) return -1;
+    int32_t k = 0;
+    for (int s = 0; s < n_sources; ++s) k += 1 << __builtin_popcount(dim_mask_host[s]);
+    return k;
+}
+
+extern "C" int bi_point_setup_sourcewise(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                                         int32_t n_sources, const uint32_t* dim_mask_host,
+                                         const int32_t* row_base_host, int64_t n_points,
+                                         const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                                         const double* eff_dev, const double* mus_rows_dev,
+                                         const uint8_t* allow_negative_host,
+                                         int32_t* cell_dev, double* frac_dev, double* mus_dev, double* musum_dev,
+                                         int32_t* status_dev, int32_t* row_dev, double* coef_dev, double* wterm_dev,
+                                         int32_t* term_source_dev, void* stream) {
+    BiGrid grid;
+    int rc = bi_fill_grid(&grid, n_dims, n_anchors_host, axes_host);
+    if (rc != BI_OK) return rc;
+    BI_REQUIRE(n_sources >= 1 && n_sources <= BI_MAX_SOURCES, "n_sources=%d outside [1,%d]", n_sources, BI_MAX_SOURCES);
+    BI_REQUIRE(dim_mask_host && row_base_host, "bi_point_setup_sourcewise: NULL descriptor");
+    BI_REQUIRE(n_points >= 0, "n_points < 0");
+    BiSourcewise sw;
+    memset(&sw, 0, sizeof(sw));
+    for (int s = 0; s < n_sources; ++s) {
+        BI_REQUIRE((dim_mask_host[s] >> n_dims) == 0, "source %d uses a shape parameter >= n_dims", s);
+        sw.mask[s] = dim_mask_host[s];
+        sw.row_base[s] = row_base_host[s];
+        sw.term_base[s + 1] = sw.term_base[s] + (1 << __builtin_popcount(dim_mask_host[s]));
+    }
+    if (n_points == 0) return BI_OK;
+    BI_REQUIRE(rate_mult_dev && mus_rows_dev && mus_dev && musum_dev && status_dev && row_dev && coef_dev && wterm_dev &&
+                   term_source_dev, "bi_point_setup_sourcewise: NULL device pointer");
+    BI_REQUIRE(n_dims == 0 || (zs_dev && cell_dev && frac_dev), "bi_point_setup_sourcewise: NULL zs/cell/frac pointer");
+    BiAllowNegative allow;
+    memset(&allow, 0, sizeof(allow));
+    if (allow_negative_host)
+        for (int s = 0; s < n_sources; ++s) { allow.flag[s] = allow_negative_host[s] ? 1 : 0; allow.any |= allow.flag[s]; }
+    const int threads = 128;
+    const int64_t blocks = (n_points + threads - 1) / threads;
+    k_point_setup_sw<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        grid, sw, n_sources, n_points, zs_dev, rate_mult_dev, scale_dev, eff_dev, mus_rows_dev, allow, cell_dev, frac_dev,
+        mus_dev, musum_dev, status_dev, row_dev, coef_dev, wterm_dev, term_source_dev);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}

@@ -149,3 +149,75 @@ extern "C" int bi_unbinned_ll_batch(int32_t n_dims, const int32_t* n_anchors_hos
                                    outlier_likelihood, target_units, base, w, logl_dev, logsum_dev, musum_dev,
                                    status_dev, stream);
 }
+
+extern "C" int bi_unbinned_ll_batch_sourcewise(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                                               int32_t n_sources, const uint32_t* dim_mask_host,
+                                               const int32_t* row_base_host, int64_t n_points,
+                                               const double* zs_dev, const double* rate_mult_dev,
+                                               const double* scale_dev, const double* eff_dev,
+                                               const double* mus_rows_dev, const uint8_t* allow_negative_host,
+                                               const double* rows_dev, int64_t ld_events, int64_t n_events,
+                                               double outlier_likelihood, int32_t target_units,
+                                               void* workspace_dev, int64_t workspace_bytes,
+                                               double* logl_dev, double* logsum_dev, double* musum_dev,
+                                               int32_t* status_dev, void* stream) {
+    BI_REQUIRE(n_points >= 0 && n_events >= 0, "negative size");
+    if (n_points == 0) return BI_OK;
+    BI_REQUIRE(n_dims >= 0 && n_dims <= BI_MAX_DIMS, "n_dims=%d outside [0,%d]", n_dims, BI_MAX_DIMS);
+    const int32_t K = bi_sourcewise_terms(n_sources, dim_mask_host);
+    BI_REQUIRE(K >= 1, "bi_unbinned_ll_batch_sourcewise: bad source descriptors");
+    const BiUnbinnedWorkspace w = bi_unbinned_layout(n_dims, n_sources, K, n_points, n_events);
+    BI_REQUIRE(workspace_dev && workspace_bytes >= w.total, "workspace too small: %lld < %lld bytes",
+               (long long)workspace_bytes, (long long)w.total);
+    BI_REQUIRE(((uintptr_t)workspace_dev & 255) == 0, "workspace_dev must be 256-byte aligned");
+    BI_REQUIRE(logl_dev && musum_dev && status_dev, "bi_unbinned_ll_batch_sourcewise: NULL output pointer");
+    char* base = (char*)workspace_dev;
+    int rc = bi_point_setup_sourcewise(n_dims, n_anchors_host, axes_host, n_sources, dim_mask_host, row_base_host,
+                                       n_points, zs_dev, rate_mult_dev, scale_dev, eff_dev, mus_rows_dev,
+                                       allow_negative_host, (int32_t*)(base + w.cell), (double*)(base + w.frac),
+                                       (double*)(base + w.mus), musum_dev, status_dev, (int32_t*)(base + w.row),
+                                       (double*)(base + w.coef), (double*)(base + w.wterm),
+                                       (int32_t*)(base + w.term_source), stream);
+    if (rc != BI_OK) return rc;
+    return bi_unbinned_after_setup(n_dims, n_anchors_host, n_sources, K, n_points, rows_dev, ld_events, n_events,
+                                   outlier_likelihood, target_units, base, w, logl_dev, logsum_dev, musum_dev,
+                                   status_dev, stream);
+}
+
+// ps[S, N] of ONE point from its contraction terms, reference operation order per source:
+// value = 0; value = value + V * w over the source's corners; a source with a single term of weight
+// exactly 1 from a 0-dimensional sub-grid is copied (likelihood.py:543-544).
+__global__ void __launch_bounds__(256)
+k_unbinned_ps_terms(const double* __restrict__ rows, int64_t ld, int64_t N, int K, int S,
+                    const int32_t* __restrict__ row, const double* __restrict__ wterm,
+                    const int32_t* __restrict__ term_source, const uint8_t* __restrict__ copy_source,
+                    double* __restrict__ out, int64_t ld_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    for (int s = 0; s < S; ++s) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) {
+            if (term_source[k] != s) continue;
+            const double v = rows[(int64_t)row[k] * ld + i];
+            acc = copy_source[s] ? v : __dadd_rn(acc, __dmul_rn(v, wterm[k]));
+        }
+        out[(int64_t)s * ld_out + i] = acc;
+    }
+}
+
+extern "C" int bi_unbinned_ps_terms(const double* rows_dev, int64_t ld_events, int64_t n_events, int32_t n_terms,
+                                    int32_t n_sources, const int32_t* row_dev, const double* wterm_dev,
+                                    const int32_t* term_source_dev, const uint8_t* copy_source_dev,
+                                    double* ps_out_dev, int64_t ld_out, void* stream) {
+    BI_REQUIRE(n_events >= 0 && n_terms >= 1 && n_sources >= 1, "bi_unbinned_ps_terms: bad sizes");
+    if (n_events == 0) return BI_OK;
+    BI_REQUIRE(rows_dev && row_dev && wterm_dev && term_source_dev && copy_source_dev && ps_out_dev && ld_out >= n_events,
+               "bi_unbinned_ps_terms: bad arguments");
+    const int64_t blocks = (n_events + 255) / 256;
+    k_unbinned_ps_terms<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows_dev, ld_events, n_events, n_terms,
+                                                                            n_sources, row_dev, wterm_dev,
+                                                                            term_source_dev, copy_source_dev,
+                                                                            ps_out_dev, ld_out);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}

@@ -304,6 +304,9 @@ class UnbinnedEngine(_EngineBase):
         v = self.torch.from_numpy(np.ascontiguousarray(np.asarray(values_host, dtype=np.float64)))
         self.ps_anchor[anchor_index, source_index, :self.n_events].copy_(v)
 
+    def _flat_row(self, anchor_index, source_index):
+        return anchor_index * self.n_sources + source_index
+
     def lookup_rows(self, rows, templates_host, edges_list, coords_dev, method):
         """K3: fill ps_anchor rows [(anchor, source), ...] from histogram templates that share edges.
 
@@ -321,8 +324,8 @@ class UnbinnedEngine(_EngineBase):
                                      self.n_events, method, _cabi.dev_ptr(out), self.ld, None, self._stream())
         _cabi.check(rc, "bi_hist_lookup")
         self.launches += 1
-        idx = torch.as_tensor([a * self.n_sources + s for a, s in rows], device=self.device, dtype=torch.int64)
-        flat = self.ps_anchor.view(self.grid.n_anchors * self.n_sources, self.ld)
+        idx = torch.as_tensor([self._flat_row(a, s) for a, s in rows], device=self.device, dtype=torch.int64)
+        flat = self.ps_anchor.view(-1, self.ld)
         if self.ld > self.n_events:
             out[:, self.n_events:] = 0.0
         flat.index_copy_(0, idx, out)
@@ -511,6 +514,141 @@ class UnbinnedEngine(_EngineBase):
         _cabi.check(rc, "bi_unbinned_ps")
         self.launches += 1
         return o["mus"].cpu().numpy().copy(), out[:, :self.n_events].cpu().numpy()
+
+
+class SourcewiseUnbinnedEngine(UnbinnedEngine):
+    """Unbinned likelihood with source-wise interpolation (likelihood.py:113-145,210-240,534-555): source s is
+    morphed over its own sub-grid (the shape parameters in source_dims[s]), so the row matrix holds
+    sum_s G_s rows instead of G * S and a point-event costs sum_s 2^D_s contraction terms instead of 2^D * S.
+
+    grid: the FULL shape-parameter grid (bounds test, cell bucketing); source_dims[s]: sorted indices of the
+    shape parameters source s depends on; mus_rows: expected events per (source, sub-anchor), sources
+    concatenated, each source's sub-anchors in C order."""
+
+    def __init__(self, grid, source_dims, mus_rows, outlier_likelihood=1e-12, allow_negative=None, device=None):
+        self.source_dims = [tuple(int(d) for d in dims) for dims in source_dims]
+        n_sources = len(self.source_dims)
+        self.sub_shapes = [tuple(grid.shape[d] for d in dims) for dims in self.source_dims]
+        n_rows_per_source = [int(np.prod(sh)) if len(sh) else 1 for sh in self.sub_shapes]
+        self.row_base = _cabi.as_i32(np.concatenate([[0], np.cumsum(n_rows_per_source)[:-1]]))
+        self.n_rows = int(np.sum(n_rows_per_source))
+        self.dim_mask = np.ascontiguousarray(
+            np.array([sum(1 << d for d in dims) for dims in self.source_dims], dtype=np.uint32))
+        mus_rows = np.ascontiguousarray(np.asarray(mus_rows, dtype=np.float64).reshape(-1))
+        if len(mus_rows) != self.n_rows:
+            raise ValueError("mus_rows must hold %d values" % self.n_rows)
+        # the base class wants a [G, S] table; it is not used by the source-wise K1
+        super().__init__(grid, np.zeros((grid.n_anchors, n_sources)), outlier_likelihood, allow_negative, device)
+        self.mus_rows_host = mus_rows
+        self.mus_rows = self.torch.from_numpy(mus_rows).to(self.device)
+        self.copy_source = self.torch.from_numpy(
+            np.array([len(d) == 0 for d in self.source_dims], dtype=np.uint8)).to(self.device)
+        self._n_terms = int(self.lib.bi_sourcewise_terms(n_sources, _cabi.host_ptr(self.dim_mask)))
+
+    @property
+    def n_terms(self):
+        return self._n_terms
+
+    def allocate_ps_anchor(self, n_events):
+        torch = self.torch
+        self.n_events = int(n_events)
+        self.ld = max(round_up(self.n_events, _LD_ALIGN), _LD_ALIGN)
+        self.ps_anchor = torch.zeros((self.n_rows, self.ld), dtype=torch.float64, device=self.device)
+        self.n_super = int(self.lib.bi_num_superblocks(self.n_events))
+        return self.ps_anchor
+
+    def set_ps_anchor(self, rows_host):
+        """rows_host: [n_rows, N] per-event pdf values, sources concatenated (see class docstring)."""
+        rows = np.ascontiguousarray(np.asarray(rows_host, dtype=np.float64)).reshape(self.n_rows, -1)
+        self.allocate_ps_anchor(rows.shape[1])
+        if rows.shape[1]:
+            self.ps_anchor[:, :rows.shape[1]].copy_(self.torch.from_numpy(rows))
+        return self
+
+    def set_rows(self, row_index, source_index, values_host):
+        """Upload one [N] row; row_index is the absolute row (row_base[source] + sub-anchor)."""
+        v = self.torch.from_numpy(np.ascontiguousarray(np.asarray(values_host, dtype=np.float64)))
+        self.ps_anchor[row_index, :self.n_events].copy_(v)
+
+    def _flat_row(self, anchor_index, source_index):
+        return anchor_index          # callers pass the absolute row (row_base[source] + sub-anchor) as "anchor"
+
+    def uses_mma(self):
+        if self.n_terms > _cabi.MMA_MAX_TERMS:
+            raise NotImplementedError("source-wise interpolation supports at most %d contraction terms "
+                                      "(sum over sources of 2^(shape parameters of the source)); got %d"
+                                      % (_cabi.MMA_MAX_TERMS, self.n_terms))
+        return True
+
+    def _sw_setup(self, P, zs_d, mult_d, scale_d, eff_d, views, outs):
+        rc = self.lib.bi_point_setup_sourcewise(
+            self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat),
+            self.n_sources, _cabi.host_ptr(self.dim_mask), _cabi.host_ptr(self.row_base), P,
+            _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
+            _cabi.dev_ptr(self.mus_rows), _cabi.host_ptr(self.allow_negative),
+            _cabi.dev_ptr(views["cell"]), _cabi.dev_ptr(views["frac"]), _cabi.dev_ptr(views["mus"]),
+            _cabi.dev_ptr(outs["musum"]), _cabi.dev_ptr(outs["status"]), _cabi.dev_ptr(views["row"]),
+            _cabi.dev_ptr(views["coef"]), _cabi.dev_ptr(views["wterm"]), _cabi.dev_ptr(views["term_source"]),
+            self._stream())
+        _cabi.check(rc, "bi_point_setup_sourcewise")
+        self.launches += 1
+
+    def run_fused(self, P, zs_d, mult_d, scale_d, eff_d):
+        torch = self.torch
+        ws, _ = self.mma_workspace(P)
+        out = dict(logl=self.ws.get("logl", P, torch.float64), logsum=self.ws.get("logsum", P, torch.float64),
+                   musum=self.ws.get("musum", P, torch.float64), status=self.ws.get("status", P, torch.int32))
+        rc = self.lib.bi_unbinned_ll_batch_sourcewise(
+            self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat),
+            self.n_sources, _cabi.host_ptr(self.dim_mask), _cabi.host_ptr(self.row_base), P,
+            _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
+            _cabi.dev_ptr(self.mus_rows), _cabi.host_ptr(self.allow_negative),
+            _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, self.outlier_likelihood, _MMA_TARGET_UNITS,
+            _cabi.dev_ptr(ws), ws.numel(), _cabi.dev_ptr(out["logl"]), _cabi.dev_ptr(out["logsum"]),
+            _cabi.dev_ptr(out["musum"]), _cabi.dev_ptr(out["status"]), self._stream())
+        _cabi.check(rc, "bi_unbinned_ll_batch_sourcewise")
+        self.launches += 4 if self.n_super > 0 else 2
+        return out
+
+    def _setup_views(self, zs, mult, scale, eff):
+        torch = self.torch
+        P = len(mult)
+        zs_d, mult_d, scale_d, eff_d, _ = self._upload_points(zs, mult, scale, eff)
+        _, views = self.mma_workspace(P)
+        outs = dict(musum=self.ws.get("musum", P, torch.float64), status=self.ws.get("status", P, torch.int32))
+        self._sw_setup(P, zs_d, mult_d, scale_d, eff_d, views, outs)
+        return views, outs
+
+    def point_setup_host(self, zs, mult, scale=None, eff=None):
+        P = len(mult)
+        D, S, K = self.grid.n_dims, self.n_sources, self.n_terms
+        views, outs = self._setup_views(np.asarray(zs, dtype=np.float64).reshape(P, D), mult, scale, eff)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return dict(cell=views["cell"][:P * max(D, 1)].cpu().numpy().reshape(P, max(D, 1))[:, :D],
+                    frac=views["frac"][:P * max(D, 1)].cpu().numpy().reshape(P, max(D, 1))[:, :D],
+                    row=views["row"][:P * K].cpu().numpy().reshape(P, K),
+                    wterm=views["wterm"][:P * K].cpu().numpy().reshape(P, K),
+                    coef=views["coef"][:P * K].cpu().numpy().reshape(P, K),
+                    term_source=views["term_source"][:K].cpu().numpy(),
+                    mus=views["mus"][:P * S].cpu().numpy().reshape(P, S),
+                    musum=outs["musum"].cpu().numpy(), status=outs["status"].cpu().numpy())
+
+    def ps(self, z_row, mult_row, scale=None, eff=None):
+        """(mus [S], ps [S, N]) for one point in the reference's operation order (full_output=True)."""
+        torch = self.torch
+        S = self.n_sources
+        views, _ = self._setup_views(np.asarray(z_row, dtype=np.float64).reshape(1, -1),
+                                     np.asarray(mult_row, dtype=np.float64).reshape(1, -1),
+                                     None if scale is None else [scale],
+                                     None if eff is None else np.asarray(eff).reshape(1, -1))
+        out = torch.empty((S, max(self.n_events, 1)), dtype=torch.float64, device=self.device)
+        rc = self.lib.bi_unbinned_ps_terms(_cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, self.n_terms, S,
+                                           _cabi.dev_ptr(views["row"]), _cabi.dev_ptr(views["wterm"]),
+                                           _cabi.dev_ptr(views["term_source"]), _cabi.dev_ptr(self.copy_source),
+                                           _cabi.dev_ptr(out), out.shape[1], self._stream())
+        _cabi.check(rc, "bi_unbinned_ps_terms")
+        self.launches += 1
+        return views["mus"][:S].cpu().numpy().copy(), out[:, :self.n_events].cpu().numpy()
 
 
 class BinnedEngine(_EngineBase):

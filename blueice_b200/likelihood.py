@@ -24,7 +24,7 @@ from scipy import stats
 
 from . import _cabi
 from . import inference
-from .engine import BinnedEngine, MorphGrid, UnbinnedEngine
+from .engine import BinnedEngine, MorphGrid, SourcewiseUnbinnedEngine, UnbinnedEngine
 from .exceptions import InvalidParameter, InvalidParameterSpecification, NotPreparedException
 from .hist import Histdd
 from .model import Model
@@ -228,9 +228,81 @@ class LogLikelihoodBase(object):
         self.is_data_set = False
         self.is_prepared = True
 
+    # -- source-wise interpolation (likelihood.py:113-145,152-169,210-240) ---------------------------
+    @property
+    def source_shape_parameters(self):
+        """source name -> OrderedDict of the shape parameters that source depends on (likelihood.py:113-131)."""
+        result = OrderedDict()
+        for sn, source, apply_eff, eff_name in zip(self.source_name_list, self.base_model.sources,
+                                                   self.source_apply_efficiency, self.source_efficiency_names):
+            ignore = set(source.config['dont_hash_settings'])
+            if apply_eff:
+                ignore.discard(eff_name)      # not hashed, but it must reach the morpher
+            own = OrderedDict((k, v) for k, v in self.shape_parameters.items() if k not in ignore)
+            if own:
+                result[sn] = own
+        return result
+
+    def _get_shape_indices(self, source_name):
+        """Indices (into self.shape_parameters) of the shape parameters used by the source."""
+        keys = self.source_shape_parameters[source_name].keys()
+        return [i for i, k in enumerate(self.shape_parameters.keys()) if k in keys]
+
+    def _get_model_anchor(self, anchor, source_name):
+        """Anchor of the full model for a source's own anchor; unused parameters are None."""
+        model_anchor = [None] * len(self.shape_parameters)
+        for i, idx in enumerate(self._get_shape_indices(source_name)):
+            model_anchor[idx] = anchor[i]
+        return tuple(model_anchor)
+
     def _prepare_source_wise(self):
-        raise NotImplementedError("source_wise_interpolation is not implemented yet in blueice_b200 "
-                                  "(SURVEY.md section 8f, row f1)")
+        """One morpher per source over the parameters it depends on; models only at the union of the
+        sources' anchors (likelihood.py:152-169,210-240).  The full grid is kept for the bounds test and
+        for bucketing points; the device tables are per (source, sub-anchor) rows."""
+        ssp = self.source_shape_parameters
+        self.source_morphers = OrderedDict(
+            (sn, MORPHERS[self.config['morpher']](self.config.get('morpher_config', {}), sp)) for sn, sp in ssp.items())
+        zs_list = []
+        for sn, morpher in self.source_morphers.items():
+            for anchor in morpher.get_anchor_points(bounds=None):
+                zs = self._get_model_anchor(anchor, sn)
+                if zs not in zs_list:
+                    zs_list.append(zs)
+        models = []
+        for zs in zs_list:
+            config = deepcopy(self.pdf_base_config)
+            for i, (setting_name, (anchors, _, _)) in enumerate(self.shape_parameters.items()):
+                if zs[i] is not None:
+                    config[setting_name] = anchors[zs[i]]
+            models.append(Model(config))
+        self.anchor_sources = OrderedDict()
+        for sn, morpher in self.source_morphers.items():
+            source_index = self.source_name_list.index(sn)
+            self.anchor_sources[sn] = OrderedDict()
+            for anchor in morpher.get_anchor_points(bounds=None):
+                model = models[zs_list.index(self._get_model_anchor(anchor, sn))]
+                self.anchor_sources[sn][anchor] = model.sources[source_index]
+        full = MORPHERS[self.config['morpher']](self.config.get('morpher_config', {}), self.shape_parameters)
+        self._grid = MorphGrid(full.anchor_z_arrays)
+        self._sw_source_dims = [self._get_shape_indices(sn) if sn in ssp else [] for sn in self.source_name_list]
+        self._sw_row_sources = []             # (source index, Source) per row, sources concatenated, C order
+        for s, (sn, base_source) in enumerate(zip(self.source_name_list, self.base_model.sources)):
+            if sn in self.source_morphers:
+                for anchor in self.source_morphers[sn].get_anchor_points(bounds=None):
+                    self._sw_row_sources.append((s, self.anchor_sources[sn][anchor]))
+            else:
+                self._sw_row_sources.append((s, base_source))
+        self._sw_mus_rows = np.array([src.expected_events for _, src in self._sw_row_sources], dtype=np.float64)
+        self._mus_anchor = None
+
+        def mus_interpolator(zs):
+            from .engine import SourcewiseUnbinnedEngine
+            engine = SourcewiseUnbinnedEngine(self._grid, self._sw_source_dims, self._sw_mus_rows,
+                                              allow_negative=self.source_allowed_negative)
+            engine.allocate_ps_anchor(0)
+            z = np.asarray(zs, dtype=np.float64).reshape(1, -1)
+            return engine.point_setup_host(z, np.ones((1, len(self.source_name_list))))["mus"][0]
+        self.mus_interpolator = mus_interpolator
 
     @_needs_preparation
     def set_data(self, d):
@@ -441,13 +513,19 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
     def set_data(self, d):
         LogLikelihoodBase.set_data(self, d)
         outlier = self.config.get('outlier_likelihood', 1e-12)
-        engine = UnbinnedEngine(self._grid, self._mus_anchor.reshape(self._grid.n_anchors, -1),
-                                outlier_likelihood=outlier, allow_negative=self.source_allowed_negative)
-        if len(self.shape_parameters):
-            models = [self.anchor_models[tuple(zs)] for _, zs in self.morpher._anchor_grid_iterator()]
+        if len(self.shape_parameters) and self.source_wise_interpolation:
+            engine = SourcewiseUnbinnedEngine(self._grid, self._sw_source_dims, self._sw_mus_rows,
+                                              outlier_likelihood=outlier, allow_negative=self.source_allowed_negative)
+            items = [(row, s, source) for row, (s, source) in enumerate(self._sw_row_sources)]
         else:
-            models = [self.base_model]
-        self._fill_anchor_rows(engine, models, d)
+            engine = UnbinnedEngine(self._grid, self._mus_anchor.reshape(self._grid.n_anchors, -1),
+                                    outlier_likelihood=outlier, allow_negative=self.source_allowed_negative)
+            if len(self.shape_parameters):
+                models = [self.anchor_models[tuple(zs)] for _, zs in self.morpher._anchor_grid_iterator()]
+            else:
+                models = [self.base_model]
+            items = [(g, s, source) for g, model in enumerate(models) for s, source in enumerate(model.sources)]
+        self._fill_anchor_rows(engine, items, d)
         self._engine = engine
         if len(self.shape_parameters):
             self.ps_interpolator = lambda zs: engine.ps(np.asarray(zs, dtype=np.float64),
@@ -455,30 +533,30 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
         else:
             self.ps = engine.ps(np.zeros(0), np.ones(engine.n_sources))[1]
 
-    def _fill_anchor_rows(self, engine, models, d):
-        """Build the per-event pdf tensor [G, S, N] in HBM (likelihood.py:557-562 -> model.py:97-99).
+    def _fill_anchor_rows(self, engine, items, d):
+        """Build the per-event pdf rows in HBM (likelihood.py:557-562 -> model.py:97-99; source-wise :534-549).
 
-        Histogram-backed sources that share bin edges and lookup method are evaluated for ALL anchors
+        items: (anchor index, source index, Source) per row to fill (source-wise: anchor index = absolute row).
+        Histogram-backed sources that share bin edges and lookup method are evaluated for ALL their rows
         with one gather kernel (K3); any other Source.pdf is called on the host and its row uploaded."""
         torch = engine.torch
-        coords = [np.asarray(c, dtype=np.float64) for c in self.base_model.to_analysis_dimensions(d)]
+        dims = self.base_model.to_analysis_dimensions(d)
+        coords = [np.asarray(c, dtype=np.float64) for c in dims]
         n = len(coords[0]) if len(coords) else len(d)
         engine.allocate_ps_anchor(n)
         if n == 0:
             return
         groups = OrderedDict()          # (edges bytes, method) -> [(anchor, source, histogram)]
-        for g, model in enumerate(models):
-            dims = model.to_analysis_dimensions(d)
-            for s, source in enumerate(model.sources):
-                on_device = (isinstance(source, HistogramPdfSource)
-                             and type(source).pdf is HistogramPdfSource.pdf
-                             and len(dims) <= _cabi.MAX_SPACE_DIMS)
-                if on_device:
-                    hist, edges, method = source.template()
-                    key = (tuple(np.asarray(e, dtype=np.float64).tobytes() for e in edges), method)
-                    groups.setdefault(key, (edges, method, []))[2].append((g, s, hist))
-                else:
-                    engine.set_rows(g, s, source.pdf(*dims))
+        for g, s, source in items:
+            on_device = (isinstance(source, HistogramPdfSource)
+                         and type(source).pdf is HistogramPdfSource.pdf
+                         and len(dims) <= _cabi.MAX_SPACE_DIMS)
+            if on_device:
+                hist, edges, method = source.template()
+                key = (tuple(np.asarray(e, dtype=np.float64).tobytes() for e in edges), method)
+                groups.setdefault(key, (edges, method, []))[2].append((g, s, hist))
+            else:
+                engine.set_rows(g, s, source.pdf(*dims))
         if groups:
             host = np.ascontiguousarray(np.asarray(coords, dtype=np.float64))
             if np.isnan(host).any() and any(m == 'linear' for _, m, _ in groups.values()):

@@ -108,6 +108,23 @@ int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, const double* 
                    int32_t* row_dev, double* coef_dev, double* wterm_dev, int32_t* term_source_dev, void* stream);
 
 /*
+ * K1, source-wise form (likelihood.py:113-145,210-240: `source_wise_interpolation`): source s is morphed
+ * over its own sub-grid spanned by the shape parameters in dim_mask_host[s] (bit d = parameter d), C order,
+ * by its own RegularGridInterpolator.  Rows of the row matrix / mus_rows_dev: row_base_host[s] + flat
+ * sub-anchor index.  Contraction terms: (source s, corner c_s), s-major; K = bi_sourcewise_terms(...).
+ * Outputs as bi_point_setup (no corner / weight: the per-term weights are wterm_dev).
+ */
+int32_t bi_sourcewise_terms(int32_t n_sources, const uint32_t* dim_mask_host);
+int bi_point_setup_sourcewise(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                              int32_t n_sources, const uint32_t* dim_mask_host, const int32_t* row_base_host,
+                              int64_t n_points,
+                              const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                              const double* eff_dev, const double* mus_rows_dev, const uint8_t* allow_negative_host,
+                              int32_t* cell_dev, double* frac_dev, double* mus_dev, double* musum_dev,
+                              int32_t* status_dev, int32_t* row_dev, double* coef_dev, double* wterm_dev,
+                              int32_t* term_source_dev, void* stream);
+
+/*
  * K2 -- fused morph + mixture density + log + reduce, unbinned (per-superblock partial sums).
  *
  * Replaces: the `ps` interpolation call (likelihood.py:356 -> pdf_morphers.py:70 ->
@@ -205,6 +222,27 @@ int bi_unbinned_ll_batch(int32_t n_dims, const int32_t* n_anchors_host, const do
                          double outlier_likelihood, int32_t target_units,
                          void* workspace_dev, int64_t workspace_bytes,
                          double* logl_dev, double* logsum_dev, double* musum_dev, int32_t* status_dev, void* stream);
+
+/* bi_unbinned_ll_batch for source-wise interpolation (K1 = bi_point_setup_sourcewise). */
+int bi_unbinned_ll_batch_sourcewise(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                                    int32_t n_sources, const uint32_t* dim_mask_host, const int32_t* row_base_host,
+                                    int64_t n_points,
+                                    const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                                    const double* eff_dev, const double* mus_rows_dev,
+                                    const uint8_t* allow_negative_host,
+                                    const double* rows_dev, int64_t ld_events, int64_t n_events,
+                                    double outlier_likelihood, int32_t target_units,
+                                    void* workspace_dev, int64_t workspace_bytes,
+                                    double* logl_dev, double* logsum_dev, double* musum_dev, int32_t* status_dev,
+                                    void* stream);
+
+/* Morphed per-event pdf values ps[S, N] of ONE point from its contraction terms (row_dev / wterm_dev point at
+ * that point's K entries), reference operation order; copy_source_dev[s] != 0: the source has no shape
+ * parameter and its single row is copied (full_output=True with source-wise interpolation). */
+int bi_unbinned_ps_terms(const double* rows_dev, int64_t ld_events, int64_t n_events, int32_t n_terms,
+                         int32_t n_sources, const int32_t* row_dev, const double* wterm_dev,
+                         const int32_t* term_source_dev, const uint8_t* copy_source_dev,
+                         double* ps_out_dev, int64_t ld_out, void* stream);
 
 /* logL[p] = -musum[p] + total(partial[p, :]) in canonical order; status != 0 -> -inf.
  * (likelihood.py:690 `-mu.sum() + np.sum(np.log(p_events))`, :347/:402 soft failures.)

@@ -74,6 +74,59 @@ class UnbinnedOracle(object):
         return np.array([self(z, m) for z, m in zip(zs_array, rate_multiplier_array)])
 
 
+class SourcewiseUnbinnedOracle(object):
+    """Source-wise interpolation (likelihood.py:113-145,152-169,210-240,534-555): one
+    RegularGridInterpolator per source over the shape parameters that source depends on
+    (pdf_morphers.py:45-70 with the source's own shape_parameters); sources without shape
+    parameters keep their base values.
+
+    axes: anchor axes of ALL shape parameters (bounds test, likelihood.py:345-347);
+    source_dims[s]: indices of the parameters source s depends on (ascending);
+    mus_sub[s] / ps_sub[s]: arrays shaped [sub-grid...] / [sub-grid..., N] (scalars / [N] for no parameters)."""
+
+    def __init__(self, axes, source_dims, mus_sub, outlier_likelihood=1e-12, allow_negative=None):
+        self.axes = [np.asarray(a, dtype=float) for a in axes]
+        self.source_dims = [list(d) for d in source_dims]
+        self.outlier_likelihood = outlier_likelihood
+        self.allow_negative = allow_negative
+        self.mus_sub = [np.asarray(m, dtype=float) for m in mus_sub]
+        self._mus_itp = [RegularGridInterpolator([self.axes[d] for d in dims], m.reshape(m.shape + (1,)))
+                         if len(dims) else None for dims, m in zip(self.source_dims, self.mus_sub)]
+        self._ps_itp = None
+
+    def set_ps(self, ps_sub):
+        self.ps_sub = [np.asarray(p, dtype=float) for p in ps_sub]
+        self._ps_itp = [RegularGridInterpolator([self.axes[d] for d in dims], p) if len(dims) else None
+                        for dims, p in zip(self.source_dims, self.ps_sub)]
+        return self
+
+    def __call__(self, zs, rate_multipliers, livetime_scale=None, full_output=False):
+        zs = np.asarray(zs, dtype=float)
+        for a, z in zip(self.axes, zs):
+            if not a[0] <= z <= a[-1]:
+                return -float('inf')
+        mus, ps = [], []
+        for s, dims in enumerate(self.source_dims):
+            if len(dims):
+                these = np.asarray([zs[d] for d in dims])
+                mus.append(self._mus_itp[s](these)[0][0])          # likelihood.py:230 (extra_dims=[1], then [0])
+                ps.append(self._ps_itp[s](these)[0])               # likelihood.py:550
+            else:
+                mus.append(float(self.mus_sub[s]))
+                ps.append(self.ps_sub[s])
+        mus = _unbinned.scale_mus(np.array(mus), rate_multipliers, livetime_scale)
+        ps = np.array(ps)
+        if _unbinned.rates_unphysical(mus, self.allow_negative):
+            return -float('inf')
+        ll = _unbinned.extended_loglikelihood(mus, ps, self.outlier_likelihood)
+        if full_output:
+            return ll, mus, ps
+        return ll
+
+    def batch(self, zs_array, rate_multiplier_array):
+        return np.array([self(z, m) for z, m in zip(zs_array, rate_multiplier_array)])
+
+
 class BinnedOracle(object):
     """likelihood.py:576-675.  pmf_anchor / n_model_anchor: [n1..nD, S, *bins]."""
 

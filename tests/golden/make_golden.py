@@ -178,10 +178,64 @@ def golden_multisource():
     save('multisource', x=d['x'], params=table, logl=logl)
 
 
+# ---------------------------------------------------------------------------------------------
+# G5: source-wise interpolation (likelihood.py:113-145,210-240,534-555): s0 depends on (mu, sigma),
+# s1 on sigma only, s2 on no shape parameter
+# ---------------------------------------------------------------------------------------------
+def sourcewise_config():
+    config = conf_for_test(n_sources=3)
+    config['sources'][0]['events_per_day'] = 700.
+    config['sources'][1].update(events_per_day=250., extra_dont_hash_settings=['mu'])
+    config['sources'][2].update(events_per_day=50., extra_dont_hash_settings=['mu', 'sigma'])
+    config['source_wise_interpolation'] = True
+    return config
+
+
+def golden_sourcewise():
+    lf = UnbinnedLogLikelihood(sourcewise_config())
+    for s in range(3):
+        lf.add_rate_parameter('s%d' % s)
+    lf.add_shape_parameter('mu', {-2: -2, 0: 0, 2: 2})
+    lf.add_shape_parameter('sigma', (0.5, 1, 2))
+    lf.prepare()
+    np.random.seed(3)
+    d = lf.base_model.simulate()
+    lf.set_data(d)
+    axes = [np.array([-2., 0., 2.]), np.array([0.5, 1., 2.])]
+    rng = np.random.default_rng(11)
+    n = 40
+    zs = np.column_stack([rng.uniform(-2, 2, n), rng.uniform(0.5, 2, n)])
+    mult = rng.uniform(0.5, 1.5, (n, 3))
+    zs, mult = special_points(zs, mult, axes)
+    logl = np.array([lf(mu=float(z[0]), sigma=float(z[1]), **{'s%d_rate_multiplier' % s: float(m[s]) for s in range(3)})
+                     for z, m in zip(zs, mult)])
+    full = [lf(mu=float(zs[i, 0]), sigma=float(zs[i, 1]), full_output=True,
+               **{'s%d_rate_multiplier' % s: float(mult[i, s]) for s in range(3)}) for i in (30, 31)]
+    # the per-source anchor rows of the reference itself, sources concatenated, sub-anchors in C order
+    rows, mus_rows = [], []
+    for sn, base_source in zip(lf.source_name_list, lf.base_model.sources):
+        if sn in lf.source_morphers:
+            for anchor in lf.source_morphers[sn].get_anchor_points(bounds=None):
+                src = lf.anchor_sources[sn][anchor]
+                rows.append(src.pdf(d['x']))
+                mus_rows.append(src.expected_events)
+        else:
+            rows.append(base_source.pdf(d['x']))
+            mus_rows.append(base_source.expected_events)
+    save('sourcewise', x=d['x'], zs=zs, mult=mult, logl=logl, rows=np.array(rows), mus_rows=np.array(mus_rows),
+         full_index=np.array([30, 31]), full_mus=np.array([f[1] for f in full]),
+         full_ps=np.array([f[2] for f in full]))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()['golden_' + name]()
+        sys.exit(0)
     golden_c1()
     golden_c2('linear')
     golden_c2('piecewise')
     golden_binned(False)
     golden_binned(True)
     golden_multisource()
+    golden_sourcewise()

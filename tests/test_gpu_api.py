@@ -155,6 +155,80 @@ def test_golden_multisource():
     assert_vector_close(lf.batch(g['params'], names), g['logl'], len(d))
 
 
+def test_golden_sourcewise():
+    """source_wise_interpolation (likelihood.py:113-145,210-240,534-555): s0 on (mu, sigma), s1 on sigma, s2 on nothing."""
+    from blueice_b200 import UnbinnedLogLikelihood
+    from blueice_b200.test_helpers import conf_for_test
+    g = load_golden('sourcewise')
+    config = conf_for_test(n_sources=3)
+    config['sources'][0]['events_per_day'] = 700.
+    config['sources'][1].update(events_per_day=250., extra_dont_hash_settings=['mu'])
+    config['sources'][2].update(events_per_day=50., extra_dont_hash_settings=['mu', 'sigma'])
+    config['source_wise_interpolation'] = True
+    lf = UnbinnedLogLikelihood(config)
+    for s in range(3):
+        lf.add_rate_parameter('s%d' % s)
+    lf.add_shape_parameter('mu', {-2: -2, 0: 0, 2: 2})
+    lf.add_shape_parameter('sigma', (0.5, 1, 2))
+    lf.prepare()
+    assert list(lf.source_shape_parameters.keys()) == ['s0', 's1']
+    assert lf._get_shape_indices('s1') == [1] and lf._get_model_anchor((2,), 's1') == (None, 2)
+    d = np.zeros(len(g['x']), dtype=[('x', float), ('source', int)])
+    d['x'] = g['x']
+    lf.set_data(d)
+    n = len(d)
+    eng = lf._engine
+    assert eng.n_rows == 13 and eng.n_terms == 4 + 2 + 1
+    # the per-(source, sub-anchor) rows equal the reference's own, bit for bit
+    assert np.array_equal(eng.ps_anchor[:, :n].cpu().numpy(), g['rows'])
+    assert np.array_equal(eng.mus_rows_host, g['mus_rows'])
+    names = ['s0_rate_multiplier', 's1_rate_multiplier', 's2_rate_multiplier', 'mu', 'sigma']
+    table = np.column_stack([g['mult'], g['zs']])
+    batch = lf.batch(table, names)
+    assert_vector_close(batch, g['logl'], n)
+    for i in (0, 5, 17, 39):
+        assert lf(**dict(zip(names, [float(v) for v in table[i]]))) == batch[i]
+    for k, i in enumerate(g['full_index']):
+        ll, mus, ps = lf(full_output=True, **dict(zip(names, [float(v) for v in table[i]])))
+        assert ll == batch[i]
+        assert np.array_equal(mus, g['full_mus'][k])
+        assert np.array_equal(ps, g['full_ps'][k])
+    np.testing.assert_allclose(lf.mus_interpolator(g['zs'][30]) * g['mult'][30], g['full_mus'][0], rtol=1e-15)
+
+
+def test_source_wise_interpolation():
+    """tests/test_likelihood.py:95-121: identical results with and without source-wise interpolation."""
+    from blueice_b200 import UnbinnedLogLikelihood
+    from blueice_b200.test_helpers import conf_for_test
+    data = np.zeros(5, dtype=[('x', float), ('source', int)])
+    data['x'] = np.linspace(0, 1, 5)
+    config = conf_for_test(events_per_day=1)
+    lf = UnbinnedLogLikelihood(config)
+    lf.add_shape_parameter("mu", anchors={-2: -2, 0: 0, 2: 2})
+    lf.prepare()
+    lf.set_data(data)
+    ret_0 = lf(full_output=True)
+    ret_1 = lf(full_output=True, mu=1)
+    config["source_wise_interpolation"] = True
+    lf_source_wise = UnbinnedLogLikelihood(config)
+    lf_source_wise.add_shape_parameter("mu", anchors={-2: -2, 0: 0, 2: 2})
+    lf_source_wise.prepare()
+    lf_source_wise.set_data(data)
+    ret_source_wise_0 = lf_source_wise(full_output=True)
+    ret_source_wise_1 = lf_source_wise(full_output=True, mu=1)
+    assert ret_0[0] == ret_source_wise_0[0]
+    assert (ret_0[1] == ret_source_wise_0[1]).all()
+    assert (ret_0[2] == ret_source_wise_0[2]).all()
+    assert ret_1[0] == ret_source_wise_1[0]
+    assert (ret_1[1] == ret_source_wise_1[1]).all()
+    assert (ret_1[2] == ret_source_wise_1[2]).all()
+    from blueice_b200 import BinnedLogLikelihood
+    lb = BinnedLogLikelihood(config)
+    lb.add_shape_parameter("mu", anchors={-2: -2, 0: 0, 2: 2})
+    with pytest.raises(NotImplementedError):
+        lb.prepare()
+
+
 # ------------------------------------------------------------------------------------------------
 # (b) the reference's own test scenarios
 # ------------------------------------------------------------------------------------------------

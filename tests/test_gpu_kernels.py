@@ -14,7 +14,7 @@ from oracle import binned as obinned
 from oracle import hist as ohist
 from oracle import morph as omorph
 from oracle import unbinned as ounbinned
-from oracle.pipeline import BinnedOracle, UnbinnedOracle
+from oracle.pipeline import BinnedOracle, SourcewiseUnbinnedOracle, UnbinnedOracle
 
 pytestmark = pytest.mark.gpu
 
@@ -247,6 +247,40 @@ def test_nan_inf_zero_and_negative_densities(outlier):
         got = eng.evaluate(zs, mult)
         ref = orc.batch(zs, mult)
         assert_logl_close(got, ref, 777, "special values, outlier=%g, %s" % (outlier, mode))
+
+
+@pytest.mark.parametrize("source_dims,n", [([[0, 1], [1], []], 1000), ([[0], [1], [0, 1, 2], [2]], 777),
+                                           ([[], []], 100), ([[0, 1, 2, 3]], 513), ([[1], [0], [1], [0], [1]], 2049)])
+def test_sourcewise_engine_matches_oracle(source_dims, n):
+    """bi_point_setup_sourcewise + K2 against one RegularGridInterpolator per source (likelihood.py:210-240,534-555)."""
+    engine = _engine_mod()
+    rng = np.random.default_rng(31 + n)
+    d = 1 + max([max(dims) for dims in source_dims if dims] + [0])
+    axes = random_axes(rng, d)
+    shapes = [tuple(len(axes[k]) for k in dims) for dims in source_dims]
+    mus_sub = [rng.uniform(50, 500, sh) for sh in shapes]
+    ps_sub = [rng.uniform(1e-4, 1e-1, sh + (n,)) for sh in shapes]
+    ps_sub[0][..., 7] = 0.0                       # source 0 contributes nothing to event 7
+    ps_sub[-1][..., 11] = np.nan                  # NaN term dropped by nansum
+    grid = engine.MorphGrid(axes)
+    eng = engine.SourcewiseUnbinnedEngine(grid, source_dims, np.concatenate([m.reshape(-1) for m in mus_sub]))
+    eng.set_ps_anchor(np.concatenate([p.reshape(-1, n) for p in ps_sub]))
+    orc = SourcewiseUnbinnedOracle(axes, source_dims, mus_sub).set_ps(ps_sub)
+    p = 70
+    zs = random_points(rng, axes, p)
+    mult = rng.uniform(0.5, 2, (p, len(source_dims)))
+    zs[60, 0] = axes[0][-1] + 1.0                 # out of range
+    mult[61, 0] = -1.0                            # unphysical
+    mult[62, :] = 0.0                             # every event an outlier
+    got = eng.evaluate(zs, mult)
+    ref = orc.batch(zs, mult)
+    assert_logl_close(got, ref, n, "source-wise %s" % (source_dims,))
+    for i in (0, 1, 33):
+        assert eng.evaluate(zs[i:i + 1], mult[i:i + 1])[0] == got[i]
+        ll, mus, ps = orc(zs[i], mult[i], full_output=True)
+        dev_mus, dev_ps = eng.ps(zs[i], mult[i])
+        assert np.array_equal(dev_mus, mus)                           # bit-exact per-source morph of the rates
+        assert np.array_equal(dev_ps, ps, equal_nan=True)             # bit-exact per-source morph of the pdf values
 
 
 def test_zero_rates_give_n_log_outlier():
