@@ -120,6 +120,16 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, taken from
+    the committed `ncu --set full` capture (profiles/ncu_traffic.json; the capture command is recorded there)."""
+    path = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(kernel_key, {}).get("dram_bytes_per_launch")
+
+
 def workload_config(n_events, n_points):
     return {"workload": "config 2: 2-source 2D (cs1,cs2) HistogramPdfSource templates 100x100 bins, "
                         "2 shape nuisances x 5 anchors, ~100k events, 4096-point profile scan",
@@ -169,7 +179,7 @@ class ClockSampler(object):
                     self.power.append(pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0)
                 except Exception:
                     pass
-                time.sleep(0.02)
+                time.sleep(0.004)
         except Exception as exc:                                   # pragma: no cover
             self.error = repr(exc)
 
@@ -241,12 +251,12 @@ def run_own_arm(args):
     zs_d, mult_d, _, _, _ = eng._upload_points(zs, mult, None, None)
     zs_d, mult_d = zs_d.clone(), mult_d.clone()
     plan_dev = tuple(None if t is None else t.clone() for t in eng.upload_plan(plan)[:3])
-    gathered = [torch.empty(P, dtype=torch.float64, device=device) for _ in range(world)] if world > 1 else None
+    gathered = torch.empty(P * world, dtype=torch.float64, device=device) if world > 1 else None
 
     def device_step():
         logl = eng.run_device(P, zs_d, mult_d, None, None, plan, plan_dev)
         if world > 1:
-            dist.all_gather(gathered, logl)
+            dist.all_gather_into_tensor(gathered, logl)
         return logl
 
     for _ in range(max(args.warmup, 3)):
@@ -280,7 +290,7 @@ def run_own_arm(args):
         t0 = time.perf_counter()
         res = ll.batch(table, names)
         if world > 1:
-            dist.all_gather(gathered, torch.from_numpy(res).to(device))
+            dist.all_gather_into_tensor(gathered, torch.from_numpy(res).to(device))
             torch.cuda.synchronize()
         e2e_s.append(time.perf_counter() - t0)
     assert np.array_equal(res, result_dev), "device-resident and e2e arms disagree"
@@ -452,7 +462,8 @@ def run_own_arm(args):
                      % ((C * S + 3) // 4, C * S) if plan.kernel == 'mma'
                      else "k_unbinned_grouped<%d> (threads=points, TMA-staged event tiles)" % C)
             roofline = {"kernel": kname, "bound": "fp64", "achieved": flops_alg / k2 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                        "frac": flops_alg / k2 / 1e12 / fp64_peak, "traffic": None,
+                        "frac": flops_alg / k2 / 1e12 / fp64_peak,
+                        "traffic": ncu_traffic("scan" if plan.kernel == 'mma' else "legacy_scan"),
                         "peak_source": "max(bi_bench_fp64_fma, bi_bench_fp64_mma) measured in this run: DFMA and DMMA "
                                        "share one pipe on sm_100a (MEASURED_PEAKS.json holds no FP64 figure)",
                         "flops_alg_per_point_event": 2 * C * S,

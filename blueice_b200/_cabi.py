@@ -32,7 +32,7 @@ SIGNATURES = {
                                                     _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
                                                     _c_void_p, _c_void_p]),
     "bi_plan_max_cells": (_i64, []),
-    "bi_unbinned_plan": (ctypes.c_int, [_i32, _c_void_p, _i64, _c_void_p, _c_void_p, _i32, _i64, _i32,
+    "bi_unbinned_plan": (ctypes.c_int, [_i32, _c_void_p, _i64, _c_void_p, _c_void_p, _i32, _i64, _i32, _i32,
                                         _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_unbinned_partials_mma": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p,
                                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,

@@ -63,7 +63,7 @@ __device__ int bi_block_exclusive_scan(int* v, int n, int* carry) {
 __global__ void __launch_bounds__(BI_PLAN_THREADS)
 k_plan_units(const __grid_constant__ BiPlanDims dims, int n_cells, int64_t n_points,
              const int32_t* __restrict__ cell, const int32_t* __restrict__ status,
-             int unit_points, int64_t n_super, int target_units,
+             int unit_points, int64_t n_super, int target_units, int full_units,
              int32_t* __restrict__ group_points, int32_t* __restrict__ groups, int32_t* __restrict__ header) {
     extern __shared__ int bi_plan_smem[];
     int* poff = bi_plan_smem;                     // [n_cells + 1] counts -> point offsets
@@ -105,7 +105,7 @@ k_plan_units(const __grid_constant__ BiPlanDims dims, int n_cells, int64_t n_poi
             int pos = poff[c];
             const int end = poff[c + 1];
             for (int i = 0; i < u; ++i) {
-                int cnt = 8 * (base + (i < rem ? 1 : 0));
+                int cnt = full_units ? unit_points : 8 * (base + (i < rem ? 1 : 0));
                 if (cnt > end - pos) cnt = end - pos;
                 groups[2 * (goff[c] + i)] = pos;
                 groups[2 * (goff[c] + i) + 1] = cnt;
@@ -148,7 +148,7 @@ extern "C" int64_t bi_plan_max_cells(void) { return BI_PLAN_MAX_CELLS; }
 
 extern "C" int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_points,
                                 const int32_t* cell_dev, const int32_t* status_dev, int32_t unit_points,
-                                int64_t n_events, int32_t target_units,
+                                int64_t n_events, int32_t target_units, int32_t full_units,
                                 int32_t* group_points_dev, int32_t* groups_dev, int32_t* header_dev, void* stream) {
     BI_REQUIRE(n_dims >= 0 && n_dims <= BI_MAX_DIMS, "n_dims=%d outside [0,%d]", n_dims, BI_MAX_DIMS);
     BI_REQUIRE(n_points >= 0 && n_points < 0x7fffffff, "n_points outside [0, 2^31)");
@@ -176,6 +176,7 @@ extern "C" int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, i
     }
     k_plan_units<<<1, BI_PLAN_THREADS, smem, (cudaStream_t)stream>>>(
         dims, (int)n_cells, n_points, cell_dev, status_dev, unit_points, bi_num_superblocks(n_events), target_units,
+        full_units,
         group_points_dev, groups_dev, header_dev);
     BI_LAUNCH_CHECK();
     return BI_OK;

@@ -104,7 +104,7 @@ static int bi_unbinned_after_setup(int32_t n_dims, const int32_t* n_anchors_host
     double* partial = (double*)(base + w.partial);
     if (n_super > 0) {
         int rc = bi_unbinned_plan(n_dims, n_anchors_host, n_points, (int32_t*)(base + w.cell), status_dev,
-                                  bi_mma_unit_points(n_terms), n_events, target_units,
+                                  bi_mma_unit_points(n_terms), n_events, target_units & 0x3fffffff, target_units >> 30,
                                   (int32_t*)(base + w.group_points), (int32_t*)(base + w.groups),
                                   (int32_t*)(base + w.header), stream);
         if (rc != BI_OK) return rc;

@@ -174,7 +174,10 @@ def plan_points(grid, zs, n_sources, n_super, force_kernel=None):
     return PointPlan(P, in_range, stream_pts.astype(np.int32), group_pts.astype(np.int32), work)
 
 
-_MMA_TARGET_UNITS = int(os.environ.get('BI_MMA_TARGET_UNITS', 148 * 12 * 2))   # ~2 units per resident warp (measured optimum)
+# ~4 units per resident warp and full units + one remainder per cell (measured optimum on the config-2 scan);
+# bit 30 selects the full-units split, 0 = sizes balanced inside a cell
+_MMA_TARGET_UNITS = (int(os.environ.get('BI_MMA_TARGET_UNITS', 148 * 12 * 4))
+                     | (int(os.environ.get('BI_MMA_FULL_UNITS', '1')) << 30))
 _EMPTY_I32 = np.zeros(0, dtype=np.int32)
 
 
@@ -370,7 +373,8 @@ class UnbinnedEngine(_EngineBase):
         """Stage 2 of the fused path alone (bench / profiling): device-side schedule into the workspace views."""
         _cabi.check(self.lib.bi_unbinned_plan(
             self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), P, _cabi.dev_ptr(views["cell"]),
-            _cabi.dev_ptr(status_d), int(self.lib.bi_mma_unit_points(self.n_terms)), self.n_events, _MMA_TARGET_UNITS,
+            _cabi.dev_ptr(status_d), int(self.lib.bi_mma_unit_points(self.n_terms)), self.n_events,
+            _MMA_TARGET_UNITS & 0x3fffffff, _MMA_TARGET_UNITS >> 30,
             _cabi.dev_ptr(views["group_points"]), _cabi.dev_ptr(views["groups"]), _cabi.dev_ptr(views["header"]),
             self._stream()), "bi_unbinned_plan")
 

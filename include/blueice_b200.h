@@ -170,13 +170,14 @@ int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t ld_events,
  *   header_dev [8]          out: n_groups, n_ranges, superblocks_per_range, n_units, 0 (fetch counter),
  *                           n_evaluable, 0, 0.  Work unit u = (group u % n_groups, range u / n_groups).
  *   target_units            aimed-at number of work units (a few per resident warp)
+ *   full_units              0: sizes balanced inside a cell (e.g. 7+7+7+6+6 m-tiles); 1: full units + one remainder
  * Grids with more than BI_PLAN_MAX_CELLS hypercube cells are rejected (BI_ERR_INVALID_ARGUMENT).
  */
 #define BI_PLAN_MAX_CELLS 16384
 int64_t bi_plan_max_cells(void);
 int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_points,
                      const int32_t* cell_dev, const int32_t* status_dev, int32_t unit_points,
-                     int64_t n_events, int32_t target_units,
+                     int64_t n_events, int32_t target_units, int32_t full_units,
                      int32_t* group_points_dev, int32_t* groups_dev, int32_t* header_dev, void* stream);
 
 /*
