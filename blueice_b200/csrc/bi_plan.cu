@@ -4,9 +4,10 @@
 // flat cell index), cuts every cell's points into point groups of at most `unit_points` points (whole
 // 8-point m-tiles, sizes balanced inside a cell) and picks the superblock range length, writing
 //     group_points [P]           point indices, cell-major
-//     groups       [n_groups][2] (first, count) into group_points
+//     groups       [n_groups][4] (first, count, range counter = 0, 0); first / count index group_points
 //     header       [8]           n_groups, n_ranges, sb_per_range, n_units, fetch counter (= 0), 0, 0, 0
-// Work unit u of the persistent K2 kernel = (group u % n_groups, superblock range u / n_groups).
+// The persistent K2 kernel hands out (group, superblock range) pairs: warps stick to a group and fetch its ranges
+// from the group's counter.
 // Results never depend on the schedule, so the order of points inside a cell
 // (decided by atomics) is free.
 #include "bi_common.cuh"
@@ -107,8 +108,10 @@ k_plan_units(const __grid_constant__ BiPlanDims dims, int n_cells, int64_t n_poi
             for (int i = 0; i < u; ++i) {
                 int cnt = full_units ? unit_points : 8 * (base + (i < rem ? 1 : 0));
                 if (cnt > end - pos) cnt = end - pos;
-                groups[2 * (goff[c] + i)] = pos;
-                groups[2 * (goff[c] + i) + 1] = cnt;
+                groups[4 * (goff[c] + i)] = pos;
+                groups[4 * (goff[c] + i) + 1] = cnt;
+                groups[4 * (goff[c] + i) + 2] = 0;                 // range counter of the persistent K2 kernel
+                groups[4 * (goff[c] + i) + 3] = 0;
                 pos += cnt;
             }
         }

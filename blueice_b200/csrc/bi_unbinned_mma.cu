@@ -8,7 +8,7 @@ static int bi_mma_k4(int K) {
 
 extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t n_events,
                                         int32_t n_terms, int32_t n_sources,
-                                        const int32_t* group_points_dev, const int32_t* groups_dev, int32_t* header_dev,
+                                        const int32_t* group_points_dev, int32_t* groups_dev, int32_t* header_dev,
                                         const int32_t* row_dev, const double* coef_dev, const double* wterm_dev,
                                         const int32_t* term_source_dev, const double* mus_dev,
                                         double outlier_likelihood, double* partial_dev, void* stream) {
@@ -20,7 +20,7 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
     BI_REQUIRE(ld_events >= n_events && (ld_events % 2) == 0, "ld_events=%lld must be even and >= n_events=%lld",
                (long long)ld_events, (long long)n_events);
     BI_REQUIRE(((uintptr_t)rows_dev & 15) == 0, "rows_dev must be 16-byte aligned");
-    BI_REQUIRE(((uintptr_t)groups_dev & 7) == 0, "groups_dev must be 8-byte aligned");
+    BI_REQUIRE(((uintptr_t)groups_dev & 15) == 0, "groups_dev must be 16-byte aligned");
     BI_REQUIRE(n_sources >= 1 && n_sources <= BI_MAX_SOURCES, "n_sources=%d outside [1,%d]", n_sources, BI_MAX_SOURCES);
     BI_REQUIRE(n_terms >= 1 && n_terms <= BI_MMA_MAX_TERMS, "bi_unbinned_partials_mma supports 1..%d contraction terms (got %d)",
                BI_MMA_MAX_TERMS, n_terms);
@@ -66,7 +66,7 @@ static BiUnbinnedWorkspace bi_unbinned_layout(int32_t D, int32_t S, int64_t K, i
     w.mus = o;          o += bi_align256(P * S * 8);
     w.partial = o;      o += bi_align256(P * (n_super > 0 ? n_super : 1) * 8);
     w.group_points = o; o += bi_align256(P * 4);
-    w.groups = o;       o += bi_align256((P + 1) * 8);
+    w.groups = o;       o += bi_align256((P + 1) * 16);
     w.header = o;       o += 256;
     w.row = o;          o += bi_align256(P * K * 4);
     w.coef = o;         o += bi_align256(P * K * 8);

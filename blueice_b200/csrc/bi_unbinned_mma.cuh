@@ -16,8 +16,10 @@
 // so the kernel is bound by that pipe instead of by instruction issue.  DMMA accumulates as a
 // sequential fma chain in k order (bit-exact, profiles/microbench/dmma_probe_b200.log).
 //
-// Work unit (one warp): up to 8*MT points that share one hypercube cell x a range of superblocks.
-// Four units per CTA; every warp owns its ring, its barriers and its TMA issue -- no CTA-wide sync.
+// Work: a point group = up to 8*MT points that share one hypercube cell.  Persistent warps pick a group, load its
+// coefficients once, then fetch superblock ranges of that group from the group's counter until none is left
+// (the TMA tile stream runs across range boundaries), then move to another group.  Every warp owns its ring,
+// its barriers and its TMA issue -- no CTA-wide sync.
 //
 // Canonical arithmetic -- what every result is defined by, independent of how the
 // batch is cut into units:
@@ -262,19 +264,89 @@ __device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, in
 // ---------------------------------------------------------------------------------------------
 // one work unit with NMT m-tiles: coefficients -> registers, then the tile loop
 // ---------------------------------------------------------------------------------------------
+// warp-private producer cursor (shared memory): the range whose tiles are being issued, the next tile of it,
+// and the range the producer has fetched ahead of the consumer (one range of lookahead)
+struct BiProducer { int range, tile, n_tiles, pending; };
+
+template <int K4>
+__device__ __forceinline__ int bi_range_tiles(int range, int sb_per, int64_t n_super, int64_t N) {
+    const int64_t sb0 = (int64_t)range * sb_per;
+    int64_t sb1 = sb0 + sb_per;
+    if (sb1 > n_super) sb1 = n_super;
+    int64_t ev1 = sb1 * BI_SUPERBLOCK;
+    if (ev1 > N) ev1 = N;
+    return (int)((ev1 - sb0 * BI_SUPERBLOCK + BiMmaCfg<K4>::T - 1) / BiMmaCfg<K4>::T);
+}
+
+// next superblock range of this point group (-1: none left); warp-collective
+__device__ __forceinline__ int bi_fetch_range(int* counter, int n_ranges, int lane) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(counter, 1);
+    r = __shfl_sync(BI_FULL_MASK, r, 0);
+    return r < n_ranges ? r : -1;
+}
+
+// issue the next tile of the warp's tile stream, fetching the following range when the current one is
+// exhausted (warp-collective, all values warp-uniform)
+template <int K4>
+__device__ __forceinline__ void bi_mma_produce(BiProducer* prod, int* counter, int n_ranges, int sb_per, int64_t n_super,
+                                               const double* __restrict__ A, const double* __restrict__ src_row,
+                                               const int32_t* __restrict__ row_lead, int64_t ld, int64_t N, int K,
+                                               double* ring, uint64_t* full_bar, unsigned& issued, int lane) {
+    using Cfg = BiMmaCfg<K4>;
+    int pr = prod->range;
+    if (pr < 0) return;
+    int pt = prod->tile;
+    if (pt == prod->n_tiles) {
+        if (prod->pending >= 0) return;                           // lookahead of one range only
+        pr = bi_fetch_range(counter, n_ranges, lane);
+        pt = 0;
+        __syncwarp();
+        if (lane == 0) {
+            prod->range = pr;
+            prod->pending = pr;
+            prod->n_tiles = pr >= 0 ? bi_range_tiles<K4>(pr, sb_per, n_super, N) : 0;
+        }
+        __syncwarp();
+        if (pr < 0) return;
+    }
+    bi_mma_issue<K4>(A, src_row, row_lead, ld, (int64_t)pr * sb_per * BI_SUPERBLOCK, pt, (int)(issued % Cfg::STAGES), K,
+                     ring, full_bar, lane);
+    ++issued;
+    if (lane == 0) prod->tile = pt + 1;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// one point group with NMT m-tiles: coefficients -> registers once, then superblock ranges of the group are
+// fetched from its counter until none is left (the TMA tile stream runs across range boundaries)
+// ---------------------------------------------------------------------------------------------
 template <int K4, int NMT>
 __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const double* __restrict__ src_row,
                                             const int32_t* __restrict__ row_lead, int64_t ld, int64_t N, int K, int S,
                                             const int32_t* __restrict__ slot_point, unsigned active_mask, int64_t lead,
-                                            int64_t sb_begin, int64_t sb_end, int64_t ev_begin, int n_tiles, int64_t n_super,
+                                            int* counter, int n_ranges, int sb_per, int64_t n_super,
                                             const double* __restrict__ coef, const int32_t* __restrict__ term_source,
                                             const double* __restrict__ wterm, const double* __restrict__ mus,
                                             double outlier, double* __restrict__ partial,
-                                            double* ring, uint64_t* full_bar, double* slow_acc, unsigned tiles_done,
-                                            int lane) {
+                                            double* ring, uint64_t* full_bar, double* slow_acc, BiProducer* prod,
+                                            unsigned& issued, unsigned& consumed, int lane) {
     using Cfg = BiMmaCfg<K4>;
     constexpr int T = Cfg::T;
     const int g = lane >> 2, t = lane & 3;
+
+    int cur = bi_fetch_range(counter, n_ranges, lane);
+    if (cur < 0) return;
+    if (lane == 0) {
+        prod->range = cur;
+        prod->tile = 0;
+        prod->n_tiles = bi_range_tiles<K4>(cur, sb_per, n_super, N);
+        prod->pending = -1;
+    }
+    __syncwarp();
+    // the first tiles are in flight while the coefficients are gathered
+    for (int i = 0; i < Cfg::STAGES; ++i)
+        bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar, issued, lane);
 
     double a[NMT][K4];
 #pragma unroll
@@ -292,16 +364,19 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
 #pragma unroll
     for (int mt = 0; mt < NMT; ++mt) { M[mt] = 1.0; E[mt] = 0; }
     bool slow_any = false;
-    int st = (int)(tiles_done % Cfg::STAGES), tile_idx = 0;
-    unsigned parity = (tiles_done / Cfg::STAGES) & 1u;
     constexpr int TILES_PER_SUPER = BI_SUPERBLOCK / T, GROUPS_PER_TILE = T / BI_GROUP_EVENTS;
 
+  while (cur >= 0) {
+    const int64_t sb_begin = (int64_t)cur * sb_per;
+    int64_t sb_end = sb_begin + sb_per;
+    if (sb_end > n_super) sb_end = n_super;
     for (int64_t sb = sb_begin; sb < sb_end; ++sb) {
         const int64_t left = N - sb * BI_SUPERBLOCK;
         const int n_ev = left < BI_SUPERBLOCK ? (int)left : BI_SUPERBLOCK;      // events of this superblock that exist
 #pragma unroll 1
-        for (int ti = 0; ti < TILES_PER_SUPER && ti * T < n_ev; ++ti, ++tile_idx) {
-            bi_mbar_wait(&full_bar[st], parity);
+        for (int ti = 0; ti < TILES_PER_SUPER && ti * T < n_ev; ++ti) {
+            const int st = (int)(consumed % Cfg::STAGES);
+            bi_mbar_wait(&full_bar[st], (consumed / Cfg::STAGES) & 1u);
             const double* tile = ring + (size_t)st * Cfg::STAGE_DOUBLES;
             const int n_valid = n_ev - ti * T;                                   // may exceed T
             if (n_valid >= T) {
@@ -320,11 +395,11 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
                                                     mus, outlier, slow_acc, slow_any, M, E, lane);
                 }
             }
-            // this warp is done with the stage: refill it with tile + STAGES
+            // this warp is done with the stage: refill it with the next tile of the stream
             __syncwarp();
-            if (tile_idx + Cfg::STAGES < n_tiles)
-                bi_mma_issue<K4>(A, src_row, row_lead, ld, ev_begin, tile_idx + Cfg::STAGES, st, K, ring, full_bar, lane);
-            if (++st == Cfg::STAGES) { st = 0; parity ^= 1u; }
+            ++consumed;
+            bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar,
+                               issued, lane);
         }
         // ---- close the superblock: combine the four classes, one log per point
         const bool any_slow = __any_sync(BI_FULL_MASK, slow_any);
@@ -370,6 +445,23 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
         for (int mt = 0; mt < NMT; ++mt) { M[mt] = 1.0; E[mt] = 0; }
         slow_any = false;
     }
+    // ---- next range: the one the producer has already fetched (its first tiles are in flight)
+    if (prod->pending < 0 && prod->range >= 0)
+        bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar, issued, lane);
+    cur = prod->pending;
+    __syncwarp();
+    if (cur >= 0) {
+        if (lane == 0) prod->pending = -1;
+        __syncwarp();
+        while (issued - consumed < (unsigned)Cfg::STAGES && prod->range >= 0 &&
+               !(prod->tile == prod->n_tiles && prod->pending >= 0)) {
+            const unsigned before = issued;
+            bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar,
+                               issued, lane);
+            if (issued == before) break;
+        }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -379,7 +471,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
 template <int K4>
 __global__ void __launch_bounds__(BiMmaCfg<K4>::THREADS, BiMmaCfg<K4>::MIN_CTAS)
 k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S,
-               const int32_t* __restrict__ group_points, const int2* __restrict__ groups, int32_t* header,
+               const int32_t* __restrict__ group_points, int4* groups, int32_t* header,
                int64_t n_super, const int32_t* __restrict__ row, const double* __restrict__ coef,
                const double* __restrict__ wterm, const int32_t* __restrict__ term_source,
                const double* __restrict__ mus, double outlier, double* __restrict__ partial) {
@@ -392,7 +484,8 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S
     double* ring = reinterpret_cast<double*>(bi_smem + Cfg::HEADER_BYTES) + (size_t)warp * Cfg::RING_DOUBLES;
     double* slow_acc = reinterpret_cast<double*>(bi_smem + Cfg::HEADER_BYTES) + (size_t)Cfg::WARPS * Cfg::RING_DOUBLES +
                        threadIdx.x;
-    const int n_groups = header[0], sb_per = header[2], n_units = header[3];
+    const int n_groups = header[0], n_ranges = header[1], sb_per = header[2];
+    BiProducer* prod = reinterpret_cast<BiProducer*>(bi_smem + 128) + warp;
 
     if (lane == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) bi_mbar_init(&full_bar[i], 1);
@@ -406,20 +499,26 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S
         ring[(size_t)st_i * Cfg::STAGE_DOUBLES + K * Cfg::RS + r] = 0.0;
     }
     __syncwarp();
-    unsigned tiles_done = 0;                                       // ring position carries over from unit to unit
+    unsigned issued = 0, consumed = 0;                             // ring position carries over from group to group
 
     for (;;) {
-        int unit = 0;
-        if (lane == 0) unit = atomicAdd(&header[4], 1);
-        unit = __shfl_sync(BI_FULL_MASK, unit, 0);
-        if (unit >= n_units) break;
-        const int range = unit / n_groups, grp = unit - range * n_groups;
-        const int2 gp = groups[grp];
+        // a point group with superblock ranges left: start at a ticket (spreads the warps over the groups), then scan
+        int grp = 0;
+        if (lane == 0) {
+            grp = (int)((unsigned)atomicAdd(&header[4], 1) % (unsigned)n_groups);
+            int tries = 0;
+            while (tries < n_groups && *reinterpret_cast<volatile int*>(&groups[grp].z) >= n_ranges) {
+                grp = grp + 1 == n_groups ? 0 : grp + 1;
+                ++tries;
+            }
+            if (tries == n_groups) grp = -1;
+        }
+        grp = __shfl_sync(BI_FULL_MASK, grp, 0);
+        if (grp < 0) break;
+        const int4 gp = groups[grp];
         const int n_pts = gp.y;
-        const int64_t sb_begin = (int64_t)range * sb_per;
-        int64_t sb_end = sb_begin + sb_per;
-        if (sb_end > n_super) sb_end = n_super;
         const int n_mt = (n_pts + 7) >> 3;
+        int* counter = const_cast<int*>(&groups[grp].z);
 
         // slots: point of (m-tile mt, row g); slots beyond n_pts replay the group's first point
         const int32_t* slot_point = group_points + gp.x;
@@ -429,23 +528,15 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S
             if (mt * 8 + g < n_pts) active_mask |= 1u << mt;
         const int64_t lead = slot_point[0];
         const int32_t* row_lead = row + lead * K;                  // every point of the group has these rows
-
-        // the first tiles are in flight while the coefficients are gathered
-        const int64_t ev_begin = sb_begin * BI_SUPERBLOCK;
-        int64_t ev_end = sb_end * BI_SUPERBLOCK;
-        if (ev_end > N) ev_end = N;
-        const int n_tiles = (int)((ev_end - ev_begin + T - 1) / T);
         const double* src_row = A;
         if (Cfg::ROWREG && lane < K) src_row = A + (int64_t)row_lead[lane] * ld;
-        for (int i = 0; i < Cfg::STAGES && i < n_tiles; ++i)
-            bi_mma_issue<K4>(A, src_row, row_lead, ld, ev_begin, i, (tiles_done + i) % Cfg::STAGES, K, ring, full_bar, lane);
 
 #define BI_MMA_UNIT(NN)                                                                                              \
     case NN:                                                                                                         \
         if (NN <= MT)                                                                                                \
             bi_mma_unit<K4, (NN <= MT ? NN : 1)>(A, src_row, row_lead, ld, N, K, S, slot_point, active_mask, lead,   \
-                                                 sb_begin, sb_end, ev_begin, n_tiles, n_super, coef, term_source,   \
-                                                 wterm, mus, outlier, partial, ring, full_bar, slow_acc, tiles_done, \
+                                                 counter, n_ranges, sb_per, n_super, coef, term_source, wterm, mus,  \
+                                                 outlier, partial, ring, full_bar, slow_acc, prod, issued, consumed, \
                                                  lane);                                                              \
         break;
         switch (n_mt) {
@@ -453,7 +544,6 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S
             BI_MMA_UNIT(5) BI_MMA_UNIT(6) BI_MMA_UNIT(7) BI_MMA_UNIT(8)
         }
 #undef BI_MMA_UNIT
-        tiles_done += (unsigned)n_tiles;
     }
 }
 
@@ -478,7 +568,7 @@ static int bi_mma_grid(int* blocks) {
 
 template <int K4>
 static int bi_launch_mma(const double* A, int64_t ld, int64_t N, int K, int S, const int32_t* group_points,
-                         const int32_t* groups, int32_t* header, int64_t n_super, const int32_t* row, const double* coef,
+                         int32_t* groups, int32_t* header, int64_t n_super, const int32_t* row, const double* coef,
                          const double* wterm, const int32_t* term_source, const double* mus, double outlier,
                          double* partial, cudaStream_t st) {
     using Cfg = BiMmaCfg<K4>;
@@ -486,7 +576,7 @@ static int bi_launch_mma(const double* A, int64_t ld, int64_t N, int K, int S, c
     int rc = bi_mma_grid<K4>(&blocks);
     if (rc != BI_OK) return rc;
     k_unbinned_mma<K4><<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
-        A, ld, N, K, S, group_points, reinterpret_cast<const int2*>(groups), header, n_super, row, coef, wterm,
+        A, ld, N, K, S, group_points, reinterpret_cast<int4*>(groups), header, n_super, row, coef, wterm,
         term_source, mus, outlier, partial);
     BI_LAUNCH_CHECK();
     return BI_OK;

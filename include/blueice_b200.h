@@ -166,9 +166,9 @@ int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t ld_events,
  * `unit_points` = bi_mma_unit_points(n_terms) points.
  *   cell_dev / status_dev   outputs of bi_point_setup ([P, max(D, 1)] and [P])
  *   group_points_dev [P]    out: point indices, cell-major
- *   groups_dev [(P + 1) * 2] out: (first, count) per point group
- *   header_dev [8]          out: n_groups, n_ranges, superblocks_per_range, n_units, 0 (fetch counter),
- *                           n_evaluable, 0, 0.  Work unit u = (group u % n_groups, range u / n_groups).
+ *   groups_dev [(P + 1) * 4] out: (first, count, range counter = 0, 0) per point group, 16-byte aligned
+ *   header_dev [8]          out: n_groups, n_ranges, superblocks_per_range, n_groups * n_ranges, 0 (group ticket
+ *                           counter), n_evaluable, 0, 0.
  *   target_units            aimed-at number of work units (a few per resident warp)
  *   full_units              0: sizes balanced inside a cell (e.g. 7+7+7+6+6 m-tiles); 1: full units + one remainder
  * Grids with more than BI_PLAN_MAX_CELLS hypercube cells are rejected (BI_ERR_INVALID_ARGUMENT).
@@ -181,21 +181,22 @@ int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_po
                      int32_t* group_points_dev, int32_t* groups_dev, int32_t* header_dev, void* stream);
 
 /*
- * bi_unbinned_partials_mma: K2 on the FP64 tensor pipe (DMMA.8x8x4), persistent: every warp fetches
- * work units (point group x superblock range) from header_dev[4] until header_dev[3] units are done.
+ * bi_unbinned_partials_mma: K2 on the FP64 tensor pipe (DMMA.8x8x4), persistent: every warp picks a point
+ * group (ticket header_dev[4]) and fetches superblock ranges from that group's counter (groups_dev[4 g + 2])
+ * until all header_dev[0] x header_dev[1] (group, range) pairs are done.
  * The density is the contraction f_i = sum_k coef[p, k] * rows[row[p, k], i] over n_terms terms
  * (bi_point_setup / bi_point_setup_sourcewise write row / coef / wterm / term_source).
  *   rows_dev   [n_rows, ld_events] per-event pdf values, one row per (anchor, source); ld_events even
  *   group_points_dev / groups_dev / header_dev as written by bi_unbinned_plan (or by the caller: all
  *   points of a group MUST share their row list, have status 0, and count <= bi_mma_unit_points(n_terms);
- *   header_dev[4] must be 0 on entry).  Requires n_terms <= BI_MMA_MAX_TERMS.
+ *   header_dev[4] and every group's range counter must be 0 on entry).  Requires n_terms <= BI_MMA_MAX_TERMS.
  * Densities that leave [2^-126, 2^127) (zero, negative, NaN, inf ...) are re-evaluated with the
  * reference's nansum / outlier semantics from wterm / term_source / mus (likelihood.py:686-689).
  */
 #define BI_MMA_MAX_TERMS 128
 int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t n_events,
                              int32_t n_terms, int32_t n_sources,
-                             const int32_t* group_points_dev, const int32_t* groups_dev, int32_t* header_dev,
+                             const int32_t* group_points_dev, int32_t* groups_dev, int32_t* header_dev,
                              const int32_t* row_dev, const double* coef_dev, const double* wterm_dev,
                              const int32_t* term_source_dev, const double* mus_dev,
                              double outlier_likelihood, double* partial_dev, void* stream);
