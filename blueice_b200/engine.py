@@ -281,6 +281,7 @@ class UnbinnedEngine(_EngineBase):
         self.ld = 0
         self.ps_anchor = None
         self.force_kernel = None      # None (auto) | 'stream' | 'grouped'  (tests / bench)
+        self._fused_cache = {}        # batch size -> staging buffers, workspace, prebuilt C arguments
 
     # -- set_data -------------------------------------------------------------------------------
     def allocate_ps_anchor(self, n_events):
@@ -391,22 +392,94 @@ class UnbinnedEngine(_EngineBase):
         """The [n_rows, ld] per-event pdf matrix K2 contracts (the anchor tensor viewed as rows)."""
         return self.ps_anchor
 
+    def _fused_args(self, P, zs_d, mult_d, scale_d, eff_d, ws, out):
+        """(C function, argument tuple) of the fused call for these device buffers."""
+        return self.lib.bi_unbinned_ll_batch, (
+            self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat),
+            self.n_sources, P, _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
+            _cabi.dev_ptr(self.mus_anchor), _cabi.host_ptr(self.allow_negative),
+            _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, self.outlier_likelihood, _MMA_TARGET_UNITS,
+            _cabi.dev_ptr(ws), ws.numel(), _cabi.dev_ptr(out["logl"]), _cabi.dev_ptr(out["logsum"]),
+            _cabi.dev_ptr(out["musum"]), _cabi.dev_ptr(out["status"]))
+
     def run_fused(self, P, zs_d, mult_d, scale_d, eff_d):
         """ONE C-ABI call: K1 -> device schedule -> K2 (DMMA) -> finalize.  Returns dict of device outputs."""
         torch = self.torch
         ws, _ = self.mma_workspace(P)
         out = dict(logl=self.ws.get("logl", P, torch.float64), logsum=self.ws.get("logsum", P, torch.float64),
                    musum=self.ws.get("musum", P, torch.float64), status=self.ws.get("status", P, torch.int32))
-        rc = self.lib.bi_unbinned_ll_batch(
-            self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat),
-            self.n_sources, P, _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
-            _cabi.dev_ptr(self.mus_anchor), _cabi.host_ptr(self.allow_negative),
-            _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, self.outlier_likelihood, _MMA_TARGET_UNITS,
-            _cabi.dev_ptr(ws), ws.numel(), _cabi.dev_ptr(out["logl"]), _cabi.dev_ptr(out["logsum"]),
-            _cabi.dev_ptr(out["musum"]), _cabi.dev_ptr(out["status"]), self._stream())
-        _cabi.check(rc, "bi_unbinned_ll_batch")
+        fn, args = self._fused_args(P, zs_d, mult_d, scale_d, eff_d, ws, out)
+        _cabi.check(fn(*args, self._stream()), fn.__name__)
         self.launches += 4 if self.n_super > 0 else 2
         return out
+
+    def _fused_state(self, P, has_scale, has_eff):
+        """Everything the e2e fast path needs for a P-point batch, built once and reused while the dataset stays:
+        pinned staging buffers both ways, device input / output buffers, the workspace and the prebuilt C arguments."""
+        key = (P, has_scale, has_eff, self.n_events, self.ps_anchor.data_ptr())
+        st = self._fused_cache.get(key)
+        if st is not None:
+            return st
+        torch = self.torch
+        D, S = self.grid.n_dims, self.n_sources
+        n_in = P * D + P * S + (P if has_scale else 0) + (P * S if has_eff else 0)
+        st = {}
+        st["pin_in"] = torch.empty(max(n_in, 1), dtype=torch.float64, pin_memory=True)
+        st["pin_in_np"] = st["pin_in"].numpy()
+        st["dev_in"] = torch.empty(max(n_in, 1), dtype=torch.float64, device=self.device)
+        o = 0
+        views = []
+        for n in (P * D, P * S, P if has_scale else 0, P * S if has_eff else 0):
+            views.append(st["dev_in"][o:o + n] if n else None)
+            o += n
+        st["n_in"] = n_in
+        off = np.zeros(14, dtype=np.int64)
+        _cabi.check(self.lib.bi_unbinned_workspace_layout(D, S, self.n_terms, P, self.n_events, _cabi.host_ptr(off)),
+                    "bi_unbinned_workspace_layout")
+        st["ws"] = torch.empty(int(off[13]), dtype=torch.uint8, device=self.device)
+        st["out_f"] = torch.empty(3 * P, dtype=torch.float64, device=self.device)      # logl | logsum | musum
+        st["out_i"] = torch.empty(P, dtype=torch.int32, device=self.device)
+        st["pin_f"] = torch.empty(3 * P, dtype=torch.float64, pin_memory=True)
+        st["pin_i"] = torch.empty(P, dtype=torch.int32, pin_memory=True)
+        st["pin_f_np"], st["pin_i_np"] = st["pin_f"].numpy(), st["pin_i"].numpy()
+        out = dict(logl=st["out_f"][:P], logsum=st["out_f"][P:2 * P], musum=st["out_f"][2 * P:], status=st["out_i"])
+        st["fn"], st["args"] = self._fused_args(P, views[0], views[1], views[2], views[3], st["ws"], out)
+        if len(self._fused_cache) >= 8:
+            self._fused_cache.clear()
+        self._fused_cache[key] = st
+        return st
+
+    def evaluate_fused(self, zs, mult, scale, eff, return_status, return_parts):
+        """The e2e path of the fused engine: stage -> H2D -> one C call -> D2H -> sync."""
+        P = len(mult)
+        st = self._fused_state(P, scale is not None, eff is not None)
+        pin = st["pin_in_np"]
+        o = 0
+        D, S = self.grid.n_dims, self.n_sources
+        for arr, size in ((zs, P * D), (mult, P * S), (scale, P), (eff, P * S)):
+            if arr is not None:
+                a = np.asarray(arr, dtype=np.float64).reshape(-1)
+                if a.size != size:
+                    raise ValueError("batch input has %d values, expected %d" % (a.size, size))
+                pin[o:o + size] = a
+                o += size
+        stream = self.torch.cuda.current_stream(self.device)
+        if st["n_in"]:
+            st["dev_in"].copy_(st["pin_in"], non_blocking=True)
+        _cabi.check(st["fn"](*st["args"], ctypes.c_void_p(stream.cuda_stream)), "bi_unbinned_ll_batch")
+        self.launches += 4 if self.n_super > 0 else 2
+        n_f = 3 * P if return_parts else P
+        st["pin_f"][:n_f].copy_(st["out_f"][:n_f], non_blocking=True)
+        st["pin_i"].copy_(st["out_i"], non_blocking=True)
+        stream.synchronize()
+        self.last_h2d_bytes = st["n_in"] * 8
+        self.last_d2h_bytes = n_f * 8 + P * 4
+        res = st["pin_f_np"]
+        if return_parts:
+            return res[P:2 * P].copy(), res[2 * P:3 * P].copy(), st["pin_i_np"].copy()
+        if return_status:
+            return res[:P].copy(), st["pin_i_np"].copy()
+        return res[:P].copy()
 
     def upload_plan(self, plan):
         """H2D of the schedule (one pinned buffer).  Returns device views + byte count."""
@@ -480,6 +553,10 @@ class UnbinnedEngine(_EngineBase):
             if return_parts:
                 return np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int32)
             return (np.zeros(0), np.zeros(0, dtype=np.int32)) if return_status else np.zeros(0)
+        if self.ps_anchor is None:
+            raise RuntimeError("set_ps_anchor / allocate_ps_anchor must be called first")
+        if self.uses_mma():
+            return self.evaluate_fused(zs, mult, scale, eff, return_status, return_parts)
         zs = np.asarray(zs, dtype=np.float64).reshape(P, self.grid.n_dims)
         plan = self.plan(zs)
         zs_d, mult_d, scale_d, eff_d, nbytes = self._upload_points(zs, mult, scale, eff)
@@ -597,22 +674,15 @@ class SourcewiseUnbinnedEngine(UnbinnedEngine):
         _cabi.check(rc, "bi_point_setup_sourcewise")
         self.launches += 1
 
-    def run_fused(self, P, zs_d, mult_d, scale_d, eff_d):
-        torch = self.torch
-        ws, _ = self.mma_workspace(P)
-        out = dict(logl=self.ws.get("logl", P, torch.float64), logsum=self.ws.get("logsum", P, torch.float64),
-                   musum=self.ws.get("musum", P, torch.float64), status=self.ws.get("status", P, torch.int32))
-        rc = self.lib.bi_unbinned_ll_batch_sourcewise(
+    def _fused_args(self, P, zs_d, mult_d, scale_d, eff_d, ws, out):
+        return self.lib.bi_unbinned_ll_batch_sourcewise, (
             self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat),
             self.n_sources, _cabi.host_ptr(self.dim_mask), _cabi.host_ptr(self.row_base), P,
             _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
             _cabi.dev_ptr(self.mus_rows), _cabi.host_ptr(self.allow_negative),
             _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, self.outlier_likelihood, _MMA_TARGET_UNITS,
             _cabi.dev_ptr(ws), ws.numel(), _cabi.dev_ptr(out["logl"]), _cabi.dev_ptr(out["logsum"]),
-            _cabi.dev_ptr(out["musum"]), _cabi.dev_ptr(out["status"]), self._stream())
-        _cabi.check(rc, "bi_unbinned_ll_batch_sourcewise")
-        self.launches += 4 if self.n_super > 0 else 2
-        return out
+            _cabi.dev_ptr(out["musum"]), _cabi.dev_ptr(out["status"]))
 
     def _setup_views(self, zs, mult, scale, eff):
         torch = self.torch
