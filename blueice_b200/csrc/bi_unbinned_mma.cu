@@ -6,12 +6,54 @@ static int bi_mma_k4(int K) {
     return k4 <= 8 ? k4 : (k4 <= 12 ? 12 : (k4 <= 16 ? 16 : (k4 <= 24 ? 24 : 32)));
 }
 
+// Tensor map of the anchor tensor [n_1]..[n_D][S][ld] (innermost first: events, sources, last shape parameter ...)
+// with a box of one event tile x all sources x the 2 anchors per shape parameter of a hypercube cell.
+// Returns the rank (0: not applicable / encoder unavailable -> per-row bulk copies).
+static int bi_make_tensor_map(CUtensorMap* tmap, const double* rows, int64_t ld, int32_t S, int32_t n_dims,
+                              const int32_t* n_anchors_host, int row_stride) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &status) == cudaSuccess &&
+            status == cudaDriverEntryPointSuccess)
+            encode = (encode_fn)fn;
+        looked_up = true;
+    }
+    if (!encode || n_dims < 0 || n_dims > 3 || S > 256) return 0;
+    const int rank = n_dims + 2;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    dims[0] = (cuuint64_t)ld;  box[0] = (cuuint32_t)row_stride;
+    dims[1] = (cuuint64_t)S;   box[1] = (cuuint32_t)S;
+    strides[0] = (cuuint64_t)ld * sizeof(double);
+    cuuint64_t stride = strides[0] * (cuuint64_t)S;
+    for (int d = 0; d < n_dims; ++d) {                   // tensor dim 2 + d = shape parameter n_dims - 1 - d
+        dims[2 + d] = (cuuint64_t)n_anchors_host[n_dims - 1 - d];
+        box[2 + d] = 2;
+        strides[1 + d] = stride;
+        stride *= dims[2 + d];
+    }
+    for (int i = 0; i < rank - 1; ++i)
+        if (strides[i] % 16 || strides[i] >= ((cuuint64_t)1 << 40)) return 0;
+    const CUresult res = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, (void*)rows, dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return res == CUDA_SUCCESS ? rank : 0;
+}
+
 extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t n_events,
                                         int32_t n_terms, int32_t n_sources,
                                         const int32_t* group_points_dev, int32_t* groups_dev, int32_t* header_dev,
                                         const int32_t* row_dev, const double* coef_dev, const double* wterm_dev,
                                         const int32_t* term_source_dev, const double* mus_dev,
-                                        double outlier_likelihood, double* partial_dev, void* stream) {
+                                        double outlier_likelihood, double* partial_dev,
+                                        int32_t grid_dims, const int32_t* n_anchors_host, const int32_t* cell_dev,
+                                        void* stream) {
     BI_REQUIRE(n_events >= 0, "n_events < 0");
     const int64_t n_super = bi_num_superblocks(n_events);
     if (n_super == 0) return BI_OK;
@@ -24,13 +66,23 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
     BI_REQUIRE(n_sources >= 1 && n_sources <= BI_MAX_SOURCES, "n_sources=%d outside [1,%d]", n_sources, BI_MAX_SOURCES);
     BI_REQUIRE(n_terms >= 1 && n_terms <= BI_MMA_MAX_TERMS, "bi_unbinned_partials_mma supports 1..%d contraction terms (got %d)",
                BI_MMA_MAX_TERMS, n_terms);
+    BI_REQUIRE(grid_dims < 0 || (grid_dims <= BI_MAX_DIMS && (grid_dims == 0 || (n_anchors_host && cell_dev))),
+               "bi_unbinned_partials_mma: grid_dims needs n_anchors_host and cell_dev");
     cudaStream_t st = (cudaStream_t)stream;
+    const int k4 = bi_mma_k4(n_terms);
+    // full-grid layout ([G][S][ld], term k = corner * S + source): one tiled TMA instruction per event tile
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int tmap_rank = 0;
+    if (grid_dims >= 0 && k4 <= 8 && n_terms == (n_sources << grid_dims) && ld_events < ((int64_t)1 << 31))
+        tmap_rank = bi_make_tensor_map(&tmap, rows_dev, ld_events, n_sources, grid_dims, n_anchors_host, bi_mma_row_stride(k4));
 #define BI_MMA_CASE(KK)                                                                                          \
     case KK:                                                                                                     \
         return bi_launch_mma<KK>(rows_dev, ld_events, n_events, n_terms, n_sources, group_points_dev, groups_dev, \
                                  header_dev, n_super, row_dev, coef_dev, wterm_dev, term_source_dev, mus_dev,    \
-                                 outlier_likelihood, partial_dev, st);
-    switch (bi_mma_k4(n_terms)) {
+                                 outlier_likelihood, partial_dev, tmap, tmap_rank, cell_dev,                     \
+                                 grid_dims > 0 ? grid_dims : 0, st);
+    switch (k4) {
         BI_MMA_CASE(1) BI_MMA_CASE(2) BI_MMA_CASE(3) BI_MMA_CASE(4)
         BI_MMA_CASE(5) BI_MMA_CASE(6) BI_MMA_CASE(7) BI_MMA_CASE(8)
         BI_MMA_CASE(12) BI_MMA_CASE(16) BI_MMA_CASE(24) BI_MMA_CASE(32)
@@ -95,7 +147,7 @@ extern "C" int bi_unbinned_workspace_layout(int32_t n_dims, int32_t n_sources, i
 }
 
 // shared tail of the fused calls: schedule -> K2 -> finalize on a workspace whose K1 regions are filled
-static int bi_unbinned_after_setup(int32_t n_dims, const int32_t* n_anchors_host, int32_t n_sources, int32_t n_terms,
+static int bi_unbinned_after_setup(int32_t n_dims, const int32_t* n_anchors_host, bool full_grid, int32_t n_sources, int32_t n_terms,
                                    int64_t n_points, const double* rows_dev, int64_t ld_events, int64_t n_events,
                                    double outlier_likelihood, int32_t target_units, char* base,
                                    const BiUnbinnedWorkspace& w, double* logl_dev, double* logsum_dev,
@@ -112,7 +164,8 @@ static int bi_unbinned_after_setup(int32_t n_dims, const int32_t* n_anchors_host
                                       (int32_t*)(base + w.group_points), (int32_t*)(base + w.groups),
                                       (int32_t*)(base + w.header), (int32_t*)(base + w.row), (double*)(base + w.coef),
                                       (double*)(base + w.wterm), (int32_t*)(base + w.term_source),
-                                      (double*)(base + w.mus), outlier_likelihood, partial, stream);
+                                      (double*)(base + w.mus), outlier_likelihood, partial,
+                                      full_grid ? n_dims : -1, n_anchors_host, (int32_t*)(base + w.cell), stream);
         if (rc != BI_OK) return rc;
     }
     return bi_unbinned_finalize(partial, n_super, musum_dev, status_dev, n_points, logl_dev, logsum_dev, stream);
@@ -145,7 +198,7 @@ extern "C" int bi_unbinned_ll_batch(int32_t n_dims, const int32_t* n_anchors_hos
                             (double*)(base + w.mus), musum_dev, status_dev, (int32_t*)(base + w.row),
                             (double*)(base + w.coef), (double*)(base + w.wterm), (int32_t*)(base + w.term_source), stream);
     if (rc != BI_OK) return rc;
-    return bi_unbinned_after_setup(n_dims, n_anchors_host, n_sources, K, n_points, ps_anchor_dev, ld_events, n_events,
+    return bi_unbinned_after_setup(n_dims, n_anchors_host, true, n_sources, K, n_points, ps_anchor_dev, ld_events, n_events,
                                    outlier_likelihood, target_units, base, w, logl_dev, logsum_dev, musum_dev,
                                    status_dev, stream);
 }
@@ -179,7 +232,7 @@ extern "C" int bi_unbinned_ll_batch_sourcewise(int32_t n_dims, const int32_t* n_
                                        (double*)(base + w.coef), (double*)(base + w.wterm),
                                        (int32_t*)(base + w.term_source), stream);
     if (rc != BI_OK) return rc;
-    return bi_unbinned_after_setup(n_dims, n_anchors_host, n_sources, K, n_points, rows_dev, ld_events, n_events,
+    return bi_unbinned_after_setup(n_dims, n_anchors_host, false, n_sources, K, n_points, rows_dev, ld_events, n_events,
                                    outlier_likelihood, target_units, base, w, logl_dev, logsum_dev, musum_dev,
                                    status_dev, stream);
 }

@@ -34,6 +34,8 @@
 //                partial = fma(E, LN2_LO, fma(E, LN2_HI, log(M))) + L           -> ONE log per 512 events
 //   events >= N count as p = 1 (exact identity).
 #pragma once
+#include <cuda.h>          // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
+
 #include "bi_common.cuh"
 
 #define BI_GROUP_EVENTS 32
@@ -101,6 +103,25 @@ __device__ __forceinline__ void bi_bulk_g2s(void* dst_smem, const void* src_gmem
                  "l"(src_gmem), "r"(bytes), "r"(bi_smem_u32(bar))
                  : "memory");
 }
+// tiled TMA copy of one whole event tile: box [T + 4 events][S sources][2 anchors per shape parameter ...] of the
+// anchor tensor viewed as [ld][S][n_D]...[n_1] -> K = S * 2^D dense rows of T + 4 doubles (SASS: UTMALDG)
+__device__ __forceinline__ void bi_tensor_g2s(void* dst_smem, const CUtensorMap* tmap, int rank, int c0, int c2, int c3,
+                                              int c4, uint64_t* bar) {
+    const uint32_t dst = bi_smem_u32(dst_smem), mb = bi_smem_u32(bar);
+    const uint64_t tm = reinterpret_cast<uint64_t>(tmap);
+    if (rank == 4)
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                     ::"r"(dst), "l"(tm), "r"(c0), "r"(0), "r"(c2), "r"(c3), "r"(mb) : "memory");
+    else if (rank == 3)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(dst), "l"(tm), "r"(c0), "r"(0), "r"(c2), "r"(mb) : "memory");
+    else if (rank == 5)
+        asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                     ::"r"(dst), "l"(tm), "r"(c0), "r"(0), "r"(c2), "r"(c3), "r"(c4), "r"(mb) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(dst), "l"(tm), "r"(c0), "r"(0), "r"(mb) : "memory");
+}
 // D(8x8) += A(8x4, row) * B(4x8, col); thread (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
 __device__ __forceinline__ void bi_dmma(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -146,6 +167,10 @@ static __device__ __noinline__ double bi_slow_group(const double* grp, int rs, i
     return __dadd_rn(quad[0], quad[1]);
 }
 
+// warp-private producer cursor (shared memory): the range whose tiles are being issued, the next tile of it,
+// and the range the producer has fetched ahead of the consumer (one range of lookahead)
+struct BiProducer { int range, tile, n_tiles, pending, c2, c3, c4, pad; };   // c2..c4: cell coordinates (tensor-map TMA)
+
 // ---------------------------------------------------------------------------------------------
 // producer step (whole warp): arm the stage's barrier and issue the K row copies of tile `tile_idx`.
 // K <= 32: src_row = this lane's row (k = lane) at event 0; otherwise rows are looked up in row_lead[K].
@@ -153,9 +178,21 @@ static __device__ __noinline__ double bi_slow_group(const double* grp, int rs, i
 template <int K4>
 __device__ __forceinline__ void bi_mma_issue(const double* __restrict__ A, const double* __restrict__ src_row,
                                              const int32_t* __restrict__ row_lead, int64_t ld, int64_t ev_begin,
-                                             int tile_idx, int st, int K, double* ring, uint64_t* full_bar, int lane) {
+                                             int tile_idx, int st, int K, double* ring, uint64_t* full_bar,
+                                             const CUtensorMap* tmap, int tmap_rank, const BiProducer* prod, int lane) {
     using Cfg = BiMmaCfg<K4>;
     const int64_t ev = ev_begin + (int64_t)tile_idx * Cfg::T;
+    double* dst = ring + (size_t)st * Cfg::STAGE_DOUBLES;
+    if (tmap_rank) {
+        // ONE tiled TMA instruction per tile; out-of-range columns are zero-filled and count as transferred bytes
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bi_mbar_expect_tx(&full_bar[st], (unsigned)(K * Cfg::RS * sizeof(double)));
+            bi_tensor_g2s(dst, tmap, tmap_rank, (int)ev, prod->c2, prod->c3, prod->c4, &full_bar[st]);
+        }
+        __syncwarp();
+        return;
+    }
     const int64_t left = ld - ev;
     const unsigned bytes = (unsigned)(left < Cfg::T ? left : Cfg::T) * (unsigned)sizeof(double);
     if (lane == 0) {
@@ -164,7 +201,6 @@ __device__ __forceinline__ void bi_mma_issue(const double* __restrict__ A, const
         bi_mbar_expect_tx(&full_bar[st], bytes * (unsigned)K);
     }
     __syncwarp();
-    double* dst = ring + (size_t)st * Cfg::STAGE_DOUBLES;
     if (Cfg::ROWREG) {
         if (lane < K) bi_bulk_g2s(dst + (size_t)lane * Cfg::RS, src_row + ev, bytes, &full_bar[st]);
     } else {
@@ -264,10 +300,6 @@ __device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, in
 // ---------------------------------------------------------------------------------------------
 // one work unit with NMT m-tiles: coefficients -> registers, then the tile loop
 // ---------------------------------------------------------------------------------------------
-// warp-private producer cursor (shared memory): the range whose tiles are being issued, the next tile of it,
-// and the range the producer has fetched ahead of the consumer (one range of lookahead)
-struct BiProducer { int range, tile, n_tiles, pending; };
-
 template <int K4>
 __device__ __forceinline__ int bi_range_tiles(int range, int sb_per, int64_t n_super, int64_t N) {
     const int64_t sb0 = (int64_t)range * sb_per;
@@ -292,7 +324,8 @@ template <int K4>
 __device__ __forceinline__ void bi_mma_produce(BiProducer* prod, int* counter, int n_ranges, int sb_per, int64_t n_super,
                                                const double* __restrict__ A, const double* __restrict__ src_row,
                                                const int32_t* __restrict__ row_lead, int64_t ld, int64_t N, int K,
-                                               double* ring, uint64_t* full_bar, unsigned& issued, int lane) {
+                                               double* ring, uint64_t* full_bar, const CUtensorMap* tmap, int tmap_rank,
+                                               unsigned& issued, int lane) {
     using Cfg = BiMmaCfg<K4>;
     int pr = prod->range;
     if (pr < 0) return;
@@ -311,7 +344,7 @@ __device__ __forceinline__ void bi_mma_produce(BiProducer* prod, int* counter, i
         if (pr < 0) return;
     }
     bi_mma_issue<K4>(A, src_row, row_lead, ld, (int64_t)pr * sb_per * BI_SUPERBLOCK, pt, (int)(issued % Cfg::STAGES), K,
-                     ring, full_bar, lane);
+                     ring, full_bar, tmap, tmap_rank, prod, lane);
     ++issued;
     if (lane == 0) prod->tile = pt + 1;
     __syncwarp();
@@ -330,6 +363,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
                                             const double* __restrict__ wterm, const double* __restrict__ mus,
                                             double outlier, double* __restrict__ partial,
                                             double* ring, uint64_t* full_bar, double* slow_acc, BiProducer* prod,
+                                            const CUtensorMap* tmap, int tmap_rank,
                                             unsigned& issued, unsigned& consumed, int lane) {
     using Cfg = BiMmaCfg<K4>;
     constexpr int T = Cfg::T;
@@ -346,7 +380,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
     __syncwarp();
     // the first tiles are in flight while the coefficients are gathered
     for (int i = 0; i < Cfg::STAGES; ++i)
-        bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar, issued, lane);
+        bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar, tmap, tmap_rank, issued, lane);
 
     double a[NMT][K4];
 #pragma unroll
@@ -399,7 +433,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
             __syncwarp();
             ++consumed;
             bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar,
-                               issued, lane);
+                               tmap, tmap_rank, issued, lane);
         }
         // ---- close the superblock: combine the four classes, one log per point
         const bool any_slow = __any_sync(BI_FULL_MASK, slow_any);
@@ -447,7 +481,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
     }
     // ---- next range: the one the producer has already fetched (its first tiles are in flight)
     if (prod->pending < 0 && prod->range >= 0)
-        bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar, issued, lane);
+        bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar, tmap, tmap_rank, issued, lane);
     cur = prod->pending;
     __syncwarp();
     if (cur >= 0) {
@@ -457,7 +491,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
                !(prod->tile == prod->n_tiles && prod->pending >= 0)) {
             const unsigned before = issued;
             bi_mma_produce<K4>(prod, counter, n_ranges, sb_per, n_super, A, src_row, row_lead, ld, N, K, ring, full_bar,
-                               issued, lane);
+                               tmap, tmap_rank, issued, lane);
             if (issued == before) break;
         }
     }
@@ -474,9 +508,10 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S
                const int32_t* __restrict__ group_points, int4* groups, int32_t* header,
                int64_t n_super, const int32_t* __restrict__ row, const double* __restrict__ coef,
                const double* __restrict__ wterm, const int32_t* __restrict__ term_source,
-               const double* __restrict__ mus, double outlier, double* __restrict__ partial) {
+               const double* __restrict__ mus, double outlier, double* __restrict__ partial,
+               const __grid_constant__ CUtensorMap tmap, int tmap_rank, const int32_t* __restrict__ cell, int n_dims) {
     using Cfg = BiMmaCfg<K4>;
-    constexpr int MT = Cfg::MT, T = Cfg::T;
+    constexpr int MT = Cfg::MT;
     extern __shared__ __align__(128) unsigned char bi_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2;
@@ -529,15 +564,27 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S
         const int64_t lead = slot_point[0];
         const int32_t* row_lead = row + lead * K;                  // every point of the group has these rows
         const double* src_row = A;
-        if (Cfg::ROWREG && lane < K) src_row = A + (int64_t)row_lead[lane] * ld;
+        if (Cfg::ROWREG && lane < K && !tmap_rank) src_row = A + (int64_t)row_lead[lane] * ld;
+        if (tmap_rank && lane == 0) {
+            // tensor coordinates of the group's hypercube cell, last shape parameter first (one-point axis: cell -1 -> 0)
+            int c[3] = {0, 0, 0};
+            for (int d = 0; d < n_dims; ++d) {
+                const int v = cell[lead * n_dims + (n_dims - 1 - d)];
+                c[d] = v < 0 ? 0 : v;
+            }
+            prod->c2 = c[0];
+            prod->c3 = c[1];
+            prod->c4 = c[2];
+        }
+        __syncwarp();
 
 #define BI_MMA_UNIT(NN)                                                                                              \
     case NN:                                                                                                         \
         if (NN <= MT)                                                                                                \
             bi_mma_unit<K4, (NN <= MT ? NN : 1)>(A, src_row, row_lead, ld, N, K, S, slot_point, active_mask, lead,   \
                                                  counter, n_ranges, sb_per, n_super, coef, term_source, wterm, mus,  \
-                                                 outlier, partial, ring, full_bar, slow_acc, prod, issued, consumed, \
-                                                 lane);                                                              \
+                                                 outlier, partial, ring, full_bar, slow_acc, prod, &tmap, tmap_rank, \
+                                                 issued, consumed, lane);                                            \
         break;
         switch (n_mt) {
             BI_MMA_UNIT(1) BI_MMA_UNIT(2) BI_MMA_UNIT(3) BI_MMA_UNIT(4)
@@ -570,14 +617,25 @@ template <int K4>
 static int bi_launch_mma(const double* A, int64_t ld, int64_t N, int K, int S, const int32_t* group_points,
                          int32_t* groups, int32_t* header, int64_t n_super, const int32_t* row, const double* coef,
                          const double* wterm, const int32_t* term_source, const double* mus, double outlier,
-                         double* partial, cudaStream_t st) {
+                         double* partial, const CUtensorMap& tmap, int tmap_rank, const int32_t* cell, int n_dims,
+                         cudaStream_t st) {
     using Cfg = BiMmaCfg<K4>;
     int blocks = 0;
     int rc = bi_mma_grid<K4>(&blocks);
     if (rc != BI_OK) return rc;
     k_unbinned_mma<K4><<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
         A, ld, N, K, S, group_points, reinterpret_cast<int4*>(groups), header, n_super, row, coef, wterm,
-        term_source, mus, outlier, partial);
+        term_source, mus, outlier, partial, tmap, tmap_rank, cell, n_dims);
     BI_LAUNCH_CHECK();
     return BI_OK;
+}
+
+// events per tile row of the K4 instantiation (box inner size of the tensor map)
+static int bi_mma_row_stride(int k4) {
+    switch (k4) {
+        case 1: return BiMmaCfg<1>::RS;  case 2: return BiMmaCfg<2>::RS;  case 3: return BiMmaCfg<3>::RS;
+        case 4: return BiMmaCfg<4>::RS;  case 5: return BiMmaCfg<5>::RS;  case 6: return BiMmaCfg<6>::RS;
+        case 7: return BiMmaCfg<7>::RS;  case 8: return BiMmaCfg<8>::RS;  case 12: return BiMmaCfg<12>::RS;
+        case 16: return BiMmaCfg<16>::RS; case 24: return BiMmaCfg<24>::RS; default: return BiMmaCfg<32>::RS;
+    }
 }

@@ -282,6 +282,7 @@ class UnbinnedEngine(_EngineBase):
         self.ps_anchor = None
         self.force_kernel = None      # None (auto) | 'stream' | 'grouped'  (tests / bench)
         self._fused_cache = {}        # batch size -> staging buffers, workspace, prebuilt C arguments
+        self.full_grid_layout = os.environ.get('BI_MMA_NO_TENSORMAP') is None   # rows = [G][S][ld] anchor tensor
 
     # -- set_data -------------------------------------------------------------------------------
     def allocate_ps_anchor(self, n_events):
@@ -386,7 +387,9 @@ class UnbinnedEngine(_EngineBase):
             _cabi.dev_ptr(views["group_points"]), _cabi.dev_ptr(views["groups"]), _cabi.dev_ptr(views["header"]),
             _cabi.dev_ptr(views["row"]), _cabi.dev_ptr(views["coef"]), _cabi.dev_ptr(views["wterm"]),
             _cabi.dev_ptr(views["term_source"]), _cabi.dev_ptr(views["mus"]), self.outlier_likelihood,
-            _cabi.dev_ptr(views["partial"]), self._stream()), "bi_unbinned_partials_mma")
+            _cabi.dev_ptr(views["partial"]), self.grid.n_dims if self.full_grid_layout else -1,
+            _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.dev_ptr(views["cell"]), self._stream()),
+            "bi_unbinned_partials_mma")
 
     def rows_tensor(self):
         """The [n_rows, ld] per-event pdf matrix K2 contracts (the anchor tensor viewed as rows)."""
@@ -622,6 +625,7 @@ class SourcewiseUnbinnedEngine(UnbinnedEngine):
         super().__init__(grid, np.zeros((grid.n_anchors, n_sources)), outlier_likelihood, allow_negative, device)
         self.mus_rows_host = mus_rows
         self.mus_rows = self.torch.from_numpy(mus_rows).to(self.device)
+        self.full_grid_layout = False
         self.copy_source = self.torch.from_numpy(
             np.array([len(d) == 0 for d in self.source_dims], dtype=np.uint8)).to(self.device)
         self._n_terms = int(self.lib.bi_sourcewise_terms(n_sources, _cabi.host_ptr(self.dim_mask)))

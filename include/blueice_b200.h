@@ -190,6 +190,10 @@ int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_po
  *   group_points_dev / groups_dev / header_dev as written by bi_unbinned_plan (or by the caller: all
  *   points of a group MUST share their row list, have status 0, and count <= bi_mma_unit_points(n_terms);
  *   header_dev[4] and every group's range counter must be 0 on entry).  Requires n_terms <= BI_MMA_MAX_TERMS.
+ * grid_dims >= 0 declares the full-grid layout (rows_dev = [G][S][ld] anchor tensor over grid_dims shape
+ * parameters with n_anchors_host anchors each, term k = corner * S + source, cell_dev = bi_point_setup's cells):
+ * event tiles are then fetched with ONE tiled TMA instruction (tensor map over [ld][S][n_D]..[n_1], grid_dims <= 3)
+ * instead of one bulk copy per row.  grid_dims = -1: arbitrary row lists (source-wise interpolation).
  * Densities that leave [2^-126, 2^127) (zero, negative, NaN, inf ...) are re-evaluated with the
  * reference's nansum / outlier semantics from wterm / term_source / mus (likelihood.py:686-689).
  */
@@ -199,7 +203,8 @@ int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t 
                              const int32_t* group_points_dev, int32_t* groups_dev, int32_t* header_dev,
                              const int32_t* row_dev, const double* coef_dev, const double* wterm_dev,
                              const int32_t* term_source_dev, const double* mus_dev,
-                             double outlier_likelihood, double* partial_dev, void* stream);
+                             double outlier_likelihood, double* partial_dev,
+                             int32_t grid_dims, const int32_t* n_anchors_host, const int32_t* cell_dev, void* stream);
 int32_t bi_mma_unit_points(int32_t n_terms);
 
 /*
