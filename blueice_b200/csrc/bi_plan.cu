@@ -117,14 +117,12 @@ k_plan_units(const __grid_constant__ BiPlanDims dims, int n_cells, int64_t n_poi
         }
     }
     if (tid == 0) {
-        // range length: short units (dynamic scheduling evens out the tail) but never lighter than about one
-        // full unit x one superblock, so a sparse batch (few points per cell, HBM-bound) streams long ranges
+        // range length: as short as the unit budget allows -- warps stick to a group and stream its ranges
+        // back to back, so a short range costs nothing and evens out the tail
         int64_t sb_per = 1, n_ranges = 0, n_units = 0;
         if (n_groups > 0 && n_super > 0) {
-            const int avg_mt = (((n_evaluable + 7) >> 3) + n_groups - 1) / n_groups;
-            const int64_t min_sb = (tiles_per_unit + max(avg_mt, 2) - 1) / max(avg_mt, 2);
             sb_per = (n_super * (int64_t)n_groups + target_units - 1) / target_units;
-            if (sb_per < min_sb) sb_per = min_sb;
+            if (sb_per < 1) sb_per = 1;
             if (sb_per > n_super) sb_per = n_super;
             n_ranges = (n_super + sb_per - 1) / sb_per;
             n_units = n_ranges * n_groups;

@@ -538,17 +538,17 @@ k_unbinned_mma(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S
 
     for (;;) {
         // a point group with superblock ranges left: start at a ticket (spreads the warps over the groups), then scan
-        int grp = 0;
-        if (lane == 0) {
-            grp = (int)((unsigned)atomicAdd(&header[4], 1) % (unsigned)n_groups);
-            int tries = 0;
-            while (tries < n_groups && *reinterpret_cast<volatile int*>(&groups[grp].z) >= n_ranges) {
-                grp = grp + 1 == n_groups ? 0 : grp + 1;
-                ++tries;
-            }
-            if (tries == n_groups) grp = -1;
+        int start = 0;
+        if (lane == 0) start = (int)((unsigned)atomicAdd(&header[4], 1) % (unsigned)n_groups);
+        start = __shfl_sync(BI_FULL_MASK, start, 0);
+        int grp = -1;
+        for (int base = 0; base < n_groups && grp < 0; base += 32) {      // 32 groups per probe, one per lane
+            int cand = start + base + lane;
+            if (cand >= n_groups) cand -= n_groups;
+            const bool open = base + lane < n_groups && *reinterpret_cast<volatile int*>(&groups[cand].z) < n_ranges;
+            const unsigned vote = __ballot_sync(BI_FULL_MASK, open);
+            if (vote) grp = __shfl_sync(BI_FULL_MASK, cand, __ffs(vote) - 1);
         }
-        grp = __shfl_sync(BI_FULL_MASK, grp, 0);
         if (grp < 0) break;
         const int4 gp = groups[grp];
         const int n_pts = gp.y;

@@ -174,9 +174,9 @@ def plan_points(grid, zs, n_sources, n_super, force_kernel=None):
     return PointPlan(P, in_range, stream_pts.astype(np.int32), group_pts.astype(np.int32), work)
 
 
-# ~4 units per resident warp and full units + one remainder per cell (measured optimum on the config-2 scan);
+# up to ~32 (group, range) pairs per resident warp and full units + one remainder per cell (measured optimum);
 # bit 30 selects the full-units split, 0 = sizes balanced inside a cell
-_MMA_TARGET_UNITS = (int(os.environ.get('BI_MMA_TARGET_UNITS', 148 * 12 * 4))
+_MMA_TARGET_UNITS = (int(os.environ.get('BI_MMA_TARGET_UNITS', 148 * 12 * 32))
                      | (int(os.environ.get('BI_MMA_FULL_UNITS', '1')) << 30))
 _EMPTY_I32 = np.zeros(0, dtype=np.int32)
 
