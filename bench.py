@@ -154,12 +154,14 @@ class ClockSampler(object):
         self.sm_max = None
         self.error = None
 
-    def _run(self):
+    def prepare(self):
+        """NVML init + device handle (tens of ms): done before the timed region, not inside the sampling thread."""
         try:
             import pynvml
+            import torch
+            self.nvml = pynvml
             pynvml.nvmlInit()
             # honour CUDA_VISIBLE_DEVICES-style remapping by matching the PCI bus id of the torch device
-            import torch
             bus = torch.cuda.get_device_properties(self.gpu_index).pci_bus_id
             handle = None
             for i in range(pynvml.nvmlDeviceGetCount()):
@@ -168,22 +170,36 @@ class ClockSampler(object):
                     handle = h
             if handle is None:
                 handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.handle = handle
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:                                   # pragma: no cover
+            self.error = repr(exc)
+
+    def _sample(self):
+        pynvml, handle = self.nvml, self.handle
+        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+        mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+        for name, bit in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+        try:
+            self.power.append(pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0)
+        except Exception:
+            pass
+
+    def _run(self):
+        try:
             while not self.stop_flag.is_set():
-                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
-                mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
-                for name, bit in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                try:
-                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0)
-                except Exception:
-                    pass
-                time.sleep(0.004)
+                self._sample()
+                time.sleep(0.002)
         except Exception as exc:                                   # pragma: no cover
             self.error = repr(exc)
 
     def start(self):
+        if getattr(self, "handle", None) is None:
+            self.prepare()
+        if self.error:
+            return
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
@@ -191,6 +207,11 @@ class ClockSampler(object):
         self.stop_flag.set()
         if self.thread is not None:
             self.thread.join(timeout=5)
+            if not self.error:
+                try:
+                    self._sample()                                 # at least one sample right at the end of the region
+                except Exception as exc:                           # pragma: no cover
+                    self.error = repr(exc)
         out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
                "samples": len(self.samples), "reasons": sorted(self.reasons),
                "power_w_max": max(self.power) if self.power else None}
@@ -218,6 +239,7 @@ def run_own_arm(args):
     os.chdir(tempfile.mkdtemp(prefix="bi_bench_"))
 
     sampler = ClockSampler(local_rank)
+    sampler.prepare()
     # ---- build the workload through the public API (prepare + set_data are not part of a step) ----
     t0 = time.perf_counter()
     ll, d, names = wl.c2_api(N_SOURCES, N_SHAPE, ANCHORS, BINS, n_events=args.events, seed=1)
