@@ -61,6 +61,22 @@ SIGNATURES = {
                                       _i64, _c_void_p]),
     "bi_hist_lookup": (ctypes.c_int, [_c_void_p, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _i64, _i64,
                                       _i32, _c_void_p, _i64, _c_void_p, _c_void_p]),
+    "bi_template_prepare_events": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _c_void_p, _i64, _i64,
+                                                  _c_void_p, _c_void_p, _i64, _c_void_p]),
+    "bi_template_partials": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _c_void_p, _i32, _c_void_p, _c_void_p, _i64,
+                                            _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                            _c_void_p, _c_void_p, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _i64,
+                                            _c_void_p, _c_void_p, _f64, _c_void_p, _c_void_p]),
+    "bi_template_finalize": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p,
+                                            _c_void_p, _c_void_p]),
+    "bi_template_mix": (ctypes.c_int, [_c_void_p, _i64, _i64, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                       _i64, _c_void_p, _c_void_p]),
+    "bi_mixture_partials": (ctypes.c_int, [_c_void_p, _i32, _c_void_p, _i32, _c_void_p, _c_void_p, _i64, _c_void_p,
+                                           _c_void_p, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p,
+                                           _c_void_p, _f64, _c_void_p, _c_void_p]),
+    "bi_toy_counts": (ctypes.c_int, [_i32, _i64, _i64, _c_void_p, _i32, ctypes.c_uint64, _c_void_p, _c_void_p]),
+    "bi_toy_events": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _c_void_p, _i64, _i64, _c_void_p, _c_void_p,
+                                     _i64, ctypes.c_uint64, _c_void_p, _i64, _c_void_p, _c_void_p]),
     "bi_histogramdd": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _c_void_p, _i64, _i64, _c_void_p,
                                       _c_void_p, _c_void_p]),
     "bi_binned_scratch_doubles": (_i64, [_i64, _i64]),
@@ -88,6 +104,8 @@ GROUP_MAX_CORNERS = 16
 STREAM_MAX_CORNERS = 32
 MMA_MAX_TERMS = 128
 PLAN_MAX_CELLS = 16384
+TS_MAX_TERMS = 256
+TS_GROUP_POINTS = 8
 POINT_OUT_OF_RANGE = 1
 POINT_UNPHYSICAL = 2
 LOOKUP_LINEAR = 0

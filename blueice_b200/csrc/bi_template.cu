@@ -1,0 +1,652 @@
+// blueice_b200 -- K5: template-space unbinned likelihood (fused template lookup + morph + mixture + log + reduce)
+// over MANY datasets (toy Monte Carlos) or one dataset too large for a dense anchor tensor.
+//
+// The anchor-tensor form (K3 -> K2) materialises A[G, S, N] = HistogramPdfSource.pdf of every anchor model at every
+// event (blueice/likelihood.py:557-562) and contracts it per point.  That tensor is 3 TB for 1e6 toys x 1e3 events x
+// 125 anchors x 3 sources and for 1e8 events x 625 anchors x 6 sources.  Here the per-event values are never stored:
+//     A[row, i] = lookup(template[row], x_i)          -- source.py:219-246, scipy's operation order, as in K3
+//     f_i       = fma chain over k of A[row_k, i] * coef_k      -- as in K2 (bi_unbinned_mma.cuh)
+// evaluated on the fly from the L2-resident templates [n_rows, n_bins] and the prepared events
+// (low-corner bin + per-dimension fractions, computed once per dataset by bi_template_prepare_events).  Every
+// intermediate is formed by the same operations in the same order as K3 + K2, and the log-sum goes through the same
+// canonical product tree, so a (dataset, point) pair evaluates BIT-IDENTICALLY to
+// set_data(dataset) + ll(point) on the anchor-tensor engine.
+//
+// Work: a pair group = up to BI_TS_GROUP_POINTS points evaluated on one dataset that share their row list (same
+// hypercube cell): the template values of an event are gathered once and contracted with every point of the group.
+// A unit = (pair group, superblock of 512 events); one warp per unit, lane = event.
+#include "bi_space.cuh"
+
+#define BI_TS_THREADS 128
+#define BI_TS_WARPS (BI_TS_THREADS / 32)
+#define BI_RANGE_LO ((1023 - 126) << 20)
+#define BI_RANGE_SPAN (253u << 20)
+
+struct BiTsSpace {
+    int32_t n_space;
+    int32_t n_corner;                              // 2^n_space lookup corners (linear), 1 (piecewise)
+    int64_t corner_off[1 << BI_MAX_SPACE_DIMS];    // element offset of lookup corner c from the low corner, x bin_stride
+};
+
+// ---------------------------------------------------------------------------------------------
+// event preparation (once per dataset): coordinates -> low-corner bin + fractions
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_template_prepare(const __grid_constant__ BiSpace sp, const __grid_constant__ BiPoints pts, int n_points_total, int linear,
+                   const double* __restrict__ coords, int64_t ld_coords, int64_t n_events,
+                   int32_t* __restrict__ ev_bin, double* __restrict__ ev_frac, int64_t ld_frac) {
+    __shared__ double s_pts[BI_MAX_EDGE_POINTS];
+    bi_stage_points(pts, n_points_total, s_pts);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_events) return;
+    if (linear) {
+        int cell[BI_MAX_SPACE_DIMS];
+        double y[BI_MAX_SPACE_DIMS];
+        ev_bin[i] = bi_event_cell_linear(sp, s_pts, coords, ld_coords, i, cell, y);
+        for (int d = 0; d < sp.n_space; ++d) ev_frac[(int64_t)d * ld_frac + i] = y[d];
+    } else {
+        ev_bin[i] = bi_event_bin_piecewise(sp, s_pts, coords, ld_coords, i);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// template value of one row at one prepared event, scipy's operation order (== k_hist_lookup_linear)
+// ---------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ double bi_ts_lookup(const double* __restrict__ V, const BiTsSpace& sp, const double (&y)[NS > 0 ? NS : 1]) {
+    if constexpr (NS == 0) {
+        return __ldg(V);                                            // piecewise: the bin's value
+    } else if constexpr (NS == 2) {
+        // evaluate_linear_2d: r = 0; r += V00*(1-y0)*(1-y1); r += V01*(1-y0)*y1; r += V10*y0*(1-y1); r += V11*y0*y1
+        const double v00 = __ldg(V), v01 = __ldg(V + sp.corner_off[1]), v10 = __ldg(V + sp.corner_off[2]),
+                     v11 = __ldg(V + sp.corner_off[3]);
+        const double u0 = __dsub_rn(1.0, y[0]), u1 = __dsub_rn(1.0, y[1]);
+        const double y1 = y[1];
+        double r = 0.0;
+        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v00, u0), u1));
+        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v01, u0), y1));
+        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v10, y[0]), u1));
+        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v11, y[0]), y1));
+        return r;
+    } else {
+        // generic corner loop (_rgi.py:520-549): first dim slowest, weight = ((1*t0)*t1)..., value = value + V*weight
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < (1 << NS); ++c) {
+            double w = 1.0;
+#pragma unroll
+            for (int d = 0; d < NS; ++d) {
+                const int bit = (c >> (NS - 1 - d)) & 1;
+                w = __dmul_rn(w, bit ? y[d] : __dsub_rn(1.0, y[d]));
+            }
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(V + sp.corner_off[c]), w));
+        }
+        return acc;
+    }
+}
+
+// density of one event with the reference's semantics (likelihood.py:686-689), rare path
+template <int NS>
+static __device__ __noinline__ double bi_ts_slow_density(const double* __restrict__ T, const int64_t* rowoff, int64_t base,
+                                                         const BiTsSpace& sp, const double (&y)[NS > 0 ? NS : 1], int K, int S,
+                                                         const int32_t* __restrict__ term_source,
+                                                         const double* __restrict__ wterm,
+                                                         const double* __restrict__ mu, double outlier) {
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        double ps = 0.0;
+        for (int k = 0; k < K; ++k)
+            if (term_source[k] == s) ps = fma(bi_ts_lookup<NS>(T + rowoff[k] + base, sp, y), wterm[k], ps);
+        const double term = __dmul_rn(mu[s], ps);
+        if (term == term) acc = __dadd_rn(acc, term);               // nansum: NaN terms count as 0
+    }
+    return bi_fix_density(acc, outlier);
+}
+
+// pair group descriptor: pairs [first, first + count) of the pair list, all on dataset `dataset`
+struct BiTsGroup { int32_t first, count, dataset, pad; };
+
+// ---------------------------------------------------------------------------------------------
+// the kernel: one warp per unit (pair group, superblock), lane = event
+// ---------------------------------------------------------------------------------------------
+template <int NP, int NS>
+__global__ void __launch_bounds__(BI_TS_THREADS)
+k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bin_stride, const __grid_constant__ BiTsSpace sp,
+                    const int32_t* __restrict__ ev_bin, const double* __restrict__ ev_frac, int64_t ld_frac,
+                    const int64_t* __restrict__ dataset_offset, int K, int S,
+                    const int32_t* __restrict__ row, const double* __restrict__ coef, const double* __restrict__ wterm,
+                    const int32_t* __restrict__ term_source, const double* __restrict__ mus,
+                    const int32_t* __restrict__ status,
+                    int64_t n_groups, const BiTsGroup* __restrict__ groups, const int64_t* __restrict__ unit_offset,
+                    const int32_t* __restrict__ unit_group, int64_t n_units,
+                    const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
+                    double outlier, double* __restrict__ partial) {
+    constexpr int NY = NS > 0 ? NS : 1;
+    extern __shared__ __align__(16) unsigned char bi_ts_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // per warp: row offsets [K] (int64) + coefficients [NP][K]
+    int64_t* rowoff = reinterpret_cast<int64_t*>(bi_ts_smem) + (size_t)warp * (size_t)K * (1 + NP);
+    double* coef_s = reinterpret_cast<double*>(rowoff + K);
+    const int t_class = (lane >> 1) & 3;
+    const int64_t n_warps = (int64_t)gridDim.x * BI_TS_WARPS;
+
+    for (int64_t u = (int64_t)blockIdx.x * BI_TS_WARPS + warp; u < n_units; u += n_warps) {
+        // ---- unit -> (pair group, superblock)
+        int64_t g;
+        if (unit_group) g = unit_group[u];
+        else {                                                      // largest g with unit_offset[g] <= u
+            int64_t lo = 0, hi = n_groups;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (unit_offset[mid] <= u) lo = mid; else hi = mid;
+            }
+            g = lo;
+        }
+        const int64_t sb = u - unit_offset[g];
+        const BiTsGroup gp = groups[g];
+        const int np = gp.count < NP ? gp.count : NP;
+        // live points of the group (status 0); the row list comes from the first live one
+        int32_t point[NP];
+        unsigned live = 0;
+        int lead = -1;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            point[q] = q < np ? pair_point[gp.first + q] : 0;
+            if (q < np && status[point[q]] == 0) {
+                live |= 1u << q;
+                if (lead < 0) lead = q;
+            }
+        }
+        if (!live) continue;                                        // their results are -inf (finalize)
+        __syncwarp();
+        for (int k = lane; k < K; k += 32) {
+            rowoff[k] = (int64_t)row[(int64_t)point[lead] * K + k] * row_stride;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) coef_s[q * K + k] = coef[(int64_t)point[(live >> q) & 1u ? q : lead] * K + k];
+        }
+        __syncwarp();
+
+        const int64_t ev_begin = dataset_offset[gp.dataset] + sb * BI_SUPERBLOCK;
+        const int64_t left = dataset_offset[gp.dataset + 1] - ev_begin;
+        const int n_ev = left < BI_SUPERBLOCK ? (int)left : BI_SUPERBLOCK;
+
+        double M[NP], Lslow[NP];
+        int E[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { M[q] = 1.0; E[q] = 0; Lslow[q] = 0.0; }
+        bool any_slow = false;
+
+#pragma unroll 1
+        for (int e0 = 0; e0 < n_ev; e0 += BI_EVENT_BLOCK) {
+            const bool valid = e0 + lane < n_ev;
+            const int64_t ev = ev_begin + e0 + lane;
+            const int64_t base = valid ? (int64_t)ev_bin[ev] * bin_stride : 0;
+            double y[NY];
+#pragma unroll
+            for (int d = 0; d < NY; ++d) y[d] = (NS > 0 && valid) ? ev_frac[(int64_t)d * ld_frac + ev] : 0.0;
+
+            double p[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) p[q] = 0.0;
+#pragma unroll 2
+            for (int k = 0; k < K; ++k) {
+                const double r = bi_ts_lookup<NS>(T + rowoff[k] + base, sp, y);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) p[q] = fma(r, coef_s[q * K + k], p[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                if (!valid) p[q] = 1.0;                             // events >= N count as p = 1
+                const bool in_range = (unsigned)(__double2hiint(p[q]) - BI_RANGE_LO) < BI_RANGE_SPAN;
+                const unsigned bad = ~__ballot_sync(BI_FULL_MASK, in_range);
+                // canonical tree: pair (events 2j, 2j+1) -> quad (octets 0,1 / 2,3) -> oct; lanes of one class agree
+                double v = __dmul_rn(p[q], __shfl_xor_sync(BI_FULL_MASK, p[q], 1));
+                v = __dmul_rn(v, __shfl_xor_sync(BI_FULL_MASK, v, 8));
+                v = __dmul_rn(v, __shfl_xor_sync(BI_FULL_MASK, v, 16));
+                double m;
+                int e;
+                bi_split(v, &m, &e);
+                // lanes of class t: 8n + 2t + {0, 1}, n = 0..3
+                const unsigned class_mask = 0x03030303u << (2 * t_class);
+                const bool class_bad = (bad & class_mask) != 0;
+                if (class_bad) { m = 1.0; e = 0; }
+                M[q] = __dmul_rn(M[q], m);
+                E[q] += e;
+                if (bad && ((live >> q) & 1u)) {                    // warp-uniform; rare: reference-semantics fallback
+                    double l = 0.0;
+                    if (class_bad && valid) {
+                        const int64_t pt = point[q];
+                        l = log(bi_ts_slow_density<NS>(T, rowoff, base, sp, y, K, S, term_source, wterm + pt * K,
+                                                       mus + pt * S, outlier));
+                    }
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 8));
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 16));
+                    if (class_bad) Lslow[q] = __dadd_rn(Lslow[q], l);
+                    any_slow = true;
+                }
+            }
+        }
+        // ---- close the superblock: M = (M_0 * M_1) * (M_2 * M_3), E = sum, L = (L_0 + L_1) + (L_2 + L_3)
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            double m = M[q];
+            m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 2));
+            m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 4));
+            int e = E[q];
+            e += __shfl_xor_sync(BI_FULL_MASK, e, 2);
+            e += __shfl_xor_sync(BI_FULL_MASK, e, 4);
+            double L = bi_block_log(m, e);
+            if (any_slow) {
+                double l = Lslow[q];
+                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 2));
+                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 4));
+                L = __dadd_rn(L, l);
+            }
+            if (lane == 0 && ((live >> q) & 1u)) partial[pair_partial_offset[gp.first + q] + sb] = L;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5b, mixture form: morph the TEMPLATES per point, then look the events up in the morphed mixture template.
+//     Tmix_q[b] = fma chain over k of T[row_{q,k}, b] * coef_{q,k}          (k_template_mix, once per point)
+//     f_i       = lookup(Tmix_q, x_i)                                        (k_mixture_partials)
+// The lookup is linear in the template values, so this equals the reference's sum_s mu_s * sum_c w_c * lookup(T_{c,s}, x_i)
+// in exact arithmetic; in floating point the operation order differs (about 1e-16 relative per event, far inside the
+// 1e-9 * N contract) -- this family is deterministic and batch-shape independent, but not bit-identical to K2 / K5a.
+// Cost per point-event: one lookup instead of K; with events sorted by bin (the engine does that once per dataset)
+// the 2^n_space template loads are warp-uniform and the kernel streams the prepared events at HBM speed.
+// Requires finite templates (the reference's per-source nansum cannot be reproduced from a mixture); a density that is
+// not a normal positive number takes  p = (outlier != 0 && !(p > 0)) ? outlier : p  (likelihood.py:686-689).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_template_mix(const double* __restrict__ T, int64_t row_stride, int64_t bin_stride, int64_t n_bins, int K,
+               const int32_t* __restrict__ row, const double* __restrict__ coef, const int32_t* __restrict__ status,
+               const int32_t* __restrict__ pair_point, int64_t n_pairs, double* __restrict__ tmix) {
+    const int64_t q = blockIdx.y;
+    const int64_t pt = pair_point ? pair_point[q] : q;
+    if (status[pt] != 0) return;
+    const int32_t* rw = row + pt * K;
+    const double* cf = coef + pt * K;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) acc = fma(__ldg(T + (int64_t)rw[k] * row_stride + b * bin_stride), cf[k], acc);
+        tmix[q * n_bins + b] = acc;
+    }
+}
+
+template <int NP, int NS>
+__global__ void __launch_bounds__(BI_TS_THREADS)
+k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins, const __grid_constant__ BiTsSpace sp,
+                   const int32_t* __restrict__ ev_bin, const double* __restrict__ ev_frac, int64_t ld_frac,
+                   const int64_t* __restrict__ dataset_offset, const int32_t* __restrict__ status,
+                   int64_t n_groups, const BiTsGroup* __restrict__ groups, const int64_t* __restrict__ unit_offset,
+                   const int32_t* __restrict__ unit_group, int64_t n_units,
+                   const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
+                   double outlier, double* __restrict__ partial) {
+    constexpr int NY = NS > 0 ? NS : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t_class = (lane >> 1) & 3;
+    const unsigned class_mask = 0x03030303u << (2 * t_class);
+    const int64_t n_warps = (int64_t)gridDim.x * BI_TS_WARPS;
+
+    for (int64_t u = (int64_t)blockIdx.x * BI_TS_WARPS + warp; u < n_units; u += n_warps) {
+        int64_t g;
+        if (unit_group) g = unit_group[u];
+        else {
+            int64_t lo = 0, hi = n_groups;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (unit_offset[mid] <= u) lo = mid; else hi = mid;
+            }
+            g = lo;
+        }
+        const int64_t sb = u - unit_offset[g];
+        const BiTsGroup gp = groups[g];
+        const int np = gp.count < NP ? gp.count : NP;
+        unsigned live = 0;
+        const double* V[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int qq = q < np ? q : 0;
+            V[q] = tmix + (int64_t)(gp.first + qq) * n_bins;
+            if (q < np && status[pair_point ? pair_point[gp.first + q] : gp.first + q] == 0) live |= 1u << q;
+        }
+        if (!live) continue;
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (!((live >> q) & 1u)) V[q] = tmix + (int64_t)(gp.first + (__ffs(live) - 1)) * n_bins;   // a written row
+
+        const int64_t ev_begin = dataset_offset[gp.dataset] + sb * BI_SUPERBLOCK;
+        const int64_t left = dataset_offset[gp.dataset + 1] - ev_begin;
+        const int n_ev = left < BI_SUPERBLOCK ? (int)left : BI_SUPERBLOCK;
+
+        double M[NP], Lslow[NP];
+        int E[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { M[q] = 1.0; E[q] = 0; Lslow[q] = 0.0; }
+        bool any_slow = false;
+
+        // software pipeline: the prepared event of the next group is in flight while this one is evaluated
+        bool valid = lane < n_ev;
+        int64_t bin = valid ? (int64_t)ev_bin[ev_begin + lane] : 0;
+        double y[NY];
+#pragma unroll
+        for (int d = 0; d < NY; ++d) y[d] = (NS > 0 && valid) ? ev_frac[(int64_t)d * ld_frac + ev_begin + lane] : 0.0;
+#pragma unroll 1
+        for (int e0 = 0; e0 < n_ev; e0 += BI_EVENT_BLOCK) {
+            const bool valid_next = e0 + BI_EVENT_BLOCK + lane < n_ev;
+            const int64_t ev_next = ev_begin + e0 + BI_EVENT_BLOCK + lane;
+            const int64_t bin_next = valid_next ? (int64_t)ev_bin[ev_next] : 0;
+            double y_next[NY];
+#pragma unroll
+            for (int d = 0; d < NY; ++d) y_next[d] = (NS > 0 && valid_next) ? ev_frac[(int64_t)d * ld_frac + ev_next] : 0.0;
+
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                double p = bi_ts_lookup<NS>(V[q] + bin, sp, y);
+                if (!valid) p = 1.0;
+                const bool in_range = (unsigned)(__double2hiint(p) - BI_RANGE_LO) < BI_RANGE_SPAN;
+                const unsigned bad = ~__ballot_sync(BI_FULL_MASK, in_range);
+                double v = __dmul_rn(p, __shfl_xor_sync(BI_FULL_MASK, p, 1));
+                v = __dmul_rn(v, __shfl_xor_sync(BI_FULL_MASK, v, 8));
+                v = __dmul_rn(v, __shfl_xor_sync(BI_FULL_MASK, v, 16));
+                double m;
+                int e;
+                bi_split(v, &m, &e);
+                const bool class_bad = (bad & class_mask) != 0;
+                if (class_bad) { m = 1.0; e = 0; }
+                M[q] = __dmul_rn(M[q], m);
+                E[q] += e;
+                if (bad && ((live >> q) & 1u)) {
+                    double l = (class_bad && valid) ? log(bi_fix_density(p, outlier)) : 0.0;
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 8));
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 16));
+                    if (class_bad) Lslow[q] = __dadd_rn(Lslow[q], l);
+                    any_slow = true;
+                }
+            }
+            valid = valid_next;
+            bin = bin_next;
+#pragma unroll
+            for (int d = 0; d < NY; ++d) y[d] = y_next[d];
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            double m = M[q];
+            m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 2));
+            m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 4));
+            int e = E[q];
+            e += __shfl_xor_sync(BI_FULL_MASK, e, 2);
+            e += __shfl_xor_sync(BI_FULL_MASK, e, 4);
+            double L = bi_block_log(m, e);
+            if (any_slow) {
+                double l = Lslow[q];
+                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 2));
+                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 4));
+                L = __dadd_rn(L, l);
+            }
+            if (lane == 0 && ((live >> q) & 1u)) partial[pair_partial_offset[gp.first + q] + sb] = L;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ragged finalize: logl[q] = -musum[point] + total(partials of pair q), the canonical total of
+// k_unbinned_finalize (256 strided lanes, xor butterfly per 32, pairwise over the 8 warp totals) by ONE warp
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_template_finalize(const double* __restrict__ partial, const int64_t* __restrict__ pair_partial_offset,
+                    const int32_t* __restrict__ pair_point, const double* __restrict__ musum,
+                    const int32_t* __restrict__ status, int64_t n_pairs, double* __restrict__ logl,
+                    double* __restrict__ logsum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= n_pairs) return;
+    const int64_t pt = pair_point ? pair_point[q] : q;
+    if (status[pt] != 0) {
+        if (lane == 0) {
+            logl[q] = -__longlong_as_double(0x7ff0000000000000LL);
+            if (logsum) logsum[q] = 0.0;
+        }
+        return;
+    }
+    const double* src = partial + pair_partial_offset[q];
+    const int64_t n = pair_partial_offset[q + 1] - pair_partial_offset[q];
+    double w[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {                                   // virtual warp v of the 256-thread finalize
+        double u = 0.0;
+        for (int64_t j = v * 32 + lane; j < n; j += 256) u = __dadd_rn(u, src[j]);
+#pragma unroll
+        for (int x = 1; x < 32; x <<= 1) u = __dadd_rn(u, __shfl_xor_sync(BI_FULL_MASK, u, x));
+        w[v] = u;
+    }
+    if (lane == 0) {
+        const double total = __dadd_rn(__dadd_rn(__dadd_rn(w[0], w[1]), __dadd_rn(w[2], w[3])),
+                                       __dadd_rn(__dadd_rn(w[4], w[5]), __dadd_rn(w[6], w[7])));
+        logl[q] = __dadd_rn(-musum[pt], total);
+        if (logsum) logsum[q] = total;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int bi_template_prepare_events(int32_t n_space, const int32_t* n_bins_host, const double* edges_host,
+                                          int32_t method, const double* coords_dev, int64_t ld_coords,
+                                          int64_t n_events, int32_t* ev_bin_dev, double* ev_frac_dev, int64_t ld_frac,
+                                          void* stream) {
+    BiSpace sp;
+    int rc = bi_fill_space(&sp, n_space, n_bins_host);
+    if (rc != BI_OK) return rc;
+    BI_REQUIRE(method == BI_LOOKUP_LINEAR || method == BI_LOOKUP_PIECEWISE, "unknown lookup method %d", method);
+    BiPoints pts;
+    int total = 0;
+    rc = bi_fill_points(&sp, &pts, edges_host, method == BI_LOOKUP_LINEAR, &total);
+    if (rc != BI_OK) return rc;
+    BI_REQUIRE(n_events >= 0, "n_events < 0");
+    if (n_events == 0) return BI_OK;
+    BI_REQUIRE(coords_dev && ev_bin_dev && ld_coords >= n_events, "bi_template_prepare_events: bad arguments");
+    BI_REQUIRE(method == BI_LOOKUP_PIECEWISE || (ev_frac_dev && ld_frac >= n_events),
+               "bi_template_prepare_events: ev_frac_dev / ld_frac needed for the linear method");
+    const int64_t blocks = (n_events + 255) / 256;
+    k_template_prepare<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        sp, pts, total, method == BI_LOOKUP_LINEAR, coords_dev, ld_coords, n_events, ev_bin_dev, ev_frac_dev, ld_frac);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}
+
+template <int NP, int NS>
+static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride, const BiTsSpace& sp,
+                        const int32_t* ev_bin, const double* ev_frac, int64_t ld_frac, const int64_t* dataset_offset,
+                        int K, int S, const int32_t* row, const double* coef, const double* wterm,
+                        const int32_t* term_source, const double* mus, const int32_t* status, int64_t n_groups,
+                        const BiTsGroup* groups, const int64_t* unit_offset, const int32_t* unit_group, int64_t n_units,
+                        const int32_t* pair_point, const int64_t* pair_partial_offset, double outlier, double* partial,
+                        cudaStream_t st) {
+    const int smem = BI_TS_WARPS * K * (1 + NP) * 8;
+    static int per_sm_cached[BI_TS_MAX_TERMS + 1] = {0};
+    static int sms = 0;
+    if (!per_sm_cached[K]) {
+        int dev = 0, per_sm = 0;
+        BI_CUDA_CHECK(cudaGetDevice(&dev));
+        BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        // the cap is per kernel, not per launch: always raise it to what the largest term count needs
+        BI_CUDA_CHECK(cudaFuncSetAttribute(k_template_partials<NP, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           BI_TS_WARPS * BI_TS_MAX_TERMS * (1 + NP) * 8));
+        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_template_partials<NP, NS>, BI_TS_THREADS, smem));
+        BI_REQUIRE(per_sm >= 1, "k_template_partials<%d,%d> does not fit on this device", NP, NS);
+        per_sm_cached[K] = per_sm;
+    }
+    int64_t blocks = (int64_t)sms * per_sm_cached[K];
+    const int64_t needed = (n_units + BI_TS_WARPS - 1) / BI_TS_WARPS;
+    if (blocks > needed) blocks = needed;
+    k_template_partials<NP, NS><<<(unsigned)blocks, BI_TS_THREADS, smem, st>>>(
+        T, row_stride, bin_stride, sp, ev_bin, ev_frac, ld_frac, dataset_offset, K, S, row, coef, wterm, term_source, mus,
+        status, n_groups, groups, unit_offset, unit_group, n_units, pair_point, pair_partial_offset, outlier, partial);
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        bi_set_error("k_template_partials<%d,%d> launch failed: %s (blocks=%lld, smem=%d, K=%d, units=%lld)", NP, NS,
+                     cudaGetErrorString(err), (long long)blocks, smem, K, (long long)n_units);
+        return BI_ERR_CUDA;
+    }
+    return BI_OK;
+}
+
+extern "C" int bi_template_partials(const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+                                    int32_t n_space, const int32_t* n_bins_host, int32_t method,
+                                    const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
+                                    const int64_t* dataset_offset_dev, int32_t n_terms, int32_t n_sources,
+                                    const int32_t* row_dev, const double* coef_dev, const double* wterm_dev,
+                                    const int32_t* term_source_dev, const double* mus_dev, const int32_t* status_dev,
+                                    int64_t n_groups, int32_t group_points, const int32_t* groups_dev,
+                                    const int64_t* unit_offset_dev, const int32_t* unit_group_dev, int64_t n_units,
+                                    const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
+                                    double outlier_likelihood, double* partial_dev, void* stream) {
+    BiSpace space;
+    int rc = bi_fill_space(&space, n_space, n_bins_host);
+    if (rc != BI_OK) return rc;
+    BI_REQUIRE(method == BI_LOOKUP_LINEAR || method == BI_LOOKUP_PIECEWISE, "unknown lookup method %d", method);
+    BI_REQUIRE(n_terms >= 1 && n_terms <= BI_TS_MAX_TERMS, "n_terms=%d outside [1,%d]", n_terms, BI_TS_MAX_TERMS);
+    BI_REQUIRE(n_sources >= 1 && n_sources <= BI_MAX_SOURCES, "n_sources=%d outside [1,%d]", n_sources, BI_MAX_SOURCES);
+    BI_REQUIRE(group_points == 1 || group_points == BI_TS_GROUP_POINTS, "group_points must be 1 or %d", BI_TS_GROUP_POINTS);
+    BI_REQUIRE(n_groups >= 0 && n_units >= 0, "negative size");
+    if (n_groups == 0 || n_units == 0) return BI_OK;
+    BI_REQUIRE(templates_dev && ev_bin_dev && dataset_offset_dev && row_dev && coef_dev && wterm_dev && term_source_dev &&
+                   mus_dev && status_dev && groups_dev && unit_offset_dev && pair_point_dev && pair_partial_offset_dev &&
+                   partial_dev,
+               "bi_template_partials: NULL device pointer");
+    BI_REQUIRE(method == BI_LOOKUP_PIECEWISE || ev_frac_dev, "bi_template_partials: ev_frac_dev is NULL");
+    BiTsSpace sp;
+    memset(&sp, 0, sizeof(sp));
+    const int ns = method == BI_LOOKUP_LINEAR ? n_space : 0;
+    sp.n_space = ns;
+    sp.n_corner = 1 << ns;
+    for (int c = 0; c < sp.n_corner; ++c) {
+        int64_t off = 0;
+        for (int d = 0; d < ns; ++d)
+            if (((c >> (ns - 1 - d)) & 1) && space.n_bins[d] > 1) off += space.stride[d];
+        sp.corner_off[c] = off * bin_stride;
+    }
+    const BiTsGroup* groups = reinterpret_cast<const BiTsGroup*>(groups_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+#define BI_TS_CASE(NPV, NSV)                                                                                            \
+    if (group_points == NPV && ns == NSV)                                                                               \
+        return bi_ts_launch<NPV, NSV>(templates_dev, row_stride, bin_stride, sp, ev_bin_dev, ev_frac_dev, ld_frac,      \
+                                      dataset_offset_dev, n_terms, n_sources, row_dev, coef_dev, wterm_dev,             \
+                                      term_source_dev, mus_dev, status_dev, n_groups, groups, unit_offset_dev,          \
+                                      unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,                 \
+                                      outlier_likelihood, partial_dev, st);
+    BI_TS_CASE(1, 0) BI_TS_CASE(1, 1) BI_TS_CASE(1, 2) BI_TS_CASE(1, 3) BI_TS_CASE(1, 4)
+    BI_TS_CASE(BI_TS_GROUP_POINTS, 0) BI_TS_CASE(BI_TS_GROUP_POINTS, 1) BI_TS_CASE(BI_TS_GROUP_POINTS, 2)
+    BI_TS_CASE(BI_TS_GROUP_POINTS, 3) BI_TS_CASE(BI_TS_GROUP_POINTS, 4)
+#undef BI_TS_CASE
+    bi_set_error("bi_template_partials: unsupported configuration");
+    return BI_ERR_UNSUPPORTED;
+}
+
+extern "C" int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_offset_dev,
+                                    const int32_t* pair_point_dev, const double* musum_dev, const int32_t* status_dev,
+                                    int64_t n_pairs, double* logl_dev, double* logsum_dev, void* stream) {
+    BI_REQUIRE(n_pairs >= 0, "n_pairs < 0");
+    if (n_pairs == 0) return BI_OK;
+    BI_REQUIRE(pair_partial_offset_dev && musum_dev && status_dev && logl_dev, "bi_template_finalize: NULL pointer");
+    const int64_t blocks = (n_pairs + 7) / 8;
+    k_template_finalize<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        partial_dev, pair_partial_offset_dev, pair_point_dev, musum_dev, status_dev, n_pairs, logl_dev, logsum_dev);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI of the mixture form
+// ---------------------------------------------------------------------------------------------
+extern "C" int bi_template_mix(const double* templates_dev, int64_t row_stride, int64_t bin_stride, int64_t n_bins,
+                               int32_t n_terms, const int32_t* row_dev, const double* coef_dev,
+                               const int32_t* status_dev, const int32_t* pair_point_dev, int64_t n_pairs,
+                               double* tmix_dev, void* stream) {
+    BI_REQUIRE(n_terms >= 1 && n_bins >= 1 && n_pairs >= 0, "bi_template_mix: bad sizes");
+    if (n_pairs == 0) return BI_OK;
+    BI_REQUIRE(n_pairs <= 65535, "bi_template_mix: at most 65535 pairs per call");
+    BI_REQUIRE(templates_dev && row_dev && coef_dev && status_dev && tmix_dev, "bi_template_mix: NULL device pointer");
+    int64_t bx = (n_bins + 255) / 256;
+    if (bx > 1024) bx = 1024;
+    dim3 grid((unsigned)bx, (unsigned)n_pairs);
+    k_template_mix<<<grid, 256, 0, (cudaStream_t)stream>>>(templates_dev, row_stride, bin_stride, n_bins, n_terms, row_dev,
+                                                         coef_dev, status_dev, pair_point_dev, n_pairs, tmix_dev);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}
+
+template <int NP, int NS>
+static int bi_mix_launch(const double* tmix, int64_t n_bins, const BiTsSpace& sp, const int32_t* ev_bin,
+                         const double* ev_frac, int64_t ld_frac, const int64_t* dataset_offset, const int32_t* status,
+                         int64_t n_groups, const BiTsGroup* groups, const int64_t* unit_offset, const int32_t* unit_group,
+                         int64_t n_units, const int32_t* pair_point, const int64_t* pair_partial_offset, double outlier,
+                         double* partial, cudaStream_t st) {
+    static int resident = 0;
+    if (!resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        BI_CUDA_CHECK(cudaGetDevice(&dev));
+        BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mixture_partials<NP, NS>, BI_TS_THREADS, 0));
+        BI_REQUIRE(per_sm >= 1, "k_mixture_partials<%d,%d> does not fit on this device", NP, NS);
+        resident = sms * per_sm;
+    }
+    int64_t blocks = resident;
+    const int64_t needed = (n_units + BI_TS_WARPS - 1) / BI_TS_WARPS;
+    if (blocks > needed) blocks = needed;
+    k_mixture_partials<NP, NS><<<(unsigned)blocks, BI_TS_THREADS, 0, st>>>(
+        tmix, n_bins, sp, ev_bin, ev_frac, ld_frac, dataset_offset, status, n_groups, groups, unit_offset, unit_group,
+        n_units, pair_point, pair_partial_offset, outlier, partial);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}
+
+extern "C" int bi_mixture_partials(const double* tmix_dev, int32_t n_space, const int32_t* n_bins_host, int32_t method,
+                                   const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
+                                   const int64_t* dataset_offset_dev, const int32_t* status_dev,
+                                   int64_t n_groups, int32_t group_points, const int32_t* groups_dev,
+                                   const int64_t* unit_offset_dev, const int32_t* unit_group_dev, int64_t n_units,
+                                   const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
+                                   double outlier_likelihood, double* partial_dev, void* stream) {
+    BiSpace space;
+    int rc = bi_fill_space(&space, n_space, n_bins_host);
+    if (rc != BI_OK) return rc;
+    BI_REQUIRE(method == BI_LOOKUP_LINEAR || method == BI_LOOKUP_PIECEWISE, "unknown lookup method %d", method);
+    BI_REQUIRE(group_points == 1 || group_points == BI_TS_GROUP_POINTS, "group_points must be 1 or %d", BI_TS_GROUP_POINTS);
+    BI_REQUIRE(n_groups >= 0 && n_units >= 0, "negative size");
+    if (n_groups == 0 || n_units == 0) return BI_OK;
+    BI_REQUIRE(tmix_dev && ev_bin_dev && dataset_offset_dev && status_dev && groups_dev && unit_offset_dev &&
+                   pair_partial_offset_dev && partial_dev,
+               "bi_mixture_partials: NULL device pointer");
+    BI_REQUIRE(method == BI_LOOKUP_PIECEWISE || ev_frac_dev, "bi_mixture_partials: ev_frac_dev is NULL");
+    BiTsSpace sp;
+    memset(&sp, 0, sizeof(sp));
+    const int ns = method == BI_LOOKUP_LINEAR ? n_space : 0;
+    sp.n_space = ns;
+    sp.n_corner = 1 << ns;
+    for (int c = 0; c < sp.n_corner; ++c) {
+        int64_t off = 0;
+        for (int d = 0; d < ns; ++d)
+            if (((c >> (ns - 1 - d)) & 1) && space.n_bins[d] > 1) off += space.stride[d];
+        sp.corner_off[c] = off;
+    }
+    const BiTsGroup* groups = reinterpret_cast<const BiTsGroup*>(groups_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+#define BI_MIX_CASE(NPV, NSV)                                                                                          \
+    if (group_points == NPV && ns == NSV)                                                                              \
+        return bi_mix_launch<NPV, NSV>(tmix_dev, space.n_cells, sp, ev_bin_dev, ev_frac_dev, ld_frac,                  \
+                                       dataset_offset_dev, status_dev, n_groups, groups, unit_offset_dev,              \
+                                       unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,               \
+                                       outlier_likelihood, partial_dev, st);
+    BI_MIX_CASE(1, 0) BI_MIX_CASE(1, 1) BI_MIX_CASE(1, 2) BI_MIX_CASE(1, 3) BI_MIX_CASE(1, 4)
+    BI_MIX_CASE(BI_TS_GROUP_POINTS, 0) BI_MIX_CASE(BI_TS_GROUP_POINTS, 1) BI_MIX_CASE(BI_TS_GROUP_POINTS, 2)
+    BI_MIX_CASE(BI_TS_GROUP_POINTS, 3) BI_MIX_CASE(BI_TS_GROUP_POINTS, 4)
+#undef BI_MIX_CASE
+    bi_set_error("bi_mixture_partials: unsupported configuration");
+    return BI_ERR_UNSUPPORTED;
+}

@@ -12,6 +12,11 @@ farms out anchor-model construction).  The hot path shards in two natural ways (
                          result does not depend on timing or collective algorithm); -sum(mu) and the
                          priors are added once.                                -> EventShardedLikelihood
 
+  toy sharding           rank r generates (Model.simulate_toys with first_toy = its slice start: counter-based
+                         random numbers keyed by the GLOBAL toy id, so the toys do not depend on the number of
+                         ranks) and evaluates a contiguous slice of the T toys; no collective inside the
+                         evaluation, one all_gather of the T results.         -> ToyShardedLikelihood
+
 Communication tensors live on the GPU for the nccl backend and on the host for gloo (CPU tests).
 """
 import numpy as np
@@ -95,6 +100,53 @@ class PointShardedLikelihood(object):
         lo, hi = bounds[rank]
         local = self.ll.batch(params[lo:hi], names, livetime_days=livetime_days) if hi > lo else np.zeros(0)
         return gather_concat(np.asarray(local, dtype=np.float64), [b - a for a, b in bounds], self.group)
+
+
+class ToyShardedLikelihood(object):
+    """Toy Monte Carlos sharded over the ranks of `group` (BASELINE config 4: 1e6 toys x 1e3 events over 8 GPUs).
+
+    `ll` is a prepared UnbinnedLogLikelihood (same model on every rank).  simulate(n_toys, ...) lets every rank
+    generate and load ITS slice of the toys on its own GPU; batch_toys(params[T, k]) evaluates toy t at params[t]
+    on the rank that owns it and returns all T results on every rank."""
+
+    def __init__(self, ll, group=None):
+        self.ll = ll
+        self.group = group
+        self.n_toys = 0
+        self.bounds = None
+
+    def _rank_world(self):
+        dist = _dist()
+        return dist.get_rank(self.group), dist.get_world_size(self.group)
+
+    def simulate(self, n_toys, rate_multipliers=None, livetime_days=None, seed=0, mus=None):
+        """Generate toys 0 .. n_toys - 1 across the ranks (rank r: its contiguous slice) and load them."""
+        rank, world = self._rank_world()
+        self.n_toys = int(n_toys)
+        self.bounds = shard_bounds(self.n_toys, world)
+        lo, hi = self.bounds[rank]
+        if mus is not None and np.ndim(mus) == 2:
+            mus = np.asarray(mus)[lo:hi]
+        toys = self.ll.base_model.simulate_toys(hi - lo, rate_multipliers, livetime_days, seed=seed, first_toy=lo,
+                                                mus=mus)
+        self.ll.set_toy_data(toys)
+        return toys
+
+    def set_local_toys(self, n_toys_total, datasets, offsets=None):
+        """Load this rank's slice of externally produced toys (slice = shard_bounds(n_toys_total, world)[rank])."""
+        rank, world = self._rank_world()
+        self.n_toys = int(n_toys_total)
+        self.bounds = shard_bounds(self.n_toys, world)
+        self.ll.set_toy_data(datasets, offsets)
+
+    def batch_toys(self, params, names=None, livetime_days=None):
+        rank, _ = self._rank_world()
+        params = np.asarray(params, dtype=np.float64)
+        if len(params) != self.n_toys:
+            raise ValueError("need one parameter point per toy: got %d for %d toys" % (len(params), self.n_toys))
+        lo, hi = self.bounds[rank]
+        local = self.ll.batch_toys(params[lo:hi], names, livetime_days=livetime_days) if hi > lo else np.zeros(0)
+        return gather_concat(np.asarray(local, dtype=np.float64), [b - a for a, b in self.bounds], self.group)
 
 
 def shard_events(d, group=None, rank=None, world_size=None):

@@ -849,3 +849,329 @@ class BinnedEngine(_EngineBase):
         self.launches += 1
         return (float(logl.cpu()[0]), mus_adj[:S].cpu().numpy().copy(),
                 out.cpu().numpy().reshape((S,) + tuple(self.bin_shape)), int(flags.cpu()[0]))
+
+
+class TemplateUnbinnedEngine(_EngineBase):
+    """Template-space unbinned likelihood (K1 + K5 + ragged finalize): the per-event pdf values of the anchor
+    tensor are looked up on the fly from HBM/L2-resident histogram templates instead of being stored.
+
+    Serves (a) MANY datasets, each evaluated at its own parameter point(s) -- toy Monte Carlos (SURVEY.md section 8d
+    config 4), and (b) one dataset whose dense anchor tensor [G, S, N] would not fit in HBM (config 5).  A
+    (dataset, point) pair evaluates bit-identically to UnbinnedEngine on that dataset alone (same operations,
+    same order: bi_template.cu).
+
+    templates: [G * S, *bins] densities, row = anchor * S + source (anchors in C order); edges_list: bin edges
+    per analysis dimension, shared by all templates; method: 'linear' | 'piecewise' (source.py:203,225-243)."""
+
+    def __init__(self, grid, mus_anchor, templates, edges_list, method='linear', outlier_likelihood=1e-12,
+                 allow_negative=None, device=None, bin_major=None, mode='exact'):
+        """mode 'exact': K5, per-event values formed like the reference (bit-identical to the anchor-tensor engine).
+        mode 'mixture': K5b, the templates are morphed per point and the events looked up in the mixture template
+        (one lookup per point-event instead of corners x sources; events are sorted by bin once per dataset so the
+        kernel streams them at HBM speed; equal to 'exact' to ~1e-13 relative, not bit-identical; needs finite
+        templates; one dataset at a time)."""
+        super().__init__(grid, mus_anchor, allow_negative, device)
+        torch = self.torch
+        if mode not in ('exact', 'mixture'):
+            raise ValueError("mode must be 'exact' or 'mixture'")
+        self.mode = mode
+        if mode == 'mixture' and not np.all(np.isfinite(np.asarray(templates, dtype=np.float64))):
+            raise ValueError("mode='mixture' needs finite templates (the reference's per-source nansum cannot be "
+                             "reproduced from a mixture template); use mode='exact'")
+        self.outlier_likelihood = float(outlier_likelihood)
+        self.edges_list = [np.ascontiguousarray(np.asarray(e, dtype=np.float64)) for e in edges_list]
+        self.n_space = len(self.edges_list)
+        if not 1 <= self.n_space <= _cabi.MAX_SPACE_DIMS:
+            raise ValueError("templates must have 1..%d analysis dimensions" % _cabi.MAX_SPACE_DIMS)
+        self.n_bins_i32 = _cabi.as_i32([len(e) - 1 for e in self.edges_list])
+        self.edges_concat = _cabi.as_f64(np.concatenate(self.edges_list))
+        self.method = {'linear': _cabi.LOOKUP_LINEAR, 'piecewise': _cabi.LOOKUP_PIECEWISE}[method]
+        t = np.ascontiguousarray(np.asarray(templates, dtype=np.float64))
+        self.n_rows = grid.n_anchors * self.n_sources
+        self.n_template_bins = int(np.prod(self.n_bins_i32))
+        t = t.reshape(self.n_rows, self.n_template_bins)
+        self.n_terms = self.n_sources * grid.n_corners
+        if self.n_terms > _cabi.TS_MAX_TERMS:
+            raise NotImplementedError("the template-space kernel supports at most %d contraction terms "
+                                      "(corners x sources); got %d" % (_cabi.TS_MAX_TERMS, self.n_terms))
+        if bin_major is None:
+            bin_major = os.environ.get('BI_TS_BIN_MAJOR', '0') != '0'       # row-major measured faster (profiles/)
+        self.bin_major = bool(bin_major)
+        self.templates_rows = torch.from_numpy(t).to(self.device)             # [n_rows, B]: K3 / full_output
+        if self.bin_major:
+            # value(row, bin) at bin * n_rows + row: the K rows of a hypercube cell at one bin are a few
+            # contiguous runs (sources fastest, then the last shape parameter's two anchors)
+            self.templates = self.templates_rows.t().contiguous()
+            self.row_stride, self.bin_stride = 1, self.n_rows
+        else:
+            self.templates = self.templates_rows
+            self.row_stride, self.bin_stride = self.n_template_bins, 1
+        self.n_events = 0
+        self.n_datasets = 0
+        self.ev_bin = None
+        self._toy_schedule = None
+
+    # -- datasets ---------------------------------------------------------------------------------
+    def set_datasets(self, coords, offsets=None):
+        """coords: [n_space, N_total] event coordinates (NumPy array or device tensor) of all datasets back to
+        back; offsets: [T + 1] first event of each dataset (default: one dataset).  Runs the event preparation
+        kernel once (low-corner bin + fractions per event)."""
+        torch = self.torch
+        if isinstance(coords, torch.Tensor):
+            coords_dev = coords.to(self.device, torch.float64).contiguous()
+        else:
+            host = np.ascontiguousarray(np.asarray(coords, dtype=np.float64)).reshape(self.n_space, -1)
+            if self.method == _cabi.LOOKUP_LINEAR and np.isnan(host).any():
+                raise ValueError("One of the requested xi is out of bounds in dimension 0")
+            coords_dev = torch.from_numpy(host).to(self.device)
+        coords_dev = coords_dev.reshape(self.n_space, -1)
+        n = int(coords_dev.shape[1])
+        if offsets is None:
+            offsets = np.array([0, n], dtype=np.int64)
+        offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+        if offsets[0] != 0 or offsets[-1] != n or np.any(np.diff(offsets) < 0):
+            raise ValueError("dataset offsets must rise from 0 to the number of events")
+        self.n_events = n
+        self.n_datasets = len(offsets) - 1
+        self.offsets_host = offsets
+        self.offsets = torch.from_numpy(offsets).to(self.device)
+        self.n_super_host = (np.diff(offsets) + _cabi.SUPERBLOCK - 1) // _cabi.SUPERBLOCK      # per dataset
+        self.ld_frac = max(n, 1)
+        self.ev_bin = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        linear = self.method == _cabi.LOOKUP_LINEAR
+        self.ev_frac = torch.empty((self.n_space, self.ld_frac), dtype=torch.float64, device=self.device) if linear else None
+        if n:
+            _cabi.check(self.lib.bi_template_prepare_events(
+                self.n_space, _cabi.host_ptr(self.n_bins_i32), _cabi.host_ptr(self.edges_concat), self.method,
+                _cabi.dev_ptr(coords_dev), coords_dev.shape[1], n, _cabi.dev_ptr(self.ev_bin),
+                _cabi.dev_ptr(self.ev_frac), self.ld_frac, self._stream()), "bi_template_prepare_events")
+            self.launches += 1
+        self.coords = coords_dev                                            # kept for full_output (ps)
+        if self.mode == 'mixture' and n > 1:
+            # events of a dataset in bin order: the template loads of a warp become uniform (plumbing, once per dataset)
+            key = self.ev_bin[:n].to(torch.int64)
+            if self.n_datasets > 1:
+                sizes = torch.from_numpy(np.diff(offsets)).to(self.device)
+                key = key + self.n_template_bins * torch.repeat_interleave(
+                    torch.arange(self.n_datasets, device=self.device, dtype=torch.int64), sizes)
+            order = torch.argsort(key, stable=True)
+            self.ev_bin = self.ev_bin[:n][order].contiguous()
+            if self.ev_frac is not None:
+                self.ev_frac = self.ev_frac[:, :n][:, order].contiguous()
+            del key, order
+        self._toy_schedule = None
+        self._single_cache = {}
+        return self
+
+    # -- schedules (host) -------------------------------------------------------------------------
+    def _upload_schedule(self, pair_point, pair_dataset, group_first, group_count, group_points):
+        """Device copies of a pair schedule.  pair_*: [Q]; groups: consecutive pairs [first, first + count)."""
+        torch = self.torch
+        Q, n_groups = len(pair_point), len(group_first)
+        n_super_pair = self.n_super_host[pair_dataset] if Q else np.zeros(0, dtype=np.int64)
+        partial_offset = np.zeros(Q + 1, dtype=np.int64)
+        np.cumsum(n_super_pair, out=partial_offset[1:])
+        groups = np.zeros((n_groups, 4), dtype=np.int32)
+        groups[:, 0], groups[:, 1] = group_first, group_count
+        groups[:, 2] = pair_dataset[group_first] if n_groups else 0
+        n_super_group = self.n_super_host[groups[:, 2]] if n_groups else np.zeros(0, dtype=np.int64)
+        unit_offset = np.zeros(n_groups + 1, dtype=np.int64)
+        np.cumsum(n_super_group, out=unit_offset[1:])
+        n_units = int(unit_offset[-1])
+        sched = dict(n_pairs=Q, n_groups=n_groups, n_units=n_units, group_points=group_points,
+                     n_partials=int(partial_offset[-1]),
+                     pair_point=torch.from_numpy(np.ascontiguousarray(pair_point, dtype=np.int32)).to(self.device),
+                     partial_offset=torch.from_numpy(partial_offset).to(self.device),
+                     groups=torch.from_numpy(groups).to(self.device),
+                     unit_offset=torch.from_numpy(unit_offset).to(self.device), unit_group=None)
+        if n_groups > 4096 and n_units < (1 << 31):
+            # many small groups (toys): a direct unit -> group table instead of a binary search per unit
+            sched["unit_group"] = torch.repeat_interleave(
+                torch.arange(n_groups, dtype=torch.int32, device=self.device),
+                torch.from_numpy(n_super_group).to(self.device))
+        sched["h2d_bytes"] = 4 * Q + 8 * (Q + 1) + 16 * n_groups + 8 * (n_groups + 1)
+        return sched
+
+    def toy_schedule(self):
+        """Pair t = (dataset t, point t), one pair per group; built once per set_datasets."""
+        if self._toy_schedule is None:
+            T = self.n_datasets
+            idx = np.arange(T, dtype=np.int64)
+            self._toy_schedule = self._upload_schedule(idx, idx, idx, np.ones(T, dtype=np.int64), 1)
+        return self._toy_schedule
+
+    def single_schedule(self, zs, dataset=0):
+        """All P points on one dataset: points bucketed by hypercube cell, cut into groups of <= TS_GROUP_POINTS
+        (the template values of an event are gathered once per group).  Returns (schedule, point order)."""
+        P = len(zs)
+        if self.grid.n_dims:
+            ok = self.grid.in_range(zs)
+            if self.mode == 'mixture':                                      # groups need not share a cell
+                cells = np.where(ok, 0, -1).astype(np.int64)
+            else:
+                cells = np.where(ok, self.grid.cell_ids(np.where(ok[:, None], zs, self.grid.axes_concat[0])), -1)
+        else:
+            cells = np.zeros(P, dtype=np.int64)
+        key = (P, dataset, cells.tobytes())
+        hit = self._single_cache.get(key)
+        if hit is not None:
+            return hit
+        order = np.argsort(cells, kind='stable')
+        sc = cells[order]
+        starts = np.flatnonzero(np.r_[True, sc[1:] != sc[:-1]]) if P else np.zeros(0, dtype=np.int64)
+        ends = np.r_[starts[1:], P] if P else starts
+        np_max = _cabi.TS_GROUP_POINTS if P > 1 else 1
+        first, count = [], []
+        for s0, e0, c in zip(starts, ends, sc[starts] if P else []):
+            step = 1 if c < 0 else np_max
+            for f in range(s0, e0, step):
+                first.append(f)
+                count.append(min(step, e0 - f))
+        sched = self._upload_schedule(order, np.full(P, dataset, dtype=np.int64), np.asarray(first, dtype=np.int64),
+                                      np.asarray(count, dtype=np.int64), np_max)
+        if len(self._single_cache) >= 8:
+            self._single_cache.clear()
+        self._single_cache[key] = (sched, order)
+        return sched, order
+
+    # -- evaluation -------------------------------------------------------------------------------
+    def _setup_terms(self, P, zs_d, mult_d, scale_d, eff_d):
+        """K1 with the contraction terms (rows, coefficients) K5 consumes."""
+        torch = self.torch
+        D, S, C, K = self.grid.n_dims, self.n_sources, self.grid.n_corners, self.n_terms
+        o = dict(cell=self.ws.get("cell", P * max(D, 1), torch.int32), frac=self.ws.get("frac", P * max(D, 1), torch.float64),
+                 corner=self.ws.get("corner", P * C, torch.int32), weight=self.ws.get("weight", P * C, torch.float64),
+                 mus=self.ws.get("mus", P * S, torch.float64), musum=self.ws.get("musum", P, torch.float64),
+                 status=self.ws.get("status", P, torch.int32), row=self.ws.get("row", P * K, torch.int32),
+                 coef=self.ws.get("coef", P * K, torch.float64), wterm=self.ws.get("wterm", P * K, torch.float64),
+                 term_source=self.ws.get("term_source", K, torch.int32))
+        _cabi.check(self.lib.bi_point_setup(
+            D, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat), S, P,
+            _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
+            _cabi.dev_ptr(self.mus_anchor), _cabi.host_ptr(self.allow_negative),
+            _cabi.dev_ptr(o["cell"]), _cabi.dev_ptr(o["frac"]), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),
+            _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["musum"]), _cabi.dev_ptr(o["status"]), _cabi.dev_ptr(o["row"]),
+            _cabi.dev_ptr(o["coef"]), _cabi.dev_ptr(o["wterm"]), _cabi.dev_ptr(o["term_source"]), self._stream()),
+            "bi_point_setup")
+        self.launches += 1
+        return o
+
+    def run_schedule(self, sched, o):
+        """K5 + ragged finalize on device-resident K1 outputs.  Returns (logl [Q], logsum [Q]) device tensors in
+        PAIR order."""
+        torch = self.torch
+        Q = sched["n_pairs"]
+        partial = self.ws.get("ts_partial", sched["n_partials"], torch.float64)
+        logl = self.ws.get("ts_logl", Q, torch.float64)
+        logsum = self.ws.get("ts_logsum", Q, torch.float64)
+        if sched["n_units"] and self.mode == 'mixture':
+            tmix = self.ws.get("ts_tmix", Q * self.n_template_bins, torch.float64)
+            _cabi.check(self.lib.bi_template_mix(
+                _cabi.dev_ptr(self.templates), self.row_stride, self.bin_stride, self.n_template_bins, self.n_terms,
+                _cabi.dev_ptr(o["row"]), _cabi.dev_ptr(o["coef"]), _cabi.dev_ptr(o["status"]),
+                _cabi.dev_ptr(sched["pair_point"]), Q, _cabi.dev_ptr(tmix), self._stream()), "bi_template_mix")
+            _cabi.check(self.lib.bi_mixture_partials(
+                _cabi.dev_ptr(tmix), self.n_space, _cabi.host_ptr(self.n_bins_i32), self.method,
+                _cabi.dev_ptr(self.ev_bin), _cabi.dev_ptr(self.ev_frac), self.ld_frac, _cabi.dev_ptr(self.offsets),
+                _cabi.dev_ptr(o["status"]), sched["n_groups"], sched["group_points"], _cabi.dev_ptr(sched["groups"]),
+                _cabi.dev_ptr(sched["unit_offset"]), _cabi.dev_ptr(sched["unit_group"]), sched["n_units"],
+                _cabi.dev_ptr(sched["pair_point"]), _cabi.dev_ptr(sched["partial_offset"]),
+                self.outlier_likelihood, _cabi.dev_ptr(partial), self._stream()), "bi_mixture_partials")
+            self.launches += 2
+        elif sched["n_units"]:
+            _cabi.check(self.lib.bi_template_partials(
+                _cabi.dev_ptr(self.templates), self.row_stride, self.bin_stride, self.n_space,
+                _cabi.host_ptr(self.n_bins_i32), self.method, _cabi.dev_ptr(self.ev_bin), _cabi.dev_ptr(self.ev_frac),
+                self.ld_frac, _cabi.dev_ptr(self.offsets), self.n_terms, self.n_sources, _cabi.dev_ptr(o["row"]),
+                _cabi.dev_ptr(o["coef"]), _cabi.dev_ptr(o["wterm"]), _cabi.dev_ptr(o["term_source"]),
+                _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]), sched["n_groups"], sched["group_points"],
+                _cabi.dev_ptr(sched["groups"]), _cabi.dev_ptr(sched["unit_offset"]), _cabi.dev_ptr(sched["unit_group"]),
+                sched["n_units"], _cabi.dev_ptr(sched["pair_point"]), _cabi.dev_ptr(sched["partial_offset"]),
+                self.outlier_likelihood, _cabi.dev_ptr(partial), self._stream()), "bi_template_partials")
+            self.launches += 1
+        _cabi.check(self.lib.bi_template_finalize(
+            _cabi.dev_ptr(partial), _cabi.dev_ptr(sched["partial_offset"]), _cabi.dev_ptr(sched["pair_point"]),
+            _cabi.dev_ptr(o["musum"]), _cabi.dev_ptr(o["status"]), Q, _cabi.dev_ptr(logl), _cabi.dev_ptr(logsum),
+            self._stream()), "bi_template_finalize")
+        self.launches += 1
+        return logl, logsum
+
+    def _evaluate(self, sched, order, zs, mult, scale, eff, return_status, return_parts):
+        torch = self.torch
+        P = len(mult)
+        if self.ev_bin is None:
+            raise RuntimeError("set_datasets must be called first")
+        zs = np.asarray(zs, dtype=np.float64).reshape(P, self.grid.n_dims)
+        zs_d, mult_d, scale_d, eff_d, nbytes = self._upload_points(zs, mult, scale, eff)
+        o = self._setup_terms(P, zs_d, mult_d, scale_d, eff_d)
+        logl, logsum = self.run_schedule(sched, o)
+        n_f = 3 * P if return_parts else P
+        out_pin = self.ws.get("d2h", 3 * P, torch.float64, pinned=True)
+        out_pin[:P].copy_(logl, non_blocking=True)
+        if return_parts:
+            out_pin[P:2 * P].copy_(logsum, non_blocking=True)
+            out_pin[2 * P:].copy_(o["musum"], non_blocking=True)
+        st_pin = self.ws.get("d2h_status", P, torch.int32, pinned=True)
+        st_pin.copy_(o["status"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.last_h2d_bytes = nbytes
+        self.last_d2h_bytes = n_f * 8 + P * 4
+        res = out_pin.numpy().copy()
+        status = st_pin.numpy().copy()
+        ll, ls = res[:P], res[P:2 * P]
+        if order is not None:                                               # pair order -> point order
+            inv = np.empty(P, dtype=np.int64)
+            inv[order] = np.arange(P)
+            ll, ls = ll[inv], ls[inv] if return_parts else ls
+        if return_parts:
+            return ls, res[2 * P:], status
+        return (ll, status) if return_status else ll
+
+    def evaluate(self, zs, mult, scale=None, eff=None, return_status=False, return_parts=False, dataset=0):
+        """P points on ONE dataset (same contract as UnbinnedEngine.evaluate)."""
+        P = len(mult)
+        if P == 0:
+            if return_parts:
+                return np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int32)
+            return (np.zeros(0), np.zeros(0, dtype=np.int32)) if return_status else np.zeros(0)
+        zs = np.asarray(zs, dtype=np.float64).reshape(P, self.grid.n_dims)
+        sched, order = self.single_schedule(zs, dataset)
+        return self._evaluate(sched, order, zs, mult, scale, eff, return_status, return_parts)
+
+    def evaluate_toys(self, zs, mult, scale=None, eff=None, return_status=False, return_parts=False):
+        """Point t on dataset t for all T datasets (one parameter point per toy)."""
+        if self.mode != 'exact':
+            raise NotImplementedError("toys are evaluated by the exact template kernel: build the engine with mode='exact'")
+        if len(mult) != self.n_datasets:
+            raise ValueError("need one parameter point per dataset: got %d points for %d datasets"
+                             % (len(mult), self.n_datasets))
+        return self._evaluate(self.toy_schedule(), None, zs, mult, scale, eff, return_status, return_parts)
+
+    def ps(self, z_row, mult_row, scale=None, eff=None, dataset=0):
+        """(mus [S], ps [S, N]) of one point on one dataset, reference operation order (full_output=True): K3 on
+        the point's K template rows, then the corner-weighted sum of bi_unbinned_ps."""
+        torch = self.torch
+        S, C, K = self.n_sources, self.grid.n_corners, self.n_terms
+        zs_d, mult_d, scale_d, eff_d, _ = self._upload_points(np.asarray(z_row, dtype=np.float64).reshape(1, -1),
+                                                              np.asarray(mult_row, dtype=np.float64).reshape(1, -1),
+                                                              None if scale is None else [scale],
+                                                              None if eff is None else np.asarray(eff).reshape(1, -1))
+        o = self._setup_terms(1, zs_d, mult_d, scale_d, eff_d)
+        lo, hi = int(self.offsets_host[dataset]), int(self.offsets_host[dataset + 1])
+        n = hi - lo
+        ld = max(round_up(n, _LD_ALIGN), _LD_ALIGN)
+        rows = self.templates_rows.index_select(0, o["row"][:K].to(torch.int64))          # [K, B], k = c * S + s
+        coords = self.coords[:, lo:hi].contiguous()
+        a_sel = torch.zeros((K, ld), dtype=torch.float64, device=self.device)
+        if n:
+            _cabi.check(self.lib.bi_hist_lookup(_cabi.dev_ptr(rows), K, self.n_space, _cabi.host_ptr(self.n_bins_i32),
+                                                _cabi.host_ptr(self.edges_concat), _cabi.dev_ptr(coords), n, n,
+                                                self.method, _cabi.dev_ptr(a_sel), ld, None, self._stream()),
+                        "bi_hist_lookup")
+        out = torch.empty((S, max(n, 1)), dtype=torch.float64, device=self.device)
+        corner = torch.arange(C, dtype=torch.int32, device=self.device)
+        _cabi.check(self.lib.bi_unbinned_ps(_cabi.dev_ptr(a_sel), ld, n, S, C, _cabi.dev_ptr(corner),
+                                            _cabi.dev_ptr(o["weight"]), _cabi.dev_ptr(out), out.shape[1], self._stream()),
+                    "bi_unbinned_ps")
+        self.launches += 2
+        return o["mus"][:S].cpu().numpy().copy(), out[:, :n].cpu().numpy()

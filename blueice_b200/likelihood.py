@@ -24,7 +24,7 @@ from scipy import stats
 
 from . import _cabi
 from . import inference
-from .engine import BinnedEngine, MorphGrid, SourcewiseUnbinnedEngine, UnbinnedEngine
+from .engine import BinnedEngine, MorphGrid, SourcewiseUnbinnedEngine, TemplateUnbinnedEngine, UnbinnedEngine
 from .exceptions import InvalidParameter, InvalidParameterSpecification, NotPreparedException
 from .hist import Histdd
 from .model import Model
@@ -507,31 +507,155 @@ class _LazyInterpolator(object):
         return self._fn(zs)
 
 
+class _ToyView(object):
+    """Engine facade for _evaluate_rows: point t is evaluated on dataset t."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.point_setup_host = engine.point_setup_host
+
+    def evaluate(self, zs, mult, scale=None, eff=None, return_status=False):
+        return self.engine.evaluate_toys(zs, mult, scale, eff, return_status=return_status)
+
+
 class UnbinnedLogLikelihood(LogLikelihoodBase):
 
     @inherit_docstring_from(LogLikelihoodBase)
     def set_data(self, d):
         LogLikelihoodBase.set_data(self, d)
         outlier = self.config.get('outlier_likelihood', 1e-12)
-        if len(self.shape_parameters) and self.source_wise_interpolation:
+        template_mode = self._wants_template_engine(len(d))
+        if template_mode:
+            engine = self._build_template_engine(template_mode)
+            dims = self.base_model.to_analysis_dimensions(d)
+            engine.set_datasets(np.asarray([np.asarray(c, dtype=np.float64) for c in dims]).reshape(len(dims), -1))
+        elif len(self.shape_parameters) and self.source_wise_interpolation:
             engine = SourcewiseUnbinnedEngine(self._grid, self._sw_source_dims, self._sw_mus_rows,
                                               outlier_likelihood=outlier, allow_negative=self.source_allowed_negative)
             items = [(row, s, source) for row, (s, source) in enumerate(self._sw_row_sources)]
+            self._fill_anchor_rows(engine, items, d)
         else:
             engine = UnbinnedEngine(self._grid, self._mus_anchor.reshape(self._grid.n_anchors, -1),
                                     outlier_likelihood=outlier, allow_negative=self.source_allowed_negative)
-            if len(self.shape_parameters):
-                models = [self.anchor_models[tuple(zs)] for _, zs in self.morpher._anchor_grid_iterator()]
-            else:
-                models = [self.base_model]
-            items = [(g, s, source) for g, model in enumerate(models) for s, source in enumerate(model.sources)]
-        self._fill_anchor_rows(engine, items, d)
+            self._fill_anchor_rows(engine, self._anchor_items(), d)
         self._engine = engine
         if len(self.shape_parameters):
             self.ps_interpolator = lambda zs: engine.ps(np.asarray(zs, dtype=np.float64),
                                                         np.ones(engine.n_sources))[1]
-        else:
+        elif not isinstance(engine, TemplateUnbinnedEngine):
             self.ps = engine.ps(np.zeros(0), np.ones(engine.n_sources))[1]
+
+    def _anchor_items(self):
+        """(anchor index, source index, Source) for every row of the full anchor grid, anchors in C order."""
+        if len(self.shape_parameters):
+            models = [self.anchor_models[tuple(zs)] for _, zs in self.morpher._anchor_grid_iterator()]
+        else:
+            models = [self.base_model]
+        return [(g, s, source) for g, model in enumerate(models) for s, source in enumerate(model.sources)]
+
+    # dense anchor tensors above this many bytes switch `unbinned_engine: 'auto'` to the template-space engine
+    _TEMPLATE_ENGINE_BYTES = 16 << 30
+
+    def _wants_template_engine(self, n_events):
+        """Template-engine mode for this dataset, or None for the dense anchor tensor.
+
+        likelihood_config['unbinned_engine']: 'anchor' (default: dense per-event anchor tensor, K3 + K2);
+        'template' (K5: per-event values looked up on the fly, bit-identical to 'anchor'); 'mixture' (K5b: templates
+        morphed per point, events looked up in the mixture template -- one lookup per point-event, HBM-bound; equal
+        to 'anchor' to ~1e-13 relative); 'auto' (the dense tensor unless it would exceed _TEMPLATE_ENGINE_BYTES,
+        then 'mixture', or 'template' if some template holds a non-finite value)."""
+        kind = self.config.get('unbinned_engine', 'anchor')
+        if kind == 'anchor':
+            return None
+        if kind not in ('template', 'mixture', 'auto'):
+            raise ValueError("unbinned_engine must be 'anchor', 'template', 'mixture' or 'auto'")
+        reason = self._template_engine_obstacle()
+        if kind in ('template', 'mixture'):
+            if reason:
+                raise NotImplementedError("unbinned_engine=%r: %s" % (kind, reason))
+            return 'exact' if kind == 'template' else 'mixture'
+        dense = 8 * self._grid.n_anchors * len(self.source_name_list) * n_events
+        if reason is not None or dense <= self._TEMPLATE_ENGINE_BYTES:
+            return None
+        finite = all(np.all(np.isfinite(source.template()[0])) for _, _, source in self._anchor_items())
+        return 'mixture' if finite else 'exact'
+
+    def _template_engine_obstacle(self):
+        """None if every row of the anchor grid is a stock histogram template on shared bin edges, else why not."""
+        if len(self.shape_parameters) and self.source_wise_interpolation:
+            return "source-wise interpolation is not supported"
+        if len(self.base_model.config['analysis_space']) > _cabi.MAX_SPACE_DIMS:
+            return "too many analysis dimensions"
+        key = None
+        for _, _, source in self._anchor_items():
+            if not (isinstance(source, HistogramPdfSource) and type(source).pdf is HistogramPdfSource.pdf):
+                return "source %r is not a stock HistogramPdfSource" % (source.name,)
+            _, edges, method = source.template()
+            k = (tuple(np.asarray(e, dtype=np.float64).tobytes() for e in edges), method)
+            if key is None:
+                key = k
+            elif k != key:
+                return "sources differ in bin edges or lookup method"
+        if self._grid.n_corners * len(self.source_name_list) > _cabi.TS_MAX_TERMS:
+            return "more than %d contraction terms" % _cabi.TS_MAX_TERMS
+        return None
+
+    def _build_template_engine(self, mode='exact'):
+        """TemplateUnbinnedEngine over the templates of all anchor models (HBM / L2 resident)."""
+        items = self._anchor_items()
+        _, edges, method = items[0][2].template()
+        templates = np.stack([source.template()[0] for _, _, source in items])
+        return TemplateUnbinnedEngine(self._grid, self._mus_anchor.reshape(self._grid.n_anchors, -1), templates,
+                                      edges, method, outlier_likelihood=self.config.get('outlier_likelihood', 1e-12),
+                                      allow_negative=self.source_allowed_negative, mode=mode)
+
+    # ------------------------------------------------------------------------------------------
+    # many datasets, one parameter point each (toy Monte Carlos; not in the reference API)
+    # ------------------------------------------------------------------------------------------
+    @_needs_preparation
+    def set_toy_data(self, datasets, offsets=None):
+        """Load T datasets for batch_toys.
+
+        datasets: a sequence of T datasets (each anything set_data accepts), ONE dataset holding the events of
+        all toys back to back together with offsets [T + 1] (first event of every toy), or a device-resident
+        blueice_b200.toys.ToyData (Model.simulate_toys).  The toys live on the
+        device next to the anchor templates; nothing per event and anchor is stored (template-space engine), so
+        1e6 toys x 1e3 events need 36 bytes per event."""
+        reason = self._template_engine_obstacle()
+        if reason:
+            raise NotImplementedError("set_toy_data: " + reason)
+        from .toys import ToyData
+        if isinstance(datasets, ToyData):
+            dims = [dim[0] for dim in self.base_model.config['analysis_space']]
+            if datasets.dims != dims:
+                raise ValueError("toy data has dimensions %s, the model %s" % (datasets.dims, dims))
+            coords, offsets = datasets.coords, datasets.offsets
+        elif offsets is None:
+            sizes = [len(d) for d in datasets]
+            offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            per_toy = [self.base_model.to_analysis_dimensions(d) for d in datasets]
+            n_space = len(self.base_model.config['analysis_space'])
+            coords = np.empty((n_space, int(offsets[-1])), dtype=np.float64)
+            for t, dims in enumerate(per_toy):
+                for k in range(n_space):
+                    coords[k, offsets[t]:offsets[t + 1]] = dims[k]
+        else:
+            dims = self.base_model.to_analysis_dimensions(datasets)
+            coords = np.asarray([np.asarray(c, dtype=np.float64) for c in dims])
+        engine = self._build_template_engine()
+        engine.set_datasets(coords, offsets)
+        self._toy_engine = engine
+        return self
+
+    def batch_toys(self, params, names=None, livetime_days=None):
+        """Log likelihood of toy t at parameter point params[t] for all T toys of set_toy_data, one device pass.
+
+        Element t equals `self.set_data(toy_t); self(**dict(zip(names, params[t])))` bit for bit."""
+        engine = getattr(self, '_toy_engine', None)
+        if engine is None:
+            raise NotPreparedException("set_toy_data must be called before batch_toys")
+        zs, mult = self._rows_from_params(params, names)
+        return self._evaluate_rows(_ToyView(engine), zs, mult, livetime_days, scalar=False)
 
     def _fill_anchor_rows(self, engine, items, d):
         """Build the per-event pdf rows in HBM (likelihood.py:557-562 -> model.py:97-99; source-wise :534-549).

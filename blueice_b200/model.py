@@ -64,6 +64,12 @@ class Model(object):
             parts.append(events)
         return self.range_cut(np.concatenate(parts))
 
+    def simulate_toys(self, n_toys, rate_multipliers=None, livetime_days=None, seed=0, first_toy=0, mus=None):
+        """n_toys toy datasets generated on the device (blueice_b200.toys): what n_toys calls of simulate() give,
+        as one device-resident ToyData for UnbinnedLogLikelihood.set_toy_data.  Not in the reference API."""
+        from .toys import simulate_toys
+        return simulate_toys(self, n_toys, rate_multipliers, livetime_days, seed, first_toy, mus)
+
     def to_analysis_dimensions(self, d):
         """List of coordinate arrays of the events, one per analysis dimension."""
         return utils._events_to_analysis_dimensions(d, self.config['analysis_space'])

@@ -286,6 +286,95 @@ int bi_hist_lookup(const double* templates_dev, int64_t n_templates, int32_t n_s
                    double* out_dev, int64_t ld_out, int32_t* bin_index_dev, void* stream);
 
 /*
+ * K5 -- template-space unbinned likelihood: fused template lookup + morph + mixture + log + reduce over many
+ * datasets (toy Monte Carlos: SURVEY.md section 8d config 4) or one dataset too large for the dense anchor tensor
+ * (config 5).  Replaces the same reference code as K3 + K2 (source.py:219-246 called by likelihood.py:557-562, then
+ * likelihood.py:355-356,678-690) without materialising A[G, S, N]; every (dataset, point) pair evaluates
+ * BIT-IDENTICALLY to bi_hist_lookup + bi_unbinned_ll_batch on that dataset alone.
+ *
+ * bi_template_prepare_events (once per dataset set): event coordinates -> low-corner bin + per-dimension fractions
+ *   coords_dev [n_space, ld_coords]; ev_bin_dev [n_events] int32; ev_frac_dev [n_space, ld_frac] (linear only)
+ *
+ * bi_template_partials:
+ *   templates_dev        value(row, bin) = templates_dev[row * row_stride + bin * bin_stride] (row-major: row_stride =
+ *                        number of bins, bin_stride = 1; bin-major: row_stride = 1, bin_stride = number of rows)
+ *   dataset_offset_dev   [n_datasets + 1] int64 first event of each dataset in ev_bin_dev / ev_frac_dev
+ *   row/coef/wterm/term_source/mus/status: outputs of bi_point_setup[_sourcewise] for the points ([P, K], ..., [P])
+ *   pair list            pair q evaluates point pair_point_dev[q] on one dataset; its superblock partials go to
+ *                        partial_dev[pair_partial_offset_dev[q] + j], j < bi_num_superblocks(events of the dataset)
+ *   groups_dev           [n_groups, 4] int32 (first pair, pair count <= group_points, dataset, 0): pairs of a group
+ *                        are consecutive, share the dataset and MUST share their row list (same hypercube cell)
+ *   group_points         1 or BI_TS_GROUP_POINTS (selects the kernel instantiation)
+ *   unit_offset_dev      [n_groups + 1] int64 prefix sum of the groups' superblock counts; n_units = its last entry
+ *   unit_group_dev       [n_units] int32 group of each unit, or NULL (binary search in unit_offset_dev)
+ * Points with status != 0 are skipped (bi_template_finalize reports -inf).
+ *
+ * bi_template_finalize: logl[q] = -musum[point of q] + total(partials of pair q) in the canonical order of
+ * bi_unbinned_finalize; pair_point_dev NULL = identity; pair_partial_offset_dev has n_pairs + 1 entries.
+ */
+#define BI_TS_MAX_TERMS 256
+#define BI_TS_GROUP_POINTS 8
+int bi_template_prepare_events(int32_t n_space, const int32_t* n_bins_host, const double* edges_host,
+                               int32_t method, const double* coords_dev, int64_t ld_coords, int64_t n_events,
+                               int32_t* ev_bin_dev, double* ev_frac_dev, int64_t ld_frac, void* stream);
+int bi_template_partials(const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+                         int32_t n_space, const int32_t* n_bins_host, int32_t method,
+                         const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
+                         const int64_t* dataset_offset_dev, int32_t n_terms, int32_t n_sources,
+                         const int32_t* row_dev, const double* coef_dev, const double* wterm_dev,
+                         const int32_t* term_source_dev, const double* mus_dev, const int32_t* status_dev,
+                         int64_t n_groups, int32_t group_points, const int32_t* groups_dev,
+                         const int64_t* unit_offset_dev, const int32_t* unit_group_dev, int64_t n_units,
+                         const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
+                         double outlier_likelihood, double* partial_dev, void* stream);
+int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_offset_dev,
+                         const int32_t* pair_point_dev, const double* musum_dev, const int32_t* status_dev,
+                         int64_t n_pairs, double* logl_dev, double* logsum_dev, void* stream);
+
+/*
+ * K5b -- mixture form of the template-space likelihood: morph the TEMPLATES per point (bi_template_mix:
+ * tmix[q, b] = fma chain over k of templates[row[q, k], b] * coef[q, k]), then look the events up in the mixture
+ * template (bi_mixture_partials: f_i = lookup(tmix[q], x_i), scipy's operation order, then the canonical log-sum).
+ * Equal to K5 / K2 in exact arithmetic (the lookup is linear in the template values); in float64 the operation order
+ * differs by ~1e-16 relative per event -- inside the 1e-9 * N contract, NOT bit-identical to the other kernels.
+ * One lookup per point-event instead of n_terms; with the events of a dataset sorted by bin the template loads are
+ * warp-uniform and the kernel streams the prepared events (4 + 8 * n_space bytes each) at HBM speed.
+ * Requires finite templates.  tmix_dev: [n_pairs, prod(n_bins)], row q belongs to pair q; groups as in
+ * bi_template_partials except that the points of a group need NOT share a hypercube cell.
+ */
+int bi_template_mix(const double* templates_dev, int64_t row_stride, int64_t bin_stride, int64_t n_bins,
+                    int32_t n_terms, const int32_t* row_dev, const double* coef_dev, const int32_t* status_dev,
+                    const int32_t* pair_point_dev, int64_t n_pairs, double* tmix_dev, void* stream);
+int bi_mixture_partials(const double* tmix_dev, int32_t n_space, const int32_t* n_bins_host, int32_t method,
+                        const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
+                        const int64_t* dataset_offset_dev, const int32_t* status_dev,
+                        int64_t n_groups, int32_t group_points, const int32_t* groups_dev,
+                        const int64_t* unit_offset_dev, const int32_t* unit_group_dev, int64_t n_units,
+                        const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
+                        double outlier_likelihood, double* partial_dev, void* stream);
+
+/*
+ * On-device toy Monte Carlo generation.
+ *
+ * Replaces Model.simulate (model.py:69-91) for models whose sources are histogram templates:
+ * HistogramPdfSource.simulate (source.py:248-264) -> multihist Histdd.get_random.  Philox4x32-10 keyed by `seed`
+ * with the counter (index, toy id, domain): toy `toy_id0 + t` is the same events whatever the batch or the number
+ * of GPUs.  Parity with the reference is distributional (its Mersenne-Twister stream is not reproduced).
+ *
+ * bi_toy_counts : counts_dev[t, s] ~ Poisson(mus_dev[t, s]) (mus_per_toy != 0) or Poisson(mus_dev[s])
+ * bi_toy_events : the events of all toys; offsets_dev [n_toys + 1] = prefix sum of the toys' total counts (caller),
+ *                 n_events = its last entry; events of a toy are grouped by source in source order (model.py:88).
+ *   cdf_dev     [S, prod(n_bins)] per source: cumsum(pmf.ravel()) / sum  (Histdd.get_random's table)
+ *   coords_dev  [n_space, ld_coords] out; source_dev [n_events] out (may be NULL): the record array's 'source' field
+ */
+int bi_toy_counts(int32_t n_sources, int64_t n_toys, int64_t toy_id0, const double* mus_dev, int32_t mus_per_toy,
+                  uint64_t seed, int32_t* counts_dev, void* stream);
+int bi_toy_events(int32_t n_space, const int32_t* n_bins_host, const double* edges_host, int32_t n_sources,
+                  const double* cdf_dev, int64_t n_toys, int64_t toy_id0, const int32_t* counts_dev,
+                  const int64_t* offsets_dev, int64_t n_events, uint64_t seed, double* coords_dev, int64_t ld_coords,
+                  int32_t* source_dev, void* stream);
+
+/*
  * Event binning with np.histogramdd semantics (multihist.Histdd.add; likelihood.py:604-609).
  *   counts_dev [prod(n_bins)] uint64, ZEROED BY THE CALLER, incremented with integer atomics
  *   bin_index_dev [N] optional out: flat bin index or -1 for dropped events (may be NULL)

@@ -177,3 +177,17 @@ class BinnedOracle(object):
 
     def batch(self, zs_array, rate_multiplier_array):
         return np.array([self(z, m) for z, m in zip(zs_array, rate_multiplier_array)])
+
+
+def toy_loglikelihoods(axes, mus_anchor, templates, edges_list, coords, offsets, zs_array, rate_multiplier_array,
+                       method='linear', outlier_likelihood=1e-12):
+    """Many datasets, one parameter point each: toy t = events offsets[t]:offsets[t+1] of `coords`, evaluated at
+    (zs_array[t], rate_multiplier_array[t]).  The reference has no such call; this is literally its loop
+    `lf.set_data(toy_t); lf(**theta_t)` (likelihood.py:531-562, :318-427) over the toys."""
+    out = np.empty(len(offsets) - 1)
+    for t in range(len(offsets) - 1):
+        sl = slice(int(offsets[t]), int(offsets[t + 1]))
+        orc = UnbinnedOracle(axes, mus_anchor, outlier_likelihood=outlier_likelihood)
+        orc.set_data_from_templates(templates, edges_list, [np.asarray(c)[sl] for c in coords], method)
+        out[t] = orc(zs_array[t], rate_multiplier_array[t])
+    return out

@@ -80,6 +80,31 @@ def _worker(rank, world, port, out_dir):
         np.testing.assert_allclose(got_ev[fin], full[fin], rtol=1e-13)
         one = sharded(mu=float(zs[0, 0]), s0_rate_multiplier=float(mult[0, 0]))
         assert one == got_ev[0]
+        # toy sharding: rank r owns a contiguous slice of the toys; the stand-in ll evaluates toy t = events
+        # [offsets[t], offsets[t+1]) at params[t] with the oracle, on whatever slice it was given
+        from oracle.pipeline import toy_loglikelihoods
+        t_axes, t_edges, t_templates, t_mus = wl.c2_arrays(2, 1, (-1., 0., 1.), (12, 10))
+        sizes = np.array([30, 0, 55, 41, 17])
+        offsets = np.concatenate([[0], np.cumsum(sizes)])
+        tx, ty = wl.c2_events(t_templates, t_mus, t_edges, int(offsets[-1]) + 5, seed=2)
+        tzs, tmult = wl.scan_points(5, 1, 2, seed=9, z_range=(-1., 1.))
+
+        class ToyLL(object):
+            def set_toy_data(self, datasets, offsets=None):
+                self.coords, self.offsets = datasets, offsets
+
+            def batch_toys(self, p, names, livetime_days=None):
+                return toy_loglikelihoods(t_axes, t_mus, t_templates, t_edges, self.coords, self.offsets, p[:, :1], p[:, 1:])
+
+        tparams = np.column_stack([tzs, tmult])
+        whole = ToyLL()
+        whole.set_toy_data([tx[:offsets[-1]], ty[:offsets[-1]]], offsets)
+        toys_full = whole.batch_toys(tparams, None)
+        sharded_toys = bdist.ToyShardedLikelihood(ToyLL(), None)
+        lo_t, hi_t = bdist.shard_bounds(5, world)[rank]
+        sl = slice(offsets[lo_t], offsets[hi_t])
+        sharded_toys.set_local_toys(5, [tx[sl], ty[sl]], offsets[lo_t:hi_t + 1] - offsets[lo_t])
+        assert np.array_equal(sharded_toys.batch_toys(tparams), toys_full)
         np.save(os.path.join(out_dir, "rank%d.npy" % rank), got_ev)
         assert bdist.rank_ordered_sum(np.array([float(rank + 1)])).tolist() == [3.0]
     finally:

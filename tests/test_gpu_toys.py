@@ -1,0 +1,119 @@
+"""On-device toy generation (blueice_b200/csrc/bi_toys.cu): the event stage is
+bit-identical to oracle/toys.py (Philox pinned by Random123 vectors); the Poisson stage and the overall
+distribution are checked statistically against the reference's rules (model.py:69-91, source.py:248-264)."""
+import numpy as np
+import pytest
+
+import bench_workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def _tables(n_sources=3, bins=(30, 20)):
+    axes, edges, templates, mus = wl.c2_arrays(n_sources, 1, (-1., 0., 1.), bins)
+    vol = np.outer(np.diff(edges[0]), np.diff(edges[1]))
+    pmf = templates[1] * vol
+    cdf = np.vstack([np.cumsum(p.ravel()) / p.sum() for p in pmf])
+    return edges, pmf, cdf
+
+
+def test_events_bit_identical_to_oracle_and_shard_invariant():
+    from blueice_b200 import toys
+    from oracle import toys as otoys
+    edges, pmf, cdf = _tables()
+    mus = np.array([40., 7., 0.5])
+    coords, source, offsets, counts = toys.generate(edges, cdf, mus, 300, seed=1234567890123, first_toy=5)
+    want_c, want_s, want_o = otoys.toy_events(edges, cdf, counts, seed=1234567890123, first_toy=5)
+    assert np.array_equal(offsets, want_o)
+    assert np.array_equal(source.cpu().numpy(), want_s)
+    assert np.array_equal(coords.cpu().numpy(), want_c)
+    # the same toys generated in two pieces (as two ranks would)
+    c_a, s_a, o_a, n_a = toys.generate(edges, cdf, mus, 120, seed=1234567890123, first_toy=5)
+    c_b, s_b, o_b, n_b = toys.generate(edges, cdf, mus, 180, seed=1234567890123, first_toy=125)
+    assert np.array_equal(np.vstack([n_a, n_b]), counts)
+    assert np.array_equal(np.hstack([c_a.cpu().numpy(), c_b.cpu().numpy()]), want_c)
+    # a different seed gives different toys
+    c2 = toys.generate(edges, cdf, mus, 300, seed=1, first_toy=5)[3]
+    assert not np.array_equal(c2, counts)
+
+
+@pytest.mark.parametrize("mu", [0.0, 0.3, 4.0, 9.99, 10.0, 37.5, 1000.0, 250000.0])
+def test_poisson_counts_distribution(mu):
+    """Both NumPy-legacy algorithms (multiplication below 10, PTRS above): mean, variance and, for small means,
+    the pmf itself."""
+    from scipy import stats
+    from blueice_b200 import toys
+    edges, pmf, cdf = _tables(1)
+    T = 200000
+    import torch
+    from blueice_b200 import _cabi
+    import ctypes
+    lib = _cabi.load()
+    dev = torch.device("cuda:0")
+    mus_d = torch.tensor([mu], dtype=torch.float64, device=dev)
+    counts_d = torch.empty((T, 1), dtype=torch.int32, device=dev)
+    _cabi.check(lib.bi_toy_counts(1, T, 0, _cabi.dev_ptr(mus_d), 0, 99, _cabi.dev_ptr(counts_d),
+                                  ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "bi_toy_counts")
+    k = counts_d.cpu().numpy().ravel().astype(np.int64)
+    if mu == 0.0:
+        assert np.all(k == 0)
+        return
+    assert np.all(k >= 0)
+    # mean within 5 sigma; variance within 5 sigma of its sampling error
+    assert abs(k.mean() - mu) <= 5 * np.sqrt(mu / T)
+    var_err = np.sqrt((mu + 2 * mu * mu) / T)           # sd of the sample variance of a Poisson (approx.)
+    assert abs(k.var() - mu) <= 5 * var_err
+    if mu <= 40:
+        top = int(mu + 8 * np.sqrt(mu) + 10)
+        obs = np.bincount(np.minimum(k, top), minlength=top + 1).astype(float)
+        exp = stats.poisson(mu).pmf(np.arange(top + 1)) * T
+        exp[top] = stats.poisson(mu).sf(top - 1) * T
+        keep = exp >= 5
+        chi2 = np.sum((obs[keep] - exp[keep]) ** 2 / exp[keep]) + (obs[~keep].sum() - exp[~keep].sum()) ** 2 / max(exp[~keep].sum(), 1e-9)
+        assert chi2 <= stats.chi2(keep.sum()).ppf(1 - 1e-6), chi2
+
+
+def test_event_distribution_follows_the_source_pmfs():
+    from scipy import stats
+    from blueice_b200 import toys
+    edges, pmf, cdf = _tables()
+    mus = np.array([600., 300., 100.])
+    coords, source, offsets, counts = toys.generate(edges, cdf, mus, 2000, seed=3)
+    c = coords.cpu().numpy()
+    s = source.cpu().numpy()
+    assert np.all((c[0] >= edges[0][0]) & (c[0] <= edges[0][-1]) & (c[1] >= edges[1][0]) & (c[1] <= edges[1][-1]))
+    for k in range(3):
+        m = s == k
+        h, _, _ = np.histogram2d(c[0][m], c[1][m], bins=edges)
+        exp = pmf[k] / pmf[k].sum() * m.sum()
+        keep = exp >= 5
+        chi2 = np.sum((h[keep] - exp[keep]) ** 2 / exp[keep])
+        assert chi2 <= stats.chi2(keep.sum() - 1).ppf(1 - 1e-6), (k, chi2, keep.sum())
+        # uniform inside the bins
+        frac = (c[0][m] - edges[0][np.searchsorted(edges[0], c[0][m], 'right') - 1]) / np.diff(edges[0])[0]
+        assert abs(frac.mean() - 0.5) <= 5 * np.sqrt(1 / 12 / m.sum())
+    # toys are grouped by source in source order
+    t = 17
+    seg = s[offsets[t]:offsets[t + 1]]
+    assert np.all(np.diff(seg) >= 0) and np.array_equal(np.bincount(seg, minlength=3), counts[t])
+
+
+def test_model_simulate_toys_feeds_batch_toys():
+    """Model.simulate_toys -> set_toy_data -> batch_toys == per-toy set_data + call, bit for bit; toy means as in
+    Model.simulate (rate multipliers, livetime)."""
+    ll, d, names = wl.c2_api(n_sources=2, n_shape=2, anchors=(-1., 0., 1.), bins=(40, 30), n_events=500, seed=3)
+    model = ll.base_model
+    td = model.simulate_toys(40, rate_multipliers={'sig': 2.0}, livetime_days=0.01, seed=5)
+    assert len(td) == 40 and td.n_events == td.offsets[-1]
+    expect = np.array([model.expected_events(s) for s in model.sources]) * np.array([1.0, 2.0]) * 0.01
+    assert abs(td.counts[:, 0].mean() - expect[0]) <= 5 * np.sqrt(expect[0] / 40)
+    assert abs(td.counts[:, 1].mean() - expect[1]) <= 5 * np.sqrt(expect[1] / 40)
+    ll.set_toy_data(td)
+    zs, mult = wl.scan_points(40, 2, 2, seed=12, z_range=(-1., 1.))
+    params = np.column_stack([mult, zs])
+    got = ll.batch_toys(params, names)
+    for t in (0, 7, 39):
+        rec = td.to_records(t)
+        assert len(rec) == td.counts[t].sum() and set(rec.dtype.names) == {'source', 'cs1', 'cs2'}
+        ll.set_data(rec)
+        assert got[t] == ll(**dict(zip(names, [float(v) for v in params[t]])))

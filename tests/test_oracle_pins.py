@@ -161,3 +161,47 @@ def test_rates_unphysical_rule():
     assert not unbinned.rates_unphysical([-1., 2.], [True, False])
     assert unbinned.rates_unphysical([-1., 2.], [False, True])
     assert unbinned.rates_unphysical([-3., 2.], [True, False])          # sum < 0
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 known-answer vectors (kat_vectors: philox4x32 10) pin the oracle's counter-based generator,
+    which in turn pins the device generator bit for bit (tests/test_gpu_toys.py)."""
+    from oracle.toys import philox4x32_10, uniform53
+    cases = [
+        ([0, 0, 0, 0], (0, 0), [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, (0xffffffff, 0xffffffff), [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], (0xa4093822, 0x299f31d0),
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, want in cases:
+        got = philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]
+        assert [int(v) for v in got] == want
+    # NumPy's 53-bit construction: in [0, 1), top value just below 1
+    u = uniform53(np.array([0, 0xffffffff], dtype=np.uint32), np.array([0, 0xffffffff], dtype=np.uint32))
+    assert u[0] == 0.0 and u[1] == 1.0 - 2.0 ** -53
+
+
+def test_toy_event_stage_matches_histdd_get_random_rule():
+    """Given the uniforms, oracle.toys.toy_events places events exactly like Histdd.get_random (cdf search on the
+    flattened pmf, uniform inside the bin) and groups them by source like Model.simulate."""
+    from oracle import toys
+    rng = np.random.default_rng(0)
+    edges = [np.linspace(0., 10., 6), np.array([0., 1., 4., 9.])]
+    pmf = rng.uniform(0.1, 1., size=(2, 5, 3))
+    cdf = np.vstack([np.cumsum(p.ravel()) / p.sum() for p in pmf])
+    counts = np.array([[3, 2], [0, 4], [0, 0], [5, 0]])
+    coords, source, offsets = toys.toy_events(edges, cdf, counts, seed=7, first_toy=100)
+    assert list(offsets) == [0, 5, 9, 9, 14]
+    assert list(source) == [0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0]
+    assert np.all((coords[0] >= 0) & (coords[0] < 10) & (coords[1] >= 0) & (coords[1] < 9))
+    # event (toy 101, index 2) by hand
+    u_bin, u0 = toys.toy_uniforms(7, [101], [2], 1)
+    u1, _ = toys.toy_uniforms(7, [101], [2], 2)
+    flat = min(int(np.searchsorted(cdf[1], u_bin[0])), 14)
+    ix, iy = divmod(flat, 3)
+    e = 5 + 2
+    assert coords[0, e] == edges[0][ix] + u0[0] * (edges[0][ix + 1] - edges[0][ix])
+    assert coords[1, e] == edges[1][iy] + u1[0] * (edges[1][iy + 1] - edges[1][iy])
+    # sharding invariance: toys 2..3 generated alone are the same events
+    c2, s2, _ = toys.toy_events(edges, cdf, counts[2:], seed=7, first_toy=102)
+    assert np.array_equal(c2, coords[:, 9:]) and np.array_equal(s2, source[9:])
