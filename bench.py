@@ -222,6 +222,153 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------------------------
 # own arm
+def other_configs(args, rank, world, device):
+    """BASELINE configs 4 and 5 through the public API on the template-space engine (K5 / K5b), bounded sizes.
+
+    config 4  toy-MC Neyman construction: `--toys` toys PER GPU x ~1000 events (Model.simulate_toys on the device,
+              counter-based RNG keyed by the global toy id), 3 sources, 3 shape parameters x 5 anchors, one
+              parameter point per toy; toys are sharded over the ranks, no collective in the evaluation.
+    config 5  large-dataset fit: `--c5-events` events on this GPU (the full config is 1e8 over 8 GPUs = 1.25e7 per
+              GPU), 6 sources, 4 shape parameters x 5 anchors; one minimiser evaluation (P = 1) and one
+              forward-difference batch (P = 11) with the mixture engine; rank 0 only."""
+    import torch
+    import torch.distributed as dist
+    out = {}
+    # ---- config 4 ----
+    t0 = time.perf_counter()
+    ll, _, names = wl.c2_api(3, 3, wl.ANCHORS_5, BINS, n_events=1000, seed=4)
+    build_s = time.perf_counter() - t0
+    base_mu = float(np.sum(ll.base_model.expected_events()))
+    lt = 1000.0 / base_mu                                            # ~1000 events per toy
+    T = args.toys
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    toys = ll.base_model.simulate_toys(T, livetime_days=lt, seed=40, first_toy=rank * T)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ll.set_toy_data(toys)
+    torch.cuda.synchronize()
+    load_s = time.perf_counter() - t0
+    zs, mult = wl.scan_points(T, 3, 3, seed=41 + rank)
+    table = np.ascontiguousarray(np.column_stack([mult, zs]))
+    res = ll.batch_toys(table, names, livetime_days=lt)
+    eng = ll._toy_engine
+    # device-resident: K1 + K5 + finalize on uploaded points
+    zs_d, mult_d, scale_d, _, _ = eng._upload_points(zs, mult, np.full(T, lt / ll.pdf_base_config['livetime_days']), None)
+    sched = eng.toy_schedule()
+    dev_ms = []
+    for k in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        o = eng._setup_terms(T, zs_d, mult_d, scale_d, None)
+        eng.run_schedule(sched, o)
+        b.record()
+        torch.cuda.synchronize()
+        if k:
+            dev_ms.append(a.elapsed_time(b))
+    e2e = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = ll.batch_toys(table, names, livetime_days=lt)
+        e2e.append(time.perf_counter() - t0)
+    t_dev, t_e2e = float(np.mean(dev_ms)) * 1e-3, float(np.mean(e2e))
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e, gen_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, gen_s = float(t[0]), float(t[1]), float(t[2])
+    n_ev = toys.n_events
+    out["config4_toys"] = {
+        "workload": "toy-MC: %d toys per GPU x ~1000 events, 3 sources, 3 shape parameters x 5 anchors (125 anchors), "
+                    "100x100 templates, one parameter point per toy" % T,
+        "kernel": "k_template_partials<1,2> (fused template lookup + morph + log-sum, bit-identical to K3 + K2)",
+        "toys_per_gpu": T, "events_per_gpu": int(n_ev), "n_gpus": world, "finite_results": int(np.isfinite(res).sum()),
+        "device": {"ms": t_dev * 1e3, "toys_per_s": world * T / t_dev, "point_events_per_s": world * n_ev / t_dev},
+        "e2e": {"ms": t_e2e * 1e3, "toys_per_s": world * T / t_e2e, "point_events_per_s": world * n_ev / t_e2e,
+                "h2d_bytes": int(eng.last_h2d_bytes), "d2h_bytes": int(eng.last_d2h_bytes)},
+        "generate_s": gen_s, "load_s": load_s, "model_build_s": build_s,
+        "extrapolated_1e6_toys_s": 1e6 / (world * T / t_e2e)}
+    del ll, toys, eng
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return out
+    # ---- config 5 ----
+    t0 = time.perf_counter()
+    ll, _, names = wl.c2_api(6, 4, wl.ANCHORS_5, BINS, n_events=1000, seed=5,
+                             likelihood_config={'unbinned_engine': 'mixture'})
+    build_s = time.perf_counter() - t0
+    base_mu = float(np.sum(ll.base_model.expected_events()))
+    n_target = args.c5_events
+    t0 = time.perf_counter()
+    td = ll.base_model.simulate_toys(1, livetime_days=n_target / base_mu, seed=50)
+    d = td.to_records()
+    gen_s = time.perf_counter() - t0
+    del td
+    t0 = time.perf_counter()
+    ll.set_data(d)
+    torch.cuda.synchronize()
+    set_data_s = time.perf_counter() - t0
+    N = len(d)
+    lt = n_target / base_mu
+    rng = np.random.default_rng(51)
+    x0 = np.concatenate([rng.uniform(0.8, 1.2, size=6), rng.uniform(-1.9, 1.9, size=4)])
+    fd = np.repeat(x0[None, :], 11, 0)
+    for j in range(10):
+        fd[j + 1, j] += 1.4901161193847656e-08
+    res5 = {}
+    eng = ll._engine
+    hbm = measured_peaks()[0]["hbm_gbs"]
+    for P, table in ((1, fd[:1]), (11, fd)):
+        ll.batch(table, names, livetime_days=lt)
+        ts = []
+        for _ in range(5):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = ll.batch(table, names, livetime_days=lt)
+            ts.append(time.perf_counter() - t0)
+        # device-resident: K1 + mix + K5b + finalize
+        zs, mult = ll._rows_from_params(table, names)
+        sched, _ = eng.single_schedule(zs)
+        zs_d, mult_d, scale_d, _, _ = eng._upload_points(zs, mult, np.full(P, lt / ll.pdf_base_config['livetime_days']), None)
+        dm = []
+        for k in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            o = eng._setup_terms(P, zs_d, mult_d, scale_d, None)
+            eng.run_schedule(sched, o)
+            b.record()
+            torch.cuda.synchronize()
+            if k:
+                dm.append(a.elapsed_time(b))
+        km = []
+        for k in range(6):                                         # the streaming kernel alone
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.mixture_kernel_only(sched, o)
+            b.record()
+            torch.cuda.synchronize()
+            if k:
+                km.append(a.elapsed_time(b))
+        t_dev, t_e2e, t_k = float(np.mean(dm)) * 1e-3, float(np.mean(ts)), float(np.mean(km)) * 1e-3
+        bytes_ev = 4 + 8 * eng.n_space                             # prepared event: bin (i32) + fractions
+        res5["P%d" % P] = {"device_ms": t_dev * 1e3, "e2e_ms": t_e2e * 1e3, "point_events_per_s_device": P * N / t_dev,
+                           "point_events_per_s_e2e": P * N / t_e2e, "finite": bool(np.all(np.isfinite(r))),
+                           "roofline": {"kernel": "k_mixture_partials<%d,2>" % sched["group_points"], "bound": "hbm",
+                                        "ms": t_k * 1e3, "bytes_alg": sched["n_groups"] * N * bytes_ev,
+                                        "achieved": sched["n_groups"] * N * bytes_ev / t_k / 1e9, "peak": hbm,
+                                        "unit": "GB/s", "frac": sched["n_groups"] * N * bytes_ev / t_k / 1e9 / hbm,
+                                        "share_of_evaluation": t_k / t_dev}}
+    out["config5_large_dataset"] = {
+        "workload": "large-dataset fit: %d events on this GPU (full config: 1e8 over 8 GPUs = 1.25e7 per GPU), 6 sources, "
+                    "4 shape parameters x 5 anchors (625 anchors), 100x100 templates" % N,
+        "kernel": "k_template_mix + k_mixture_partials<NP,2> (mixture form: one lookup per point-event, events sorted "
+                  "by bin, prepared events streamed once per group of <= 8 points)",
+        "bytes_per_event": 4 + 8 * eng.n_space, "n_events": int(N), **res5,
+        "generate_s": gen_s, "set_data_s": set_data_s, "model_build_s": build_s}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_own_arm(args):
     import torch
@@ -463,6 +610,13 @@ def run_own_arm(args):
                        "plain_read_gbs_this_run": float(max(rd))}
         del big
 
+    # ---- the other BASELINE configs on the template-space engine (informational; the headline stays config 2) ----
+    other = None
+    if not args.skip_other:
+        del flush
+        torch.cuda.empty_cache()
+        other = other_configs(args, rank, world, device)
+
     # ---- reduce over ranks -------------------------------------------------------------------------
     total_ms_max, e2e_total_max = total_ms, e2e_total
     if world > 1:
@@ -483,7 +637,7 @@ def run_own_arm(args):
             kname = ("k_unbinned_mma<K4=%d> (DMMA.8x8x4 contraction over K=C*S=%d, per-warp TMA ring)"
                      % ((C * S + 3) // 4, C * S) if plan.kernel == 'mma'
                      else "k_unbinned_grouped<%d> (threads=points, TMA-staged event tiles)" % C)
-            roofline = {"kernel": kname, "bound": "fp64", "achieved": flops_alg / k2 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+            roofline = {"kernel": kname, "bound": "tensor", "pipe": "fp64 (DMMA.8x8x4 = the FP64 tensor instruction; it shares one pipe with DFMA)", "achieved": flops_alg / k2 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": flops_alg / k2 / 1e12 / fp64_peak,
                         "traffic": ncu_traffic("scan" if plan.kernel == 'mma' else "legacy_scan"),
                         "peak_source": "max(bi_bench_fp64_fma, bi_bench_fp64_mma) measured in this run: DFMA and DMMA "
@@ -513,7 +667,8 @@ def run_own_arm(args):
                 "plan": sched if sched is not None else
                 {"grouped_points": int(n_grouped), "stream_points": int(len(plan.stream_points)),
                  "work_items": int(len(plan.work))},
-                "step_ms_min_max": [float(np.min(step_ms)), float(np.max(step_ms))]}
+                "step_ms_min_max": [float(np.min(step_ms)), float(np.max(step_ms))],
+                "other_configs": other}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -535,6 +690,9 @@ def main():
     ap.add_argument("--kernel", default=None, choices=[None, "mma", "grouped", "stream"],
                     help="force a K2 kernel for the scan (default: the engine's own choice)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-other", action="store_true", help="skip the config-4 / config-5 template-engine runs")
+    ap.add_argument("--toys", type=int, default=100000, help="config 4: toys per GPU")
+    ap.add_argument("--c5-events", type=int, default=100000000, help="config 5: events on this GPU")
     ap.add_argument("--ref-points-per-core", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -67,8 +67,8 @@ SIGNATURES = {
                                             _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                             _c_void_p, _c_void_p, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _i64,
                                             _c_void_p, _c_void_p, _f64, _c_void_p, _c_void_p]),
-    "bi_template_finalize": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p,
-                                            _c_void_p, _c_void_p]),
+    "bi_template_finalize": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i64,
+                                            _c_void_p, _c_void_p, _c_void_p]),
     "bi_template_mix": (ctypes.c_int, [_c_void_p, _i64, _i64, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                        _i64, _c_void_p, _c_void_p]),
     "bi_mixture_partials": (ctypes.c_int, [_c_void_p, _i32, _c_void_p, _i32, _c_void_p, _c_void_p, _i64, _c_void_p,

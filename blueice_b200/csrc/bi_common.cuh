@@ -138,6 +138,29 @@ __device__ __forceinline__ double bi_fix_density(double p_nansum, double outlier
     return p_nansum;
 }
 
+// u = ((0 + src[first]) + src[first + 256]) + ...  -- one lane of the canonical total; the loads of 32 (then 8) terms are
+// issued together (the chain of adds is short, the latency of dependent-looking loads is what costs)
+__device__ __forceinline__ double bi_strided_sum(const double* __restrict__ src, int64_t first, int64_t n) {
+    double u = 0.0;
+    int64_t j = first;
+    for (; j + 31 * 256 < n; j += 32 * 256) {
+        double t[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t[i] = src[j + i * 256];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) u = __dadd_rn(u, t[i]);
+    }
+    for (; j + 7 * 256 < n; j += 8 * 256) {
+        double t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = src[j + i * 256];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u = __dadd_rn(u, t[i]);
+    }
+    for (; j < n; j += 256) u = __dadd_rn(u, src[j]);
+    return u;
+}
+
 __device__ __forceinline__ double bi_warp_sum_xor(double v) {
 #pragma unroll
     for (int k = 1; k < 32; k <<= 1) v += __shfl_xor_sync(BI_FULL_MASK, v, k);

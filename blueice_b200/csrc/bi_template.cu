@@ -17,6 +17,9 @@
 // A unit = (pair group, superblock of 512 events); one warp per unit, lane = event.
 #include "bi_space.cuh"
 
+#ifndef BI_TS_UNROLL
+#define BI_TS_UNROLL 2      /* 2, 4, 8 measured equal on B200: the gathers are L2-throughput bound */
+#endif
 #define BI_TS_THREADS 128
 #define BI_TS_WARPS (BI_TS_THREADS / 32)
 #define BI_RANGE_LO ((1023 - 126) << 20)
@@ -188,42 +191,58 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
             double p[NP];
 #pragma unroll
             for (int q = 0; q < NP; ++q) p[q] = 0.0;
-#pragma unroll 2
-            for (int k = 0; k < K; ++k) {
+            constexpr int UNROLL_K = BI_TS_UNROLL;
+#pragma unroll UNROLL_K
+            for (int k = 0; k < K; ++k) {                            // independent L2 gathers: the more in flight the better
                 const double r = bi_ts_lookup<NS>(T + rowoff[k] + base, sp, y);
 #pragma unroll
                 for (int q = 0; q < NP; ++q) p[q] = fma(r, coef_s[q * K + k], p[q]);
             }
+            // range test + canonical tree: pair (events 2j, 2j+1) -> quad (octets 0,1 / 2,3) -> oct; lanes of one class
+            // agree.  Every tree level runs over all points before the next one (no serialisation behind the shuffles).
+            const unsigned class_mask = 0x03030303u << (2 * t_class);       // lanes of class t: 8n + 2t + {0, 1}
+            unsigned bad_any = 0;
+            unsigned bad[NP];
+            double v[NP];
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 if (!valid) p[q] = 1.0;                             // events >= N count as p = 1
                 const bool in_range = (unsigned)(__double2hiint(p[q]) - BI_RANGE_LO) < BI_RANGE_SPAN;
-                const unsigned bad = ~__ballot_sync(BI_FULL_MASK, in_range);
-                // canonical tree: pair (events 2j, 2j+1) -> quad (octets 0,1 / 2,3) -> oct; lanes of one class agree
-                double v = __dmul_rn(p[q], __shfl_xor_sync(BI_FULL_MASK, p[q], 1));
-                v = __dmul_rn(v, __shfl_xor_sync(BI_FULL_MASK, v, 8));
-                v = __dmul_rn(v, __shfl_xor_sync(BI_FULL_MASK, v, 16));
+                bad[q] = ~__ballot_sync(BI_FULL_MASK, in_range);
+                if ((live >> q) & 1u) bad_any |= bad[q];
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q) v[q] = __dmul_rn(p[q], __shfl_xor_sync(BI_FULL_MASK, p[q], 1));
+#pragma unroll
+            for (int q = 0; q < NP; ++q) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 8));
+#pragma unroll
+            for (int q = 0; q < NP; ++q) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 16));
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
                 double m;
                 int e;
-                bi_split(v, &m, &e);
-                // lanes of class t: 8n + 2t + {0, 1}, n = 0..3
-                const unsigned class_mask = 0x03030303u << (2 * t_class);
-                const bool class_bad = (bad & class_mask) != 0;
-                if (class_bad) { m = 1.0; e = 0; }
+                bi_split(v[q], &m, &e);
+                if (bad[q] & class_mask) { m = 1.0; e = 0; }
                 M[q] = __dmul_rn(M[q], m);
                 E[q] += e;
-                if (bad && ((live >> q) & 1u)) {                    // warp-uniform; rare: reference-semantics fallback
-                    double l = 0.0;
-                    if (class_bad && valid) {
-                        const int64_t pt = point[q];
-                        l = log(bi_ts_slow_density<NS>(T, rowoff, base, sp, y, K, S, term_source, wterm + pt * K,
-                                                       mus + pt * S, outlier));
+            }
+            if (bad_any) {                                          // warp-uniform; rare: reference-semantics fallback
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (bad[q] && ((live >> q) & 1u)) {
+                        const bool class_bad = (bad[q] & class_mask) != 0;
+                        double l = 0.0;
+                        if (class_bad && valid) {
+                            const int64_t pt = point[q];
+                            l = log(bi_ts_slow_density<NS>(T, rowoff, base, sp, y, K, S, term_source, wterm + pt * K,
+                                                           mus + pt * S, outlier));
+                        }
+                        l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
+                        l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 8));
+                        l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 16));
+                        if (class_bad) Lslow[q] = __dadd_rn(Lslow[q], l);
+                        any_slow = true;
                     }
-                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
-                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 8));
-                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 16));
-                    if (class_bad) Lslow[q] = __dadd_rn(Lslow[q], l);
-                    any_slow = true;
                 }
             }
         }
@@ -271,11 +290,128 @@ k_template_mix(const double* __restrict__ T, int64_t row_stride, int64_t bin_str
     const double* cf = coef + pt * K;
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x) {
         double acc = 0.0;
-        for (int k = 0; k < K; ++k) acc = fma(__ldg(T + (int64_t)rw[k] * row_stride + b * bin_stride), cf[k], acc);
+        int k = 0;
+        for (; k + 8 <= K; k += 8) {                                 // 8 independent loads in flight, then the chain
+            double t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = __ldg(T + (int64_t)rw[k + i] * row_stride + b * bin_stride);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = fma(t[i], cf[k + i], acc);
+        }
+        for (; k < K; ++k) acc = fma(__ldg(T + (int64_t)rw[k] * row_stride + b * bin_stride), cf[k], acc);
         tmix[q * n_bins + b] = acc;
     }
 }
 
+// lookup in a mixture template with PRE-MULTIPLIED corner weights (this family's own operation order):
+//     w_c = ((1 * t_0) * t_1) ...  per event, r = fma chain over the corners c of V[c] * w_c  (all terms positive)
+template <int NS>
+__device__ __forceinline__ void bi_mix_weights(const double (&y)[NS > 0 ? NS : 1], double (&w)[1 << NS]) {
+#pragma unroll
+    for (int c = 0; c < (1 << NS); ++c) {
+        double v = 1.0;
+#pragma unroll
+        for (int d = 0; d < NS; ++d) v = __dmul_rn(v, ((c >> (NS - 1 - d)) & 1) ? y[d] : __dsub_rn(1.0, y[d]));
+        w[c] = v;
+    }
+}
+template <int NS>
+__device__ __forceinline__ double bi_mix_lookup(const double* __restrict__ V, const BiTsSpace& sp, const double (&w)[1 << NS]) {
+    double r = __dmul_rn(__ldg(V), w[0]);
+#pragma unroll
+    for (int c = 1; c < (1 << NS); ++c) r = fma(__ldg(V + sp.corner_off[c]), w[c], r);
+    return r;
+}
+
+// One canonical group (32 events) of one superblock per HALF-WARP: lane l16 of the half owns the adjacent events
+// 2 l16, 2 l16 + 1 (one canonical pair), so the pair product is formed in the lane and the tree needs two shuffle
+// levels; the two halves of a warp walk two consecutive superblocks in lock step.
+// FULL: both superblocks hold 512 events (no masking).
+template <int NP, int NS, bool FULL>
+__device__ __forceinline__ void bi_mix_group(const double* const (&V)[NP], const BiTsSpace& sp, const int (&bin)[2],
+                                             const double (&y)[2][NS > 0 ? NS : 1], int n_left, int l16, unsigned half_shift,
+                                             unsigned live, double outlier, double (&M)[NP], int (&E)[NP],
+                                             double (&Lslow)[NP], bool& any_slow) {
+    // n_left: events of this half's superblock from this group's first event on (may be <= 0)
+    const bool valid0 = FULL || 2 * l16 < n_left, valid1 = FULL || 2 * l16 + 1 < n_left;
+    double w0[1 << NS], w1[1 << NS];
+    bi_mix_weights<NS>(y[0], w0);
+    bi_mix_weights<NS>(y[1], w1);
+    double p0[NP], p1[NP], v[NP];
+    unsigned bad[NP], bad_any = 0;
+    const unsigned class_mask = (0x1111u << (l16 & 3)) << half_shift;     // lanes of class t in this half
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        p0[q] = bi_mix_lookup<NS>(V[q] + bin[0], sp, w0);
+        p1[q] = bi_mix_lookup<NS>(V[q] + bin[1], sp, w1);
+        if (!FULL) {
+            if (!valid0) p0[q] = 1.0;                                      // events >= N count as p = 1
+            if (!valid1) p1[q] = 1.0;
+        }
+        const bool ok = ((unsigned)(__double2hiint(p0[q]) - BI_RANGE_LO) < BI_RANGE_SPAN) &&
+                        ((unsigned)(__double2hiint(p1[q]) - BI_RANGE_LO) < BI_RANGE_SPAN);
+        bad[q] = ~__ballot_sync(BI_FULL_MASK, ok);
+        if ((live >> q) & 1u) bad_any |= bad[q];
+        v[q] = __dmul_rn(p0[q], p1[q]);                                    // pair
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 4));    // quad: octets (0,1), (2,3)
+#pragma unroll
+    for (int q = 0; q < NP; ++q) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 8));    // oct
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        double m;
+        int e;
+        bi_split(v[q], &m, &e);
+        if (bad[q] & class_mask) { m = 1.0; e = 0; }
+        M[q] = __dmul_rn(M[q], m);
+        E[q] += e;
+    }
+    if (bad_any) {                                                         // rare, warp-uniform
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            if (bad[q] && ((live >> q) & 1u)) {
+                const bool class_bad = (bad[q] & class_mask) != 0;
+                double l = 0.0;
+                if (class_bad)
+                    l = __dadd_rn(valid0 ? log(bi_fix_density(p0[q], outlier)) : 0.0,
+                                  valid1 ? log(bi_fix_density(p1[q], outlier)) : 0.0);
+                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 4));
+                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 8));
+                if (class_bad) Lslow[q] = __dadd_rn(Lslow[q], l);
+                any_slow = true;
+            }
+        }
+    }
+}
+
+// prepared events of one group for this lane: two adjacent events (vector loads when the pair is 8 / 16-byte aligned)
+template <int NS>
+__device__ __forceinline__ void bi_mix_load(const int32_t* __restrict__ ev_bin, const double* __restrict__ ev_frac,
+                                            int64_t ld_frac, int64_t ev, int n_left2, bool vec, int (&bin)[2],
+                                            double (&y)[2][NS > 0 ? NS : 1]) {
+    // ev: this lane's first event; n_left2: events left from ev on (<= 0: none)
+    if (vec && n_left2 >= 2) {
+        const int2 b = *reinterpret_cast<const int2*>(ev_bin + ev);
+        bin[0] = b.x; bin[1] = b.y;
+#pragma unroll
+        for (int d = 0; d < NS; ++d) {
+            const double2 f = *reinterpret_cast<const double2*>(ev_frac + (int64_t)d * ld_frac + ev);
+            y[0][d] = f.x; y[1][d] = f.y;
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool ok = h < n_left2;
+            bin[h] = ok ? ev_bin[ev + h] : 0;
+#pragma unroll
+            for (int d = 0; d < NS; ++d) y[h][d] = ok ? ev_frac[(int64_t)d * ld_frac + ev + h] : 0.0;
+        }
+    }
+    if (NS == 0) y[0][0] = y[1][0] = 0.0;
+}
+
+// unit = (pair group, PAIR of consecutive superblocks): half-warp h walks superblock 2 * unit_sb + h
 template <int NP, int NS>
 __global__ void __launch_bounds__(BI_TS_THREADS)
 k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins, const __grid_constant__ BiTsSpace sp,
@@ -286,9 +422,10 @@ k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins, const __grid
                    const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
                    double outlier, double* __restrict__ partial) {
     constexpr int NY = NS > 0 ? NS : 1;
+    constexpr int CH = NP == 1 ? 2 : 1;                              // groups per prefetch chunk
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t_class = (lane >> 1) & 3;
-    const unsigned class_mask = 0x03030303u << (2 * t_class);
+    const int half = lane >> 4, l16 = lane & 15;
+    const unsigned half_shift = 16u * half;
     const int64_t n_warps = (int64_t)gridDim.x * BI_TS_WARPS;
 
     for (int64_t u = (int64_t)blockIdx.x * BI_TS_WARPS + warp; u < n_units; u += n_warps) {
@@ -302,25 +439,26 @@ k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins, const __grid
             }
             g = lo;
         }
-        const int64_t sb = u - unit_offset[g];
         const BiTsGroup gp = groups[g];
         const int np = gp.count < NP ? gp.count : NP;
         unsigned live = 0;
-        const double* V[NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            const int qq = q < np ? q : 0;
-            V[q] = tmix + (int64_t)(gp.first + qq) * n_bins;
-            if (q < np && status[pair_point ? pair_point[gp.first + q] : gp.first + q] == 0) live |= 1u << q;
-        }
-        if (!live) continue;
 #pragma unroll
         for (int q = 0; q < NP; ++q)
-            if (!((live >> q) & 1u)) V[q] = tmix + (int64_t)(gp.first + (__ffs(live) - 1)) * n_bins;   // a written row
+            if (q < np && status[pair_point ? pair_point[gp.first + q] : gp.first + q] == 0) live |= 1u << q;
+        if (!live) continue;
+        const double* V[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q)                                // dead slots replay a written mixture row
+            V[q] = tmix + (int64_t)(gp.first + (((live >> q) & 1u) ? q : __ffs(live) - 1)) * n_bins;
 
-        const int64_t ev_begin = dataset_offset[gp.dataset] + sb * BI_SUPERBLOCK;
-        const int64_t left = dataset_offset[gp.dataset + 1] - ev_begin;
-        const int n_ev = left < BI_SUPERBLOCK ? (int)left : BI_SUPERBLOCK;
+        const int64_t ds_begin = dataset_offset[gp.dataset], ds_end = dataset_offset[gp.dataset + 1];
+        const int64_t sb = 2 * (u - unit_offset[g]) + half;          // this half's superblock
+        const int64_t ev_begin = ds_begin + sb * BI_SUPERBLOCK;
+        const int64_t left = ds_end - ev_begin;                      // <= 0: this half has no superblock
+        const int n_ev = left < BI_SUPERBLOCK ? (left > 0 ? (int)left : 0) : BI_SUPERBLOCK;
+        const bool all_full = __all_sync(BI_FULL_MASK, n_ev == BI_SUPERBLOCK);
+        const int n_max = max(n_ev, __shfl_xor_sync(BI_FULL_MASK, n_ev, 16));
+        const bool vec = ((ev_begin | ld_frac) & 1) == 0;            // pairs 8-byte (bins) / 16-byte (fractions) aligned
 
         double M[NP], Lslow[NP];
         int E[NP];
@@ -328,67 +466,55 @@ k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins, const __grid
         for (int q = 0; q < NP; ++q) { M[q] = 1.0; E[q] = 0; Lslow[q] = 0.0; }
         bool any_slow = false;
 
-        // software pipeline: the prepared event of the next group is in flight while this one is evaluated
-        bool valid = lane < n_ev;
-        int64_t bin = valid ? (int64_t)ev_bin[ev_begin + lane] : 0;
-        double y[NY];
+        int bin[CH][2], bin_next[CH][2];
+        double y[CH][2][NY], y_next[CH][2][NY];
 #pragma unroll
-        for (int d = 0; d < NY; ++d) y[d] = (NS > 0 && valid) ? ev_frac[(int64_t)d * ld_frac + ev_begin + lane] : 0.0;
+        for (int j = 0; j < CH; ++j) {
+            const int e = j * BI_EVENT_BLOCK + 2 * l16;
+            bi_mix_load<NS>(ev_bin, ev_frac, ld_frac, ev_begin + e, n_ev - e, vec, bin[j], y[j]);
+        }
 #pragma unroll 1
-        for (int e0 = 0; e0 < n_ev; e0 += BI_EVENT_BLOCK) {
-            const bool valid_next = e0 + BI_EVENT_BLOCK + lane < n_ev;
-            const int64_t ev_next = ev_begin + e0 + BI_EVENT_BLOCK + lane;
-            const int64_t bin_next = valid_next ? (int64_t)ev_bin[ev_next] : 0;
-            double y_next[NY];
+        for (int c0 = 0; c0 < n_max; c0 += CH * BI_EVENT_BLOCK) {
 #pragma unroll
-            for (int d = 0; d < NY; ++d) y_next[d] = (NS > 0 && valid_next) ? ev_frac[(int64_t)d * ld_frac + ev_next] : 0.0;
-
+            for (int j = 0; j < CH; ++j) {
+                const int e = c0 + (CH + j) * BI_EVENT_BLOCK + 2 * l16;
+                bi_mix_load<NS>(ev_bin, ev_frac, ld_frac, ev_begin + e, n_ev - e, vec, bin_next[j], y_next[j]);
+            }
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                double p = bi_ts_lookup<NS>(V[q] + bin, sp, y);
-                if (!valid) p = 1.0;
-                const bool in_range = (unsigned)(__double2hiint(p) - BI_RANGE_LO) < BI_RANGE_SPAN;
-                const unsigned bad = ~__ballot_sync(BI_FULL_MASK, in_range);
-                double v = __dmul_rn(p, __shfl_xor_sync(BI_FULL_MASK, p, 1));
-                v = __dmul_rn(v, __shfl_xor_sync(BI_FULL_MASK, v, 8));
-                v = __dmul_rn(v, __shfl_xor_sync(BI_FULL_MASK, v, 16));
-                double m;
-                int e;
-                bi_split(v, &m, &e);
-                const bool class_bad = (bad & class_mask) != 0;
-                if (class_bad) { m = 1.0; e = 0; }
-                M[q] = __dmul_rn(M[q], m);
-                E[q] += e;
-                if (bad && ((live >> q) & 1u)) {
-                    double l = (class_bad && valid) ? log(bi_fix_density(p, outlier)) : 0.0;
-                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
-                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 8));
-                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 16));
-                    if (class_bad) Lslow[q] = __dadd_rn(Lslow[q], l);
-                    any_slow = true;
+            for (int j = 0; j < CH; ++j) {
+                const int e0 = c0 + j * BI_EVENT_BLOCK;
+                if (all_full)
+                    bi_mix_group<NP, NS, true>(V, sp, bin[j], y[j], BI_SUPERBLOCK, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
+                else if (e0 < n_max)
+                    bi_mix_group<NP, NS, false>(V, sp, bin[j], y[j], n_ev - e0, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    bin[j][h] = bin_next[j][h];
+#pragma unroll
+                    for (int d = 0; d < NY; ++d) y[j][h][d] = y_next[j][h][d];
                 }
             }
-            valid = valid_next;
-            bin = bin_next;
-#pragma unroll
-            for (int d = 0; d < NY; ++d) y[d] = y_next[d];
         }
+        // ---- close the superblocks: M = (M_0 * M_1) * (M_2 * M_3), E = sum, L = (L_0 + L_1) + (L_2 + L_3)
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             double m = M[q];
+            m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 1));
             m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 2));
-            m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 4));
             int e = E[q];
+            e += __shfl_xor_sync(BI_FULL_MASK, e, 1);
             e += __shfl_xor_sync(BI_FULL_MASK, e, 2);
-            e += __shfl_xor_sync(BI_FULL_MASK, e, 4);
             double L = bi_block_log(m, e);
             if (any_slow) {
                 double l = Lslow[q];
+                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
                 l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 2));
-                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 4));
                 L = __dadd_rn(L, l);
             }
-            if (lane == 0 && ((live >> q) & 1u)) partial[pair_partial_offset[gp.first + q] + sb] = L;
+            if (l16 == 0 && n_ev > 0 && ((live >> q) & 1u)) partial[pair_partial_offset[gp.first + q] + sb] = L;
         }
     }
 }
@@ -418,8 +544,7 @@ k_template_finalize(const double* __restrict__ partial, const int64_t* __restric
     double w[8];
 #pragma unroll
     for (int v = 0; v < 8; ++v) {                                   // virtual warp v of the 256-thread finalize
-        double u = 0.0;
-        for (int64_t j = v * 32 + lane; j < n; j += 256) u = __dadd_rn(u, src[j]);
+        double u = bi_strided_sum(src, v * 32 + lane, n);
 #pragma unroll
         for (int x = 1; x < 32; x <<= 1) u = __dadd_rn(u, __shfl_xor_sync(BI_FULL_MASK, u, x));
         w[v] = u;
@@ -427,6 +552,37 @@ k_template_finalize(const double* __restrict__ partial, const int64_t* __restric
     if (lane == 0) {
         const double total = __dadd_rn(__dadd_rn(__dadd_rn(w[0], w[1]), __dadd_rn(w[2], w[3])),
                                        __dadd_rn(__dadd_rn(w[4], w[5]), __dadd_rn(w[6], w[7])));
+        logl[q] = __dadd_rn(-musum[pt], total);
+        if (logsum) logsum[q] = total;
+    }
+}
+
+// the same total with one 256-thread CTA per pair (k_unbinned_finalize's own shape): pairs with many partials
+__global__ void __launch_bounds__(256)
+k_template_finalize_cta(const double* __restrict__ partial, const int64_t* __restrict__ pair_partial_offset,
+                        const int32_t* __restrict__ pair_point, const double* __restrict__ musum,
+                        const int32_t* __restrict__ status, double* __restrict__ logl, double* __restrict__ logsum) {
+    __shared__ double warp_tot[8];
+    const int64_t q = blockIdx.x;
+    const int t = threadIdx.x;
+    const int64_t pt = pair_point ? pair_point[q] : q;
+    if (status[pt] != 0) {                                        // block-uniform
+        if (t == 0) {
+            logl[q] = -__longlong_as_double(0x7ff0000000000000LL);
+            if (logsum) logsum[q] = 0.0;
+        }
+        return;
+    }
+    const double* src = partial + pair_partial_offset[q];
+    const int64_t n = pair_partial_offset[q + 1] - pair_partial_offset[q];
+    double u = bi_strided_sum(src, t, n);
+#pragma unroll
+    for (int x = 1; x < 32; x <<= 1) u = __dadd_rn(u, __shfl_xor_sync(BI_FULL_MASK, u, x));
+    if ((t & 31) == 0) warp_tot[t >> 5] = u;
+    __syncthreads();
+    if (t == 0) {
+        const double total = __dadd_rn(__dadd_rn(__dadd_rn(warp_tot[0], warp_tot[1]), __dadd_rn(warp_tot[2], warp_tot[3])),
+                                       __dadd_rn(__dadd_rn(warp_tot[4], warp_tot[5]), __dadd_rn(warp_tot[6], warp_tot[7])));
         logl[q] = __dadd_rn(-musum[pt], total);
         if (logsum) logsum[q] = total;
     }
@@ -550,10 +706,17 @@ extern "C" int bi_template_partials(const double* templates_dev, int64_t row_str
 
 extern "C" int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_offset_dev,
                                     const int32_t* pair_point_dev, const double* musum_dev, const int32_t* status_dev,
-                                    int64_t n_pairs, double* logl_dev, double* logsum_dev, void* stream) {
+                                    int64_t n_pairs, int64_t max_partials, double* logl_dev, double* logsum_dev,
+                                    void* stream) {
     BI_REQUIRE(n_pairs >= 0, "n_pairs < 0");
     if (n_pairs == 0) return BI_OK;
     BI_REQUIRE(pair_partial_offset_dev && musum_dev && status_dev && logl_dev, "bi_template_finalize: NULL pointer");
+    if (max_partials > 256 && n_pairs < (1LL << 31)) {            // few long pairs: one CTA each (same summation order)
+        k_template_finalize_cta<<<(unsigned)n_pairs, 256, 0, (cudaStream_t)stream>>>(
+            partial_dev, pair_partial_offset_dev, pair_point_dev, musum_dev, status_dev, logl_dev, logsum_dev);
+        BI_LAUNCH_CHECK();
+        return BI_OK;
+    }
     const int64_t blocks = (n_pairs + 7) / 8;
     k_template_finalize<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         partial_dev, pair_partial_offset_dev, pair_point_dev, musum_dev, status_dev, n_pairs, logl_dev, logsum_dev);

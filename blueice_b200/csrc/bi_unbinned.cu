@@ -199,8 +199,7 @@ k_unbinned_finalize(const double* __restrict__ partial, int64_t n_super, const d
         }
         return;
     }
-    double u = 0.0;
-    for (int64_t j = t; j < n_super; j += 256) u = __dadd_rn(u, partial[p * n_super + j]);
+    double u = bi_strided_sum(partial + p * n_super, t, n_super);
 #pragma unroll
     for (int x = 1; x < 32; x <<= 1) u = __dadd_rn(u, __shfl_xor_sync(BI_FULL_MASK, u, x));
     if ((t & 31) == 0) warp_tot[t >> 5] = u;

@@ -936,7 +936,7 @@ class TemplateUnbinnedEngine(_EngineBase):
         self.offsets_host = offsets
         self.offsets = torch.from_numpy(offsets).to(self.device)
         self.n_super_host = (np.diff(offsets) + _cabi.SUPERBLOCK - 1) // _cabi.SUPERBLOCK      # per dataset
-        self.ld_frac = max(n, 1)
+        self.ld_frac = round_up(max(n, 1), 2)                                # even: 16-byte aligned fraction pairs
         self.ev_bin = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
         linear = self.method == _cabi.LOOKUP_LINEAR
         self.ev_frac = torch.empty((self.n_space, self.ld_frac), dtype=torch.float64, device=self.device) if linear else None
@@ -957,7 +957,9 @@ class TemplateUnbinnedEngine(_EngineBase):
             order = torch.argsort(key, stable=True)
             self.ev_bin = self.ev_bin[:n][order].contiguous()
             if self.ev_frac is not None:
-                self.ev_frac = self.ev_frac[:, :n][:, order].contiguous()
+                sorted_frac = torch.empty_like(self.ev_frac)
+                sorted_frac[:, :n] = self.ev_frac[:, :n][:, order]
+                self.ev_frac = sorted_frac
             del key, order
         self._toy_schedule = None
         self._single_cache = {}
@@ -975,11 +977,13 @@ class TemplateUnbinnedEngine(_EngineBase):
         groups[:, 0], groups[:, 1] = group_first, group_count
         groups[:, 2] = pair_dataset[group_first] if n_groups else 0
         n_super_group = self.n_super_host[groups[:, 2]] if n_groups else np.zeros(0, dtype=np.int64)
+        if self.mode == 'mixture':                                           # K5b: a unit is a PAIR of superblocks
+            n_super_group = (n_super_group + 1) // 2
         unit_offset = np.zeros(n_groups + 1, dtype=np.int64)
         np.cumsum(n_super_group, out=unit_offset[1:])
         n_units = int(unit_offset[-1])
         sched = dict(n_pairs=Q, n_groups=n_groups, n_units=n_units, group_points=group_points,
-                     n_partials=int(partial_offset[-1]),
+                     n_partials=int(partial_offset[-1]), max_partials=int(n_super_pair.max()) if Q else 0,
                      pair_point=torch.from_numpy(np.ascontiguousarray(pair_point, dtype=np.int32)).to(self.device),
                      partial_offset=torch.from_numpy(partial_offset).to(self.device),
                      groups=torch.from_numpy(groups).to(self.device),
@@ -1091,10 +1095,25 @@ class TemplateUnbinnedEngine(_EngineBase):
             self.launches += 1
         _cabi.check(self.lib.bi_template_finalize(
             _cabi.dev_ptr(partial), _cabi.dev_ptr(sched["partial_offset"]), _cabi.dev_ptr(sched["pair_point"]),
-            _cabi.dev_ptr(o["musum"]), _cabi.dev_ptr(o["status"]), Q, _cabi.dev_ptr(logl), _cabi.dev_ptr(logsum),
-            self._stream()), "bi_template_finalize")
+            _cabi.dev_ptr(o["musum"]), _cabi.dev_ptr(o["status"]), Q, sched["max_partials"], _cabi.dev_ptr(logl),
+            _cabi.dev_ptr(logsum), self._stream()), "bi_template_finalize")
         self.launches += 1
         return logl, logsum
+
+    def mixture_kernel_only(self, sched, o):
+        """bi_mixture_partials alone on the mixture templates the last run_schedule left in the workspace
+        (bench / profiling: the HBM-bound kernel without K1, the template morph and the finalize)."""
+        torch = self.torch
+        Q = sched["n_pairs"]
+        tmix = self.ws.get("ts_tmix", Q * self.n_template_bins, torch.float64)
+        partial = self.ws.get("ts_partial", sched["n_partials"], torch.float64)
+        _cabi.check(self.lib.bi_mixture_partials(
+            _cabi.dev_ptr(tmix), self.n_space, _cabi.host_ptr(self.n_bins_i32), self.method,
+            _cabi.dev_ptr(self.ev_bin), _cabi.dev_ptr(self.ev_frac), self.ld_frac, _cabi.dev_ptr(self.offsets),
+            _cabi.dev_ptr(o["status"]), sched["n_groups"], sched["group_points"], _cabi.dev_ptr(sched["groups"]),
+            _cabi.dev_ptr(sched["unit_offset"]), _cabi.dev_ptr(sched["unit_group"]), sched["n_units"],
+            _cabi.dev_ptr(sched["pair_point"]), _cabi.dev_ptr(sched["partial_offset"]),
+            self.outlier_likelihood, _cabi.dev_ptr(partial), self._stream()), "bi_mixture_partials")
 
     def _evaluate(self, sched, order, zs, mult, scale, eff, return_status, return_parts):
         torch = self.torch

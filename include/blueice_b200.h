@@ -310,7 +310,8 @@ int bi_hist_lookup(const double* templates_dev, int64_t n_templates, int32_t n_s
  * Points with status != 0 are skipped (bi_template_finalize reports -inf).
  *
  * bi_template_finalize: logl[q] = -musum[point of q] + total(partials of pair q) in the canonical order of
- * bi_unbinned_finalize; pair_point_dev NULL = identity; pair_partial_offset_dev has n_pairs + 1 entries.
+ * bi_unbinned_finalize; pair_point_dev NULL = identity; pair_partial_offset_dev has n_pairs + 1 entries;
+ * max_partials = the largest number of partials of one pair (a hint: picks one CTA or one warp per pair).
  */
 #define BI_TS_MAX_TERMS 256
 #define BI_TS_GROUP_POINTS 8
@@ -329,7 +330,7 @@ int bi_template_partials(const double* templates_dev, int64_t row_stride, int64_
                          double outlier_likelihood, double* partial_dev, void* stream);
 int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_offset_dev,
                          const int32_t* pair_point_dev, const double* musum_dev, const int32_t* status_dev,
-                         int64_t n_pairs, double* logl_dev, double* logsum_dev, void* stream);
+                         int64_t n_pairs, int64_t max_partials, double* logl_dev, double* logsum_dev, void* stream);
 
 /*
  * K5b -- mixture form of the template-space likelihood: morph the TEMPLATES per point (bi_template_mix:
@@ -340,7 +341,9 @@ int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_
  * One lookup per point-event instead of n_terms; with the events of a dataset sorted by bin the template loads are
  * warp-uniform and the kernel streams the prepared events (4 + 8 * n_space bytes each) at HBM speed.
  * Requires finite templates.  tmix_dev: [n_pairs, prod(n_bins)], row q belongs to pair q; groups as in
- * bi_template_partials except that the points of a group need NOT share a hypercube cell.
+ * bi_template_partials except that the points of a group need NOT share a hypercube cell and that a unit is a PAIR
+ * of consecutive superblocks (one per half-warp): unit_offset_dev = prefix sum of ceil(superblocks / 2) per group.
+ * The lookup uses pre-multiplied corner weights, r = fma chain over corners of V[c] * w_c (this form's own order).
  */
 int bi_template_mix(const double* templates_dev, int64_t row_stride, int64_t bin_stride, int64_t n_bins,
                     int32_t n_terms, const int32_t* row_dev, const double* coef_dev, const int32_t* status_dev,
