@@ -278,6 +278,21 @@ def other_configs(args, rank, world, device):
         t = torch.tensor([t_dev, t_e2e, gen_s], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e, gen_s = float(t[0]), float(t[1]), float(t[2])
+    # per-toy maximum-likelihood fits in lock step (the Neyman construction's inner loop) on a slice of the toys
+    from blueice_b200.inference import bestfit_toys
+    n_fit = min(args.fit_toys, T)
+    fit_info = None
+    if n_fit:
+        sub = ll.base_model.simulate_toys(n_fit, livetime_days=lt, seed=40, first_toy=rank * T)
+        ll.set_toy_data(sub)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, fit_ll, info = bestfit_toys(ll, livetime_days=lt)
+        fit_s = time.perf_counter() - t0
+        fit_info = {"toys": n_fit, "free_parameters": 6, "seconds": fit_s, "toys_per_s": n_fit / fit_s,
+                    "iterations": int(info["iterations"]), "likelihood_evaluations": int(info["evaluations"]),
+                    "evaluations_per_s": info["evaluations"] / fit_s, "converged": int(info["converged"].sum())}
+        ll.set_toy_data(toys)
     n_ev = toys.n_events
     out["config4_toys"] = {
         "workload": "toy-MC: %d toys per GPU x ~1000 events, 3 sources, 3 shape parameters x 5 anchors (125 anchors), "
@@ -288,11 +303,58 @@ def other_configs(args, rank, world, device):
         "e2e": {"ms": t_e2e * 1e3, "toys_per_s": world * T / t_e2e, "point_events_per_s": world * n_ev / t_e2e,
                 "h2d_bytes": int(eng.last_h2d_bytes), "d2h_bytes": int(eng.last_d2h_bytes)},
         "generate_s": gen_s, "load_s": load_s, "model_build_s": build_s,
-        "extrapolated_1e6_toys_s": 1e6 / (world * T / t_e2e)}
+        "extrapolated_1e6_toys_s": 1e6 / (world * T / t_e2e), "lock_step_fits": fit_info}
     del ll, toys, eng
     torch.cuda.empty_cache()
     if rank != 0:
         return out
+    # ---- config 3 (binned + Beeston-Barlow; K4) ----
+    from blueice_b200.engine import BinnedEngine, MorphGrid
+    t0 = time.perf_counter()
+    axes, edges, mus3, pmf, n_model, observed = wl.c3_arrays((200, 200, 20), 4, 3, (-1., 0., 1.), seed=3)
+    beng = BinnedEngine(MorphGrid(axes), mus3.reshape(27, 4), pmf, n_model, 0)
+    beng.set_observed(observed)
+    build_s = time.perf_counter() - t0
+    del pmf, n_model
+    P3 = 256
+    zs3, mult3 = wl.scan_points(P3, 3, 4, seed=31, z_range=(-1., 1.), mult_range=(0.8, 1.2))
+    r3 = beng.evaluate(zs3, mult3)
+    zs_d, mult_d, _, _, _ = beng._upload_points(zs3, mult3, None, None)
+    zs_d, mult_d = zs_d.clone(), mult_d.clone()
+    dm = []
+    for k in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        beng.run_device(P3, zs_d, mult_d, None, None)
+        b.record()
+        torch.cuda.synchronize()
+        if k:
+            dm.append(a.elapsed_time(b))
+    ts = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        beng.evaluate(zs3, mult3)
+        ts.append(time.perf_counter() - t0)
+    B, C3, S3 = beng.n_bins, beng.grid.n_corners, beng.n_sources
+    t_dev, t_e2e = float(np.mean(dm)) * 1e-3, float(np.mean(ts))
+    # 8 * B * (C*S + C + 1) bytes per point (pmf corners, BB-source n_model corners, observed)
+    bytes_alg = 8.0 * B * (C3 * S3 + C3 + 1) * P3
+    hbm = measured_peaks()[0]["hbm_gbs"]
+    out["config3_binned_bb"] = {
+        "workload": "BinnedLogLikelihood + Beeston-Barlow: 200x200x20 bins, 4 sources, 3 shape parameters x 3 anchors "
+                    "(27 anchors), %d-point scan" % P3,
+        "kernel": "k_binned_pass<1> + k_binned_pass<2> (two passes over the bins: BB roots, then Poisson terms)",
+        "points": P3, "bins": int(B), "finite_results": int(np.isfinite(r3).sum()),
+        "device": {"ms": t_dev * 1e3, "point_bins_sources_per_s": P3 * B * S3 / t_dev},
+        "e2e": {"ms": t_e2e * 1e3, "point_bins_sources_per_s": P3 * B * S3 / t_e2e},
+        "roofline": {"bound": "hbm", "bytes_alg": bytes_alg, "achieved": bytes_alg / t_dev / 1e9, "peak": hbm,
+                     "unit": "GB/s", "frac": bytes_alg / t_dev / 1e9 / hbm,
+                     "note": "whole 5-launch evaluation; the BB form reads the corner tensors in both passes, so the "
+                             "single-pass algorithmic bytes cap this fraction near 0.5"},
+        "build_s": build_s}
+    del beng
+    torch.cuda.empty_cache()
     # ---- config 5 ----
     t0 = time.perf_counter()
     ll, _, names = wl.c2_api(6, 4, wl.ANCHORS_5, BINS, n_events=1000, seed=5,
@@ -692,6 +754,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-other", action="store_true", help="skip the config-4 / config-5 template-engine runs")
     ap.add_argument("--toys", type=int, default=100000, help="config 4: toys per GPU")
+    ap.add_argument("--fit-toys", type=int, default=5000, help="config 4: toys fitted in lock step (bestfit_toys)")
     ap.add_argument("--c5-events", type=int, default=100000000, help="config 5: events on this GPU")
     ap.add_argument("--ref-points-per-core", type=int, default=8)
     args = ap.parse_args()

@@ -1004,39 +1004,55 @@ class TemplateUnbinnedEngine(_EngineBase):
             self._toy_schedule = self._upload_schedule(idx, idx, idx, np.ones(T, dtype=np.int64), 1)
         return self._toy_schedule
 
-    def single_schedule(self, zs, dataset=0):
-        """All P points on one dataset: points bucketed by hypercube cell, cut into groups of <= TS_GROUP_POINTS
-        (the template values of an event are gathered once per group).  Returns (schedule, point order)."""
+    def _cells_for_grouping(self, zs):
+        """Host copy of the hypercube cell of every point (-1: out of range, evaluated alone and skipped on the
+        device).  The mixture form may group any points, so all in-range points share the key 0 there."""
         P = len(zs)
-        if self.grid.n_dims:
-            ok = self.grid.in_range(zs)
-            if self.mode == 'mixture':                                      # groups need not share a cell
-                cells = np.where(ok, 0, -1).astype(np.int64)
-            else:
-                cells = np.where(ok, self.grid.cell_ids(np.where(ok[:, None], zs, self.grid.axes_concat[0])), -1)
-        else:
-            cells = np.zeros(P, dtype=np.int64)
-        key = (P, dataset, cells.tobytes())
-        hit = self._single_cache.get(key)
-        if hit is not None:
-            return hit
-        order = np.argsort(cells, kind='stable')
-        sc = cells[order]
-        starts = np.flatnonzero(np.r_[True, sc[1:] != sc[:-1]]) if P else np.zeros(0, dtype=np.int64)
+        if not self.grid.n_dims:
+            return np.zeros(P, dtype=np.int64)
+        ok = self.grid.in_range(zs)
+        if self.mode == 'mixture':
+            return np.where(ok, 0, -1).astype(np.int64)
+        return np.where(ok, self.grid.cell_ids(np.where(ok[:, None], zs, self.grid.axes_concat[0])), -1)
+
+    def pair_schedule(self, dataset_index, zs):
+        """Pairs (dataset_index[q], point q): sorted by (dataset, hypercube cell) and cut into groups of at most
+        TS_GROUP_POINTS pairs that share both (the template values of an event are gathered once per group).
+        Returns (schedule, order): pair position j evaluates point order[j]."""
+        P = len(zs)
+        dataset_index = np.asarray(dataset_index, dtype=np.int64).reshape(P)
+        if P and (dataset_index.min() < 0 or dataset_index.max() >= self.n_datasets):
+            raise ValueError("dataset index outside [0, %d)" % self.n_datasets)
+        cells = self._cells_for_grouping(zs)
+        n_cells = int(np.prod(self.grid.cells_per_dim)) if self.grid.n_dims else 1
+        key = dataset_index * (n_cells + 1) + (cells + 1)
+        order = np.argsort(key, kind='stable')
+        sk = key[order]
+        starts = np.flatnonzero(np.r_[True, sk[1:] != sk[:-1]]) if P else np.zeros(0, dtype=np.int64)
         ends = np.r_[starts[1:], P] if P else starts
         np_max = _cabi.TS_GROUP_POINTS if P > 1 else 1
-        first, count = [], []
-        for s0, e0, c in zip(starts, ends, sc[starts] if P else []):
-            step = 1 if c < 0 else np_max
-            for f in range(s0, e0, step):
-                first.append(f)
-                count.append(min(step, e0 - f))
-        sched = self._upload_schedule(order, np.full(P, dataset, dtype=np.int64), np.asarray(first, dtype=np.int64),
-                                      np.asarray(count, dtype=np.int64), np_max)
-        if len(self._single_cache) >= 8:
-            self._single_cache.clear()
-        self._single_cache[key] = (sched, order)
+        step = np.where(cells[order[starts]] < 0, 1, np_max) if P else starts
+        n_chunks = -(-(ends - starts) // np.maximum(step, 1))
+        run = np.repeat(np.arange(len(starts)), n_chunks)
+        idx_in_run = np.arange(int(n_chunks.sum())) - np.repeat(np.cumsum(n_chunks) - n_chunks, n_chunks)
+        first = starts[run] + idx_in_run * step[run]
+        count = np.minimum(step[run], ends[run] - first)
+        if P and count.max() == 1:
+            np_max = 1
+        sched = self._upload_schedule(order, dataset_index[order], first.astype(np.int64), count.astype(np.int64), np_max)
         return sched, order
+
+    def single_schedule(self, zs, dataset=0):
+        """All P points on one dataset (cached while the points stay in their cells)."""
+        P = len(zs)
+        key = (P, dataset, self._cells_for_grouping(zs).tobytes())
+        hit = self._single_cache.get(key)
+        if hit is None:
+            hit = self.pair_schedule(np.full(P, dataset, dtype=np.int64), zs)
+            if len(self._single_cache) >= 8:
+                self._single_cache.clear()
+            self._single_cache[key] = hit
+        return hit
 
     # -- evaluation -------------------------------------------------------------------------------
     def _setup_terms(self, P, zs_d, mult_d, scale_d, eff_d):
@@ -1165,6 +1181,18 @@ class TemplateUnbinnedEngine(_EngineBase):
             raise ValueError("need one parameter point per dataset: got %d points for %d datasets"
                              % (len(mult), self.n_datasets))
         return self._evaluate(self.toy_schedule(), None, zs, mult, scale, eff, return_status, return_parts)
+
+    def evaluate_pairs(self, dataset_index, zs, mult, scale=None, eff=None, return_status=False):
+        """Point q on dataset dataset_index[q]: several points per toy in one pass (finite-difference batches and
+        line searches of many toy fits in lock step)."""
+        if self.mode != 'exact':
+            raise NotImplementedError("toys are evaluated by the exact template kernel: build the engine with mode='exact'")
+        P = len(mult)
+        if P == 0:
+            return (np.zeros(0), np.zeros(0, dtype=np.int32)) if return_status else np.zeros(0)
+        zs = np.asarray(zs, dtype=np.float64).reshape(P, self.grid.n_dims)
+        sched, order = self.pair_schedule(dataset_index, zs)
+        return self._evaluate(sched, order, zs, mult, scale, eff, return_status, False)
 
     def ps(self, z_row, mult_row, scale=None, eff=None, dataset=0):
         """(mus [S], ps [S, N]) of one point on one dataset, reference operation order (full_output=True): K3 on

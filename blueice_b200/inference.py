@@ -144,6 +144,139 @@ def bestfit_scipy(lf, minimize_kwargs=None, rates_in_log_space=False, pass_bound
     return fit, -res.fun
 
 
+def bestfit_toys(lf, guess=None, livetime_days=None, max_iter=60, gtol=1e-3, ftol=1e-10, fd_step=1e-5,
+                 line_search=(2.0, 1.0, 0.5, 0.25, 0.1, 0.02), **kwargs):
+    """Maximise the likelihood of EVERY toy of lf.set_toy_data over the parameters not fixed in kwargs, all toys
+    in lock step on the device (the per-toy fits of a Neyman construction; not in the reference, whose callers run
+    bestfit_scipy toy by toy, inference.py:131-178).
+
+    Projected BFGS per toy: central-difference gradients (2k points per toy) and a fixed set of trial steps
+    (len(line_search) points per toy), each evaluated for all unconverged toys by ONE batch_toys(toy_index=...)
+    pass; box bounds as make_objective reports them (rates >= 0, shape parameters inside their anchor range).
+
+    :returns: (dict name -> array [T] of best-fit values, max log likelihood [T], dict(converged=[T], iterations=int,
+              evaluations=int))"""
+    T = lf.n_toys
+    if T == 0:
+        raise ValueError("bestfit_toys needs lf.set_toy_data(...) first")
+    guess = guess or {}
+    names, start, lo, hi = [], [], [], []
+    for source_name in lf.rate_parameters.keys():
+        key = source_name + _RATE_SUFFIX
+        if key not in kwargs:
+            names.append(key); start.append(guess.get(key, 1.0)); lo.append(0.0); hi.append(np.inf)
+    for setting, (_, _, base_value) in lf.shape_parameters.items():
+        if setting in kwargs:
+            continue
+        s0 = guess.get(setting)
+        if s0 is None:
+            s0 = lf.pdf_base_config.get(setting)
+            if not isinstance(s0, (int, float)):
+                s0 = base_value
+        b = lf.get_bounds(setting)
+        names.append(setting); start.append(s0); lo.append(b[0]); hi.append(b[1])
+    if not names:
+        raise NoOpimizationNecessary("There are no parameters to fit, no optimization is necessary")
+    k = len(names)
+    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    fixed = list(kwargs.keys())
+    columns = names + fixed
+    n_eval = [0]
+
+    def minus_ll(points, toy_index):
+        cols = np.empty((len(points), k + len(fixed)))
+        cols[:, :k] = points
+        for j, key in enumerate(fixed):
+            cols[:, k + j] = kwargs[key]
+        n_eval[0] += len(points)
+        return -lf.batch_toys(cols, columns, livetime_days=livetime_days, toy_index=toy_index)
+
+    x = np.empty((T, k))
+    for j in range(k):
+        x[:, j] = np.broadcast_to(np.asarray(start[j], dtype=np.float64), (T,))
+    x = np.clip(x, lo, hi)
+    all_toys = np.arange(T)
+    f = minus_ll(x, all_toys)
+    if not np.all(np.isfinite(f)):
+        raise OptimizationFailed("the starting point has a non-finite likelihood for %d toys" % int((~np.isfinite(f)).sum()))
+    H = np.broadcast_to(np.eye(k), (T, k, k)).copy()
+    fresh = np.ones(T, dtype=bool)                 # H must be (re)built from the diagonal second differences
+    g_old, x_old = np.zeros((T, k)), x.copy()
+    converged = np.zeros(T, dtype=bool)
+    stalled = np.zeros(T, dtype=int)
+    small_gains = np.zeros(T, dtype=int)
+    eye = np.eye(k)
+    steps = np.asarray(line_search, dtype=np.float64)
+    it = 0
+    for it in range(1, max_iter + 1):
+        act = np.flatnonzero(~converged)
+        if not len(act):
+            break
+        A = len(act)
+        xa, fa = x[act], f[act]
+        # ---- central differences inside the box (one-sided where a bound is closer than the step)
+        h = fd_step * np.maximum(1.0, np.abs(xa))
+        up = np.minimum(xa + h, hi)
+        dn = np.maximum(xa - h, lo)
+        pts = np.repeat(xa[:, None, :], 2 * k, axis=1)                 # [A, 2k, k]
+        for j in range(k):
+            pts[:, 2 * j, j] = up[:, j]
+            pts[:, 2 * j + 1, j] = dn[:, j]
+        vals = minus_ll(pts.reshape(A * 2 * k, k), np.repeat(act, 2 * k)).reshape(A, 2 * k)
+        f_up, f_dn = vals[:, 0::2], vals[:, 1::2]
+        g = (f_up - f_dn) / (up - dn)
+        g = np.where(np.isfinite(g), g, 0.0)
+        # diagonal curvature from the same points (used to scale the first step and every restart)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            curv = 2.0 * ((f_up - fa[:, None]) / (up - xa) - (fa[:, None] - f_dn) / (xa - dn)) / (up - dn)
+        curv = np.where(np.isfinite(curv) & (curv > 1e-8), curv, np.nan)
+        # ---- BFGS update of the inverse Hessian with the step taken last iteration
+        sv = xa - x_old[act]
+        yv = g - g_old[act]
+        sy = np.einsum('ij,ij->i', sv, yv)
+        ok = (~fresh[act]) & (sy > 1e-10 * np.sqrt(np.einsum('ij,ij->i', yv, yv) * np.einsum('ij,ij->i', sv, sv)))
+        rho = np.where(ok, 1.0 / np.where(ok, sy, 1.0), 0.0)
+        V = eye[None] - rho[:, None, None] * sv[:, :, None] * yv[:, None, :]
+        Hn = np.einsum('aij,ajk,alk->ail', V, H[act], V) + rho[:, None, None] * sv[:, :, None] * sv[:, None, :]
+        Ha = np.where(ok[:, None, None], Hn, H[act])
+        scale = np.where(np.isnan(curv), np.nanmedian(np.where(np.isnan(curv), np.nan, 1.0 / curv), axis=1, keepdims=True),
+                         1.0 / curv)
+        scale = np.where(np.isfinite(scale), scale, 1.0)
+        H0 = scale[:, :, None] * eye[None]
+        Ha = np.where(fresh[act][:, None, None], H0, Ha)
+        # ---- projected direction: parameters pinned at a bound by the gradient do not move
+        pinned = ((xa <= lo) & (g > 0)) | ((xa >= hi) & (g < 0))
+        gp = np.where(pinned, 0.0, g)
+        d = np.where(pinned, 0.0, -np.einsum('aij,aj->ai', Ha, gp))
+        uphill = np.einsum('ij,ij->i', d, gp) >= 0
+        d = np.where(uphill[:, None], np.where(pinned, 0.0, -np.einsum('aij,aj->ai', H0, gp)), d)
+        Ha = np.where(uphill[:, None, None], H0, Ha)
+        H[act] = Ha
+        # ---- trial steps, all in one batch
+        n_ls = len(steps)
+        trial = np.clip(xa[:, None, :] + steps[None, :, None] * d[:, None, :], lo, hi)
+        ft = minus_ll(trial.reshape(A * n_ls, k), np.repeat(act, n_ls)).reshape(A, n_ls)
+        ft = np.where(np.isfinite(ft), ft, np.inf)
+        best = np.argmin(ft, axis=1)
+        fb = ft[np.arange(A), best]
+        better = fb < fa
+        g_old[act] = g
+        x_old[act] = xa
+        gain = np.where(better, fa - fb, 0.0)
+        x[act[better]] = trial[np.arange(A), best][better]
+        f[act[better]] = fb[better]
+        was_fresh = fresh[act]
+        fresh[act] = ~better                                           # failed line search: restart from the scaled diagonal
+        stalled[act] = np.where(better, 0, stalled[act] + np.where(was_fresh, 1, 0))
+        small = better & (gain <= ftol * np.maximum(1.0, np.abs(fa)))
+        small_gains[act] = np.where(small, small_gains[act] + 1, 0)
+        small_gradient = np.max(np.abs(gp * np.sqrt(scale)), axis=1) <= gtol     # gradient in units of the curvature
+        done = small_gradient | (small_gains[act] >= 2) | (stalled[act] >= 2)
+        converged[act[done]] = True
+    result = OrderedDict((n, x[:, j].copy()) for j, n in enumerate(names))
+    return result, -f, dict(converged=converged, iterations=it, evaluations=n_eval[0])
+
+
 def bestfit_minuit(lf, minimize_kwargs=None, rates_in_log_space=False, **kwargs):
     """Minimise with iminuit 1.x (optional dependency)."""
     from iminuit import Minuit

@@ -510,11 +510,16 @@ class _LazyInterpolator(object):
 class _ToyView(object):
     """Engine facade for _evaluate_rows: point t is evaluated on dataset t."""
 
-    def __init__(self, engine):
+    def __init__(self, engine, toy_index=None):
         self.engine = engine
+        self.toy_index = toy_index
         self.point_setup_host = engine.point_setup_host
 
     def evaluate(self, zs, mult, scale=None, eff=None, return_status=False):
+        if self.toy_index is not None:
+            if len(self.toy_index) != len(mult):
+                raise ValueError("toy_index must hold one toy per parameter row")
+            return self.engine.evaluate_pairs(self.toy_index, zs, mult, scale, eff, return_status=return_status)
         return self.engine.evaluate_toys(zs, mult, scale, eff, return_status=return_status)
 
 
@@ -647,15 +652,23 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
         self._toy_engine = engine
         return self
 
-    def batch_toys(self, params, names=None, livetime_days=None):
+    def batch_toys(self, params, names=None, livetime_days=None, toy_index=None):
         """Log likelihood of toy t at parameter point params[t] for all T toys of set_toy_data, one device pass.
 
-        Element t equals `self.set_data(toy_t); self(**dict(zip(names, params[t])))` bit for bit."""
+        Element t equals `self.set_data(toy_t); self(**dict(zip(names, params[t])))` bit for bit.
+        With toy_index [Q], row q of params is evaluated on toy toy_index[q] instead (any number of points per
+        toy: the finite-difference batches and line searches of many toy fits in lock step)."""
         engine = getattr(self, '_toy_engine', None)
         if engine is None:
             raise NotPreparedException("set_toy_data must be called before batch_toys")
         zs, mult = self._rows_from_params(params, names)
-        return self._evaluate_rows(_ToyView(engine), zs, mult, livetime_days, scalar=False)
+        view = _ToyView(engine, None if toy_index is None else np.asarray(toy_index, dtype=np.int64))
+        return self._evaluate_rows(view, zs, mult, livetime_days, scalar=False)
+
+    @property
+    def n_toys(self):
+        engine = getattr(self, '_toy_engine', None)
+        return 0 if engine is None else engine.n_datasets
 
     def _fill_anchor_rows(self, engine, items, d):
         """Build the per-event pdf rows in HBM (likelihood.py:557-562 -> model.py:97-99; source-wise :534-549).

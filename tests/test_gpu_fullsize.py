@@ -126,3 +126,108 @@ def test_config3_binned_full_size(bb):
     # device binning of 2e5 events into the same 8e5 bins reproduces np.histogramdd exactly
     cols = wl.events_from_counts(edges, observed, seed=1)
     assert np.array_equal(eng.histogram_events(edges, cols), observed)
+
+
+# ------------------------------------------------------------------------------------------------
+# configs 4 and 5 on the template-space engine (no dense anchor tensor), BASELINE shapes
+# ------------------------------------------------------------------------------------------------
+def test_config4_toy_mc_shape():
+    """3 sources, 3 shape parameters x 5 anchors (125 anchors), 100x100 templates, 1e5 toys x ~1000 events generated
+    on the device (1e8 events; the full config is 10 such sweeps or 8 GPUs x 1.25e5 toys), one point per toy."""
+    from blueice_b200 import toys as btoys
+    from blueice_b200.engine import MorphGrid, TemplateUnbinnedEngine
+    from oracle.pipeline import toy_loglikelihoods
+    axes, edges, templates, mus = wl.c2_arrays(3, 3, wl.ANCHORS_5, (100, 100))
+    grid = MorphGrid(axes)
+    rows = templates.reshape((125 * 3, 100, 100))
+    eng = TemplateUnbinnedEngine(grid, mus.reshape(125, 3), rows, edges)
+    centre = (2, 2, 2)
+    vol = np.outer(np.diff(edges[0]), np.diff(edges[1]))
+    cdf = np.vstack([np.cumsum((templates[centre + (s,)] * vol).ravel()) for s in range(3)])
+    cdf /= cdf[:, -1:]
+    scale = 1000.0 / mus[centre].sum()
+    T = 100000
+    coords, source, offsets, counts = btoys.generate(edges, cdf, mus[centre] * scale, T, seed=7)
+    assert abs(counts.sum(axis=1).mean() - 1000.0) < 1.0 and offsets[-1] == counts.sum()
+    eng.set_datasets(coords, offsets)
+    zs, mult = wl.scan_points(T, 3, 3, seed=4)
+    sc = np.full(T, scale)
+    got, status = eng.evaluate_toys(zs, mult, scale=sc, return_status=True)
+    assert np.all(status == 0) and np.all(np.isfinite(got))
+    # toy t through the single-dataset path (grouped schedule): same bits
+    for t in (0, 1234, T - 1):
+        assert eng.evaluate(zs[t:t + 1], mult[t:t + 1], scale=sc[:1], dataset=t)[0] == got[t]
+    # the reference's own loop (oracle) on three toys
+    pick = [3, 50000, 99998]
+    sub_off = np.concatenate([[0], np.cumsum([offsets[t + 1] - offsets[t] for t in pick])])
+    c_host = [np.concatenate([coords[k, offsets[t]:offsets[t + 1]].cpu().numpy() for t in pick]) for k in range(2)]
+    want = toy_loglikelihoods(axes, mus * scale, templates, edges, c_host, sub_off, zs[pick], mult[pick])
+    assert np.all(np.abs(got[pick] - want) <= 1e-9 * 1000)
+    # toys generated in two pieces (two ranks) are the same toys: same likelihoods, bit for bit
+    ca, _, oa, _ = btoys.generate(edges, cdf, mus[centre] * scale, 60000, seed=7)
+    cb, _, ob, _ = btoys.generate(edges, cdf, mus[centre] * scale, 40000, seed=7, first_toy=60000)
+    import torch
+    eng.set_datasets(torch.cat([ca, cb], dim=1), np.concatenate([oa, oa[-1] + ob[1:]]))
+    assert np.array_equal(eng.evaluate_toys(zs, mult, scale=sc), got)
+    # on average a toy prefers the truth (base model) over a far-away point
+    truth = eng.evaluate_toys(np.zeros((T, 3)), np.ones((T, 3)), scale=sc)
+    far = eng.evaluate_toys(np.full((T, 3), 1.5), np.ones((T, 3)), scale=sc)
+    assert truth.mean() > far.mean()
+
+
+def test_config5_large_dataset_shape():
+    """6 sources, 4 shape parameters x 5 anchors (625 anchors): 1.25e7 events (one GPU's share of the 1e8-event
+    config) on the mixture engine -- batch-shape independence, event shards adding up, agreement with the exact
+    template kernel and, on a sub-sample, with the anchor-tensor engine and the oracle."""
+    import torch
+    from blueice_b200 import toys as btoys
+    from blueice_b200.engine import MorphGrid, TemplateUnbinnedEngine
+    from oracle.pipeline import UnbinnedOracle
+    axes, edges, templates, mus = wl.c2_arrays(6, 4, wl.ANCHORS_5, (100, 100))
+    grid = MorphGrid(axes)
+    rows = templates.reshape((625 * 6, 100, 100))
+    centre = (2, 2, 2, 2)
+    vol = np.outer(np.diff(edges[0]), np.diff(edges[1]))
+    cdf = np.vstack([np.cumsum((templates[centre + (s,)] * vol).ravel()) for s in range(6)])
+    cdf /= cdf[:, -1:]
+    N_target = 12500000
+    scale = N_target / mus[centre].sum()
+    coords, _, offsets, _ = btoys.generate(edges, cdf, mus[centre] * scale, 1, seed=5)
+    N = int(offsets[-1])
+    mix = TemplateUnbinnedEngine(grid, mus.reshape(625, 6), rows, edges, mode='mixture')
+    mix.set_datasets(coords)
+    rng = np.random.default_rng(51)
+    x0m, x0z = rng.uniform(0.8, 1.2, size=6), rng.uniform(-1.9, 1.9, size=4)
+    zs = np.repeat(x0z[None], 11, 0)
+    mult = np.repeat(x0m[None], 11, 0)
+    for j in range(10):
+        (mult if j < 6 else zs)[j + 1, j if j < 6 else j - 6] += 1.4901161193847656e-08
+    sc = np.full(11, scale)
+    got = mix.evaluate(zs, mult, scale=sc)
+    assert np.all(np.isfinite(got))
+    for p in (0, 4, 10):                                            # a finite-difference batch == single evaluations
+        assert mix.evaluate(zs[p:p + 1], mult[p:p + 1], scale=sc[:1])[0] == got[p]
+    # events split into 8 superblock-aligned shards (8 GPUs): the shards' log sums add up to the whole
+    logsum, musum, _ = mix.evaluate(zs, mult, scale=sc, return_parts=True)
+    from blueice_b200.distributed import shard_bounds
+    bounds = shard_bounds(N, 8, align=512)
+    offs = np.array([b[0] for b in bounds] + [N])
+    mix.set_datasets(coords, offs)
+    total = np.zeros(11)
+    for r in range(8):
+        total = total + mix.evaluate(zs, mult, scale=sc, return_parts=True, dataset=r)[0]
+    assert np.all(np.abs(total - logsum) <= 1e-9 * N)
+    assert np.all(np.abs(total - logsum) <= 1e-12 * (np.abs(logsum) + N))
+    # exact template kernel on the same events
+    exact = TemplateUnbinnedEngine(grid, mus.reshape(625, 6), rows, edges)
+    exact.set_datasets(coords)
+    ref = exact.evaluate(zs[:2], mult[:2], scale=sc[:2])
+    assert np.all(np.abs(got[:2] - ref) <= 1e-9 * N) and np.all(np.abs(got[:2] - ref) <= 1e-12 * (np.abs(ref) + N))
+    # oracle (the reference's dense path) on the first 2000 events
+    sub = coords[:, :2000].cpu().numpy()
+    mix.set_datasets(sub)
+    small = mix.evaluate(zs[:2], mult[:2], scale=sc[:2])
+    want = UnbinnedOracle(axes, mus * scale).set_data_from_templates(templates, edges, list(sub)).batch(zs[:2], mult[:2])
+    assert np.all(np.abs(small - want) <= 1e-9 * 2000)
+    del exact, mix
+    torch.cuda.empty_cache()

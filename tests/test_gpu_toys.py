@@ -117,3 +117,50 @@ def test_model_simulate_toys_feeds_batch_toys():
         assert len(rec) == td.counts[t].sum() and set(rec.dtype.names) == {'source', 'cs1', 'cs2'}
         ll.set_data(rec)
         assert got[t] == ll(**dict(zip(names, [float(v) for v in params[t]])))
+
+
+def test_toy_index_evaluates_any_point_on_any_toy():
+    ll, d, names = wl.c2_api(n_sources=2, n_shape=2, anchors=(-1., 0., 1.), bins=(40, 30), n_events=500, seed=3)
+    td = ll.base_model.simulate_toys(30, livetime_days=0.01, seed=6)
+    ll.set_toy_data(td)
+    zs, mult = wl.scan_points(30, 2, 2, seed=12, z_range=(-1., 1.))
+    params = np.column_stack([mult, zs])
+    base = ll.batch_toys(params, names, livetime_days=0.01)
+    # several points per toy, toys in arbitrary order; finite-difference neighbours share the group of their toy
+    toy_index = np.array([5, 5, 5, 29, 0, 5, 17, 0])
+    rows = params[[5, 6, 7, 29, 0, 5, 17, 3]].copy()
+    rows[1, 0] += 1e-8
+    got = ll.batch_toys(rows, names, livetime_days=0.01, toy_index=toy_index)
+    assert got[0] == base[5] and got[5] == base[5] and got[3] == base[29] and got[4] == base[0] and got[6] == base[17]
+    for q in (1, 2, 7):
+        ll.set_data(td.to_records(int(toy_index[q])))
+        assert got[q] == ll(livetime_days=0.01, **dict(zip(names, [float(v) for v in rows[q]])))
+    with pytest.raises(ValueError):
+        ll.batch_toys(rows, names, toy_index=toy_index[:3])
+    with pytest.raises(ValueError):
+        ll.batch_toys(rows[:1], names, toy_index=[30])
+
+
+def test_bestfit_toys_matches_per_toy_scipy_fits():
+    """All toys fitted in lock step on the device reach the optimum scipy finds toy by toy (the reference's way)."""
+    from blueice_b200.inference import bestfit_scipy, bestfit_toys
+    ll, d, names = wl.c2_api(n_sources=2, n_shape=2, anchors=(-2., -1., 0., 1., 2.), bins=(40, 30), n_events=500, seed=3)
+    lt = 0.02
+    td = ll.base_model.simulate_toys(24, livetime_days=lt, seed=8)
+    ll.set_toy_data(td)
+    fit, maxll, info = bestfit_toys(ll, livetime_days=lt)
+    assert set(fit.keys()) == set(names) and maxll.shape == (24,)
+    assert info['converged'].all(), info
+    truth = ll.batch_toys(np.tile([1., 1., 0., 0.], (24, 1)), names, livetime_days=lt)
+    assert np.all(maxll >= truth)                                    # a fit is at least as good as the truth
+    for t in (0, 11, 23):
+        ll.set_data(td.to_records(t))
+        ref_fit, ref_ll = bestfit_scipy(ll, pass_bounds_to_minimizer=True,
+                                        minimize_kwargs=dict(method='L-BFGS-B'), livetime_days=lt)
+        assert maxll[t] >= ref_ll - 2e-3, (t, maxll[t], ref_ll)
+        assert abs(maxll[t] - ref_ll) <= 5e-2, (t, maxll[t], ref_ll)
+        got_ll = ll(livetime_days=lt, **{n: float(fit[n][t]) for n in names})
+        assert got_ll == maxll[t]                                    # the reported maximum is the likelihood at the fit
+    # a fixed parameter stays fixed (conditional fits of a profile-likelihood test statistic)
+    cfit, cll, _ = bestfit_toys(ll, livetime_days=lt, sig_rate_multiplier=0.0)
+    assert 'sig_rate_multiplier' not in cfit and np.all(cll <= maxll + 1e-6)
