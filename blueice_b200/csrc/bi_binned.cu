@@ -45,6 +45,25 @@ __device__ __forceinline__ double bi_morph_value(const double* __restrict__ base
     return acc;
 }
 
+// the same morph with the point's corner offsets (corner * row_stride) and weights staged in shared memory: the C loads
+// are independent of the accumulation chain, four of them are issued together
+__device__ __forceinline__ double bi_morph_staged(const double* __restrict__ base, int64_t off,
+                                                  const int64_t* __restrict__ s_off, const double* __restrict__ s_w, int C) {
+    if (C == 1) return __ldg(base + s_off[0] + off);
+    double acc = 0.0;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+        const double v0 = __ldg(base + s_off[c] + off), v1 = __ldg(base + s_off[c + 1] + off);
+        const double v2 = __ldg(base + s_off[c + 2] + off), v3 = __ldg(base + s_off[c + 3] + off);
+        acc = __dadd_rn(acc, __dmul_rn(v0, s_w[c]));
+        acc = __dadd_rn(acc, __dmul_rn(v1, s_w[c + 1]));
+        acc = __dadd_rn(acc, __dmul_rn(v2, s_w[c + 2]));
+        acc = __dadd_rn(acc, __dmul_rn(v3, s_w[c + 3]));
+    }
+    for (; c < C; ++c) acc = __dadd_rn(acc, __dmul_rn(__ldg(base + s_off[c] + off), s_w[c]));
+    return acc;
+}
+
 // scipy.stats.poisson(lam).logpmf(k) with lgk = gammaln(k + 1) precomputed
 __device__ __forceinline__ double bi_poisson_logpmf(double k, double lgk, double lam) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -81,6 +100,12 @@ __device__ __forceinline__ void bi_bb_roots(double a, double p, double U, double
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_binned_pass(const __grid_constant__ BiBinnedArgs a) {
+    // per warp: the point's corner offsets into the pmf / n_model tensors and its corner weights
+    __shared__ int64_t s_off_pmf_all[8][1 << BI_MAX_DIMS], s_off_nm_all[8][1 << BI_MAX_DIMS];
+    __shared__ double s_w_all[8][1 << BI_MAX_DIMS];
+    int64_t* s_off_pmf = s_off_pmf_all[threadIdx.x >> 5];
+    int64_t* s_off_nm = s_off_nm_all[threadIdx.x >> 5];
+    double* s_w = s_w_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -89,12 +114,21 @@ __global__ void __launch_bounds__(256) k_binned_pass(const __grid_constant__ BiB
     const int64_t row_stride = (int64_t)S * a.ld;
 
     for (int64_t task = warp_global; task < n_tasks; task += n_warps) {
-        const int64_t p = task / a.n_chunks;
-        const int64_t j = task - p * a.n_chunks;
+        // chunk-major task order: warps that run together work on the SAME 512-bin chunk for different points, so the
+        // anchor rows of the chunk (C * (S + 1) * 4 kB per hypercube cell) are served from L1 / L2 instead of HBM
+        const int64_t j = task / a.n_points;
+        const int64_t p = task - j * a.n_points;
         if (a.status[p] != 0) continue;
         const int32_t* corner = a.corner + p * C;
         const double* w = a.weight + p * C;
         const double* mu = a.mus + p * S;
+        __syncwarp();
+        for (int c = lane; c < C; c += 32) {
+            s_off_pmf[c] = (int64_t)corner[c] * row_stride;
+            s_off_nm[c] = (int64_t)corner[c] * a.ld;
+            s_w[c] = w[c];
+        }
+        __syncwarp();
 
         double sum_a = 0.0, p_cal = 0.0, mu_adj = 0.0, sum_t = 0.0;
         if (MODE != 0) {
@@ -114,16 +148,30 @@ __global__ void __launch_bounds__(256) k_binned_pass(const __grid_constant__ BiB
             if (b < a.n_bins) {
                 const double d = a.observed[b];
                 double t_b = 0.0, pmf_i = 0.0;
+                double pm_keep[8];
                 if (MODE != 0) {
                     // u_b: sum over sources in order, the BB source contributes pmf_i * 0. (likelihood.py:635-641)
                     double u = 0.0;
-                    for (int s = 0; s < S; ++s) {
-                        const double pm = bi_morph_value(a.pmf_anchor, row_stride, (int64_t)s * a.ld + b, corner, w, C);
-                        if (s == bi) pmf_i = pm;
-                        const double term = __dmul_rn(pm, s == bi ? 0.0 : mu[s]);
-                        u = (s == 0) ? term : __dadd_rn(u, term);
+                    if (S <= 8) {                                     // keep the morphed pmfs for the lambda_b sum below
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            if (s < S) {
+                                const double pm = bi_morph_staged(a.pmf_anchor, (int64_t)s * a.ld + b, s_off_pmf, s_w, C);
+                                pm_keep[s] = pm;
+                                if (s == bi) pmf_i = pm;
+                                const double term = __dmul_rn(pm, s == bi ? 0.0 : mu[s]);
+                                u = (s == 0) ? term : __dadd_rn(u, term);
+                            }
+                        }
+                    } else {
+                        for (int s = 0; s < S; ++s) {
+                            const double pm = bi_morph_staged(a.pmf_anchor, (int64_t)s * a.ld + b, s_off_pmf, s_w, C);
+                            if (s == bi) pmf_i = pm;
+                            const double term = __dmul_rn(pm, s == bi ? 0.0 : mu[s]);
+                            u = (s == 0) ? term : __dadd_rn(u, term);
+                        }
                     }
-                    const double a_b = bi_morph_value(a.nm_anchor, a.ld, b, corner, w, C);
+                    const double a_b = bi_morph_staged(a.nm_anchor, b, s_off_nm, s_w, C);
                     const double w_b = __dmul_rn(__ddiv_rn(pmf_i, a_b), sum_a);       // likelihood.py:646
                     double r1, r2;
                     bi_bb_roots(a_b, __dmul_rn(w_b, p_cal), u, d, &r1, &r2);
@@ -138,15 +186,26 @@ __global__ void __launch_bounds__(256) k_binned_pass(const __grid_constant__ BiB
                 } else {
                     // lambda_b = sum_s pmf_s * mu_s in source order (likelihood.py:667-670)
                     double lam = 0.0;
-                    for (int s = 0; s < S; ++s) {
-                        double term;
-                        if (MODE == 2 && s == bi) {
-                            term = __dmul_rn(__ddiv_rn(t_b, sum_t), mu_adj);          // :657-658
-                        } else {
-                            const double pm = bi_morph_value(a.pmf_anchor, row_stride, (int64_t)s * a.ld + b, corner, w, C);
-                            term = __dmul_rn(pm, mu[s]);
+                    if (MODE == 2 && S <= 8) {
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            if (s < S) {
+                                const double term = (s == bi) ? __dmul_rn(__ddiv_rn(t_b, sum_t), mu_adj)   // :657-658
+                                                              : __dmul_rn(pm_keep[s], mu[s]);
+                                lam = (s == 0) ? term : __dadd_rn(lam, term);
+                            }
                         }
-                        lam = (s == 0) ? term : __dadd_rn(lam, term);
+                    } else {
+                        for (int s = 0; s < S; ++s) {
+                            double term;
+                            if (MODE == 2 && s == bi) {
+                                term = __dmul_rn(__ddiv_rn(t_b, sum_t), mu_adj);      // :657-658
+                            } else {
+                                const double pm = bi_morph_staged(a.pmf_anchor, (int64_t)s * a.ld + b, s_off_pmf, s_w, C);
+                                term = __dmul_rn(pm, mu[s]);
+                            }
+                            lam = (s == 0) ? term : __dadd_rn(lam, term);
+                        }
                     }
                     val = bi_poisson_logpmf(d, a.lgamma_obs[b], lam);                 // :674
                 }
