@@ -564,23 +564,23 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
     def _wants_template_engine(self, n_events):
         """Template-engine mode for this dataset, or None for the dense anchor tensor.
 
-        likelihood_config['unbinned_engine']: 'anchor' (default: dense per-event anchor tensor, K3 + K2);
+        likelihood_config['unbinned_engine']: 'anchor' (dense per-event anchor tensor, K3 + K2);
         'template' (K5: per-event values looked up on the fly, bit-identical to 'anchor'); 'mixture' (K5b: templates
         morphed per point, events looked up in the mixture template -- one lookup per point-event, HBM-bound; equal
-        to 'anchor' to ~1e-13 relative); 'auto' (the dense tensor unless it would exceed _TEMPLATE_ENGINE_BYTES,
-        then 'mixture', or 'template' if some template holds a non-finite value)."""
-        kind = self.config.get('unbinned_engine', 'anchor')
+        to 'anchor' to ~1e-13 relative); 'auto' (default: the dense tensor unless it would exceed
+        _TEMPLATE_ENGINE_BYTES, then 'mixture', or 'template' if some template holds a non-finite value)."""
+        kind = self.config.get('unbinned_engine', 'auto')
         if kind == 'anchor':
             return None
         if kind not in ('template', 'mixture', 'auto'):
             raise ValueError("unbinned_engine must be 'anchor', 'template', 'mixture' or 'auto'")
-        reason = self._template_engine_obstacle()
         if kind in ('template', 'mixture'):
+            reason = self._template_engine_obstacle()
             if reason:
                 raise NotImplementedError("unbinned_engine=%r: %s" % (kind, reason))
             return 'exact' if kind == 'template' else 'mixture'
         dense = 8 * self._grid.n_anchors * len(self.source_name_list) * n_events
-        if reason is not None or dense <= self._TEMPLATE_ENGINE_BYTES:
+        if dense <= self._TEMPLATE_ENGINE_BYTES or self._template_engine_obstacle() is not None:
             return None
         finite = all(np.all(np.isfinite(source.template()[0])) for _, _, source in self._anchor_items())
         return 'mixture' if finite else 'exact'
