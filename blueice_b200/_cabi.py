@@ -83,6 +83,11 @@ SIGNATURES = {
     "bi_binned_ll_batch": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _i64, _i32, _i32, _i32,
                                           _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                           _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "bi_histogramdd_toys": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _c_void_p, _i64, _i64, _c_void_p, _i64,
+                                           _c_void_p, _i64, _c_void_p]),
+    "bi_binned_ll_batch_toys": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _i64, _i32, _i32, _i32,
+                                               _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                               _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_binned_pmfs": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _i64, _i32, _i32, _i32,
                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                       _i64, _c_void_p]),

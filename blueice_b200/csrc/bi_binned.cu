@@ -23,8 +23,8 @@ struct BiBinnedArgs {
     const double* pmf_anchor;      // [G, S, ld]
     const double* nm_anchor;       // [G, ld] calibration events of the BB source (or NULL)
     const double* nm_sum_anchor;   // [G] sum over bins of nm_anchor (or NULL)
-    const double* observed;        // [B]
-    const double* lgamma_obs;      // [B]
+    const double* observed;        // [B], or [P, obs_stride] when obs_stride != 0 (one dataset per point: toys)
+    const double* lgamma_obs;      // same layout
     const int32_t* corner;         // [P, C]
     const double* weight;          // [P, C]
     const double* mus;             // [P, S]
@@ -32,7 +32,7 @@ struct BiBinnedArgs {
     const double* sum_t;           // [P] (MODE 2)
     double* partial;               // [P, n_chunks]
     int32_t* flags;                // [P]
-    int64_t ld, n_bins, n_points, n_chunks;
+    int64_t ld, n_bins, n_points, n_chunks, obs_stride;
     int32_t S, C, bb_source;
 };
 
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_binned_pass(const __grid_constant__ BiB
             const int64_t b = b0 + lane;
             double val = 0.0;
             if (b < a.n_bins) {
-                const double d = a.observed[b];
+                const double d = a.observed[p * a.obs_stride + b];
                 double t_b = 0.0, pmf_i = 0.0;
                 double pm_keep[8];
                 if (MODE != 0) {
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_binned_pass(const __grid_constant__ BiB
                             lam = (s == 0) ? term : __dadd_rn(lam, term);
                         }
                     }
-                    val = bi_poisson_logpmf(d, a.lgamma_obs[b], lam);                 // :674
+                    val = bi_poisson_logpmf(d, a.lgamma_obs[p * a.obs_stride + b], lam);   // :674
                 }
             }
 #pragma unroll
@@ -323,7 +323,22 @@ extern "C" int bi_binned_ll_batch(const double* pmf_anchor_dev, const double* n_
                                   const int32_t* corner_dev, const double* weight_dev, const double* mus_dev,
                                   const int32_t* status_dev, int64_t n_points, double* scratch_dev,
                                   double* logl_dev, double* mus_adj_dev, int32_t* flags_dev, void* stream) {
+    return bi_binned_ll_batch_toys(pmf_anchor_dev, n_model_anchor_dev, n_model_sum_anchor_dev, ld_bins, n_bins, n_sources,
+                                   n_corners, bb_source, observed_dev, lgamma_obs_dev, 0, corner_dev, weight_dev, mus_dev,
+                                   status_dev, n_points, scratch_dev, logl_dev, mus_adj_dev, flags_dev, stream);
+}
+
+extern "C" int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const double* n_model_anchor_dev,
+                                       const double* n_model_sum_anchor_dev,
+                                       int64_t ld_bins, int64_t n_bins, int32_t n_sources, int32_t n_corners,
+                                       int32_t bb_source, const double* observed_dev, const double* lgamma_obs_dev,
+                                       int64_t observed_stride,
+                                       const int32_t* corner_dev, const double* weight_dev, const double* mus_dev,
+                                       const int32_t* status_dev, int64_t n_points, double* scratch_dev,
+                                       double* logl_dev, double* mus_adj_dev, int32_t* flags_dev, void* stream) {
     BI_REQUIRE(n_points >= 0, "n_points < 0");
+    BI_REQUIRE(observed_stride == 0 || observed_stride >= n_bins, "observed_stride=%lld smaller than n_bins=%lld",
+               (long long)observed_stride, (long long)n_bins);
     if (n_points == 0) return BI_OK;
     BiBinnedArgs a;
     int rc = bi_binned_fill(&a, pmf_anchor_dev, n_model_anchor_dev, n_model_sum_anchor_dev, ld_bins, n_bins, n_sources,
@@ -331,6 +346,7 @@ extern "C" int bi_binned_ll_batch(const double* pmf_anchor_dev, const double* n_
                             status_dev, n_points);
     if (rc != BI_OK) return rc;
     BI_REQUIRE(lgamma_obs_dev && scratch_dev && logl_dev && flags_dev, "bi_binned_ll_batch: NULL pointer");
+    a.obs_stride = observed_stride;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_tasks = n_points * a.n_chunks;
     int64_t blocks = (n_tasks + 7) / 8;

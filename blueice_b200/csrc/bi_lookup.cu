@@ -114,6 +114,38 @@ k_histogramdd(const __grid_constant__ BiSpace sp, const __grid_constant__ BiPoin
     if (keep) atomicAdd(&counts[flat], 1ULL);
 }
 
+// the same binning for MANY datasets back to back (toys): event e of dataset t (binary search in the offsets)
+// increments counts[t, bin]
+__global__ void __launch_bounds__(256)
+k_histogramdd_toys(const __grid_constant__ BiSpace sp, const __grid_constant__ BiPoints pts, int n_points_total,
+                   const double* __restrict__ coords, int64_t ld_coords, int64_t n_events,
+                   const int64_t* __restrict__ offsets, int64_t n_datasets,
+                   unsigned long long* __restrict__ counts, int64_t ld_counts) {
+    __shared__ double s_pts[BI_MAX_EDGE_POINTS];
+    bi_stage_points(pts, n_points_total, s_pts);
+    const double* edges = s_pts;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_events) return;
+    int flat = 0;
+    bool keep = true;
+    for (int d = 0; d < sp.n_space; ++d) {
+        const double* e = edges + sp.offset[d];
+        const int nb = sp.n_bins[d];
+        const double x = coords[(int64_t)d * ld_coords + i];
+        int k = bi_upper_bound(e, nb + 1, x) - 1;
+        if (x == e[nb]) k = nb - 1;                           // right-most edge is inclusive
+        if (!(x >= e[0] && x <= e[nb])) keep = false;         // outside or NaN
+        flat += (keep ? k : 0) * sp.stride[d];
+    }
+    if (!keep) return;
+    int64_t lo = 0, hi = n_datasets;                          // largest t with offsets[t] <= i
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= i) lo = mid; else hi = mid;
+    }
+    atomicAdd(&counts[lo * ld_counts + flat], 1ULL);
+}
+
 // ---------------------------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------------------------
@@ -161,6 +193,28 @@ extern "C" int bi_histogramdd(int32_t n_space, const int32_t* n_bins_host, const
     const int64_t blocks = (n_events + 255) / 256;
     k_histogramdd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sp, pts, total, coords_dev, ld_coords, n_events,
                                                                       counts_dev, bin_index_dev);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}
+
+extern "C" int bi_histogramdd_toys(int32_t n_space, const int32_t* n_bins_host, const double* edges_host,
+                                   const double* coords_dev, int64_t ld_coords, int64_t n_events,
+                                   const int64_t* dataset_offset_dev, int64_t n_datasets,
+                                   unsigned long long* counts_dev, int64_t ld_counts, void* stream) {
+    BiSpace sp;
+    int rc = bi_fill_space(&sp, n_space, n_bins_host);
+    if (rc != BI_OK) return rc;
+    BiPoints pts;
+    int total = 0;
+    rc = bi_fill_points(&sp, &pts, edges_host, false, &total);
+    if (rc != BI_OK) return rc;
+    BI_REQUIRE(n_events >= 0 && n_datasets >= 0, "negative size");
+    if (n_events == 0 || n_datasets == 0) return BI_OK;
+    BI_REQUIRE(coords_dev && counts_dev && dataset_offset_dev && ld_coords >= n_events && ld_counts >= sp.n_cells,
+               "bi_histogramdd_toys: bad arguments");
+    const int64_t blocks = (n_events + 255) / 256;
+    k_histogramdd_toys<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sp, pts, total, coords_dev, ld_coords, n_events,
+                                                                           dataset_offset_dev, n_datasets, counts_dev, ld_counts);
     BI_LAUNCH_CHECK();
     return BI_OK;
 }

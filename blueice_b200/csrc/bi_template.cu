@@ -17,8 +17,8 @@
 // A unit = (pair group, superblock of 512 events); one warp per unit, lane = event.
 #include "bi_space.cuh"
 
-#ifndef BI_TS_UNROLL
-#define BI_TS_UNROLL 2      /* 2, 4, 8 measured equal on B200: the gathers are L2-throughput bound */
+#ifndef BI_TS_BATCH
+#define BI_TS_BATCH 4       /* template rows whose gathers are in flight together (K5) */
 #endif
 #define BI_TS_THREADS 128
 #define BI_TS_WARPS (BI_TS_THREADS / 32)
@@ -55,24 +55,35 @@ k_template_prepare(const __grid_constant__ BiSpace sp, const __grid_constant__ B
 // ---------------------------------------------------------------------------------------------
 // template value of one row at one prepared event, scipy's operation order (== k_hist_lookup_linear)
 // ---------------------------------------------------------------------------------------------
+// Template values of one row at one prepared event.  Linear lookups read the PAIR layout: element (row, bin) holds
+// (T[row, bin], T[row, bin + 1 along the last dimension]) in 16 aligned bytes, so the two last-dimension neighbours of
+// a lookup corner come with ONE 128-bit load (half as many scattered L2 requests, the resource that bounds K5).
 template <int NS>
-__device__ __forceinline__ double bi_ts_lookup(const double* __restrict__ V, const BiTsSpace& sp, const double (&y)[NS > 0 ? NS : 1]) {
+__device__ __forceinline__ void bi_ts_gather(const double* __restrict__ V, const BiTsSpace& sp, double (&v)[1 << NS]) {
     if constexpr (NS == 0) {
-        return __ldg(V);                                            // piecewise: the bin's value
+        v[0] = __ldg(V);                                            // piecewise: the bin's value (plain layout)
+    } else {
+#pragma unroll
+        for (int c = 0; c < (1 << NS); c += 2) {
+            const double2 t = __ldg(reinterpret_cast<const double2*>(V + (c ? sp.corner_off[c] : 0)));
+            v[c] = t.x;
+            v[c + 1] = t.y;
+        }
+    }
+}
+template <int NS>
+__device__ __forceinline__ double bi_ts_eval(const double (&v)[1 << NS], const double (&y)[NS > 0 ? NS : 1]) {
+    if constexpr (NS == 0) {
+        return v[0];
     } else if constexpr (NS == 2) {
-        // evaluate_linear_2d: r = 0; r += V00*(1-y0)*(1-y1); r += V01*(1-y0)*y1; r += V10*y0*(1-y1); r += V11*y0*y1
-        const double v00 = __ldg(V), v01 = __ldg(V + sp.corner_off[1]), v10 = __ldg(V + sp.corner_off[2]),
-                     v11 = __ldg(V + sp.corner_off[3]);
         const double u0 = __dsub_rn(1.0, y[0]), u1 = __dsub_rn(1.0, y[1]);
-        const double y1 = y[1];
         double r = 0.0;
-        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v00, u0), u1));
-        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v01, u0), y1));
-        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v10, y[0]), u1));
-        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v11, y[0]), y1));
+        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v[0], u0), u1));
+        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v[1], u0), y[1]));
+        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v[2], y[0]), u1));
+        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v[3], y[0]), y[1]));
         return r;
     } else {
-        // generic corner loop (_rgi.py:520-549): first dim slowest, weight = ((1*t0)*t1)..., value = value + V*weight
         double acc = 0.0;
 #pragma unroll
         for (int c = 0; c < (1 << NS); ++c) {
@@ -82,10 +93,17 @@ __device__ __forceinline__ double bi_ts_lookup(const double* __restrict__ V, con
                 const int bit = (c >> (NS - 1 - d)) & 1;
                 w = __dmul_rn(w, bit ? y[d] : __dsub_rn(1.0, y[d]));
             }
-            acc = __dadd_rn(acc, __dmul_rn(__ldg(V + sp.corner_off[c]), w));
+            acc = __dadd_rn(acc, __dmul_rn(v[c], w));
         }
         return acc;
     }
+}
+
+template <int NS>
+__device__ __forceinline__ double bi_ts_lookup(const double* __restrict__ V, const BiTsSpace& sp, const double (&y)[NS > 0 ? NS : 1]) {
+    double v[1 << NS];
+    bi_ts_gather<NS>(V, sp, v);
+    return bi_ts_eval<NS>(v, y);
 }
 
 // density of one event with the reference's semantics (likelihood.py:686-689), rare path
@@ -191,9 +209,24 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
             double p[NP];
 #pragma unroll
             for (int q = 0; q < NP; ++q) p[q] = 0.0;
-            constexpr int UNROLL_K = BI_TS_UNROLL;
-#pragma unroll UNROLL_K
-            for (int k = 0; k < K; ++k) {                            // independent L2 gathers: the more in flight the better
+            // BI_TS_BATCH rows at a time: all their gathers are issued before the first value is used (the kernel is
+            // bound by the latency / throughput of scattered L2 loads); the contraction keeps the term order
+            constexpr int KB = (1 << NS) <= 4 ? BI_TS_BATCH : (BI_TS_BATCH / 2 > 0 ? BI_TS_BATCH / 2 : 1);
+            int k = 0;
+#pragma unroll 1
+            for (; k + KB <= K; k += KB) {
+                double v[KB][1 << NS];
+#pragma unroll
+                for (int i = 0; i < KB; ++i) bi_ts_gather<NS>(T + rowoff[k + i] + base, sp, v[i]);
+#pragma unroll
+                for (int i = 0; i < KB; ++i) {
+                    const double r = bi_ts_eval<NS>(v[i], y);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) p[q] = fma(r, coef_s[q * K + k + i], p[q]);
+                }
+            }
+#pragma unroll 1
+            for (; k < K; ++k) {
                 const double r = bi_ts_lookup<NS>(T + rowoff[k] + base, sp, y);
 #pragma unroll
                 for (int q = 0; q < NP; ++q) p[q] = fma(r, coef_s[q * K + k], p[q]);
@@ -676,6 +709,8 @@ extern "C" int bi_template_partials(const double* templates_dev, int64_t row_str
                    partial_dev,
                "bi_template_partials: NULL device pointer");
     BI_REQUIRE(method == BI_LOOKUP_PIECEWISE || ev_frac_dev, "bi_template_partials: ev_frac_dev is NULL");
+    BI_REQUIRE(method == BI_LOOKUP_PIECEWISE || (((uintptr_t)templates_dev & 15) == 0 && (row_stride % 2) == 0 && (bin_stride % 2) == 0),
+               "bi_template_partials: the linear method reads the 16-byte aligned pair layout (even strides)");
     BiTsSpace sp;
     memset(&sp, 0, sizeof(sp));
     const int ns = method == BI_LOOKUP_LINEAR ? n_space : 0;

@@ -783,9 +783,72 @@ class BinnedEngine(_EngineBase):
             self.launches += 1
         return counts.cpu().numpy().astype(np.float64).reshape([int(b) for b in n_bins])
 
-    def run_device(self, P, zs_d, mult_d, scale_d, eff_d, want_all=False):
+    # -- many datasets, one parameter point each (binned toys) -------------------------------------------------
+    def set_observed_rows(self, observed):
+        """observed: [T, *bins] counts of T datasets (NumPy array or device tensor); point t of evaluate_toys is
+        evaluated on row t.  gammaln(k + 1) comes from a host-computed table (scipy), as in set_observed, so a toy
+        evaluates bit-identically to set_observed(row t) + evaluate."""
+        from scipy.special import gammaln
         torch = self.torch
-        if self.observed is None:
+        if isinstance(observed, torch.Tensor):
+            obs = observed.to(self.device, torch.float64).reshape(-1, self.n_bins)
+        else:
+            obs = torch.from_numpy(np.ascontiguousarray(np.asarray(observed, dtype=np.float64)).reshape(-1, self.n_bins)).to(self.device)
+        T = obs.shape[0]
+        k_max = int(obs.max().item()) if obs.numel() else 0
+        integral = bool(torch.all((obs >= 0) & (obs == torch.floor(obs)))) if obs.numel() else True
+        if not integral:
+            raise ValueError("toy histograms must hold non-negative integer counts")
+        table = torch.from_numpy(np.ascontiguousarray(gammaln(np.arange(k_max + 1, dtype=np.float64) + 1))).to(self.device)
+        self.toy_observed = torch.zeros((T, self.ld), dtype=torch.float64, device=self.device)
+        self.toy_observed[:, :self.n_bins] = obs
+        self.toy_lgamma = torch.zeros((T, self.ld), dtype=torch.float64, device=self.device)
+        self.toy_lgamma[:, :self.n_bins] = table[obs.to(torch.int64)]
+        self.n_toys = T
+        return self
+
+    def set_observed_toys(self, edges_list, coords, offsets):
+        """Bin the events of T toys on the device (np.histogramdd semantics per toy: likelihood.py:604-609 applied to
+        every toy) and keep the [T, bins] counts as the toys' observed histograms.  coords: [n_space, N] (device
+        tensor or host array), offsets [T + 1]."""
+        torch = self.torch
+        n_space = len(edges_list)
+        n_bins = _cabi.as_i32([len(e) - 1 for e in edges_list])
+        if int(np.prod(n_bins)) != self.n_bins:
+            raise ValueError("bin edges do not match the engine's %d bins" % self.n_bins)
+        edges = _cabi.as_f64(np.concatenate([np.asarray(e, dtype=np.float64) for e in edges_list]))
+        if not isinstance(coords, torch.Tensor):
+            coords = torch.from_numpy(np.ascontiguousarray(np.asarray(coords, dtype=np.float64)))
+        coords = coords.to(self.device, torch.float64).reshape(n_space, -1).contiguous()
+        offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+        T, n = len(offsets) - 1, int(coords.shape[1])
+        if offsets[0] != 0 or offsets[-1] != n or np.any(np.diff(offsets) < 0):
+            raise ValueError("dataset offsets must rise from 0 to the number of events")
+        counts = torch.zeros((max(T, 1), self.n_bins), dtype=torch.int64, device=self.device)
+        if n and T:
+            off_d = torch.from_numpy(offsets).to(self.device)
+            _cabi.check(self.lib.bi_histogramdd_toys(n_space, _cabi.host_ptr(n_bins), _cabi.host_ptr(edges),
+                                                     _cabi.dev_ptr(coords), coords.shape[1], n, _cabi.dev_ptr(off_d), T,
+                                                     _cabi.dev_ptr(counts), self.n_bins, self._stream()),
+                        "bi_histogramdd_toys")
+            self.launches += 1
+        return self.set_observed_rows(counts[:T].to(torch.float64))
+
+    def evaluate_toys(self, zs, mult, scale=None, eff=None, return_status=False):
+        """Point t on toy t (set_observed_rows / set_observed_toys).  Returns logl [T] (+ status, bb flags)."""
+        if getattr(self, 'toy_observed', None) is None:
+            raise RuntimeError("set_observed_rows / set_observed_toys must be called first")
+        if len(mult) != self.n_toys:
+            raise ValueError("need one parameter point per toy: got %d points for %d toys" % (len(mult), self.n_toys))
+        return self.evaluate(zs, mult, scale, eff, return_status, toys=True)
+
+    def run_device(self, P, zs_d, mult_d, scale_d, eff_d, want_all=False, toys=False):
+        torch = self.torch
+        if toys:
+            observed, lgamma_obs, stride = self.toy_observed, self.toy_lgamma, self.ld
+        else:
+            observed, lgamma_obs, stride = self.observed, self.lgamma_obs, 0
+        if observed is None:
             raise RuntimeError("set_observed must be called first")
         S, C = self.n_sources, self.grid.n_corners
         o = self._setup(P, zs_d, mult_d, scale_d, eff_d)
@@ -794,18 +857,18 @@ class BinnedEngine(_EngineBase):
         logl = self.ws.get("logl", P, torch.float64)
         mus_adj = self.ws.get("mus_adj", P * S, torch.float64)
         flags = self.ws.get("flags", P, torch.int32)
-        rc = self.lib.bi_binned_ll_batch(
+        rc = self.lib.bi_binned_ll_batch_toys(
             _cabi.dev_ptr(self.pmf_anchor), _cabi.dev_ptr(self.nm_anchor), _cabi.dev_ptr(self.nm_sum_anchor),
-            self.ld, self.n_bins, S, C, self.bb_source, _cabi.dev_ptr(self.observed), _cabi.dev_ptr(self.lgamma_obs),
+            self.ld, self.n_bins, S, C, self.bb_source, _cabi.dev_ptr(observed), _cabi.dev_ptr(lgamma_obs), stride,
             _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]), _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]),
             P, _cabi.dev_ptr(scratch), _cabi.dev_ptr(logl), _cabi.dev_ptr(mus_adj), _cabi.dev_ptr(flags), self._stream())
-        _cabi.check(rc, "bi_binned_ll_batch")
+        _cabi.check(rc, "bi_binned_ll_batch_toys")
         self.launches += 5 if self.bb_source >= 0 else 3
         if want_all:
             return logl, o, mus_adj, flags, scratch
         return logl
 
-    def evaluate(self, zs, mult, scale=None, eff=None, return_status=False):
+    def evaluate(self, zs, mult, scale=None, eff=None, return_status=False, toys=False):
         """Host in / host out.  Returns logl [P] (+ status [P], bb flags [P])."""
         torch = self.torch
         P = len(mult)
@@ -814,7 +877,7 @@ class BinnedEngine(_EngineBase):
             return (z, z.astype(np.int32), z.astype(np.int32)) if return_status else z
         zs = np.asarray(zs, dtype=np.float64).reshape(P, self.grid.n_dims)
         zs_d, mult_d, scale_d, eff_d, nbytes = self._upload_points(zs, mult, scale, eff)
-        logl, o, mus_adj, flags, _ = self.run_device(P, zs_d, mult_d, scale_d, eff_d, want_all=True)
+        logl, o, mus_adj, flags, _ = self.run_device(P, zs_d, mult_d, scale_d, eff_d, want_all=True, toys=toys)
         out_pin = self.ws.get("d2h", P, torch.float64, pinned=True)
         out_pin.copy_(logl, non_blocking=True)
         st_pin = self.ws.get("d2h_status", 2 * P, torch.int32, pinned=True)
@@ -864,7 +927,7 @@ class TemplateUnbinnedEngine(_EngineBase):
     per analysis dimension, shared by all templates; method: 'linear' | 'piecewise' (source.py:203,225-243)."""
 
     def __init__(self, grid, mus_anchor, templates, edges_list, method='linear', outlier_likelihood=1e-12,
-                 allow_negative=None, device=None, bin_major=None, mode='exact'):
+                 allow_negative=None, device=None, mode='exact'):
         """mode 'exact': K5, per-event values formed like the reference (bit-identical to the anchor-tensor engine).
         mode 'mixture': K5b, the templates are morphed per point and the events looked up in the mixture template
         (one lookup per point-event instead of corners x sources; events are sorted by bin once per dataset so the
@@ -894,15 +957,15 @@ class TemplateUnbinnedEngine(_EngineBase):
         if self.n_terms > _cabi.TS_MAX_TERMS:
             raise NotImplementedError("the template-space kernel supports at most %d contraction terms "
                                       "(corners x sources); got %d" % (_cabi.TS_MAX_TERMS, self.n_terms))
-        if bin_major is None:
-            bin_major = os.environ.get('BI_TS_BIN_MAJOR', '0') != '0'       # row-major measured faster (profiles/)
-        self.bin_major = bool(bin_major)
-        self.templates_rows = torch.from_numpy(t).to(self.device)             # [n_rows, B]: K3 / full_output
-        if self.bin_major:
-            # value(row, bin) at bin * n_rows + row: the K rows of a hypercube cell at one bin are a few
-            # contiguous runs (sources fastest, then the last shape parameter's two anchors)
-            self.templates = self.templates_rows.t().contiguous()
-            self.row_stride, self.bin_stride = 1, self.n_rows
+        self.templates_rows = torch.from_numpy(t).to(self.device)             # [n_rows, B]: K3 / full_output / K5b
+        linear = self.method == _cabi.LOOKUP_LINEAR
+        if linear and mode == 'exact':
+            # K5 reads the PAIR layout: (T[row, bin], T[row, bin + 1 along the last dimension]) in 16 aligned bytes, one
+            # 128-bit gather per two lookup corners; the neighbour of the last bin of an axis is never used (cell <= n - 2)
+            shift = 1 if self.n_bins_i32[-1] > 1 else 0
+            self.templates = torch.stack([self.templates_rows, torch.roll(self.templates_rows, -shift, dims=1)],
+                                         dim=2).contiguous()
+            self.row_stride, self.bin_stride = 2 * self.n_template_bins, 2
         else:
             self.templates = self.templates_rows
             self.row_stride, self.bin_stride = self.n_template_bins, 1

@@ -523,6 +523,17 @@ class _ToyView(object):
         return self.engine.evaluate_toys(zs, mult, scale, eff, return_status=return_status)
 
 
+class _BinnedToyView(object):
+    """Engine facade for _evaluate_rows: point t is evaluated on the observed histogram of toy t."""
+
+    def __init__(self, ll, engine):
+        self.ll, self.engine = ll, engine
+        self.point_setup_host = engine.point_setup_host
+
+    def evaluate(self, zs, mult, scale=None, eff=None, return_status=False):
+        return self.engine.evaluate_toys(zs, mult, scale, eff, return_status=return_status)
+
+
 class UnbinnedLogLikelihood(LogLikelihoodBase):
 
     @inherit_docstring_from(LogLikelihoodBase)
@@ -817,6 +828,44 @@ class BinnedLogLikelihood(LogLikelihoodBase):
     def batch(self, *args, **kwargs):
         self._ensure_engine()
         return LogLikelihoodBase.batch(self, *args, **kwargs)
+
+    # -- many datasets, one parameter point each (binned toys; not in the reference API) -------------------
+    @_needs_preparation
+    def set_toy_data(self, datasets, offsets=None):
+        """Load T datasets for batch_toys: every toy is binned like set_data bins one dataset (likelihood.py:604-609).
+
+        datasets: a device-resident blueice_b200.toys.ToyData (Model.simulate_toys), a sequence of T datasets, or ONE
+        dataset holding all toys back to back together with offsets [T + 1]."""
+        from .toys import ToyData
+        dimnames, bins = zip(*self.base_model.config['analysis_space'])
+        if isinstance(datasets, ToyData):
+            coords, offsets = datasets.coords, datasets.offsets
+        elif offsets is None:
+            sizes = [len(d) for d in datasets]
+            offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            coords = np.empty((len(bins), int(offsets[-1])), dtype=np.float64)
+            for t, d in enumerate(datasets):
+                for k, c in enumerate(self.base_model.to_analysis_dimensions(d)):
+                    coords[k, offsets[t]:offsets[t + 1]] = c
+        else:
+            coords = np.asarray([np.asarray(c, dtype=np.float64) for c in self.base_model.to_analysis_dimensions(datasets)])
+        if self._engine is None:
+            self._engine = self._build_engine()
+            self._observed_dirty = True
+        self._engine.set_observed_toys(bins, coords, offsets)
+        return self
+
+    @property
+    def n_toys(self):
+        return 0 if self._engine is None else getattr(self._engine, 'n_toys', 0)
+
+    def batch_toys(self, params, names=None, livetime_days=None):
+        """Log likelihood of toy t at params[t] for all T toys of set_toy_data, one device pass; element t equals
+        `self.set_data(toy_t); self(**dict(zip(names, params[t])))` bit for bit."""
+        if self._engine is None or not getattr(self._engine, 'n_toys', 0):
+            raise NotPreparedException("set_toy_data must be called before batch_toys")
+        zs, mult = self._rows_from_params(params, names)
+        return self._evaluate_rows(_BinnedToyView(self, self._engine), zs, mult, livetime_days, scalar=False)
 
     @staticmethod
     def _raise_bb_flags(flags):

@@ -296,8 +296,11 @@ int bi_hist_lookup(const double* templates_dev, int64_t n_templates, int32_t n_s
  *   coords_dev [n_space, ld_coords]; ev_bin_dev [n_events] int32; ev_frac_dev [n_space, ld_frac] (linear only)
  *
  * bi_template_partials:
- *   templates_dev        value(row, bin) = templates_dev[row * row_stride + bin * bin_stride] (row-major: row_stride =
- *                        number of bins, bin_stride = 1; bin-major: row_stride = 1, bin_stride = number of rows)
+ *   templates_dev        element (row, bin) at templates_dev + row * row_stride + bin * bin_stride (in doubles).
+ *                        PIECEWISE: the bin's value (plain [n_rows, n_bins]: row_stride = n_bins, bin_stride = 1).
+ *                        LINEAR: the PAIR layout [n_rows, n_bins, 2] = (T[row, bin], T[row, bin + 1 along the last
+ *                        dimension]) (row_stride = 2 * n_bins, bin_stride = 2, 16-byte aligned): the two last-dimension
+ *                        neighbours of a lookup corner come with one 128-bit gather
  *   dataset_offset_dev   [n_datasets + 1] int64 first event of each dataset in ev_bin_dev / ev_frac_dev
  *   row/coef/wterm/term_source/mus/status: outputs of bi_point_setup[_sourcewise] for the points ([P, K], ..., [P])
  *   pair list            pair q evaluates point pair_point_dev[q] on one dataset; its superblock partials go to
@@ -386,6 +389,13 @@ int bi_histogramdd(int32_t n_space, const int32_t* n_bins_host, const double* ed
                    const double* coords_dev, int64_t ld_coords, int64_t n_events,
                    unsigned long long* counts_dev, int32_t* bin_index_dev, void* stream);
 
+/* bi_histogramdd for MANY datasets back to back (binned toys): dataset_offset_dev [n_datasets + 1] first event of each
+ * dataset; counts_dev [n_datasets, ld_counts] uint64, zeroed by the caller. */
+int bi_histogramdd_toys(int32_t n_space, const int32_t* n_bins_host, const double* edges_host,
+                        const double* coords_dev, int64_t ld_coords, int64_t n_events,
+                        const int64_t* dataset_offset_dev, int64_t n_datasets,
+                        unsigned long long* counts_dev, int64_t ld_counts, void* stream);
+
 /*
  * K4 -- binned Poisson log-likelihood with optional Beeston-Barlow adjustment, batch of points.
  *
@@ -414,6 +424,17 @@ int bi_binned_ll_batch(const double* pmf_anchor_dev, const double* n_model_ancho
                        const int32_t* corner_dev, const double* weight_dev, const double* mus_dev,
                        const int32_t* status_dev, int64_t n_points, double* scratch_dev,
                        double* logl_dev, double* mus_adj_dev, int32_t* flags_dev, void* stream);
+
+/* bi_binned_ll_batch with ONE DATASET PER POINT (binned toys): point p is evaluated on the observed counts
+ * observed_dev[p * observed_stride + b] (lgamma_obs_dev likewise); observed_stride = 0 is bi_binned_ll_batch. */
+int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const double* n_model_anchor_dev,
+                            const double* n_model_sum_anchor_dev,
+                            int64_t ld_bins, int64_t n_bins, int32_t n_sources, int32_t n_corners,
+                            int32_t bb_source, const double* observed_dev, const double* lgamma_obs_dev,
+                            int64_t observed_stride,
+                            const int32_t* corner_dev, const double* weight_dev, const double* mus_dev,
+                            const int32_t* status_dev, int64_t n_points, double* scratch_dev,
+                            double* logl_dev, double* mus_adj_dev, int32_t* flags_dev, void* stream);
 
 /* Morphed (and BB-adjusted) pmf grid [S, n_bins] for ONE point (full_output=True);
  * corner/weight/mus point at that point's rows, sum_t_dev at its sum over bins of A*w. */

@@ -54,8 +54,7 @@ def build(n_sources, n_shape, bin_major, mode='exact'):
     axes, edges, templates, mus = wl.c2_arrays(n_sources, n_shape, wl.ANCHORS_5, (100, 100))
     grid = MorphGrid(axes)
     rows = templates.reshape((grid.n_anchors * n_sources, 100, 100))
-    eng = TemplateUnbinnedEngine(grid, mus.reshape(grid.n_anchors, n_sources), rows, edges, 'linear', bin_major=bin_major,
-                                 mode=mode)
+    eng = TemplateUnbinnedEngine(grid, mus.reshape(grid.n_anchors, n_sources), rows, edges, 'linear', mode=mode)
     centre = tuple(len(a) // 2 for a in axes)
     return eng, templates[centre], mus[centre], edges
 

@@ -65,16 +65,16 @@ def test_single_dataset_bit_identical_to_anchor_engine(method, n_events):
     assert one[0] == got[0]
 
 
-def test_row_major_and_bin_major_layouts_agree():
+def test_pair_layout_holds_the_last_dimension_neighbours():
+    """K5's template layout for linear lookups: (T[row, bin], T[row, bin + 1 along the last dimension])."""
     axes, edges, templates, mus = _model(3, 3, (-1., 0., 1.), (25, 20))
-    x, y = wl.c2_events(templates, mus, edges, 3000, seed=9)
-    zs, mult = wl.scan_points(40, 3, 3, seed=4, z_range=(-1., 1.))
-    res = []
-    for bin_major in (False, True):
-        _, te, _, _ = _engines(axes, edges, templates, mus, bin_major=bin_major)
-        te.set_datasets(np.vstack([x, y]))
-        res.append(te.evaluate(zs, mult))
-    assert np.array_equal(res[0], res[1])
+    _, te, _, rows = _engines(axes, edges, templates, mus)
+    flat = rows.reshape(len(rows), -1)
+    pairs = te.templates.cpu().numpy()
+    assert pairs.shape == (len(rows), 500, 2) and te.row_stride == 1000 and te.bin_stride == 2
+    assert np.array_equal(pairs[:, :, 0], flat) and np.array_equal(pairs[:, :-1, 1], flat[:, 1:])
+    _, tp, _, _ = _engines(axes, edges, templates, mus, 'piecewise')
+    assert tp.templates.shape == (len(rows), 500) and tp.bin_stride == 1
 
 
 def test_zero_density_events_take_the_reference_outlier_path():

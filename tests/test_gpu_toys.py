@@ -164,3 +164,70 @@ def test_bestfit_toys_matches_per_toy_scipy_fits():
     # a fixed parameter stays fixed (conditional fits of a profile-likelihood test statistic)
     cfit, cll, _ = bestfit_toys(ll, livetime_days=lt, sig_rate_multiplier=0.0)
     assert 'sig_rate_multiplier' not in cfit and np.all(cll <= maxll + 1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# binned toys: every toy binned on the device, K4 with one observed histogram per point
+# ------------------------------------------------------------------------------------------------
+def _binned_model(bb):
+    from blueice_b200.engine import BinnedEngine, MorphGrid
+    axes, edges, mus, pmf, n_model, observed = wl.c3_arrays((12, 10, 4), 3, 2, (-1., 0., 1.), seed=3, total_events=3000.)
+    grid = MorphGrid(axes)
+    eng = BinnedEngine(grid, mus.reshape(9, 3), pmf, n_model if bb is not None else None, bb)
+    return eng, edges, mus, pmf
+
+
+@pytest.mark.parametrize("bb", [None, 0])
+def test_binned_toys_equal_per_toy_evaluation(bb):
+    eng, edges, mus, pmf = _binned_model(bb)
+    rng = np.random.default_rng(5)
+    T = 17
+    sizes = rng.poisson(2500, size=T)
+    sizes[4] = 0
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    n = int(offsets[-1])
+    coords = np.vstack([rng.uniform(-6.5, 6.5, n), rng.uniform(-6, 6, n), rng.uniform(0, 1, n)])   # some outside: dropped
+    coords[0, 7] = 6.0                                                  # on the right-most edge: last bin
+    eng.set_observed_toys(edges, coords, offsets)
+    # device binning of every toy == np.histogramdd of that toy
+    for t in (0, 4, T - 1):
+        ref, _ = np.histogramdd(coords[:, offsets[t]:offsets[t + 1]].T, bins=edges)
+        assert np.array_equal(eng.toy_observed[t, :eng.n_bins].cpu().numpy().reshape(ref.shape), ref)
+    zs, mult = wl.scan_points(T, 2, 3, seed=4, z_range=(-1., 1.), mult_range=(0.8, 1.2))
+    zs[2] = [1.5, 0.]                                                   # out of range -> -inf
+    got, status, flags = eng.evaluate_toys(zs, mult, return_status=True)
+    assert np.isneginf(got[2]) and status[2] != 0
+    for t in range(T):
+        ref, _ = np.histogramdd(coords[:, offsets[t]:offsets[t + 1]].T, bins=edges)
+        eng.set_observed(ref)
+        one, st1, fl1 = eng.evaluate(zs[t:t + 1], mult[t:t + 1], return_status=True)
+        assert (one[0] == got[t]) or (np.isneginf(one[0]) and np.isneginf(got[t])), (t, one[0], got[t])
+        assert fl1[0] == flags[t]
+    with pytest.raises(ValueError):
+        eng.evaluate_toys(zs[:3], mult[:3])
+
+
+def test_binned_toys_through_the_api():
+    """BinnedLogLikelihood.set_toy_data(Model.simulate_toys(...)) + batch_toys == set_data(toy) + call per toy."""
+    from blueice_b200 import BinnedLogLikelihood, HistogramPdfSource
+    ll_u, d, names = wl.c2_api(n_sources=2, n_shape=2, anchors=(-1., 0., 1.), bins=(20, 15), n_events=400, seed=3)
+    config = ll_u.pdf_base_config
+    ll = BinnedLogLikelihood(config)
+    for spec in config['sources']:
+        ll.add_rate_parameter(spec['name'])
+    for n in ('shift1', 'shift2'):
+        ll.add_shape_parameter(n, (-1., 0., 1.))
+    ll.prepare()
+    td = ll.base_model.simulate_toys(12, livetime_days=0.02, seed=9)
+    ll.set_toy_data(td)
+    assert ll.n_toys == 12
+    zs, mult = wl.scan_points(12, 2, 2, seed=12, z_range=(-1., 1.))
+    params = np.column_stack([mult, zs])
+    got = ll.batch_toys(params, names, livetime_days=0.02)
+    assert np.all(np.isfinite(got))
+    for t in (0, 5, 11):
+        ll.set_data(td.to_records(t))
+        assert got[t] == ll(livetime_days=0.02, **dict(zip(names, [float(v) for v in params[t]])))
+    # a list of record arrays gives the same toys
+    ll.set_toy_data([td.to_records(t) for t in range(12)])
+    assert np.array_equal(ll.batch_toys(params, names, livetime_days=0.02), got)
