@@ -361,58 +361,76 @@ __device__ __forceinline__ double bi_mix_lookup(const double* __restrict__ V, co
 // levels; the two halves of a warp walk two consecutive superblocks in lock step.
 // FULL: both superblocks hold 512 events (no masking).
 template <int NP, int NS, bool FULL>
-__device__ __forceinline__ void bi_mix_group(const double* const (&V)[NP], const BiTsSpace& sp, const int (&bin)[2],
-                                             const double (&y)[2][NS > 0 ? NS : 1], int n_left, int l16, unsigned half_shift,
-                                             unsigned live, double outlier, double (&M)[NP], int (&E)[NP],
+__device__ __forceinline__ void bi_mix_group(const double* __restrict__ Vbase, int64_t n_bins, int np, const BiTsSpace& sp,
+                                             const int (&bin)[2], const double (&y)[2][NS > 0 ? NS : 1], int n_left, int l16,
+                                             unsigned half_shift, unsigned live, double outlier, double (&M)[NP], int (&E)[NP],
                                              double (&Lslow)[NP], bool& any_slow) {
+    // Vbase: mixture template of the group's first pair (pair q: Vbase + q * n_bins); np <= NP pairs in the group (slots
+    // q >= np are skipped; a dead pair's row is unwritten memory whose results are ignored);
     // n_left: events of this half's superblock from this group's first event on (may be <= 0)
     const bool valid0 = FULL || 2 * l16 < n_left, valid1 = FULL || 2 * l16 + 1 < n_left;
     double w0[1 << NS], w1[1 << NS];
     bi_mix_weights<NS>(y[0], w0);
     bi_mix_weights<NS>(y[1], w1);
-    double p0[NP], p1[NP], v[NP];
-    unsigned bad[NP], bad_any = 0;
+    double v[NP];
+    unsigned class_bad_mask = 0, bad_any = 0;                              // bit q: this lane's class of pair q left the fast range
     const unsigned class_mask = (0x1111u << (l16 & 3)) << half_shift;     // lanes of class t in this half
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-        p0[q] = bi_mix_lookup<NS>(V[q] + bin[0], sp, w0);
-        p1[q] = bi_mix_lookup<NS>(V[q] + bin[1], sp, w1);
-        if (!FULL) {
-            if (!valid0) p0[q] = 1.0;                                      // events >= N count as p = 1
-            if (!valid1) p1[q] = 1.0;
+        if (NP == 1 || q < np) {
+            const double* V = Vbase + (int64_t)q * n_bins;
+            double p0 = bi_mix_lookup<NS>(V + bin[0], sp, w0);
+            double p1 = bi_mix_lookup<NS>(V + bin[1], sp, w1);
+            if (!FULL) {
+                if (!valid0) p0 = 1.0;                                     // events >= N count as p = 1
+                if (!valid1) p1 = 1.0;
+            }
+            const bool ok = ((unsigned)(__double2hiint(p0) - BI_RANGE_LO) < BI_RANGE_SPAN) &&
+                            ((unsigned)(__double2hiint(p1) - BI_RANGE_LO) < BI_RANGE_SPAN);
+            const unsigned bad = ~__ballot_sync(BI_FULL_MASK, ok);
+            if ((live >> q) & 1u) bad_any |= bad;
+            if (bad & class_mask) class_bad_mask |= 1u << q;
+            v[q] = __dmul_rn(p0, p1);                                      // pair
         }
-        const bool ok = ((unsigned)(__double2hiint(p0[q]) - BI_RANGE_LO) < BI_RANGE_SPAN) &&
-                        ((unsigned)(__double2hiint(p1[q]) - BI_RANGE_LO) < BI_RANGE_SPAN);
-        bad[q] = ~__ballot_sync(BI_FULL_MASK, ok);
-        if ((live >> q) & 1u) bad_any |= bad[q];
-        v[q] = __dmul_rn(p0[q], p1[q]);                                    // pair
     }
 #pragma unroll
-    for (int q = 0; q < NP; ++q) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 4));    // quad: octets (0,1), (2,3)
+    for (int q = 0; q < NP; ++q)
+        if (NP == 1 || q < np) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 4));    // quad: octets (0,1), (2,3)
 #pragma unroll
-    for (int q = 0; q < NP; ++q) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 8));    // oct
+    for (int q = 0; q < NP; ++q)
+        if (NP == 1 || q < np) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 8));    // oct
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-        double m;
-        int e;
-        bi_split(v[q], &m, &e);
-        if (bad[q] & class_mask) { m = 1.0; e = 0; }
-        M[q] = __dmul_rn(M[q], m);
-        E[q] += e;
+        if (NP == 1 || q < np) {
+            double m;
+            int e;
+            bi_split(v[q], &m, &e);
+            if ((class_bad_mask >> q) & 1u) { m = 1.0; e = 0; }
+            M[q] = __dmul_rn(M[q], m);
+            E[q] += e;
+        }
     }
-    if (bad_any) {                                                         // rare, warp-uniform
+    if (bad_any) {                                                         // rare, warp-uniform: the densities are formed again
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            if (bad[q] && ((live >> q) & 1u)) {
-                const bool class_bad = (bad[q] & class_mask) != 0;
-                double l = 0.0;
-                if (class_bad)
-                    l = __dadd_rn(valid0 ? log(bi_fix_density(p0[q], outlier)) : 0.0,
-                                  valid1 ? log(bi_fix_density(p1[q], outlier)) : 0.0);
-                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 4));
-                l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 8));
-                if (class_bad) Lslow[q] = __dadd_rn(Lslow[q], l);
-                any_slow = true;
+            if ((NP == 1 || q < np) && ((live >> q) & 1u)) {
+                const double* V = Vbase + (int64_t)q * n_bins;
+                double p0 = bi_mix_lookup<NS>(V + bin[0], sp, w0);
+                double p1 = bi_mix_lookup<NS>(V + bin[1], sp, w1);
+                if (!valid0) p0 = 1.0;
+                if (!valid1) p1 = 1.0;
+                const bool ok = ((unsigned)(__double2hiint(p0) - BI_RANGE_LO) < BI_RANGE_SPAN) &&
+                                ((unsigned)(__double2hiint(p1) - BI_RANGE_LO) < BI_RANGE_SPAN);
+                const unsigned bad = ~__ballot_sync(BI_FULL_MASK, ok);
+                if (bad) {
+                    const bool class_bad = (bad & class_mask) != 0;
+                    double l = 0.0;
+                    if (class_bad) l = __dadd_rn(log(bi_fix_density(p0, outlier)), log(bi_fix_density(p1, outlier)));
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 4));
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 8));
+                    if (class_bad) Lslow[q] = __dadd_rn(Lslow[q], l);
+                    any_slow = true;
+                }
             }
         }
     }
@@ -479,10 +497,7 @@ k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins, const __grid
         for (int q = 0; q < NP; ++q)
             if (q < np && status[pair_point ? pair_point[gp.first + q] : gp.first + q] == 0) live |= 1u << q;
         if (!live) continue;
-        const double* V[NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q)                                // dead slots replay a written mixture row
-            V[q] = tmix + (int64_t)(gp.first + (((live >> q) & 1u) ? q : __ffs(live) - 1)) * n_bins;
+        const double* Vbase = tmix + (int64_t)gp.first * n_bins;    // pair q of the group: Vbase + q * n_bins
 
         const int64_t ds_begin = dataset_offset[gp.dataset], ds_end = dataset_offset[gp.dataset + 1];
         const int64_t sb = 2 * (u - unit_offset[g]) + half;          // this half's superblock
@@ -517,9 +532,9 @@ k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins, const __grid
             for (int j = 0; j < CH; ++j) {
                 const int e0 = c0 + j * BI_EVENT_BLOCK;
                 if (all_full)
-                    bi_mix_group<NP, NS, true>(V, sp, bin[j], y[j], BI_SUPERBLOCK, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
+                    bi_mix_group<NP, NS, true>(Vbase, n_bins, np, sp, bin[j], y[j], BI_SUPERBLOCK, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
                 else if (e0 < n_max)
-                    bi_mix_group<NP, NS, false>(V, sp, bin[j], y[j], n_ev - e0, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
+                    bi_mix_group<NP, NS, false>(Vbase, n_bins, np, sp, bin[j], y[j], n_ev - e0, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
             }
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
