@@ -144,61 +144,20 @@ def bestfit_scipy(lf, minimize_kwargs=None, rates_in_log_space=False, pass_bound
     return fit, -res.fun
 
 
-def bestfit_toys(lf, guess=None, livetime_days=None, max_iter=60, gtol=1e-3, ftol=1e-10, fd_step=1e-5,
-                 line_search=(2.0, 1.0, 0.5, 0.25, 0.1, 0.02), **kwargs):
-    """Maximise the likelihood of EVERY toy of lf.set_toy_data over the parameters not fixed in kwargs, all toys
-    in lock step on the device (the per-toy fits of a Neyman construction; not in the reference, whose callers run
-    bestfit_scipy toy by toy, inference.py:131-178).
+def _lockstep_bfgs(minus_ll, x0, lo, hi, max_iter=60, gtol=1e-3, ftol=1e-10, fd_step=1e-5,
+                   line_search=(2.0, 1.0, 0.5, 0.25, 0.1, 0.02)):
+    """F independent box-constrained minimisations advanced in lock step.
 
-    Projected BFGS per toy: central-difference gradients (2k points per toy) and a fixed set of trial steps
-    (len(line_search) points per toy), each evaluated for all unconverged toys by ONE batch_toys(toy_index=...)
-    pass; box bounds as make_objective reports them (rates >= 0, shape parameters inside their anchor range).
-
-    :returns: (dict name -> array [T] of best-fit values, max log likelihood [T], dict(converged=[T], iterations=int,
-              evaluations=int))"""
-    T = lf.n_toys
-    if T == 0:
-        raise ValueError("bestfit_toys needs lf.set_toy_data(...) first")
-    guess = guess or {}
-    names, start, lo, hi = [], [], [], []
-    for source_name in lf.rate_parameters.keys():
-        key = source_name + _RATE_SUFFIX
-        if key not in kwargs:
-            names.append(key); start.append(guess.get(key, 1.0)); lo.append(0.0); hi.append(np.inf)
-    for setting, (_, _, base_value) in lf.shape_parameters.items():
-        if setting in kwargs:
-            continue
-        s0 = guess.get(setting)
-        if s0 is None:
-            s0 = lf.pdf_base_config.get(setting)
-            if not isinstance(s0, (int, float)):
-                s0 = base_value
-        b = lf.get_bounds(setting)
-        names.append(setting); start.append(s0); lo.append(b[0]); hi.append(b[1])
-    if not names:
-        raise NoOpimizationNecessary("There are no parameters to fit, no optimization is necessary")
-    k = len(names)
-    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
-    fixed = list(kwargs.keys())
-    columns = names + fixed
-    n_eval = [0]
-
-    def minus_ll(points, toy_index):
-        cols = np.empty((len(points), k + len(fixed)))
-        cols[:, :k] = points
-        for j, key in enumerate(fixed):
-            cols[:, k + j] = kwargs[key]
-        n_eval[0] += len(points)
-        return -lf.batch_toys(cols, columns, livetime_days=livetime_days, toy_index=toy_index)
-
-    x = np.empty((T, k))
-    for j in range(k):
-        x[:, j] = np.broadcast_to(np.asarray(start[j], dtype=np.float64), (T,))
-    x = np.clip(x, lo, hi)
-    all_toys = np.arange(T)
-    f = minus_ll(x, all_toys)
+    minus_ll(points [Q, k], fit_index [Q]) -> values [Q] evaluates point q of fit fit_index[q]; every iteration makes
+    two calls for all unconverged fits together: the 2k central-difference points (which also give the diagonal
+    curvature that scales the first step and every restart) and the trial steps of the line search.  Projected BFGS:
+    parameters pinned at a bound by the gradient do not move.  Returns (x [F, k], f [F], converged [F], iterations)."""
+    x = np.clip(np.array(x0, dtype=np.float64).reshape(-1, len(lo)), lo, hi)
+    T, k = x.shape
+    f = minus_ll(x, np.arange(T))
     if not np.all(np.isfinite(f)):
-        raise OptimizationFailed("the starting point has a non-finite likelihood for %d toys" % int((~np.isfinite(f)).sum()))
+        raise OptimizationFailed("the starting point has a non-finite likelihood for %d of the %d fits"
+                                 % (int((~np.isfinite(f)).sum()), T))
     H = np.broadcast_to(np.eye(k), (T, k, k)).copy()
     fresh = np.ones(T, dtype=bool)                 # H must be (re)built from the diagonal second differences
     g_old, x_old = np.zeros((T, k)), x.copy()
@@ -273,8 +232,109 @@ def bestfit_toys(lf, guess=None, livetime_days=None, max_iter=60, gtol=1e-3, fto
         small_gradient = np.max(np.abs(gp * np.sqrt(scale)), axis=1) <= gtol     # gradient in units of the curvature
         done = small_gradient | (small_gains[act] >= 2) | (stalled[act] >= 2)
         converged[act[done]] = True
+    return x, f, converged, it
+
+
+def bestfit_toys(lf, guess=None, livetime_days=None, max_iter=60, gtol=1e-3, ftol=1e-10, fd_step=1e-5,
+                 line_search=(2.0, 1.0, 0.5, 0.25, 0.1, 0.02), **kwargs):
+    """Maximise the likelihood of EVERY toy of lf.set_toy_data over the parameters not fixed in kwargs, all toys
+    in lock step on the device (the per-toy fits of a Neyman construction; not in the reference, whose callers run
+    bestfit_scipy toy by toy, inference.py:131-178).
+
+    Projected BFGS per toy: central-difference gradients (2k points per toy) and a fixed set of trial steps
+    (len(line_search) points per toy), each evaluated for all unconverged toys by ONE batch_toys(toy_index=...)
+    pass; box bounds as make_objective reports them (rates >= 0, shape parameters inside their anchor range).
+
+    :returns: (dict name -> array [T] of best-fit values, max log likelihood [T], dict(converged=[T], iterations=int,
+              evaluations=int))"""
+    T = lf.n_toys
+    if T == 0:
+        raise ValueError("bestfit_toys needs lf.set_toy_data(...) first")
+    guess = guess or {}
+    names, start, lo, hi = [], [], [], []
+    for source_name in lf.rate_parameters.keys():
+        key = source_name + _RATE_SUFFIX
+        if key not in kwargs:
+            names.append(key); start.append(guess.get(key, 1.0)); lo.append(0.0); hi.append(np.inf)
+    for setting, (_, _, base_value) in lf.shape_parameters.items():
+        if setting in kwargs:
+            continue
+        s0 = guess.get(setting)
+        if s0 is None:
+            s0 = lf.pdf_base_config.get(setting)
+            if not isinstance(s0, (int, float)):
+                s0 = base_value
+        b = lf.get_bounds(setting)
+        names.append(setting); start.append(s0); lo.append(b[0]); hi.append(b[1])
+    if not names:
+        raise NoOpimizationNecessary("There are no parameters to fit, no optimization is necessary")
+    k = len(names)
+    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    fixed = list(kwargs.keys())
+    columns = names + fixed
+    n_eval = [0]
+
+    def minus_ll(points, toy_index):
+        cols = np.empty((len(points), k + len(fixed)))
+        cols[:, :k] = points
+        for j, key in enumerate(fixed):
+            cols[:, k + j] = kwargs[key]
+        n_eval[0] += len(points)
+        return -lf.batch_toys(cols, columns, livetime_days=livetime_days, toy_index=toy_index)
+
+    x0 = np.empty((T, k))
+    for j in range(k):
+        x0[:, j] = np.broadcast_to(np.asarray(start[j], dtype=np.float64), (T,))
+    x, f, converged, it = _lockstep_bfgs(minus_ll, x0, lo, hi, max_iter=max_iter, gtol=gtol, ftol=ftol, fd_step=fd_step,
+                                         line_search=line_search)
     result = OrderedDict((n, x[:, j].copy()) for j, n in enumerate(names))
     return result, -f, dict(converged=converged, iterations=it, evaluations=n_eval[0])
+
+
+def profile_scan(lf, target, values, guess=None, livetime_days=None, max_iter=60, **kwargs):
+    """Profile likelihood of ONE dataset over a grid of hypotheses for `target`: the conditional fits of all
+    hypotheses (every other free parameter floated) advance in lock step, each iteration being two lf.batch passes
+    (the batched form of the loop in one_parameter_interval / plot_likelihood_ratio, inference.py:332-443).
+
+    :returns: (max log likelihood per hypothesis [H], dict name -> conditional best-fit values [H])"""
+    values = np.asarray(values, dtype=np.float64).reshape(-1)
+    H = len(values)
+    guess = guess or {}
+    fixed_kwargs = dict(kwargs)
+    fixed_kwargs[target] = 0.0                                       # the target is fixed per fit, not floated
+    names, start, lo, hi = [], [], [], []
+    for source_name in lf.rate_parameters.keys():
+        key = source_name + _RATE_SUFFIX
+        if key not in fixed_kwargs:
+            names.append(key); start.append(guess.get(key, 1.0)); lo.append(0.0); hi.append(np.inf)
+    for setting, (_, _, base_value) in lf.shape_parameters.items():
+        if setting in fixed_kwargs:
+            continue
+        s0 = guess.get(setting)
+        if s0 is None:
+            s0 = lf.pdf_base_config.get(setting)
+            if not isinstance(s0, (int, float)):
+                s0 = base_value
+        b = lf.get_bounds(setting)
+        names.append(setting); start.append(s0); lo.append(b[0]); hi.append(b[1])
+    fixed = list(kwargs.keys())
+    columns = names + [target] + fixed
+    k = len(names)
+
+    def minus_ll(points, fit_index):
+        cols = np.empty((len(points), k + 1 + len(fixed)))
+        cols[:, :k] = points
+        cols[:, k] = values[fit_index]
+        for j, key in enumerate(fixed):
+            cols[:, k + 1 + j] = kwargs[key]
+        return -lf.batch(cols, columns, livetime_days=livetime_days)
+
+    if k == 0:
+        return -minus_ll(np.zeros((H, 0)), np.arange(H)), OrderedDict()
+    x0 = np.tile(np.asarray(start, dtype=np.float64), (H, 1))
+    x, f, _, _ = _lockstep_bfgs(minus_ll, x0, np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64),
+                                max_iter=max_iter)
+    return -f, OrderedDict((n, x[:, j].copy()) for j, n in enumerate(names))
 
 
 def bestfit_minuit(lf, minimize_kwargs=None, rates_in_log_space=False, **kwargs):

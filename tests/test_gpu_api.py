@@ -657,3 +657,21 @@ def test_likelihood_sum_composes_batches():
         kw = dict(zip(names, [float(v) for v in row]))
         assert g == total(**kw)
         assert g == lfs[0](**kw) + 0.5 * lfs[1](**kw)
+
+
+def test_profile_scan_lockstep_matches_per_hypothesis_fits():
+    """inference.profile_scan: conditional fits of a grid of hypotheses in lock step (two ll.batch passes per
+    iteration) against bestfit_scipy with the hypothesis fixed (the loop of one_parameter_interval)."""
+    from blueice_b200.inference import bestfit_scipy, profile_scan
+    ll, d, names = wl.c2_api(n_sources=2, n_shape=2, anchors=(-2., -1., 0., 1., 2.), bins=(40, 30), n_events=3000, seed=3)
+    values = np.linspace(0.6, 1.4, 9)
+    prof, cond = profile_scan(ll, 'sig_rate_multiplier', values)
+    assert prof.shape == (9,) and set(cond.keys()) == {'bg_rate_multiplier', 'shift1', 'shift2'}
+    for h in (0, 4, 8):
+        _, ref = bestfit_scipy(ll, pass_bounds_to_minimizer=True, minimize_kwargs=dict(method='L-BFGS-B'),
+                               sig_rate_multiplier=float(values[h]))
+        assert prof[h] >= ref - 2e-3 and abs(prof[h] - ref) <= 5e-2, (h, prof[h], ref)
+        kw = {n: float(cond[n][h]) for n in cond}
+        assert ll(sig_rate_multiplier=float(values[h]), **kw) == prof[h]
+    # the profile has a single maximum inside the scanned range
+    assert 0 < int(np.argmax(prof)) < 8

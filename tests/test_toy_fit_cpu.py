@@ -68,3 +68,31 @@ def test_bestfit_toys_fixed_parameters_and_bounds():
     # a guess outside the box is clipped into it, not rejected
     g, gll, _ = inference.bestfit_toys(ll, guess={'shift1': 5.0})
     assert np.all(np.abs(gll - free_ll) <= 1e-2)
+
+
+def test_profile_scan_matches_conditional_scipy_fits():
+    """All hypotheses of a profile-likelihood scan fitted in lock step == one scipy fit per hypothesis."""
+    toy = OracleToyLikelihood(n_toys=1)
+    orc = toy.oracles[0]
+
+    class OneDataset(object):
+        rate_parameters, shape_parameters, pdf_base_config = toy.rate_parameters, toy.shape_parameters, toy.pdf_base_config
+        get_bounds = staticmethod(lambda name: (-2., 2.))
+
+        def batch(self, cols, names, livetime_days=None):
+            cols = np.asarray(cols, dtype=float)
+            im = [names.index('bg_rate_multiplier'), names.index('sig_rate_multiplier')]
+            iz = [names.index('shift1'), names.index('shift2')]
+            return np.array([orc(row[iz], row[im]) for row in cols])
+
+    values = np.array([0.0, 0.5, 1.0, 1.6])
+    prof, cond = inference.profile_scan(OneDataset(), 'sig_rate_multiplier', values)
+    assert list(cond.keys()) == ['bg_rate_multiplier', 'shift1', 'shift2'] and prof.shape == (4,)
+    for h, v in enumerate(values):
+        res = minimize(lambda x: -orc(x[1:], [x[0], v]), [1, 0, 0], method='L-BFGS-B',
+                       bounds=[(0, None), (-2, 2), (-2, 2)])
+        assert abs(prof[h] + res.fun) <= 1e-2 and prof[h] >= -res.fun - 1e-4, (h, prof[h], -res.fun)
+    # everything else fixed: the scan is one batch evaluation
+    flat, none = inference.profile_scan(OneDataset(), 'sig_rate_multiplier', values, bg_rate_multiplier=1.0,
+                                        shift1=0.0, shift2=0.0)
+    assert len(none) == 0 and flat[2] == orc([0., 0.], [1., 1.])
