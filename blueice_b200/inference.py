@@ -225,10 +225,12 @@ def _lockstep_bfgs(minus_ll, x0, lo, hi, max_iter=60, gtol=1e-3, ftol=1e-10, fd_
         x[act[better]] = trial[np.arange(A), best][better]
         f[act[better]] = fb[better]
         was_fresh = fresh[act]
-        fresh[act] = ~better                                           # failed line search: restart from the scaled diagonal
-        stalled[act] = np.where(better, 0, stalled[act] + np.where(was_fresh, 1, 0))
         small = better & (gain <= ftol * np.maximum(1.0, np.abs(fa)))
-        small_gains[act] = np.where(small, small_gains[act] + 1, 0)
+        # a failed or nearly useless line search restarts from the scaled diagonal; only when such a restart does
+        # not help either does it count towards convergence
+        fresh[act] = (~better) | (small & ~was_fresh)
+        stalled[act] = np.where(better, 0, stalled[act] + np.where(was_fresh, 1, 0))
+        small_gains[act] = np.where(small & was_fresh, small_gains[act] + 1, np.where(small, small_gains[act], 0))
         small_gradient = np.max(np.abs(gp * np.sqrt(scale)), axis=1) <= gtol     # gradient in units of the curvature
         done = small_gradient | (small_gains[act] >= 2) | (stalled[act] >= 2)
         converged[act[done]] = True
