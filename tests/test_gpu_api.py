@@ -673,5 +673,5 @@ def test_profile_scan_lockstep_matches_per_hypothesis_fits():
         assert abs(prof[h] - ref) <= 5e-2, (h, prof[h], ref)          # kinks at the anchors: neighbouring local optima
         kw = {n: float(cond[n][h]) for n in cond}
         assert ll(sig_rate_multiplier=float(values[h]), **kw) == prof[h]
-    # the profile has a single maximum inside the scanned range
-    assert 0 < int(np.argmax(prof)) < 8
+    # 3000 events against ~1e5 expected: the profile falls monotonically with the signal rate
+    assert np.all(np.diff(prof) < 0)
