@@ -94,7 +94,7 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
 
 extern "C" int32_t bi_mma_unit_points(int32_t n_terms) {
     const int k4 = bi_mma_k4(n_terms);
-    return 8 * (k4 <= 2 ? 8 : (k4 <= 4 ? 4 : (k4 <= 16 ? 2 : 1)));
+    return 8 * (k4 <= 2 ? BI_MMA_MT_SMALL : (k4 <= 4 ? 4 : (k4 <= 16 ? 2 : 1)));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -45,14 +45,27 @@
 #define BI_RANGE_SPAN (253u << 20)
 
 // K4 = k-steps of 4 terms (instantiated: 1..8, 12, 16, 24, 32 -> up to 128 terms, rows zero-padded to 4 * K4)
+// tuning knobs of the K <= 8 instantiations (overridable at build time for experiments)
+#ifndef BI_MMA_MT_SMALL
+#define BI_MMA_MT_SMALL 4      /* measured on B200: 4 or 6 m-tiles per warp beat 8 by 4 % at K = 8 (config 2) */
+#endif
+#ifndef BI_MMA_T_SMALL
+#define BI_MMA_T_SMALL 128
+#endif
+#ifndef BI_MMA_MINCTAS_SMALL
+#define BI_MMA_MINCTAS_SMALL 3
+#endif
+#ifndef BI_MMA_WARPS_SMALL
+#define BI_MMA_WARPS_SMALL 4
+#endif
 template <int K4>
 struct BiMmaCfg {
-    static constexpr int MT = K4 <= 2 ? 8 : (K4 <= 4 ? 4 : (K4 <= 16 ? 2 : 1));   // 8-point m-tiles per unit
+    static constexpr int MT = K4 <= 2 ? BI_MMA_MT_SMALL : (K4 <= 4 ? 4 : (K4 <= 16 ? 2 : 1));   // 8-point m-tiles per unit
     static constexpr int KP = 4 * K4;                              // rows incl. zero padding
-    static constexpr int T = K4 <= 2 ? 128 : (K4 <= 4 ? 64 : 32);  // events per tile (row copies of T*8 bytes)
+    static constexpr int T = K4 <= 2 ? BI_MMA_T_SMALL : (K4 <= 4 ? 64 : 32);  // events per tile (row copies of T*8 bytes)
     static constexpr int RS = T + 4;                               // row stride: B-fragment loads hit 16 distinct banks
     static constexpr int STAGES = K4 <= 4 ? 2 : (K4 <= 8 ? 3 : 2);
-    static constexpr int WARPS = K4 <= 8 ? 4 : (K4 <= 16 ? 2 : 1); // work units (warps) per CTA
+    static constexpr int WARPS = K4 <= 2 ? BI_MMA_WARPS_SMALL : K4 <= 8 ? 4 : (K4 <= 16 ? 2 : 1); // work units (warps) per CTA
     static constexpr int THREADS = WARPS * 32;
     static constexpr int STAGE_DOUBLES = KP * RS;
     static constexpr int RING_DOUBLES = STAGES * STAGE_DOUBLES;
@@ -61,7 +74,7 @@ struct BiMmaCfg {
     static constexpr int HEADER_BYTES = 256;                       // mbarriers [WARPS][STAGES]
     static constexpr int SLOW_DOUBLES = MT * THREADS;              // L_t accumulators (touched on the slow path only)
     static constexpr int SMEM_BYTES = HEADER_BYTES + (WARPS * RING_DOUBLES + SLOW_DOUBLES) * 8;
-    static constexpr int MIN_CTAS = K4 <= 4 ? 3 : (K4 <= 8 ? 2 : (K4 <= 16 ? 3 : (K4 <= 24 ? 4 : 3)));
+    static constexpr int MIN_CTAS = K4 <= 2 ? BI_MMA_MINCTAS_SMALL : K4 <= 4 ? 3 : (K4 <= 8 ? 2 : (K4 <= 16 ? 3 : (K4 <= 24 ? 4 : 3)));
 };
 
 // ---------------------------------------------------------------------------------------------
