@@ -70,6 +70,9 @@ k_point_setup(const __grid_constant__ BiGrid grid, int n_sources, int64_t n_poin
     }
 
     // corners, first dim slowest (itertools.product order), weight = ((1*t_0)*t_1)*...
+    // (kept in thread-local arrays too: reading the just-written global rows back costs a round trip per term)
+    int corner_l[1 << BI_MAX_DIMS];
+    double weight_l[1 << BI_MAX_DIMS];
     for (int c = 0; c < C; ++c) {
         double w = 1.0;
         int flat = 0;
@@ -83,6 +86,8 @@ k_point_setup(const __grid_constant__ BiGrid grid, int n_sources, int64_t n_poin
         }
         corner_out[p * C + c] = flat;
         weight_out[p * C + c] = w;
+        corner_l[c] = flat;
+        weight_l[c] = w;
     }
 
     // mus: value = 0; value = value + M[corner] * weight   (then the three in-place scalings)
@@ -94,8 +99,7 @@ k_point_setup(const __grid_constant__ BiGrid grid, int n_sources, int64_t n_poin
         } else {
             acc = 0.0;
             for (int c = 0; c < C; ++c)
-                acc = __dadd_rn(acc, __dmul_rn(mus_anchor[(int64_t)corner_out[p * C + c] * S + s],
-                                               weight_out[p * C + c]));
+                acc = __dadd_rn(acc, __dmul_rn(__ldg(mus_anchor + (int64_t)corner_l[c] * S + s), weight_l[c]));
         }
         acc = __dmul_rn(acc, rate_mult[p * S + s]);
         if (scale) acc = __dmul_rn(acc, scale[p]);
@@ -110,8 +114,8 @@ k_point_setup(const __grid_constant__ BiGrid grid, int n_sources, int64_t n_poin
     if (row_out) {
         const int64_t K = (int64_t)C * S;
         for (int c = 0; c < C; ++c) {
-            const int flat = corner_out[p * C + c];
-            const double w = weight_out[p * C + c];
+            const int flat = corner_l[c];
+            const double w = weight_l[c];
             for (int s = 0; s < S; ++s) {
                 row_out[p * K + c * S + s] = flat * S + s;
                 wterm_out[p * K + c * S + s] = w;

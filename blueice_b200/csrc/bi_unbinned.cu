@@ -212,6 +212,39 @@ k_unbinned_finalize(const double* __restrict__ partial, int64_t n_super, const d
     }
 }
 
+// the same total with ONE WARP per point (lane l plays threads l, l + 32, ... of the 256-thread finalize): for short
+// partial lists the cost of k_unbinned_finalize is the scheduling of P 256-thread CTAs, not the sums
+__global__ void __launch_bounds__(256)
+k_unbinned_finalize_warp(const double* __restrict__ partial, int64_t n_super, const double* __restrict__ musum,
+                         const int32_t* __restrict__ status, int64_t n_points, double* __restrict__ logl,
+                         double* __restrict__ logsum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n_points) return;
+    if (status[p] != 0) {
+        if (lane == 0) {
+            logl[p] = -__longlong_as_double(0x7ff0000000000000LL);
+            if (logsum) logsum[p] = 0.0;
+        }
+        return;
+    }
+    const double* src = partial + p * n_super;
+    double w[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        double u = bi_strided_sum(src, v * 32 + lane, n_super);
+#pragma unroll
+        for (int x = 1; x < 32; x <<= 1) u = __dadd_rn(u, __shfl_xor_sync(BI_FULL_MASK, u, x));
+        w[v] = u;
+    }
+    if (lane == 0) {
+        const double total = __dadd_rn(__dadd_rn(__dadd_rn(w[0], w[1]), __dadd_rn(w[2], w[3])),
+                                       __dadd_rn(__dadd_rn(w[4], w[5]), __dadd_rn(w[6], w[7])));
+        logl[p] = __dadd_rn(-musum[p], total);               // likelihood.py:690
+        if (logsum) logsum[p] = total;
+    }
+}
+
 // =============================================================================================
 // ps[S, N] for one point, reference operation order (value = value + V * w), full_output=True
 // =============================================================================================
@@ -348,8 +381,12 @@ extern "C" int bi_unbinned_finalize(const double* partial_dev, int64_t n_super, 
     BI_REQUIRE(n_points >= 0 && n_super >= 0, "negative size");
     if (n_points == 0) return BI_OK;
     BI_REQUIRE(musum_dev && status_dev && logl_dev && (n_super == 0 || partial_dev), "bi_unbinned_finalize: NULL pointer");
-    k_unbinned_finalize<<<(unsigned)n_points, 256, 0, (cudaStream_t)stream>>>(partial_dev, n_super, musum_dev,
-                                                                              status_dev, logl_dev, logsum_dev);
+    if (n_super <= 1024 && n_points >= 64)                       // many short lists: one warp per point
+        k_unbinned_finalize_warp<<<(unsigned)((n_points + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+            partial_dev, n_super, musum_dev, status_dev, n_points, logl_dev, logsum_dev);
+    else
+        k_unbinned_finalize<<<(unsigned)n_points, 256, 0, (cudaStream_t)stream>>>(partial_dev, n_super, musum_dev,
+                                                                                  status_dev, logl_dev, logsum_dev);
     BI_LAUNCH_CHECK();
     return BI_OK;
 }
