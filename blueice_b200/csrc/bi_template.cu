@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(256)
 k_template_mix(const double* __restrict__ T, int64_t row_stride, int64_t bin_stride, int64_t n_bins, int K,
                const int32_t* __restrict__ row, const double* __restrict__ coef, const int32_t* __restrict__ status,
                const int32_t* __restrict__ pair_point, int64_t n_pairs, double* __restrict__ tmix) {
-    const int64_t q = blockIdx.y;
+  for (int64_t q = blockIdx.y; q < n_pairs; q += gridDim.y) {
     const int64_t pt = pair_point ? pair_point[q] : q;
-    if (status[pt] != 0) return;
+    if (status[pt] != 0) continue;
     const int32_t* rw = row + pt * K;
     const double* cf = coef + pt * K;
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x) {
@@ -334,6 +334,7 @@ k_template_mix(const double* __restrict__ T, int64_t row_stride, int64_t bin_str
         for (; k < K; ++k) acc = fma(__ldg(T + (int64_t)rw[k] * row_stride + b * bin_stride), cf[k], acc);
         tmix[q * n_bins + b] = acc;
     }
+  }
 }
 
 // lookup in a mixture template with PRE-MULTIPLIED corner weights (this family's own operation order):
@@ -783,11 +784,10 @@ extern "C" int bi_template_mix(const double* templates_dev, int64_t row_stride, 
                                double* tmix_dev, void* stream) {
     BI_REQUIRE(n_terms >= 1 && n_bins >= 1 && n_pairs >= 0, "bi_template_mix: bad sizes");
     if (n_pairs == 0) return BI_OK;
-    BI_REQUIRE(n_pairs <= 65535, "bi_template_mix: at most 65535 pairs per call");
     BI_REQUIRE(templates_dev && row_dev && coef_dev && status_dev && tmix_dev, "bi_template_mix: NULL device pointer");
     int64_t bx = (n_bins + 255) / 256;
     if (bx > 1024) bx = 1024;
-    dim3 grid((unsigned)bx, (unsigned)n_pairs);
+    dim3 grid((unsigned)bx, (unsigned)(n_pairs < 65535 ? n_pairs : 65535));
     k_template_mix<<<grid, 256, 0, (cudaStream_t)stream>>>(templates_dev, row_stride, bin_stride, n_bins, n_terms, row_dev,
                                                          coef_dev, status_dev, pair_point_dev, n_pairs, tmix_dev);
     BI_LAUNCH_CHECK();

@@ -191,9 +191,20 @@ class DensityEstimatingSource(HistogramPdfSource):
         provider = self.get_events_for_density_estimate
         batches = provider() if inspect.isgeneratorfunction(provider) else [provider()]
         n_simulated = 0
+        # Template construction is model building (prepare()), not the likelihood path: with a CUDA device the 1e6+
+        # samples per anchor model and source are binned by bi_histogramdd (np.histogramdd semantics, bit-identical
+        # counts), without one by NumPy -- host-only model building stays possible.
+        import torch
+        on_device = torch.cuda.is_available()
+        if on_device:
+            from . import device_ops
         for events, n in batches:
             n_simulated += n
-            counts.add(*utils._events_to_analysis_dimensions(events, space))
+            coords = utils._events_to_analysis_dimensions(events, space)
+            if on_device and len(events):
+                counts.histogram = counts.histogram + device_ops.histogramdd(bins, coords)
+            else:
+                counts.add(*coords)
 
         self.fraction_in_range = counts.n / n_simulated
         # density = counts / (events in range) / bin volume
