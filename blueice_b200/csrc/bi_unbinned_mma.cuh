@@ -55,6 +55,9 @@
 #ifndef BI_MMA_MINCTAS_SMALL
 #define BI_MMA_MINCTAS_SMALL 3
 #endif
+#ifndef BI_MMA_STAGES_SMALL
+#define BI_MMA_STAGES_SMALL 2
+#endif
 #ifndef BI_MMA_WARPS_SMALL
 #define BI_MMA_WARPS_SMALL 4
 #endif
@@ -64,7 +67,7 @@ struct BiMmaCfg {
     static constexpr int KP = 4 * K4;                              // rows incl. zero padding
     static constexpr int T = K4 <= 2 ? BI_MMA_T_SMALL : (K4 <= 4 ? 64 : 32);  // events per tile (row copies of T*8 bytes)
     static constexpr int RS = T + 4;                               // row stride: B-fragment loads hit 16 distinct banks
-    static constexpr int STAGES = K4 <= 4 ? 2 : (K4 <= 8 ? 3 : 2);
+    static constexpr int STAGES = K4 <= 2 ? BI_MMA_STAGES_SMALL : K4 <= 4 ? 2 : (K4 <= 8 ? 3 : 2);
     static constexpr int WARPS = K4 <= 2 ? BI_MMA_WARPS_SMALL : K4 <= 8 ? 4 : (K4 <= 16 ? 2 : 1); // work units (warps) per CTA
     static constexpr int THREADS = WARPS * 32;
     static constexpr int STAGE_DOUBLES = KP * RS;

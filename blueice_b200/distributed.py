@@ -82,6 +82,66 @@ def rank_ordered_sum(local, group=None):
     return acc
 
 
+class PeerGather(object):
+    """All-gather of n float64 results per rank as P2P stores over NVLink (bi_peer_broadcast) into peer-mapped
+    buffers (torch symmetric memory), followed by a signal-pad barrier: no collective launch, ~10 us instead of the
+    20-40 us of an NCCL all_gather of a few kB.  Device tensors in, device tensor [world, n] out, all on the current
+    stream.  Falls back to NCCL all_gather_into_tensor when symmetric memory is unavailable (construction fails)."""
+
+    def __init__(self, n, group=None):
+        import ctypes
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        dist = _dist()
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n = int(n)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.lib = _cabi.load()
+        self.fallback = None
+        try:
+            # two gather buffers used alternately: a rank may only overwrite the rows of gather k - 2, and it cannot
+            # start gather k before every rank has passed the barrier of gather k - 1, which each rank enqueues after
+            # its own (same-stream) reads of gather k - 2 -- so ONE barrier per gather is enough
+            self.buffer = symm_mem.empty(2 * self.world * max(self.n, 1), dtype=torch.float64, device=self.device)
+            self.handle = symm_mem.rendezvous(self.buffer, self.group)
+            self.peer_ptrs = np.ascontiguousarray(np.array([int(p) for p in self.handle.buffer_ptrs], dtype=np.uint64))
+            self.handle.barrier(channel=0)
+        except Exception as exc:                                    # no peer mapping on this system: NCCL
+            self.fallback = repr(exc)
+            self.buffer = torch.empty(2 * self.world * max(self.n, 1), dtype=torch.float64, device=self.device)
+        self.parity = 0
+        self._ctypes = ctypes
+
+    def barrier(self):
+        """Cross-GPU barrier on the current stream (signal pads; NCCL barrier in the fallback)."""
+        if self.fallback is not None:
+            _dist().barrier(group=self.group)
+        else:
+            self.handle.barrier(channel=0)
+
+    def gather(self, local, wait=True):
+        """local: device tensor of n float64 -> device tensor [world, n] holding every rank's values.
+
+        wait=False only issues this rank's stores (no waiting for the other ranks): the rows are complete after the
+        next barrier(); a caller doing so must not let more than one un-waited gather overtake a reader."""
+        import torch
+        if local.numel() != self.n:
+            raise ValueError("PeerGather was built for %d values per rank, got %d" % (self.n, local.numel()))
+        self.parity ^= 1
+        half = self.world * max(self.n, 1)
+        out = self.buffer[self.parity * half:(self.parity + 1) * half]
+        if self.fallback is not None:
+            _dist().all_gather_into_tensor(out, local.contiguous(), group=self.group)
+            return out.view(self.world, -1)[:, :self.n]
+        stream = self._ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _cabi.check(self.lib.bi_peer_broadcast(_cabi.dev_ptr(local), self.n, _cabi.host_ptr(self.peer_ptrs), self.world,
+                                               self.parity * half + self.rank * self.n, stream), "bi_peer_broadcast")
+        if wait:
+            self.handle.barrier(channel=0)
+        return out.view(self.world, -1)[:, :self.n]
+
+
 class PointShardedLikelihood(object):
     """Shard the points of ll.batch over the ranks of `group`; every rank returns the full result.
 
@@ -91,6 +151,21 @@ class PointShardedLikelihood(object):
     def __init__(self, ll, group=None):
         self.ll = ll
         self.group = group
+        self._gathers = {}
+
+    def _device_gather_engine(self, n_rows):
+        """The ll's fused unbinned engine with a PeerGather for n_rows rows per rank, or None (binned likelihoods,
+        gloo, engines without the fused path): then the results are gathered on the host."""
+        if _dist().get_backend(self.group) != 'nccl':
+            return None
+        engine = getattr(self.ll, '_engine', None)
+        if engine is None or not hasattr(engine, 'evaluate_fused') or not engine.uses_mma():
+            return None
+        pg = self._gathers.get(n_rows)
+        if pg is None:
+            pg = self._gathers[n_rows] = PeerGather(n_rows, self.group)
+        engine.peer_gather = pg
+        return engine
 
     def batch(self, params, names=None, livetime_days=None):
         dist = _dist()
@@ -98,8 +173,31 @@ class PointShardedLikelihood(object):
         params = np.asarray(params, dtype=np.float64)
         bounds = shard_bounds(len(params), world)
         lo, hi = bounds[rank]
-        local = self.ll.batch(params[lo:hi], names, livetime_days=livetime_days) if hi > lo else np.zeros(0)
-        return gather_concat(np.asarray(local, dtype=np.float64), [b - a for a, b in bounds], self.group)
+        counts = [b - a for a, b in bounds]
+        n_rows = max(counts) if counts else 0
+        engine = self._device_gather_engine(n_rows) if n_rows else None
+        if engine is None:
+            local = self.ll.batch(params[lo:hi], names, livetime_days=livetime_days) if hi > lo else np.zeros(0)
+            return gather_concat(np.asarray(local, dtype=np.float64), counts, self.group)
+        # device-side gather: every rank evaluates n_rows rows (short shards repeat their last row, or row 0 of the
+        # table when they are empty); the logl rows (without priors) of all ranks arrive over NVLink before the D2H
+        rows = params[lo:hi] if hi > lo else params[:1]
+        if len(rows) < n_rows:
+            rows = np.vstack([rows, np.repeat(rows[-1:], n_rows - len(rows), axis=0)])
+        try:
+            self.ll.batch(rows, names, livetime_days=livetime_days)        # local checks ('error' mode) + the gather
+            gathered = engine.last_gathered
+        finally:
+            engine.peer_gather = None
+        device_ll = gathered.reshape(-1) if min(counts) == n_rows else \
+            np.concatenate([gathered[r, :c] for r, c in enumerate(counts)])
+        has_priors = any(p is not None for _, p, _ in self.ll.shape_parameters.values()) or \
+            any(p is not None for p in self.ll.rate_parameters.values())
+        if not has_priors:
+            return device_ll
+        zs, mult = self.ll._rows_from_params(params, names)
+        priors = self.ll._prior_sum(zs, mult)
+        return np.where(np.isneginf(device_ll), -np.inf, priors + device_ll)
 
 
 class ToyShardedLikelihood(object):

@@ -282,6 +282,8 @@ class UnbinnedEngine(_EngineBase):
         self.ps_anchor = None
         self.force_kernel = None      # None (auto) | 'stream' | 'grouped'  (tests / bench)
         self._fused_cache = {}        # batch size -> staging buffers, workspace, prebuilt C arguments
+        self.peer_gather = None       # distributed.PeerGather: all-gather the logl rows on the device (point sharding)
+        self.last_gathered = None
         self.full_grid_layout = os.environ.get('BI_MMA_NO_TENSORMAP') is None   # rows = [G][S][ld] anchor tensor
 
     # -- set_data -------------------------------------------------------------------------------
@@ -474,9 +476,18 @@ class UnbinnedEngine(_EngineBase):
         n_f = 3 * P if return_parts else P
         st["pin_f"][:n_f].copy_(st["out_f"][:n_f], non_blocking=True)
         st["pin_i"].copy_(st["out_i"], non_blocking=True)
+        gathered_pin = None
+        if self.peer_gather is not None:
+            # point-sharded evaluation: this rank's logl rows go to every rank over NVLink before the D2H
+            g = self.peer_gather.gather(st["out_f"][:P])
+            gathered_pin = st.get("pin_g")
+            if gathered_pin is None or gathered_pin.numel() != g.numel():
+                gathered_pin = st["pin_g"] = self.torch.empty(g.numel(), dtype=self.torch.float64, pin_memory=True)
+            gathered_pin.view(g.shape).copy_(g, non_blocking=True)
         stream.synchronize()
+        self.last_gathered = None if gathered_pin is None else gathered_pin.numpy().reshape(self.peer_gather.world, -1).copy()
         self.last_h2d_bytes = st["n_in"] * 8
-        self.last_d2h_bytes = n_f * 8 + P * 4
+        self.last_d2h_bytes = n_f * 8 + P * 4 + (0 if gathered_pin is None else gathered_pin.numel() * 8)
         res = st["pin_f_np"]
         if return_parts:
             return res[P:2 * P].copy(), res[2 * P:3 * P].copy(), st["pin_i_np"].copy()

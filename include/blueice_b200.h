@@ -446,6 +446,17 @@ int bi_binned_pmfs(const double* pmf_anchor_dev, const double* n_model_anchor_de
                    const double* sum_t_dev, double* pmf_out_dev, int64_t ld_out, void* stream);
 
 /*
+ * The all-gather of a point / toy sharded evaluation as plain P2P stores over NVLink: every
+ * rank stores its n results into the gather buffer of EVERY rank at its own slot,
+ *     peer[r][dst_offset + i] = src_dev[i]     for all r < world,
+ * peer_ptrs_host[r] being rank r's gather buffer mapped into THIS process (peer-mapped device memory, e.g. torch
+ * symmetric memory's buffer_ptrs).  No collective launch; the caller follows it with a cross-GPU barrier before
+ * anybody reads the gathered rows.  world <= 16.
+ */
+int bi_peer_broadcast(const double* src_dev, int64_t n, const uint64_t* peer_ptrs_host, int32_t world,
+                      int64_t dst_offset, void* stream);
+
+/*
  * Micro-benchmarks used by bench.py to measure the roofline denominators that
  * MEASURED_PEAKS.json does not hold: dependent-free FP64 FMA throughput
  * and a plain streaming read.  Each returns elapsed milliseconds (CUDA events on `stream`) in *ms_host.
