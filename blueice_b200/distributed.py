@@ -265,6 +265,7 @@ class EventShardedLikelihood(object):
     def __init__(self, ll, group=None):
         self.ll = ll
         self.group = group
+        self._gathers = {}
 
     def combine(self, logsum, musum, status, priors):
         """-musum + (rank-ordered sum of the shards' log sums) + priors; status != 0 -> -inf."""
@@ -272,8 +273,29 @@ class EventShardedLikelihood(object):
         return np.where(status != 0, -np.inf, priors + (-musum + total))
 
     def batch(self, params, names=None, livetime_days=None):
-        logsum, musum, status, priors = self.ll.batch_parts(params, names, livetime_days=livetime_days)
-        return self.combine(logsum, musum, status, priors)
+        engine = getattr(self.ll, '_engine', None)
+        n_points = len(np.asarray(params, dtype=np.float64).reshape(-1, max(len(names or self.ll.parameter_names()), 1)))
+        device_gather = (_dist().get_backend(self.group) == 'nccl' and engine is not None
+                         and hasattr(engine, 'peer_gather') and n_points > 0
+                         and (not hasattr(engine, 'uses_mma') or engine.uses_mma()))
+        if not device_gather:
+            logsum, musum, status, priors = self.ll.batch_parts(params, names, livetime_days=livetime_days)
+            return self.combine(logsum, musum, status, priors)
+        # the shards' log sums are gathered on the device (P2P stores over NVLink) before the D2H; every rank then
+        # adds them in rank order, so all ranks hold bit-identical results
+        pg = self._gathers.get(n_points)
+        if pg is None:
+            pg = self._gathers[n_points] = PeerGather(n_points, self.group)
+        engine.peer_gather = pg
+        try:
+            logsum, musum, status, priors = self.ll.batch_parts(params, names, livetime_days=livetime_days)
+            rows = engine.last_gathered
+        finally:
+            engine.peer_gather = None
+        total = np.where(status != 0, 0.0, rows[0])
+        for r in range(1, len(rows)):
+            total = total + np.where(status != 0, 0.0, rows[r])
+        return np.where(status != 0, -np.inf, priors + (-musum + total))
 
     def __call__(self, livetime_days=None, **kwargs):
         names = list(kwargs.keys())

@@ -478,8 +478,9 @@ class UnbinnedEngine(_EngineBase):
         st["pin_i"].copy_(st["out_i"], non_blocking=True)
         gathered_pin = None
         if self.peer_gather is not None:
-            # point-sharded evaluation: this rank's logl rows go to every rank over NVLink before the D2H
-            g = self.peer_gather.gather(st["out_f"][:P])
+            # sharded evaluation: this rank's logl rows (point sharding) or log sums (event sharding, return_parts)
+            # go to every rank over NVLink before the D2H
+            g = self.peer_gather.gather(st["out_f"][P:2 * P] if return_parts else st["out_f"][:P])
             gathered_pin = st.get("pin_g")
             if gathered_pin is None or gathered_pin.numel() != g.numel():
                 gathered_pin = st["pin_g"] = self.torch.empty(g.numel(), dtype=self.torch.float64, pin_memory=True)
@@ -983,6 +984,8 @@ class TemplateUnbinnedEngine(_EngineBase):
         self.n_events = 0
         self.n_datasets = 0
         self.ev_bin = None
+        self.peer_gather = None       # distributed.PeerGather (sharded evaluations), see UnbinnedEngine
+        self.last_gathered = None
         self._toy_schedule = None
 
     # -- datasets ---------------------------------------------------------------------------------
@@ -1222,16 +1225,26 @@ class TemplateUnbinnedEngine(_EngineBase):
             out_pin[2 * P:].copy_(o["musum"], non_blocking=True)
         st_pin = self.ws.get("d2h_status", P, torch.int32, pinned=True)
         st_pin.copy_(o["status"], non_blocking=True)
+        g_pin = None
+        if self.peer_gather is not None:
+            # sharded evaluation: the log sums (event sharding) or logl rows of all ranks, gathered over NVLink
+            g = self.peer_gather.gather(logsum[:P] if return_parts else logl[:P])
+            g_pin = self.ws.get("d2h_gather", g.numel(), torch.float64, pinned=True)
+            g_pin.view(g.shape).copy_(g, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         self.last_h2d_bytes = nbytes
-        self.last_d2h_bytes = n_f * 8 + P * 4
+        self.last_d2h_bytes = n_f * 8 + P * 4 + (0 if g_pin is None else g_pin.numel() * 8)
         res = out_pin.numpy().copy()
         status = st_pin.numpy().copy()
         ll, ls = res[:P], res[P:2 * P]
+        gathered = None if g_pin is None else g_pin.numpy().reshape(self.peer_gather.world, -1).copy()
         if order is not None:                                               # pair order -> point order
             inv = np.empty(P, dtype=np.int64)
             inv[order] = np.arange(P)
             ll, ls = ll[inv], ls[inv] if return_parts else ls
+            if gathered is not None:
+                gathered = gathered[:, inv]
+        self.last_gathered = gathered
         if return_parts:
             return ls, res[2 * P:], status
         return (ll, status) if return_status else ll
