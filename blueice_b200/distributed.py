@@ -126,7 +126,7 @@ class PeerGather(object):
         wait=False only issues this rank's stores (no waiting for the other ranks): the rows are complete after the
         next barrier(); a caller doing so must not let more than one un-waited gather overtake a reader."""
         import torch
-        if local.numel() != self.n:
+        if local.numel() > self.n or (self.fallback is not None and local.numel() != self.n):
             raise ValueError("PeerGather was built for %d values per rank, got %d" % (self.n, local.numel()))
         self.parity ^= 1
         half = self.world * max(self.n, 1)
@@ -135,7 +135,7 @@ class PeerGather(object):
             _dist().all_gather_into_tensor(out, local.contiguous(), group=self.group)
             return out.view(self.world, -1)[:, :self.n]
         stream = self._ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _cabi.check(self.lib.bi_peer_broadcast(_cabi.dev_ptr(local), self.n, _cabi.host_ptr(self.peer_ptrs), self.world,
+        _cabi.check(self.lib.bi_peer_broadcast(_cabi.dev_ptr(local), local.numel(), _cabi.host_ptr(self.peer_ptrs), self.world,
                                                self.parity * half + self.rank * self.n, stream), "bi_peer_broadcast")
         if wait:
             self.handle.barrier(channel=0)
@@ -212,6 +212,7 @@ class ToyShardedLikelihood(object):
         self.group = group
         self.n_toys = 0
         self.bounds = None
+        self._gather = None
 
     def _rank_world(self):
         dist = _dist()
@@ -243,8 +244,32 @@ class ToyShardedLikelihood(object):
         if len(params) != self.n_toys:
             raise ValueError("need one parameter point per toy: got %d for %d toys" % (len(params), self.n_toys))
         lo, hi = self.bounds[rank]
-        local = self.ll.batch_toys(params[lo:hi], names, livetime_days=livetime_days) if hi > lo else np.zeros(0)
-        return gather_concat(np.asarray(local, dtype=np.float64), [b - a for a, b in self.bounds], self.group)
+        counts = [b - a for a, b in self.bounds]
+        engine = getattr(self.ll, '_toy_engine', None)
+        device_gather = (_dist().get_backend(self.group) == 'nccl' and engine is not None and min(counts) > 0
+                         and hasattr(engine, 'peer_gather'))
+        if not device_gather:
+            local = self.ll.batch_toys(params[lo:hi], names, livetime_days=livetime_days) if hi > lo else np.zeros(0)
+            return gather_concat(np.asarray(local, dtype=np.float64), counts, self.group)
+        # the logl rows of all ranks (without priors) arrive over NVLink before the D2H (PeerGather)
+        if self._gather is None or self._gather.n != max(counts):
+            self._gather = PeerGather(max(counts), self.group)
+        if self._gather.fallback is not None and min(counts) != max(counts):
+            local = self.ll.batch_toys(params[lo:hi], names, livetime_days=livetime_days)
+            return gather_concat(np.asarray(local, dtype=np.float64), counts, self.group)
+        engine.peer_gather = self._gather
+        try:
+            self.ll.batch_toys(params[lo:hi], names, livetime_days=livetime_days)
+            gathered = engine.last_gathered
+        finally:
+            engine.peer_gather = None
+        device_ll = np.concatenate([gathered[r, :c] for r, c in enumerate(counts)])
+        has_priors = any(p is not None for _, p, _ in self.ll.shape_parameters.values()) or \
+            any(p is not None for p in self.ll.rate_parameters.values())
+        if not has_priors:
+            return device_ll
+        zs, mult = self.ll._rows_from_params(params, names)
+        return np.where(np.isneginf(device_ll), -np.inf, self.ll._prior_sum(zs, mult) + device_ll)
 
 
 def shard_events(d, group=None, rank=None, world_size=None):
