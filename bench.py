@@ -518,7 +518,7 @@ def run_own_arm(args):
     barrier()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(np.sum(step_ms))
-    launches_timed = eng.launches - launches0
+    launches_timed = eng.launches - launches0 + (args.steps if world > 1 else 0)      # + bi_peer_broadcast per step
     result_dev = logl.cpu().numpy().copy()
     gathered_host = gathered_dev.cpu().numpy().copy() if world > 1 else None
 
