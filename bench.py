@@ -310,6 +310,28 @@ def other_configs(args, rank, world, device):
     torch.cuda.empty_cache()
     if rank != 0:
         return out
+    # ---- config 1 (the reference's own CPU-runnable case): latency of one evaluation and a 4096-point batch ----
+    ll1, d1, names1 = wl.c1_api(seed=0)
+    rng1 = np.random.default_rng(1)
+    pts1 = np.column_stack([rng1.uniform(0.5, 2.0, 4096), rng1.uniform(-2.0, 2.0, 4096)])
+    kw1 = dict(zip(names1, [float(v) for v in pts1[0]]))
+    for _ in range(20):
+        ll1(**kw1)
+    t0 = time.perf_counter()
+    for _ in range(300):
+        ll1(**kw1)
+    lat = (time.perf_counter() - t0) / 300
+    b1 = ll1.batch(pts1, names1)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        b1 = ll1.batch(pts1, names1)
+    tb = (time.perf_counter() - t0) / 20
+    out["config1_gaussian"] = {
+        "workload": "conf_for_test() Gaussian-source UnbinnedLogLikelihood, shape parameter mu (3 anchors), %d events" % len(d1),
+        "n_events": int(len(d1)), "single_call_latency_us": lat * 1e6, "single_call_point_events_per_s": len(d1) / lat,
+        "batch_points": 4096, "batch_ms": tb * 1e3, "batch_point_events_per_s": 4096 * len(d1) / tb,
+        "batch_equals_single_call": bool(b1[0] == ll1(**kw1))}
+    del ll1
     # ---- config 3 (binned + Beeston-Barlow; K4) ----
     from blueice_b200.engine import BinnedEngine, MorphGrid
     t0 = time.perf_counter()
