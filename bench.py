@@ -331,6 +331,19 @@ def other_configs(args, rank, world, device):
         "n_events": int(len(d1)), "single_call_latency_us": lat * 1e6, "single_call_point_events_per_s": len(d1) / lat,
         "batch_points": 4096, "batch_ms": tb * 1e3, "batch_point_events_per_s": 4096 * len(d1) / tb,
         "batch_equals_single_call": bool(b1[0] == ll1(**kw1))}
+    if not args.skip_cpu:
+        # cpu_baseline leg for this config: the oracle port (same third-party calls as the reference), one core
+        from oracle.pipeline import UnbinnedOracle
+        axes1, mus1, ps1, x1 = wl.c1_arrays(seed=0)
+        orc1 = UnbinnedOracle(axes1, mus1).set_ps(ps1)
+        for _ in range(20):
+            orc1([0.3], [1.1])
+        t0 = time.perf_counter()
+        for _ in range(500):
+            orc1([0.3], [1.1])
+        cpu_lat = (time.perf_counter() - t0) / 500
+        out["config1_gaussian"]["cpu_port_single_call_us"] = cpu_lat * 1e6
+        out["config1_gaussian"]["cpu_port_events"] = int(len(x1))
     del ll1
     # ---- config 3 (binned + Beeston-Barlow; K4) ----
     from blueice_b200.engine import BinnedEngine, MorphGrid
