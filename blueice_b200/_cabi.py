@@ -74,6 +74,14 @@ SIGNATURES = {
     "bi_mixture_partials": (ctypes.c_int, [_c_void_p, _i32, _c_void_p, _i32, _c_void_p, _c_void_p, _i64, _c_void_p,
                                            _c_void_p, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p,
                                            _c_void_p, _f64, _c_void_p, _c_void_p]),
+    "bi_template_workspace_bytes": (_i64, [_i32, _i32, _i64, _i64, _i64, _i64, _i32]),
+    "bi_template_ll_batch": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _i64,
+                                            _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                            _c_void_p, _i64, _i64, _i32, _c_void_p, _i32, _i32,
+                                            _c_void_p, _c_void_p, _i64, _c_void_p,
+                                            _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
+                                            _i64, _i64, _i64, _f64, _c_void_p, _i64,
+                                            _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_toy_counts": (ctypes.c_int, [_i32, _i64, _i64, _c_void_p, _i32, ctypes.c_uint64, _c_void_p, _c_void_p]),
     "bi_toy_events": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _c_void_p, _i64, _i64, _c_void_p, _c_void_p,
                                      _i64, ctypes.c_uint64, _c_void_p, _i64, _c_void_p, _c_void_p]),

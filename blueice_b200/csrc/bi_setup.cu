@@ -140,6 +140,137 @@ k_point_setup(const __grid_constant__ BiGrid grid, int n_sources, int64_t n_poin
     status_out[p] = status;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same set-up with ONE WARP per point (small batches: minimiser steps, finite-difference batches): the corners,
+// the sources and the contraction terms of a point are spread over the lanes, so the latency of a single evaluation is
+// a few dependent steps instead of a serial walk over C * S terms.  Every value is formed by the same operations in the
+// same order as in k_point_setup (bit-identical outputs).
+// ---------------------------------------------------------------------------------------------
+#define BI_SETUP_WARPS 4
+#ifndef BI_SETUP_WARP_MAX_POINTS
+#define BI_SETUP_WARP_MAX_POINTS 8192     /* above: one thread per point (k_point_setup) */
+#endif
+__global__ void __launch_bounds__(BI_SETUP_WARPS * 32)
+k_point_setup_warp(const __grid_constant__ BiGrid grid, int n_sources, int64_t n_points,
+                   const double* __restrict__ zs, const double* __restrict__ rate_mult,
+                   const double* __restrict__ scale, const double* __restrict__ eff,
+                   const double* __restrict__ mus_anchor, const __grid_constant__ BiAllowNegative allow,
+                   int32_t* __restrict__ cell_out, double* __restrict__ frac_out,
+                   int32_t* __restrict__ corner_out, double* __restrict__ weight_out,
+                   double* __restrict__ mus_out, double* __restrict__ musum_out,
+                   int32_t* __restrict__ status_out, int32_t* __restrict__ row_out, double* __restrict__ coef_out,
+                   double* __restrict__ wterm_out, int32_t* __restrict__ term_source_out) {
+    __shared__ int s_corner_all[BI_SETUP_WARPS][1 << BI_MAX_DIMS];
+    __shared__ double s_weight_all[BI_SETUP_WARPS][1 << BI_MAX_DIMS];
+    __shared__ double s_mu_all[BI_SETUP_WARPS][BI_MAX_SOURCES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* s_corner = s_corner_all[warp];
+    double* s_weight = s_weight_all[warp];
+    double* s_mu = s_mu_all[warp];
+    const int64_t p = (int64_t)blockIdx.x * BI_SETUP_WARPS + warp;
+    const int D = grid.n_dims, C = grid.n_corners, S = n_sources;
+    if (p == 0 && term_source_out)
+        for (int k = lane; k < C * S; k += 32) term_source_out[k] = k % S;
+    if (p >= n_points) return;
+
+    // (a) cell and fraction of dimension d by lane d, then known to every lane
+    int my_cell = 0;
+    double my_frac = 0.0;
+    bool out_of_range = false;
+    if (lane < D) {
+        const double* axis = grid.axes + grid.axis_offset[lane];
+        const int n = grid.n_anchors[lane];
+        const double z = zs[p * D + lane];
+        out_of_range = !(axis[0] <= z && z <= axis[n - 1]);           // likelihood.py:345-346 (NaN fails)
+        if (n == 1) { my_cell = -1; my_frac = 0.0; }
+        else {
+            int c = bi_upper_bound(axis, n, z) - 1;
+            c = c < 0 ? 0 : (c > n - 2 ? n - 2 : c);
+            my_cell = c;
+            my_frac = __ddiv_rn(__dsub_rn(z, axis[c]), __dsub_rn(axis[c + 1], axis[c]));
+        }
+        cell_out[p * D + lane] = my_cell;
+        frac_out[p * D + lane] = my_frac;
+    }
+    int status = __any_sync(BI_FULL_MASK, out_of_range) ? BI_POINT_OUT_OF_RANGE : BI_POINT_OK;
+    int cell[BI_MAX_DIMS];
+    double frac[BI_MAX_DIMS];
+#pragma unroll
+    for (int d = 0; d < BI_MAX_DIMS; ++d) {
+        cell[d] = __shfl_sync(BI_FULL_MASK, my_cell, d);
+        frac[d] = __shfl_sync(BI_FULL_MASK, my_frac, d);
+    }
+
+    // (b) corners over the lanes: first dim slowest, weight = ((1*t_0)*t_1)*...
+    for (int c = lane; c < C; c += 32) {
+        double w = 1.0;
+        int flat = 0;
+#pragma unroll
+        for (int d = 0; d < BI_MAX_DIMS; ++d) {
+            if (d < D) {
+                const int bit = (c >> (D - 1 - d)) & 1;
+                w = __dmul_rn(w, bit ? frac[d] : __dsub_rn(1.0, frac[d]));
+                int idx = cell[d] + bit;
+                if (idx < 0) idx += grid.n_anchors[d];
+                flat += idx * grid.stride[d];
+            }
+        }
+        corner_out[p * C + c] = flat;
+        weight_out[p * C + c] = w;
+        s_corner[c] = flat;
+        s_weight[c] = w;
+    }
+    __syncwarp();
+
+    // (c) mus over the lanes: value = 0; value = value + M[corner] * weight over the corners in order, then the scalings
+    for (int s = lane; s < S; s += 32) {
+        double acc;
+        if (D == 0) {
+            acc = mus_anchor[s];
+        } else {
+            acc = 0.0;
+            for (int c = 0; c < C; ++c)
+                acc = __dadd_rn(acc, __dmul_rn(__ldg(mus_anchor + (int64_t)s_corner[c] * S + s), s_weight[c]));
+        }
+        acc = __dmul_rn(acc, rate_mult[p * S + s]);
+        if (scale) acc = __dmul_rn(acc, scale[p]);
+        if (eff) acc = __dmul_rn(acc, eff[p * S + s]);
+        s_mu[s] = acc;
+        mus_out[p * S + s] = acc;
+    }
+    __syncwarp();
+
+    // (d) mu.sum() in NumPy's order and the unphysical-rate test (likelihood.py:397-415) by lane 0
+    if (lane == 0) {
+        const double musum = bi_numpy_sum_small(s_mu, S);
+        musum_out[p] = musum;
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        bool bad = false;
+        if (!allow.any) {
+            for (int s = 0; s < S; ++s) bad |= !((s_mu[s] >= 0.0) && (s_mu[s] < inf));
+        } else {
+            bool any_finite = false;
+            for (int s = 0; s < S; ++s) any_finite |= (s_mu[s] < inf);
+            if (!any_finite || (musum < 0.0)) bad = true;
+            for (int s = 0; s < S; ++s)
+                if (!(0.0 <= s_mu[s]) && !allow.flag[s]) bad = true;
+        }
+        if (bad) status |= BI_POINT_UNPHYSICAL;
+        status_out[p] = status;
+    }
+
+    // (e) contraction terms k = c * S + s over the lanes
+    if (row_out) {
+        const int K = C * S;
+        for (int k = lane; k < K; k += 32) {
+            const int c = k / S, s = k - c * S;
+            row_out[p * K + k] = s_corner[c] * S + s;
+            wterm_out[p * K + k] = s_weight[c];
+            coef_out[p * K + k] = __dmul_rn(s_weight[c], s_mu[s]);
+        }
+    }
+}
+
 int bi_fill_grid(BiGrid* g, int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host) {
     BI_REQUIRE(n_dims >= 0 && n_dims <= BI_MAX_DIMS, "n_dims=%d outside [0,%d]", n_dims, BI_MAX_DIMS);
     BI_REQUIRE(n_dims == 0 || (n_anchors_host && axes_host), "anchor grid pointers are NULL");
@@ -188,6 +319,15 @@ extern "C" int bi_point_setup(int32_t n_dims, const int32_t* n_anchors_host, con
     memset(&allow, 0, sizeof(allow));
     if (allow_negative_host)
         for (int s = 0; s < n_sources; ++s) { allow.flag[s] = allow_negative_host[s] ? 1 : 0; allow.any |= allow.flag[s]; }
+    if (n_points <= BI_SETUP_WARP_MAX_POINTS) {                   // small batches: one warp per point (latency)
+        const int64_t wblocks = (n_points + BI_SETUP_WARPS - 1) / BI_SETUP_WARPS;
+        k_point_setup_warp<<<(unsigned)wblocks, BI_SETUP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            grid, n_sources, n_points, zs_dev, rate_mult_dev, scale_dev, eff_dev, mus_anchor_dev, allow,
+            cell_dev, frac_dev, corner_dev, weight_dev, mus_dev, musum_dev, status_dev, row_dev, coef_dev, wterm_dev,
+            term_source_dev);
+        BI_LAUNCH_CHECK();
+        return BI_OK;
+    }
     const int threads = 128;
     const int64_t blocks = (n_points + threads - 1) / threads;
     k_point_setup<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(

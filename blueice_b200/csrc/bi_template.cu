@@ -324,7 +324,14 @@ k_template_mix(const double* __restrict__ T, int64_t row_stride, int64_t bin_str
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x) {
         double acc = 0.0;
         int k = 0;
-        for (; k + 8 <= K; k += 8) {                                 // 8 independent loads in flight, then the chain
+        for (; k + 32 <= K; k += 32) {                               // 32 independent loads in flight, then the chain
+            double t[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __ldg(T + (int64_t)rw[k + i] * row_stride + b * bin_stride);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc = fma(t[i], cf[k + i], acc);
+        }
+        for (; k + 8 <= K; k += 8) {
             double t[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) t[i] = __ldg(T + (int64_t)rw[k + i] * row_stride + b * bin_stride);
@@ -785,10 +792,10 @@ extern "C" int bi_template_mix(const double* templates_dev, int64_t row_stride, 
     BI_REQUIRE(n_terms >= 1 && n_bins >= 1 && n_pairs >= 0, "bi_template_mix: bad sizes");
     if (n_pairs == 0) return BI_OK;
     BI_REQUIRE(templates_dev && row_dev && coef_dev && status_dev && tmix_dev, "bi_template_mix: NULL device pointer");
-    int64_t bx = (n_bins + 255) / 256;
-    if (bx > 1024) bx = 1024;
+    int64_t bx = (n_bins + 63) / 64;
+    if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)(n_pairs < 65535 ? n_pairs : 65535));
-    k_template_mix<<<grid, 256, 0, (cudaStream_t)stream>>>(templates_dev, row_stride, bin_stride, n_bins, n_terms, row_dev,
+    k_template_mix<<<grid, 64, 0, (cudaStream_t)stream>>>(templates_dev, row_stride, bin_stride, n_bins, n_terms, row_dev,
                                                          coef_dev, status_dev, pair_point_dev, n_pairs, tmix_dev);
     BI_LAUNCH_CHECK();
     return BI_OK;
@@ -862,4 +869,101 @@ extern "C" int bi_mixture_partials(const double* tmix_dev, int32_t n_space, cons
 #undef BI_MIX_CASE
     bi_set_error("bi_mixture_partials: unsupported configuration");
     return BI_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The whole template-space evaluation in ONE call: K1 -> (template morph) -> K5 / K5b -> ragged finalize, four or
+// five launches back to back with no host round trip in between (the counterpart of bi_unbinned_ll_batch).
+// ---------------------------------------------------------------------------------------------
+static inline int64_t bi_ts_align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+struct BiTemplateWorkspace { int64_t cell, frac, corner, weight, mus, row, coef, wterm, term_source, partial, tmix, total; };
+
+static BiTemplateWorkspace bi_template_layout(int32_t D, int32_t S, int64_t P, int64_t n_partials, int64_t n_pairs,
+                                              int64_t n_bins, int32_t mixture) {
+    const int64_t C = (int64_t)1 << D, Dd = D > 0 ? D : 1, K = C * S;
+    BiTemplateWorkspace w;
+    int64_t o = 0;
+    w.cell = o;        o += bi_ts_align256(P * Dd * 4);
+    w.frac = o;        o += bi_ts_align256(P * Dd * 8);
+    w.corner = o;      o += bi_ts_align256(P * C * 4);
+    w.weight = o;      o += bi_ts_align256(P * C * 8);
+    w.mus = o;         o += bi_ts_align256(P * S * 8);
+    w.row = o;         o += bi_ts_align256(P * K * 4);
+    w.coef = o;        o += bi_ts_align256(P * K * 8);
+    w.wterm = o;       o += bi_ts_align256(P * K * 8);
+    w.term_source = o; o += bi_ts_align256(K * 4);
+    w.partial = o;     o += bi_ts_align256((n_partials > 0 ? n_partials : 1) * 8);
+    w.tmix = o;        o += mixture ? bi_ts_align256(n_pairs * n_bins * 8) : 0;
+    w.total = o;
+    return w;
+}
+
+extern "C" int64_t bi_template_workspace_bytes(int32_t n_dims, int32_t n_sources, int64_t n_points, int64_t n_partials,
+                                               int64_t n_pairs, int64_t n_template_bins, int32_t mixture) {
+    if (n_dims < 0 || n_dims > BI_MAX_DIMS || n_sources < 1 || n_points < 0 || n_partials < 0 || n_pairs < 0 ||
+        n_template_bins < 1)
+        return -1;
+    return bi_template_layout(n_dims, n_sources, n_points, n_partials, n_pairs, n_template_bins, mixture).total;
+}
+
+extern "C" int bi_template_ll_batch(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                                    int32_t n_sources, int64_t n_points,
+                                    const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                                    const double* eff_dev, const double* mus_anchor_dev, const uint8_t* allow_negative_host,
+                                    const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+                                    int32_t n_space, const int32_t* n_bins_host, int32_t method, int32_t mixture,
+                                    const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
+                                    const int64_t* dataset_offset_dev,
+                                    int64_t n_groups, int32_t group_points, const int32_t* groups_dev,
+                                    const int64_t* unit_offset_dev, const int32_t* unit_group_dev, int64_t n_units,
+                                    const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
+                                    int64_t n_pairs, int64_t n_partials, int64_t max_partials,
+                                    double outlier_likelihood, void* workspace_dev, int64_t workspace_bytes,
+                                    double* logl_dev, double* logsum_dev, double* musum_dev, int32_t* status_dev,
+                                    void* stream) {
+    BI_REQUIRE(n_points >= 0 && n_pairs >= 0, "negative size");
+    if (n_points == 0 || n_pairs == 0) return BI_OK;
+    BiSpace space;
+    int rc = bi_fill_space(&space, n_space, n_bins_host);
+    if (rc != BI_OK) return rc;
+    BI_REQUIRE(n_dims >= 0 && n_dims <= BI_MAX_DIMS, "n_dims=%d outside [0,%d]", n_dims, BI_MAX_DIMS);
+    BI_REQUIRE(n_sources >= 1 && n_sources <= BI_MAX_SOURCES, "n_sources=%d outside [1,%d]", n_sources, BI_MAX_SOURCES);
+    const int32_t K = (1 << n_dims) * n_sources;
+    const BiTemplateWorkspace w = bi_template_layout(n_dims, n_sources, n_points, n_partials, n_pairs, space.n_cells, mixture);
+    BI_REQUIRE(workspace_dev && workspace_bytes >= w.total, "workspace too small: %lld < %lld bytes",
+               (long long)workspace_bytes, (long long)w.total);
+    BI_REQUIRE(((uintptr_t)workspace_dev & 255) == 0, "workspace_dev must be 256-byte aligned");
+    BI_REQUIRE(logl_dev && musum_dev && status_dev, "bi_template_ll_batch: NULL output pointer");
+    char* base = (char*)workspace_dev;
+    int32_t* row = (int32_t*)(base + w.row);
+    double* coef = (double*)(base + w.coef);
+    double* wterm = (double*)(base + w.wterm);
+    int32_t* term_source = (int32_t*)(base + w.term_source);
+    double* mus = (double*)(base + w.mus);
+    double* partial = (double*)(base + w.partial);
+    rc = bi_point_setup(n_dims, n_anchors_host, axes_host, n_sources, n_points, zs_dev, rate_mult_dev, scale_dev, eff_dev,
+                        mus_anchor_dev, allow_negative_host, (int32_t*)(base + w.cell), (double*)(base + w.frac),
+                        (int32_t*)(base + w.corner), (double*)(base + w.weight), mus, musum_dev, status_dev, row, coef,
+                        wterm, term_source, stream);
+    if (rc != BI_OK) return rc;
+    if (n_units > 0) {
+        if (mixture) {
+            double* tmix = (double*)(base + w.tmix);
+            rc = bi_template_mix(templates_dev, row_stride, bin_stride, space.n_cells, K, row, coef, status_dev,
+                                 pair_point_dev, n_pairs, tmix, stream);
+            if (rc != BI_OK) return rc;
+            rc = bi_mixture_partials(tmix, n_space, n_bins_host, method, ev_bin_dev, ev_frac_dev, ld_frac, dataset_offset_dev,
+                                     status_dev, n_groups, group_points, groups_dev, unit_offset_dev, unit_group_dev,
+                                     n_units, pair_point_dev, pair_partial_offset_dev, outlier_likelihood, partial, stream);
+        } else {
+            rc = bi_template_partials(templates_dev, row_stride, bin_stride, n_space, n_bins_host, method, ev_bin_dev,
+                                      ev_frac_dev, ld_frac, dataset_offset_dev, K, n_sources, row, coef, wterm, term_source,
+                                      mus, status_dev, n_groups, group_points, groups_dev, unit_offset_dev, unit_group_dev,
+                                      n_units, pair_point_dev, pair_partial_offset_dev, outlier_likelihood, partial, stream);
+        }
+        if (rc != BI_OK) return rc;
+    }
+    return bi_template_finalize(partial, pair_partial_offset_dev, pair_point_dev, musum_dev, status_dev, n_pairs,
+                                max_partials, logl_dev, logsum_dev, stream);
 }

@@ -1234,6 +1234,34 @@ class TemplateUnbinnedEngine(_EngineBase):
         self.launches += 1
         return logl, logsum
 
+    def run_one_call(self, P, sched, zs_d, mult_d, scale_d, eff_d):
+        """ONE C-ABI call (bi_template_ll_batch): K1 -> (template morph) -> K5 / K5b -> ragged finalize, launched back to
+        back.  Returns (dict with musum / status device tensors, logl [Q], logsum [Q]) in PAIR order."""
+        torch = self.torch
+        Q = sched["n_pairs"]
+        mixture = int(self.mode == 'mixture')
+        nbytes = int(self.lib.bi_template_workspace_bytes(self.grid.n_dims, self.n_sources, P, sched["n_partials"], Q,
+                                                          self.n_template_bins, mixture))
+        ws = self.ws.get("ts_ws", nbytes, torch.uint8)
+        o = dict(musum=self.ws.get("musum", P, torch.float64), status=self.ws.get("status", P, torch.int32))
+        logl = self.ws.get("ts_logl", Q, torch.float64)
+        logsum = self.ws.get("ts_logsum", Q, torch.float64)
+        templates = self.templates_rows if mixture else self.templates
+        row_stride, bin_stride = (self.n_template_bins, 1) if mixture else (self.row_stride, self.bin_stride)
+        _cabi.check(self.lib.bi_template_ll_batch(
+            self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat),
+            self.n_sources, P, _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
+            _cabi.dev_ptr(self.mus_anchor), _cabi.host_ptr(self.allow_negative),
+            _cabi.dev_ptr(templates), row_stride, bin_stride, self.n_space, _cabi.host_ptr(self.n_bins_i32), self.method,
+            mixture, _cabi.dev_ptr(self.ev_bin), _cabi.dev_ptr(self.ev_frac), self.ld_frac, _cabi.dev_ptr(self.offsets),
+            sched["n_groups"], sched["group_points"], _cabi.dev_ptr(sched["groups"]), _cabi.dev_ptr(sched["unit_offset"]),
+            _cabi.dev_ptr(sched["unit_group"]), sched["n_units"], _cabi.dev_ptr(sched["pair_point"]),
+            _cabi.dev_ptr(sched["partial_offset"]), Q, sched["n_partials"], sched["max_partials"],
+            self.outlier_likelihood, _cabi.dev_ptr(ws), ws.numel(), _cabi.dev_ptr(logl), _cabi.dev_ptr(logsum),
+            _cabi.dev_ptr(o["musum"]), _cabi.dev_ptr(o["status"]), self._stream()), "bi_template_ll_batch")
+        self.launches += (2 + (2 if mixture else 1)) if sched["n_units"] else 2
+        return o, logl, logsum
+
     def mixture_kernel_only(self, sched, o):
         """bi_mixture_partials alone on the mixture templates the last run_schedule left in the workspace
         (bench / profiling: the HBM-bound kernel without K1, the template morph and the finalize)."""
@@ -1256,8 +1284,7 @@ class TemplateUnbinnedEngine(_EngineBase):
             raise RuntimeError("set_datasets must be called first")
         zs = np.asarray(zs, dtype=np.float64).reshape(P, self.grid.n_dims)
         zs_d, mult_d, scale_d, eff_d, nbytes = self._upload_points(zs, mult, scale, eff)
-        o = self._setup_terms(P, zs_d, mult_d, scale_d, eff_d)
-        logl, logsum = self.run_schedule(sched, o)
+        o, logl, logsum = self.run_one_call(P, sched, zs_d, mult_d, scale_d, eff_d)
         n_f = 3 * P if return_parts else P
         out_pin = self.ws.get("d2h", 3 * P, torch.float64, pinned=True)
         out_pin[:P].copy_(logl, non_blocking=True)

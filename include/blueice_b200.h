@@ -360,6 +360,31 @@ int bi_mixture_partials(const double* tmix_dev, int32_t n_space, const int32_t* 
                         double outlier_likelihood, double* partial_dev, void* stream);
 
 /*
+ * The whole template-space evaluation in ONE call (the counterpart of bi_unbinned_ll_batch): K1 bi_point_setup ->
+ * (mixture != 0: bi_template_mix) -> bi_template_partials / bi_mixture_partials -> bi_template_finalize, launched back
+ * to back.  Arguments as in those entry points; n_partials = pair_partial_offset[n_pairs]; mixture != 0 selects K5b
+ * (templates_dev then is the plain [n_rows, n_bins] layout).  workspace_dev: bi_template_workspace_bytes(...) bytes,
+ * 256-byte aligned (K1 outputs, partials, mixture templates).  Outputs: logl_dev / logsum_dev [n_pairs] in PAIR order,
+ * musum_dev / status_dev [n_points].
+ */
+int64_t bi_template_workspace_bytes(int32_t n_dims, int32_t n_sources, int64_t n_points, int64_t n_partials,
+                                    int64_t n_pairs, int64_t n_template_bins, int32_t mixture);
+int bi_template_ll_batch(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                         int32_t n_sources, int64_t n_points,
+                         const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                         const double* eff_dev, const double* mus_anchor_dev, const uint8_t* allow_negative_host,
+                         const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+                         int32_t n_space, const int32_t* n_bins_host, int32_t method, int32_t mixture,
+                         const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
+                         const int64_t* dataset_offset_dev,
+                         int64_t n_groups, int32_t group_points, const int32_t* groups_dev,
+                         const int64_t* unit_offset_dev, const int32_t* unit_group_dev, int64_t n_units,
+                         const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
+                         int64_t n_pairs, int64_t n_partials, int64_t max_partials,
+                         double outlier_likelihood, void* workspace_dev, int64_t workspace_bytes,
+                         double* logl_dev, double* logsum_dev, double* musum_dev, int32_t* status_dev, void* stream);
+
+/*
  * On-device toy Monte Carlo generation.
  *
  * Replaces Model.simulate (model.py:69-91) for models whose sources are histogram templates:
