@@ -266,3 +266,28 @@ def test_api_mixture_engine():
                               likelihood_config={'unbinned_engine': 'auto'})
     from blueice_b200.engine import UnbinnedEngine
     assert type(ll_auto._engine) is UnbinnedEngine
+
+
+@pytest.mark.parametrize("mode", ["exact", "mixture"])
+def test_one_call_entry_equals_the_staged_calls(mode):
+    """bi_template_ll_batch (K1 -> morph -> K5 / K5b -> finalize in one C call) == the same stages called one by one
+    (bi_point_setup, bi_template_mix, bi_template_partials / bi_mixture_partials, bi_template_finalize), bit for bit."""
+    axes, edges, templates, mus = _model(3, 2, (-1., 0., 1.), (30, 24))
+    _, te, _, _ = _engines(axes, edges, templates, mus, mode=mode)
+    x, y = wl.c2_events(templates, mus, edges, 5000, seed=9)
+    offsets = np.array([0, 1200, 1200, 3300, 5000])
+    te.set_datasets(np.vstack([x, y])[:, :5000], offsets)
+    zs, mult = wl.scan_points(23, 2, 3, seed=4, z_range=(-1.1, 1.1))
+    datasets = np.arange(23) % 4
+    sched, order = te.pair_schedule(datasets, zs)
+    zs_d, mult_d, scale_d, eff_d, _ = te._upload_points(zs, mult, None, None)
+    zs_d, mult_d = zs_d.clone(), mult_d.clone()
+    o1, logl1, logsum1 = te.run_one_call(23, sched, zs_d, mult_d, None, None)
+    a = (logl1.cpu().numpy().copy(), logsum1.cpu().numpy().copy(), o1["musum"].cpu().numpy().copy(),
+         o1["status"].cpu().numpy().copy())
+    o2 = te._setup_terms(23, zs_d, mult_d, None, None)
+    logl2, logsum2 = te.run_schedule(sched, o2)
+    b = (logl2.cpu().numpy(), logsum2.cpu().numpy(), o2["musum"].cpu().numpy(), o2["status"].cpu().numpy())
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    assert np.any(a[3] != 0) and np.any(np.isneginf(a[0]))           # out-of-range points included
