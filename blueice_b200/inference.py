@@ -442,6 +442,73 @@ def one_parameter_interval(lf, target, bound, confidence_level=0.9, kind='upper'
     raise ValueError("kind must be 'upper', 'lower' or 'central'")
 
 
+def one_parameter_interval_scan(lf, target, bound, confidence_level=0.9, kind='upper', n_grid=17, refinements=3,
+                                t_ppf=None, **kwargs):
+    """one_parameter_interval with the conditional fits of a whole grid of hypotheses advanced in lock step
+    (profile_scan) instead of one bestfit per brentq step: the crossing of the test statistic with its critical value
+    is bracketed on n_grid hypotheses, the bracket is re-scanned `refinements` times and the crossing interpolated
+    linearly.  Same conventions as one_parameter_interval (inference.py:332-389): Wilks' chi2(1) unless t_ppf is given;
+    kind 'upper' / 'lower' / 'central'; bound = search limit (2-tuple for 'central')."""
+    if target is None:
+        target = lf.source_list[-1] + _RATE_SUFFIX
+    # global best fit: the lock-step fitter on a single 'hypothesis-free' fit (target floats)
+    names_free = [n for n in lf.parameter_names() if n not in kwargs]
+    x_best, f_best = _global_fit(lf, names_free, kwargs)
+    global_best, max_ll = x_best[target], f_best
+
+    def crossing(lo, hi, quantile, rising):
+        """hypothesis in [lo, hi] where 2 (max_ll - ll_cond(h)) - critical(h) changes sign."""
+        for _ in range(refinements + 1):
+            grid = np.linspace(lo, hi, n_grid)
+            prof, _ = profile_scan(lf, target, grid, **kwargs)
+            crit = np.array([stats.norm.ppf(quantile) ** 2 if t_ppf is None else t_ppf(h, quantile) for h in grid])
+            t = 2 * (max_ll - prof) - crit
+            sign = t > 0
+            flips = np.flatnonzero(sign[1:] != sign[:-1])
+            if not len(flips):
+                raise OptimizationFailed("the test statistic does not cross its critical value inside the bound")
+            i = flips[0] if rising else flips[-1]
+            lo, hi = grid[i], grid[i + 1]
+            t_lo, t_hi = t[i], t[i + 1]
+        return lo + (hi - lo) * (0.0 - t_lo) / (t_hi - t_lo)
+
+    if kind == 'upper':
+        return crossing(global_best, bound, confidence_level, True)
+    if kind == 'lower':
+        return crossing(bound, global_best, 1 - confidence_level, False)
+    if kind == 'central':
+        return (crossing(bound[0], global_best, (1 - confidence_level) / 2, False),
+                crossing(global_best, bound[1], 1 - (1 - confidence_level) / 2, True))
+    raise ValueError("kind must be 'upper', 'lower' or 'central'")
+
+
+def _global_fit(lf, names_free, fixed):
+    """Best fit of one dataset over names_free with the lock-step BFGS core (one fit): ({name: value}, max logL)."""
+    lo, hi, start = [], [], []
+    for n in names_free:
+        if n.endswith(_RATE_SUFFIX):
+            lo.append(0.0); hi.append(np.inf); start.append(1.0)
+        else:
+            b = lf.get_bounds(n)
+            s0 = lf.pdf_base_config.get(n)
+            if not isinstance(s0, (int, float)):
+                s0 = lf.shape_parameters[n][2]
+            lo.append(b[0]); hi.append(b[1]); start.append(s0)
+    fixed_names = list(fixed.keys())
+    columns = names_free + fixed_names
+
+    def minus_ll(points, fit_index):
+        cols = np.empty((len(points), len(columns)))
+        cols[:, :len(names_free)] = points
+        for j, key in enumerate(fixed_names):
+            cols[:, len(names_free) + j] = fixed[key]
+        return -lf.batch(cols, columns)
+
+    x, f, _, _ = _lockstep_bfgs(minus_ll, np.asarray(start, dtype=np.float64)[None, :],
+                                np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64))
+    return dict(zip(names_free, x[0])), -f[0]
+
+
 def plot_likelihood_ratio(lf, *space, vmax=15, bestfit_routine=None, plot_kwargs=None, **kwargs):
     """Plot the profile -log likelihood ratio over 1 or 2 parameters (needs matplotlib)."""
     import matplotlib.pyplot as plt

@@ -100,3 +100,43 @@ def test_profile_scan_matches_conditional_scipy_fits():
     flat, none = inference.profile_scan(OneDataset(), 'sig_rate_multiplier', values, bg_rate_multiplier=1.0,
                                         shift1=0.0, shift2=0.0)
     assert len(none) == 0 and flat[2] == orc([0., 0.], [1., 1.])
+
+
+def test_interval_scan_matches_the_sequential_interval():
+    """one_parameter_interval_scan (grids of conditional fits in lock step) lands where brentq over sequential scipy
+    fits does (the reference's one_parameter_interval, inference.py:332-389)."""
+    from scipy import stats
+    from scipy.optimize import brentq
+    toy = OracleToyLikelihood(n_toys=1)
+    orc = toy.oracles[0]
+
+    class OneDataset(object):
+        rate_parameters, shape_parameters, pdf_base_config = toy.rate_parameters, toy.shape_parameters, toy.pdf_base_config
+        get_bounds = staticmethod(lambda name: (-2., 2.))
+        source_list = ['bg', 'sig']
+
+        def parameter_names(self):
+            return ['bg_rate_multiplier', 'sig_rate_multiplier', 'shift1', 'shift2']
+
+        def batch(self, cols, names, livetime_days=None):
+            cols = np.asarray(cols, dtype=float)
+            im = [names.index('bg_rate_multiplier'), names.index('sig_rate_multiplier')]
+            iz = [names.index('shift1'), names.index('shift2')]
+            return np.array([orc(row[iz], row[im]) for row in cols])
+
+    lf = OneDataset()
+    # shift parameters fixed: a smooth 2-parameter problem, so both methods must agree closely
+    limit = inference.one_parameter_interval_scan(lf, 'sig_rate_multiplier', 3.0, confidence_level=0.9, kind='upper',
+                                                  shift1=0.0, shift2=0.0)
+    bounds = [(0, None)]
+    free = minimize(lambda x: -orc([0., 0.], [x[0], x[1]]), [1, 1], method='L-BFGS-B', bounds=[(0, None), (0, None)])
+
+    def t(h):
+        cond = minimize(lambda x: -orc([0., 0.], [x[0], h]), [1], method='L-BFGS-B', bounds=bounds)
+        return 2 * (-free.fun + cond.fun) - stats.norm.ppf(0.9) ** 2
+
+    ref = brentq(t, free.x[1], 3.0)
+    assert abs(limit - ref) <= 2e-3 * ref, (limit, ref)
+    lo, hi = inference.one_parameter_interval_scan(lf, 'sig_rate_multiplier', (0.0, 3.0), confidence_level=0.68,
+                                                   kind='central', shift1=0.0, shift2=0.0)
+    assert lo < free.x[1] < hi
