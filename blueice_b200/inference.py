@@ -28,7 +28,9 @@ DEFAULT_BESTFIT_ROUTINE = 'scipy'
 _RATE_SUFFIX = '_rate_multiplier'
 
 __all__ = ['best_anchor', 'make_objective', 'bestfit_scipy', 'bestfit_minuit', 'plot_likelihood_ratio',
-           'one_parameter_interval', 'bestfit_emcee']
+           'one_parameter_interval', 'bestfit_emcee',
+           # batched drivers (not in the reference): many fits advanced in lock step on the device
+           'bestfit_toys', 'profile_scan', 'one_parameter_interval_scan']
 
 
 def best_anchor(lf):
