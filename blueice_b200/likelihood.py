@@ -360,15 +360,28 @@ class LogLikelihoodBase(object):
         if params.ndim != 2 or params.shape[1] != len(names):
             raise ValueError("params must have shape [n_points, %d]" % len(names))
         P = params.shape[0]
-        self._kwargs_to_settings(**{n: 1.0 for n in names})          # same name validation as __call__
-        defaults_mult, defaults_settings = self._kwargs_to_settings()
-        zs = np.empty((P, len(self.shape_parameters)), dtype=np.float64)
-        for j, name in enumerate(self.shape_parameters):
-            zs[:, j] = params[:, names.index(name)] if name in names else defaults_settings[name]
-        mult = np.empty((P, len(self.source_name_list)), dtype=np.float64)
-        for j, source_name in enumerate(self.source_name_list):
-            key = source_name + _RATE_SUFFIX
-            mult[:, j] = params[:, names.index(key)] if key in names else defaults_mult[j]
+        # the column map of a name list is resolved (and validated like __call__ validates its kwargs) once per list
+        key = (tuple(names), len(self.rate_parameters),
+               tuple(repr(self._default_z(n, bv)) for n, (_, _, bv) in self.shape_parameters.items()))
+        cache = self.__dict__.setdefault('_column_maps', {})
+        cmap = cache.get(key)
+        if cmap is None:
+            self._kwargs_to_settings(**{n: 1.0 for n in names})      # same name validation as __call__
+            defaults_mult, defaults_settings = self._kwargs_to_settings()
+            z_cols = [(names.index(name) if name in names else -1, defaults_settings[name]) for name in self.shape_parameters]
+            m_cols = [(names.index(s + _RATE_SUFFIX) if s + _RATE_SUFFIX in names else -1, defaults_mult[j])
+                      for j, s in enumerate(self.source_name_list)]
+            numeric = all(c >= 0 or _is_number(v) for c, v in z_cols)
+            cmap = (z_cols, m_cols)
+            if numeric and len(cache) < 64:
+                cache[key] = cmap
+        z_cols, m_cols = cmap
+        zs = np.empty((P, len(z_cols)), dtype=np.float64)
+        for j, (c, default) in enumerate(z_cols):
+            zs[:, j] = params[:, c] if c >= 0 else default
+        mult = np.empty((P, len(m_cols)), dtype=np.float64)
+        for j, (c, default) in enumerate(m_cols):
+            mult[:, j] = params[:, c] if c >= 0 else default
         return zs, mult
 
     def _livetime_scale(self, livetime_days):
