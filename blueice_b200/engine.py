@@ -472,7 +472,7 @@ class UnbinnedEngine(_EngineBase):
         try:
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
                 cap = torch.cuda.current_stream(self.device)
                 if st["n_in"]:
                     st["dev_in"].copy_(st["pin_in"], non_blocking=True)
@@ -1333,7 +1333,7 @@ class TemplateUnbinnedEngine(_EngineBase):
                 try:                                                # the first calls size the workspace buffers eagerly
                     torch.cuda.current_stream(self.device).synchronize()
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
                         device_sequence()
                     entry["graph"] = g
                     entry["ptrs"] = tuple(t.data_ptr() for t in self.ws.buf.values())
