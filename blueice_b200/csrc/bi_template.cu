@@ -55,19 +55,26 @@ k_template_prepare(const __grid_constant__ BiSpace sp, const __grid_constant__ B
 // ---------------------------------------------------------------------------------------------
 // template value of one row at one prepared event, scipy's operation order (== k_hist_lookup_linear)
 // ---------------------------------------------------------------------------------------------
-// Template values of one row at one prepared event.  Linear lookups read the PAIR layout: element (row, bin) holds
-// (T[row, bin], T[row, bin + 1 along the last dimension]) in 16 aligned bytes, so the two last-dimension neighbours of
-// a lookup corner come with ONE 128-bit load (half as many scattered L2 requests, the resource that bounds K5).
+// Template values of one row at one prepared event.  Linear lookups read a PACKED layout in which element (row, bin)
+// holds the bin together with its neighbours along the last (and second-last) dimension, so that the lookup corners come
+// with ONE wide load -- K5 is bound by the number of scattered L2 requests, not by bytes:
+//   1-D:    [row][bin][2] = (T[b], T[b + 1])                                   one 128-bit load
+//   >= 2-D: [row][bin][4] = (T[b], T[b + 1], T[b + s], T[b + s + 1])            one 256-bit load (LDG.E.256) per
+//           s = stride of the second-last dimension                             four lookup corners
 template <int NS>
 __device__ __forceinline__ void bi_ts_gather(const double* __restrict__ V, const BiTsSpace& sp, double (&v)[1 << NS]) {
     if constexpr (NS == 0) {
         v[0] = __ldg(V);                                            // piecewise: the bin's value (plain layout)
+    } else if constexpr (NS == 1) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(V));
+        v[0] = t.x;
+        v[1] = t.y;
     } else {
 #pragma unroll
-        for (int c = 0; c < (1 << NS); c += 2) {
-            const double2 t = __ldg(reinterpret_cast<const double2*>(V + (c ? sp.corner_off[c] : 0)));
-            v[c] = t.x;
-            v[c + 1] = t.y;
+        for (int c = 0; c < (1 << NS); c += 4) {
+            const double* q = V + (c ? sp.corner_off[c] : 0);
+            asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                : "=d"(v[c]), "=d"(v[c + 1]), "=d"(v[c + 2]), "=d"(v[c + 3]) : "l"(q));
         }
     }
 }
@@ -732,8 +739,10 @@ extern "C" int bi_template_partials(const double* templates_dev, int64_t row_str
                    partial_dev,
                "bi_template_partials: NULL device pointer");
     BI_REQUIRE(method == BI_LOOKUP_PIECEWISE || ev_frac_dev, "bi_template_partials: ev_frac_dev is NULL");
-    BI_REQUIRE(method == BI_LOOKUP_PIECEWISE || (((uintptr_t)templates_dev & 15) == 0 && (row_stride % 2) == 0 && (bin_stride % 2) == 0),
-               "bi_template_partials: the linear method reads the 16-byte aligned pair layout (even strides)");
+    const int pack = method == BI_LOOKUP_PIECEWISE ? 1 : (n_space == 1 ? 2 : 4);
+    BI_REQUIRE(((uintptr_t)templates_dev & (8 * pack - 1)) == 0 && (row_stride % pack) == 0 && (bin_stride % pack) == 0,
+               "bi_template_partials: the lookup reads %d-double packed template elements (aligned, strides multiples of %d)",
+               pack, pack);
     BiTsSpace sp;
     memset(&sp, 0, sizeof(sp));
     const int ns = method == BI_LOOKUP_LINEAR ? n_space : 0;

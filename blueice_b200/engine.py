@@ -1013,12 +1013,17 @@ class TemplateUnbinnedEngine(_EngineBase):
         self.templates_rows = torch.from_numpy(t).to(self.device)             # [n_rows, B]: K3 / full_output / K5b
         linear = self.method == _cabi.LOOKUP_LINEAR
         if linear and mode == 'exact':
-            # K5 reads the PAIR layout: (T[row, bin], T[row, bin + 1 along the last dimension]) in 16 aligned bytes, one
-            # 128-bit gather per two lookup corners; the neighbour of the last bin of an axis is never used (cell <= n - 2)
-            shift = 1 if self.n_bins_i32[-1] > 1 else 0
-            self.templates = torch.stack([self.templates_rows, torch.roll(self.templates_rows, -shift, dims=1)],
-                                         dim=2).contiguous()
-            self.row_stride, self.bin_stride = 2 * self.n_template_bins, 2
+            # K5 reads a PACKED layout: every bin with its neighbours along the last (and second-last) dimension in 16 /
+            # 32 aligned bytes, so the lookup corners come with one 128- / 256-bit gather; the neighbours of the last bin
+            # of an axis are never used (cell <= n - 2)
+            r = self.templates_rows
+            s1 = 1 if self.n_bins_i32[-1] > 1 else 0
+            parts = [r, torch.roll(r, -s1, dims=1)]
+            if self.n_space >= 2:
+                s2 = int(self.n_bins_i32[-1]) if self.n_bins_i32[-2] > 1 else 0
+                parts += [torch.roll(r, -s2, dims=1), torch.roll(r, -(s2 + s1), dims=1)]
+            self.templates = torch.stack(parts, dim=2).contiguous()
+            self.row_stride, self.bin_stride = len(parts) * self.n_template_bins, len(parts)
         else:
             self.templates = self.templates_rows
             self.row_stride, self.bin_stride = self.n_template_bins, 1

@@ -298,9 +298,11 @@ int bi_hist_lookup(const double* templates_dev, int64_t n_templates, int32_t n_s
  * bi_template_partials:
  *   templates_dev        element (row, bin) at templates_dev + row * row_stride + bin * bin_stride (in doubles).
  *                        PIECEWISE: the bin's value (plain [n_rows, n_bins]: row_stride = n_bins, bin_stride = 1).
- *                        LINEAR: the PAIR layout [n_rows, n_bins, 2] = (T[row, bin], T[row, bin + 1 along the last
- *                        dimension]) (row_stride = 2 * n_bins, bin_stride = 2, 16-byte aligned): the two last-dimension
- *                        neighbours of a lookup corner come with one 128-bit gather
+ *                        LINEAR: a PACKED layout holding every bin together with its lookup neighbours, so that the
+ *                        corners come with one wide gather (the kernel is bound by the number of L2 requests):
+ *                        1-D  [n_rows, n_bins, 2] = (T[b], T[b + 1])                          (strides 2 n_bins, 2; 16-byte aligned)
+ *                        >=2-D [n_rows, n_bins, 4] = (T[b], T[b + 1], T[b + s], T[b + s + 1]) (strides 4 n_bins, 4; 32-byte aligned),
+ *                        s = stride of the second-last dimension (0 for a one-bin dimension, as the + 1)
  *   dataset_offset_dev   [n_datasets + 1] int64 first event of each dataset in ev_bin_dev / ev_frac_dev
  *   row/coef/wterm/term_source/mus/status: outputs of bi_point_setup[_sourcewise] for the points ([P, K], ..., [P])
  *   pair list            pair q evaluates point pair_point_dev[q] on one dataset; its superblock partials go to

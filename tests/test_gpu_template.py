@@ -65,14 +65,15 @@ def test_single_dataset_bit_identical_to_anchor_engine(method, n_events):
     assert one[0] == got[0]
 
 
-def test_pair_layout_holds_the_last_dimension_neighbours():
-    """K5's template layout for linear lookups: (T[row, bin], T[row, bin + 1 along the last dimension])."""
+def test_packed_layout_holds_the_lookup_neighbours():
+    """K5's template layout for linear lookups: every bin with its neighbours along the last two dimensions."""
     axes, edges, templates, mus = _model(3, 3, (-1., 0., 1.), (25, 20))
     _, te, _, rows = _engines(axes, edges, templates, mus)
     flat = rows.reshape(len(rows), -1)
-    pairs = te.templates.cpu().numpy()
-    assert pairs.shape == (len(rows), 500, 2) and te.row_stride == 1000 and te.bin_stride == 2
-    assert np.array_equal(pairs[:, :, 0], flat) and np.array_equal(pairs[:, :-1, 1], flat[:, 1:])
+    packed = te.templates.cpu().numpy()
+    assert packed.shape == (len(rows), 500, 4) and te.row_stride == 2000 and te.bin_stride == 4
+    assert np.array_equal(packed[:, :, 0], flat) and np.array_equal(packed[:, :-1, 1], flat[:, 1:])
+    assert np.array_equal(packed[:, :-20, 2], flat[:, 20:]) and np.array_equal(packed[:, :-21, 3], flat[:, 21:])
     _, tp, _, _ = _engines(axes, edges, templates, mus, 'piecewise')
     assert tp.templates.shape == (len(rows), 500) and tp.bin_stride == 1
 
