@@ -69,8 +69,8 @@ SIGNATURES = {
                                             _c_void_p, _c_void_p, _f64, _c_void_p, _c_void_p]),
     "bi_template_finalize": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i64,
                                             _c_void_p, _c_void_p, _c_void_p]),
-    "bi_template_mix": (ctypes.c_int, [_c_void_p, _i64, _i64, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                                       _i64, _c_void_p, _c_void_p]),
+    "bi_template_mix": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _c_void_p, _i32, _i32, _c_void_p, _c_void_p,
+                                       _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p]),
     "bi_mixture_partials": (ctypes.c_int, [_c_void_p, _i32, _c_void_p, _i32, _c_void_p, _c_void_p, _i64, _c_void_p,
                                            _c_void_p, _i64, _i32, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p,
                                            _c_void_p, _f64, _c_void_p, _c_void_p]),
@@ -120,6 +120,7 @@ MMA_MAX_TERMS = 128
 PLAN_MAX_CELLS = 16384
 TS_MAX_TERMS = 256
 TS_GROUP_POINTS = 8
+MIX_GROUP_POINTS = 8
 POINT_OUT_OF_RANGE = 1
 POINT_UNPHYSICAL = 2
 LOOKUP_LINEAR = 0

@@ -322,7 +322,8 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
 __global__ void __launch_bounds__(256)
 k_template_mix(const double* __restrict__ T, int64_t row_stride, int64_t bin_stride, int64_t n_bins, int K,
                const int32_t* __restrict__ row, const double* __restrict__ coef, const int32_t* __restrict__ status,
-               const int32_t* __restrict__ pair_point, int64_t n_pairs, double* __restrict__ tmix) {
+               const int32_t* __restrict__ pair_point, int64_t n_pairs, double* __restrict__ tmix,
+               int pack, int64_t off1, int64_t off2) {
   for (int64_t q = blockIdx.y; q < n_pairs; q += gridDim.y) {
     const int64_t pt = pair_point ? pair_point[q] : q;
     if (status[pt] != 0) continue;
@@ -346,7 +347,15 @@ k_template_mix(const double* __restrict__ T, int64_t row_stride, int64_t bin_str
             for (int i = 0; i < 8; ++i) acc = fma(t[i], cf[k + i], acc);
         }
         for (; k < K; ++k) acc = fma(__ldg(T + (int64_t)rw[k] * row_stride + b * bin_stride), cf[k], acc);
-        tmix[q * n_bins + b] = acc;
+        // packed output (as K5's templates): element (q, b) = (m[b], m[b + off1], m[b + off2], m[b + off2 + off1]);
+        // every bin stores its value into the (up to four) elements it belongs to
+        double* dst = tmix + q * n_bins * pack;
+        dst[b * pack] = acc;
+        if (pack >= 2 && b - off1 >= 0) dst[(b - off1) * pack + 1] = acc;
+        if (pack == 4) {
+            if (b - off2 >= 0) dst[(b - off2) * 4 + 2] = acc;
+            if (b - off2 - off1 >= 0) dst[(b - off2 - off1) * 4 + 3] = acc;
+        }
     }
   }
 }
@@ -363,26 +372,54 @@ __device__ __forceinline__ void bi_mix_weights(const double (&y)[NS > 0 ? NS : 1
         w[c] = v;
     }
 }
+// the packed element(s) of the event's low-corner bin: one wide load per four lookup corners
+template <int NS>
+__device__ __forceinline__ void bi_mix_gather(const double* __restrict__ V, const BiTsSpace& sp, double (&v)[1 << NS]) {
+    if constexpr (NS == 0) {
+        v[0] = __ldg(V);
+    } else if constexpr (NS == 1) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(V));
+        v[0] = t.x;
+        v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < (1 << NS); c += 4) {
+            const double* q = V + (c ? sp.corner_off[c] : 0);
+            asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                : "=d"(v[c]), "=d"(v[c + 1]), "=d"(v[c + 2]), "=d"(v[c + 3]) : "l"(q));
+        }
+    }
+}
+// corners c ascending: r = v[0] * w[0], then fma
+template <int NS>
+__device__ __forceinline__ double bi_mix_eval(const double (&v)[1 << NS], const double (&w)[1 << NS]) {
+    double r = __dmul_rn(v[0], w[0]);
+#pragma unroll
+    for (int c = 1; c < (1 << NS); ++c) r = fma(v[c], w[c], r);
+    return r;
+}
 template <int NS>
 __device__ __forceinline__ double bi_mix_lookup(const double* __restrict__ V, const BiTsSpace& sp, const double (&w)[1 << NS]) {
-    double r = __dmul_rn(__ldg(V), w[0]);
-#pragma unroll
-    for (int c = 1; c < (1 << NS); ++c) r = fma(__ldg(V + sp.corner_off[c]), w[c], r);
-    return r;
+    double v[1 << NS];
+    bi_mix_gather<NS>(V, sp, v);
+    return bi_mix_eval<NS>(v, w);
 }
 
 // One canonical group (32 events) of one superblock per HALF-WARP: lane l16 of the half owns the adjacent events
 // 2 l16, 2 l16 + 1 (one canonical pair), so the pair product is formed in the lane and the tree needs two shuffle
 // levels; the two halves of a warp walk two consecutive superblocks in lock step.
 // FULL: both superblocks hold 512 events (no masking).
-template <int NP, int NS, bool FULL>
+template <int NP, int NS, bool FULL, bool FG>
 __device__ __forceinline__ void bi_mix_group(const double* __restrict__ Vbase, int64_t n_bins, int np, const BiTsSpace& sp,
                                              const int (&bin)[2], const double (&y)[2][NS > 0 ? NS : 1], int n_left, int l16,
                                              unsigned half_shift, unsigned live, double outlier, double (&M)[NP], int (&E)[NP],
                                              double (&Lslow)[NP], bool& any_slow) {
+    // FG: the group is full (np == NP): no guards, one basic block.
     // Vbase: mixture template of the group's first pair (pair q: Vbase + q * n_bins); np <= NP pairs in the group (slots
     // q >= np are skipped; a dead pair's row is unwritten memory whose results are ignored);
     // n_left: events of this half's superblock from this group's first event on (may be <= 0)
+    constexpr int PACK = NS == 0 ? 1 : (NS == 1 ? 2 : 4);
+    const int64_t e0 = (int64_t)bin[0] * PACK, e1 = (int64_t)bin[1] * PACK;      // packed elements of the two events
     const bool valid0 = FULL || 2 * l16 < n_left, valid1 = FULL || 2 * l16 + 1 < n_left;
     double w0[1 << NS], w1[1 << NS];
     bi_mix_weights<NS>(y[0], w0);
@@ -392,10 +429,10 @@ __device__ __forceinline__ void bi_mix_group(const double* __restrict__ Vbase, i
     const unsigned class_mask = (0x1111u << (l16 & 3)) << half_shift;     // lanes of class t in this half
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-        if (NP == 1 || q < np) {
+        if (FG || q < np) {
             const double* V = Vbase + (int64_t)q * n_bins;
-            double p0 = bi_mix_lookup<NS>(V + bin[0], sp, w0);
-            double p1 = bi_mix_lookup<NS>(V + bin[1], sp, w1);
+            double p0 = bi_mix_lookup<NS>(V + e0, sp, w0);
+            double p1 = bi_mix_lookup<NS>(V + e1, sp, w1);
             if (!FULL) {
                 if (!valid0) p0 = 1.0;                                     // events >= N count as p = 1
                 if (!valid1) p1 = 1.0;
@@ -410,13 +447,13 @@ __device__ __forceinline__ void bi_mix_group(const double* __restrict__ Vbase, i
     }
 #pragma unroll
     for (int q = 0; q < NP; ++q)
-        if (NP == 1 || q < np) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 4));    // quad: octets (0,1), (2,3)
+        if (FG || q < np) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 4));    // quad: octets (0,1), (2,3)
 #pragma unroll
     for (int q = 0; q < NP; ++q)
-        if (NP == 1 || q < np) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 8));    // oct
+        if (FG || q < np) v[q] = __dmul_rn(v[q], __shfl_xor_sync(BI_FULL_MASK, v[q], 8));    // oct
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-        if (NP == 1 || q < np) {
+        if (FG || q < np) {
             double m;
             int e;
             bi_split(v[q], &m, &e);
@@ -428,10 +465,10 @@ __device__ __forceinline__ void bi_mix_group(const double* __restrict__ Vbase, i
     if (bad_any) {                                                         // rare, warp-uniform: the densities are formed again
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            if ((NP == 1 || q < np) && ((live >> q) & 1u)) {
+            if ((FG || q < np) && ((live >> q) & 1u)) {
                 const double* V = Vbase + (int64_t)q * n_bins;
-                double p0 = bi_mix_lookup<NS>(V + bin[0], sp, w0);
-                double p1 = bi_mix_lookup<NS>(V + bin[1], sp, w1);
+                double p0 = bi_mix_lookup<NS>(V + e0, sp, w0);
+                double p1 = bi_mix_lookup<NS>(V + e1, sp, w1);
                 if (!valid0) p0 = 1.0;
                 if (!valid1) p1 = 1.0;
                 const bool ok = ((unsigned)(__double2hiint(p0) - BI_RANGE_LO) < BI_RANGE_SPAN) &&
@@ -480,7 +517,8 @@ __device__ __forceinline__ void bi_mix_load(const int32_t* __restrict__ ev_bin, 
 // unit = (pair group, PAIR of consecutive superblocks): half-warp h walks superblock 2 * unit_sb + h
 template <int NP, int NS>
 __global__ void __launch_bounds__(BI_TS_THREADS)
-k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins, const __grid_constant__ BiTsSpace sp,
+k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins /* doubles per mixture row: bins x pack */,
+                   const __grid_constant__ BiTsSpace sp,
                    const int32_t* __restrict__ ev_bin, const double* __restrict__ ev_frac, int64_t ld_frac,
                    const int64_t* __restrict__ dataset_offset, const int32_t* __restrict__ status,
                    int64_t n_groups, const BiTsGroup* __restrict__ groups, const int64_t* __restrict__ unit_offset,
@@ -546,10 +584,12 @@ k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins, const __grid
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
                 const int e0 = c0 + j * BI_EVENT_BLOCK;
-                if (all_full)
-                    bi_mix_group<NP, NS, true>(Vbase, n_bins, np, sp, bin[j], y[j], BI_SUPERBLOCK, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
+                if (all_full && np == NP)
+                    bi_mix_group<NP, NS, true, true>(Vbase, n_bins, np, sp, bin[j], y[j], BI_SUPERBLOCK, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
+                else if (all_full)
+                    bi_mix_group<NP, NS, true, false>(Vbase, n_bins, np, sp, bin[j], y[j], BI_SUPERBLOCK, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
                 else if (e0 < n_max)
-                    bi_mix_group<NP, NS, false>(Vbase, n_bins, np, sp, bin[j], y[j], n_ev - e0, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
+                    bi_mix_group<NP, NS, false, false>(Vbase, n_bins, np, sp, bin[j], y[j], n_ev - e0, l16, half_shift, live, outlier, M, E, Lslow, any_slow);
             }
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
@@ -794,10 +834,29 @@ extern "C" int bi_template_finalize(const double* partial_dev, const int64_t* pa
 // ---------------------------------------------------------------------------------------------
 // C-ABI of the mixture form
 // ---------------------------------------------------------------------------------------------
-extern "C" int bi_template_mix(const double* templates_dev, int64_t row_stride, int64_t bin_stride, int64_t n_bins,
+// packing of the mixture templates (as K5's template layout): doubles per bin and the bin offsets of the neighbours
+static void bi_ts_packing(const BiSpace& space, int method, int* pack, int64_t* off1, int64_t* off2) {
+    *pack = 1; *off1 = 0; *off2 = 0;
+    if (method != BI_LOOKUP_LINEAR) return;
+    const int ns = space.n_space;
+    *off1 = space.n_bins[ns - 1] > 1 ? 1 : 0;
+    if (ns == 1) { *pack = 2; return; }
+    *pack = 4;
+    *off2 = space.n_bins[ns - 2] > 1 ? space.stride[ns - 2] : 0;
+}
+
+extern "C" int bi_template_mix(const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+                               int32_t n_space, const int32_t* n_bins_host, int32_t method,
                                int32_t n_terms, const int32_t* row_dev, const double* coef_dev,
                                const int32_t* status_dev, const int32_t* pair_point_dev, int64_t n_pairs,
                                double* tmix_dev, void* stream) {
+    BiSpace space;
+    int rc = bi_fill_space(&space, n_space, n_bins_host);
+    if (rc != BI_OK) return rc;
+    const int64_t n_bins = space.n_cells;
+    int pack;
+    int64_t off1, off2;
+    bi_ts_packing(space, method, &pack, &off1, &off2);
     BI_REQUIRE(n_terms >= 1 && n_bins >= 1 && n_pairs >= 0, "bi_template_mix: bad sizes");
     if (n_pairs == 0) return BI_OK;
     BI_REQUIRE(templates_dev && row_dev && coef_dev && status_dev && tmix_dev, "bi_template_mix: NULL device pointer");
@@ -805,7 +864,7 @@ extern "C" int bi_template_mix(const double* templates_dev, int64_t row_stride, 
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)(n_pairs < 65535 ? n_pairs : 65535));
     k_template_mix<<<grid, 64, 0, (cudaStream_t)stream>>>(templates_dev, row_stride, bin_stride, n_bins, n_terms, row_dev,
-                                                         coef_dev, status_dev, pair_point_dev, n_pairs, tmix_dev);
+                                                         coef_dev, status_dev, pair_point_dev, n_pairs, tmix_dev, pack, off1, off2);
     BI_LAUNCH_CHECK();
     return BI_OK;
 }
@@ -846,7 +905,7 @@ extern "C" int bi_mixture_partials(const double* tmix_dev, int32_t n_space, cons
     int rc = bi_fill_space(&space, n_space, n_bins_host);
     if (rc != BI_OK) return rc;
     BI_REQUIRE(method == BI_LOOKUP_LINEAR || method == BI_LOOKUP_PIECEWISE, "unknown lookup method %d", method);
-    BI_REQUIRE(group_points == 1 || group_points == BI_TS_GROUP_POINTS, "group_points must be 1 or %d", BI_TS_GROUP_POINTS);
+    BI_REQUIRE(group_points == 1 || group_points == BI_MIX_GROUP_POINTS, "group_points must be 1 or %d", BI_MIX_GROUP_POINTS);
     BI_REQUIRE(n_groups >= 0 && n_units >= 0, "negative size");
     if (n_groups == 0 || n_units == 0) return BI_OK;
     BI_REQUIRE(tmix_dev && ev_bin_dev && dataset_offset_dev && status_dev && groups_dev && unit_offset_dev &&
@@ -862,19 +921,21 @@ extern "C" int bi_mixture_partials(const double* tmix_dev, int32_t n_space, cons
         int64_t off = 0;
         for (int d = 0; d < ns; ++d)
             if (((c >> (ns - 1 - d)) & 1) && space.n_bins[d] > 1) off += space.stride[d];
-        sp.corner_off[c] = off;
+        sp.corner_off[c] = off * (ns == 0 ? 1 : (ns == 1 ? 2 : 4));       // packed mixture rows (bi_template_mix)
     }
+    const int64_t row_doubles = space.n_cells * (ns == 0 ? 1 : (ns == 1 ? 2 : 4));
+    BI_REQUIRE(((uintptr_t)tmix_dev & 31) == 0, "bi_mixture_partials: tmix_dev must be 32-byte aligned");
     const BiTsGroup* groups = reinterpret_cast<const BiTsGroup*>(groups_dev);
     cudaStream_t st = (cudaStream_t)stream;
 #define BI_MIX_CASE(NPV, NSV)                                                                                          \
     if (group_points == NPV && ns == NSV)                                                                              \
-        return bi_mix_launch<NPV, NSV>(tmix_dev, space.n_cells, sp, ev_bin_dev, ev_frac_dev, ld_frac,                  \
+        return bi_mix_launch<NPV, NSV>(tmix_dev, row_doubles, sp, ev_bin_dev, ev_frac_dev, ld_frac,                    \
                                        dataset_offset_dev, status_dev, n_groups, groups, unit_offset_dev,              \
                                        unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,               \
                                        outlier_likelihood, partial_dev, st);
     BI_MIX_CASE(1, 0) BI_MIX_CASE(1, 1) BI_MIX_CASE(1, 2) BI_MIX_CASE(1, 3) BI_MIX_CASE(1, 4)
-    BI_MIX_CASE(BI_TS_GROUP_POINTS, 0) BI_MIX_CASE(BI_TS_GROUP_POINTS, 1) BI_MIX_CASE(BI_TS_GROUP_POINTS, 2)
-    BI_MIX_CASE(BI_TS_GROUP_POINTS, 3) BI_MIX_CASE(BI_TS_GROUP_POINTS, 4)
+    BI_MIX_CASE(BI_MIX_GROUP_POINTS, 0) BI_MIX_CASE(BI_MIX_GROUP_POINTS, 1) BI_MIX_CASE(BI_MIX_GROUP_POINTS, 2)
+    BI_MIX_CASE(BI_MIX_GROUP_POINTS, 3) BI_MIX_CASE(BI_MIX_GROUP_POINTS, 4)
 #undef BI_MIX_CASE
     bi_set_error("bi_mixture_partials: unsupported configuration");
     return BI_ERR_UNSUPPORTED;
@@ -903,7 +964,7 @@ static BiTemplateWorkspace bi_template_layout(int32_t D, int32_t S, int64_t P, i
     w.wterm = o;       o += bi_ts_align256(P * K * 8);
     w.term_source = o; o += bi_ts_align256(K * 4);
     w.partial = o;     o += bi_ts_align256((n_partials > 0 ? n_partials : 1) * 8);
-    w.tmix = o;        o += mixture ? bi_ts_align256(n_pairs * n_bins * 8) : 0;
+    w.tmix = o;        o += mixture ? bi_ts_align256(n_pairs * n_bins * 8 * 4) : 0;     // packed: up to 4 doubles per bin
     w.total = o;
     return w;
 }
@@ -959,8 +1020,8 @@ extern "C" int bi_template_ll_batch(int32_t n_dims, const int32_t* n_anchors_hos
     if (n_units > 0) {
         if (mixture) {
             double* tmix = (double*)(base + w.tmix);
-            rc = bi_template_mix(templates_dev, row_stride, bin_stride, space.n_cells, K, row, coef, status_dev,
-                                 pair_point_dev, n_pairs, tmix, stream);
+            rc = bi_template_mix(templates_dev, row_stride, bin_stride, n_space, n_bins_host, method, K, row, coef,
+                                 status_dev, pair_point_dev, n_pairs, tmix, stream);
             if (rc != BI_OK) return rc;
             rc = bi_mixture_partials(tmix, n_space, n_bins_host, method, ev_bin_dev, ev_frac_dev, ld_frac, dataset_offset_dev,
                                      status_dev, n_groups, group_points, groups_dev, unit_offset_dev, unit_group_dev,

@@ -1155,7 +1155,7 @@ class TemplateUnbinnedEngine(_EngineBase):
         sk = key[order]
         starts = np.flatnonzero(np.r_[True, sk[1:] != sk[:-1]]) if P else np.zeros(0, dtype=np.int64)
         ends = np.r_[starts[1:], P] if P else starts
-        np_max = _cabi.TS_GROUP_POINTS if P > 1 else 1
+        np_max = (_cabi.MIX_GROUP_POINTS if self.mode == 'mixture' else _cabi.TS_GROUP_POINTS) if P > 1 else 1
         step = np.where(cells[order[starts]] < 0, 1, np_max) if P else starts
         n_chunks = -(-(ends - starts) // np.maximum(step, 1))
         run = np.repeat(np.arange(len(starts)), n_chunks)
@@ -1210,9 +1210,10 @@ class TemplateUnbinnedEngine(_EngineBase):
         logl = self.ws.get("ts_logl", Q, torch.float64)
         logsum = self.ws.get("ts_logsum", Q, torch.float64)
         if sched["n_units"] and self.mode == 'mixture':
-            tmix = self.ws.get("ts_tmix", Q * self.n_template_bins, torch.float64)
+            tmix = self.ws.get("ts_tmix", 4 * Q * self.n_template_bins, torch.float64)     # packed: <= 4 doubles per bin
             _cabi.check(self.lib.bi_template_mix(
-                _cabi.dev_ptr(self.templates), self.row_stride, self.bin_stride, self.n_template_bins, self.n_terms,
+                _cabi.dev_ptr(self.templates), self.row_stride, self.bin_stride, self.n_space,
+                _cabi.host_ptr(self.n_bins_i32), self.method, self.n_terms,
                 _cabi.dev_ptr(o["row"]), _cabi.dev_ptr(o["coef"]), _cabi.dev_ptr(o["status"]),
                 _cabi.dev_ptr(sched["pair_point"]), Q, _cabi.dev_ptr(tmix), self._stream()), "bi_template_mix")
             _cabi.check(self.lib.bi_mixture_partials(
@@ -1274,7 +1275,7 @@ class TemplateUnbinnedEngine(_EngineBase):
         (bench / profiling: the HBM-bound kernel without K1, the template morph and the finalize)."""
         torch = self.torch
         Q = sched["n_pairs"]
-        tmix = self.ws.get("ts_tmix", Q * self.n_template_bins, torch.float64)
+        tmix = self.ws.get("ts_tmix", 4 * Q * self.n_template_bins, torch.float64)
         partial = self.ws.get("ts_partial", sched["n_partials"], torch.float64)
         _cabi.check(self.lib.bi_mixture_partials(
             _cabi.dev_ptr(tmix), self.n_space, _cabi.host_ptr(self.n_bins_i32), self.method,

@@ -320,6 +320,7 @@ int bi_hist_lookup(const double* templates_dev, int64_t n_templates, int32_t n_s
  */
 #define BI_TS_MAX_TERMS 256
 #define BI_TS_GROUP_POINTS 8
+#define BI_MIX_GROUP_POINTS 8      /* points per group of bi_mixture_partials (K5b) */
 int bi_template_prepare_events(int32_t n_space, const int32_t* n_bins_host, const double* edges_host,
                                int32_t method, const double* coords_dev, int64_t ld_coords, int64_t n_events,
                                int32_t* ev_bin_dev, double* ev_frac_dev, int64_t ld_frac, void* stream);
@@ -345,12 +346,17 @@ int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_
  * differs by ~1e-16 relative per event -- inside the 1e-9 * N contract, NOT bit-identical to the other kernels.
  * One lookup per point-event instead of n_terms; with the events of a dataset sorted by bin the template loads are
  * warp-uniform and the kernel streams the prepared events (4 + 8 * n_space bytes each) at HBM speed.
- * Requires finite templates.  tmix_dev: [n_pairs, prod(n_bins)], row q belongs to pair q; groups as in
+ * Requires finite templates.  templates_dev of bi_template_mix: the plain [n_rows, prod(n_bins)] layout.
+ * tmix_dev: [n_pairs, prod(n_bins), pack] (32-byte aligned), row q belongs to pair q, PACKED like K5's templates:
+ * pack = 1 (piecewise), 2 (1-D linear: m[b], m[b + 1]) or 4 (m[b], m[b + 1], m[b + s], m[b + s + 1]); size it as
+ * n_pairs * prod(n_bins) * 4 doubles.  Groups as in
  * bi_template_partials except that the points of a group need NOT share a hypercube cell and that a unit is a PAIR
- * of consecutive superblocks (one per half-warp): unit_offset_dev = prefix sum of ceil(superblocks / 2) per group.
+ * of consecutive superblocks (one per half-warp): unit_offset_dev = prefix sum of ceil(superblocks / 2) per group;
+ * group_points is 1 or BI_MIX_GROUP_POINTS.
  * The lookup uses pre-multiplied corner weights, r = fma chain over corners of V[c] * w_c (this form's own order).
  */
-int bi_template_mix(const double* templates_dev, int64_t row_stride, int64_t bin_stride, int64_t n_bins,
+int bi_template_mix(const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+                    int32_t n_space, const int32_t* n_bins_host, int32_t method,
                     int32_t n_terms, const int32_t* row_dev, const double* coef_dev, const int32_t* status_dev,
                     const int32_t* pair_point_dev, int64_t n_pairs, double* tmix_dev, void* stream);
 int bi_mixture_partials(const double* tmix_dev, int32_t n_space, const int32_t* n_bins_host, int32_t method,
