@@ -519,7 +519,7 @@ __device__ __forceinline__ void bi_mix_load(const int32_t* __restrict__ ev_bin, 
 #define BI_MIX_MINCTAS 3      /* 168 registers: measured best for the grouped instantiations (1: 246 regs, 4: spills) */
 #endif
 template <int NP, int NS>
-__global__ void __launch_bounds__(BI_TS_THREADS, (NP > 1 ? BI_MIX_MINCTAS : 1))
+__global__ void __launch_bounds__(BI_TS_THREADS, (NP > 1 ? BI_MIX_MINCTAS : 5))      // NP = 1: <= 96 registers, 20 warps / SM
 k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins /* doubles per mixture row: bins x pack */,
                    const __grid_constant__ BiTsSpace sp,
                    const int32_t* __restrict__ ev_bin, const double* __restrict__ ev_frac, int64_t ld_frac,
