@@ -968,6 +968,33 @@ class BinnedEngine(_EngineBase):
                 out.cpu().numpy().reshape((S,) + tuple(self.bin_shape)), int(flags.cpu()[0]))
 
 
+def group_pairs(dataset_index, cells, n_cells, group_points):
+    """Host-side grouping of (dataset, point) pairs for the template-space kernels (pure function).
+
+    dataset_index [Q], cells [Q] (hypercube cell of every pair's point, -1 = out of range).  Pairs are sorted (stably) by
+    (dataset, cell) and every run of equal keys is cut into groups of at most group_points pairs; out-of-range pairs are
+    groups of their own.  Returns (order [Q], first [n_groups], count [n_groups]): group g holds the sorted positions
+    first[g] .. first[g] + count[g] - 1, position j being pair order[j]."""
+    dataset_index = np.asarray(dataset_index, dtype=np.int64)
+    cells = np.asarray(cells, dtype=np.int64)
+    Q = len(dataset_index)
+    if Q == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z
+    key = dataset_index * (int(n_cells) + 1) + (cells + 1)
+    order = np.argsort(key, kind='stable')
+    sk = key[order]
+    starts = np.flatnonzero(np.r_[True, sk[1:] != sk[:-1]])
+    ends = np.r_[starts[1:], Q]
+    step = np.where(cells[order[starts]] < 0, 1, max(int(group_points), 1))
+    n_chunks = -(-(ends - starts) // step)
+    run = np.repeat(np.arange(len(starts)), n_chunks)
+    idx_in_run = np.arange(int(n_chunks.sum())) - np.repeat(np.cumsum(n_chunks) - n_chunks, n_chunks)
+    first = starts[run] + idx_in_run * step[run]
+    count = np.minimum(step[run], ends[run] - first)
+    return order, first.astype(np.int64), count.astype(np.int64)
+
+
 class TemplateUnbinnedEngine(_EngineBase):
     """Template-space unbinned likelihood (K1 + K5 + ragged finalize): the per-event pdf values of the anchor
     tensor are looked up on the fly from HBM/L2-resident histogram templates instead of being stored.
@@ -1151,21 +1178,11 @@ class TemplateUnbinnedEngine(_EngineBase):
             raise ValueError("dataset index outside [0, %d)" % self.n_datasets)
         cells = self._cells_for_grouping(zs)
         n_cells = int(np.prod(self.grid.cells_per_dim)) if self.grid.n_dims else 1
-        key = dataset_index * (n_cells + 1) + (cells + 1)
-        order = np.argsort(key, kind='stable')
-        sk = key[order]
-        starts = np.flatnonzero(np.r_[True, sk[1:] != sk[:-1]]) if P else np.zeros(0, dtype=np.int64)
-        ends = np.r_[starts[1:], P] if P else starts
         np_max = (_cabi.MIX_GROUP_POINTS if self.mode == 'mixture' else _cabi.TS_GROUP_POINTS) if P > 1 else 1
-        step = np.where(cells[order[starts]] < 0, 1, np_max) if P else starts
-        n_chunks = -(-(ends - starts) // np.maximum(step, 1))
-        run = np.repeat(np.arange(len(starts)), n_chunks)
-        idx_in_run = np.arange(int(n_chunks.sum())) - np.repeat(np.cumsum(n_chunks) - n_chunks, n_chunks)
-        first = starts[run] + idx_in_run * step[run]
-        count = np.minimum(step[run], ends[run] - first)
+        order, first, count = group_pairs(dataset_index, cells, n_cells, np_max)
         if P and count.max() == 1:
             np_max = 1
-        sched = self._upload_schedule(order, dataset_index[order], first.astype(np.int64), count.astype(np.int64), np_max)
+        sched = self._upload_schedule(order, dataset_index[order], first, count, np_max)
         return sched, order
 
     def single_schedule(self, zs, dataset=0):

@@ -214,3 +214,32 @@ def test_plan_points_covers_every_in_range_point_exactly_once():
     assert len(engine.plan_points(grid, zs, 2, n_super, 'grouped').stream_points) == 0
     # too many sources for the grouped kernel -> everything streams
     assert len(engine.plan_points(grid, zs, 9, n_super).work) == 0
+
+
+def test_group_pairs_invariants():
+    """Host-side schedule of the template-space kernels: every pair in exactly one group, groups never larger than
+    allowed, a group never mixes datasets or hypercube cells, out-of-range pairs stay alone."""
+    from blueice_b200.engine import group_pairs
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        Q = int(rng.integers(0, 400))
+        n_cells = int(rng.integers(1, 20))
+        dataset = rng.integers(0, 7, size=Q)
+        cells = rng.integers(-1, n_cells, size=Q)
+        gp = int(rng.choice([1, 4, 8]))
+        order, first, count = group_pairs(dataset, cells, n_cells, gp)
+        assert sorted(order.tolist()) == list(range(Q))
+        assert int(count.sum()) == Q and (Q == 0 or (count.min() >= 1 and count.max() <= gp))
+        covered = np.zeros(Q, dtype=int)
+        for f, c in zip(first, count):
+            members = order[f:f + c]
+            covered[members] += 1
+            assert len(set(dataset[members].tolist())) == 1 and len(set(cells[members].tolist())) == 1
+            if cells[members[0]] < 0:
+                assert c == 1
+        assert np.all(covered == 1)
+        # groups are laid out back to back in sorted order
+        assert Q == 0 or (first[0] == 0 and np.array_equal(first[1:], np.cumsum(count)[:-1]))
+    # stable: pairs of one (dataset, cell) keep their relative order
+    order, first, count = group_pairs([1, 0, 1, 0, 1], [2, 2, 2, 2, 2], 5, 8)
+    assert order.tolist() == [1, 3, 0, 2, 4] and first.tolist() == [0, 2] and count.tolist() == [2, 3]
