@@ -243,3 +243,41 @@ def test_group_pairs_invariants():
     # stable: pairs of one (dataset, cell) keep their relative order
     order, first, count = group_pairs([1, 0, 1, 0, 1], [2, 2, 2, 2, 2], 5, 8)
     assert order.tolist() == [1, 3, 0, 2, 4] and first.tolist() == [0, 2] and count.tolist() == [2, 3]
+
+
+def test_toy_tables_and_means_follow_model_simulate():
+    """Host side of on-device toy generation: the cdf tables are Histdd.get_random's (cumsum of the flattened pmf, last
+    entry 1) and the Poisson means are Model.simulate's (model.py:80-84: rate multipliers, livetime, fraction in range)."""
+    from blueice_b200 import HistogramPdfSource, Model
+    from blueice_b200 import toys
+    from blueice_b200.hist import Histdd
+    from blueice_b200.test_helpers import conf_for_test
+
+    edges = [np.linspace(0, 10, 6), np.linspace(-1, 1, 4)]
+
+    class Flat(HistogramPdfSource):
+        def build_histogram(self):
+            dens = np.arange(1., 16.).reshape(5, 3) * self.config.get('tilt', 1.0)
+            vol = np.outer(np.diff(edges[0]), np.diff(edges[1]))
+            dens = dens / np.sum(dens * vol)
+            self._pdf_histogram = Histdd.from_histogram(dens, edges, axis_names=['a', 'b'])
+            self._bin_volumes = self._pdf_histogram.bin_volumes()
+            self._n_events_histogram = Histdd.from_histogram(np.full(dens.shape, np.inf), edges, ['a', 'b'])
+
+    config = dict(sources=[dict(name='s0', events_per_day=30.), dict(name='s1', events_per_day=5., tilt=2.0)],
+                  default_source_class=Flat, analysis_space=[['a', edges[0]], ['b', edges[1]]], livetime_days=2.,
+                  force_recalculation=True, never_save_to_cache=True)
+    model = Model(config)
+    got_edges, cdf = toys.source_tables(model)
+    assert all(np.array_equal(a, b) for a, b in zip(got_edges, edges)) and cdf.shape == (2, 15)
+    assert np.all(np.diff(cdf, axis=1) > 0) and np.allclose(cdf[:, -1], 1.0)
+    pmf0 = (model.sources[0]._pdf_histogram.histogram * model.sources[0]._bin_volumes).ravel()
+    assert np.array_equal(cdf[0], np.cumsum(pmf0) / np.cumsum(pmf0)[-1])
+    mus = toys.toy_means(model, rate_multipliers={'s1': 3.0}, livetime_days=1.0)
+    expect = [model.expected_events(model.sources[0]) * 1 / model.sources[0].fraction_in_range * 0.5,
+              model.expected_events(model.sources[1]) * 3.0 / model.sources[1].fraction_in_range * 0.5]
+    assert np.array_equal(mus, np.asarray(expect))
+    # sources that are not stock histogram templates cannot be generated on the device
+    gauss = Model(conf_for_test(n_sources=1))
+    with pytest.raises(NotImplementedError):
+        toys.source_tables(gauss)
