@@ -198,7 +198,7 @@ def _lockstep_bfgs(minus_ll, x0, lo, hi, max_iter=60, gtol=1e-3, ftol=1e-10, fd_
         ok = (~fresh[act]) & (sy > 1e-10 * np.sqrt(np.einsum('ij,ij->i', yv, yv) * np.einsum('ij,ij->i', sv, sv)))
         rho = np.where(ok, 1.0 / np.where(ok, sy, 1.0), 0.0)
         V = eye[None] - rho[:, None, None] * sv[:, :, None] * yv[:, None, :]
-        Hn = np.einsum('aij,ajk,alk->ail', V, H[act], V) + rho[:, None, None] * sv[:, :, None] * sv[:, None, :]
+        Hn = np.matmul(np.matmul(V, H[act]), np.transpose(V, (0, 2, 1))) + rho[:, None, None] * sv[:, :, None] * sv[:, None, :]
         Ha = np.where(ok[:, None, None], Hn, H[act])
         scale = np.where(np.isnan(curv), np.nanmedian(np.where(np.isnan(curv), np.nan, 1.0 / curv), axis=1, keepdims=True),
                          1.0 / curv)
@@ -208,9 +208,9 @@ def _lockstep_bfgs(minus_ll, x0, lo, hi, max_iter=60, gtol=1e-3, ftol=1e-10, fd_
         # ---- projected direction: parameters pinned at a bound by the gradient do not move
         pinned = ((xa <= lo) & (g > 0)) | ((xa >= hi) & (g < 0))
         gp = np.where(pinned, 0.0, g)
-        d = np.where(pinned, 0.0, -np.einsum('aij,aj->ai', Ha, gp))
+        d = np.where(pinned, 0.0, -np.matmul(Ha, gp[:, :, None])[:, :, 0])
         uphill = np.einsum('ij,ij->i', d, gp) >= 0
-        d = np.where(uphill[:, None], np.where(pinned, 0.0, -np.einsum('aij,aj->ai', H0, gp)), d)
+        d = np.where(uphill[:, None], np.where(pinned, 0.0, -scale * gp), d)
         Ha = np.where(uphill[:, None, None], H0, Ha)
         H[act] = Ha
         # ---- trial steps, all in one batch
