@@ -121,6 +121,7 @@ PLAN_MAX_CELLS = 16384
 TS_MAX_TERMS = 256
 TS_GROUP_POINTS = 8
 MIX_GROUP_POINTS = 8
+MIX_GROUP_POINTS_WIDE = 16
 POINT_OUT_OF_RANGE = 1
 POINT_UNPHYSICAL = 2
 LOOKUP_LINEAR = 0

@@ -15,6 +15,8 @@
 // Work: a pair group = up to BI_TS_GROUP_POINTS points evaluated on one dataset that share their row list (same
 // hypercube cell): the template values of an event are gathered once and contracted with every point of the group.
 // A unit = (pair group, superblock of 512 events); one warp per unit, lane = event.
+#include <stdlib.h>
+
 #include "bi_space.cuh"
 
 #ifndef BI_TS_BATCH
@@ -626,6 +628,360 @@ k_mixture_partials(const double* __restrict__ tmix, int64_t n_bins /* doubles pe
 }
 
 // ---------------------------------------------------------------------------------------------
+// K5b on the FP64 tensor pipe: groups of up to 8 * MT points (the finite-difference batch of a minimiser step, a scan).
+// With the events sorted by bin, the 8 events of an octet almost always share their low-corner bin, and the lookup of
+// 8 points x 8 events is ONE 8x8x4 contraction over the lookup corners:
+//     f[q, i] = sum_c Tmix_q[bin, c] * w_c(x_i)       A = 8 points x 4 corners (one 8-byte load per lane from the packed
+//                                                     mixture rows), B = 4 corner weights x 8 events, D = densities
+// DMMA accumulates as the fma chain of bi_mix_eval (fma(v0, w0, +0) = fl(v0 * w0), then corners ascending; proved on the
+// device, profiles/microbench/dmma_probe_b200.log), and its D fragment hands lane (g, t) the events 8n + 2t, 8n + 2t + 1
+// of point g -- the canonical class layout -- so the product tree runs inside the lane and every result is BIT-IDENTICAL
+// to k_mixture_partials<1 | 8, NS>.  An octet whose events straddle a bin edge takes 8 contractions (one per event's
+// bin, its own column kept).  Per 32 events x 8 points: 4 loads + 4 DMMA per corner quartet instead of 16 256-bit
+// gathers per lane; the prepared events are loaded coalesced, 4 groups (2.5 kB per warp) ahead, and handed to the
+// fragment lanes by shuffles (shared by the MT m-tiles of the warp).  A chunk of 4 groups whose octets all share
+// their bins (the common case) runs branch-free with the A fragments of the next group in flight.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bi_ts_dmma(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+#define BI_MIXM_CHUNK 4        /* groups (of 32 events) per prefetch chunk */
+#ifndef BI_MIXM_MINCTAS
+#define BI_MIXM_MINCTAS 4
+#endif
+#ifndef BI_MIXM_MINCTAS2
+#define BI_MIXM_MINCTAS2 3
+#endif
+
+template <int NS>
+struct BiMixm {
+    static constexpr int NY = NS > 0 ? NS : 1;
+    static constexpr int PACK = NS == 0 ? 1 : (NS == 1 ? 2 : 4);      // doubles per bin of a packed mixture row
+    static constexpr int KS = NS <= 2 ? 1 : (1 << NS) / 4;            // corner quartets = DMMA k-steps
+    static constexpr int CORNERS = 1 << NS;                           // k >= CORNERS of the only quartet: zero padding
+};
+
+template <int NS>
+struct BiMixChunk {
+    int bin[BI_MIXM_CHUNK];
+    double y[BiMixm<NS>::NY][BI_MIXM_CHUNK];
+};
+
+// lane's events c0 + 32 i + lane of the superblock (events >= n_ev: bin 0, fractions 0; their densities count as 1)
+template <int NS>
+__device__ __forceinline__ void bi_mixm_load(const int32_t* __restrict__ ev_bin, const double* __restrict__ ev_frac,
+                                             int64_t ld_frac, int64_t ev_begin, int c0, int n_ev, int lane, BiMixChunk<NS>& ch) {
+#pragma unroll
+    for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
+        const int e = c0 + 32 * i + lane;
+        const bool ok = e < n_ev;
+        ch.bin[i] = ok ? __ldg(ev_bin + ev_begin + e) : 0;
+#pragma unroll
+        for (int d = 0; d < NS; ++d) ch.y[d][i] = ok ? __ldg(ev_frac + (int64_t)d * ld_frac + ev_begin + e) : 0.0;
+        if (NS == 0) ch.y[0][i] = 0.0;
+    }
+}
+
+// (class, group) fallback: the canonical tree over log(p_i) of the class's 8 events (noinline: out of the hot loop)
+static __device__ __noinline__ double bi_mixm_slow(double p00, double p01, double p10, double p11, double p20, double p21,
+                                                   double p30, double p31, double outlier) {
+    const double l0 = __dadd_rn(log(bi_fix_density(p00, outlier)), log(bi_fix_density(p01, outlier)));
+    const double l1 = __dadd_rn(log(bi_fix_density(p10, outlier)), log(bi_fix_density(p11, outlier)));
+    const double l2 = __dadd_rn(log(bi_fix_density(p20, outlier)), log(bi_fix_density(p21, outlier)));
+    const double l3 = __dadd_rn(log(bi_fix_density(p30, outlier)), log(bi_fix_density(p31, outlier)));
+    return __dadd_rn(__dadd_rn(l0, l1), __dadd_rn(l2, l3));
+}
+
+// B fragments of one group: weight of this lane's corner (of every quartet) at event 8n + g, w = ((1 * x_0) * x_1) ...
+template <int NS>
+__device__ __forceinline__ void bi_mixm_weights(const double (&y)[BiMixm<NS>::NY], int g, int t, bool a_zero,
+                                                double (&w)[4][BiMixm<NS>::KS]) {
+    constexpr int KS = BiMixm<NS>::KS;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        double x[BiMixm<NS>::NY];
+#pragma unroll
+        for (int dd = 0; dd < NS; ++dd) x[dd] = __shfl_sync(BI_FULL_MASK, y[dd], 8 * n + g);
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            const int c = (NS <= 1) ? (t & 1) : 4 * j + t;
+            double v = 1.0;
+#pragma unroll
+            for (int dd = 0; dd < NS; ++dd) {
+                const double f = ((c >> (NS - 1 - dd)) & 1) ? x[dd] : __dsub_rn(1.0, x[dd]);
+                v = dd == 0 ? f : __dmul_rn(v, f);
+            }
+            w[n][j] = a_zero ? 0.0 : v;
+        }
+    }
+}
+
+// densities of this lane's class -> canonical product tree -> (M, E) of the superblock; slow path when out of range
+template <bool FULL>
+__device__ __forceinline__ void bi_mixm_tree(double (&d)[4][2], int n_left, int t, bool live_me, double outlier,
+                                             double& M, int& E, double& L, bool& any_slow) {
+    if (!FULL) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const int e = 8 * n + 2 * t;
+            if (e >= n_left) d[n][0] = 1.0;                           // events >= N count as p = 1
+            if (e + 1 >= n_left) d[n][1] = 1.0;
+        }
+    }
+    unsigned tmax = (unsigned)(__double2hiint(d[0][0]) - BI_RANGE_LO);
+    tmax = max(tmax, (unsigned)(__double2hiint(d[0][1]) - BI_RANGE_LO));
+#pragma unroll
+    for (int n = 1; n < 4; ++n) {
+        tmax = max(tmax, (unsigned)(__double2hiint(d[n][0]) - BI_RANGE_LO));
+        tmax = max(tmax, (unsigned)(__double2hiint(d[n][1]) - BI_RANGE_LO));
+    }
+    const double q0 = __dmul_rn(__dmul_rn(d[0][0], d[0][1]), __dmul_rn(d[1][0], d[1][1]));
+    const double q1 = __dmul_rn(__dmul_rn(d[2][0], d[2][1]), __dmul_rn(d[3][0], d[3][1]));
+    double m;
+    int e;
+    bi_split(__dmul_rn(q0, q1), &m, &e);
+    const bool bad = tmax >= BI_RANGE_SPAN;
+    if (bad) { m = 1.0; e = 0; }
+    M = __dmul_rn(M, m);
+    E += e;
+    if (bad && live_me) {                                             // rare: the class's 8 events through the log tree
+        L = __dadd_rn(L, bi_mixm_slow(d[0][0], d[0][1], d[1][0], d[1][1], d[2][0], d[2][1], d[3][0], d[3][1], outlier));
+        any_slow = true;
+    }
+}
+
+// A fragments of a group whose four octets each share one bin: element t of the packed bin of point slot g
+template <int NS, int MT>
+__device__ __forceinline__ void bi_mixm_load_a(const double* const (&Vq)[MT], bool a_zero, const BiTsSpace& sp, int bin,
+                                               double (&a)[MT][4][BiMixm<NS>::KS]) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        const int64_t e = (int64_t)__shfl_sync(BI_FULL_MASK, bin, 8 * n) * BiMixm<NS>::PACK;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int j = 0; j < BiMixm<NS>::KS; ++j) a[mt][n][j] = a_zero ? 0.0 : __ldg(Vq[mt] + e + sp.corner_off[4 * j]);
+    }
+}
+
+// one full group with shared bins per octet: branch-free up to the (rare) slow path
+template <int NS, int MT>
+__device__ __forceinline__ void bi_mixm_group_fast(const double (&a)[MT][4][BiMixm<NS>::KS], const double (&y)[BiMixm<NS>::NY],
+                                                   int g, int t, bool a_zero, const bool (&live_me)[MT], double outlier,
+                                                   double (&M)[MT], int (&E)[MT], double (&L)[MT], bool& any_slow) {
+    double w[4][BiMixm<NS>::KS];
+    bi_mixm_weights<NS>(y, g, t, a_zero, w);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        double d[4][2];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            d[n][0] = d[n][1] = 0.0;
+#pragma unroll
+            for (int j = 0; j < BiMixm<NS>::KS; ++j) bi_ts_dmma(d[n][0], d[n][1], a[mt][n][j], w[n][j]);
+        }
+        bi_mixm_tree<true>(d, 32, t, live_me[mt], outlier, M[mt], E[mt], L[mt], any_slow);
+    }
+}
+
+// any group: octets that straddle a bin edge take one contraction per event; events >= n_left count as p = 1
+template <int NS, int MT>
+__device__ __forceinline__ void bi_mixm_group_any(const double* const (&Vq)[MT], const BiTsSpace& sp, int bin,
+                                                  const double (&y)[BiMixm<NS>::NY], int n_left, int g, int t, bool a_zero,
+                                                  const bool (&live_me)[MT], double outlier, double (&M)[MT], int (&E)[MT],
+                                                  double (&L)[MT], bool& any_slow) {
+    constexpr int KS = BiMixm<NS>::KS, PACK = BiMixm<NS>::PACK;
+    const int first = __shfl_sync(BI_FULL_MASK, bin, threadIdx.x & 24);
+    const unsigned neq = __ballot_sync(BI_FULL_MASK, bin != first);   // octets whose 8 events do not share one bin
+    double w[4][KS];
+    bi_mixm_weights<NS>(y, g, t, a_zero, w);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        double d[4][2];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            d[n][0] = d[n][1] = 0.0;
+            if (((neq >> (8 * n)) & 0xffu) == 0) {                    // warp-uniform
+                const int64_t e = (int64_t)__shfl_sync(BI_FULL_MASK, bin, 8 * n) * PACK;
+#pragma unroll
+                for (int j = 0; j < KS; ++j)
+                    bi_ts_dmma(d[n][0], d[n][1], a_zero ? 0.0 : __ldg(Vq[mt] + e + sp.corner_off[4 * j]), w[n][j]);
+            } else if constexpr (KS <= 2) {                           // event 8n + jj: its own bin, its own column
+                double a8[8][KS];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {                      // the eight loads in flight together
+                    const int64_t e = (int64_t)__shfl_sync(BI_FULL_MASK, bin, 8 * n + jj) * PACK;
+#pragma unroll
+                    for (int j = 0; j < KS; ++j) a8[jj][j] = a_zero ? 0.0 : __ldg(Vq[mt] + e + sp.corner_off[4 * j]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < KS; ++j) bi_ts_dmma(t0, t1, a8[jj][j], w[n][j]);
+                    if (2 * t == jj) d[n][0] = t0;
+                    if (2 * t + 1 == jj) d[n][1] = t1;
+                }
+            } else {
+#pragma unroll 1
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int64_t e = (int64_t)__shfl_sync(BI_FULL_MASK, bin, 8 * n + jj) * PACK;
+                    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < KS; ++j)
+                        bi_ts_dmma(t0, t1, a_zero ? 0.0 : __ldg(Vq[mt] + e + sp.corner_off[4 * j]), w[n][j]);
+                    if (2 * t == jj) d[n][0] = t0;
+                    if (2 * t + 1 == jj) d[n][1] = t1;
+                }
+            }
+        }
+        if (n_left >= 32) bi_mixm_tree<true>(d, 32, t, live_me[mt], outlier, M[mt], E[mt], L[mt], any_slow);
+        else bi_mixm_tree<false>(d, n_left, t, live_me[mt], outlier, M[mt], E[mt], L[mt], any_slow);
+    }
+}
+
+// unit = (pair group, pair of consecutive superblocks), as k_mixture_partials: the warp walks the two superblocks in turn;
+// lane (g, t) owns class t of the point slots g, g + 8, ... of the group
+template <int NS, int MT>
+__global__ void __launch_bounds__(BI_TS_THREADS, (MT == 1 ? BI_MIXM_MINCTAS : BI_MIXM_MINCTAS2))
+k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* doubles per mixture row: bins x pack */,
+                       const __grid_constant__ BiTsSpace sp,
+                       const int32_t* __restrict__ ev_bin, const double* __restrict__ ev_frac, int64_t ld_frac,
+                       const int64_t* __restrict__ dataset_offset, const int32_t* __restrict__ status,
+                       int64_t n_groups, const BiTsGroup* __restrict__ groups, const int64_t* __restrict__ unit_offset,
+                       const int32_t* __restrict__ unit_group, int64_t n_units,
+                       const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
+                       double outlier, double* __restrict__ partial) {
+    static_assert(NS >= 0 && NS <= 4, "piecewise lookups or linear lookups in 1..4 dimensions");
+    constexpr int NY = BiMixm<NS>::NY, KS = BiMixm<NS>::KS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t n_warps = (int64_t)gridDim.x * BI_TS_WARPS;
+    const bool a_zero = t >= BiMixm<NS>::CORNERS;                     // fewer than 4 lookup corners: zero padding
+
+    for (int64_t u = (int64_t)blockIdx.x * BI_TS_WARPS + warp; u < n_units; u += n_warps) {
+        int64_t gi;
+        if (unit_group) gi = unit_group[u];
+        else {
+            int64_t lo = 0, hi = n_groups;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (unit_offset[mid] <= u) lo = mid; else hi = mid;
+            }
+            gi = lo;
+        }
+        const BiTsGroup gp = groups[gi];
+        const int np = gp.count < 8 * MT ? gp.count : 8 * MT;
+        int64_t pair[MT];
+        bool live_me[MT];
+        const double* Vq[MT];
+        bool any_live = false;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int slot = 8 * mt + g;
+            pair[mt] = gp.first + (slot < np ? slot : np - 1);       // slots >= np repeat the last pair; results unused
+            live_me[mt] = slot < np && status[pair_point ? pair_point[pair[mt]] : pair[mt]] == 0;
+            any_live |= live_me[mt];
+            Vq[mt] = tmix + pair[mt] * n_bins + (a_zero ? 0 : t);
+        }
+        if (!__any_sync(BI_FULL_MASK, any_live)) continue;
+        const int64_t ds_begin = dataset_offset[gp.dataset], ds_end = dataset_offset[gp.dataset + 1];
+
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int64_t sb = 2 * (u - unit_offset[gi]) + h;
+            const int64_t ev_begin = ds_begin + sb * BI_SUPERBLOCK;
+            const int64_t left = ds_end - ev_begin;
+            if (left <= 0) break;
+            const int n_ev = left < BI_SUPERBLOCK ? (int)left : BI_SUPERBLOCK;
+            double M[MT], L[MT];
+            int E[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) { M[mt] = 1.0; L[mt] = 0.0; E[mt] = 0; }
+            bool any_slow = false;
+            BiMixChunk<NS> cur, nxt;
+            bi_mixm_load<NS>(ev_bin, ev_frac, ld_frac, ev_begin, 0, n_ev, lane, cur);
+#pragma unroll 1
+            for (int c0 = 0; c0 < n_ev; c0 += 32 * BI_MIXM_CHUNK) {
+                bi_mixm_load<NS>(ev_bin, ev_frac, ld_frac, ev_begin, c0 + 32 * BI_MIXM_CHUNK, n_ev, lane, nxt);
+                bool ne = false;
+#pragma unroll
+                for (int i = 0; i < BI_MIXM_CHUNK; ++i)
+                    ne |= cur.bin[i] != __shfl_sync(BI_FULL_MASK, cur.bin[i], lane & 24);
+                if (n_ev - c0 >= 32 * BI_MIXM_CHUNK && !__any_sync(BI_FULL_MASK, ne)) {
+                    // every octet of the chunk shares its bin: branch-free, the next group's A fragments in flight
+                    double a[MT][4][KS], an[MT][4][KS];
+                    bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, cur.bin[0], a);
+#pragma unroll
+                    for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
+                        if (i + 1 < BI_MIXM_CHUNK) bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, cur.bin[i + 1], an);
+                        double yy[NY];
+#pragma unroll
+                        for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][i];
+                        bi_mixm_group_fast<NS, MT>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
+                        if (i + 1 < BI_MIXM_CHUNK) {
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                                for (int n = 0; n < 4; ++n)
+#pragma unroll
+                                    for (int j = 0; j < KS; ++j) a[mt][n][j] = an[mt][n][j];
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
+                        const int e0 = c0 + 32 * i;
+                        if (e0 >= n_ev) break;
+                        int bin_i = cur.bin[0];
+                        double yy[NY];
+#pragma unroll
+                        for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][0];
+#pragma unroll
+                        for (int k = 1; k < BI_MIXM_CHUNK; ++k) {
+                            if (i == k) {
+                                bin_i = cur.bin[k];
+#pragma unroll
+                                for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][k];
+                            }
+                        }
+                        const bool shared = !__any_sync(BI_FULL_MASK, bin_i != __shfl_sync(BI_FULL_MASK, bin_i, lane & 24));
+                        if (shared && n_ev - e0 >= 32) {                  // the group's octets share their bins
+                            double a[MT][4][KS];
+                            bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, bin_i, a);
+                            bi_mixm_group_fast<NS, MT>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
+                        } else {
+                            bi_mixm_group_any<NS, MT>(Vq, sp, bin_i, yy, n_ev - e0, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
+                        }
+                    }
+                }
+                cur = nxt;
+            }
+            // ---- close the superblock: M = (M_0 * M_1) * (M_2 * M_3), E = sum, L = (L_0 + L_1) + (L_2 + L_3)
+            const bool slow = __any_sync(BI_FULL_MASK, any_slow);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                double m = M[mt];
+                m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 1));
+                m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 2));
+                int e = E[mt];
+                e += __shfl_xor_sync(BI_FULL_MASK, e, 1);
+                e += __shfl_xor_sync(BI_FULL_MASK, e, 2);
+                double r = bi_block_log(m, e);
+                if (slow) {
+                    double l = L[mt];
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 2));
+                    r = __dadd_rn(r, l);
+                }
+                if (t == 0 && live_me[mt]) partial[pair_partial_offset[pair[mt]] + sb] = r;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // ragged finalize: logl[q] = -musum[point] + total(partials of pair q), the canonical total of
 // k_unbinned_finalize (256 strided lanes, xor butterfly per 32, pairwise over the 8 warp totals) by ONE warp
 // ---------------------------------------------------------------------------------------------
@@ -897,6 +1253,42 @@ static int bi_mix_launch(const double* tmix, int64_t n_bins, const BiTsSpace& sp
     return BI_OK;
 }
 
+template <int NS, int MT>
+static int bi_mixm_launch(const double* tmix, int64_t n_bins, const BiTsSpace& sp, const int32_t* ev_bin,
+                          const double* ev_frac, int64_t ld_frac, const int64_t* dataset_offset, const int32_t* status,
+                          int64_t n_groups, const BiTsGroup* groups, const int64_t* unit_offset, const int32_t* unit_group,
+                          int64_t n_units, const int32_t* pair_point, const int64_t* pair_partial_offset, double outlier,
+                          double* partial, cudaStream_t st) {
+    static int resident = 0;
+    if (!resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        BI_CUDA_CHECK(cudaGetDevice(&dev));
+        BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mixture_partials_mma<NS, MT>, BI_TS_THREADS, 0));
+        BI_REQUIRE(per_sm >= 1, "k_mixture_partials_mma<%d,%d> does not fit on this device", NS, MT);
+        resident = sms * per_sm;
+    }
+    int64_t blocks = resident;
+    const int64_t needed = (n_units + BI_TS_WARPS - 1) / BI_TS_WARPS;
+    if (blocks > needed) blocks = needed;
+    k_mixture_partials_mma<NS, MT><<<(unsigned)blocks, BI_TS_THREADS, 0, st>>>(
+        tmix, n_bins, sp, ev_bin, ev_frac, ld_frac, dataset_offset, status, n_groups, groups, unit_offset, unit_group,
+        n_units, pair_point, pair_partial_offset, outlier, partial);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}
+
+// grouped linear lookups run on the tensor-pipe kernel (bit-identical results); BI_MIX_MMA=0 in the environment keeps
+// the gather kernel for A/B measurements
+static bool bi_mix_use_mma() {
+    static int use = -1;
+    if (use < 0) {
+        const char* v = getenv("BI_MIX_MMA");
+        use = (v && v[0] == '0') ? 0 : 1;
+    }
+    return use != 0;
+}
+
 extern "C" int bi_mixture_partials(const double* tmix_dev, int32_t n_space, const int32_t* n_bins_host, int32_t method,
                                    const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
                                    const int64_t* dataset_offset_dev, const int32_t* status_dev,
@@ -908,7 +1300,9 @@ extern "C" int bi_mixture_partials(const double* tmix_dev, int32_t n_space, cons
     int rc = bi_fill_space(&space, n_space, n_bins_host);
     if (rc != BI_OK) return rc;
     BI_REQUIRE(method == BI_LOOKUP_LINEAR || method == BI_LOOKUP_PIECEWISE, "unknown lookup method %d", method);
-    BI_REQUIRE(group_points == 1 || group_points == BI_MIX_GROUP_POINTS, "group_points must be 1 or %d", BI_MIX_GROUP_POINTS);
+    BI_REQUIRE(group_points == 1 || group_points == BI_MIX_GROUP_POINTS ||
+                   (group_points == BI_MIX_GROUP_POINTS_WIDE && bi_mix_use_mma()),
+               "group_points must be 1, %d or %d", BI_MIX_GROUP_POINTS, BI_MIX_GROUP_POINTS_WIDE);
     BI_REQUIRE(n_groups >= 0 && n_units >= 0, "negative size");
     if (n_groups == 0 || n_units == 0) return BI_OK;
     BI_REQUIRE(tmix_dev && ev_bin_dev && dataset_offset_dev && status_dev && groups_dev && unit_offset_dev &&
@@ -936,6 +1330,19 @@ extern "C" int bi_mixture_partials(const double* tmix_dev, int32_t n_space, cons
                                        dataset_offset_dev, status_dev, n_groups, groups, unit_offset_dev,              \
                                        unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,               \
                                        outlier_likelihood, partial_dev, st);
+#define BI_MIXM_CASE(NSV)                                                                                              \
+    if (group_points > 1 && ns == NSV && bi_mix_use_mma()) {                                                           \
+        if (group_points == BI_MIX_GROUP_POINTS)                                                                       \
+            return bi_mixm_launch<NSV, 1>(tmix_dev, row_doubles, sp, ev_bin_dev, ev_frac_dev, ld_frac,                 \
+                                          dataset_offset_dev, status_dev, n_groups, groups, unit_offset_dev,           \
+                                          unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,            \
+                                          outlier_likelihood, partial_dev, st);                                        \
+        return bi_mixm_launch<NSV, 2>(tmix_dev, row_doubles, sp, ev_bin_dev, ev_frac_dev, ld_frac, dataset_offset_dev, \
+                                      status_dev, n_groups, groups, unit_offset_dev, unit_group_dev, n_units,          \
+                                      pair_point_dev, pair_partial_offset_dev, outlier_likelihood, partial_dev, st);   \
+    }
+    BI_MIXM_CASE(0) BI_MIXM_CASE(1) BI_MIXM_CASE(2) BI_MIXM_CASE(3) BI_MIXM_CASE(4)
+#undef BI_MIXM_CASE
     BI_MIX_CASE(1, 0) BI_MIX_CASE(1, 1) BI_MIX_CASE(1, 2) BI_MIX_CASE(1, 3) BI_MIX_CASE(1, 4)
     BI_MIX_CASE(BI_MIX_GROUP_POINTS, 0) BI_MIX_CASE(BI_MIX_GROUP_POINTS, 1) BI_MIX_CASE(BI_MIX_GROUP_POINTS, 2)
     BI_MIX_CASE(BI_MIX_GROUP_POINTS, 3) BI_MIX_CASE(BI_MIX_GROUP_POINTS, 4)

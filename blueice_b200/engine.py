@@ -968,6 +968,9 @@ class BinnedEngine(_EngineBase):
                 out.cpu().numpy().reshape((S,) + tuple(self.bin_shape)), int(flags.cpu()[0]))
 
 
+_MIX_WIDE_MIN_SUPERBLOCKS = 16384       # 8.4e6 events (168 MB of prepared 2-D events): wide K5b groups from here on
+
+
 def group_pairs(dataset_index, cells, n_cells, group_points):
     """Host-side grouping of (dataset, point) pairs for the template-space kernels (pure function).
 
@@ -1178,10 +1181,23 @@ class TemplateUnbinnedEngine(_EngineBase):
             raise ValueError("dataset index outside [0, %d)" % self.n_datasets)
         cells = self._cells_for_grouping(zs)
         n_cells = int(np.prod(self.grid.cells_per_dim)) if self.grid.n_dims else 1
-        np_max = (_cabi.MIX_GROUP_POINTS if self.mode == 'mixture' else _cabi.TS_GROUP_POINTS) if P > 1 else 1
+        if P <= 1:
+            np_max = 1
+        elif self.mode != 'mixture':
+            np_max = _cabi.TS_GROUP_POINTS
+        elif (P > _cabi.MIX_GROUP_POINTS and os.environ.get('BI_MIX_MMA') != '0'
+              and int(self.n_super_host[dataset_index].min()) >= getattr(self, 'mix_wide_min_superblocks',
+                                                                          _MIX_WIDE_MIN_SUPERBLOCKS)):
+            # two 8-point m-tiles per warp: one pass over the events per 16 points (datasets that outgrow the L2 and
+            # still fill the device with half as many units)
+            np_max = _cabi.MIX_GROUP_POINTS_WIDE
+        else:
+            np_max = _cabi.MIX_GROUP_POINTS
         order, first, count = group_pairs(dataset_index, cells, n_cells, np_max)
         if P and count.max() == 1:
             np_max = 1
+        elif P and self.mode == 'mixture' and count.max() <= _cabi.MIX_GROUP_POINTS:
+            np_max = _cabi.MIX_GROUP_POINTS
         sched = self._upload_schedule(order, dataset_index[order], first, count, np_max)
         return sched, order
 

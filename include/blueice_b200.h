@@ -321,6 +321,7 @@ int bi_hist_lookup(const double* templates_dev, int64_t n_templates, int32_t n_s
 #define BI_TS_MAX_TERMS 256
 #define BI_TS_GROUP_POINTS 8
 #define BI_MIX_GROUP_POINTS 8      /* points per group of bi_mixture_partials (K5b) */
+#define BI_MIX_GROUP_POINTS_WIDE 16 /* two 8-point m-tiles per warp (tensor-pipe kernel only) */
 int bi_template_prepare_events(int32_t n_space, const int32_t* n_bins_host, const double* edges_host,
                                int32_t method, const double* coords_dev, int64_t ld_coords, int64_t n_events,
                                int32_t* ev_bin_dev, double* ev_frac_dev, int64_t ld_frac, void* stream);
@@ -352,7 +353,10 @@ int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_
  * n_pairs * prod(n_bins) * 4 doubles.  Groups as in
  * bi_template_partials except that the points of a group need NOT share a hypercube cell and that a unit is a PAIR
  * of consecutive superblocks (one per half-warp): unit_offset_dev = prefix sum of ceil(superblocks / 2) per group;
- * group_points is 1 or BI_MIX_GROUP_POINTS.
+ * group_points is 1, BI_MIX_GROUP_POINTS or BI_MIX_GROUP_POINTS_WIDE.  Groups of more than one point run on the FP64
+ * tensor pipe (k_mixture_partials_mma: the lookup of 8 points x 8 events that share a bin is one DMMA.8x8x4 over the
+ * lookup corners, bit-identical to the single-point kernel); BI_MIX_MMA=0 in the environment keeps the 8-point gather
+ * kernel (A/B measurements; it does not take the wide groups).
  * The lookup uses pre-multiplied corner weights, r = fma chain over corners of V[c] * w_c (this form's own order).
  */
 int bi_template_mix(const double* templates_dev, int64_t row_stride, int64_t bin_stride,

@@ -100,11 +100,13 @@ def main():
         eng, tb, mb, edges = build(6, 4, bin_major, mode)
         coords = draw_events(tb, mb, edges, n_c5, dev, 5)
         eng.set_datasets(coords)
+        if os.environ.get('TPL_WIDE_MIN'):                                # K5b: dataset size from which groups hold 16 points
+            eng.mix_wide_min_superblocks = int(os.environ['TPL_WIDE_MIN'])
         torch.cuda.synchronize()
         rng = np.random.default_rng(5)
         z0 = rng.uniform(-1.9, 1.9, size=(1, 4))
         m0 = rng.uniform(0.8, 1.2, size=(1, 6))
-        for P in (1, 11):
+        for P in tuple(int(v) for v in os.environ.get('TPL_POINTS', '1,11').split(',')):
             zs = np.repeat(z0, P, 0)
             mult = np.repeat(m0, P, 0)
             for j in range(1, P):                                     # forward-difference batch: one parameter each

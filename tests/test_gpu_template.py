@@ -227,6 +227,43 @@ def test_mixture_form_matches_exact_form_and_oracle(method, n_events):
     assert np.array_equal(-musum[ok] + logsum[ok], got[ok])
 
 
+@pytest.mark.parametrize("n_space", [1, 2, 3, 4])
+@pytest.mark.parametrize("n_events", [40, 1000, 30000])
+def test_grouped_mixture_kernel_equals_single_point_kernel_bitwise(n_space, n_events):
+    """Groups of up to 8 points run on the FP64 tensor pipe (k_mixture_partials_mma: one 8 x 8 x 4 contraction per octet
+    of events that share a bin, eight when they straddle a bin edge); a single point runs on the gather kernel.  Same
+    bits, for few events per bin (mostly straddling octets), many events per bin (mostly shared bins), empty bins
+    (p = 0 -> outlier path) and several ragged datasets."""
+    from blueice_b200.engine import MorphGrid, TemplateUnbinnedEngine
+    from oracle.pipeline import UnbinnedOracle
+    rng = np.random.default_rng(10 * n_space + 1)
+    axes = [np.array([-1., 0., 2.])]
+    n_bins = (23, 9, 5, 3)[:n_space]
+    edges = [np.linspace(0., 1. + d, n + 1) for d, n in enumerate(n_bins)]
+    templates = rng.uniform(0.2, 1.5, size=(3, 2) + n_bins)
+    templates[:, :, :3] = 0.0                                           # a dead region in every template
+    mus = rng.uniform(50., 100., size=(3, 2))
+    coords = np.vstack([rng.uniform(-0.1, 1.1 + d, n_events) for d in range(n_space)])
+    offsets = np.array([0, n_events // 3 + 1, n_events // 3 + 1, n_events])
+    grid = MorphGrid(axes)
+    tm = TemplateUnbinnedEngine(grid, mus, templates.reshape((6,) + n_bins), edges, mode='mixture')
+    tm.mix_wide_min_superblocks = 0                                     # groups of 16 whatever the dataset size
+    tm.set_datasets(coords, offsets)
+    zs = rng.uniform(-1., 2., size=(29, 1))
+    zs[3] = 2.5                                                         # out of range -> -inf inside a group
+    mult = rng.uniform(0.5, 1.5, size=(29, 2))
+    for t in range(3):
+        got = tm.evaluate(zs, mult, dataset=t)
+        single = np.array([tm.evaluate(zs[i:i + 1], mult[i:i + 1], dataset=t)[0] for i in range(len(zs))])
+        assert np.array_equal(got, single)                              # groups of 16: two 8-point m-tiles per warp
+        assert np.array_equal(tm.evaluate(zs[:7], mult[:7], dataset=t), single[:7])      # one m-tile
+        assert np.isneginf(got[3]) and np.all(np.isfinite(np.delete(got, 3)))
+        if n_events <= 1000:
+            sl = slice(offsets[t], offsets[t + 1])
+            want = UnbinnedOracle(axes, mus).set_data_from_templates(templates, edges, list(coords[:, sl])).batch(zs, mult)
+            assert_close(got, want, sl.stop - sl.start)
+
+
 def test_mixture_form_outlier_semantics_and_datasets():
     """Dead template regions (p = 0 -> outlier_likelihood) and several datasets on one engine."""
     axes, edges, templates, mus = _model(2, 1, (-1., 0., 1.), (20, 20))
