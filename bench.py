@@ -456,7 +456,10 @@ def other_configs(args, rank, world, device):
         bytes_ev = 4 + 8 * eng.n_space                             # prepared event: bin (i32) + fractions
         res5["P%d" % P] = {"device_ms": t_dev * 1e3, "e2e_ms": t_e2e * 1e3, "point_events_per_s_device": P * N / t_dev,
                            "point_events_per_s_e2e": P * N / t_e2e, "finite": bool(np.all(np.isfinite(r))),
-                           "roofline": {"kernel": "k_mixture_partials<%d,2>" % sched["group_points"], "bound": "hbm",
+                           "roofline": {"kernel": ("k_mixture_partials<1,2>" if sched["group_points"] == 1 else
+                                                   "k_mixture_partials_mma<2,%d> (DMMA.8x8x4 over the lookup corners, "
+                                                   "%d-point groups)" % (sched["group_points"] // 8, sched["group_points"])),
+                                        "bound": "hbm",
                                         "ms": t_k * 1e3, "bytes_alg": sched["n_groups"] * N * bytes_ev,
                                         "achieved": sched["n_groups"] * N * bytes_ev / t_k / 1e9, "peak": hbm,
                                         "unit": "GB/s", "frac": sched["n_groups"] * N * bytes_ev / t_k / 1e9 / hbm,
@@ -464,8 +467,9 @@ def other_configs(args, rank, world, device):
     out["config5_large_dataset"] = {
         "workload": "large-dataset fit: %d events on this GPU (full config: 1e8 over 8 GPUs = 1.25e7 per GPU), 6 sources, "
                     "4 shape parameters x 5 anchors (625 anchors), 100x100 templates" % N,
-        "kernel": "k_template_mix + k_mixture_partials<NP,2> (mixture form: one lookup per point-event, events sorted "
-                  "by bin, prepared events streamed once per group of <= 8 points)",
+        "kernel": "k_template_mix + k_mixture_partials<1,2> / k_mixture_partials_mma<2,MT> (mixture form: one lookup per "
+                  "point-event, events sorted by bin, prepared events streamed once per group of <= 16 points; groups on "
+                  "the FP64 tensor pipe)",
         "bytes_per_event": 4 + 8 * eng.n_space, "n_events": int(N), **res5,
         "generate_s": gen_s, "set_data_s": set_data_s, "model_build_s": build_s}
     return out

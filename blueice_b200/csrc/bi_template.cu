@@ -646,6 +646,9 @@ __device__ __forceinline__ void bi_ts_dmma(double& d0, double& d1, double a, dou
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+#ifndef BI_MIXM_RELOAD
+#define BI_MIXM_RELOAD 0      /* 1: fractions re-read from L1 instead of shuffled (measured slower on B200) */
+#endif
 #define BI_MIXM_CHUNK 4        /* groups (of 32 events) per prefetch chunk */
 #ifndef BI_MIXM_MINCTAS
 #define BI_MIXM_MINCTAS 4
@@ -694,15 +697,19 @@ static __device__ __noinline__ double bi_mixm_slow(double p00, double p01, doubl
 }
 
 // B fragments of one group: weight of this lane's corner (of every quartet) at event 8n + g, w = ((1 * x_0) * x_1) ...
+// yl != NULL: the fractions of event 8n + g are re-read from global memory (an L1 hit: the coalesced chunk load brought
+// the lines in; the four t-lanes of an event share the address) instead of being shuffled out of the loading lane --
+// half the LSU wavefronts of the 64-bit shuffles.  yl points at fraction 0 of event g of the group.
 template <int NS>
-__device__ __forceinline__ void bi_mixm_weights(const double (&y)[BiMixm<NS>::NY], int g, int t, bool a_zero,
-                                                double (&w)[4][BiMixm<NS>::KS]) {
+__device__ __forceinline__ void bi_mixm_weights(const double (&y)[BiMixm<NS>::NY], const double* __restrict__ yl,
+                                                int64_t ld_frac, int g, int t, bool a_zero, double (&w)[4][BiMixm<NS>::KS]) {
     constexpr int KS = BiMixm<NS>::KS;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
         double x[BiMixm<NS>::NY];
 #pragma unroll
-        for (int dd = 0; dd < NS; ++dd) x[dd] = __shfl_sync(BI_FULL_MASK, y[dd], 8 * n + g);
+        for (int dd = 0; dd < NS; ++dd)
+            x[dd] = (BI_MIXM_RELOAD && yl) ? __ldg(yl + (int64_t)dd * ld_frac + 8 * n) : __shfl_sync(BI_FULL_MASK, y[dd], 8 * n + g);
 #pragma unroll
         for (int j = 0; j < KS; ++j) {
             const int c = (NS <= 1) ? (t & 1) : 4 * j + t;
@@ -768,10 +775,11 @@ __device__ __forceinline__ void bi_mixm_load_a(const double* const (&Vq)[MT], bo
 // one full group with shared bins per octet: branch-free up to the (rare) slow path
 template <int NS, int MT>
 __device__ __forceinline__ void bi_mixm_group_fast(const double (&a)[MT][4][BiMixm<NS>::KS], const double (&y)[BiMixm<NS>::NY],
+                                                   const double* __restrict__ yl, int64_t ld_frac,
                                                    int g, int t, bool a_zero, const bool (&live_me)[MT], double outlier,
                                                    double (&M)[MT], int (&E)[MT], double (&L)[MT], bool& any_slow) {
     double w[4][BiMixm<NS>::KS];
-    bi_mixm_weights<NS>(y, g, t, a_zero, w);
+    bi_mixm_weights<NS>(y, yl, ld_frac, g, t, a_zero, w);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         double d[4][2];
@@ -795,7 +803,7 @@ __device__ __forceinline__ void bi_mixm_group_any(const double* const (&Vq)[MT],
     const int first = __shfl_sync(BI_FULL_MASK, bin, threadIdx.x & 24);
     const unsigned neq = __ballot_sync(BI_FULL_MASK, bin != first);   // octets whose 8 events do not share one bin
     double w[4][KS];
-    bi_mixm_weights<NS>(y, g, t, a_zero, w);
+    bi_mixm_weights<NS>(y, nullptr, 0, g, t, a_zero, w);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         double d[4][2];
@@ -852,7 +860,7 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                        int64_t n_groups, const BiTsGroup* __restrict__ groups, const int64_t* __restrict__ unit_offset,
                        const int32_t* __restrict__ unit_group, int64_t n_units,
                        const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
-                       double outlier, double* __restrict__ partial) {
+                       double outlier, double* __restrict__ partial, int reload_fractions) {
     static_assert(NS >= 0 && NS <= 4, "piecewise lookups or linear lookups in 1..4 dimensions");
     constexpr int NY = BiMixm<NS>::NY, KS = BiMixm<NS>::KS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -911,22 +919,48 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                     ne |= cur.bin[i] != __shfl_sync(BI_FULL_MASK, cur.bin[i], lane & 24);
                 if (n_ev - c0 >= 32 * BI_MIXM_CHUNK && !__any_sync(BI_FULL_MASK, ne)) {
                     // every octet of the chunk shares its bin: branch-free, the next group's A fragments in flight
+                    const double* yl0 = (BI_MIXM_RELOAD && NS > 0 && reload_fractions) ? ev_frac + ev_begin + c0 + g : nullptr;
+                    const int b0 = __shfl_sync(BI_FULL_MASK, cur.bin[0], 0);
+                    bool one = true;
+#pragma unroll
+                    for (int i = 0; i < BI_MIXM_CHUNK; ++i) one &= cur.bin[i] == b0;
                     double a[MT][4][KS], an[MT][4][KS];
-                    bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, cur.bin[0], a);
+                    if (__all_sync(BI_FULL_MASK, one)) {
+                        // the whole chunk lies in ONE bin (dense datasets): one A fragment per m-tile for its 16 octets
 #pragma unroll
-                    for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
-                        if (i + 1 < BI_MIXM_CHUNK) bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, cur.bin[i + 1], an);
-                        double yy[NY];
+                        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                        for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][i];
-                        bi_mixm_group_fast<NS, MT>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
-                        if (i + 1 < BI_MIXM_CHUNK) {
+                            for (int j = 0; j < KS; ++j) {
+                                const double v = a_zero ? 0.0 : __ldg(Vq[mt] + (int64_t)b0 * BiMixm<NS>::PACK + sp.corner_off[4 * j]);
 #pragma unroll
-                            for (int mt = 0; mt < MT; ++mt)
+                                for (int n = 0; n < 4; ++n) a[mt][n][j] = v;
+                            }
 #pragma unroll
-                                for (int n = 0; n < 4; ++n)
+                        for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
+                            double yy[NY];
 #pragma unroll
-                                    for (int j = 0; j < KS; ++j) a[mt][n][j] = an[mt][n][j];
+                            for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][i];
+                            bi_mixm_group_fast<NS, MT>(a, yy, yl0 ? yl0 + 32 * i : nullptr, ld_frac, g, t, a_zero, live_me, outlier,
+                                                       M, E, L, any_slow);
+                        }
+                    } else {
+                        bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, cur.bin[0], a);
+#pragma unroll
+                        for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
+                            if (i + 1 < BI_MIXM_CHUNK) bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, cur.bin[i + 1], an);
+                            double yy[NY];
+#pragma unroll
+                            for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][i];
+                            bi_mixm_group_fast<NS, MT>(a, yy, yl0 ? yl0 + 32 * i : nullptr, ld_frac, g, t, a_zero, live_me, outlier,
+                                                       M, E, L, any_slow);
+                            if (i + 1 < BI_MIXM_CHUNK) {
+#pragma unroll
+                                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                                    for (int n = 0; n < 4; ++n)
+#pragma unroll
+                                        for (int j = 0; j < KS; ++j) a[mt][n][j] = an[mt][n][j];
+                            }
                         }
                     }
                 } else {
@@ -950,7 +984,7 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                         if (shared && n_ev - e0 >= 32) {                  // the group's octets share their bins
                             double a[MT][4][KS];
                             bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, bin_i, a);
-                            bi_mixm_group_fast<NS, MT>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
+                            bi_mixm_group_fast<NS, MT>(a, yy, nullptr, 0, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
                         } else {
                             bi_mixm_group_any<NS, MT>(Vq, sp, bin_i, yy, n_ev - e0, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
                         }
@@ -1253,6 +1287,16 @@ static int bi_mix_launch(const double* tmix, int64_t n_bins, const BiTsSpace& sp
     return BI_OK;
 }
 
+// BI_MIX_RELOAD=0|1: fractions handed to the fragment lanes by shuffles (0) or re-read from L1 (1)
+static int bi_mix_reload_fractions() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* v = getenv("BI_MIX_RELOAD");
+        mode = (v && v[0] == '1') ? 1 : 0;
+    }
+    return mode;
+}
+
 template <int NS, int MT>
 static int bi_mixm_launch(const double* tmix, int64_t n_bins, const BiTsSpace& sp, const int32_t* ev_bin,
                           const double* ev_frac, int64_t ld_frac, const int64_t* dataset_offset, const int32_t* status,
@@ -1273,7 +1317,7 @@ static int bi_mixm_launch(const double* tmix, int64_t n_bins, const BiTsSpace& s
     if (blocks > needed) blocks = needed;
     k_mixture_partials_mma<NS, MT><<<(unsigned)blocks, BI_TS_THREADS, 0, st>>>(
         tmix, n_bins, sp, ev_bin, ev_frac, ld_frac, dataset_offset, status, n_groups, groups, unit_offset, unit_group,
-        n_units, pair_point, pair_partial_offset, outlier, partial);
+        n_units, pair_point, pair_partial_offset, outlier, partial, bi_mix_reload_fractions());
     BI_LAUNCH_CHECK();
     return BI_OK;
 }

@@ -110,10 +110,11 @@ def main():
             zs = np.repeat(z0, P, 0)
             mult = np.repeat(m0, P, 0)
             for j in range(1, P):                                     # forward-difference batch: one parameter each
-                if j - 1 < 6:
-                    mult[j, j - 1] += 1.5e-8
+                k = (j - 1) % 10
+                if k < 6:
+                    mult[j, k] += 1.5e-8 * (1 + (j - 1) // 10)
                 else:
-                    zs[j, j - 7] += 1.5e-8
+                    zs[j, k - 6] += 1.5e-8 * (1 + (j - 1) // 10)
             sched, order = eng.single_schedule(zs)
             ms = timed(device_eval(eng, sched, zs, mult))
             bytes_ev = 4 + 8 * eng.n_space
