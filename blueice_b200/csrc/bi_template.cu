@@ -646,9 +646,6 @@ __device__ __forceinline__ void bi_ts_dmma(double& d0, double& d1, double a, dou
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-#ifndef BI_MIXM_RELOAD
-#define BI_MIXM_RELOAD 0      /* 1: fractions re-read from L1 instead of shuffled (measured slower on B200) */
-#endif
 #define BI_MIXM_CHUNK 4        /* groups (of 32 events) per prefetch chunk */
 #ifndef BI_MIXM_MINCTAS
 #define BI_MIXM_MINCTAS 4
@@ -697,19 +694,16 @@ static __device__ __noinline__ double bi_mixm_slow(double p00, double p01, doubl
 }
 
 // B fragments of one group: weight of this lane's corner (of every quartet) at event 8n + g, w = ((1 * x_0) * x_1) ...
-// yl != NULL: the fractions of event 8n + g are re-read from global memory (an L1 hit: the coalesced chunk load brought
-// the lines in; the four t-lanes of an event share the address) instead of being shuffled out of the loading lane --
-// half the LSU wavefronts of the 64-bit shuffles.  yl points at fraction 0 of event g of the group.
+// (re-reading the fractions from L1 in fragment layout instead of shuffling them measured slower on B200)
 template <int NS>
-__device__ __forceinline__ void bi_mixm_weights(const double (&y)[BiMixm<NS>::NY], const double* __restrict__ yl,
-                                                int64_t ld_frac, int g, int t, bool a_zero, double (&w)[4][BiMixm<NS>::KS]) {
+__device__ __forceinline__ void bi_mixm_weights(const double (&y)[BiMixm<NS>::NY], int g, int t, bool a_zero,
+                                                double (&w)[4][BiMixm<NS>::KS]) {
     constexpr int KS = BiMixm<NS>::KS;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
         double x[BiMixm<NS>::NY];
 #pragma unroll
-        for (int dd = 0; dd < NS; ++dd)
-            x[dd] = (BI_MIXM_RELOAD && yl) ? __ldg(yl + (int64_t)dd * ld_frac + 8 * n) : __shfl_sync(BI_FULL_MASK, y[dd], 8 * n + g);
+        for (int dd = 0; dd < NS; ++dd) x[dd] = __shfl_sync(BI_FULL_MASK, y[dd], 8 * n + g);
 #pragma unroll
         for (int j = 0; j < KS; ++j) {
             const int c = (NS <= 1) ? (t & 1) : 4 * j + t;
@@ -724,10 +718,10 @@ __device__ __forceinline__ void bi_mixm_weights(const double (&y)[BiMixm<NS>::NY
     }
 }
 
-// densities of this lane's class -> canonical product tree -> (M, E) of the superblock; slow path when out of range
+// densities of this lane's class -> canonical product tree -> (M, E) of the superblock; returns true when a density left
+// the fast range (the class then contributes (m, e) = (1, 0) and its events go through bi_mixm_slow)
 template <bool FULL>
-__device__ __forceinline__ void bi_mixm_tree(double (&d)[4][2], int n_left, int t, bool live_me, double outlier,
-                                             double& M, int& E, double& L, bool& any_slow) {
+__device__ __forceinline__ bool bi_mixm_tree(double (&d)[4][2], int n_left, int t, double& M, int& E) {
     if (!FULL) {
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
@@ -752,10 +746,12 @@ __device__ __forceinline__ void bi_mixm_tree(double (&d)[4][2], int n_left, int 
     if (bad) { m = 1.0; e = 0; }
     M = __dmul_rn(M, m);
     E += e;
-    if (bad && live_me) {                                             // rare: the class's 8 events through the log tree
-        L = __dadd_rn(L, bi_mixm_slow(d[0][0], d[0][1], d[1][0], d[1][1], d[2][0], d[2][1], d[3][0], d[3][1], outlier));
-        any_slow = true;
-    }
+    return bad;
+}
+// rare: the class's 8 events through the log tree
+__device__ __forceinline__ void bi_mixm_slow_apply(const double (&d)[4][2], double outlier, double& L, bool& any_slow) {
+    L = __dadd_rn(L, bi_mixm_slow(d[0][0], d[0][1], d[1][0], d[1][1], d[2][0], d[2][1], d[3][0], d[3][1], outlier));
+    any_slow = true;
 }
 
 // A fragments of a group whose four octets each share one bin: element t of the packed bin of point slot g
@@ -772,14 +768,16 @@ __device__ __forceinline__ void bi_mixm_load_a(const double* const (&Vq)[MT], bo
     }
 }
 
-// one full group with shared bins per octet: branch-free up to the (rare) slow path
-template <int NS, int MT>
-__device__ __forceinline__ void bi_mixm_group_fast(const double (&a)[MT][4][BiMixm<NS>::KS], const double (&y)[BiMixm<NS>::NY],
-                                                   const double* __restrict__ yl, int64_t ld_frac,
-                                                   int g, int t, bool a_zero, const bool (&live_me)[MT], double outlier,
-                                                   double (&M)[MT], int (&E)[MT], double (&L)[MT], bool& any_slow) {
+// one full group with shared bins per octet.  DEFER = false: the (rare) slow path runs right after each m-tile.
+// DEFER = true: branch-free -- bit mt of the result flags an m-tile whose class left the fast range; the caller runs
+// bi_mixm_group_redo for such groups afterwards, in group order (the order in which L accumulates).
+template <int NS, int MT, bool DEFER>
+__device__ __forceinline__ unsigned bi_mixm_group_fast(const double (&a)[MT][4][BiMixm<NS>::KS], const double (&y)[BiMixm<NS>::NY],
+                                                       int g, int t, bool a_zero, const bool (&live_me)[MT], double outlier,
+                                                       double (&M)[MT], int (&E)[MT], double (&L)[MT], bool& any_slow) {
     double w[4][BiMixm<NS>::KS];
-    bi_mixm_weights<NS>(y, yl, ld_frac, g, t, a_zero, w);
+    bi_mixm_weights<NS>(y, g, t, a_zero, w);
+    unsigned flags = 0;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         double d[4][2];
@@ -789,7 +787,29 @@ __device__ __forceinline__ void bi_mixm_group_fast(const double (&a)[MT][4][BiMi
 #pragma unroll
             for (int j = 0; j < BiMixm<NS>::KS; ++j) bi_ts_dmma(d[n][0], d[n][1], a[mt][n][j], w[n][j]);
         }
-        bi_mixm_tree<true>(d, 32, t, live_me[mt], outlier, M[mt], E[mt], L[mt], any_slow);
+        const bool bad = bi_mixm_tree<true>(d, 32, t, M[mt], E[mt]);
+        if (DEFER) flags |= (bad && live_me[mt]) ? 1u << mt : 0u;
+        else if (bad && live_me[mt]) bi_mixm_slow_apply(d, outlier, L[mt], any_slow);
+    }
+    return flags;
+}
+// the densities of a flagged group again (warp-collective), then the log tree in the lanes that flagged it
+template <int NS, int MT>
+__device__ __forceinline__ void bi_mixm_group_redo(const double (&a)[MT][4][BiMixm<NS>::KS], const double (&y)[BiMixm<NS>::NY],
+                                                   int g, int t, bool a_zero, unsigned flags, double outlier, double (&L)[MT],
+                                                   bool& any_slow) {
+    double w[4][BiMixm<NS>::KS];
+    bi_mixm_weights<NS>(y, g, t, a_zero, w);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        double d[4][2];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            d[n][0] = d[n][1] = 0.0;
+#pragma unroll
+            for (int j = 0; j < BiMixm<NS>::KS; ++j) bi_ts_dmma(d[n][0], d[n][1], a[mt][n][j], w[n][j]);
+        }
+        if ((flags >> mt) & 1u) bi_mixm_slow_apply(d, outlier, L[mt], any_slow);
     }
 }
 
@@ -803,7 +823,7 @@ __device__ __forceinline__ void bi_mixm_group_any(const double* const (&Vq)[MT],
     const int first = __shfl_sync(BI_FULL_MASK, bin, threadIdx.x & 24);
     const unsigned neq = __ballot_sync(BI_FULL_MASK, bin != first);   // octets whose 8 events do not share one bin
     double w[4][KS];
-    bi_mixm_weights<NS>(y, nullptr, 0, g, t, a_zero, w);
+    bi_mixm_weights<NS>(y, g, t, a_zero, w);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         double d[4][2];
@@ -844,8 +864,8 @@ __device__ __forceinline__ void bi_mixm_group_any(const double* const (&Vq)[MT],
                 }
             }
         }
-        if (n_left >= 32) bi_mixm_tree<true>(d, 32, t, live_me[mt], outlier, M[mt], E[mt], L[mt], any_slow);
-        else bi_mixm_tree<false>(d, n_left, t, live_me[mt], outlier, M[mt], E[mt], L[mt], any_slow);
+        const bool bad = n_left >= 32 ? bi_mixm_tree<true>(d, 32, t, M[mt], E[mt]) : bi_mixm_tree<false>(d, n_left, t, M[mt], E[mt]);
+        if (bad && live_me[mt]) bi_mixm_slow_apply(d, outlier, L[mt], any_slow);
     }
 }
 
@@ -860,7 +880,7 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                        int64_t n_groups, const BiTsGroup* __restrict__ groups, const int64_t* __restrict__ unit_offset,
                        const int32_t* __restrict__ unit_group, int64_t n_units,
                        const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
-                       double outlier, double* __restrict__ partial, int reload_fractions) {
+                       double outlier, double* __restrict__ partial) {
     static_assert(NS >= 0 && NS <= 4, "piecewise lookups or linear lookups in 1..4 dimensions");
     constexpr int NY = BiMixm<NS>::NY, KS = BiMixm<NS>::KS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -919,7 +939,6 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                     ne |= cur.bin[i] != __shfl_sync(BI_FULL_MASK, cur.bin[i], lane & 24);
                 if (n_ev - c0 >= 32 * BI_MIXM_CHUNK && !__any_sync(BI_FULL_MASK, ne)) {
                     // every octet of the chunk shares its bin: branch-free, the next group's A fragments in flight
-                    const double* yl0 = (BI_MIXM_RELOAD && NS > 0 && reload_fractions) ? ev_frac + ev_begin + c0 + g : nullptr;
                     const int b0 = __shfl_sync(BI_FULL_MASK, cur.bin[0], 0);
                     bool one = true;
 #pragma unroll
@@ -935,13 +954,30 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
 #pragma unroll
                                 for (int n = 0; n < 4; ++n) a[mt][n][j] = v;
                             }
+                        unsigned flags = 0;                                   // bit i * MT + mt: group i, m-tile mt left the fast range
 #pragma unroll
-                        for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
+                        for (int i = 0; i < BI_MIXM_CHUNK; ++i) {             // one branch-free block: the groups interleave
                             double yy[NY];
 #pragma unroll
                             for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][i];
-                            bi_mixm_group_fast<NS, MT>(a, yy, yl0 ? yl0 + 32 * i : nullptr, ld_frac, g, t, a_zero, live_me, outlier,
-                                                       M, E, L, any_slow);
+                            flags |= bi_mixm_group_fast<NS, MT, true>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow) << (i * MT);
+                        }
+                        if (__any_sync(BI_FULL_MASK, flags != 0)) {           // rare: log trees, in group order
+#pragma unroll 1
+                            for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
+                                const unsigned f = (flags >> (i * MT)) & ((1u << MT) - 1u);
+                                if (!__any_sync(BI_FULL_MASK, f != 0)) continue;
+                                double yy[NY];
+#pragma unroll
+                                for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][0];
+#pragma unroll
+                                for (int k = 1; k < BI_MIXM_CHUNK; ++k)
+                                    if (i == k) {
+#pragma unroll
+                                        for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][k];
+                                    }
+                                bi_mixm_group_redo<NS, MT>(a, yy, g, t, a_zero, f, outlier, L, any_slow);
+                            }
                         }
                     } else {
                         bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, cur.bin[0], a);
@@ -951,8 +987,7 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                             double yy[NY];
 #pragma unroll
                             for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][i];
-                            bi_mixm_group_fast<NS, MT>(a, yy, yl0 ? yl0 + 32 * i : nullptr, ld_frac, g, t, a_zero, live_me, outlier,
-                                                       M, E, L, any_slow);
+                            bi_mixm_group_fast<NS, MT, false>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
                             if (i + 1 < BI_MIXM_CHUNK) {
 #pragma unroll
                                 for (int mt = 0; mt < MT; ++mt)
@@ -984,7 +1019,7 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                         if (shared && n_ev - e0 >= 32) {                  // the group's octets share their bins
                             double a[MT][4][KS];
                             bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, bin_i, a);
-                            bi_mixm_group_fast<NS, MT>(a, yy, nullptr, 0, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
+                            bi_mixm_group_fast<NS, MT, false>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
                         } else {
                             bi_mixm_group_any<NS, MT>(Vq, sp, bin_i, yy, n_ev - e0, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
                         }
@@ -1287,16 +1322,6 @@ static int bi_mix_launch(const double* tmix, int64_t n_bins, const BiTsSpace& sp
     return BI_OK;
 }
 
-// BI_MIX_RELOAD=0|1: fractions handed to the fragment lanes by shuffles (0) or re-read from L1 (1)
-static int bi_mix_reload_fractions() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* v = getenv("BI_MIX_RELOAD");
-        mode = (v && v[0] == '1') ? 1 : 0;
-    }
-    return mode;
-}
-
 template <int NS, int MT>
 static int bi_mixm_launch(const double* tmix, int64_t n_bins, const BiTsSpace& sp, const int32_t* ev_bin,
                           const double* ev_frac, int64_t ld_frac, const int64_t* dataset_offset, const int32_t* status,
@@ -1317,7 +1342,7 @@ static int bi_mixm_launch(const double* tmix, int64_t n_bins, const BiTsSpace& s
     if (blocks > needed) blocks = needed;
     k_mixture_partials_mma<NS, MT><<<(unsigned)blocks, BI_TS_THREADS, 0, st>>>(
         tmix, n_bins, sp, ev_bin, ev_frac, ld_frac, dataset_offset, status, n_groups, groups, unit_offset, unit_group,
-        n_units, pair_point, pair_partial_offset, outlier, partial, bi_mix_reload_fractions());
+        n_units, pair_point, pair_partial_offset, outlier, partial);
     BI_LAUNCH_CHECK();
     return BI_OK;
 }
