@@ -971,6 +971,20 @@ class BinnedEngine(_EngineBase):
 _MIX_WIDE_MIN_SUPERBLOCKS = 16384       # 8.4e6 events (168 MB of prepared 2-D events): wide K5b groups from here on
 
 
+def mixture_group_width(n_points, min_superblocks, wide_min_superblocks=None, tensor_pipe=True):
+    """Points per group of a K5b (mixture-form) schedule, before the pairs are cut: 1 for a single point, 16 (two 8-point
+    m-tiles per warp, one pass over the events per 16 points) when more than 8 points are evaluated on datasets of at
+    least wide_min_superblocks superblocks -- large enough to outgrow the L2 and to fill the device with half as many
+    units -- and the tensor-pipe kernel is in use (BI_MIX_MMA != '0'), else 8."""
+    if wide_min_superblocks is None:
+        wide_min_superblocks = _MIX_WIDE_MIN_SUPERBLOCKS
+    if n_points <= 1:
+        return 1
+    if tensor_pipe and n_points > _cabi.MIX_GROUP_POINTS and min_superblocks >= wide_min_superblocks:
+        return _cabi.MIX_GROUP_POINTS_WIDE
+    return _cabi.MIX_GROUP_POINTS
+
+
 def group_pairs(dataset_index, cells, n_cells, group_points):
     """Host-side grouping of (dataset, point) pairs for the template-space kernels (pure function).
 
@@ -1185,14 +1199,10 @@ class TemplateUnbinnedEngine(_EngineBase):
             np_max = 1
         elif self.mode != 'mixture':
             np_max = _cabi.TS_GROUP_POINTS
-        elif (P > _cabi.MIX_GROUP_POINTS and os.environ.get('BI_MIX_MMA') != '0'
-              and int(self.n_super_host[dataset_index].min()) >= getattr(self, 'mix_wide_min_superblocks',
-                                                                          _MIX_WIDE_MIN_SUPERBLOCKS)):
-            # two 8-point m-tiles per warp: one pass over the events per 16 points (datasets that outgrow the L2 and
-            # still fill the device with half as many units)
-            np_max = _cabi.MIX_GROUP_POINTS_WIDE
         else:
-            np_max = _cabi.MIX_GROUP_POINTS
+            np_max = mixture_group_width(P, int(self.n_super_host[dataset_index].min()),
+                                         getattr(self, 'mix_wide_min_superblocks', None),
+                                         os.environ.get('BI_MIX_MMA') != '0')
         order, first, count = group_pairs(dataset_index, cells, n_cells, np_max)
         if P and count.max() == 1:
             np_max = 1

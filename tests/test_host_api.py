@@ -245,6 +245,27 @@ def test_group_pairs_invariants():
     assert order.tolist() == [1, 3, 0, 2, 4] and first.tolist() == [0, 2] and count.tolist() == [2, 3]
 
 
+def test_mixture_group_width_rules():
+    """Points per group of a mixture-form (K5b) schedule: 1 point streams alone, up to 8 points share one pass over
+    the events, and 16 (two m-tiles per warp on the FP64 tensor pipe) only for more than 8 points on datasets that
+    outgrow the L2; the gather kernel (BI_MIX_MMA=0) never gets wide groups.  group_pairs cuts runs accordingly."""
+    from blueice_b200 import _cabi
+    from blueice_b200.engine import _MIX_WIDE_MIN_SUPERBLOCKS, group_pairs, mixture_group_width
+    big, small = _MIX_WIDE_MIN_SUPERBLOCKS, _MIX_WIDE_MIN_SUPERBLOCKS - 1
+    assert mixture_group_width(0, big) == 1 and mixture_group_width(1, big) == 1
+    assert mixture_group_width(2, big) == 8 and mixture_group_width(8, big) == 8
+    assert mixture_group_width(9, big) == 16 and mixture_group_width(4096, big) == 16
+    assert mixture_group_width(11, small) == 8
+    assert mixture_group_width(11, big, tensor_pipe=False) == 8
+    assert mixture_group_width(11, 3, wide_min_superblocks=0) == 16          # the override the GPU tests use
+    assert _cabi.MIX_GROUP_POINTS == 8 and _cabi.MIX_GROUP_POINTS_WIDE == 16
+    # an 11-point finite-difference batch in one cell: one wide group, or 8 + 3
+    cells = np.zeros(11, dtype=np.int64)
+    for width, want in ((16, [11]), (8, [8, 3])):
+        _, first, count = group_pairs(np.zeros(11, dtype=np.int64), cells, 1, width)
+        assert count.tolist() == want and first.tolist() == np.concatenate([[0], np.cumsum(want)[:-1]]).tolist()
+
+
 def test_toy_tables_and_means_follow_model_simulate():
     """Host side of on-device toy generation: the cdf tables are Histdd.get_random's (cumsum of the flattened pmf, last
     entry 1) and the Poisson means are Model.simulate's (model.py:80-84: rate multipliers, livetime, fraction in range)."""
