@@ -419,7 +419,8 @@ def other_configs(args, rank, world, device):
     res5 = {}
     eng = ll._engine
     hbm = measured_peaks()[0]["hbm_gbs"]
-    for P, table in ((1, fd[:1]), (11, fd)):
+    scan = np.column_stack([rng.uniform(0.8, 1.2, size=(64, 6)), rng.uniform(-1.9, 1.9, size=(64, 4))])   # 64-point scan
+    for P, table in ((1, fd[:1]), (11, fd), (64, scan)):
         for _ in range(4):                                          # warm-up: the third call captures the CUDA graph
             ll.batch(table, names, livetime_days=lt)
         ts = []
