@@ -224,6 +224,132 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------------------------
 # own arm
+def _median_max_over_ranks(fn, n_warm, n_rep, world, device):
+    """Wall time of fn() (median of n_rep calls after n_warm warm-ups; every call starts behind a barrier), the maximum
+    over the ranks, and the same for the device span (CUDA events around the call)."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(n_warm):
+        fn()
+    wall, dev = [], []
+    for _ in range(n_rep):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        fn()
+        b.record()
+        wall.append(time.perf_counter() - t0)
+        torch.cuda.synchronize()
+        dev.append(a.elapsed_time(b) * 1e-3)
+    t = torch.tensor([float(np.median(wall)), float(np.median(dev))], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]), float(t[1])
+
+
+def config5_event_sharded(args, rank, world, device):
+    """BASELINE config 5 as north_star splits it: `--c5-events` events IN TOTAL (strong scaling), sharded over the ranks
+    in superblock-aligned contiguous slices; every minimiser step evaluates its P points on the rank's shard (mixture
+    engine, K5b) and ends with ONE exchange launch (bi_peer_exchange: the shards' log sums to every rank over NVLink peer
+    memory, summed in rank order on the device), all inside one CUDA graph per step."""
+    import torch
+    import torch.distributed as dist
+    from blueice_b200 import distributed as bdist
+    ll, _, names = wl.c2_api(6, 4, wl.ANCHORS_5, BINS, n_events=1000, seed=5,
+                             likelihood_config={'unbinned_engine': 'mixture'})
+    base_mu = float(np.sum(ll.base_model.expected_events()))
+    n_target = args.c5_events
+    lt = n_target / base_mu
+    t0 = time.perf_counter()
+    td = ll.base_model.simulate_toys(1, livetime_days=lt, seed=50)          # the same events on every rank (Philox)
+    N = td.n_events
+    lo, hi = bdist.shard_bounds(N, world, align=512)[rank]
+    d = np.zeros(hi - lo, dtype=[('source', int)] + [(name, float) for name in td.dims])
+    host = td.coords[:, lo:hi].cpu().numpy()
+    for k, name in enumerate(td.dims):
+        d[name] = host[k]
+    del td, host
+    torch.cuda.empty_cache()
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ll.set_data(d)
+    torch.cuda.synchronize()
+    set_data_s = time.perf_counter() - t0
+    sharded = bdist.EventShardedLikelihood(ll)
+    rng = np.random.default_rng(51)
+    x0 = np.concatenate([rng.uniform(0.8, 1.2, size=6), rng.uniform(-1.9, 1.9, size=4)])
+    fd = np.repeat(x0[None, :], 11, 0)
+    for j in range(10):
+        fd[j + 1, j] += 1.4901161193847656e-08
+    scan = np.column_stack([rng.uniform(0.8, 1.2, size=(64, 6)), rng.uniform(-1.9, 1.9, size=(64, 4))])
+    res = {}
+    for P, table in ((1, fd[:1]), (11, fd), (64, scan)):
+        got = sharded.batch(table, names, livetime_days=lt)
+        rows = bdist.all_gather_rows(got)
+        assert all(np.array_equal(rows[0], r) for r in rows), "ranks disagree on the event-sharded result"
+        wall, dev = _median_max_over_ranks(lambda: sharded.batch(table, names, livetime_days=lt), 4, 20, world, device)
+        res["P%d" % P] = {"e2e_ms": wall * 1e3, "device_span_ms": dev * 1e3, "point_events_per_s_e2e": P * N / wall,
+                          "finite": bool(np.all(np.isfinite(got))), "logl0": float(got[0])}
+    # the exchange launch alone, all ranks in the same loop (P = 11 values per rank)
+    pg = sharded._gathers[11]
+    x = torch.zeros(11, dtype=torch.float64, device=device)
+    for _ in range(10):
+        pg.reduce(x)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(200):
+        pg.reduce(x)
+    b.record()
+    torch.cuda.synchronize()
+    exchange_us = a.elapsed_time(b) * 1e3 / 200
+    err = pg.error()
+    return {"workload": "large-dataset fit, events sharded: %d events in total over %d GPUs (%d on this rank), 6 sources, "
+                        "4 shape parameters x 5 anchors (625 anchors), 100x100 templates" % (N, world, hi - lo),
+            "api": "distributed.EventShardedLikelihood.batch", "n_events_total": int(N), "n_gpus": world,
+            "exchange": "bi_peer_exchange mode sum (%s)" % ("nvlink peer memory" if pg.fallback is None else "nccl fallback: " + pg.fallback),
+            "exchange_launch_us": exchange_us, "exchange_error_word": int(err), **res,
+            "generate_s": gen_s, "set_data_s": set_data_s}
+
+
+def sharded_summary(world, P, n_events, e2e_obj, strong, other):
+    """Flat scalars of the three multi-GPU splits for the e2e object: config 2 strongly scaled (P points in total), config 5
+    event-sharded (all events in total, P = 11 minimiser step including the exchange), config 4 toy-sharded."""
+    out = {}
+    if world == 1:
+        out["c2_strong_points_total"] = P
+        out["c2_strong_ms"] = e2e_obj["ms_per_step"]
+        out["c2_strong_pe_per_s"] = e2e_obj["value"]
+    elif strong is not None:
+        out["c2_strong_points_total"] = strong["points_total"]
+        out["c2_strong_ms"] = strong["e2e_ms"]
+        out["c2_strong_pe_per_s"] = strong["point_events_per_s_e2e"]
+    if not other:
+        return out
+    c4 = other.get("config4_toys")
+    if c4:
+        out["c4_toys_total"] = c4["toys_per_gpu"] * world
+        out["c4_sweep_ms_e2e"] = c4["e2e"]["ms"]
+        out["c4_toys_per_s_e2e"] = c4["e2e"]["toys_per_s"]
+        out["c4_toys_per_s_device"] = c4["device"]["toys_per_s"]
+    c5 = other.get("config5_event_sharded") or other.get("config5_large_dataset")
+    if c5:
+        out["c5_events_total"] = c5.get("n_events_total", c5.get("n_events"))
+        for P5 in (1, 11, 64):
+            r = c5.get("P%d" % P5)
+            if r:
+                out["c5_P%d_step_ms_e2e" % P5] = r["e2e_ms"]
+        if "P11" in c5:
+            out["c5_P11_pe_per_s_e2e"] = c5["P11"]["point_events_per_s_e2e"]
+        if "exchange_launch_us" in c5:
+            out["c5_exchange_launch_us"] = c5["exchange_launch_us"]
+    return out
+
+
 def other_configs(args, rank, world, device):
     """BASELINE configs 4 and 5 through the public API on the template-space engine (K5 / K5b), bounded sizes.
 
@@ -245,16 +371,32 @@ def other_configs(args, rank, world, device):
     T = args.toys
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    toys = ll.base_model.simulate_toys(T, livetime_days=lt, seed=40, first_toy=rank * T)
-    torch.cuda.synchronize()
-    gen_s = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    ll.set_toy_data(toys)
-    torch.cuda.synchronize()
-    load_s = time.perf_counter() - t0
-    zs, mult = wl.scan_points(T, 3, 3, seed=41 + rank)
-    table = np.ascontiguousarray(np.column_stack([mult, zs]))
-    res = ll.batch_toys(table, names, livetime_days=lt)
+    if world > 1:
+        # toys sharded over the ranks (weak: `--toys` toys per GPU): rank r generates and holds toys [r T, (r + 1) T)
+        from blueice_b200.distributed import ToyShardedLikelihood
+        sharded_toys = ToyShardedLikelihood(ll)
+        toys = sharded_toys.simulate(T * world, livetime_days=lt, seed=40)
+        torch.cuda.synchronize()
+        gen_s, load_s = time.perf_counter() - t0, 0.0                # generation + load (event preparation) together
+    else:
+        toys = ll.base_model.simulate_toys(T, livetime_days=lt, seed=40, first_toy=rank * T)
+        torch.cuda.synchronize()
+        gen_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ll.set_toy_data(toys)
+        torch.cuda.synchronize()
+        load_s = time.perf_counter() - t0
+    zs_all4, mult_all4 = wl.scan_points(T * world, 3, 3, seed=41)
+    table_all4 = np.ascontiguousarray(np.column_stack([mult_all4, zs_all4]))
+    zs, mult = zs_all4[rank * T:(rank + 1) * T], mult_all4[rank * T:(rank + 1) * T]
+    table = table_all4[rank * T:(rank + 1) * T]
+    if world > 1:
+        def toy_call():
+            return sharded_toys.batch_toys(table_all4, names, livetime_days=lt)[rank * T:(rank + 1) * T]
+    else:
+        def toy_call():
+            return ll.batch_toys(table, names, livetime_days=lt)
+    res = toy_call()
     eng = ll._toy_engine
     # device-resident: K1 + K5 + finalize on uploaded points
     zs_d, mult_d, scale_d, _, _ = eng._upload_points(zs, mult, np.full(T, lt / ll.pdf_base_config['livetime_days']), None)
@@ -269,21 +411,23 @@ def other_configs(args, rank, world, device):
         if k:
             dev_ms.append(a.elapsed_time(b))
     for _ in range(3):                                             # warm-up: the third call captures the CUDA graph
-        ll.batch_toys(table, names, livetime_days=lt)
+        toy_call()
     e2e = []
-    for _ in range(3):
+    for _ in range(5):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        res = ll.batch_toys(table, names, livetime_days=lt)
+        res = toy_call()
         e2e.append(time.perf_counter() - t0)
-    t_dev, t_e2e = float(np.mean(dev_ms)) * 1e-3, float(np.mean(e2e))
+    t_dev, t_e2e = float(np.mean(dev_ms)) * 1e-3, float(np.median(e2e))
     if world > 1:
         t = torch.tensor([t_dev, t_e2e, gen_s], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e, gen_s = float(t[0]), float(t[1]), float(t[2])
     # per-toy maximum-likelihood fits in lock step (the Neyman construction's inner loop) on a slice of the toys
     from blueice_b200.inference import bestfit_toys
-    n_fit = min(args.fit_toys, T)
+    n_fit = min(args.fit_toys, T) if world == 1 else 0
     fit_info = None
     if n_fit:
         sub = ll.base_model.simulate_toys(n_fit, livetime_days=lt, seed=40, first_toy=rank * T)
@@ -300,6 +444,8 @@ def other_configs(args, rank, world, device):
     out["config4_toys"] = {
         "workload": "toy-MC: %d toys per GPU x ~1000 events, 3 sources, 3 shape parameters x 5 anchors (125 anchors), "
                     "100x100 templates, one parameter point per toy" % T,
+        "api": "ll.batch_toys" if world == 1 else "distributed.ToyShardedLikelihood.batch_toys (toys sharded over the ranks, "
+               "results of all ranks gathered over NVLink by one bi_peer_exchange launch inside the evaluation's CUDA graph)",
         "kernel": "k_template_partials<1,2> (fused template lookup + morph + log-sum, bit-identical to K3 + K2)",
         "toys_per_gpu": T, "events_per_gpu": int(n_ev), "n_gpus": world, "finite_results": int(np.isfinite(res).sum()),
         "device": {"ms": t_dev * 1e3, "toys_per_s": world * T / t_dev, "point_events_per_s": world * n_ev / t_dev},
@@ -309,7 +455,10 @@ def other_configs(args, rank, world, device):
         "extrapolated_1e6_toys_s": 1e6 / (world * T / t_e2e), "lock_step_fits": fit_info}
     del ll, toys, eng
     torch.cuda.empty_cache()
-    if rank != 0:
+    if world > 1:
+        # the other two splits of north_star, strongly scaled; configs 1 / 3 and the single-GPU config-5 breakdown
+        # are reported by the N = 1 run only
+        out["config5_event_sharded"] = config5_event_sharded(args, rank, world, device)
         return out
     # ---- config 1 (the reference's own CPU-runnable case): latency of one evaluation and a 4096-point batch ----
     ll1, d1, names1 = wl.c1_api(seed=0)
@@ -540,7 +689,7 @@ def run_own_arm(args):
         if world > 1:
             # this rank's rows go to every rank (stores only): point sharding has no data-path collective, the ranks
             # do not wait for each other inside a step; delivery is confirmed by ONE barrier after the timed loop
-            gathered_dev = peer_gather.gather(logl, wait=args.gather_wait)
+            gathered_dev = peer_gather.gather(logl) if args.gather_wait else peer_gather.broadcast(logl)
         return logl
 
     for _ in range(max(args.warmup, 3)):
@@ -596,6 +745,34 @@ def run_own_arm(args):
     assert np.array_equal(res, result_dev), "device-resident and e2e arms disagree"
     e2e_total = float(np.sum(e2e_s))
     h2d, d2h = int(eng.last_h2d_bytes), int(eng.last_d2h_bytes)
+
+    # ---- strong scaling of the same scan: P points IN TOTAL, sharded over the ranks (N = 1: the e2e arm itself) ------
+    strong = None
+    if world > 1:
+        table_strong = table_all[:P]
+        for _ in range(3):
+            flush_l2()
+            res_s = sharded.batch(table_strong, names)
+        ts, ds = [], []
+        for k in range(args.steps):
+            flush_l2()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            res_s = sharded.batch(table_strong, names)
+            b.record()
+            ts.append(time.perf_counter() - t0)
+            torch.cuda.synchronize()
+            ds.append(a.elapsed_time(b) * 1e-3)
+        # rank 0 evaluated rows [0, P / world) of the weak scan too: the sharded result must reproduce them bit for bit
+        if rank == 0:
+            assert np.array_equal(res_s[:P // world], result_dev[:P // world]), "strong-scaled scan differs"
+        t = torch.tensor([float(np.sum(ts)), float(np.sum(ds))], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"points_total": P, "e2e_ms": float(t[0]) * 1e3 / args.steps, "device_span_ms": float(t[1]) * 1e3 / args.steps,
+                  "point_events_per_s_e2e": P * n_events * args.steps / float(t[0])}
 
     # ---- dominant kernel alone (grouped K2), for the roofline --------------------------------------
     S, C = eng.n_sources, eng.grid.n_corners
@@ -784,12 +961,15 @@ def run_own_arm(args):
                                 "note": "shared-dataset scan: the anchor tensor is read once per launch, "
                                         "so this kernel is FP64-pipe bound, not HBM bound (SURVEY.md 8d)"}}
         cpu = cpu_baseline_single_core(args.events) if not args.skip_cpu else None
+        e2e_obj = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": 1e3 * e2e_total_max / args.steps}
+        # flat scalar copies of the multi-GPU splits (the driver's record keeps scalars of the contract objects only)
+        e2e_obj.update(sharded_summary(world, P, n_events, e2e_obj, strong, other))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": workload_config(n_events, P),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": 1e3 * e2e_total_max / args.steps},
+                "e2e": e2e_obj, "config2_strong_scaling": strong,
                 "gpu_launches": int(launches_timed),
                 "launches_per_step": launches_timed / args.steps,
                 "roofline": roofline, "roofline_stream": stream_info, "cpu_baseline": cpu,

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libblueice_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["bi_util.cu", "bi_setup.cu", "bi_unbinned.cu", "bi_unbinned_mma.cu", "bi_plan.cu", "bi_lookup.cu", "bi_template.cu", "bi_toys.cu", "bi_binned.cu",
+SOURCES = ["bi_util.cu", "bi_peer.cu", "bi_setup.cu", "bi_unbinned.cu", "bi_unbinned_mma.cu", "bi_plan.cu", "bi_lookup.cu", "bi_template.cu", "bi_toys.cu", "bi_binned.cu",
            "bi_grouped_c1.cu", "bi_grouped_c2.cu", "bi_grouped_c4.cu", "bi_grouped_c8.cu", "bi_grouped_c16.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -49,8 +49,16 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     from concurrent.futures import ThreadPoolExecutor
 
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    headers.append(os.path.join(HERE, "..", "include", "blueice_b200.h"))
+    headers.append(os.path.abspath(__file__))
+    header_time = max(os.path.getmtime(h) for h in headers)
+
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        if (not force and not verbose and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(header_time, os.path.getmtime(os.path.join(CSRC, src)))):
+            return src, obj, None                                  # object is newer than its source and every header
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, res
@@ -58,9 +66,9 @@ def build(force=False, verbose=False):
     objects = []
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
         for src, obj, res in pool.map(compile_one, SOURCES):
-            if verbose or res.returncode != 0:
+            if res is not None and (verbose or res.returncode != 0):
                 sys.stderr.write(res.stdout + res.stderr)
-            if res.returncode != 0:
+            if res is not None and res.returncode != 0:
                 raise RuntimeError("nvcc failed on %s" % src)
             objects.append(obj)
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objects

@@ -136,41 +136,3 @@ extern "C" int bi_bench_stream_read(const double* src_dev, int64_t n_doubles, do
     cudaEventDestroy(e1);
     return BI_OK;
 }
-
-// ---------------------------------------------------------------------------------------------
-// Peer broadcast over NVLink: every rank stores its n results into the gather buffer of EVERY rank
-// (peer-mapped device pointers, e.g. torch symmetric memory) at its own slot -- the all-gather of the
-// point / toy sharded evaluation as plain P2P stores, without a collective launch.  The caller follows it
-// with a cross-GPU barrier (signal pads) before anybody reads the gathered rows.
-// ---------------------------------------------------------------------------------------------
-#define BI_MAX_PEERS 16
-struct BiPeers { double* p[BI_MAX_PEERS]; };
-
-__global__ void __launch_bounds__(256)
-k_peer_broadcast(const double* __restrict__ src, int64_t n, const __grid_constant__ BiPeers peers, int world,
-                 int64_t dst_offset) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double v = src[i];
-        for (int r = 0; r < world; ++r) peers.p[r][dst_offset + i] = v;
-    }
-    __threadfence_system();
-}
-
-extern "C" int bi_peer_broadcast(const double* src_dev, int64_t n, const uint64_t* peer_ptrs_host, int32_t world,
-                                 int64_t dst_offset, void* stream) {
-    BI_REQUIRE(world >= 1 && world <= BI_MAX_PEERS, "world=%d outside [1,%d]", world, BI_MAX_PEERS);
-    BI_REQUIRE(n >= 0 && dst_offset >= 0, "negative size");
-    if (n == 0) return BI_OK;
-    BI_REQUIRE(src_dev && peer_ptrs_host, "bi_peer_broadcast: NULL pointer");
-    BiPeers peers;
-    memset(&peers, 0, sizeof(peers));
-    for (int r = 0; r < world; ++r) {
-        BI_REQUIRE(peer_ptrs_host[r] != 0, "bi_peer_broadcast: peer %d has no buffer", r);
-        peers.p[r] = reinterpret_cast<double*>(peer_ptrs_host[r]);
-    }
-    int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    k_peer_broadcast<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src_dev, n, peers, world, dst_offset);
-    BI_LAUNCH_CHECK();
-    return BI_OK;
-}

@@ -83,35 +83,43 @@ def rank_ordered_sum(local, group=None):
 
 
 class PeerGather(object):
-    """All-gather of n float64 results per rank as P2P stores over NVLink (bi_peer_broadcast) into peer-mapped
-    buffers (torch symmetric memory), followed by a signal-pad barrier: no collective launch, ~10 us instead of the
-    20-40 us of an NCCL all_gather of a few kB.  Device tensors in, device tensor [world, n] out, all on the current
-    stream.  Falls back to NCCL all_gather_into_tensor when symmetric memory is unavailable (construction fails)."""
+    """The exchange step of a sharded evaluation over NVLink peer memory (bi_peer_exchange): ONE kernel launch stores this
+    rank's n float64 values into peer-mapped buffers of every rank (torch symmetric memory), releases its flag on every
+    rank, waits for every rank's flag and then either copies the gathered rows out (gather) or adds them up in rank order
+    (reduce).  No collective launch, no host round trip; the epoch counter lives on the device, so the launch can be
+    captured in a CUDA graph together with the evaluation it follows.  Device tensors in, device tensors out, all on the
+    current stream.  Falls back to NCCL all_gather_into_tensor when symmetric memory is unavailable."""
 
     def __init__(self, n, group=None):
         import ctypes
         import torch
-        import torch.distributed._symmetric_memory as symm_mem
         dist = _dist()
         self.group = dist.group.WORLD if group is None else group
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        self.n = int(n)
+        self.n = max(int(n), 1)
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.lib = _cabi.load()
         self.fallback = None
+        self.words = int(self.lib.bi_peer_exchange_words(self.world, self.n))
         try:
-            # two gather buffers used alternately: a rank may only overwrite the rows of gather k - 2, and it cannot
-            # start gather k before every rank has passed the barrier of gather k - 1, which each rank enqueues after
-            # its own (same-stream) reads of gather k - 2 -- so ONE barrier per gather is enough
-            self.buffer = symm_mem.empty(2 * self.world * max(self.n, 1), dtype=torch.float64, device=self.device)
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buffer = symm_mem.empty(self.words, dtype=torch.float64, device=self.device)
+            self.buffer.zero_()
             self.handle = symm_mem.rendezvous(self.buffer, self.group)
             self.peer_ptrs = np.ascontiguousarray(np.array([int(p) for p in self.handle.buffer_ptrs], dtype=np.uint64))
-            self.handle.barrier(channel=0)
+            self.handle.barrier(channel=0)                         # every rank's flags are zero before anybody signals
         except Exception as exc:                                    # no peer mapping on this system: NCCL
             self.fallback = repr(exc)
-            self.buffer = torch.empty(2 * self.world * max(self.n, 1), dtype=torch.float64, device=self.device)
-        self.parity = 0
+            self.buffer = None
+        self.out = torch.zeros(self.world * self.n, dtype=torch.float64, device=self.device)      # gathered rows
+        self.total = torch.zeros(self.n, dtype=torch.float64, device=self.device)                 # reduced values
+        self.launches = 0
+        self._parity = 0
         self._ctypes = ctypes
+
+    def _stream(self):
+        import torch
+        return self._ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def barrier(self):
         """Cross-GPU barrier on the current stream (signal pads; NCCL barrier in the fallback)."""
@@ -120,26 +128,73 @@ class PeerGather(object):
         else:
             self.handle.barrier(channel=0)
 
-    def gather(self, local, wait=True):
-        """local: device tensor of n float64 -> device tensor [world, n] holding every rank's values.
-
-        wait=False only issues this rank's stores (no waiting for the other ranks): the rows are complete after the
-        next barrier(); a caller doing so must not let more than one un-waited gather overtake a reader."""
+    def error(self):
+        """0, or the epoch at which a peer failed to arrive in time (synchronises the stream)."""
+        if self.fallback is not None:
+            return 0
         import torch
+        words = self.buffer.view(torch.int64)
+        return int(words[2 * self.world * self.n + self.world + 3].item())
+
+    def _check(self, local):
         if local.numel() > self.n or (self.fallback is not None and local.numel() != self.n):
             raise ValueError("PeerGather was built for %d values per rank, got %d" % (self.n, local.numel()))
-        self.parity ^= 1
-        half = self.world * max(self.n, 1)
-        out = self.buffer[self.parity * half:(self.parity + 1) * half]
+
+    def gather(self, local):
+        """local: device tensor of <= n float64 -> device tensor [world, n] holding every rank's values (rows of ranks that
+        passed fewer than n values keep stale tails)."""
+        self._check(local)
         if self.fallback is not None:
-            _dist().all_gather_into_tensor(out, local.contiguous(), group=self.group)
-            return out.view(self.world, -1)[:, :self.n]
-        stream = self._ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _cabi.check(self.lib.bi_peer_broadcast(_cabi.dev_ptr(local), local.numel(), _cabi.host_ptr(self.peer_ptrs), self.world,
-                                               self.parity * half + self.rank * self.n, stream), "bi_peer_broadcast")
-        if wait:
-            self.handle.barrier(channel=0)
-        return out.view(self.world, -1)[:, :self.n]
+            _dist().all_gather_into_tensor(self.out, local.contiguous(), group=self.group)
+            return self.out.view(self.world, self.n)
+        _cabi.check(self.lib.bi_peer_exchange(_cabi.dev_ptr(local), local.numel(), self.n, _cabi.host_ptr(self.peer_ptrs),
+                                              self.world, self.rank, 0, None, None, _cabi.dev_ptr(self.out), self._stream()),
+                    "bi_peer_exchange")
+        self.launches += 1
+        return self.out.view(self.world, self.n)
+
+    def reduce(self, local, musum=None, status=None):
+        """Sum over ranks, accumulated in rank order ((r0 + r1) + r2) + ... on every rank -> device tensor [len(local)];
+        with musum / status (device tensors of the same length): -musum + total, -inf where status != 0
+        (the event-sharded log likelihood without priors)."""
+        import torch
+        self._check(local)
+        m = local.numel()
+        if self.fallback is not None:
+            if m != self.n:
+                raise ValueError("NCCL fallback needs exactly %d values" % self.n)
+            _dist().all_gather_into_tensor(self.out, local.contiguous(), group=self.group)
+            rows = self.out.view(self.world, self.n)
+            acc = rows[0].clone()
+            for r in range(1, self.world):
+                acc = acc + rows[r]
+            if musum is not None:
+                acc = -musum + acc
+            if status is not None:
+                acc = torch.where(status != 0, torch.full_like(acc, -float('inf')), acc)
+            self.total.copy_(acc)
+            return self.total[:m]
+        _cabi.check(self.lib.bi_peer_exchange(_cabi.dev_ptr(local), m, self.n, _cabi.host_ptr(self.peer_ptrs),
+                                              self.world, self.rank, 1, _cabi.dev_ptr(musum), _cabi.dev_ptr(status),
+                                              _cabi.dev_ptr(self.total), self._stream()), "bi_peer_exchange")
+        self.launches += 1
+        return self.total[:m]
+
+    def broadcast(self, local):
+        """Stores only (bi_peer_broadcast): this rank's values go to slot (parity, rank) of every rank without waiting for
+        anybody; the rows are complete after the next barrier().  Host-tracked parity: do NOT mix with gather() / reduce()
+        on the same object, and let at most one un-waited broadcast overtake a reader.  Returns the [world, n] view the
+        rows arrive in."""
+        self._check(local)
+        if self.fallback is not None:
+            return self.gather(local)
+        self._parity ^= 1
+        half = self.world * self.n
+        _cabi.check(self.lib.bi_peer_broadcast(_cabi.dev_ptr(local), local.numel(), _cabi.host_ptr(self.peer_ptrs),
+                                               self.world, self._parity * half + self.rank * self.n, self._stream()),
+                    "bi_peer_broadcast")
+        self.launches += 1
+        return self.buffer[self._parity * half:(self._parity + 1) * half].view(self.world, self.n)
 
 
 class PointShardedLikelihood(object):
@@ -164,7 +219,7 @@ class PointShardedLikelihood(object):
         pg = self._gathers.get(n_rows)
         if pg is None:
             pg = self._gathers[n_rows] = PeerGather(n_rows, self.group)
-        engine.peer_gather = pg
+        engine.peer_gather, engine.peer_mode = pg, 'gather'
         return engine
 
     def batch(self, params, names=None, livetime_days=None):
@@ -257,7 +312,7 @@ class ToyShardedLikelihood(object):
         if self._gather.fallback is not None and min(counts) != max(counts):
             local = self.ll.batch_toys(params[lo:hi], names, livetime_days=livetime_days)
             return gather_concat(np.asarray(local, dtype=np.float64), counts, self.group)
-        engine.peer_gather = self._gather
+        engine.peer_gather, engine.peer_mode = self._gather, 'gather'
         try:
             self.ll.batch_toys(params[lo:hi], names, livetime_days=livetime_days)
             gathered = engine.last_gathered
@@ -306,21 +361,19 @@ class EventShardedLikelihood(object):
         if not device_gather:
             logsum, musum, status, priors = self.ll.batch_parts(params, names, livetime_days=livetime_days)
             return self.combine(logsum, musum, status, priors)
-        # the shards' log sums are gathered on the device (P2P stores over NVLink) before the D2H; every rank then
-        # adds them in rank order, so all ranks hold bit-identical results
+        # ONE launch after the evaluation (bi_peer_exchange, inside the evaluation's CUDA graph): the shards' log sums go
+        # to every rank over NVLink peer memory and are added up in rank order on the device, so all ranks hold
+        # bit-identical results; -sum(mu) is added there too, the priors (Python callables) here
         pg = self._gathers.get(n_points)
         if pg is None:
             pg = self._gathers[n_points] = PeerGather(n_points, self.group)
-        engine.peer_gather = pg
+        engine.peer_gather, engine.peer_mode = pg, 'sum'
         try:
             logsum, musum, status, priors = self.ll.batch_parts(params, names, livetime_days=livetime_days)
-            rows = engine.last_gathered
+            total = engine.last_total
         finally:
             engine.peer_gather = None
-        total = np.where(status != 0, 0.0, rows[0])
-        for r in range(1, len(rows)):
-            total = total + np.where(status != 0, 0.0, rows[r])
-        return np.where(status != 0, -np.inf, priors + (-musum + total))
+        return np.where(status != 0, -np.inf, priors + total)
 
     def __call__(self, livetime_days=None, **kwargs):
         names = list(kwargs.keys())

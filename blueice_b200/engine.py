@@ -284,8 +284,10 @@ class UnbinnedEngine(_EngineBase):
         self.ps_anchor = None
         self.force_kernel = None      # None (auto) | 'stream' | 'grouped'  (tests / bench)
         self._fused_cache = {}        # batch size -> staging buffers, workspace, prebuilt C arguments
-        self.peer_gather = None       # distributed.PeerGather: all-gather the logl rows on the device (point sharding)
-        self.last_gathered = None
+        self.peer_gather = None       # distributed.PeerGather: the exchange step of a sharded evaluation, issued on the
+        self.peer_mode = 'gather'     # device right after finalize ('gather': logl rows of all ranks, point sharding;
+        self.last_gathered = None     # 'sum': rank-ordered sum of the shards' log sums, event sharding)
+        self.last_total = None
         self.full_grid_layout = os.environ.get('BI_MMA_NO_TENSORMAP') is None   # rows = [G][S][ld] anchor tensor
 
     # -- set_data -------------------------------------------------------------------------------
@@ -430,7 +432,7 @@ class UnbinnedEngine(_EngineBase):
         torch = self.torch
         D, S = self.grid.n_dims, self.n_sources
         n_in = P * D + P * S + (P if has_scale else 0) + (P * S if has_eff else 0)
-        st = {}
+        st = {"P": P}
         st["pin_in"] = torch.empty(max(n_in, 1), dtype=torch.float64, pin_memory=True)
         st["pin_in_np"] = st["pin_in"].numpy()
         st["dev_in"] = torch.empty(max(n_in, 1), dtype=torch.float64, device=self.device)
@@ -456,17 +458,47 @@ class UnbinnedEngine(_EngineBase):
         self._fused_cache[key] = st
         return st
 
+    def _fused_sequence(self, st, n_f, stream):
+        """Everything the device does for one e2e evaluation of a cached state, issued on `stream`: H2D of the staged
+        inputs, the fused call (four launches), the exchange step of a sharded evaluation (one launch), D2H."""
+        P = st["P"]
+        if st["n_in"]:
+            st["dev_in"].copy_(st["pin_in"], non_blocking=True)
+        _cabi.check(st["fn"](*st["args"], ctypes.c_void_p(stream.cuda_stream)), "bi_unbinned_ll_batch")
+        pg = self.peer_gather
+        if pg is not None:
+            if self.peer_mode == 'sum':
+                # event sharding: -musum + (rank-ordered sum of the shards' log sums), -inf where the point is unphysical
+                x = pg.reduce(st["out_f"][P:2 * P], st["out_f"][2 * P:3 * P], st["out_i"])
+            else:
+                x = pg.gather(st["out_f"][:P]).reshape(-1)          # point sharding: the logl rows of all ranks
+            self._pin_x(st, x.numel()).copy_(x, non_blocking=True)
+        st["pin_f"][:n_f].copy_(st["out_f"][:n_f], non_blocking=True)
+        st["pin_i"].copy_(st["out_i"], non_blocking=True)
+
+    def _pin_x(self, st, n):
+        """Pinned landing buffer of the exchange results of a cached state (one per size)."""
+        pin_x = st.get(("pin_x", n))
+        if pin_x is None:
+            pin_x = st[("pin_x", n)] = self.torch.empty(n, dtype=self.torch.float64, pin_memory=True)
+        return pin_x
+
     def _fused_graph(self, st, n_f):
         """CUDA graph of the e2e sequence of this cached state (None: not built yet, disabled, or capture failed).
         Built on the SECOND call with a state, so that one-off evaluations and the lazily initialised kernel
-        attributes of the first call stay outside the capture."""
+        attributes of the first call stay outside the capture.  A sharded evaluation captures its exchange launch too
+        (bi_peer_exchange keeps its epoch on the device); every rank issues one exchange per call either way."""
         if not _E2E_GRAPHS:
             return None
-        key = ("graph", n_f)
+        pg = self.peer_gather
+        if pg is not None and pg.fallback is not None:
+            return None                                             # NCCL fallback: stay eager
+        key = ("graph", n_f, None if pg is None else (id(pg), self.peer_mode))
         if key in st:
             return st[key]
-        st["calls"] = st.get("calls", 0) + 1
-        if st["calls"] < 2:
+        ckey = ("calls",) + key[1:]
+        st[ckey] = st.get(ckey, 0) + 1
+        if st[ckey] < 2:
             return None
         torch = self.torch
         graph = None
@@ -474,12 +506,7 @@ class UnbinnedEngine(_EngineBase):
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
-                cap = torch.cuda.current_stream(self.device)
-                if st["n_in"]:
-                    st["dev_in"].copy_(st["pin_in"], non_blocking=True)
-                _cabi.check(st["fn"](*st["args"], ctypes.c_void_p(cap.cuda_stream)), "bi_unbinned_ll_batch")
-                st["pin_f"][:n_f].copy_(st["out_f"][:n_f], non_blocking=True)
-                st["pin_i"].copy_(st["out_i"], non_blocking=True)
+                self._fused_sequence(st, n_f, torch.cuda.current_stream(self.device))
             graph = g
         except Exception:                                           # capture not possible here: stay on the eager path
             graph = None
@@ -491,7 +518,7 @@ class UnbinnedEngine(_EngineBase):
         return graph
 
     def evaluate_fused(self, zs, mult, scale, eff, return_status, return_parts):
-        """The e2e path of the fused engine: stage -> H2D -> one C call -> D2H -> sync."""
+        """The e2e path of the fused engine: stage -> H2D -> one C call (-> exchange) -> D2H -> sync."""
         P = len(mult)
         st = self._fused_state(P, scale is not None, eff is not None)
         pin = st["pin_in_np"]
@@ -506,31 +533,27 @@ class UnbinnedEngine(_EngineBase):
                 o += size
         stream = self.torch.cuda.current_stream(self.device)
         n_f = 3 * P if return_parts else P
-        graph = self._fused_graph(st, n_f) if self.peer_gather is None else None
+        pg = self.peer_gather
+        graph = self._fused_graph(st, n_f)
         if graph is not None:
-            # H2D, the four launches and the two D2H copies replayed as ONE CUDA graph (built on the second call of a
-            # batch size): one launch instead of seven API calls on the host, tighter dependencies on the device
+            # H2D, the four launches, the exchange and the D2H copies replayed as ONE CUDA graph (built on the second call
+            # of a batch size): one launch instead of seven API calls on the host, tighter dependencies on the device
             graph.replay()
         else:
-            if st["n_in"]:
-                st["dev_in"].copy_(st["pin_in"], non_blocking=True)
-            _cabi.check(st["fn"](*st["args"], ctypes.c_void_p(stream.cuda_stream)), "bi_unbinned_ll_batch")
-            st["pin_f"][:n_f].copy_(st["out_f"][:n_f], non_blocking=True)
-            st["pin_i"].copy_(st["out_i"], non_blocking=True)
-        self.launches += 4 if self.n_super > 0 else 2
-        gathered_pin = None
-        if self.peer_gather is not None:
-            # sharded evaluation: this rank's logl rows (point sharding) or log sums (event sharding, return_parts)
-            # go to every rank over NVLink before the D2H
-            g = self.peer_gather.gather(st["out_f"][P:2 * P] if return_parts else st["out_f"][:P])
-            gathered_pin = st.get("pin_g")
-            if gathered_pin is None or gathered_pin.numel() != g.numel():
-                gathered_pin = st["pin_g"] = self.torch.empty(g.numel(), dtype=self.torch.float64, pin_memory=True)
-            gathered_pin.view(g.shape).copy_(g, non_blocking=True)
+            self._fused_sequence(st, n_f, stream)
+        self.launches += (4 if self.n_super > 0 else 2) + (0 if pg is None or pg.fallback is not None else 1)
         stream.synchronize()
-        self.last_gathered = None if gathered_pin is None else gathered_pin.numpy().reshape(self.peer_gather.world, -1).copy()
+        self.last_gathered = self.last_total = None
+        n_x = 0
+        if pg is not None:
+            n_x = P if self.peer_mode == 'sum' else pg.world * pg.n
+            x = self._pin_x(st, n_x).numpy()
+            if self.peer_mode == 'sum':
+                self.last_total = x[:P].copy()
+            else:
+                self.last_gathered = x.reshape(pg.world, -1).copy()
         self.last_h2d_bytes = st["n_in"] * 8
-        self.last_d2h_bytes = n_f * 8 + P * 4 + (0 if gathered_pin is None else gathered_pin.numel() * 8)
+        self.last_d2h_bytes = n_f * 8 + P * 4 + n_x * 8
         res = st["pin_f_np"]
         if return_parts:
             return res[P:2 * P].copy(), res[2 * P:3 * P].copy(), st["pin_i_np"].copy()
@@ -1076,7 +1099,9 @@ class TemplateUnbinnedEngine(_EngineBase):
         self.n_datasets = 0
         self.ev_bin = None
         self.peer_gather = None       # distributed.PeerGather (sharded evaluations), see UnbinnedEngine
+        self.peer_mode = 'gather'
         self.last_gathered = None
+        self.last_total = None
         self._graphs = {}             # CUDA graphs of repeated evaluations, per (schedule, batch shape)
         self._toy_schedule = None
 
@@ -1355,12 +1380,21 @@ class TemplateUnbinnedEngine(_EngineBase):
         nbytes = total * 8
         out_pin = self.ws.get("d2h", 3 * P, torch.float64, pinned=True)
         st_pin = self.ws.get("d2h_status", P, torch.int32, pinned=True)
+        pg, mode = self.peer_gather, self.peer_mode
+        n_x = 0 if pg is None else (P if mode == 'sum' else pg.world * pg.n)
+        g_pin = self.ws.get("d2h_gather", n_x, torch.float64, pinned=True) if pg is not None else None
         state = {}
 
         def device_sequence():
-            """H2D of the staged inputs, bi_template_ll_batch, D2H of the results: everything the device does."""
+            """H2D of the staged inputs, bi_template_ll_batch, the exchange step of a sharded evaluation, D2H of the
+            results: everything the device does."""
             dev.copy_(pin, non_blocking=True)
             o, logl, logsum = self.run_one_call(P, sched, views[0], views[1], views[2], views[3])
+            if pg is not None:
+                # sharded evaluation, exchanged over NVLink peer memory by one launch: the rank-ordered sum of the
+                # shards' log sums (event sharding; pair order) or the logl rows of all ranks (point / toy sharding)
+                x = pg.reduce(logsum[:P]) if mode == 'sum' else pg.gather(logl[:P]).reshape(-1)
+                g_pin.copy_(x, non_blocking=True)
             out_pin[:P].copy_(logl, non_blocking=True)
             if return_parts:
                 out_pin[P:2 * P].copy_(logsum, non_blocking=True)
@@ -1368,11 +1402,12 @@ class TemplateUnbinnedEngine(_EngineBase):
             st_pin.copy_(o["status"], non_blocking=True)
             state["o"], state["logl"], state["logsum"] = o, logl, logsum
 
-        # ---- repeated evaluations of one schedule replay the sequence as ONE CUDA graph (not when sharded: the peer
-        # gather below waits for other ranks)
+        # ---- repeated evaluations of one schedule replay the sequence as ONE CUDA graph (sharded evaluations too: the
+        # exchange launch keeps its epoch on the device; every rank issues one exchange per call, eager or replayed)
         graph = None
-        if _E2E_GRAPHS and self.peer_gather is None:
-            gkey = (id(sched), P, sizes, return_parts)
+        use_graphs = _E2E_GRAPHS and (pg is None or pg.fallback is None)
+        if use_graphs:
+            gkey = (id(sched), P, sizes, return_parts, None if pg is None else (id(pg), mode))
             entry = self._graphs.get(gkey)
             if entry is None:
                 if len(self._graphs) >= 8:
@@ -1399,34 +1434,36 @@ class TemplateUnbinnedEngine(_EngineBase):
             elif entry["graph"]:
                 entry["graph"], entry["calls"] = None, 1             # a workspace buffer moved: capture again later
         t_start = _time.perf_counter()
+        n_launch = ((2 + (2 if self.mode == 'mixture' else 1)) if sched["n_units"] else 2) + \
+            (0 if pg is None or pg.fallback is not None else 1)
         if graph is not None:
             graph.replay()
-            self.launches += (2 + (2 if self.mode == 'mixture' else 1)) if sched["n_units"] else 2
+            self.launches += n_launch
         else:
             device_sequence()
-        g_pin = None
-        logl, logsum = state.get("logl"), state.get("logsum")
-        if self.peer_gather is not None:
-            # sharded evaluation: the log sums (event sharding) or logl rows of all ranks, gathered over NVLink
-            g = self.peer_gather.gather(logsum[:P] if return_parts else logl[:P])
-            g_pin = self.ws.get("d2h_gather", g.numel(), torch.float64, pinned=True)
-            g_pin.view(g.shape).copy_(g, non_blocking=True)
+            if pg is not None and pg.fallback is None:
+                self.launches += 1
         torch.cuda.current_stream(self.device).synchronize()
-        if _E2E_GRAPHS and self.peer_gather is None:
+        if use_graphs:
             self._graphs[gkey]["last_s"] = _time.perf_counter() - t_start
         self.last_h2d_bytes = nbytes
-        self.last_d2h_bytes = n_f * 8 + P * 4 + (0 if g_pin is None else g_pin.numel() * 8)
+        self.last_d2h_bytes = n_f * 8 + P * 4 + n_x * 8
         res = out_pin.numpy().copy()
         status = st_pin.numpy().copy()
         ll, ls = res[:P], res[P:2 * P]
-        gathered = None if g_pin is None else g_pin.numpy().reshape(self.peer_gather.world, -1).copy()
+        inv = None
         if order is not None:                                               # pair order -> point order
             inv = np.empty(P, dtype=np.int64)
             inv[order] = np.arange(P)
             ll, ls = ll[inv], ls[inv] if return_parts else ls
-            if gathered is not None:
-                gathered = gathered[:, inv]
-        self.last_gathered = gathered
+        self.last_gathered = self.last_total = None
+        if pg is not None and mode == 'sum':
+            total = g_pin.numpy()[:P].copy()                                # rank-ordered sum of the log sums, pair order
+            total = total if inv is None else total[inv]
+            self.last_total = np.where(status != 0, -np.inf, -res[2 * P:3 * P] + total)
+        elif pg is not None:
+            gathered = g_pin.numpy().reshape(pg.world, -1).copy()
+            self.last_gathered = gathered if inv is None else np.concatenate([gathered[:, :P][:, inv], gathered[:, P:]], axis=1)
         if return_parts:
             return ls, res[2 * P:], status
         return (ll, status) if return_status else ll

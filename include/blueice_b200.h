@@ -483,13 +483,30 @@ int bi_binned_pmfs(const double* pmf_anchor_dev, const double* n_model_anchor_de
                    const double* sum_t_dev, double* pmf_out_dev, int64_t ld_out, void* stream);
 
 /*
- * The all-gather of a point / toy sharded evaluation as plain P2P stores over NVLink: every
- * rank stores its n results into the gather buffer of EVERY rank at its own slot,
- *     peer[r][dst_offset + i] = src_dev[i]     for all r < world,
- * peer_ptrs_host[r] being rank r's gather buffer mapped into THIS process (peer-mapped device memory, e.g. torch
- * symmetric memory's buffer_ptrs).  No collective launch; the caller follows it with a cross-GPU barrier before
- * anybody reads the gathered rows.  world <= 16.
+ * The exchange steps of the sharded evaluations (the reference has no multi-device path) over
+ * NVLink / NVSwitch PEER MEMORY: every rank maps every rank's exchange buffer into its own address space (e.g. torch
+ * symmetric memory's buffer_ptrs) and passes the mapped pointers as peer_ptrs_host[world]; world <= 16.
+ *
+ * bi_peer_exchange: ONE launch = the whole exchange.  (1) this rank's n_src values are stored into every rank's buffer
+ * (P2P stores), (2) this rank's flag is released on every rank, (3) the kernel waits (acquire) until every rank's flag has
+ * arrived here, (4) epilogue:
+ *   mode 0 (gather, point / toy sharding): out_dev[r * n + i] = value i of rank r          (out_dev: world * n doubles)
+ *   mode 1 (sum, event sharding):          total_i = ((v_0i + v_1i) + v_2i) + ... in RANK ORDER (bit-identical on every
+ *                                          rank, independent of timing); out_dev[i] = -musum_dev[i] + total_i
+ *                                          (likelihood.py:690), -inf where status_dev[i] != 0; musum_dev / status_dev may
+ *                                          be NULL (then out_dev[i] = total_i)
+ * The epoch counter lives in the buffer itself, so the launch can be captured in a CUDA graph and replayed; every rank
+ * must issue the same sequence of exchanges on a buffer.  The buffer holds bi_peer_exchange_words(world, n) 8-byte
+ * words: data [2][world][n] (two slots used alternately), flag [world], local [4] (epoch, two CTA counters, error: set
+ * to the epoch if a peer did not arrive within 20 s).  It must be ZEROED, followed by one cross-rank barrier, before
+ * the first exchange.  Results a caller reads out of out_dev are stream-ordered after the launch.
+ *
+ * bi_peer_broadcast: step (1) alone, peer[r][dst_offset + i] = src_dev[i]; the caller provides the barrier.
  */
+int64_t bi_peer_exchange_words(int32_t world, int64_t n);
+int bi_peer_exchange(const double* src_dev, int64_t n_src, int64_t n, const uint64_t* peer_ptrs_host,
+                     int32_t world, int32_t rank, int32_t mode, const double* musum_dev,
+                     const int32_t* status_dev, double* out_dev, void* stream);
 int bi_peer_broadcast(const double* src_dev, int64_t n, const uint64_t* peer_ptrs_host, int32_t world,
                       int64_t dst_offset, void* stream);
 
