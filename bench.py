@@ -53,6 +53,7 @@ def measured_peaks():
 # reference arm / cpu baseline: the oracle pipeline on the host cores
 # ------------------------------------------------------------------------------------------------
 _ORACLE = None
+_REF_LL = None
 
 
 def build_oracle(n_events, seed=1):
@@ -64,57 +65,123 @@ def build_oracle(n_events, seed=1):
     return orc, len(x), time.perf_counter() - t0
 
 
+def build_reference_ll(n_events, seed=1):
+    """The config-2 workload through the API of the UNMODIFIED reference package (oracle/_ref: a copy of
+    /root/reference/blueice made by __graft_entry__.build(), with the two test-only stand-ins for multihist /
+    atomicwrites).  Returns (lf, n_events, set_data seconds) or None when oracle/_ref is absent."""
+    from oracle.build_ref import import_reference
+    if import_reference() is None:
+        return None
+    from blueice.likelihood import UnbinnedLogLikelihood          # the reference
+    from blueice.source import HistogramPdfSource
+    from multihist import Histdd
+    os.chdir(tempfile.mkdtemp(prefix="bi_ref_"))                  # the reference writes ./pdf_cache
+    axes, edges, templates, mus = wl.c2_arrays(N_SOURCES, N_SHAPE, ANCHORS, BINS)
+    space, params = ['cs1', 'cs2'], ['shift%d' % (i + 1) for i in range(N_SHAPE)]
+    cls = wl.array_source_class(HistogramPdfSource, Histdd, axes, edges, space, mus, templates, None, params)
+    lf = UnbinnedLogLikelihood(wl.array_model_config(cls, edges, space, N_SOURCES, params, 'linear'))
+    for s_ in range(N_SOURCES):
+        lf.add_rate_parameter('src%d' % s_)
+    for p_ in params:
+        lf.add_shape_parameter(p_, ANCHORS)
+    lf.prepare()
+    x, y = wl.c2_events(templates, mus, edges, n_events, seed)
+    d = np.zeros(len(x), dtype=[('cs1', float), ('cs2', float), ('source', int)])
+    d['cs1'], d['cs2'] = x, y
+    t0 = time.perf_counter()
+    lf.set_data(d)
+    return lf, len(x), time.perf_counter() - t0
+
+
+def _reference_points(lf, zs, mult):
+    out = np.empty(len(zs))
+    for i in range(len(zs)):
+        kw = {'shift%d' % (j + 1): float(zs[i, j]) for j in range(N_SHAPE)}
+        kw.update({'src%d_rate_multiplier' % j: float(mult[i, j]) for j in range(N_SOURCES)})
+        out[i] = lf(**kw)
+    return out
+
+
 def _oracle_chunk(args):
     zs, mult = args
+    if _REF_LL is not None:
+        return _reference_points(_REF_LL, zs, mult)
     return _ORACLE.batch(zs, mult)
 
 
 def cpu_baseline_single_core(n_events, budget_s=12.0):
-    """Oracle (kind 'port') on ONE core (the reference evaluation path is single-threaded)."""
-    orc, n, set_data_s = build_oracle(n_events)
+    """The reference evaluation path on ONE core (it is single-threaded): the unmodified reference package when
+    oracle/_ref is present (kind 'reference'), else the oracle port (kind 'port')."""
     zs, mult = wl.scan_points(4096, N_SHAPE, N_SOURCES, seed=2)
-    orc(zs[0], mult[0])                                     # warm-up
+    ref = build_reference_ll(n_events)
+    if ref is not None:
+        lf, n, set_data_s = ref
+        kind, what = "reference", "unmodified reference package (oracle/_ref) called point by point, lf(**params)"
+
+        def one(i):
+            return _reference_points(lf, zs[i:i + 1], mult[i:i + 1])[0]
+    else:
+        orc, n, set_data_s = build_oracle(n_events)
+        kind, what = "port", "oracle.pipeline.UnbinnedOracle (scipy RegularGridInterpolator + NumPy, as the reference)"
+
+        def one(i):
+            return orc(zs[i], mult[i])
+    one(0)                                                  # warm-up
     done, t0 = 0, time.perf_counter()
     while done < len(zs) and time.perf_counter() - t0 < budget_s:
-        orc(zs[done], mult[done])
+        one(done)
         done += 1
     dt = time.perf_counter() - t0
-    return {"value": done * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "%d of the 4096 scan points x %d events, %.1f s; oracle.pipeline.UnbinnedOracle "
-                      "(scipy RegularGridInterpolator + NumPy, as the reference); set_data %.2f s"
-                      % (done, n, dt, set_data_s),
+    return {"value": done * n / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "%d of the 4096 scan points x %d events, %.1f s; %s; set_data %.2f s"
+                      % (done, n, dt, what, set_data_s),
             "ms_per_point": 1e3 * dt / done, "set_data_s": set_data_s}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) with all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores -- the unmodified
+    reference package (oracle/_ref) when present, else the oracle port -- on the own arm's workload: every step is the
+    whole 4096-point scan of config 2, its points dealt out to one worker process per core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    global _ORACLE
+    global _ORACLE, _REF_LL
     n_events = args.events
-    _ORACLE, n, set_data_s = build_oracle(n_events)
+    ref = build_reference_ll(n_events)
+    check = None
+    if ref is not None:
+        _REF_LL, n, set_data_s = ref
+        kind = "reference"
+        what = "unmodified reference package (oracle/_ref: /root/reference/blueice + stand-ins for multihist / atomicwrites)"
+        # the oracle restatement must give the reference's numbers (bit for bit) on this very workload
+        orc, _, _ = build_oracle(n_events)
+        z4, m4 = wl.scan_points(4, N_SHAPE, N_SOURCES, seed=2)
+        check = bool(np.array_equal(_reference_points(_REF_LL, z4, m4), orc.batch(z4, m4)))
+    else:
+        _ORACLE, n, set_data_s = build_oracle(n_events)
+        kind, what = "port", "oracle.pipeline.UnbinnedOracle"
     cores = os.cpu_count() or 1
-    per_worker = max(2, args.ref_points_per_core)
-    zs, mult = wl.scan_points(cores * per_worker, N_SHAPE, N_SOURCES, seed=2)
+    n_points = args.points
+    zs, mult = wl.scan_points(n_points, N_SHAPE, N_SOURCES, seed=2)
     chunks = [(zs[i::cores], mult[i::cores]) for i in range(cores)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        for _ in range(args.warmup):
+        for _ in range(min(args.warmup, 1)):                    # a CPU has no clocks to ramp: one warm-up pass
             pool.map(_oracle_chunk, chunks)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             pool.map(_oracle_chunk, chunks)
         dt = time.perf_counter() - t0
     value = args.steps * len(zs) * n / dt
-    sample = ("%d points x %d events per step over %d worker processes (disjoint point chunks); "
-              "oracle.pipeline.UnbinnedOracle; set_data %.2f s" % (len(zs), n, cores, set_data_s))
+    sample = ("%d points x %d events per step (the whole scan) over %d worker processes (disjoint point chunks); %s; "
+              "set_data %.2f s" % (len(zs), n, cores, what, set_data_s))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(n, len(zs)),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "reference_equals_oracle_port": check},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -481,7 +548,55 @@ def other_configs(args, rank, world, device):
         "n_events": int(len(d1)), "single_call_latency_us": lat * 1e6, "single_call_point_events_per_s": len(d1) / lat,
         "batch_points": 4096, "batch_ms": tb * 1e3, "batch_point_events_per_s": 4096 * len(d1) / tb,
         "batch_equals_single_call": bool(b1[0] == ll1(**kw1))}
+    # the caller this regime lives in: one_parameter_interval (inference.py:332-389) = a brentq search whose every step is
+    # a conditional fit of sequential ll(**params) calls
+    n_calls = [0]
+    inner_call = type(ll1).__call__
+
+    def counting_call(self, *a_, **k_):
+        n_calls[0] += 1
+        return inner_call(self, *a_, **k_)
+    type(ll1).__call__ = counting_call
+    limit, interval_s = float('nan'), float('nan')
+    try:
+        t0 = time.perf_counter()
+        limit = ll1.one_parameter_interval('s0_rate_multiplier', 2.0, kind='upper')
+        interval_s = time.perf_counter() - t0
+    except Exception as exc:
+        out["config1_gaussian"]["one_parameter_interval_error"] = repr(exc)
+    finally:
+        type(ll1).__call__ = inner_call
+    out["config1_gaussian"]["one_parameter_interval"] = {
+        "call": "ll.one_parameter_interval('s0_rate_multiplier', 2.0, kind='upper')  (mu profiled)", "upper_limit": float(limit),
+        "seconds": interval_s, "likelihood_calls": n_calls[0], "us_per_call": 1e6 * interval_s / max(n_calls[0], 1)}
     if not args.skip_cpu:
+        # the same search through the unmodified reference package on the same data, when oracle/_ref travelled here
+        try:
+            from oracle.build_ref import import_reference
+            if import_reference() is not None:
+                from blueice.likelihood import UnbinnedLogLikelihood as RefLL
+                from blueice.test_helpers import conf_for_test as ref_conf
+                os.chdir(tempfile.mkdtemp(prefix="bi_ref1_"))
+                lr = RefLL(ref_conf(n_sources=1))
+                lr.add_rate_parameter('s0')
+                lr.add_shape_parameter('mu', {-2: -2, 0: 0, 2: 2})
+                lr.prepare()
+                lr.set_data(d1)
+                for _ in range(20):
+                    lr(**kw1)
+                t0 = time.perf_counter()
+                for _ in range(300):
+                    lr(**kw1)
+                ref_lat = (time.perf_counter() - t0) / 300
+                t0 = time.perf_counter()
+                ref_limit = lr.one_parameter_interval('s0_rate_multiplier', 2.0, kind='upper')
+                ref_interval_s = time.perf_counter() - t0
+                out["config1_gaussian"]["reference"] = {
+                    "what": "unmodified reference package (oracle/_ref), same data, one core",
+                    "single_call_us": ref_lat * 1e6, "one_parameter_interval_s": ref_interval_s,
+                    "upper_limit": float(ref_limit), "logl_abs_diff": float(abs(lr(**kw1) - ll1(**kw1)))}
+        except Exception as exc:                                    # the baseline leg must never break the bench line
+            out["config1_gaussian"]["reference"] = {"error": repr(exc)}
         # cpu_baseline leg for this config: the oracle port (same third-party calls as the reference), one core
         from oracle.pipeline import UnbinnedOracle
         axes1, mus1, ps1, x1 = wl.c1_arrays(seed=0)
@@ -506,39 +621,54 @@ def other_configs(args, rank, world, device):
     P3 = 256
     zs3, mult3 = wl.scan_points(P3, 3, 4, seed=31, z_range=(-1., 1.), mult_range=(0.8, 1.2))
     r3 = beng.evaluate(zs3, mult3)
-    zs_d, mult_d, _, _, _ = beng._upload_points(zs3, mult3, None, None)
-    zs_d, mult_d = zs_d.clone(), mult_d.clone()
-    dm = []
-    for k in range(6):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        beng.run_device(P3, zs_d, mult_d, None, None)
-        b.record()
-        torch.cuda.synchronize()
-        if k:
-            dm.append(a.elapsed_time(b))
-    ts = []
-    for _ in range(3):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        beng.evaluate(zs3, mult3)
-        ts.append(time.perf_counter() - t0)
     B, C3, S3 = beng.n_bins, beng.grid.n_corners, beng.n_sources
-    t_dev, t_e2e = float(np.mean(dm)) * 1e-3, float(np.mean(ts))
-    # 8 * B * (C*S + C + 1) bytes per point (pmf corners, BB-source n_model corners, observed)
-    bytes_alg = 8.0 * B * (C3 * S3 + C3 + 1) * P3
     hbm = measured_peaks()[0]["hbm_gbs"]
+    k4 = {}
+    for P in (1, P3):
+        zs_d, mult_d, _, _, _ = beng._upload_points(zs3[:P], mult3[:P], None, None)
+        zs_d, mult_d = zs_d.clone(), mult_d.clone()
+        dm = []
+        for k in range(8):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            beng.run_device(P, zs_d, mult_d, None, None)
+            b.record()
+            torch.cuda.synchronize()
+            if k > 1:
+                dm.append(a.elapsed_time(b))
+        ts = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            beng.evaluate(zs3[:P], mult3[:P])
+            ts.append(time.perf_counter() - t0)
+        k4[P] = (float(np.mean(dm)) * 1e-3, float(np.mean(ts)))
+    # the Beeston-Barlow pass A alone at P = 1 (the HBM-bound kernel: it streams exactly SURVEY.md 8d's per-point bytes,
+    # 8 B (C S + C + 1): pmf corners, calibration-count corners, observed), timed by CUDA events around a launch sequence
+    # that is identical except for that kernel being skipped is not possible through the C-ABI, so the kernel's own
+    # duration comes from the committed ncu launch list (profiles/r2_k4_ncu.md); here: whole evaluations
+    bytes_pt = 8.0 * B * (C3 * S3 + C3 + 1)
+    flop_pt = float(B) * (2 * C3 * S3 + 60)
+    t1, t256 = k4[1][0], k4[P3][0]
     out["config3_binned_bb"] = {
         "workload": "BinnedLogLikelihood + Beeston-Barlow: 200x200x20 bins, 4 sources, 3 shape parameters x 3 anchors "
-                    "(27 anchors), %d-point scan" % P3,
-        "kernel": "k_binned_pass<1> + k_binned_pass<2> (two passes over the bins: BB roots, then Poisson terms)",
+                    "(27 anchors); one point and a %d-point scan" % P3,
+        "kernel": "k_binned_tile<1> + k_binned_tile<2> (anchor rows of a 256-bin tile staged in shared memory by TMA bulk "
+                  "copies once per group of <= 32 points of one hypercube cell; pass A keeps t_b, pass B adds the Poisson terms)",
         "points": P3, "bins": int(B), "finite_results": int(np.isfinite(r3).sum()),
-        "device": {"ms": t_dev * 1e3, "point_bins_sources_per_s": P3 * B * S3 / t_dev},
-        "e2e": {"ms": t_e2e * 1e3, "point_bins_sources_per_s": P3 * B * S3 / t_e2e},
-        "roofline": {"bound": "hbm", "bytes_alg": bytes_alg, "achieved": bytes_alg / t_dev / 1e9, "peak": hbm,
-                     "unit": "GB/s", "frac": bytes_alg / t_dev / 1e9 / hbm,
-                     "note": "whole 5-launch evaluation; the BB form reads the corner tensors in both passes, so the "
-                             "single-pass algorithmic bytes cap this fraction near 0.5"},
+        "single_point": {"device_ms": t1 * 1e3, "e2e_ms": k4[1][1] * 1e3,
+                         "roofline": {"bound": "hbm", "bytes_alg": bytes_pt, "achieved": bytes_pt / t1 / 1e9, "peak": hbm,
+                                      "unit": "GB/s", "frac": bytes_pt / t1 / 1e9 / hbm,
+                                      "note": "whole 5-launch evaluation (schedule, pass A, total, pass B, total) against "
+                                              "SURVEY.md 8d's per-point bytes; pass A alone streams those bytes"}},
+        "scan": {"device_ms": t256 * 1e3, "e2e_ms": k4[P3][1] * 1e3, "point_bins_sources_per_s": P3 * B * S3 / t256,
+                 "roofline": {"bound": "fp64 pipe (shared-data scan: the %d points read one anchor tensor set of %.2f GB through "
+                                       "L2 / shared memory, HBM does not bind)" % (P3, 8.0 * B * 27 * (S3 + 1) / 1e9),
+                              "flops_alg": flop_pt * P3, "achieved_tflops": flop_pt * P3 / t256 / 1e12,
+                              "note": "SURVEY.md 8d's flop count (2 C S + ~60 per point-bin); division, sqrt and log expand to "
+                                      "~20-45 FP64 instructions each and the reference's separately rounded multiply-adds "
+                                      "cannot be fused, so the instruction-level pipe utilisation is in the ncu summary",
+                              "dram_bytes_shared": 8.0 * B * 27 * (S3 + 1)}},
         "build_s": build_s}
     del beng
     torch.cuda.empty_cache()

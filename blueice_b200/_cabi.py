@@ -44,6 +44,11 @@ SIGNATURES = {
                                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                             _c_void_p, _i64, _i64, _f64, _i32, _c_void_p, _i64,
                                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "bi_unbinned_small_ok": (_i32, [_i32, _i32, _i64, _i64]),
+    "bi_unbinned_ll_small": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _i64,
+                                            _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                            _c_void_p, _i64, _i64, _f64,
+                                            _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_sourcewise_terms": (_i32, [_i32, _c_void_p]),
     "bi_point_setup_sourcewise": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _i32, _c_void_p, _c_void_p, _i64,
                                                  _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
@@ -88,6 +93,7 @@ SIGNATURES = {
     "bi_histogramdd": (ctypes.c_int, [_i32, _c_void_p, _c_void_p, _c_void_p, _i64, _i64, _c_void_p,
                                       _c_void_p, _c_void_p]),
     "bi_binned_scratch_doubles": (_i64, [_i64, _i64]),
+    "bi_binned_sum_t_offset": (_i64, [_i64, _i64]),
     "bi_binned_ll_batch": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _i64, _i32, _i32, _i32,
                                           _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                           _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),

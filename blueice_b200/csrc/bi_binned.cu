@@ -17,7 +17,11 @@
 //   MODE 0  no Beeston-Barlow: lambda_b, log pmf, partial sums
 //   MODE 1  BB pass A: t_b = A_b * w_b, partial sums of t (needs sum_b a_b, morphed from per-anchor sums)
 //   MODE 2  BB pass B: pmf_i' = t_b / sum t, mu_i' = sum t * p_cal, lambda_b, log pmf, partial sums
+#include <stdlib.h>
+#include <string.h>
+
 #include "bi_common.cuh"
+#include "bi_tma.cuh"
 
 struct BiBinnedArgs {
     const double* pmf_anchor;      // [G, S, ld]
@@ -34,6 +38,15 @@ struct BiBinnedArgs {
     int32_t* flags;                // [P]
     int64_t ld, n_bins, n_points, n_chunks, obs_stride;
     int32_t S, C, bb_source;
+    // tiled kernels (k_binned_tile): schedule written by bi_unbinned_plan, per-bin scratch, per-block sums
+    const int32_t* group_points;   // [P] point indices, cell-major
+    const int32_t* groups;         // [n_groups, 4] (first, count, -, -): points of a group share their hypercube cell
+    const int32_t* header;         // header[0] = n_groups
+    double* tbuf;                  // [P, ld] t_b = A_b * w_b of the Beeston-Barlow pass (written by MODE 1, read by MODE 2)
+    double* blockval;              // [P, n_blocks] tree-reduced sums of 32-bin blocks
+    int64_t n_blocks, n_tiles, tb_ld;
+    int32_t tile;                  // bins per tile: 128 or 256
+    int32_t store_terms;           // MODE 1: keep all S terms of lambda_b per (point, bin) in tbuf [P, BI_BIN_STORE_S, tb_ld]
 };
 
 __device__ __forceinline__ double bi_morph_value(const double* __restrict__ base, int64_t row_stride, int64_t off,
@@ -96,6 +109,31 @@ __device__ __forceinline__ void bi_bb_roots(double a, double p, double U, double
     const double den = __dmul_rn(__dmul_rn(2.0, p), __dadd_rn(p, 1.0));     // 2*p*(p + 1)
     *r1 = __ddiv_rn(__dsub_rn(lin, sq), den);
     *r2 = __ddiv_rn(__dadd_rn(lin, sq), den);
+}
+
+// the same arithmetic with root 1 left undivided: returns den, *x1 = numerator of root 1 (root1 = x1 / den), *r2 = root 2
+__device__ __forceinline__ double bi_bb_roots_lazy(double a, double p, double U, double d, double* x1, double* r2) {
+    const double U2 = __dmul_rn(U, U), p2 = __dmul_rn(p, p), a2 = __dmul_rn(a, a), d2 = __dmul_rn(d, d);
+    const double twoU = __dmul_rn(2.0, U);
+    double disc = __dmul_rn(U2, p2);
+    disc = __dadd_rn(disc, __dmul_rn(__dmul_rn(2.0, U2), p));
+    disc = __dadd_rn(disc, U2);
+    disc = __dadd_rn(disc, __dmul_rn(__dmul_rn(twoU, a), p2));
+    disc = __dadd_rn(disc, __dmul_rn(__dmul_rn(twoU, a), p));
+    disc = __dsub_rn(disc, __dmul_rn(__dmul_rn(twoU, d), p2));
+    disc = __dsub_rn(disc, __dmul_rn(__dmul_rn(twoU, d), p));
+    disc = __dadd_rn(disc, __dmul_rn(a2, p2));
+    disc = __dadd_rn(disc, __dmul_rn(__dmul_rn(__dmul_rn(2.0, a), d), p2));
+    disc = __dadd_rn(disc, __dmul_rn(d2, p2));
+    const double sq = sqrt(disc);
+    double lin = __dmul_rn(-U, p);
+    lin = __dsub_rn(lin, U);
+    lin = __dadd_rn(lin, __dmul_rn(a, p));
+    lin = __dadd_rn(lin, __dmul_rn(d, p));
+    const double den = __dmul_rn(__dmul_rn(2.0, p), __dadd_rn(p, 1.0));
+    *x1 = __dsub_rn(lin, sq);
+    *r2 = __ddiv_rn(__dadd_rn(lin, sq), den);
+    return den;
 }
 
 template <int MODE>
@@ -223,6 +261,325 @@ __global__ void __launch_bounds__(256) k_binned_pass(const __grid_constant__ BiB
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tiled form: the anchor rows of a bin tile live in shared memory, staged ONCE per (tile, point group) by 1-D TMA bulk
+// copies, and every point of the group (points that share their hypercube cell, bi_unbinned_plan) is evaluated on them.
+// One CTA per task (tile-major, so the cells of a scan find the tile's anchors in L2); inside, one warp per
+// (point, 32-bin block), lane = bin.  The per-bin arithmetic is exactly that of k_binned_pass (reference operation
+// order, separately rounded); the sum over the bins of a block is the same xor tree, and the 16 block sums of a
+// 512-bin superblock are added sequentially by k_canonical_total_blocks -- so results are bit-identical to k_binned_pass.
+//   MODE 0  no Beeston-Barlow: stages S rows per corner
+//   MODE 1  BB pass A: stages S + 1 rows per corner (pmfs + calibration counts); t_b -> tbuf, block sums of t
+//   MODE 2  BB pass B: stages the S - 1 pmf rows of the other sources; t_b from tbuf; block sums of log pmf
+// ---------------------------------------------------------------------------------------------
+#define BI_BIN_TILE 256                 /* largest tile: 8 blocks of 32 bins (the kernel runs 128- or 256-bin tiles) */
+#define BI_BIN_STORE_S 8                /* stored-terms form of the Beeston-Barlow passes: up to 8 sources */
+#define BI_BIN_GROUP_POINTS 32          /* points per group */
+
+// byte offset of the staged rows inside the dynamic shared memory of k_binned_tile (tables first, rows 128-byte aligned)
+__host__ __device__ inline int bi_bin_rows_offset(int C, int S) {
+    return (128 + (BI_BIN_GROUP_POINTS * (C + S + 4)) * 8 + (BI_BIN_GROUP_POINTS + C) * 4 + 127) & ~127;
+}
+
+// morph of staged row kind k at tile offset off: rows[(k * C + c) * NB + off] over the corners c (compile-time stride:
+// the corner loop costs no address arithmetic), accumulated like bi_morph_value
+template <int CT, int NB>   // CT = compile-time corner count (1, 2, 4, 8) or 0: run-time C
+__device__ __forceinline__ double bi_morph_smem(const double* __restrict__ rows_k, const double* __restrict__ w, int C) {
+    const int n_c = CT ? CT : C;
+    if (n_c == 1) return rows_k[0];
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < n_c; ++c) acc = __dadd_rn(acc, __dmul_rn(rows_k[c * NB], w[c]));
+    return acc;
+}
+
+// dynamic shared memory of k_binned_tile: two stages (the next task's tile is fetched while the current one is evaluated),
+// each = tables (bi_bin_rows_offset bytes: mbarrier, weights, mus, per-point constants, point indices, corners) + rows
+__host__ __device__ inline int bi_bin_stage_bytes(int C, int S, int n_kinds, int NB) {
+    return bi_bin_rows_offset(C, S) + C * n_kinds * NB * 8;
+}
+
+template <int MODE, int CT, int NB, int NT, int NSTAGE>
+__global__ void __launch_bounds__(NT, 1024 / NT) k_binned_tile(const __grid_constant__ BiBinnedArgs a) {
+    extern __shared__ __align__(128) unsigned char bi_bin_smem[];
+    const int S = a.S, C = CT ? CT : a.C, bi = a.bb_source;
+    const int n_kinds = MODE == 0 ? S : (MODE == 1 ? S + 1 : S - 1);          // staged row kinds (x C corners each)
+    const int n_rows = C * n_kinds;
+    const int stage_bytes = bi_bin_stage_bytes(C, S, n_kinds, NB);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_groups = a.header[0];
+    const int64_t n_tasks = a.n_tiles * n_groups;
+    if (tid < NSTAGE) bi_mbar_init(reinterpret_cast<uint64_t*>(bi_bin_smem + tid * stage_bytes), 1);
+    __syncthreads();
+
+    // stage a task: tables by ordinary stores, rows by TMA bulk copies that complete on the stage's mbarrier
+    auto stage = [&](int64_t task, int buf) {
+        unsigned char* base = bi_bin_smem + buf * stage_bytes;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(base);
+        double* s_w = reinterpret_cast<double*>(base + 128);
+        double* s_mu = s_w + BI_BIN_GROUP_POINTS * C;
+        double* s_pt = s_mu + BI_BIN_GROUP_POINTS * S;
+        int32_t* s_pidx = reinterpret_cast<int32_t*>(s_pt + BI_BIN_GROUP_POINTS * 4);
+        double* s_rows = reinterpret_cast<double*>(base + bi_bin_rows_offset(C, S));
+        const int64_t tile = task / n_groups;
+        const int g = (int)(task - tile * n_groups);
+        const int first = a.groups[4 * g], count = a.groups[4 * g + 1];
+        const int64_t bin0 = tile * NB;
+        const int tile_bins = (int)min((int64_t)NB, a.ld - bin0);            // even (ld is)
+        if (tid == 0) bi_mbar_expect_tx(bar, (unsigned)(n_rows * tile_bins * 8));
+        const int64_t lead = a.group_points[first];                          // the group's cell = its first point's
+        for (int r = tid; r < n_rows; r += NT) {
+            const int k = r / C, c = r - k * C;
+            const int64_t anchor = a.corner[lead * C + c];
+            const double* src;
+            if (MODE == 1 && k == S) {
+                src = a.nm_anchor + anchor * a.ld + bin0;
+            } else {
+                const int s = (MODE == 2 && k >= bi) ? k + 1 : k;            // MODE 2 skips the BB source's row
+                src = a.pmf_anchor + (anchor * S + s) * a.ld + bin0;
+            }
+            bi_bulk_g2s(s_rows + (int64_t)r * NB, src, (unsigned)(tile_bins * 8), bar);
+        }
+        if (tid < count) s_pidx[tid] = a.group_points[first + tid];
+        for (int i = tid; i < count * C; i += NT) {
+            const int q = i / C, c = i - q * C;
+            s_w[q * C + c] = a.weight[(int64_t)a.group_points[first + q] * C + c];
+        }
+        for (int i = tid; i < count * S; i += NT) {
+            const int q = i / S, s2 = i - q * S;
+            s_mu[q * S + s2] = a.mus[(int64_t)a.group_points[first + q] * S + s2];
+        }
+        if (MODE != 0 && tid < count) {
+            const int64_t p = a.group_points[first + tid];
+            const double sum_a = bi_morph_value(a.nm_sum_anchor, 1, 0, a.corner + p * C, a.weight + p * C, C);
+            const double p_cal = __ddiv_rn(a.mus[p * S + bi], sum_a);                       // likelihood.py:645
+            double sum_t = 0.0, mu_adj = 0.0;
+            if (MODE == 2) { sum_t = a.sum_t[p]; mu_adj = __dmul_rn(sum_t, p_cal); }        // likelihood.py:658
+            s_pt[tid * 4] = sum_a; s_pt[tid * 4 + 1] = p_cal; s_pt[tid * 4 + 2] = sum_t; s_pt[tid * 4 + 3] = mu_adj;
+        }
+    };
+
+    unsigned parity[2] = {0, 0};
+    int buf = 0;
+    if (NSTAGE == 2 && (int64_t)blockIdx.x < n_tasks) stage(blockIdx.x, 0);
+    for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        // NSTAGE = 2: the other stage was released by the __syncthreads that closed the previous iteration: prefetch the
+        // next task.  NSTAGE = 1: one stage, filled now (the co-resident CTA evaluates meanwhile)
+        if (NSTAGE == 2) { if (task + gridDim.x < n_tasks) stage(task + gridDim.x, buf ^ 1); }
+        else stage(task, 0);
+        unsigned char* base = bi_bin_smem + buf * stage_bytes;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(base);
+        const double* s_w = reinterpret_cast<const double*>(base + 128);
+        const double* s_mu = s_w + BI_BIN_GROUP_POINTS * C;
+        const double* s_pt = s_mu + BI_BIN_GROUP_POINTS * S;
+        const int32_t* s_pidx = reinterpret_cast<const int32_t*>(s_pt + BI_BIN_GROUP_POINTS * 4);
+        const double* s_rows = reinterpret_cast<const double*>(base + bi_bin_rows_offset(C, S));
+        const int64_t tile = task / n_groups;
+        const int g = (int)(task - tile * n_groups);
+        const int count = a.groups[4 * g + 1];
+        const int64_t bin0 = tile * NB;
+        __syncthreads();                       // this stage's tables (written by other threads) are visible
+        bi_mbar_wait(bar, parity[buf]);
+        parity[buf] ^= 1;
+
+        // ---- compute: items = (point q of the group, PAIR of 32-bin blocks kk, kk + half): the two blocks are independent
+        // dependency chains the compiler interleaves (the FP64 chains of one block alone leave the pipe idle)
+        const int n_blk = (int)min((int64_t)(NB / 32), (a.n_bins - bin0 + 31) / 32);
+        const int half = (n_blk + 1) >> 1;
+        for (int item = warp; item < count * half; item += NT / 32) {
+            const int q = item / half, kk = item - q * half;
+            const int64_t p = s_pidx[q];
+            double wr[CT ? CT : 1];
+            const double* w = s_w + q * C;
+            if (CT) {
+#pragma unroll
+                for (int c = 0; c < (CT ? CT : 1); ++c) wr[c] = w[c];
+                w = wr;
+            }
+            const double* mu = s_mu + q * S;
+            double val[2] = {0.0, 0.0};
+            int flag = 0;
+            const double* obs_p = a.observed + p * a.obs_stride;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int k = kk + j * half;
+                const int off = k * 32 + lane;
+                const int64_t b = bin0 + off;
+                if (k < n_blk && b < a.n_bins) {
+                    const double d = obs_p[b];
+                    const double* r0 = s_rows + off;
+                    if (MODE == 1) {
+                        const double sum_a = s_pt[q * 4], p_cal = s_pt[q * 4 + 1];
+                        // u_b: sum over sources in order, the BB source contributes pmf_i * 0. (likelihood.py:635-641)
+                        double u = 0.0, pmf_i = 0.0;
+                        for (int s = 0; s < S; ++s) {
+                            const double pm = bi_morph_smem<CT, NB>(r0 + s * C * NB, w, C);
+                            if (s == bi) pmf_i = pm;
+                            const double term = __dmul_rn(pm, s == bi ? 0.0 : mu[s]);
+                            u = (s == 0) ? term : __dadd_rn(u, term);
+                            if (a.store_terms && s != bi)                              // the term lambda_b takes (:667-670)
+                                a.tbuf[(p * BI_BIN_STORE_S + s) * a.tb_ld + b] = __dmul_rn(pm, mu[s]);
+                        }
+                        const double a_b = bi_morph_smem<CT, NB>(r0 + S * C * NB, w, C);
+                        const double w_b = __dmul_rn(__ddiv_rn(pmf_i, a_b), sum_a);   // likelihood.py:646
+                        double x1, r2;
+                        const double den = bi_bb_roots_lazy(a_b, __dmul_rn(w_b, p_cal), u, d, &x1, &r2);
+                        // A = where(u == 0, (d + a) / (1 + p_cal), root2)  (:652-653); the special case is rare
+                        const double A = (u == 0.0) ? __ddiv_rn(__dadd_rn(d, a_b), __dadd_rn(1.0, p_cal)) : r2;
+                        // assert all(root1 <= 0) (:649): root1 = x1 / den; finite x1 <= 0 < den (or x1 >= 0 > den) gives a
+                        // quotient that is <= 0 (or -0) without dividing; anything else (equal signs, zero / NaN den) is divided
+                        if (!(fabs(x1) <= 1.7976931348623157e308 && fabs(den) <= 1.7976931348623157e308 &&
+                              ((x1 <= 0.0 && den > 0.0) || (x1 >= 0.0 && den < 0.0)))) {
+                            if (!(__ddiv_rn(x1, den) <= 0.0)) flag |= BI_BB_ROOT1_POSITIVE;
+                        }
+                        if (!(0.0 <= A)) flag |= BI_BB_NEGATIVE_A;                    // :655
+                        val[j] = __dmul_rn(A, w_b);                                   // :656
+                        if (a.store_terms) a.tbuf[(p * BI_BIN_STORE_S + bi) * a.tb_ld + b] = val[j];
+                        else a.tbuf[p * a.tb_ld + b] = val[j];
+                    } else {
+                        // lambda_b = sum_s pmf_s * mu_s in source order (likelihood.py:667-670)
+                        double lam = 0.0;
+                        for (int s = 0; s < S; ++s) {
+                            double term;
+                            if (MODE == 2 && s == bi) {
+                                term = __dmul_rn(__ddiv_rn(a.tbuf[p * a.tb_ld + b], s_pt[q * 4 + 2]), s_pt[q * 4 + 3]);   // :657-658
+                            } else {
+                                const int k_row = (MODE == 2 && s > bi) ? s - 1 : s;
+                                term = __dmul_rn(bi_morph_smem<CT, NB>(r0 + k_row * C * NB, w, C), mu[s]);
+                            }
+                            lam = (s == 0) ? term : __dadd_rn(lam, term);
+                        }
+                        val[j] = bi_poisson_logpmf(d, a.lgamma_obs[p * a.obs_stride + b], lam);   // :674
+                    }
+                }
+            }
+#pragma unroll
+            for (int x = 1; x < 32; x <<= 1) {
+                val[0] = __dadd_rn(val[0], __shfl_xor_sync(BI_FULL_MASK, val[0], x));
+                val[1] = __dadd_rn(val[1], __shfl_xor_sync(BI_FULL_MASK, val[1], x));
+            }
+            if (MODE == 1) {
+#pragma unroll
+                for (int x = 1; x < 32; x <<= 1) flag |= __shfl_xor_sync(BI_FULL_MASK, flag, x);
+                if (lane == 0 && flag) atomicOr(&a.flags[p], flag);
+            }
+            if (lane == 0) {
+                a.blockval[p * a.n_blocks + (bin0 >> 5) + kk] = val[0];
+                if (kk + half < n_blk) a.blockval[p * a.n_blocks + (bin0 >> 5) + kk + half] = val[1];
+            }
+        }
+        __syncthreads();                       // every warp is done with this stage: it may be refilled
+        if (NSTAGE == 2) buf ^= 1;
+    }
+}
+
+// schedule of k_binned_tile for a chunk of <= 1024 points: the evaluable points sorted by hypercube cell (key = anchor
+// index of the cell's first corner) and cut into groups of <= BI_BIN_GROUP_POINTS points of one cell.  One CTA, O(P^2)
+// rank counting in shared memory (P <= 1024: a few microseconds, no global atomics, deterministic order).
+#define BI_BIN_CHUNK_MAX 1024
+__global__ void __launch_bounds__(BI_BIN_CHUNK_MAX)
+k_binned_plan(const int32_t* __restrict__ corner, const int32_t* __restrict__ status, int C, int n_points,
+              int32_t* __restrict__ group_points, int32_t* __restrict__ groups, int32_t* __restrict__ header,
+              int32_t* __restrict__ flags) {
+    __shared__ int key[BI_BIN_CHUNK_MAX];
+    __shared__ int skey[BI_BIN_CHUNK_MAX];
+    __shared__ int gflag[BI_BIN_CHUNK_MAX];
+    const int t = threadIdx.x;
+    const int none = 0x7fffffff;
+    key[t] = (t < n_points && status[t] == 0) ? corner[(int64_t)t * C] : none;
+    if (t < n_points) flags[t] = 0;
+    __syncthreads();
+    const int my = key[t];
+    int rank = 0, run_start = 0;
+    for (int j = 0; j < n_points; ++j) {
+        const int kj = key[j];
+        rank += (kj < my) || (kj == my && j < t);
+        run_start += (kj < my);
+    }
+    if (t < n_points && my != none) { group_points[rank] = t; skey[rank] = my; gflag[rank] = ((rank - run_start) % BI_BIN_GROUP_POINTS) == 0; }
+    __syncthreads();
+    int n_eval = 0;
+    for (int j = 0; j < n_points; ++j) n_eval += key[j] != none;
+    if (t < n_eval && gflag[t]) {
+        int gi = 0;
+        for (int j = 0; j < t; ++j) gi += gflag[j];
+        int cnt = 1;
+        while (t + cnt < n_eval && !gflag[t + cnt]) ++cnt;
+        groups[4 * gi] = t; groups[4 * gi + 1] = cnt; groups[4 * gi + 2] = skey[t]; groups[4 * gi + 3] = 0;
+    }
+    if (t == 0) {
+        int ng = 0;
+        for (int j = 0; j < n_eval; ++j) ng += gflag[j];
+        header[0] = ng; header[1] = n_eval;
+    }
+}
+
+// Beeston-Barlow pass B from the terms pass A stored (few points: the evaluation is HBM-bound and re-reading the anchor
+// rows would cost more than 16 S bytes per (point, bin)): lambda_b = sum over s in source order of the stored terms, the
+// BB source's being (t_b / sum_t) * mu_adj (likelihood.py:657-658,667-670); one warp per (point, 32-bin block)
+__global__ void __launch_bounds__(256) k_binned_passb_stored(const __grid_constant__ BiBinnedArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int S = a.S, C = a.C, bi = a.bb_source;
+    for (int64_t item = warp_global; item < a.n_points * a.n_blocks; item += n_warps) {
+        const int64_t p = item / a.n_blocks, k = item - p * a.n_blocks;
+        if (a.status[p] != 0) continue;
+        const int64_t b = k * 32 + lane;
+        double val = 0.0;
+        if (b < a.n_bins) {
+            const double sum_a = bi_morph_value(a.nm_sum_anchor, 1, 0, a.corner + p * C, a.weight + p * C, C);
+            const double p_cal = __ddiv_rn(a.mus[p * S + bi], sum_a);
+            const double sum_t = a.sum_t[p], mu_adj = __dmul_rn(sum_t, p_cal);
+            double lam = 0.0;
+            for (int s = 0; s < S; ++s) {
+                const double v = a.tbuf[(p * BI_BIN_STORE_S + s) * a.tb_ld + b];
+                const double term = (s == bi) ? __dmul_rn(__ddiv_rn(v, sum_t), mu_adj) : v;
+                lam = (s == 0) ? term : __dadd_rn(lam, term);
+            }
+            val = bi_poisson_logpmf(a.observed[p * a.obs_stride + b], a.lgamma_obs[p * a.obs_stride + b], lam);
+        }
+#pragma unroll
+        for (int x = 1; x < 32; x <<= 1) val = __dadd_rn(val, __shfl_xor_sync(BI_FULL_MASK, val, x));
+        if (lane == 0) a.blockval[p * a.n_blocks + k] = val;
+    }
+}
+
+// canonical total from per-block sums: superblock j = ((0 + v_16j) + v_16j+1) + ... (the sequential sum k_binned_pass
+// forms in its loop), then the 256-lane strided total of k_canonical_total
+__global__ void __launch_bounds__(256)
+k_canonical_total_blocks(const double* __restrict__ blockval, int64_t n_blocks, const int32_t* __restrict__ status,
+                         double fill, double* __restrict__ out) {
+    __shared__ double warp_tot[8];
+    const int64_t p = blockIdx.x;
+    const int t = threadIdx.x;
+    if (status[p] != 0) { if (t == 0) out[p] = fill; return; }
+    const double* v = blockval + p * n_blocks;
+    const int64_t n_super = (n_blocks + 15) / 16;
+    double u = 0.0;
+    for (int64_t j = t; j < n_super; j += 256) {
+        const int64_t k0 = j * 16, k1 = min(k0 + 16, n_blocks);
+        double sj = 0.0;
+        if (k1 - k0 == 16) {                                       // all 16 loads in flight before the sequential adds
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = v[k0 + k];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sj = __dadd_rn(sj, x[k]);
+        } else {
+            for (int64_t k = k0; k < k1; ++k) sj = __dadd_rn(sj, v[k]);
+        }
+        u = __dadd_rn(u, sj);
+    }
+#pragma unroll
+    for (int x = 1; x < 32; x <<= 1) u = __dadd_rn(u, __shfl_xor_sync(BI_FULL_MASK, u, x));
+    if ((t & 31) == 0) warp_tot[t >> 5] = u;
+    __syncthreads();
+    if (t == 0)
+        out[p] = __dadd_rn(__dadd_rn(__dadd_rn(warp_tot[0], warp_tot[1]), __dadd_rn(warp_tot[2], warp_tot[3])),
+                           __dadd_rn(__dadd_rn(warp_tot[4], warp_tot[5]), __dadd_rn(warp_tot[6], warp_tot[7])));
+}
+
 // canonical total of [P, n_chunks] partials (same order as k_unbinned_finalize); status != 0 -> fill
 __global__ void __launch_bounds__(256)
 k_canonical_total(const double* __restrict__ partial, int64_t n_chunks, const int32_t* __restrict__ status,
@@ -292,9 +649,31 @@ k_binned_pmfs(const __grid_constant__ BiBinnedArgs a, double* __restrict__ out, 
 // ---------------------------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------------------------
-extern "C" int64_t bi_binned_scratch_doubles(int64_t n_points, int64_t n_bins) {
-    return n_points * (2 * bi_num_superblocks(n_bins) + 1);
+// points evaluated per pass: bounds the per-bin scratch (t_b of the Beeston-Barlow pass) to 2 GiB and fits the planner
+static int64_t bi_bin_chunk_points(int64_t n_points, int64_t n_bins) {
+    const int64_t tb_ld = (n_bins + 63) / 64 * 64;
+    int64_t pc = ((int64_t)1 << 28) / tb_ld;
+    if (pc > BI_BIN_CHUNK_MAX) pc = BI_BIN_CHUNK_MAX;
+    if (pc < BI_BIN_GROUP_POINTS) pc = BI_BIN_GROUP_POINTS;
+    return n_points < pc ? n_points : pc;
 }
+
+// stored-terms form of the two Beeston-Barlow passes (few points, HBM-bound): all points in one pass, S <= 8 terms kept
+static bool bi_bin_store_terms(int64_t n_points, int64_t n_bins) {
+    const int64_t tb_ld = (n_bins + 63) / 64 * 64;
+    return n_points * BI_BIN_STORE_S * tb_ld <= ((int64_t)1 << 26);
+}
+
+// scratch layout (doubles): sum_t [P] | block sums A [PC, n_blocks] | block sums B [PC, n_blocks] | t_b [PC, tb_ld] (or the
+// stored terms [P, 8, tb_ld]) | schedule (int32: group_points [PC], groups [(PC + 1) * 4], header [8]); PC = points per pass
+extern "C" int64_t bi_binned_scratch_doubles(int64_t n_points, int64_t n_bins) {
+    if (n_points <= 0 || n_bins <= 0) return 0;
+    const int64_t pc = bi_bin_chunk_points(n_points, n_bins);
+    const int64_t n_blocks = (n_bins + 31) / 32, tb_ld = (n_bins + 63) / 64 * 64;
+    const int64_t per_bin = bi_bin_store_terms(n_points, n_bins) ? n_points * BI_BIN_STORE_S * tb_ld : pc * tb_ld;
+    return n_points + 2 * pc * n_blocks + per_bin + (5 * pc + 12 + 1) / 2 + 8;
+}
+extern "C" int64_t bi_binned_sum_t_offset(int64_t n_points, int64_t n_bins) { (void)n_points; (void)n_bins; return 0; }
 
 static int bi_binned_fill(BiBinnedArgs* a, const double* pmf_anchor_dev, const double* n_model_anchor_dev,
                           const double* n_model_sum_anchor_dev, int64_t ld_bins, int64_t n_bins, int32_t n_sources,
@@ -328,6 +707,34 @@ extern "C" int bi_binned_ll_batch(const double* pmf_anchor_dev, const double* n_
                                    status_dev, n_points, scratch_dev, logl_dev, mus_adj_dev, flags_dev, stream);
 }
 
+template <int MODE, int NB, int NT, int NSTAGE>
+static int bi_binned_launch_tile_nb(const BiBinnedArgs& a, int smem, int grid, cudaStream_t st) {
+#define BI_BIN_LAUNCH(CT)                                                                                          \
+    do {                                                                                                           \
+        BI_CUDA_CHECK(cudaFuncSetAttribute(k_binned_tile<MODE, CT, NB, NT, NSTAGE>,                                \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
+        k_binned_tile<MODE, CT, NB, NT, NSTAGE><<<grid, NT, smem, st>>>(a);                                        \
+    } while (0)
+    switch (a.C) {
+        case 1: BI_BIN_LAUNCH(1); break;
+        case 2: BI_BIN_LAUNCH(2); break;
+        case 4: BI_BIN_LAUNCH(4); break;
+        case 8: BI_BIN_LAUNCH(8); break;
+        default: BI_BIN_LAUNCH(0); break;
+    }
+#undef BI_BIN_LAUNCH
+    return BI_OK;
+}
+
+// 512-thread CTAs, two per SM (64 registers), one stage each: while one CTA waits for its tile the other evaluates.
+// Measured on B200 (config 3, 256-point scan / single point): this shape 9.9 ms / 0.20 ms; a two-stage prefetch pipeline in
+// one 1024-thread CTA per SM 11.5 / 0.26; 256-thread CTAs 12.7 / 0.19; 128-bin tiles 10.8 / 0.25.
+template <int MODE>
+static int bi_binned_launch_tile(const BiBinnedArgs& a, int smem, int grid, cudaStream_t st) {
+    return a.tile == 128 ? bi_binned_launch_tile_nb<MODE, 128, 512, 1>(a, smem, grid, st)
+                         : bi_binned_launch_tile_nb<MODE, 256, 512, 1>(a, smem, grid, st);
+}
+
 extern "C" int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const double* n_model_anchor_dev,
                                        const double* n_model_sum_anchor_dev,
                                        int64_t ld_bins, int64_t n_bins, int32_t n_sources, int32_t n_corners,
@@ -340,38 +747,100 @@ extern "C" int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const doubl
     BI_REQUIRE(observed_stride == 0 || observed_stride >= n_bins, "observed_stride=%lld smaller than n_bins=%lld",
                (long long)observed_stride, (long long)n_bins);
     if (n_points == 0) return BI_OK;
-    BiBinnedArgs a;
-    int rc = bi_binned_fill(&a, pmf_anchor_dev, n_model_anchor_dev, n_model_sum_anchor_dev, ld_bins, n_bins, n_sources,
+    BiBinnedArgs a0;
+    int rc = bi_binned_fill(&a0, pmf_anchor_dev, n_model_anchor_dev, n_model_sum_anchor_dev, ld_bins, n_bins, n_sources,
                             n_corners, bb_source, observed_dev, lgamma_obs_dev, corner_dev, weight_dev, mus_dev,
                             status_dev, n_points);
     if (rc != BI_OK) return rc;
     BI_REQUIRE(lgamma_obs_dev && scratch_dev && logl_dev && flags_dev, "bi_binned_ll_batch: NULL pointer");
-    a.obs_stride = observed_stride;
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n_tasks = n_points * a.n_chunks;
-    int64_t blocks = (n_tasks + 7) / 8;
-    if (blocks > 148 * 8 * 4) blocks = 148 * 8 * 4;
-    double* part_a = scratch_dev;
-    double* part_b = scratch_dev + n_points * a.n_chunks;
-    double* sum_t = scratch_dev + 2 * n_points * a.n_chunks;
-    a.flags = flags_dev;
-    BI_CUDA_CHECK(cudaMemsetAsync(flags_dev, 0, sizeof(int32_t) * n_points, st));
+    const int S = n_sources, C = n_corners;
+    const int64_t pc = bi_bin_chunk_points(n_points, n_bins);
+    const int64_t n_blocks = (n_bins + 31) / 32, tb_ld = (n_bins + 63) / 64 * 64;
+    const bool store_terms = bb_source >= 0 && S <= BI_BIN_STORE_S && bi_bin_store_terms(n_points, n_bins) && pc == n_points;
+    double* sum_t_all = scratch_dev;
+    double* bva = scratch_dev + n_points;
+    double* bvb = bva + pc * n_blocks;
+    double* tbuf = bvb + pc * n_blocks;
+    int32_t* plan = reinterpret_cast<int32_t*>(
+        tbuf + (bi_bin_store_terms(n_points, n_bins) ? n_points * BI_BIN_STORE_S * tb_ld : pc * tb_ld));
+    int32_t* group_points = plan;
+    int32_t* groups = plan + ((pc + 3) & ~(int64_t)3);
+    int32_t* header = groups + 4 * (pc + 1);
+    // tiled path: the staged rows of a tile must fit in shared memory, every row segment must be a valid bulk copy
+    const char* legacy_str = getenv("BI_BINNED_LEGACY");
+    const bool legacy_env = legacy_str != nullptr && legacy_str[0] == '1';
+    const char* tile_str = getenv("BI_BINNED_TILE");                         // experiments: force 128 / 256
+    int tile = tile_str ? atoi(tile_str) : 256;                              // measured: 256-bin tiles win at P = 1 and at P = 256
+    if (tile != 128 && tile != 256) tile = 256;
+    if (bi_bin_stage_bytes(C, S, S + 1, tile) > 110 * 1024) tile = 128;      // two CTAs per SM
+    const int smem_full = bi_bin_stage_bytes(C, S, S + 1, tile);
+    const bool tiled = !legacy_env && smem_full <= 220 * 1024 && ld_bins % 2 == 0 &&
+                       ((uintptr_t)pmf_anchor_dev & 15) == 0 && (bb_source < 0 || ((uintptr_t)n_model_anchor_dev & 15) == 0);
+    if (!tiled) BI_CUDA_CHECK(cudaMemsetAsync(flags_dev, 0, sizeof(int32_t) * n_points, st));
     const double ninf = -INFINITY;
-    if (bb_source < 0) {
-        a.partial = part_b;
-        k_binned_pass<0><<<(unsigned)blocks, 256, 0, st>>>(a);
-    } else {
-        a.partial = part_a;
-        k_binned_pass<1><<<(unsigned)blocks, 256, 0, st>>>(a);
-        k_canonical_total<<<(unsigned)n_points, 256, 0, st>>>(part_a, a.n_chunks, status_dev, 0.0, sum_t);
-        a.partial = part_b;
-        a.sum_t = sum_t;
-        k_binned_pass<2><<<(unsigned)blocks, 256, 0, st>>>(a);
+    for (int64_t p0 = 0; p0 < n_points; p0 += pc) {
+        const int64_t np = n_points - p0 < pc ? n_points - p0 : pc;
+        BiBinnedArgs a = a0;
+        a.n_points = np;
+        a.corner = corner_dev + p0 * C; a.weight = weight_dev + p0 * C; a.mus = mus_dev + p0 * S;
+        a.status = status_dev + p0; a.flags = flags_dev + p0;
+        a.observed = observed_dev + p0 * observed_stride; a.lgamma_obs = lgamma_obs_dev + p0 * observed_stride;
+        a.obs_stride = observed_stride;
+        double* sum_t = sum_t_all + p0;
+        if (tiled) {
+            a.group_points = group_points; a.groups = groups; a.header = header;
+            a.tbuf = tbuf; a.n_blocks = n_blocks; a.tile = tile; a.n_tiles = (n_bins + tile - 1) / tile;
+            a.tb_ld = tb_ld;
+            a.store_terms = store_terms ? 1 : 0;
+            k_binned_plan<<<1, BI_BIN_CHUNK_MAX, 0, st>>>(a.corner, a.status, C, (int)np, group_points, groups, header, a.flags);
+            auto launch = [&](int mode, double* blockval) -> int {
+                a.blockval = blockval;
+                const int n_kinds = mode == 0 ? S : (mode == 1 ? S + 1 : S - 1);
+                const int smem = bi_bin_stage_bytes(C, S, n_kinds, tile);
+                const int per_sm = 2 * (smem + 1024) <= 227 * 1024 ? 2 : 1;
+                const int grid = 148 * per_sm;
+                if (mode == 0) return bi_binned_launch_tile<0>(a, smem, grid, st);
+                if (mode == 1) return bi_binned_launch_tile<1>(a, smem, grid, st);
+                return bi_binned_launch_tile<2>(a, smem, grid, st);
+            };
+            if (bb_source < 0) {
+                if ((rc = launch(0, bvb)) != BI_OK) return rc;
+            } else {
+                if ((rc = launch(1, bva)) != BI_OK) return rc;
+                k_canonical_total_blocks<<<(unsigned)np, 256, 0, st>>>(bva, n_blocks, a.status, 0.0, sum_t);
+                a.sum_t = sum_t;
+                if (store_terms) {
+                    a.blockval = bvb;
+                    int64_t blocks = (np * n_blocks + 7) / 8;
+                    if (blocks > 148 * 16) blocks = 148 * 16;
+                    k_binned_passb_stored<<<(unsigned)blocks, 256, 0, st>>>(a);
+                } else if ((rc = launch(2, bvb)) != BI_OK) {
+                    return rc;
+                }
+            }
+            k_canonical_total_blocks<<<(unsigned)np, 256, 0, st>>>(bvb, n_blocks, a.status, ninf, logl_dev + p0);
+        } else {
+            const int64_t n_tasks = np * a.n_chunks;
+            int64_t blocks = (n_tasks + 7) / 8;
+            if (blocks > 148 * 8 * 4) blocks = 148 * 8 * 4;
+            if (bb_source < 0) {
+                a.partial = bvb;
+                k_binned_pass<0><<<(unsigned)blocks, 256, 0, st>>>(a);
+            } else {
+                a.partial = bva;
+                k_binned_pass<1><<<(unsigned)blocks, 256, 0, st>>>(a);
+                k_canonical_total<<<(unsigned)np, 256, 0, st>>>(bva, a.n_chunks, a.status, 0.0, sum_t);
+                a.partial = bvb;
+                a.sum_t = sum_t;
+                k_binned_pass<2><<<(unsigned)blocks, 256, 0, st>>>(a);
+            }
+            k_canonical_total<<<(unsigned)np, 256, 0, st>>>(bvb, a.n_chunks, a.status, ninf, logl_dev + p0);
+        }
     }
-    k_canonical_total<<<(unsigned)n_points, 256, 0, st>>>(part_b, a.n_chunks, status_dev, ninf, logl_dev);
     if (mus_adj_dev) {
         const int64_t nb = (n_points + 127) / 128;
-        k_binned_mus_adj<<<(unsigned)nb, 128, 0, st>>>(mus_dev, sum_t, n_model_sum_anchor_dev, corner_dev, weight_dev,
+        k_binned_mus_adj<<<(unsigned)nb, 128, 0, st>>>(mus_dev, sum_t_all, n_model_sum_anchor_dev, corner_dev, weight_dev,
                                                        status_dev, n_sources, n_corners, bb_source, n_points, mus_adj_dev);
     }
     BI_LAUNCH_CHECK();

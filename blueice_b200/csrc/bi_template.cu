@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "bi_space.cuh"
+#include "bi_plan.cuh"
 
 #ifndef BI_TS_BATCH
 #define BI_TS_BATCH 4       /* template rows whose gathers are in flight together (K5) */
@@ -150,7 +151,8 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
                     int64_t n_groups, const BiTsGroup* __restrict__ groups, const int64_t* __restrict__ unit_offset,
                     const int32_t* __restrict__ unit_group, int64_t n_units,
                     const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
-                    double outlier, double* __restrict__ partial) {
+                    double outlier, double* __restrict__ partial,
+                    const int32_t* __restrict__ group_order, const int32_t* __restrict__ n_ordered, int sb_max) {
     constexpr int NY = NS > 0 ? NS : 1;
     extern __shared__ __align__(16) unsigned char bi_ts_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -160,19 +162,29 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
     const int t_class = (lane >> 1) & 3;
     const int64_t n_warps = (int64_t)gridDim.x * BI_TS_WARPS;
 
-    for (int64_t u = (int64_t)blockIdx.x * BI_TS_WARPS + warp; u < n_units; u += n_warps) {
+    // ordered mode (toy Monte Carlos): the groups are walked in hypercube-cell order (group_order, written by
+    // k_ts_order_groups), every group's superblocks back to back -- co-resident warps then gather from the SAME few
+    // template rows, which stay in L2 (in toy order the 120 MB of packed templates thrash it: 7x the algorithmic DRAM bytes)
+    const int64_t n_iter = group_order ? (int64_t)n_ordered[0] * sb_max : n_units;
+    for (int64_t u = (int64_t)blockIdx.x * BI_TS_WARPS + warp; u < n_iter; u += n_warps) {
         // ---- unit -> (pair group, superblock)
-        int64_t g;
-        if (unit_group) g = unit_group[u];
-        else {                                                      // largest g with unit_offset[g] <= u
-            int64_t lo = 0, hi = n_groups;
-            while (hi - lo > 1) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (unit_offset[mid] <= u) lo = mid; else hi = mid;
+        int64_t g, sb;
+        if (group_order) {
+            g = group_order[u / sb_max];
+            sb = u - (u / sb_max) * sb_max;
+            if (sb >= unit_offset[g + 1] - unit_offset[g]) continue;
+        } else {
+            if (unit_group) g = unit_group[u];
+            else {                                                  // largest g with unit_offset[g] <= u
+                int64_t lo = 0, hi = n_groups;
+                while (hi - lo > 1) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (unit_offset[mid] <= u) lo = mid; else hi = mid;
+                }
+                g = lo;
             }
-            g = lo;
+            sb = u - unit_offset[g];
         }
-        const int64_t sb = u - unit_offset[g];
         const BiTsGroup gp = groups[g];
         const int np = gp.count < NP ? gp.count : NP;
         // live points of the group (status 0); the row list comes from the first live one
@@ -1146,6 +1158,37 @@ extern "C" int bi_template_prepare_events(int32_t n_space, const int32_t* n_bins
     return BI_OK;
 }
 
+// groups of one pair each (toys) bucketed by the hypercube cell of their point: counting sort in ONE CTA (shared-memory
+// histogram over the cells, scan, scatter).  group_order [n_groups]: live groups (status 0), cell-major; n_ordered[0]: their
+// number.  The order inside a cell is decided by atomics -- results never depend on the schedule.
+__global__ void __launch_bounds__(BI_PLAN_THREADS)
+k_ts_order_groups(const __grid_constant__ BiPlanDims dims, int n_cells, int64_t n_groups,
+                  const int32_t* __restrict__ cell, const int32_t* __restrict__ status,
+                  const int32_t* __restrict__ pair_point, const BiTsGroup* __restrict__ groups,
+                  int32_t* __restrict__ group_order, int32_t* __restrict__ n_ordered) {
+    extern __shared__ int bi_order_smem[];
+    int* off = bi_order_smem;                      // [n_cells + 1]
+    int* cursor = off + n_cells + 1;               // [n_cells]
+    __shared__ int carry[33];
+    const int tid = threadIdx.x, D = dims.n_dims;
+    for (int c = tid; c <= n_cells; c += BI_PLAN_THREADS) { off[c] = 0; if (c < n_cells) cursor[c] = 0; }
+    __syncthreads();
+    for (int64_t g = tid; g < n_groups; g += BI_PLAN_THREADS) {
+        const int32_t pt = pair_point[groups[g].first];
+        if (status[pt] == 0) atomicAdd(&off[bi_flat_cell(dims, cell + (int64_t)pt * D)], 1);
+    }
+    __syncthreads();
+    const int total = bi_block_exclusive_scan(off, n_cells, carry);
+    for (int64_t g = tid; g < n_groups; g += BI_PLAN_THREADS) {
+        const int32_t pt = pair_point[groups[g].first];
+        if (status[pt] == 0) {
+            const int c = bi_flat_cell(dims, cell + (int64_t)pt * D);
+            group_order[off[c] + atomicAdd(&cursor[c], 1)] = (int32_t)g;
+        }
+    }
+    if (tid == 0) n_ordered[0] = total;
+}
+
 template <int NP, int NS>
 static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride, const BiTsSpace& sp,
                         const int32_t* ev_bin, const double* ev_frac, int64_t ld_frac, const int64_t* dataset_offset,
@@ -1153,7 +1196,7 @@ static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride,
                         const int32_t* term_source, const double* mus, const int32_t* status, int64_t n_groups,
                         const BiTsGroup* groups, const int64_t* unit_offset, const int32_t* unit_group, int64_t n_units,
                         const int32_t* pair_point, const int64_t* pair_partial_offset, double outlier, double* partial,
-                        cudaStream_t st) {
+                        const int32_t* group_order, const int32_t* n_ordered, int sb_max, cudaStream_t st) {
     const int smem = BI_TS_WARPS * K * (1 + NP) * 8;
     static int per_sm_cached[BI_TS_MAX_TERMS + 1] = {0};
     static int sms = 0;
@@ -1173,7 +1216,8 @@ static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride,
     if (blocks > needed) blocks = needed;
     k_template_partials<NP, NS><<<(unsigned)blocks, BI_TS_THREADS, smem, st>>>(
         T, row_stride, bin_stride, sp, ev_bin, ev_frac, ld_frac, dataset_offset, K, S, row, coef, wterm, term_source, mus,
-        status, n_groups, groups, unit_offset, unit_group, n_units, pair_point, pair_partial_offset, outlier, partial);
+        status, n_groups, groups, unit_offset, unit_group, n_units, pair_point, pair_partial_offset, outlier, partial,
+        group_order, n_ordered, sb_max);
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         bi_set_error("k_template_partials<%d,%d> launch failed: %s (blocks=%lld, smem=%d, K=%d, units=%lld)", NP, NS,
@@ -1183,7 +1227,7 @@ static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride,
     return BI_OK;
 }
 
-extern "C" int bi_template_partials(const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+static int bi_template_partials_impl(const double* templates_dev, int64_t row_stride, int64_t bin_stride,
                                     int32_t n_space, const int32_t* n_bins_host, int32_t method,
                                     const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
                                     const int64_t* dataset_offset_dev, int32_t n_terms, int32_t n_sources,
@@ -1192,7 +1236,9 @@ extern "C" int bi_template_partials(const double* templates_dev, int64_t row_str
                                     int64_t n_groups, int32_t group_points, const int32_t* groups_dev,
                                     const int64_t* unit_offset_dev, const int32_t* unit_group_dev, int64_t n_units,
                                     const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
-                                    double outlier_likelihood, double* partial_dev, void* stream) {
+                                    double outlier_likelihood, double* partial_dev,
+                                    const int32_t* group_order_dev, const int32_t* n_ordered_dev, int32_t sb_max,
+                                    void* stream) {
     BiSpace space;
     int rc = bi_fill_space(&space, n_space, n_bins_host);
     if (rc != BI_OK) return rc;
@@ -1230,13 +1276,30 @@ extern "C" int bi_template_partials(const double* templates_dev, int64_t row_str
                                       dataset_offset_dev, n_terms, n_sources, row_dev, coef_dev, wterm_dev,             \
                                       term_source_dev, mus_dev, status_dev, n_groups, groups, unit_offset_dev,          \
                                       unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,                 \
-                                      outlier_likelihood, partial_dev, st);
+                                      outlier_likelihood, partial_dev, group_order_dev, n_ordered_dev, sb_max, st);
     BI_TS_CASE(1, 0) BI_TS_CASE(1, 1) BI_TS_CASE(1, 2) BI_TS_CASE(1, 3) BI_TS_CASE(1, 4)
     BI_TS_CASE(BI_TS_GROUP_POINTS, 0) BI_TS_CASE(BI_TS_GROUP_POINTS, 1) BI_TS_CASE(BI_TS_GROUP_POINTS, 2)
     BI_TS_CASE(BI_TS_GROUP_POINTS, 3) BI_TS_CASE(BI_TS_GROUP_POINTS, 4)
 #undef BI_TS_CASE
     bi_set_error("bi_template_partials: unsupported configuration");
     return BI_ERR_UNSUPPORTED;
+}
+
+extern "C" int bi_template_partials(const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+                                    int32_t n_space, const int32_t* n_bins_host, int32_t method,
+                                    const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
+                                    const int64_t* dataset_offset_dev, int32_t n_terms, int32_t n_sources,
+                                    const int32_t* row_dev, const double* coef_dev, const double* wterm_dev,
+                                    const int32_t* term_source_dev, const double* mus_dev, const int32_t* status_dev,
+                                    int64_t n_groups, int32_t group_points, const int32_t* groups_dev,
+                                    const int64_t* unit_offset_dev, const int32_t* unit_group_dev, int64_t n_units,
+                                    const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
+                                    double outlier_likelihood, double* partial_dev, void* stream) {
+    return bi_template_partials_impl(templates_dev, row_stride, bin_stride, n_space, n_bins_host, method, ev_bin_dev,
+                                     ev_frac_dev, ld_frac, dataset_offset_dev, n_terms, n_sources, row_dev, coef_dev,
+                                     wterm_dev, term_source_dev, mus_dev, status_dev, n_groups, group_points, groups_dev,
+                                     unit_offset_dev, unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,
+                                     outlier_likelihood, partial_dev, nullptr, nullptr, 1, stream);
 }
 
 extern "C" int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_offset_dev,
@@ -1426,7 +1489,7 @@ extern "C" int bi_mixture_partials(const double* tmix_dev, int32_t n_space, cons
 // ---------------------------------------------------------------------------------------------
 static inline int64_t bi_ts_align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
-struct BiTemplateWorkspace { int64_t cell, frac, corner, weight, mus, row, coef, wterm, term_source, partial, tmix, total; };
+struct BiTemplateWorkspace { int64_t cell, frac, corner, weight, mus, row, coef, wterm, term_source, partial, tmix, order, total; };
 
 static BiTemplateWorkspace bi_template_layout(int32_t D, int32_t S, int64_t P, int64_t n_partials, int64_t n_pairs,
                                               int64_t n_bins, int32_t mixture) {
@@ -1444,6 +1507,7 @@ static BiTemplateWorkspace bi_template_layout(int32_t D, int32_t S, int64_t P, i
     w.term_source = o; o += bi_ts_align256(K * 4);
     w.partial = o;     o += bi_ts_align256((n_partials > 0 ? n_partials : 1) * 8);
     w.tmix = o;        o += mixture ? bi_ts_align256(n_pairs * n_bins * 8 * 4) : 0;     // packed: up to 4 doubles per bin
+    w.order = o;       o += mixture ? 0 : bi_ts_align256((n_pairs + 8) * 4);            // cell-major group order (toys)
     w.total = o;
     return w;
 }
@@ -1506,10 +1570,43 @@ extern "C" int bi_template_ll_batch(int32_t n_dims, const int32_t* n_anchors_hos
                                      status_dev, n_groups, group_points, groups_dev, unit_offset_dev, unit_group_dev,
                                      n_units, pair_point_dev, pair_partial_offset_dev, outlier_likelihood, partial, stream);
         } else {
-            rc = bi_template_partials(templates_dev, row_stride, bin_stride, n_space, n_bins_host, method, ev_bin_dev,
-                                      ev_frac_dev, ld_frac, dataset_offset_dev, K, n_sources, row, coef, wterm, term_source,
-                                      mus, status_dev, n_groups, group_points, groups_dev, unit_offset_dev, unit_group_dev,
-                                      n_units, pair_point_dev, pair_partial_offset_dev, outlier_likelihood, partial, stream);
+            // many single-pair groups (toy Monte Carlos): walk them in hypercube-cell order (BI_TS_ORDER=0: toy order)
+            const int32_t* group_order = nullptr;
+            const int32_t* n_ordered = nullptr;
+            const char* order_env = getenv("BI_TS_ORDER");
+            if (group_points == 1 && n_groups >= 4096 && n_groups <= n_pairs && n_dims > 0 && max_partials >= 1 &&
+                max_partials < 64 && !(order_env && order_env[0] == '0')) {
+                BiPlanDims dims;
+                memset(&dims, 0, sizeof(dims));
+                dims.n_dims = n_dims;
+                int64_t n_cells = 1;
+                for (int d = n_dims - 1; d >= 0; --d) {
+                    dims.cells[d] = n_anchors_host[d] > 1 ? n_anchors_host[d] - 1 : 1;
+                    dims.stride[d] = (int32_t)n_cells;
+                    n_cells *= dims.cells[d];
+                }
+                if (n_cells > 1 && n_cells <= BI_PLAN_MAX_CELLS) {
+                    int32_t* order = (int32_t*)(base + w.order);
+                    static bool configured = false;
+                    if (!configured) {
+                        BI_CUDA_CHECK(cudaFuncSetAttribute(k_ts_order_groups, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           (int)((2 * BI_PLAN_MAX_CELLS + 2) * sizeof(int))));
+                        configured = true;
+                    }
+                    k_ts_order_groups<<<1, BI_PLAN_THREADS, (size_t)(2 * n_cells + 2) * sizeof(int), (cudaStream_t)stream>>>(
+                        dims, (int)n_cells, n_groups, (const int32_t*)(base + w.cell), status_dev, pair_point_dev,
+                        reinterpret_cast<const BiTsGroup*>(groups_dev), order + 8, order);
+                    BI_LAUNCH_CHECK();
+                    group_order = order + 8;
+                    n_ordered = order;
+                }
+            }
+            rc = bi_template_partials_impl(templates_dev, row_stride, bin_stride, n_space, n_bins_host, method, ev_bin_dev,
+                                           ev_frac_dev, ld_frac, dataset_offset_dev, K, n_sources, row, coef, wterm,
+                                           term_source, mus, status_dev, n_groups, group_points, groups_dev, unit_offset_dev,
+                                           unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,
+                                           outlier_likelihood, partial, group_order, n_ordered, (int32_t)max_partials,
+                                           stream);
         }
         if (rc != BI_OK) return rc;
     }

@@ -1,4 +1,6 @@
 // blueice_b200 -- C-ABI entry of the DMMA K2 kernel (bi_unbinned_mma.cuh), K = C*S <= 32 contraction terms.
+#include <stdlib.h>
+
 #include "bi_unbinned_mma.cuh"
 
 static int bi_mma_k4(int K) {
@@ -191,6 +193,12 @@ extern "C" int bi_unbinned_ll_batch(int32_t n_dims, const int32_t* n_anchors_hos
                (long long)workspace_bytes, (long long)w.total);
     BI_REQUIRE(((uintptr_t)workspace_dev & 255) == 0, "workspace_dev must be 256-byte aligned");
     BI_REQUIRE(logl_dev && musum_dev && status_dev, "bi_unbinned_ll_batch: NULL output pointer");
+    // tiny batches: the whole evaluation in ONE launch (bit-identical; BI_SMALL=0 keeps the four launches, for A/B runs)
+    const char* small_env = getenv("BI_SMALL");
+    if ((small_env == nullptr || small_env[0] != '0') && bi_unbinned_small_ok(n_dims, n_sources, n_points, n_events))
+        return bi_unbinned_ll_small(n_dims, n_anchors_host, axes_host, n_sources, n_points, zs_dev, rate_mult_dev, scale_dev,
+                                    eff_dev, mus_anchor_dev, allow_negative_host, ps_anchor_dev, ld_events, n_events,
+                                    outlier_likelihood, logl_dev, logsum_dev, musum_dev, status_dev, stream);
     char* base = (char*)workspace_dev;
     int rc = bi_point_setup(n_dims, n_anchors_host, axes_host, n_sources, n_points, zs_dev, rate_mult_dev, scale_dev,
                             eff_dev, mus_anchor_dev, allow_negative_host, (int32_t*)(base + w.cell),

@@ -397,6 +397,12 @@ class UnbinnedEngine(_EngineBase):
             _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.dev_ptr(views["cell"]), self._stream()),
             "bi_unbinned_partials_mma")
 
+    def _small_ok(self, P):
+        """True when bi_unbinned_ll_batch evaluates a P-point batch with its single fused launch (tiny batches)."""
+        if os.environ.get('BI_SMALL') == '0' or self.n_events <= 0 or not self.uses_mma():
+            return False
+        return bool(self.lib.bi_unbinned_small_ok(self.grid.n_dims, self.n_sources, P, self.n_events))
+
     def rows_tensor(self):
         """The [n_rows, ld] per-event pdf matrix K2 contracts (the anchor tensor viewed as rows)."""
         return self.ps_anchor
@@ -419,20 +425,55 @@ class UnbinnedEngine(_EngineBase):
                    musum=self.ws.get("musum", P, torch.float64), status=self.ws.get("status", P, torch.int32))
         fn, args = self._fused_args(P, zs_d, mult_d, scale_d, eff_d, ws, out)
         _cabi.check(fn(*args, self._stream()), fn.__name__)
-        self.launches += 4 if self.n_super > 0 else 2
+        self.launches += 1 if self._small_ok(P) else (4 if self.n_super > 0 else 2)
         return out
+
+    def scalar_runner(self, has_scale):
+        """The leanest e2e path, for ONE point at a time (ll(**params) inside a minimiser or an interval search):
+        returns (pinned input array [D + S (+ 1)], run) where run() evaluates the staged point and returns
+        (logl, status).  With the single-launch kernel the call is one ctypes call + one stream synchronisation (inputs
+        and results travel over PCIe inside the kernel); otherwise the cached sequence / CUDA graph of evaluate_fused."""
+        st = self._fused_state(1, has_scale, False)
+        stream = self.torch.cuda.current_stream(self.device)
+        stream_ptr = ctypes.c_void_p(stream.cuda_stream)
+        pin_f, pin_i = st["pin_f_np"], st["pin_i_np"]
+        sync = stream.synchronize
+        if st["zero_copy"]:
+            fn, args = st["fn"], st["args"] + (stream_ptr,)
+
+            def run():
+                rc = fn(*args)
+                if rc:
+                    _cabi.check(rc, "bi_unbinned_ll_batch")
+                sync()
+                self.launches += 1
+                return pin_f[0], pin_i[0]
+        else:
+            n_launch = 4 if self.n_super > 0 else 2
+
+            def run():
+                graph = self._fused_graph(st, 1)
+                if graph is not None:
+                    graph.replay()
+                else:
+                    self._fused_sequence(st, 1, stream)
+                sync()
+                self.launches += n_launch
+                return pin_f[0], pin_i[0]
+        return st["pin_in_np"], run
 
     def _fused_state(self, P, has_scale, has_eff):
         """Everything the e2e fast path needs for a P-point batch, built once and reused while the dataset stays:
         pinned staging buffers both ways, device input / output buffers, the workspace and the prebuilt C arguments."""
-        key = (P, has_scale, has_eff, self.n_events, self.ps_anchor.data_ptr())
+        zero_copy = self.peer_gather is None and self._small_ok(P)
+        key = (P, has_scale, has_eff, self.n_events, self.ps_anchor.data_ptr(), zero_copy)
         st = self._fused_cache.get(key)
         if st is not None:
             return st
         torch = self.torch
         D, S = self.grid.n_dims, self.n_sources
         n_in = P * D + P * S + (P if has_scale else 0) + (P * S if has_eff else 0)
-        st = {"P": P}
+        st = {"P": P, "zero_copy": zero_copy}
         st["pin_in"] = torch.empty(max(n_in, 1), dtype=torch.float64, pin_memory=True)
         st["pin_in_np"] = st["pin_in"].numpy()
         st["dev_in"] = torch.empty(max(n_in, 1), dtype=torch.float64, device=self.device)
@@ -452,6 +493,15 @@ class UnbinnedEngine(_EngineBase):
         st["pin_i"] = torch.empty(P, dtype=torch.int32, pin_memory=True)
         st["pin_f_np"], st["pin_i_np"] = st["pin_f"].numpy(), st["pin_i"].numpy()
         out = dict(logl=st["out_f"][:P], logsum=st["out_f"][P:2 * P], musum=st["out_f"][2 * P:], status=st["out_i"])
+        if zero_copy:
+            # tiny batch: bi_unbinned_ll_batch runs ONE fused launch (bi_unbinned_ll_small) that reads the staged inputs
+            # from pinned host memory and writes the results there -- no copy surrounds the launch
+            o = 0
+            views = []
+            for n in (P * D, P * S, P if has_scale else 0, P * S if has_eff else 0):
+                views.append(st["pin_in"][o:o + n] if n else None)
+                o += n
+            out = dict(logl=st["pin_f"][:P], logsum=st["pin_f"][P:2 * P], musum=st["pin_f"][2 * P:], status=st["pin_i"])
         st["fn"], st["args"] = self._fused_args(P, views[0], views[1], views[2], views[3], st["ws"], out)
         if len(self._fused_cache) >= 8:
             self._fused_cache.clear()
@@ -462,6 +512,9 @@ class UnbinnedEngine(_EngineBase):
         """Everything the device does for one e2e evaluation of a cached state, issued on `stream`: H2D of the staged
         inputs, the fused call (four launches), the exchange step of a sharded evaluation (one launch), D2H."""
         P = st["P"]
+        if st["zero_copy"]:
+            _cabi.check(st["fn"](*st["args"], ctypes.c_void_p(stream.cuda_stream)), "bi_unbinned_ll_batch")
+            return
         if st["n_in"]:
             st["dev_in"].copy_(st["pin_in"], non_blocking=True)
         _cabi.check(st["fn"](*st["args"], ctypes.c_void_p(stream.cuda_stream)), "bi_unbinned_ll_batch")
@@ -541,7 +594,8 @@ class UnbinnedEngine(_EngineBase):
             graph.replay()
         else:
             self._fused_sequence(st, n_f, stream)
-        self.launches += (4 if self.n_super > 0 else 2) + (0 if pg is None or pg.fallback is not None else 1)
+        self.launches += 1 if st["zero_copy"] else \
+            (4 if self.n_super > 0 else 2) + (0 if pg is None or pg.fallback is not None else 1)
         stream.synchronize()
         self.last_gathered = self.last_total = None
         n_x = 0
@@ -552,8 +606,8 @@ class UnbinnedEngine(_EngineBase):
                 self.last_total = x[:P].copy()
             else:
                 self.last_gathered = x.reshape(pg.world, -1).copy()
-        self.last_h2d_bytes = st["n_in"] * 8
-        self.last_d2h_bytes = n_f * 8 + P * 4 + n_x * 8
+        self.last_h2d_bytes = st["n_in"] * 8            # zero-copy batches: read by the kernel over PCIe, same bytes
+        self.last_d2h_bytes = (3 * P * 8 if st["zero_copy"] else n_f * 8) + P * 4 + n_x * 8
         res = st["pin_f_np"]
         if return_parts:
             return res[P:2 * P].copy(), res[2 * P:3 * P].copy(), st["pin_i_np"].copy()
@@ -734,6 +788,9 @@ class SourcewiseUnbinnedEngine(UnbinnedEngine):
 
     def _flat_row(self, anchor_index, source_index):
         return anchor_index          # callers pass the absolute row (row_base[source] + sub-anchor) as "anchor"
+
+    def _small_ok(self, P):
+        return False                  # the single-launch path covers the full anchor grid only
 
     def uses_mma(self):
         if self.n_terms > _cabi.MMA_MAX_TERMS:
@@ -919,7 +976,7 @@ class BinnedEngine(_EngineBase):
             raise ValueError("need one parameter point per toy: got %d points for %d toys" % (len(mult), self.n_toys))
         return self.evaluate(zs, mult, scale, eff, return_status, toys=True)
 
-    def run_device(self, P, zs_d, mult_d, scale_d, eff_d, want_all=False, toys=False):
+    def run_device(self, P, zs_d, mult_d, scale_d, eff_d, want_all=False, toys=False, need_mus_adj=False):
         torch = self.torch
         if toys:
             observed, lgamma_obs, stride = self.toy_observed, self.toy_lgamma, self.ld
@@ -932,7 +989,7 @@ class BinnedEngine(_EngineBase):
         n_scratch = int(self.lib.bi_binned_scratch_doubles(P, self.n_bins))
         scratch = self.ws.get("scratch", n_scratch, torch.float64)
         logl = self.ws.get("logl", P, torch.float64)
-        mus_adj = self.ws.get("mus_adj", P * S, torch.float64)
+        mus_adj = self.ws.get("mus_adj", P * S, torch.float64) if need_mus_adj else None    # full_output only
         flags = self.ws.get("flags", P, torch.int32)
         rc = self.lib.bi_binned_ll_batch_toys(
             _cabi.dev_ptr(self.pmf_anchor), _cabi.dev_ptr(self.nm_anchor), _cabi.dev_ptr(self.nm_sum_anchor),
@@ -940,7 +997,7 @@ class BinnedEngine(_EngineBase):
             _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]), _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]),
             P, _cabi.dev_ptr(scratch), _cabi.dev_ptr(logl), _cabi.dev_ptr(mus_adj), _cabi.dev_ptr(flags), self._stream())
         _cabi.check(rc, "bi_binned_ll_batch_toys")
-        self.launches += 5 if self.bb_source >= 0 else 3
+        self.launches += (5 if self.bb_source >= 0 else 3) + (1 if need_mus_adj else 0)
         if want_all:
             return logl, o, mus_adj, flags, scratch
         return logl
@@ -977,9 +1034,10 @@ class BinnedEngine(_EngineBase):
                                                               np.asarray(mult_row, dtype=np.float64).reshape(1, -1),
                                                               None if scale is None else [scale],
                                                               None if eff is None else np.asarray(eff).reshape(1, -1))
-        logl, o, mus_adj, flags, scratch = self.run_device(1, zs_d, mult_d, scale_d, eff_d, want_all=True)
+        logl, o, mus_adj, flags, scratch = self.run_device(1, zs_d, mult_d, scale_d, eff_d, want_all=True, need_mus_adj=True)
         out = torch.empty((S, self.n_bins), dtype=torch.float64, device=self.device)
-        sum_t = scratch[2 * self.n_chunks:2 * self.n_chunks + 1]
+        o_t = int(self.lib.bi_binned_sum_t_offset(1, self.n_bins))
+        sum_t = scratch[o_t:o_t + 1]
         rc = self.lib.bi_binned_pmfs(
             _cabi.dev_ptr(self.pmf_anchor), _cabi.dev_ptr(self.nm_anchor), _cabi.dev_ptr(self.nm_sum_anchor),
             self.ld, self.n_bins, S, C, self.bb_source, _cabi.dev_ptr(self.observed),

@@ -15,6 +15,7 @@ What runs where
         tensors, rate scaling, unphysical-rate test, mixture density, log, reduction; binned Poisson
         with Beeston-Barlow; template lookup and event binning in set_data.
 """
+import os
 from collections import OrderedDict
 from copy import deepcopy
 from functools import wraps
@@ -33,7 +34,7 @@ from .source import HistogramPdfSource
 from .utils import combine_dicts, inherit_docstring_from
 
 __all__ = ['LogLikelihoodBase', 'BinnedLogLikelihood', 'UnbinnedLogLikelihood', 'LogLikelihoodSum',
-           'LogAncillaryLikelihood', 'extended_loglikelihood',
+           'LogAncillaryLikelihood', 'LogLikelihoodReParam', 'extended_loglikelihood',
            'beeston_barlow_root1', 'beeston_barlow_root2', 'beeston_barlow_roots']
 
 _RATE_SUFFIX = '_rate_multiplier'
@@ -102,6 +103,7 @@ class LogLikelihoodBase(object):
         self.n_model_events_interpolator = lambda x: None
         self.n_model_events = None
         self._engine = None                      # device engine, built by set_data (unbinned) / prepare (binned)
+        self._scalar_plans = None                # lean single-evaluation closures per keyword-name tuple (unbinned)
         self._grid = None
         self._mus_anchor = None
 
@@ -568,11 +570,85 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
                                     outlier_likelihood=outlier, allow_negative=self.source_allowed_negative)
             self._fill_anchor_rows(engine, self._anchor_items(), d)
         self._engine = engine
+        self._scalar_plans = {} if os.environ.get('BI_SCALAR_FAST', '1') != '0' else None
         if len(self.shape_parameters):
             self.ps_interpolator = lambda zs: engine.ps(np.asarray(zs, dtype=np.float64),
                                                         np.ones(engine.n_sources))[1]
         elif not isinstance(engine, TemplateUnbinnedEngine):
             self.ps = engine.ps(np.zeros(0), np.ones(engine.n_sources))[1]
+
+    # ------------------------------------------------------------------------------------------
+    # single evaluations: the lean path (a minimiser or an interval search calls ll(**params) thousands of times,
+    # inference.py:131-178,332-389; there the Python around the kernels is what costs)
+    # ------------------------------------------------------------------------------------------
+    def __call__(self, livetime_days=None, compute_pdf=False, full_output=False, **kwargs):
+        if not (compute_pdf or full_output) and self.is_data_set and self._scalar_plans is not None:
+            key = (tuple(kwargs), livetime_days is None)
+            plan = self._scalar_plans.get(key)
+            if plan is None:
+                plan = self._scalar_plans[key] = self._make_scalar_plan(key[0], livetime_days) or False
+            if plan:
+                result = plan(kwargs, livetime_days)
+                if result is not NotImplemented:
+                    return result
+        return LogLikelihoodBase.__call__(self, livetime_days=livetime_days, compute_pdf=compute_pdf,
+                                          full_output=full_output, **kwargs)
+
+    def _make_scalar_plan(self, names, livetime_days):
+        """Closure evaluating ll(**kwargs) for this set of keyword names, or None when the general path must be used.
+        It reproduces LogLikelihoodBase.__call__ for P = 1 (same defaults, priors in the same order, same device call);
+        anything unusual (non-numeric arguments, unknown names, efficiencies, 'error'-mode failures) returns
+        NotImplemented so that the general path produces the reference's behaviour."""
+        engine = self._engine
+        if type(engine) is not UnbinnedEngine or not engine.uses_mma() or engine.n_events <= 0:
+            return None
+        if True in self.source_apply_efficiency:
+            return None
+        try:
+            self._kwargs_to_settings(**{n: 1.0 for n in names})       # the name validation of __call__
+            scale, zero_base = self._livetime_scale(livetime_days)
+            defaults_mult, defaults_settings = self._kwargs_to_settings()
+        except Exception:
+            return None
+        if zero_base or any(not _is_number(v) for v in defaults_settings.values()):
+            return None
+        has_scale = scale is not None
+        pin, run = engine.scalar_runner(has_scale)
+        shape_names = list(self.shape_parameters.keys())
+        D, S = len(shape_names), len(self.source_name_list)
+        z_slots = [(j, n, float(defaults_settings[n])) for j, n in enumerate(shape_names)]
+        m_slots = [(D + j, s + _RATE_SUFFIX, float(defaults_mult[j])) for j, s in enumerate(self.source_name_list)]
+        priors = [(prior, j) for j, (_, prior, _) in enumerate(self.shape_parameters.values()) if prior is not None]
+        priors += [(self.rate_parameters.get(s), D + j) for j, s in enumerate(self.source_name_list)
+                   if self.rate_parameters.get(s) is not None]
+        error_mode = self.config.get('unphysical_behaviour') == 'error'
+        base_livetime = self.pdf_base_config.get('livetime_days')
+        number = (float, int)
+        f64 = np.float64
+
+        def plan(kwargs, livetime_days):
+            get = kwargs.get
+            for j, name, default in z_slots:
+                v = get(name)
+                if v is None:
+                    v = default
+                elif not isinstance(v, number):
+                    return NotImplemented
+                pin[j] = v
+            for j, name, default in m_slots:
+                pin[j] = get(name, default)
+            if has_scale:
+                pin[D + S] = livetime_days / base_livetime
+            logl, status = run()
+            if status != 0:
+                return NotImplemented if error_mode else _NEG_INF
+            if priors:
+                total = f64(0.0)
+                for prior, j in priors:
+                    total = total + prior(float(pin[j]))
+                return total + logl
+            return f64(0.0) + logl
+        return plan
 
     def _anchor_items(self):
         """(anchor index, source index, Source) for every row of the full anchor grid, anchors in C order."""
@@ -1075,7 +1151,144 @@ class LogAncillaryLikelihood(object):
         return self.func(values, **self.func_kwargs)
 
 
+class LogLikelihoodReParam(object):
+    """A likelihood seen through new parameters (likelihood.py:715-864).
+
+    conv_config maps
+        '<source>_rate_multiplier' -> dict(params=[new parameter names], func=callable)   the rate multiplier of the
+                                      wrapped likelihood becomes func(*new) / func(*base values of new)
+        '<new parameter>'          -> (anchor values, log prior, base value)             declared as a shape parameter
+    New parameters must have a (truthy) base value in the model config.  Pure keyword plumbing over the wrapped
+    likelihood; `batch` converts whole columns and makes ONE ll.batch call."""
+
+    def __init__(self, likelihood, conv_config):
+        self._wrapped = likelihood
+        self.conv_config = conv_config
+        self.check_conv_config()
+        self.pdf_base_config = likelihood.pdf_base_config
+
+    # -- bookkeeping ------------------------------------------------------------------------------
+    def _conversions(self):
+        """[(rate multiplier name, new parameter names, func)] in conv_config order."""
+        return [(k, list(v["params"]), v["func"]) for k, v in self.conv_config.items() if k.endswith(_RATE_SUFFIX)]
+
+    def check_conv_config(self):
+        """The new parameters declared and the ones the conversions use must be the same set, and each needs a base
+        value in the model config (likelihood.py:732-760)."""
+        declared = [k for k in self.conv_config if not k.endswith(_RATE_SUFFIX)]
+        used = []
+        for v in self.conv_config.values():
+            if isinstance(v, dict):
+                used += [p for p in v["params"] if p not in used]
+        assert set(declared) == set(used), "New parameters are not consistent, double check conv_config..."
+        config = self._wrapped.base_model.config
+        missing = ", ".join(p for p in declared if not config.get(p, False))
+        assert missing == "", "%s are missing in the config" % missing
+
+    @property
+    def rate_parameters(self):
+        """The wrapped rate parameters without the ones now computed from new parameters."""
+        kept = deepcopy(self._wrapped.rate_parameters)
+        for source_name in self._wrapped.rate_parameters:
+            if source_name + _RATE_SUFFIX in self.conv_config:
+                kept.pop(source_name)
+        return kept
+
+    @property
+    def shape_parameters(self):
+        """The wrapped shape parameters plus the new parameters of conv_config."""
+        out = deepcopy(self._wrapped.shape_parameters)
+        for name, spec in self.conv_config.items():
+            if not name.endswith(_RATE_SUFFIX):
+                out[name] = ({z: z for z in spec[0]}, spec[1], spec[2])
+        return out
+
+    @property
+    def base_model(self):
+        model = deepcopy(self._wrapped.base_model)
+        model.simulate = self._simulate
+        return model
+
+    def set_data(self, d):
+        self._wrapped.set_data(d)
+
+    def get_bounds(self, parameter_name=None):
+        if parameter_name is None:
+            return [self.get_bounds(p) for p in self.shape_parameters.keys()]
+        if parameter_name in list(self._wrapped.rate_parameters) + list(self._wrapped.shape_parameters):
+            return self._wrapped.get_bounds(parameter_name)
+        zs = list(self.shape_parameters[parameter_name][0].keys())
+        return min(zs), max(zs)
+
+    # -- conversion ---------------------------------------------------------------------------------
+    def _parameter_converter(self, with_suffix=True, **kwargs):
+        """New-parameter keywords -> keywords of the wrapped likelihood (likelihood.py:812-864).  with_suffix=False:
+        rate parameters are named by their source (Model.simulate's rate_multipliers convention) on both sides."""
+        rate_names = list(self._wrapped.rate_parameters.keys())
+        if not with_suffix:
+            kwargs = {(k + _RATE_SUFFIX if k in rate_names else k): v for k, v in kwargs.items()}
+        converted = OrderedDict()
+        consumed = set()
+        for target, params, func in self._conversions():
+            base = [self.pdf_base_config.get(p) for p in params]
+            values = [kwargs.get(p, b) for p, b in zip(params, base)]
+            converted[target] = func(*values) / func(*base)
+            consumed.update(params)
+        for k, v in kwargs.items():
+            if k not in consumed:
+                converted[k] = v
+        if not with_suffix:
+            converted = OrderedDict((k.split(_RATE_SUFFIX)[0], v) for k, v in converted.items())
+        return deepcopy(converted)
+
+    def _simulate(self, kwargs=None, livetime_days=None):
+        """base_model.simulate in terms of the new parameters (likelihood.py:796-810)."""
+        converted = self._parameter_converter(with_suffix=False, **(kwargs or {}))
+        multipliers = {k: v for k, v in converted.items() if k in self._wrapped.rate_parameters}
+        return self._wrapped.base_model.simulate(rate_multipliers=multipliers, livetime_days=livetime_days)
+
+    # -- evaluation ---------------------------------------------------------------------------------
+    def __call__(self, compute_pdf=False, livetime_days=None, **kwargs):
+        return self._wrapped(compute_pdf=compute_pdf, livetime_days=livetime_days,
+                             **self._parameter_converter(**kwargs))
+
+    def parameter_names(self):
+        return [s + _RATE_SUFFIX for s in self.rate_parameters.keys()] + list(self.shape_parameters.keys())
+
+    def batch(self, params, names=None, livetime_days=None):
+        """P parameter points in the NEW parameters with one device pass: row p equals
+        self(**dict(zip(names, params[p]))).  The conversion functions are applied to whole columns when they accept
+        arrays, row by row otherwise."""
+        names = self.parameter_names() if names is None else list(names)
+        params = np.asarray(params, dtype=np.float64).reshape(-1, max(len(names), 1))
+        P = len(params)
+        columns = OrderedDict()
+        consumed = set()
+        for target, new_names, func in self._conversions():
+            base = [self.pdf_base_config.get(p) for p in new_names]
+            cols = [params[:, names.index(p)] if p in names else np.full(P, b, dtype=np.float64)
+                    for p, b in zip(new_names, base)]
+            denominator = func(*base)
+            values = None
+            if P > 1:
+                try:
+                    values = np.asarray(func(*cols), dtype=np.float64) / denominator
+                    if values.shape != (P,):
+                        values = None
+                except Exception:
+                    values = None
+            if values is None:
+                values = np.array([func(*[c[i] for c in cols]) / denominator for i in range(P)], dtype=np.float64)
+            columns[target] = values
+            consumed.update(new_names)
+        for j, name in enumerate(names):
+            if name not in consumed:
+                columns[name] = params[:, j]
+        table = np.column_stack(list(columns.values())) if columns else np.zeros((P, 0))
+        return self._wrapped.batch(table, list(columns.keys()), livetime_days=livetime_days)
+
+
 # the inference helpers double as methods of every likelihood class (likelihood.py:1004-1007)
 for _name in inference.__all__:
-    for _cls in (LogLikelihoodBase, LogLikelihoodSum, LogAncillaryLikelihood):
+    for _cls in (LogLikelihoodBase, LogLikelihoodSum, LogAncillaryLikelihood, LogLikelihoodReParam):
         setattr(_cls, _name, getattr(inference, _name))

@@ -1,7 +1,8 @@
 """Fixtures shared by the tests and by bench.py's config-1 workload.
 
 Same names and behaviour as blueice/test_helpers.py (GaussianSource :22-37, GaussianMCSource :40-43,
-FixedSampleSource :46-52, BASE_CONFIG :55-66, conf_for_test :79-84, make_data :103-126,
+FixedSampleSource :46-52, BASE_CONFIG :55-66, BASE_CONV_CONFIG :70-76, conf_for_test :79-84,
+conf_for_reparam_test :86-97, make_data :103-126,
 almost_equal :99-100), so that the parity tests read like the reference's own tests.
 """
 from copy import deepcopy
@@ -76,6 +77,26 @@ def conf_for_test(n_sources=1, mc=False, **kwargs):
     if mc:
         conf['default_source_class'] = GaussianMCSource
     return combine_dicts(conf, kwargs)
+
+
+# conv_config of the re-parameterisation tests (blueice/test_helpers.py:70-76): two new parameters np0, np1 drive the
+# rates of the three sources op0, op1, op2 of conf_for_reparam_test
+BASE_CONV_CONFIG = dict(
+    np0=(np.linspace(1e-12, 10, 2), None, None),
+    np1=(np.linspace(1e-12, 10, 2), None, None),
+    op0_rate_multiplier=dict(params=["np0"], func=lambda np0: np0**2),
+    op1_rate_multiplier=dict(params=["np1"], func=lambda np1: np1**2),
+    op2_rate_multiplier=dict(params=["np0", "np1"], func=lambda np0, np1: np0*np1),
+)
+
+
+def conf_for_reparam_test(n_source=1, mc=False, **kwargs):
+    """conf_for_test with the sources op0..op2 and the new parameters np0 = np1 = 1 (blueice/test_helpers.py:86-97)."""
+    conf = conf_for_test(n_source, mc, **kwargs)
+    conf["sources"] = [dict(name="op0"), dict(name="op1"), dict(name="op2")]
+    conf["np0"] = 1
+    conf["np1"] = 1
+    return conf
 
 
 def almost_equal(a, b, fraction=1e-6):

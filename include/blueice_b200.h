@@ -230,6 +230,24 @@ int bi_unbinned_ll_batch(int32_t n_dims, const int32_t* n_anchors_host, const do
                          void* workspace_dev, int64_t workspace_bytes,
                          double* logl_dev, double* logsum_dev, double* musum_dev, int32_t* status_dev, void* stream);
 
+/*
+ * The same evaluation for a TINY batch in ONE launch (K1 + K2 + finalize fused: one CTA per point; the latency regime of
+ * a minimiser or interval search calling ll(**params) thousands of times, inference.py:131-178,332-389).  Results are
+ * bit-identical to bi_unbinned_ll_batch's four launches, which calls it by itself whenever bi_unbinned_small_ok(...)
+ * says the batch qualifies (terms <= 128, events <= 8192, points x superblocks <= 2048; BI_SMALL=0 in the environment
+ * disables that).  The point inputs (zs, rate_mult, scale, eff) and the outputs (logl, logsum, musum, status) only need
+ * to be DEVICE-ACCESSIBLE: pinned host memory works, the kernel then reads / writes it directly and no copy surrounds
+ * the launch.
+ */
+int32_t bi_unbinned_small_ok(int32_t n_dims, int32_t n_sources, int64_t n_points, int64_t n_events);
+int bi_unbinned_ll_small(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                         int32_t n_sources, int64_t n_points,
+                         const double* zs, const double* rate_mult, const double* scale, const double* eff,
+                         const double* mus_anchor_dev, const uint8_t* allow_negative_host,
+                         const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
+                         double outlier_likelihood,
+                         double* logl, double* logsum, double* musum, int32_t* status, void* stream);
+
 /* bi_unbinned_ll_batch for source-wise interpolation (K1 = bi_point_setup_sourcewise). */
 int bi_unbinned_ll_batch_sourcewise(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
                                     int32_t n_sources, const uint32_t* dim_mask_host, const int32_t* row_base_host,
@@ -447,13 +465,20 @@ int bi_histogramdd_toys(int32_t n_space, const int32_t* n_bins_host, const doubl
  *                       n_model_events[source_i].sum() (likelihood.py:645) is taken as the morph of these
  *   observed_dev        [n_bins] observed counts (float64)
  *   lgamma_obs_dev      [n_bins] gammaln(observed + 1), computed once per dataset by the caller
- *   scratch_dev         bi_binned_scratch_doubles(P, n_bins) doubles
+ *   scratch_dev         bi_binned_scratch_doubles(P, n_bins) doubles, 16-byte aligned
  * outputs
  *   logl_dev [P] (status != 0 -> -inf), mus_adj_dev [P, S] adjusted mus (may be NULL),
  *   flags_dev [P] BI_BB_* bits; the sum over bins of A*w of each point is left in
- *   scratch_dev[2 * P * bi_num_superblocks(n_bins) + p] (input of bi_binned_pmfs).
+ *   scratch_dev[bi_binned_sum_t_offset(P, n_bins) + p] (input of bi_binned_pmfs).
+ * Kernel: the anchor rows of a 256-bin tile are staged in shared memory by 1-D TMA bulk copies once per (tile, group of
+ * <= 32 points that share their hypercube cell) and every point of the group is evaluated on them; with Beeston-Barlow
+ * the first pass stores t_b = A_b * w_b per (point, bin) so that the second pass neither repeats the root solve nor
+ * re-reads the calibration counts.  Points are processed in passes of <= 1024 (per-bin scratch <= 2 GiB).
+ * ld_bins must be even and the tensors 16-byte aligned for the tiled kernel (else a gather kernel is used; BI_BINNED_LEGACY=1
+ * in the environment forces it, for A/B runs); both give bit-identical results.
  */
 int64_t bi_binned_scratch_doubles(int64_t n_points, int64_t n_bins);
+int64_t bi_binned_sum_t_offset(int64_t n_points, int64_t n_bins);
 int bi_binned_ll_batch(const double* pmf_anchor_dev, const double* n_model_anchor_dev,
                        const double* n_model_sum_anchor_dev,
                        int64_t ld_bins, int64_t n_bins, int32_t n_sources, int32_t n_corners,

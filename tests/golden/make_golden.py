@@ -227,6 +227,45 @@ def golden_sourcewise():
          full_ps=np.array([f[2] for f in full]))
 
 
+# ---------------------------------------------------------------------------------------------
+# G6: LogLikelihoodReParam (likelihood.py:715-864) on the reference's own fixtures
+# (test_helpers.py:70-97, tests/test_likelihood_reparam.py)
+# ---------------------------------------------------------------------------------------------
+def golden_reparam():
+    from copy import deepcopy
+    from blueice.likelihood import LogLikelihoodReParam
+    from blueice.test_helpers import BASE_CONV_CONFIG, conf_for_reparam_test
+    # events_per_day as a FLOAT: with the test's integer 1 the reference's mus array is an integer array and
+    # `mus[s] *= mult` (likelihood.py:368) truncates non-integer products -- invisible in the reference's own test
+    # (integer points only), and a quirk blueice_b200 does not reproduce
+    lf_old = UnbinnedLogLikelihood(conf_for_reparam_test(events_per_day=1.))
+    for name in ('op0', 'op1', 'op2'):
+        lf_old.add_rate_parameter(name)
+    lf_old.prepare()
+    lf = LogLikelihoodReParam(lf_old, deepcopy(BASE_CONV_CONFIG))
+    rng = np.random.default_rng(6)
+    x = rng.normal(0., 1., 7)
+    d = np.zeros(len(x), dtype=[('x', float), ('source', int)])
+    d['x'] = x
+    lf.set_data(d)
+    pts = np.column_stack([rng.uniform(0.3, 4., 24), rng.uniform(0.3, 4., 24)])
+    pts[0] = [1., 1.]
+    pts[1] = [2., 1.]
+    pts[2] = [1., 2.]
+    logl = np.array([lf(np0=float(a), np1=float(b)) for a, b in pts])
+    only_np0 = np.array([lf(np0=float(a)) for a, _ in pts])
+    converted = np.array([[lf._parameter_converter(np0=float(a), np1=float(b))[k]
+                           for k in ('op0_rate_multiplier', 'op1_rate_multiplier', 'op2_rate_multiplier')]
+                          for a, b in pts])
+    no_suffix = lf._parameter_converter(with_suffix=False, np0=2., op1=3.)
+    save('reparam', x=x, points=pts, logl=logl, logl_only_np0=only_np0, converted=converted,
+         default=np.array([lf()]), bounds_np0=np.array(lf.get_bounds('np0')),
+         bounds_all=np.array(lf.get_bounds(), dtype=float),
+         no_suffix_keys=np.array(list(no_suffix.keys())), no_suffix_values=np.array(list(no_suffix.values()), dtype=float),
+         rate_parameters=np.array(list(lf.rate_parameters.keys()), dtype=str),
+         shape_parameters=np.array(list(lf.shape_parameters.keys())))
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -239,3 +278,4 @@ if __name__ == '__main__':
     golden_binned(True)
     golden_multisource()
     golden_sourcewise()
+    golden_reparam()

@@ -675,3 +675,62 @@ def test_profile_scan_lockstep_matches_per_hypothesis_fits():
         assert ll(sig_rate_multiplier=float(values[h]), **kw) == prof[h]
     # 3000 events against ~1e5 expected: the profile falls monotonically with the signal rate
     assert np.all(np.diff(prof) < 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# LogLikelihoodReParam (blueice/likelihood.py:715-864; the reference's tests/test_likelihood_reparam.py)
+# ------------------------------------------------------------------------------------------------
+def _reparam_pair():
+    from copy import deepcopy
+    from blueice_b200.likelihood import LogLikelihoodReParam, UnbinnedLogLikelihood
+    from blueice_b200.test_helpers import BASE_CONV_CONFIG, conf_for_reparam_test
+    lf_old = UnbinnedLogLikelihood(conf_for_reparam_test(events_per_day=1.))
+    for name in ("op0", "op1", "op2"):
+        lf_old.add_rate_parameter(name)
+    lf_old.prepare()
+    return lf_old, LogLikelihoodReParam(lf_old, deepcopy(BASE_CONV_CONFIG))
+
+
+def test_golden_reparam():
+    """Values of the unmodified reference's LogLikelihoodReParam (tests/golden/make_golden.py reparam)."""
+    g = load_golden('reparam')
+    _, lf = _reparam_pair()
+    d = np.zeros(len(g['x']), dtype=[('x', float), ('source', int)])
+    d['x'] = g['x']
+    lf.set_data(d)
+    n = len(d)
+    got = np.array([lf(np0=float(a), np1=float(b)) for a, b in g['points']])
+    assert np.all(np.abs(got - g['logl']) <= 1e-9 * n)
+    assert np.all(np.abs(got - g['logl']) <= 1e-13 * (np.abs(g['logl']) + n))
+    assert np.array_equal(lf.batch(g['points'], ['np0', 'np1']), got)               # batch == scalar, bit for bit
+    only = lf.batch(g['points'][:, :1], ['np0'])
+    assert np.all(np.abs(only - g['logl_only_np0']) <= 1e-9 * n)
+    assert abs(lf() - g['default'][0]) <= 1e-9 * n
+
+
+def test_reparam_likelihood_value():
+    """tests/test_likelihood_reparam.py:9-41."""
+    _, lf = _reparam_pair()
+    d = np.zeros(3, dtype=[('x', float), ('source', int)])
+    lf.set_data(d)
+    for v in (1, 2, 3):
+        total = v ** 2 + v ** 2 + v * v
+        expect = -total + 3 * np.log(total) + 3 * stats.norm.logpdf(0)
+        assert np.isclose(lf(np0=v, np1=v), expect, atol=1e-08)
+
+
+def test_reparam_likelihoods_before_after():
+    """tests/test_likelihood_reparam.py:44-72: the wrapped and the re-parameterised likelihood agree; here exactly."""
+    lf_old, lf = _reparam_pair()
+    np.random.seed(2)
+    d = lf.base_model.simulate()
+    lf.set_data(d)
+    lf_old.set_data(d)
+    assert lf() == lf_old()
+    assert lf(np0=2) == lf_old(op0_rate_multiplier=4, op2_rate_multiplier=2)
+    assert lf(np1=2) == lf_old(op1_rate_multiplier=4, op2_rate_multiplier=2)
+    assert lf(np0=2, np1=2) == lf_old(op0_rate_multiplier=4, op1_rate_multiplier=4, op2_rate_multiplier=4)
+    d2 = lf.base_model.simulate(dict(np0=2.0), livetime_days=3.0)                   # _simulate through the converter
+    assert len(d2) >= 0
+    best, ll_max = lf.bestfit_scipy()
+    assert set(best) == {'np0', 'np1'} and np.isfinite(ll_max)

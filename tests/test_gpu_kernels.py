@@ -484,3 +484,84 @@ def test_beeston_barlow_known_answers_through_the_kernel():
     A = obinned.beeston_barlow_root2(a, 0.2, np.array([0.]), d)
     np.testing.assert_almost_equal(A, [15.833, 29.166, 28.333, 28.333], decimal=2)
     assert abs((got - np.sum(stats.poisson(0.2 * A).logpmf(d))) / got) <= 1e-6
+
+
+@pytest.mark.parametrize("d,s,bins,bb,p", [(0, 2, (5,), 0, 3), (1, 3, (1100,), None, 70), (2, 3, (37, 29), 1, 300),
+                                           (3, 4, (20, 20, 7), 0, 90), (2, 2, (9, 7), 0, 1500), (4, 2, (25, 13), None, 40)])
+def test_binned_tiled_kernel_is_bitwise_identical_to_the_gather_kernel(d, s, bins, bb, p, monkeypatch):
+    """k_binned_tile (anchor rows of a 256-bin tile staged in shared memory by TMA, points grouped by hypercube cell,
+    t_b kept between the Beeston-Barlow passes) against k_binned_pass (BI_BINNED_LEGACY=1): same bits, for bin counts
+    with ragged tiles and blocks, groups of more than 32 points per cell, several point passes, status != 0 points."""
+    engine = _engine_mod()
+    rng = np.random.default_rng(7000 + 10 * d + s)
+    axes, mus, pmf, n_model, observed = binned_case(rng, d, s, bins)
+    grid = engine.MorphGrid(axes)
+    eng = engine.BinnedEngine(grid, mus.reshape(grid.n_anchors, s), pmf, n_model if bb is not None else None, bb)
+    eng.set_observed(observed)
+    zs = random_points(rng, axes, p)
+    mult = rng.uniform(0.5, 1.5, (p, s))
+    mult[min(4, p - 1), 0] = -1.0                             # unphysical -> -inf, no work
+    if d:
+        zs[min(5, p - 1), 0] = axes[0][0] - 1                 # out of range
+        zs[0] = [a[-1] for a in axes]                         # on the upper boundary
+    monkeypatch.setenv("BI_BINNED_LEGACY", "1")
+    want, st_w, fl_w = eng.evaluate(zs, mult, return_status=True)
+    want_full = eng.pmfs(zs[0], mult[0])
+    monkeypatch.setenv("BI_BINNED_LEGACY", "0")
+    got, st_g, fl_g = eng.evaluate(zs, mult, return_status=True)
+    got_full = eng.pmfs(zs[0], mult[0])
+    assert np.array_equal(got, want) and np.array_equal(st_g, st_w) and np.array_equal(fl_g, fl_w)
+    assert got_full[0] == want_full[0] and np.array_equal(got_full[1], want_full[1])
+    assert np.array_equal(got_full[2], want_full[2])
+    assert np.isfinite(got).sum() >= p - 2
+    # one observed histogram per point (binned toys)
+    rows = rng.poisson(np.maximum(observed.reshape(1, -1), 0.3), size=(p, observed.size)).astype(float)
+    eng.set_observed_rows(rows)
+    monkeypatch.setenv("BI_BINNED_LEGACY", "1")
+    want_t = eng.evaluate_toys(zs, mult)
+    monkeypatch.setenv("BI_BINNED_LEGACY", "0")
+    got_t = eng.evaluate_toys(zs, mult)
+    assert np.array_equal(got_t, want_t)
+
+
+@pytest.mark.parametrize("d,s,n,p", [(1, 1, 1012, 1), (0, 2, 1, 3), (1, 2, 31, 5), (2, 2, 32, 1), (2, 3, 33, 9),
+                                     (2, 2, 511, 4), (2, 2, 512, 4), (2, 2, 513, 60), (3, 3, 5000, 17), (4, 6, 700, 2),
+                                     (2, 5, 8192, 100), (5, 4, 2000, 3)])
+def test_single_launch_path_is_bitwise_identical_to_the_four_launches(d, s, n, p, monkeypatch):
+    """bi_unbinned_ll_small (K1 + K2 + finalize in one launch, inputs and results in pinned host memory) against the
+    K1 -> schedule -> k_unbinned_mma -> finalize sequence (BI_SMALL=0): same bits for logL, log sum, mu sum and status,
+    including special densities (the reference-semantics fallback), out-of-range and unphysical points, live-time
+    scaling; and the lean scalar runner returns the batch's numbers."""
+    rng = np.random.default_rng(9000 + 100 * d + s + n)
+    axes, mus_anchor, ps_anchor = make_case(rng, d, s, n)
+    if n > 40:
+        for k, v in enumerate([0.0, np.nan, np.inf, -1.0, 1e-320, 1e305]):
+            ps_anchor[..., 0, 3 + 5 * k] = v
+        ps_anchor[..., :, 37] = 0.0
+    eng = build_engine(axes, mus_anchor, ps_anchor)
+    zs = random_points(rng, axes, p)
+    mult = rng.uniform(0.5, 2, (p, s))
+    if p > 3:
+        mult[2, 0] = -1.0
+        if d:
+            zs[3, 0] = axes[0][-1] + 0.1
+    scale = rng.uniform(0.5, 2.0, p)
+    assert eng._small_ok(p)
+    res = {}
+    for small in ("0", "1"):
+        monkeypatch.setenv("BI_SMALL", small)
+        assert eng._small_ok(p) == (small == "1")
+        launches = eng.launches
+        res[small] = (eng.evaluate(zs, mult, return_status=True), eng.evaluate(zs, mult, scale=scale, return_parts=True),
+                      eng.evaluate(zs, mult, return_status=True))          # the third call replays the cached state
+        assert eng.launches - launches == (3 if small == "1" else 12)
+    for a, b in zip(res["0"], res["1"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y, equal_nan=True)
+    pin, run = eng.scalar_runner(False)
+    pin[:d] = zs[0]
+    pin[d:d + s] = mult[0]
+    logl, status = run()
+    assert logl == res["1"][0][0][0] and status == res["1"][0][1][0]
+    orc = UnbinnedOracle(axes, mus_anchor).set_ps(ps_anchor)
+    assert_logl_close(res["1"][0][0], orc.batch(zs, mult), n, "single launch vs oracle")
