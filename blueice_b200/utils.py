@@ -57,9 +57,57 @@ def data_file_name(filename, data_dirs=None):
     return FileNotFoundError(filename)     # (sic) the reference returns the exception object here
 
 
+# -- pdf-cache format (blueice/source.py:106-128,155-160; blueice/utils.py:65-77) -----------------------------------------
+# A reference cache file is a (dill) pickle of {attribute: value} whose histograms are `multihist.Histdd` instances.
+# Reading: such pickles load here even without multihist -- its histogram classes are mapped onto blueice_b200.hist.Histdd,
+# which takes over their instance dict (histogram, bin_edges, dimensions, axis_names).  Writing: when multihist can be
+# imported, histograms are written as multihist objects, so the reference can load caches made here.  (The state of real
+# multihist objects is restated from memory of multihist 0.6.x -- SURVEY.md 8c; pinned against the test stand-in only.)
+_MULTIHIST_CLASSES = ('Histdd', 'Hist1d', 'MultiHistBase')
+
+
+class _CacheUnpickler(getattr(_serializer, 'Unpickler', _pickle.Unpickler)):
+    def find_class(self, module, name):
+        if module.split('.')[0] == 'multihist' and name in _MULTIHIST_CLASSES:
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                from .hist import Histdd
+                return Histdd
+        return super().find_class(module, name)
+
+
+def _own_histograms(obj):
+    """multihist histograms anywhere in a cache dict -> blueice_b200.hist.Histdd (the device paths expect those)."""
+    from .hist import Histdd
+    if isinstance(obj, dict):
+        return {k: _own_histograms(v) for k, v in obj.items()}
+    if type(obj).__module__.split('.')[0] == 'multihist' and hasattr(obj, 'histogram') and hasattr(obj, 'bin_edges'):
+        edges = obj.bin_edges if getattr(obj, 'dimensions', 2) != 1 or isinstance(obj.bin_edges, (list, tuple)) \
+            else [obj.bin_edges]
+        return Histdd.from_histogram(obj.histogram, edges, axis_names=getattr(obj, 'axis_names', None))
+    return obj
+
+
+def _reference_histograms(obj):
+    """blueice_b200.hist.Histdd anywhere in a cache dict -> multihist.Histdd when multihist is importable."""
+    from .hist import Histdd
+    if isinstance(obj, dict):
+        return {k: _reference_histograms(v) for k, v in obj.items()}
+    if type(obj) is Histdd:
+        try:
+            import multihist
+        except ImportError:
+            return obj
+        out = multihist.Histdd(bins=obj.bin_edges, axis_names=obj.axis_names)
+        out.histogram = np.array(obj.histogram, dtype=float)
+        return out
+    return obj
+
+
 def read_pickle(filename):
     with open(filename, 'rb') as f:
-        return _serializer.load(f)
+        return _own_histograms(_CacheUnpickler(f).load())
 
 
 def save_pickle(stuff, filename):
@@ -67,6 +115,7 @@ def save_pickle(stuff, filename):
     directory = os.path.dirname(filename)
     if directory:
         os.makedirs(directory, exist_ok=True)
+    stuff = _reference_histograms(stuff)
     fd, tmp = tempfile.mkstemp(dir=directory or '.')
     try:
         with os.fdopen(fd, 'wb') as f:

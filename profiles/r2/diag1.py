@@ -59,6 +59,16 @@ if "c1" in cases:
     lat_r = timeit(run, 2000)
     out["c1_single_call"] = {"ll_kwargs_us": lat * 1e6, "ll_batch_P1_us": lat_b * 1e6, "scalar_runner_us": lat_r * 1e6,
                              "small_path": bool(eng._small_ok(1)), "n_events": int(len(d1))}
+    rng1 = np.random.default_rng(1)
+    pts1 = np.column_stack([rng1.uniform(0.5, 2.0, 4096), rng1.uniform(-2.0, 2.0, 4096)])
+    firsts = []
+    for _ in range(8):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ll1.batch(pts1, names1)
+        firsts.append((time.perf_counter() - t0) * 1e3)
+    out["c1_batch4096_first_calls_ms"] = firsts
+    out["c1_batch4096_steady_ms"] = timeit(lambda: ll1.batch(pts1, names1), 50) * 1e3
     pr = cProfile.Profile()
     pr.enable()
     for _ in range(2000):
