@@ -181,6 +181,8 @@ _MMA_TARGET_UNITS = (int(os.environ.get('BI_MMA_TARGET_UNITS', 148 * 12 * 32))
                      | (int(os.environ.get('BI_MMA_FULL_UNITS', '1')) << 30))
 _EMPTY_I32 = np.zeros(0, dtype=np.int32)
 _E2E_GRAPHS = os.environ.get('BI_E2E_GRAPHS', '1') != '0'     # replay the e2e sequence of a batch size as one CUDA graph
+_DIRECT_IO = os.environ.get('BI_DIRECT_IO', '1') != '0'        # kernels read / write small batches in pinned host memory
+_DIRECT_IO_MAX_BYTES = 1 << 20
 
 
 class _EngineBase(object):
@@ -462,18 +464,51 @@ class UnbinnedEngine(_EngineBase):
                 return pin_f[0], pin_i[0]
         return st["pin_in_np"], run
 
+    def batch_runner(self, P, has_scale):
+        """The lean e2e path for a P-point batch (ll.batch inside a minimiser or scan driver): returns
+        (zs view [P, D], mult view [P, S], scale view [P] or None -- all in the pinned staging buffer -- and run), where
+        run() evaluates the staged points and returns (logl [P], status [P]) as views of the pinned result buffers
+        (valid until the next evaluation).  Same device sequence as evaluate_fused."""
+        st = self._fused_state(P, has_scale, False)
+        D, S = self.grid.n_dims, self.n_sources
+        pin = st["pin_in_np"]
+        zs_v = pin[:P * D].reshape(P, D)
+        mult_v = pin[P * D:P * D + P * S].reshape(P, S)
+        scale_v = pin[P * D + P * S:P * D + P * S + P] if has_scale else None
+        stream = self.torch.cuda.current_stream(self.device)
+        sync = stream.synchronize
+        logl_v, status_v = st["pin_f_np"][:P], st["pin_i_np"]
+        n_launch = 1 if st["zero_copy"] else (4 if self.n_super > 0 else 2)
+        h2d, d2h = st["n_in"] * 8, P * 12
+
+        def run():
+            graph = self._fused_graph(st, P)
+            if graph is not None:
+                graph.replay()
+            else:
+                self._fused_sequence(st, P, stream)
+            sync()
+            self.launches += n_launch
+            self.last_h2d_bytes, self.last_d2h_bytes = h2d, d2h
+            return logl_v, status_v
+        return zs_v, mult_v, scale_v, run
+
     def _fused_state(self, P, has_scale, has_eff):
         """Everything the e2e fast path needs for a P-point batch, built once and reused while the dataset stays:
         pinned staging buffers both ways, device input / output buffers, the workspace and the prebuilt C arguments."""
         zero_copy = self.peer_gather is None and self._small_ok(P)
-        key = (P, has_scale, has_eff, self.n_events, self.ps_anchor.data_ptr(), zero_copy)
+        D, S = self.grid.n_dims, self.n_sources
+        n_in = P * D + P * S + (P if has_scale else 0) + (P * S if has_eff else 0)
+        # mid-size batches: K1 reads the staged points from pinned host memory and the finalize kernel writes logL there
+        # (both over PCIe, inside the kernels), which removes two of the three copy nodes around the four launches
+        direct_in = not zero_copy and _DIRECT_IO and 0 < n_in * 8 <= _DIRECT_IO_MAX_BYTES
+        direct_out = direct_in and self.peer_gather is None
+        key = (P, has_scale, has_eff, self.n_events, self.ps_anchor.data_ptr(), zero_copy, direct_in, direct_out)
         st = self._fused_cache.get(key)
         if st is not None:
             return st
         torch = self.torch
-        D, S = self.grid.n_dims, self.n_sources
-        n_in = P * D + P * S + (P if has_scale else 0) + (P * S if has_eff else 0)
-        st = {"P": P, "zero_copy": zero_copy}
+        st = {"P": P, "zero_copy": zero_copy, "direct_in": direct_in, "direct_out": direct_out}
         st["pin_in"] = torch.empty(max(n_in, 1), dtype=torch.float64, pin_memory=True)
         st["pin_in_np"] = st["pin_in"].numpy()
         st["dev_in"] = torch.empty(max(n_in, 1), dtype=torch.float64, device=self.device)
@@ -493,7 +528,7 @@ class UnbinnedEngine(_EngineBase):
         st["pin_i"] = torch.empty(P, dtype=torch.int32, pin_memory=True)
         st["pin_f_np"], st["pin_i_np"] = st["pin_f"].numpy(), st["pin_i"].numpy()
         out = dict(logl=st["out_f"][:P], logsum=st["out_f"][P:2 * P], musum=st["out_f"][2 * P:], status=st["out_i"])
-        if zero_copy:
+        if zero_copy or direct_in:
             # tiny batch: bi_unbinned_ll_batch runs ONE fused launch (bi_unbinned_ll_small) that reads the staged inputs
             # from pinned host memory and writes the results there -- no copy surrounds the launch
             o = 0
@@ -501,7 +536,10 @@ class UnbinnedEngine(_EngineBase):
             for n in (P * D, P * S, P if has_scale else 0, P * S if has_eff else 0):
                 views.append(st["pin_in"][o:o + n] if n else None)
                 o += n
+        if zero_copy:
             out = dict(logl=st["pin_f"][:P], logsum=st["pin_f"][P:2 * P], musum=st["pin_f"][2 * P:], status=st["pin_i"])
+        elif direct_out:
+            out = dict(logl=st["pin_f"][:P], logsum=st["pin_f"][P:2 * P], musum=st["out_f"][2 * P:], status=st["out_i"])
         st["fn"], st["args"] = self._fused_args(P, views[0], views[1], views[2], views[3], st["ws"], out)
         if len(self._fused_cache) >= 8:
             self._fused_cache.clear()
@@ -515,9 +553,14 @@ class UnbinnedEngine(_EngineBase):
         if st["zero_copy"]:
             _cabi.check(st["fn"](*st["args"], ctypes.c_void_p(stream.cuda_stream)), "bi_unbinned_ll_batch")
             return
-        if st["n_in"]:
+        if st["n_in"] and not st["direct_in"]:
             st["dev_in"].copy_(st["pin_in"], non_blocking=True)
         _cabi.check(st["fn"](*st["args"], ctypes.c_void_p(stream.cuda_stream)), "bi_unbinned_ll_batch")
+        if st["direct_out"]:
+            if n_f > 2 * P:                                         # return_parts: the mu sums (K1 keeps them on the device)
+                st["pin_f"][2 * P:3 * P].copy_(st["out_f"][2 * P:3 * P], non_blocking=True)
+            st["pin_i"].copy_(st["out_i"], non_blocking=True)
+            return
         pg = self.peer_gather
         if pg is not None:
             if self.peer_mode == 'sum':
@@ -1369,9 +1412,10 @@ class TemplateUnbinnedEngine(_EngineBase):
         self.launches += 1
         return logl, logsum
 
-    def run_one_call(self, P, sched, zs_d, mult_d, scale_d, eff_d):
+    def run_one_call(self, P, sched, zs_d, mult_d, scale_d, eff_d, logl_out=None, logsum_out=None):
         """ONE C-ABI call (bi_template_ll_batch): K1 -> (template morph) -> K5 / K5b -> ragged finalize, launched back to
-        back.  Returns (dict with musum / status device tensors, logl [Q], logsum [Q]) in PAIR order."""
+        back.  Returns (dict with musum / status device tensors, logl [Q], logsum [Q]) in PAIR order.  The point inputs and
+        logl_out / logsum_out may be pinned host tensors (the kernels then read / write them over PCIe directly)."""
         torch = self.torch
         Q = sched["n_pairs"]
         mixture = int(self.mode == 'mixture')
@@ -1379,8 +1423,8 @@ class TemplateUnbinnedEngine(_EngineBase):
                                                           self.n_template_bins, mixture))
         ws = self.ws.get("ts_ws", nbytes, torch.uint8)
         o = dict(musum=self.ws.get("musum", P, torch.float64), status=self.ws.get("status", P, torch.int32))
-        logl = self.ws.get("ts_logl", Q, torch.float64)
-        logsum = self.ws.get("ts_logsum", Q, torch.float64)
+        logl = self.ws.get("ts_logl", Q, torch.float64) if logl_out is None else logl_out
+        logsum = self.ws.get("ts_logsum", Q, torch.float64) if logsum_out is None else logsum_out
         templates = self.templates_rows if mixture else self.templates
         row_stride, bin_stride = (self.n_template_bins, 1) if mixture else (self.row_stride, self.bin_stride)
         _cabi.check(self.lib.bi_template_ll_batch(
@@ -1443,10 +1487,29 @@ class TemplateUnbinnedEngine(_EngineBase):
         g_pin = self.ws.get("d2h_gather", n_x, torch.float64, pinned=True) if pg is not None else None
         state = {}
 
+        # small batches: K1 reads the staged points from pinned host memory and (unsharded) the finalize kernel writes
+        # logl / logsum there -- no copy node for them
+        direct_in = _DIRECT_IO and 0 < nbytes <= _DIRECT_IO_MAX_BYTES and sched["n_pairs"] == P
+        direct_out = direct_in and pg is None
+        if direct_in:
+            views, off = [], 0
+            for size in sizes:
+                views.append(pin[off:off + size] if size else None)
+                off += size
+
         def device_sequence():
             """H2D of the staged inputs, bi_template_ll_batch, the exchange step of a sharded evaluation, D2H of the
             results: everything the device does."""
-            dev.copy_(pin, non_blocking=True)
+            if not direct_in:
+                dev.copy_(pin, non_blocking=True)
+            if direct_out:
+                o, logl, logsum = self.run_one_call(P, sched, views[0], views[1], views[2], views[3],
+                                                    out_pin[:P], out_pin[P:2 * P])
+                if return_parts:
+                    out_pin[2 * P:].copy_(o["musum"], non_blocking=True)
+                st_pin.copy_(o["status"], non_blocking=True)
+                state["o"], state["logl"], state["logsum"] = o, logl, logsum
+                return
             o, logl, logsum = self.run_one_call(P, sched, views[0], views[1], views[2], views[3])
             if pg is not None:
                 # sharded evaluation, exchanged over NVLink peer memory by one launch: the rank-ordered sum of the

@@ -594,6 +594,73 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
         return LogLikelihoodBase.__call__(self, livetime_days=livetime_days, compute_pdf=compute_pdf,
                                           full_output=full_output, **kwargs)
 
+    def batch(self, params, names=None, livetime_days=None):
+        plans = self._scalar_plans
+        if plans is not None and self.is_data_set and getattr(self._engine, 'peer_gather', None) is None:
+            params = np.asarray(params, dtype=np.float64)
+            if params.ndim == 2 and params.shape[0] > 0:
+                key = ('batch', None if names is None else tuple(names), params.shape, livetime_days is None)
+                plan = plans.get(key)
+                if plan is None:
+                    if len(plans) > 64:
+                        plans.clear()
+                    plan = plans[key] = self._make_batch_plan(names, params.shape, livetime_days) or False
+                if plan:
+                    result = plan(params, livetime_days)
+                    if result is not NotImplemented:
+                        return result
+        return LogLikelihoodBase.batch(self, params, names, livetime_days=livetime_days)
+
+    def _make_batch_plan(self, names, shape, livetime_days):
+        """Closure evaluating ll.batch(params, names) for tables of this shape and column list, or None when the general
+        path must be used.  Same defaults, priors, device sequence and result arithmetic as LogLikelihoodBase.batch; the
+        columns go straight into the pinned staging buffer and the result is read straight out of the pinned result."""
+        engine = self._engine
+        if type(engine) is not UnbinnedEngine or not engine.uses_mma() or engine.n_events <= 0 or engine.peer_gather is not None:
+            return None
+        if True in self.source_apply_efficiency:
+            return None
+        names = self.parameter_names() if names is None else list(names)
+        P, k = shape
+        if k != len(names):
+            return None
+        try:
+            self._kwargs_to_settings(**{n: 1.0 for n in names})
+            scale, zero_base = self._livetime_scale(livetime_days)
+            defaults_mult, defaults_settings = self._kwargs_to_settings()
+        except Exception:
+            return None
+        if zero_base or any(not _is_number(v) for v in defaults_settings.values()):
+            return None
+        has_scale = scale is not None
+        zs_v, mult_v, scale_v, run = engine.batch_runner(P, has_scale)
+        z_cols = [(j, names.index(n) if n in names else -1, float(defaults_settings[n]))
+                  for j, n in enumerate(self.shape_parameters)]
+        m_cols = [(j, names.index(s + _RATE_SUFFIX) if s + _RATE_SUFFIX in names else -1, float(defaults_mult[j]))
+                  for j, s in enumerate(self.source_name_list)]
+        has_priors = any(p is not None for _, p, _ in self.shape_parameters.values()) or \
+            any(p is not None for p in self.rate_parameters.values())
+        error_mode = self.config.get('unphysical_behaviour') == 'error'
+        base_livetime = self.pdf_base_config.get('livetime_days')
+
+        def plan(params, livetime_days):
+            if engine.peer_gather is not None:
+                return NotImplemented
+            for j, c, default in z_cols:
+                zs_v[:, j] = params[:, c] if c >= 0 else default
+            for j, c, default in m_cols:
+                mult_v[:, j] = params[:, c] if c >= 0 else default
+            if has_scale:
+                scale_v[:] = livetime_days / base_livetime
+            priors = self._prior_sum(zs_v, mult_v) if has_priors else 0.0
+            logl, status = run()
+            if status.any():
+                if error_mode:
+                    return NotImplemented                      # the general path raises the reference's error
+                return np.where(status != 0, _NEG_INF, priors + logl)
+            return priors + logl
+        return plan
+
     def _make_scalar_plan(self, names, livetime_days):
         """Closure evaluating ll(**kwargs) for this set of keyword names, or None when the general path must be used.
         It reproduces LogLikelihoodBase.__call__ for P = 1 (same defaults, priors in the same order, same device call);
