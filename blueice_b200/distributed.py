@@ -140,20 +140,25 @@ class PeerGather(object):
         if local.numel() > self.n or (self.fallback is not None and local.numel() != self.n):
             raise ValueError("PeerGather was built for %d values per rank, got %d" % (self.n, local.numel()))
 
-    def gather(self, local):
-        """local: device tensor of <= n float64 -> device tensor [world, n] holding every rank's values (rows of ranks that
-        passed fewer than n values keep stale tails)."""
+    def gather(self, local, out=None):
+        """local: device tensor of <= n float64 -> tensor [world, n] holding every rank's values (rows of ranks that
+        passed fewer than n values keep stale tails).  out: where the kernel writes the rows (default: a device buffer);
+        a pinned host tensor of world * n float64 makes the kernel deliver them to the host itself, without a copy."""
         self._check(local)
         if self.fallback is not None:
             _dist().all_gather_into_tensor(self.out, local.contiguous(), group=self.group)
+            if out is not None:
+                out.copy_(self.out, non_blocking=True)
+                return out.view(self.world, self.n)
             return self.out.view(self.world, self.n)
+        dst = self.out if out is None else out
         _cabi.check(self.lib.bi_peer_exchange(_cabi.dev_ptr(local), local.numel(), self.n, _cabi.host_ptr(self.peer_ptrs),
-                                              self.world, self.rank, 0, None, None, _cabi.dev_ptr(self.out), self._stream()),
+                                              self.world, self.rank, 0, None, None, _cabi.dev_ptr(dst), self._stream()),
                     "bi_peer_exchange")
         self.launches += 1
-        return self.out.view(self.world, self.n)
+        return dst.view(self.world, self.n)
 
-    def reduce(self, local, musum=None, status=None):
+    def reduce(self, local, musum=None, status=None, out=None):
         """Sum over ranks, accumulated in rank order ((r0 + r1) + r2) + ... on every rank -> device tensor [len(local)];
         with musum / status (device tensors of the same length): -musum + total, -inf where status != 0
         (the event-sharded log likelihood without priors)."""
@@ -173,12 +178,16 @@ class PeerGather(object):
             if status is not None:
                 acc = torch.where(status != 0, torch.full_like(acc, -float('inf')), acc)
             self.total.copy_(acc)
+            if out is not None:
+                out[:m].copy_(self.total[:m], non_blocking=True)
+                return out[:m]
             return self.total[:m]
+        dst = self.total if out is None else out                   # out: e.g. a pinned host tensor (no copy afterwards)
         _cabi.check(self.lib.bi_peer_exchange(_cabi.dev_ptr(local), m, self.n, _cabi.host_ptr(self.peer_ptrs),
                                               self.world, self.rank, 1, _cabi.dev_ptr(musum), _cabi.dev_ptr(status),
-                                              _cabi.dev_ptr(self.total), self._stream()), "bi_peer_exchange")
+                                              _cabi.dev_ptr(dst), self._stream()), "bi_peer_exchange")
         self.launches += 1
-        return self.total[:m]
+        return dst[:m]
 
     def broadcast(self, local):
         """Stores only (bi_peer_broadcast): this rank's values go to slot (parity, rank) of every rank without waiting for
@@ -244,7 +253,8 @@ class PointShardedLikelihood(object):
             gathered = engine.last_gathered
         finally:
             engine.peer_gather = None
-        device_ll = gathered.reshape(-1) if min(counts) == n_rows else \
+        # (gathered may be a view of the engine's pinned result buffer: copy out)
+        device_ll = gathered.reshape(-1).copy() if min(counts) == n_rows else \
             np.concatenate([gathered[r, :c] for r, c in enumerate(counts)])
         has_priors = any(p is not None for _, p, _ in self.ll.shape_parameters.values()) or \
             any(p is not None for p in self.ll.rate_parameters.values())

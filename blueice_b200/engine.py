@@ -478,10 +478,20 @@ class UnbinnedEngine(_EngineBase):
         stream = self.torch.cuda.current_stream(self.device)
         sync = stream.synchronize
         logl_v, status_v = st["pin_f_np"][:P], st["pin_i_np"]
+        pg, mode = self.peer_gather, self.peer_mode            # a sharded evaluation: the exchange launch rides along
         n_launch = 1 if st["zero_copy"] else (4 if self.n_super > 0 else 2)
-        h2d, d2h = st["n_in"] * 8, P * 12
+        n_x = 0
+        x_view = None
+        if pg is not None:
+            n_launch += 0 if pg.fallback is not None else 1
+            n_x = P if mode == 'sum' else pg.world * pg.n
+            x_view = self._pin_x(st, n_x).numpy()
+            x_view = x_view[:P] if mode == 'sum' else x_view.reshape(pg.world, -1)
+        h2d, d2h = st["n_in"] * 8, P * 12 + n_x * 8
 
         def run():
+            if self.peer_gather is not pg or self.peer_mode != mode:
+                raise RuntimeError("batch_runner: the engine's exchange set-up changed since the runner was built")
             graph = self._fused_graph(st, P)
             if graph is not None:
                 graph.replay()
@@ -490,6 +500,8 @@ class UnbinnedEngine(_EngineBase):
             sync()
             self.launches += n_launch
             self.last_h2d_bytes, self.last_d2h_bytes = h2d, d2h
+            if pg is not None:                                   # views of the pinned exchange result (no copies)
+                self.last_gathered, self.last_total = (None, x_view) if mode == 'sum' else (x_view, None)
             return logl_v, status_v
         return zs_v, mult_v, scale_v, run
 
@@ -563,12 +575,12 @@ class UnbinnedEngine(_EngineBase):
             return
         pg = self.peer_gather
         if pg is not None:
+            # the exchange kernel delivers its result to pinned host memory itself (no copy node)
             if self.peer_mode == 'sum':
                 # event sharding: -musum + (rank-ordered sum of the shards' log sums), -inf where the point is unphysical
-                x = pg.reduce(st["out_f"][P:2 * P], st["out_f"][2 * P:3 * P], st["out_i"])
+                pg.reduce(st["out_f"][P:2 * P], st["out_f"][2 * P:3 * P], st["out_i"], out=self._pin_x(st, P))
             else:
-                x = pg.gather(st["out_f"][:P]).reshape(-1)          # point sharding: the logl rows of all ranks
-            self._pin_x(st, x.numel()).copy_(x, non_blocking=True)
+                pg.gather(st["out_f"][:P], out=self._pin_x(st, pg.world * pg.n))    # point sharding: all ranks' logl rows
         st["pin_f"][:n_f].copy_(st["out_f"][:n_f], non_blocking=True)
         st["pin_i"].copy_(st["out_i"], non_blocking=True)
 
@@ -1514,8 +1526,10 @@ class TemplateUnbinnedEngine(_EngineBase):
             if pg is not None:
                 # sharded evaluation, exchanged over NVLink peer memory by one launch: the rank-ordered sum of the
                 # shards' log sums (event sharding; pair order) or the logl rows of all ranks (point / toy sharding)
-                x = pg.reduce(logsum[:P]) if mode == 'sum' else pg.gather(logl[:P]).reshape(-1)
-                g_pin.copy_(x, non_blocking=True)
+                if mode == 'sum':                                    # the kernel writes to pinned host memory itself
+                    pg.reduce(logsum[:P], out=g_pin)
+                else:
+                    pg.gather(logl[:P], out=g_pin)
             out_pin[:P].copy_(logl, non_blocking=True)
             if return_parts:
                 out_pin[P:2 * P].copy_(logsum, non_blocking=True)

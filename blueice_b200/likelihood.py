@@ -596,10 +596,12 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
 
     def batch(self, params, names=None, livetime_days=None):
         plans = self._scalar_plans
-        if plans is not None and self.is_data_set and getattr(self._engine, 'peer_gather', None) is None:
+        if plans is not None and self.is_data_set:
             params = np.asarray(params, dtype=np.float64)
             if params.ndim == 2 and params.shape[0] > 0:
-                key = ('batch', None if names is None else tuple(names), params.shape, livetime_days is None)
+                pg = getattr(self._engine, 'peer_gather', None)          # sharded evaluations get plans of their own
+                key = ('batch', None if names is None else tuple(names), params.shape, livetime_days is None,
+                       None if pg is None else (id(pg), self._engine.peer_mode))
                 plan = plans.get(key)
                 if plan is None:
                     if len(plans) > 64:
@@ -616,8 +618,9 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
         path must be used.  Same defaults, priors, device sequence and result arithmetic as LogLikelihoodBase.batch; the
         columns go straight into the pinned staging buffer and the result is read straight out of the pinned result."""
         engine = self._engine
-        if type(engine) is not UnbinnedEngine or not engine.uses_mma() or engine.n_events <= 0 or engine.peer_gather is not None:
+        if type(engine) is not UnbinnedEngine or not engine.uses_mma() or engine.n_events <= 0:
             return None
+        pg = engine.peer_gather
         if True in self.source_apply_efficiency:
             return None
         names = self.parameter_names() if names is None else list(names)
@@ -644,7 +647,7 @@ class UnbinnedLogLikelihood(LogLikelihoodBase):
         base_livetime = self.pdf_base_config.get('livetime_days')
 
         def plan(params, livetime_days):
-            if engine.peer_gather is not None:
+            if engine.peer_gather is not pg:
                 return NotImplemented
             for j, c, default in z_cols:
                 zs_v[:, j] = params[:, c] if c >= 0 else default
