@@ -203,9 +203,12 @@ def workload_config(n_events, n_points):
             "n_events": int(n_events), "n_points_per_gpu": int(n_points), "n_sources": N_SOURCES,
             "n_anchors": len(ANCHORS) ** N_SHAPE, "lookup": "linear",
             "l2": "flushed between timed steps (512 MB write, outside the timed intervals)",
-            "parallelism": "points sharded over GPUs, dataset replicated, every step stores its results on every rank over NVLink "
-                           "(bi_peer_broadcast into symmetric memory, no waiting inside a step), one signal-pad barrier "
-                           "after the timed loop; the e2e arm (PointShardedLikelihood.batch) waits for all ranks per call"}
+            "parallelism": "weak: every GPU evaluates its own 4096 points of the scan on a replicated dataset (point sharding "
+                           "has no data-path collective); device arm: each step stores its results on every rank over NVLink "
+                           "(bi_peer_broadcast), one barrier after the timed loop; e2e arm: PointShardedLikelihood.batch, "
+                           "every call ends with one bi_peer_exchange launch (stores + flags + wait + delivery to pinned "
+                           "host memory) inside the call's CUDA graph; e2e also carries the strongly scaled scan, the "
+                           "event-sharded config 5 and the toy-sharded config 4 as flat keys"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -661,7 +661,9 @@ static int64_t bi_bin_chunk_points(int64_t n_points, int64_t n_bins) {
 // stored-terms form of the two Beeston-Barlow passes (few points, HBM-bound): all points in one pass, S <= 8 terms kept
 static bool bi_bin_store_terms(int64_t n_points, int64_t n_bins) {
     const int64_t tb_ld = (n_bins + 63) / 64 * 64;
-    return n_points * BI_BIN_STORE_S * tb_ld <= ((int64_t)1 << 26);
+    const char* e = getenv("BI_BINNED_STORE_LOG2");                  // experiments: scratch limit of the stored-terms form
+    const int lg = e ? atoi(e) : 26;
+    return n_points * BI_BIN_STORE_S * tb_ld <= ((int64_t)1 << lg);
 }
 
 // scratch layout (doubles): sum_t [P] | block sums A [PC, n_blocks] | block sums B [PC, n_blocks] | t_b [PC, tb_ld] (or the
@@ -731,8 +733,11 @@ static int bi_binned_launch_tile_nb(const BiBinnedArgs& a, int smem, int grid, c
 // one 1024-thread CTA per SM 11.5 / 0.26; 256-thread CTAs 12.7 / 0.19; 128-bin tiles 10.8 / 0.25.
 template <int MODE>
 static int bi_binned_launch_tile(const BiBinnedArgs& a, int smem, int grid, cudaStream_t st) {
-    return a.tile == 128 ? bi_binned_launch_tile_nb<MODE, 128, 512, 1>(a, smem, grid, st)
-                         : bi_binned_launch_tile_nb<MODE, 256, 512, 1>(a, smem, grid, st);
+    if (a.tile == 128) return bi_binned_launch_tile_nb<MODE, 128, 512, 1>(a, smem, grid, st);
+    // a handful of points: the evaluation streams the tensors once (HBM-bound) and a tile holds 8 (point, block) items
+    // at most per point -- 256-thread CTAs measured faster there (pass A at P = 1: 63 us against 77 us)
+    if (a.n_points <= 8) return bi_binned_launch_tile_nb<MODE, 256, 256, 1>(a, smem, grid, st);
+    return bi_binned_launch_tile_nb<MODE, 256, 512, 1>(a, smem, grid, st);
 }
 
 extern "C" int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const double* n_model_anchor_dev,

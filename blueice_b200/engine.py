@@ -91,12 +91,14 @@ class _Workspace(object):
         self.device = device
         self.capacity = {}
         self.buf = {}
+        self.version = 0              # bumped whenever a buffer is (re)allocated: captured CUDA graphs hold the old pointers
 
     def get(self, name, n, dtype, pinned=False):
         n = max(int(n), 1)
         key = (name, dtype, pinned)
         if self.capacity.get(key, 0) < n:
             cap = max(n, int(self.capacity.get(key, 0) * 1.5))
+            self.version += 1
             if pinned:
                 self.buf[key] = self.torch.empty(cap, dtype=dtype, pin_memory=True)
             else:
@@ -1557,14 +1559,14 @@ class TemplateUnbinnedEngine(_EngineBase):
                     with torch.cuda.graph(g, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
                         device_sequence()
                     entry["graph"] = g
-                    entry["ptrs"] = tuple(t.data_ptr() for t in self.ws.buf.values())
+                    entry["ptrs"] = self.ws.version
                 except Exception:
                     entry["graph"] = False
                     try:
                         torch.cuda.synchronize(self.device)
                     except Exception:
                         pass
-            if entry["graph"] and entry["ptrs"] == tuple(t.data_ptr() for t in self.ws.buf.values()):
+            if entry["graph"] and entry["ptrs"] == self.ws.version:
                 graph = entry["graph"]
             elif entry["graph"]:
                 entry["graph"], entry["calls"] = None, 1             # a workspace buffer moved: capture again later
