@@ -19,20 +19,8 @@
 
 #include "bi_space.cuh"
 #include "bi_plan.cuh"
+#include "bi_ts.cuh"
 
-#ifndef BI_TS_BATCH
-#define BI_TS_BATCH 4       /* template rows whose gathers are in flight together (K5) */
-#endif
-#define BI_TS_THREADS 128
-#define BI_TS_WARPS (BI_TS_THREADS / 32)
-#define BI_RANGE_LO ((1023 - 126) << 20)
-#define BI_RANGE_SPAN (253u << 20)
-
-struct BiTsSpace {
-    int32_t n_space;
-    int32_t n_corner;                              // 2^n_space lookup corners (linear), 1 (piecewise)
-    int64_t corner_off[1 << BI_MAX_SPACE_DIMS];    // element offset of lookup corner c from the low corner, x bin_stride
-};
 
 // ---------------------------------------------------------------------------------------------
 // event preparation (once per dataset): coordinates -> low-corner bin + fractions
@@ -55,87 +43,6 @@ k_template_prepare(const __grid_constant__ BiSpace sp, const __grid_constant__ B
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// template value of one row at one prepared event, scipy's operation order (== k_hist_lookup_linear)
-// ---------------------------------------------------------------------------------------------
-// Template values of one row at one prepared event.  Linear lookups read a PACKED layout in which element (row, bin)
-// holds the bin together with its neighbours along the last (and second-last) dimension, so that the lookup corners come
-// with ONE wide load -- K5 is bound by the number of scattered L2 requests, not by bytes:
-//   1-D:    [row][bin][2] = (T[b], T[b + 1])                                   one 128-bit load
-//   >= 2-D: [row][bin][4] = (T[b], T[b + 1], T[b + s], T[b + s + 1])            one 256-bit load (LDG.E.256) per
-//           s = stride of the second-last dimension                             four lookup corners
-template <int NS>
-__device__ __forceinline__ void bi_ts_gather(const double* __restrict__ V, const BiTsSpace& sp, double (&v)[1 << NS]) {
-    if constexpr (NS == 0) {
-        v[0] = __ldg(V);                                            // piecewise: the bin's value (plain layout)
-    } else if constexpr (NS == 1) {
-        const double2 t = __ldg(reinterpret_cast<const double2*>(V));
-        v[0] = t.x;
-        v[1] = t.y;
-    } else {
-#pragma unroll
-        for (int c = 0; c < (1 << NS); c += 4) {
-            const double* q = V + (c ? sp.corner_off[c] : 0);
-            asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
-                : "=d"(v[c]), "=d"(v[c + 1]), "=d"(v[c + 2]), "=d"(v[c + 3]) : "l"(q));
-        }
-    }
-}
-template <int NS>
-__device__ __forceinline__ double bi_ts_eval(const double (&v)[1 << NS], const double (&y)[NS > 0 ? NS : 1]) {
-    if constexpr (NS == 0) {
-        return v[0];
-    } else if constexpr (NS == 2) {
-        const double u0 = __dsub_rn(1.0, y[0]), u1 = __dsub_rn(1.0, y[1]);
-        double r = 0.0;
-        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v[0], u0), u1));
-        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v[1], u0), y[1]));
-        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v[2], y[0]), u1));
-        r = __dadd_rn(r, __dmul_rn(__dmul_rn(v[3], y[0]), y[1]));
-        return r;
-    } else {
-        double acc = 0.0;
-#pragma unroll
-        for (int c = 0; c < (1 << NS); ++c) {
-            double w = 1.0;
-#pragma unroll
-            for (int d = 0; d < NS; ++d) {
-                const int bit = (c >> (NS - 1 - d)) & 1;
-                w = __dmul_rn(w, bit ? y[d] : __dsub_rn(1.0, y[d]));
-            }
-            acc = __dadd_rn(acc, __dmul_rn(v[c], w));
-        }
-        return acc;
-    }
-}
-
-template <int NS>
-__device__ __forceinline__ double bi_ts_lookup(const double* __restrict__ V, const BiTsSpace& sp, const double (&y)[NS > 0 ? NS : 1]) {
-    double v[1 << NS];
-    bi_ts_gather<NS>(V, sp, v);
-    return bi_ts_eval<NS>(v, y);
-}
-
-// density of one event with the reference's semantics (likelihood.py:686-689), rare path
-template <int NS>
-static __device__ __noinline__ double bi_ts_slow_density(const double* __restrict__ T, const int64_t* rowoff, int64_t base,
-                                                         const BiTsSpace& sp, const double (&y)[NS > 0 ? NS : 1], int K, int S,
-                                                         const int32_t* __restrict__ term_source,
-                                                         const double* __restrict__ wterm,
-                                                         const double* __restrict__ mu, double outlier) {
-    double acc = 0.0;
-    for (int s = 0; s < S; ++s) {
-        double ps = 0.0;
-        for (int k = 0; k < K; ++k)
-            if (term_source[k] == s) ps = fma(bi_ts_lookup<NS>(T + rowoff[k] + base, sp, y), wterm[k], ps);
-        const double term = __dmul_rn(mu[s], ps);
-        if (term == term) acc = __dadd_rn(acc, term);               // nansum: NaN terms count as 0
-    }
-    return bi_fix_density(acc, outlier);
-}
-
-// pair group descriptor: pairs [first, first + count) of the pair list, all on dataset `dataset`
-struct BiTsGroup { int32_t first, count, dataset, pad; };
 
 // ---------------------------------------------------------------------------------------------
 // the kernel: one warp per unit (pair group, superblock), lane = event
@@ -152,7 +59,10 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
                     const int32_t* __restrict__ unit_group, int64_t n_units,
                     const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
                     double outlier, double* __restrict__ partial,
-                    const int32_t* __restrict__ group_order, const int32_t* __restrict__ n_ordered, int sb_max) {
+                    const int32_t* __restrict__ group_order, const int32_t* __restrict__ n_ordered, int sb_max,
+                    const double* __restrict__ pre) {
+    // pre (NP = 1 only): densities p_i already formed by the bin-major pass (bi_template_bm.cu), in event order -- the
+    // gather + contraction loop is skipped, the range test, the canonical tree and the rare path are the code below
     constexpr int NY = NS > 0 ? NS : 1;
     extern __shared__ __align__(16) unsigned char bi_ts_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -234,6 +144,10 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
             // bound by the latency / throughput of scattered L2 loads); the contraction keeps the term order
             constexpr int KB = (1 << NS) <= 4 ? BI_TS_BATCH : (BI_TS_BATCH / 2 > 0 ? BI_TS_BATCH / 2 : 1);
             int k = 0;
+            if (NP == 1 && pre) {
+                p[0] = valid ? pre[ev] : 1.0;
+                k = K;
+            }
 #pragma unroll 1
             for (; k + KB <= K; k += KB) {
                 double v[KB][1 << NS];
@@ -1196,7 +1110,8 @@ static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride,
                         const int32_t* term_source, const double* mus, const int32_t* status, int64_t n_groups,
                         const BiTsGroup* groups, const int64_t* unit_offset, const int32_t* unit_group, int64_t n_units,
                         const int32_t* pair_point, const int64_t* pair_partial_offset, double outlier, double* partial,
-                        const int32_t* group_order, const int32_t* n_ordered, int sb_max, cudaStream_t st) {
+                        const int32_t* group_order, const int32_t* n_ordered, int sb_max, const double* pre,
+                        cudaStream_t st) {
     const int smem = BI_TS_WARPS * K * (1 + NP) * 8;
     static int per_sm_cached[BI_TS_MAX_TERMS + 1] = {0};
     static int sms = 0;
@@ -1217,7 +1132,7 @@ static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride,
     k_template_partials<NP, NS><<<(unsigned)blocks, BI_TS_THREADS, smem, st>>>(
         T, row_stride, bin_stride, sp, ev_bin, ev_frac, ld_frac, dataset_offset, K, S, row, coef, wterm, term_source, mus,
         status, n_groups, groups, unit_offset, unit_group, n_units, pair_point, pair_partial_offset, outlier, partial,
-        group_order, n_ordered, sb_max);
+        group_order, n_ordered, sb_max, pre);
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         bi_set_error("k_template_partials<%d,%d> launch failed: %s (blocks=%lld, smem=%d, K=%d, units=%lld)", NP, NS,
@@ -1227,7 +1142,7 @@ static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride,
     return BI_OK;
 }
 
-static int bi_template_partials_impl(const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+int bi_template_partials_impl(const double* templates_dev, int64_t row_stride, int64_t bin_stride,
                                     int32_t n_space, const int32_t* n_bins_host, int32_t method,
                                     const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
                                     const int64_t* dataset_offset_dev, int32_t n_terms, int32_t n_sources,
@@ -1238,7 +1153,7 @@ static int bi_template_partials_impl(const double* templates_dev, int64_t row_st
                                     const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
                                     double outlier_likelihood, double* partial_dev,
                                     const int32_t* group_order_dev, const int32_t* n_ordered_dev, int32_t sb_max,
-                                    void* stream) {
+                                    const double* pre_dev, void* stream) {
     BiSpace space;
     int rc = bi_fill_space(&space, n_space, n_bins_host);
     if (rc != BI_OK) return rc;
@@ -1276,7 +1191,8 @@ static int bi_template_partials_impl(const double* templates_dev, int64_t row_st
                                       dataset_offset_dev, n_terms, n_sources, row_dev, coef_dev, wterm_dev,             \
                                       term_source_dev, mus_dev, status_dev, n_groups, groups, unit_offset_dev,          \
                                       unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,                 \
-                                      outlier_likelihood, partial_dev, group_order_dev, n_ordered_dev, sb_max, st);
+                                      outlier_likelihood, partial_dev, group_order_dev, n_ordered_dev, sb_max,         \
+                                      group_points == 1 ? pre_dev : nullptr, st);
     BI_TS_CASE(1, 0) BI_TS_CASE(1, 1) BI_TS_CASE(1, 2) BI_TS_CASE(1, 3) BI_TS_CASE(1, 4)
     BI_TS_CASE(BI_TS_GROUP_POINTS, 0) BI_TS_CASE(BI_TS_GROUP_POINTS, 1) BI_TS_CASE(BI_TS_GROUP_POINTS, 2)
     BI_TS_CASE(BI_TS_GROUP_POINTS, 3) BI_TS_CASE(BI_TS_GROUP_POINTS, 4)
@@ -1299,7 +1215,7 @@ extern "C" int bi_template_partials(const double* templates_dev, int64_t row_str
                                      ev_frac_dev, ld_frac, dataset_offset_dev, n_terms, n_sources, row_dev, coef_dev,
                                      wterm_dev, term_source_dev, mus_dev, status_dev, n_groups, group_points, groups_dev,
                                      unit_offset_dev, unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,
-                                     outlier_likelihood, partial_dev, nullptr, nullptr, 1, stream);
+                                     outlier_likelihood, partial_dev, nullptr, nullptr, 1, nullptr, stream);
 }
 
 extern "C" int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_offset_dev,
@@ -1606,10 +1522,79 @@ extern "C" int bi_template_ll_batch(int32_t n_dims, const int32_t* n_anchors_hos
                                            term_source, mus, status_dev, n_groups, group_points, groups_dev, unit_offset_dev,
                                            unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,
                                            outlier_likelihood, partial, group_order, n_ordered, (int32_t)max_partials,
-                                           stream);
+                                           nullptr, stream);
         }
         if (rc != BI_OK) return rc;
     }
     return bi_template_finalize(partial, pair_partial_offset_dev, pair_point_dev, musum_dev, status_dev, n_pairs,
+                                max_partials, logl_dev, logsum_dev, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// A toy sweep (one parameter point per dataset) with the densities formed bin-major (bi_template_bm.cu), in ONE call:
+// K1 -> point records -> k_bm_density -> k_template_partials on those densities (range test, canonical tree, rare path)
+// -> ragged finalize.  Same workspace as bi_template_ll_batch (mixture = 0); results bit-identical to it.
+// ---------------------------------------------------------------------------------------------
+extern "C" int bi_template_ll_toys_bm(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                                      int32_t n_sources, int64_t n_points,
+                                      const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                                      const double* eff_dev, const double* mus_anchor_dev, const uint8_t* allow_negative_host,
+                                      const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+                                      const double* templates_bm_dev, int64_t n_rows,
+                                      int32_t n_space, const int32_t* n_bins_host,
+                                      const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
+                                      const int64_t* dataset_offset_dev,
+                                      const int32_t* task_bin_dev, const int64_t* task_start_dev,
+                                      const int32_t* task_count_dev, int64_t n_tasks,
+                                      const int32_t* bm_toy_dev, const int32_t* bm_src_dev, const double* bm_frac_dev,
+                                      int64_t ld_bm,
+                                      int64_t n_groups, const int32_t* groups_dev, const int64_t* unit_offset_dev,
+                                      const int32_t* unit_group_dev, int64_t n_units, const int32_t* pair_point_dev,
+                                      const int64_t* pair_partial_offset_dev, int64_t n_partials, int64_t max_partials,
+                                      double outlier_likelihood, void* workspace_dev, int64_t workspace_bytes,
+                                      double* record_dev, double* density_dev,
+                                      double* logl_dev, double* logsum_dev, double* musum_dev, int32_t* status_dev,
+                                      void* stream) {
+    BI_REQUIRE(n_points >= 0, "negative size");
+    if (n_points == 0) return BI_OK;
+    BI_REQUIRE(n_groups == n_points, "bi_template_ll_toys_bm: one pair per dataset and point (got %lld groups for %lld points)",
+               (long long)n_groups, (long long)n_points);
+    BiSpace space;
+    int rc = bi_fill_space(&space, n_space, n_bins_host);
+    if (rc != BI_OK) return rc;
+    BI_REQUIRE(n_dims >= 0 && n_dims <= BI_MAX_DIMS, "n_dims=%d outside [0,%d]", n_dims, BI_MAX_DIMS);
+    BI_REQUIRE(n_sources >= 1 && n_sources <= BI_MAX_SOURCES, "n_sources=%d outside [1,%d]", n_sources, BI_MAX_SOURCES);
+    const int32_t K = (1 << n_dims) * n_sources;
+    const BiTemplateWorkspace w = bi_template_layout(n_dims, n_sources, n_points, n_partials, n_points, space.n_cells, 0);
+    BI_REQUIRE(workspace_dev && workspace_bytes >= w.total, "workspace too small: %lld < %lld bytes",
+               (long long)workspace_bytes, (long long)w.total);
+    BI_REQUIRE(((uintptr_t)workspace_dev & 255) == 0, "workspace_dev must be 256-byte aligned");
+    BI_REQUIRE(logl_dev && musum_dev && status_dev, "bi_template_ll_toys_bm: NULL output pointer");
+    char* base = (char*)workspace_dev;
+    int32_t* row = (int32_t*)(base + w.row);
+    double* coef = (double*)(base + w.coef);
+    double* wterm = (double*)(base + w.wterm);
+    int32_t* term_source = (int32_t*)(base + w.term_source);
+    double* mus = (double*)(base + w.mus);
+    double* partial = (double*)(base + w.partial);
+    rc = bi_point_setup(n_dims, n_anchors_host, axes_host, n_sources, n_points, zs_dev, rate_mult_dev, scale_dev, eff_dev,
+                        mus_anchor_dev, allow_negative_host, (int32_t*)(base + w.cell), (double*)(base + w.frac),
+                        (int32_t*)(base + w.corner), (double*)(base + w.weight), mus, musum_dev, status_dev, row, coef,
+                        wterm, term_source, stream);
+    if (rc != BI_OK) return rc;
+    if (n_units > 0) {
+        rc = bi_template_bm_density(templates_bm_dev, n_rows, n_space, n_dims, n_anchors_host, n_sources, n_points,
+                                    (const int32_t*)(base + w.cell), (const double*)(base + w.frac), mus, status_dev,
+                                    task_bin_dev, task_start_dev, task_count_dev, n_tasks, bm_toy_dev, bm_src_dev,
+                                    bm_frac_dev, ld_bm, record_dev, density_dev, stream);
+        if (rc != BI_OK) return rc;
+        rc = bi_template_partials_impl(templates_dev, row_stride, bin_stride, n_space, n_bins_host, BI_LOOKUP_LINEAR,
+                                       ev_bin_dev, ev_frac_dev, ld_frac, dataset_offset_dev, K, n_sources, row, coef, wterm,
+                                       term_source, mus, status_dev, n_groups, 1, groups_dev, unit_offset_dev,
+                                       unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,
+                                       outlier_likelihood, partial, nullptr, nullptr, 1, density_dev, stream);
+        if (rc != BI_OK) return rc;
+    }
+    return bi_template_finalize(partial, pair_partial_offset_dev, pair_point_dev, musum_dev, status_dev, n_points,
                                 max_partials, logl_dev, logsum_dev, stream);
 }

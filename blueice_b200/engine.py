@@ -185,6 +185,7 @@ _EMPTY_I32 = np.zeros(0, dtype=np.int32)
 _E2E_GRAPHS = os.environ.get('BI_E2E_GRAPHS', '1') != '0'     # replay the e2e sequence of a batch size as one CUDA graph
 _DIRECT_IO = os.environ.get('BI_DIRECT_IO', '1') != '0'        # kernels read / write small batches in pinned host memory
 _DIRECT_IO_MAX_BYTES = 1 << 20
+_BM_MIN_EVENTS = 4000000                                      # toy sets from this size on are swept bin-major (K5c)
 
 
 class _EngineBase(object):
@@ -1307,12 +1308,53 @@ class TemplateUnbinnedEngine(_EngineBase):
         return sched
 
     def toy_schedule(self):
-        """Pair t = (dataset t, point t), one pair per group; built once per set_datasets."""
+        """Pair t = (dataset t, point t), one pair per group; built once per set_datasets.  Large toy sets also get the
+        bin-major event order of bi_template_ll_toys_bm (key "bm")."""
         if self._toy_schedule is None:
             T = self.n_datasets
             idx = np.arange(T, dtype=np.int64)
             self._toy_schedule = self._upload_schedule(idx, idx, idx, np.ones(T, dtype=np.int64), 1)
+            self._toy_schedule["bm"] = self._bin_major_state()
         return self._toy_schedule
+
+    def _bin_major_state(self):
+        """Plumbing of the bin-major toy sweep (K5c, bi_template_bm.cu), once per toy set: the events of all toys sorted
+        by their low-corner bin (with their toy, their position in toy order and their lookup fractions), the task list
+        (bin, first event, <= 2048 events) and a bin-major copy of the packed templates.  None when the shape is not
+        served or the toy set is too small for the per-bin set-up to pay (BI_TS_BM=1 / 0 forces / forbids it)."""
+        torch = self.torch
+        env = os.environ.get('BI_TS_BM')
+        n, T = self.n_events, self.n_datasets
+        if env == '0' or self.mode != 'exact' or self.method != _cabi.LOOKUP_LINEAR or n == 0 or T < 2:
+            return None
+        if env != '1' and (n < _BM_MIN_EVENTS or T < 1024):
+            return None
+        if not self.lib.bi_template_bm_supported(self.n_space, self.method, self.grid.n_dims,
+                                                 _cabi.host_ptr(self.grid.n_anchors_i32), self.n_sources, self.n_rows):
+            return None
+        chunk = _cabi.BM_CHUNK
+        key = self.ev_bin[:n]
+        order = torch.argsort(key, stable=True)
+        sizes = torch.from_numpy(np.diff(self.offsets_host)).to(self.device)
+        toy_of_event = torch.repeat_interleave(torch.arange(T, device=self.device, dtype=torch.int32), sizes)
+        counts = torch.bincount(key.to(torch.int64), minlength=self.n_template_bins).cpu().numpy().astype(np.int64)
+        first = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        n_chunks = (counts + chunk - 1) // chunk
+        task_bin = np.repeat(np.arange(self.n_template_bins, dtype=np.int64), n_chunks)
+        within = np.arange(len(task_bin), dtype=np.int64) - np.repeat(np.cumsum(n_chunks) - n_chunks, n_chunks)
+        task_start = first[task_bin] + within * chunk
+        task_count = np.minimum(counts[task_bin] - within * chunk, chunk)
+        big_first = np.argsort(-task_count, kind='stable')               # long tasks first: the static round-robin balances
+        if getattr(self, "_templates_bm", None) is None:
+            self._templates_bm = self.templates.reshape(self.n_rows, self.n_template_bins, self.bin_stride) \
+                .permute(1, 0, 2).contiguous()
+        return dict(n_tasks=len(task_bin),
+                    task_bin=torch.from_numpy(task_bin[big_first].astype(np.int32)).to(self.device),
+                    task_start=torch.from_numpy(task_start[big_first]).to(self.device),
+                    task_count=torch.from_numpy(task_count[big_first].astype(np.int32)).to(self.device),
+                    toy=toy_of_event[order].contiguous(), src=order.to(torch.int32).contiguous(),
+                    frac=self.ev_frac[:, :n][:, order].contiguous(), ld=n,
+                    record_doubles=int(self.lib.bi_template_bm_record_doubles(self.grid.n_dims, self.n_sources)))
 
     def _cells_for_grouping(self, zs):
         """Host copy of the hypercube cell of every point (-1: out of range, evaluated alone and skipped on the
@@ -1441,6 +1483,28 @@ class TemplateUnbinnedEngine(_EngineBase):
         logsum = self.ws.get("ts_logsum", Q, torch.float64) if logsum_out is None else logsum_out
         templates = self.templates_rows if mixture else self.templates
         row_stride, bin_stride = (self.n_template_bins, 1) if mixture else (self.row_stride, self.bin_stride)
+        bm = sched.get("bm")
+        if bm is not None and sched["n_units"]:
+            # toy sweep with the densities formed bin-major (K5c): K1, records, densities, tree, finalize
+            record = self.ws.get("bm_record", P * bm["record_doubles"] + 8, torch.float64)
+            density = self.ws.get("bm_density", self.n_events, torch.float64)
+            _cabi.check(self.lib.bi_template_ll_toys_bm(
+                self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat),
+                self.n_sources, P, _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
+                _cabi.dev_ptr(self.mus_anchor), _cabi.host_ptr(self.allow_negative),
+                _cabi.dev_ptr(templates), row_stride, bin_stride, _cabi.dev_ptr(self._templates_bm), self.n_rows,
+                self.n_space, _cabi.host_ptr(self.n_bins_i32),
+                _cabi.dev_ptr(self.ev_bin), _cabi.dev_ptr(self.ev_frac), self.ld_frac, _cabi.dev_ptr(self.offsets),
+                _cabi.dev_ptr(bm["task_bin"]), _cabi.dev_ptr(bm["task_start"]), _cabi.dev_ptr(bm["task_count"]),
+                bm["n_tasks"], _cabi.dev_ptr(bm["toy"]), _cabi.dev_ptr(bm["src"]), _cabi.dev_ptr(bm["frac"]), bm["ld"],
+                sched["n_groups"], _cabi.dev_ptr(sched["groups"]), _cabi.dev_ptr(sched["unit_offset"]),
+                _cabi.dev_ptr(sched["unit_group"]), sched["n_units"], _cabi.dev_ptr(sched["pair_point"]),
+                _cabi.dev_ptr(sched["partial_offset"]), sched["n_partials"], sched["max_partials"],
+                self.outlier_likelihood, _cabi.dev_ptr(ws), ws.numel(), _cabi.dev_ptr(record), _cabi.dev_ptr(density),
+                _cabi.dev_ptr(logl), _cabi.dev_ptr(logsum), _cabi.dev_ptr(o["musum"]), _cabi.dev_ptr(o["status"]),
+                self._stream()), "bi_template_ll_toys_bm")
+            self.launches += 5
+            return o, logl, logsum
         _cabi.check(self.lib.bi_template_ll_batch(
             self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.host_ptr(self.grid.axes_concat),
             self.n_sources, P, _cabi.dev_ptr(zs_d), _cabi.dev_ptr(mult_d), _cabi.dev_ptr(scale_d), _cabi.dev_ptr(eff_d),
@@ -1572,7 +1636,7 @@ class TemplateUnbinnedEngine(_EngineBase):
                 entry["graph"], entry["calls"] = None, 1             # a workspace buffer moved: capture again later
         t_start = _time.perf_counter()
         n_launch = ((2 + (2 if self.mode == 'mixture' else 1)) if sched["n_units"] else 2) + \
-            (0 if pg is None or pg.fallback is not None else 1)
+            (0 if pg is None or pg.fallback is not None else 1) + (2 if sched.get("bm") is not None and sched["n_units"] else 0)
         if graph is not None:
             graph.replay()
             self.launches += n_launch

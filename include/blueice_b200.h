@@ -415,6 +415,59 @@ int bi_template_ll_batch(int32_t n_dims, const int32_t* n_anchors_host, const do
                          double* logl_dev, double* logsum_dev, double* musum_dev, int32_t* status_dev, void* stream);
 
 /*
+ * K5c -- a toy sweep (ONE parameter point per dataset) with the densities formed BIN-MAJOR (bi_template_bm.cu).
+ * Replaces, per toy, set_data -> Model.score_events -> HistogramPdfSource.pdf and the density of
+ * extended_loglikelihood (likelihood.py:531-562,678-690, model.py:97-99, source.py:225-240), bit-identical to
+ * bi_template_ll_batch on the same toys.
+ *
+ * Plumbing the caller prepares once per toy set (engine.TemplateUnbinnedEngine.set_datasets): the events of all toys sorted
+ * by their low-corner bin -- bm_toy_dev / bm_src_dev [N] (dataset index = point index, and position in toy order, of the
+ * bin-sorted event), bm_frac_dev [n_space, ld_bm] (lookup fractions, bin-sorted) -- and the task list: task t evaluates
+ * task_count[t] <= 2048 events of bin task_bin[t] starting at bin-sorted position task_start[t].
+ * templates_bm_dev: [prod(n_bins)][n_rows][pack] the packed templates of bi_template_partials, bin-major.
+ *
+ * bi_template_bm_supported     : 1 when the shape is served (linear lookup, 1-2 analysis dimensions, 1-4 shape
+ *                                parameters, <= 8 sources, <= 4096 hypercube cells, rows of one bin <= 160 kB)
+ * bi_template_bm_record_doubles: doubles per point record; record_dev holds n_points of them, 32-byte aligned
+ * bi_template_bm_density       : density_dev[i] = f(theta_{toy(i)}, x_i) for every event i (toy order) of a toy whose
+ *                                point has status 0; cell_dev / frac_dev / mus_dev / status_dev are K1's outputs
+ * bi_template_ll_toys_bm       : the whole sweep in one call: K1 -> records -> densities -> range test + canonical tree
+ *                                (bi_template_partials' kernel on the densities) -> bi_template_finalize.  Schedule
+ *                                arguments: the one-pair-per-dataset schedule of bi_template_ll_batch; workspace_dev:
+ *                                bi_template_workspace_bytes(..., mixture = 0).
+ */
+int bi_template_bm_supported(int32_t n_space, int32_t method, int32_t n_dims, const int32_t* n_anchors_host,
+                             int32_t n_sources, int64_t n_rows);
+int64_t bi_template_bm_record_doubles(int32_t n_dims, int32_t n_sources);
+int bi_template_bm_density(const double* templates_bm_dev, int64_t n_rows, int32_t n_space,
+                           int32_t n_dims, const int32_t* n_anchors_host, int32_t n_sources, int64_t n_points,
+                           const int32_t* cell_dev, const double* frac_dev, const double* mus_dev,
+                           const int32_t* status_dev,
+                           const int32_t* task_bin_dev, const int64_t* task_start_dev,
+                           const int32_t* task_count_dev, int64_t n_tasks,
+                           const int32_t* bm_toy_dev, const int32_t* bm_src_dev, const double* bm_frac_dev,
+                           int64_t ld_bm, double* record_dev, double* density_dev, void* stream);
+int bi_template_ll_toys_bm(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
+                           int32_t n_sources, int64_t n_points,
+                           const double* zs_dev, const double* rate_mult_dev, const double* scale_dev,
+                           const double* eff_dev, const double* mus_anchor_dev, const uint8_t* allow_negative_host,
+                           const double* templates_dev, int64_t row_stride, int64_t bin_stride,
+                           const double* templates_bm_dev, int64_t n_rows,
+                           int32_t n_space, const int32_t* n_bins_host,
+                           const int32_t* ev_bin_dev, const double* ev_frac_dev, int64_t ld_frac,
+                           const int64_t* dataset_offset_dev,
+                           const int32_t* task_bin_dev, const int64_t* task_start_dev,
+                           const int32_t* task_count_dev, int64_t n_tasks,
+                           const int32_t* bm_toy_dev, const int32_t* bm_src_dev, const double* bm_frac_dev,
+                           int64_t ld_bm,
+                           int64_t n_groups, const int32_t* groups_dev, const int64_t* unit_offset_dev,
+                           const int32_t* unit_group_dev, int64_t n_units, const int32_t* pair_point_dev,
+                           const int64_t* pair_partial_offset_dev, int64_t n_partials, int64_t max_partials,
+                           double outlier_likelihood, void* workspace_dev, int64_t workspace_bytes,
+                           double* record_dev, double* density_dev,
+                           double* logl_dev, double* logsum_dev, double* musum_dev, int32_t* status_dev, void* stream);
+
+/*
  * On-device toy Monte Carlo generation.
  *
  * Replaces Model.simulate (model.py:69-91) for models whose sources are histogram templates:

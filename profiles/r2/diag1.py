@@ -171,6 +171,17 @@ if "k5" in cases:
     zs_d, mult_d, scale_d, _, _ = eng._upload_points(zs, mult, np.full(T, lt), None)
     sched = eng.toy_schedule()
     out["k5_toys_1e5"] = {"device_ms": dev_time(lambda: eng.run_one_call(T, sched, zs_d, mult_d, scale_d, None), 6),
-                          "events": int(toys.n_events)}
+                          "events": int(toys.n_events), "bin_major": sched.get("bm") is not None,
+                          "n_tasks": None if sched.get("bm") is None else sched["bm"]["n_tasks"]}
+    if sched.get("bm") is not None:                    # the same sweep toy by toy (K5): bit-identical, slower
+        _, logl, _ = eng.run_one_call(T, sched, zs_d, mult_d, scale_d, None)
+        a = logl[:T].cpu().numpy().copy()
+        plain = dict(sched)
+        plain["bm"] = None
+        out["k5_toys_1e5"]["toy_major_device_ms"] = dev_time(lambda: eng.run_one_call(T, plain, zs_d, mult_d, scale_d, None), 4)
+        _, logl, _ = eng.run_one_call(T, plain, zs_d, mult_d, scale_d, None)
+        b = logl[:T].cpu().numpy().copy()
+        out["k5_toys_1e5"]["bit_identical"] = bool(np.array_equal(a, b))
+        out["k5_toys_1e5"]["finite"] = int(np.isfinite(a).sum())
 
 print("DIAG " + json.dumps(out))

@@ -329,3 +329,59 @@ def test_one_call_entry_equals_the_staged_calls(mode):
     for u, v in zip(a, b):
         assert np.array_equal(u, v)
     assert np.any(a[3] != 0) and np.any(np.isneginf(a[0]))           # out-of-range points included
+
+
+@pytest.mark.parametrize("shape", [(3, 3, (30, 24)), (2, 1, (40,)), (5, 2, (25, 20)), (1, 4, (12, 10))])
+def test_bin_major_toy_sweep_is_bit_identical_to_k5(shape, monkeypatch):
+    """K5c (bi_template_bm.cu): the densities of a toy sweep formed bin-major == the toy-by-toy kernel, bit for bit --
+    ragged and empty toys, out-of-range and unphysical points, dead template regions (rare path), 1-D and 2-D templates,
+    1..4 shape parameters."""
+    n_sources, n_shape, bins = shape
+    anchors = (-1., 0., 1.) if n_shape < 4 else (-1., 1.)
+    if len(bins) == 2:
+        axes, edges, templates, mus = _model(n_sources, n_shape, anchors, bins)
+    else:
+        rng0 = np.random.default_rng(3)
+        axes = [np.asarray(anchors)] * n_shape
+        edges = [np.linspace(0., 2., bins[0] + 1)]
+        g = len(anchors) ** n_shape
+        templates = rng0.uniform(0.2, 1.5, size=(len(anchors),) * n_shape + (n_sources,) + bins)
+        mus = rng0.uniform(50., 100., size=(len(anchors),) * n_shape + (n_sources,))
+    templates = templates.copy()
+    templates[..., :3] = 0.0                                    # a dead strip: p = 0 -> outlier path in some toys
+    rng = np.random.default_rng(17)
+    T = 300
+    sizes = rng.poisson(40, size=T)
+    sizes[[3, 77]] = 0
+    sizes[10] = 1
+    sizes[12] = 1100
+    sizes[13] = 5000                                            # one bin-major task cannot hold all events of a bin
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    n = int(offsets[-1])
+    coords = np.vstack([rng.uniform(e[0] - 0.05, e[-1] + 0.05, n) for e in edges])            # some outside: clipped
+    coords[:, offsets[13]:offsets[13] + 3000] = coords[:, offsets[13]:offsets[13] + 1]       # 3000 events in ONE bin
+    zs, mult = wl.scan_points(T, n_shape, n_sources, seed=6, z_range=(-1., 1.))
+    zs[20, 0] = 2.0                                             # out of range
+    mult[21, 0] = -1.0                                          # unphysical
+    zs[22] = -1.0                                               # grid corner
+    zs[23] = 0.0 if n_shape < 4 else 1.0                        # on an anchor
+
+    monkeypatch.setenv("BI_TS_BM", "0")
+    _, te0, _, _ = _engines(axes, edges, templates, mus)
+    te0.set_datasets(coords, offsets)
+    want, st0 = te0.evaluate_toys(zs, mult, return_status=True)
+    assert te0.toy_schedule()["bm"] is None
+    monkeypatch.setenv("BI_TS_BM", "1")
+    _, te1, _, _ = _engines(axes, edges, templates, mus)
+    te1.set_datasets(coords, offsets)
+    assert te1.toy_schedule()["bm"] is not None
+    for _ in range(4):                                          # eager calls, then the CUDA-graph replay
+        got, st1 = te1.evaluate_toys(zs, mult, return_status=True)
+        assert np.array_equal(got, want) and np.array_equal(st0, st1)
+    assert np.isneginf(got[20]) and np.isneginf(got[21]) and np.isfinite(got[22]) and np.isfinite(got[23])
+    ls0, mu0, _ = te0.evaluate_toys(zs, mult, return_parts=True)
+    ls1, mu1, _ = te1.evaluate_toys(zs, mult, return_parts=True)
+    assert np.array_equal(ls0, ls1) and np.array_equal(mu0, mu1)
+    # other points on the same toys (the records are rebuilt per call)
+    zs2, mult2 = wl.scan_points(T, n_shape, n_sources, seed=9, z_range=(-1., 1.))
+    assert np.array_equal(te1.evaluate_toys(zs2, mult2), te0.evaluate_toys(zs2, mult2))
