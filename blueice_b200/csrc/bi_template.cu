@@ -60,9 +60,14 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
                     const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
                     double outlier, double* __restrict__ partial,
                     const int32_t* __restrict__ group_order, const int32_t* __restrict__ n_ordered, int sb_max,
-                    const double* __restrict__ pre) {
+                    const double* __restrict__ pre, const int32_t* __restrict__ pre_corner,
+                    const double* __restrict__ pre_weight) {
     // pre (NP = 1 only): densities p_i already formed by the bin-major pass (bi_template_bm.cu), in event order -- the
-    // gather + contraction loop is skipped, the range test, the canonical tree and the rare path are the code below
+    // gather + contraction loop is skipped, the range test, the canonical tree and the rare path are the code below.
+    // The rows / weights of the rare path then come from K1's corner / weight outputs [P, C] (pre_corner, pre_weight:
+    // row_k = corner[k / S] * S + k % S, wterm_k = weight[k / S]) when a unit first needs them; row / coef / wterm and
+    // the prepared events are not read otherwise.
+    const bool use_pre = NP == 1 && pre != nullptr;
     constexpr int NY = NS > 0 ? NS : 1;
     extern __shared__ __align__(16) unsigned char bi_ts_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -111,12 +116,15 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
         }
         if (!live) continue;                                        // their results are -inf (finalize)
         __syncwarp();
-        for (int k = lane; k < K; k += 32) {
-            rowoff[k] = (int64_t)row[(int64_t)point[lead] * K + k] * row_stride;
+        if (!use_pre) {
+            for (int k = lane; k < K; k += 32) {
+                rowoff[k] = (int64_t)row[(int64_t)point[lead] * K + k] * row_stride;
 #pragma unroll
-            for (int q = 0; q < NP; ++q) coef_s[q * K + k] = coef[(int64_t)point[(live >> q) & 1u ? q : lead] * K + k];
+                for (int q = 0; q < NP; ++q) coef_s[q * K + k] = coef[(int64_t)point[(live >> q) & 1u ? q : lead] * K + k];
+            }
         }
         __syncwarp();
+        bool rows_ready = !use_pre;
 
         const int64_t ev_begin = dataset_offset[gp.dataset] + sb * BI_SUPERBLOCK;
         const int64_t left = dataset_offset[gp.dataset + 1] - ev_begin;
@@ -132,10 +140,15 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
         for (int e0 = 0; e0 < n_ev; e0 += BI_EVENT_BLOCK) {
             const bool valid = e0 + lane < n_ev;
             const int64_t ev = ev_begin + e0 + lane;
-            const int64_t base = valid ? (int64_t)ev_bin[ev] * bin_stride : 0;
+            int64_t base = 0;
             double y[NY];
 #pragma unroll
-            for (int d = 0; d < NY; ++d) y[d] = (NS > 0 && valid) ? ev_frac[(int64_t)d * ld_frac + ev] : 0.0;
+            for (int d = 0; d < NY; ++d) y[d] = 0.0;
+            if (!use_pre) {
+                base = valid ? (int64_t)ev_bin[ev] * bin_stride : 0;
+#pragma unroll
+                for (int d = 0; d < NY; ++d) y[d] = (NS > 0 && valid) ? ev_frac[(int64_t)d * ld_frac + ev] : 0.0;
+            }
 
             double p[NP];
 #pragma unroll
@@ -144,7 +157,7 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
             // bound by the latency / throughput of scattered L2 loads); the contraction keeps the term order
             constexpr int KB = (1 << NS) <= 4 ? BI_TS_BATCH : (BI_TS_BATCH / 2 > 0 ? BI_TS_BATCH / 2 : 1);
             int k = 0;
-            if (NP == 1 && pre) {
+            if (use_pre) {
                 p[0] = valid ? pre[ev] : 1.0;
                 k = K;
             }
@@ -195,6 +208,21 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
                 E[q] += e;
             }
             if (bad_any) {                                          // warp-uniform; rare: reference-semantics fallback
+                if (use_pre) {
+                    if (!rows_ready) {
+                        const int64_t pt = point[0];
+                        const int C = K / S;
+                        for (int k2 = lane; k2 < K; k2 += 32) {
+                            rowoff[k2] = ((int64_t)pre_corner[pt * C + k2 / S] * S + k2 % S) * row_stride;
+                            coef_s[k2] = pre_weight[pt * C + k2 / S];
+                        }
+                        __syncwarp();
+                        rows_ready = true;
+                    }
+                    base = valid ? (int64_t)ev_bin[ev] * bin_stride : 0;
+#pragma unroll
+                    for (int d = 0; d < NY; ++d) y[d] = (NS > 0 && valid) ? ev_frac[(int64_t)d * ld_frac + ev] : 0.0;
+                }
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     if (bad[q] && ((live >> q) & 1u)) {
@@ -202,8 +230,8 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
                         double l = 0.0;
                         if (class_bad && valid) {
                             const int64_t pt = point[q];
-                            l = log(bi_ts_slow_density<NS>(T, rowoff, base, sp, y, K, S, term_source, wterm + pt * K,
-                                                           mus + pt * S, outlier));
+                            l = log(bi_ts_slow_density<NS>(T, rowoff, base, sp, y, K, S, term_source,
+                                                           use_pre ? coef_s : wterm + pt * K, mus + pt * S, outlier));
                         }
                         l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
                         l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 8));
@@ -1111,7 +1139,7 @@ static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride,
                         const BiTsGroup* groups, const int64_t* unit_offset, const int32_t* unit_group, int64_t n_units,
                         const int32_t* pair_point, const int64_t* pair_partial_offset, double outlier, double* partial,
                         const int32_t* group_order, const int32_t* n_ordered, int sb_max, const double* pre,
-                        cudaStream_t st) {
+                        const int32_t* pre_corner, const double* pre_weight, cudaStream_t st) {
     const int smem = BI_TS_WARPS * K * (1 + NP) * 8;
     static int per_sm_cached[BI_TS_MAX_TERMS + 1] = {0};
     static int sms = 0;
@@ -1132,7 +1160,7 @@ static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride,
     k_template_partials<NP, NS><<<(unsigned)blocks, BI_TS_THREADS, smem, st>>>(
         T, row_stride, bin_stride, sp, ev_bin, ev_frac, ld_frac, dataset_offset, K, S, row, coef, wterm, term_source, mus,
         status, n_groups, groups, unit_offset, unit_group, n_units, pair_point, pair_partial_offset, outlier, partial,
-        group_order, n_ordered, sb_max, pre);
+        group_order, n_ordered, sb_max, pre, pre_corner, pre_weight);
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         bi_set_error("k_template_partials<%d,%d> launch failed: %s (blocks=%lld, smem=%d, K=%d, units=%lld)", NP, NS,
@@ -1153,7 +1181,8 @@ int bi_template_partials_impl(const double* templates_dev, int64_t row_stride, i
                                     const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
                                     double outlier_likelihood, double* partial_dev,
                                     const int32_t* group_order_dev, const int32_t* n_ordered_dev, int32_t sb_max,
-                                    const double* pre_dev, void* stream) {
+                                    const double* pre_dev, const int32_t* pre_corner_dev, const double* pre_weight_dev,
+                                    void* stream) {
     BiSpace space;
     int rc = bi_fill_space(&space, n_space, n_bins_host);
     if (rc != BI_OK) return rc;
@@ -1163,10 +1192,12 @@ int bi_template_partials_impl(const double* templates_dev, int64_t row_stride, i
     BI_REQUIRE(group_points == 1 || group_points == BI_TS_GROUP_POINTS, "group_points must be 1 or %d", BI_TS_GROUP_POINTS);
     BI_REQUIRE(n_groups >= 0 && n_units >= 0, "negative size");
     if (n_groups == 0 || n_units == 0) return BI_OK;
-    BI_REQUIRE(templates_dev && ev_bin_dev && dataset_offset_dev && row_dev && coef_dev && wterm_dev && term_source_dev &&
+    BI_REQUIRE(templates_dev && ev_bin_dev && dataset_offset_dev && term_source_dev &&
                    mus_dev && status_dev && groups_dev && unit_offset_dev && pair_point_dev && pair_partial_offset_dev &&
                    partial_dev,
                "bi_template_partials: NULL device pointer");
+    BI_REQUIRE(pre_dev ? (group_points == 1 && pre_corner_dev && pre_weight_dev) : (row_dev && coef_dev && wterm_dev),
+               "bi_template_partials: NULL term pointer");
     BI_REQUIRE(method == BI_LOOKUP_PIECEWISE || ev_frac_dev, "bi_template_partials: ev_frac_dev is NULL");
     const int pack = method == BI_LOOKUP_PIECEWISE ? 1 : (n_space == 1 ? 2 : 4);
     BI_REQUIRE(((uintptr_t)templates_dev & (8 * pack - 1)) == 0 && (row_stride % pack) == 0 && (bin_stride % pack) == 0,
@@ -1192,7 +1223,7 @@ int bi_template_partials_impl(const double* templates_dev, int64_t row_stride, i
                                       term_source_dev, mus_dev, status_dev, n_groups, groups, unit_offset_dev,          \
                                       unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,                 \
                                       outlier_likelihood, partial_dev, group_order_dev, n_ordered_dev, sb_max,         \
-                                      group_points == 1 ? pre_dev : nullptr, st);
+                                      pre_dev, pre_corner_dev, pre_weight_dev, st);
     BI_TS_CASE(1, 0) BI_TS_CASE(1, 1) BI_TS_CASE(1, 2) BI_TS_CASE(1, 3) BI_TS_CASE(1, 4)
     BI_TS_CASE(BI_TS_GROUP_POINTS, 0) BI_TS_CASE(BI_TS_GROUP_POINTS, 1) BI_TS_CASE(BI_TS_GROUP_POINTS, 2)
     BI_TS_CASE(BI_TS_GROUP_POINTS, 3) BI_TS_CASE(BI_TS_GROUP_POINTS, 4)
@@ -1215,7 +1246,7 @@ extern "C" int bi_template_partials(const double* templates_dev, int64_t row_str
                                      ev_frac_dev, ld_frac, dataset_offset_dev, n_terms, n_sources, row_dev, coef_dev,
                                      wterm_dev, term_source_dev, mus_dev, status_dev, n_groups, group_points, groups_dev,
                                      unit_offset_dev, unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,
-                                     outlier_likelihood, partial_dev, nullptr, nullptr, 1, nullptr, stream);
+                                     outlier_likelihood, partial_dev, nullptr, nullptr, 1, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int bi_template_finalize(const double* partial_dev, const int64_t* pair_partial_offset_dev,
@@ -1522,7 +1553,7 @@ extern "C" int bi_template_ll_batch(int32_t n_dims, const int32_t* n_anchors_hos
                                            term_source, mus, status_dev, n_groups, group_points, groups_dev, unit_offset_dev,
                                            unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,
                                            outlier_likelihood, partial, group_order, n_ordered, (int32_t)max_partials,
-                                           nullptr, stream);
+                                           nullptr, nullptr, nullptr, stream);
         }
         if (rc != BI_OK) return rc;
     }
@@ -1571,16 +1602,13 @@ extern "C" int bi_template_ll_toys_bm(int32_t n_dims, const int32_t* n_anchors_h
     BI_REQUIRE(((uintptr_t)workspace_dev & 255) == 0, "workspace_dev must be 256-byte aligned");
     BI_REQUIRE(logl_dev && musum_dev && status_dev, "bi_template_ll_toys_bm: NULL output pointer");
     char* base = (char*)workspace_dev;
-    int32_t* row = (int32_t*)(base + w.row);
-    double* coef = (double*)(base + w.coef);
-    double* wterm = (double*)(base + w.wterm);
     int32_t* term_source = (int32_t*)(base + w.term_source);
     double* mus = (double*)(base + w.mus);
     double* partial = (double*)(base + w.partial);
     rc = bi_point_setup(n_dims, n_anchors_host, axes_host, n_sources, n_points, zs_dev, rate_mult_dev, scale_dev, eff_dev,
                         mus_anchor_dev, allow_negative_host, (int32_t*)(base + w.cell), (double*)(base + w.frac),
-                        (int32_t*)(base + w.corner), (double*)(base + w.weight), mus, musum_dev, status_dev, row, coef,
-                        wterm, term_source, stream);
+                        (int32_t*)(base + w.corner), (double*)(base + w.weight), mus, musum_dev, status_dev, nullptr, nullptr,
+                        nullptr, term_source, stream);           // no per-point term lists: the records carry the inputs
     if (rc != BI_OK) return rc;
     if (n_units > 0) {
         rc = bi_template_bm_density(templates_bm_dev, n_rows, n_space, n_dims, n_anchors_host, n_sources, n_points,
@@ -1589,10 +1617,11 @@ extern "C" int bi_template_ll_toys_bm(int32_t n_dims, const int32_t* n_anchors_h
                                     bm_frac_dev, ld_bm, record_dev, density_dev, stream);
         if (rc != BI_OK) return rc;
         rc = bi_template_partials_impl(templates_dev, row_stride, bin_stride, n_space, n_bins_host, BI_LOOKUP_LINEAR,
-                                       ev_bin_dev, ev_frac_dev, ld_frac, dataset_offset_dev, K, n_sources, row, coef, wterm,
-                                       term_source, mus, status_dev, n_groups, 1, groups_dev, unit_offset_dev,
+                                       ev_bin_dev, ev_frac_dev, ld_frac, dataset_offset_dev, K, n_sources, nullptr, nullptr,
+                                       nullptr, term_source, mus, status_dev, n_groups, 1, groups_dev, unit_offset_dev,
                                        unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,
-                                       outlier_likelihood, partial, nullptr, nullptr, 1, density_dev, stream);
+                                       outlier_likelihood, partial, nullptr, nullptr, 1, density_dev,
+                                       (const int32_t*)(base + w.corner), (const double*)(base + w.weight), stream);
         if (rc != BI_OK) return rc;
     }
     return bi_template_finalize(partial, pair_partial_offset_dev, pair_point_dev, musum_dev, status_dev, n_points,

@@ -29,6 +29,9 @@
 #define BI_BM_CHUNK 2048                 /* events per task */
 #define BI_BM_PER_THREAD (BI_BM_CHUNK / BI_BM_THREADS)
 #define BI_BM_MAX_SOURCES 8
+#ifndef BI_BM_MIN_CTAS
+#define BI_BM_MIN_CTAS 3
+#endif
 #define BI_BM_MAX_DIMS 4
 #define BI_BM_MAX_CELLS 4096
 #define BI_BM_MAX_ROW_BYTES (160 * 1024)
@@ -103,12 +106,12 @@ static __device__ void bi_bm_scan(int* v, int n, int* carry) {
 
 // shared memory: [stages] row stages (row_bytes each, 128-byte aligned) | event slots: y [NS][CHUNK], toy, src |
 // hist [n_cells + 2] | carry [8] | mbarriers [2]
-template <int NS, int D>
-__global__ void __launch_bounds__(BI_BM_THREADS)
+template <int NS, int D, int S>
+__global__ void __launch_bounds__(BI_BM_THREADS, BI_BM_MIN_CTAS)
 k_bm_density(const __grid_constant__ BiBmArgs a) {
     constexpr int C = 1 << D;
     constexpr int PACK = NS == 1 ? 2 : 4;
-    constexpr int RMAX = (1 + D + BI_BM_MAX_SOURCES + 3) / 4 * 4;
+    constexpr int R = (1 + D + S + 3) / 4 * 4;
     extern __shared__ __align__(128) unsigned char bi_bm_smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int row_stage = (a.row_bytes + 127) & ~127;
@@ -119,7 +122,7 @@ k_bm_density(const __grid_constant__ BiBmArgs a) {
     int* s_hist = s_src + BI_BM_CHUNK;                                                             // [n_cells + 2]
     int* s_carry = s_hist + a.n_cells + 2;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_carry + 8) + 7) & ~(uintptr_t)7);
-    const int S = a.S, R = a.R, n_cells = a.n_cells;
+    const int n_cells = a.n_cells;
 
     if (tid < 2) bi_mbar_init(&s_bar[tid], 1);
     if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -128,6 +131,14 @@ k_bm_density(const __grid_constant__ BiBmArgs a) {
         bi_mbar_expect_tx(&s_bar[buf], (unsigned)a.row_bytes);
         bi_bulk_g2s(reinterpret_cast<unsigned char*>(s_rows) + (size_t)buf * row_stage,
                     a.tbm + (int64_t)a.task_bin[task] * a.n_rows * a.pack, (unsigned)a.row_bytes, &s_bar[buf]);
+    };
+    // the record of one point: {int2(base anchor, cell id)}, frac [D], mus [S] -- R / 4 256-bit loads
+    auto load_record = [&](int toy, double (&rb)[R]) {
+        const double* rp = a.rec + (int64_t)toy * R;
+#pragma unroll
+        for (int i = 0; i < R / 4; ++i)
+            asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                : "=d"(rb[4 * i]), "=d"(rb[4 * i + 1]), "=d"(rb[4 * i + 2]), "=d"(rb[4 * i + 3]) : "l"(rp + 4 * i));
     };
     unsigned parity[2] = {0, 0};
     int buf = 0;
@@ -154,10 +165,11 @@ k_bm_density(const __grid_constant__ BiBmArgs a) {
 #pragma unroll
         for (int i = 0; i < BI_BM_PER_THREAD; ++i) {
             const int j = tid + BI_BM_THREADS * i;
-            const bool ok = j < count;
-            toy[i] = ok ? __ldg(a.bm_toy + start + j) : 0;
-            cid[i] = ok ? __double2hiint(__ldg(a.rec + (int64_t)toy[i] * R)) : n_cells + 1;
+            toy[i] = j < count ? __ldg(a.bm_toy + start + j) : -1;
         }
+#pragma unroll
+        for (int i = 0; i < BI_BM_PER_THREAD; ++i)
+            cid[i] = toy[i] >= 0 ? __double2hiint(__ldg(a.rec + (int64_t)toy[i] * R)) : n_cells + 1;
 #pragma unroll
         for (int i = 0; i < BI_BM_PER_THREAD; ++i) {
             // warp-aggregated counter: one shared-memory atomic per distinct cell of the warp
@@ -174,7 +186,7 @@ k_bm_density(const __grid_constant__ BiBmArgs a) {
 #pragma unroll
         for (int i = 0; i < BI_BM_PER_THREAD; ++i) {
             const int j = tid + BI_BM_THREADS * i;
-            if (j < count) {
+            if (toy[i] >= 0) {
                 const int slot = s_hist[cid[i]] + pos[i];
                 s_toy[slot] = toy[i];
                 s_src[slot] = __ldg(a.bm_src + start + j);
@@ -188,72 +200,90 @@ k_bm_density(const __grid_constant__ BiBmArgs a) {
         parity[buf] ^= 1;
         const double* rows = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(s_rows) + (size_t)buf * row_stage);
 
-        // ---- phase 3: one event per thread and step; lanes of a warp mostly share their cell (broadcast row loads)
+        // ---- phase 3: one event per thread and step; lanes of a warp mostly share their cell (broadcast row loads).
+        // The record of the thread's next event and the rows of the next morph corner are in flight while one corner's
+        // S rows are evaluated.
+        double rb[R];
+        if (tid < n_live) load_record(s_toy[tid], rb);
         for (int q = tid; q < n_live; q += BI_BM_THREADS) {
             double y[NS];
 #pragma unroll
             for (int d = 0; d < NS; ++d) y[d] = s_y[d * BI_BM_CHUNK + q];
-            const double* rp = a.rec + (int64_t)s_toy[q] * R;
-            double rb[RMAX];
-#pragma unroll
-            for (int i = 0; i < RMAX / 4; ++i) {
-                if (4 * i < R)
-                    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
-                        : "=d"(rb[4 * i]), "=d"(rb[4 * i + 1]), "=d"(rb[4 * i + 2]), "=d"(rb[4 * i + 3]) : "l"(rp + 4 * i));
-                else rb[4 * i] = rb[4 * i + 1] = rb[4 * i + 2] = rb[4 * i + 3] = 0.0;
-            }
+            const int out = s_src[q];
             const int base_anchor = __double2loint(rb[0]);
-            double f1[D], f0[D];
+            double f1[D], f0[D], mu[S];
 #pragma unroll
             for (int d = 0; d < D; ++d) { f1[d] = rb[1 + d]; f0[d] = __dsub_rn(1.0, f1[d]); }
+#pragma unroll
+            for (int s = 0; s < S; ++s) mu[s] = rb[1 + D + s];
+            if (q + BI_BM_THREADS < n_live) load_record(s_toy[q + BI_BM_THREADS], rb);
+            double v[2][S][PACK];
+            auto load_corner = [&](int c, double (&vc)[S][PACK]) {
+                const double* rc = rows + (size_t)(base_anchor + a.corner_delta[c]) * (S * PACK);
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+#pragma unroll
+                    for (int h = 0; h < PACK; h += 2) {
+                        const double2 t = *reinterpret_cast<const double2*>(rc + s * PACK + h);
+                        vc[s][h] = t.x;
+                        vc[s][h + 1] = t.y;
+                    }
+                }
+            };
+            load_corner(0, v[0]);
             double p = 0.0;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
+                if (c + 1 < C) load_corner(c + 1, v[(c + 1) & 1]);
                 double w = ((c >> (D - 1)) & 1) ? f1[0] : f0[0];                   // fl(1 * t_0) = t_0
 #pragma unroll
                 for (int d = 1; d < D; ++d) w = __dmul_rn(w, ((c >> (D - 1 - d)) & 1) ? f1[d] : f0[d]);
-                const double* rc = rows + (size_t)(base_anchor + a.corner_delta[c]) * S * PACK;
 #pragma unroll
-                for (int s = 0; s < BI_BM_MAX_SOURCES; ++s) {
-                    if (s < S) {
-                        const double coef = __dmul_rn(w, rb[1 + D + s]);
-                        double v[1 << NS];
-                        if (NS == 1) {
-                            const double2 t = *reinterpret_cast<const double2*>(rc + s * PACK);
-                            v[0] = t.x; v[1] = t.y;
-                        } else {
-                            const double2 t0 = *reinterpret_cast<const double2*>(rc + s * PACK);
-                            const double2 t1 = *reinterpret_cast<const double2*>(rc + s * PACK + 2);
-                            v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
-                        }
-                        p = fma(bi_ts_eval<NS>(v, y), coef, p);
-                    }
+                for (int s = 0; s < S; ++s) {
+                    double vv[1 << NS];
+#pragma unroll
+                    for (int h = 0; h < PACK; ++h) vv[h] = v[c & 1][s][h];
+                    p = fma(bi_ts_eval<NS>(vv, y), __dmul_rn(w, mu[s]), p);
                 }
             }
-            a.pbuf[s_src[q]] = p;
+            a.pbuf[out] = p;
         }
         __syncthreads();                                          // slots, histogram and this row stage may be reused
         if (a.stages == 2) buf ^= 1;
     }
 }
 
-template <int NS, int D>
+template <int NS, int D, int S>
 static int bi_bm_launch(const BiBmArgs& a, int smem, cudaStream_t st) {
     static int per_sm = 0, sms = 0, smem_set = 0;
     if (!per_sm || smem > smem_set) {
         int dev = 0;
         BI_CUDA_CHECK(cudaGetDevice(&dev));
         BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        BI_CUDA_CHECK(cudaFuncSetAttribute(k_bm_density<NS, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BI_CUDA_CHECK(cudaFuncSetAttribute(k_bm_density<NS, D, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_set = smem;
-        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bm_density<NS, D>, BI_BM_THREADS, smem));
-        BI_REQUIRE(per_sm >= 1, "k_bm_density<%d,%d> does not fit on this device (%d bytes of shared memory)", NS, D, smem);
+        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bm_density<NS, D, S>, BI_BM_THREADS, smem));
+        BI_REQUIRE(per_sm >= 1, "k_bm_density<%d,%d,%d> does not fit on this device (%d bytes of shared memory)", NS, D, S, smem);
     }
     int64_t blocks = (int64_t)sms * per_sm;
     if (blocks > a.n_tasks) blocks = a.n_tasks;
-    k_bm_density<NS, D><<<(unsigned)blocks, BI_BM_THREADS, smem, st>>>(a);
+    k_bm_density<NS, D, S><<<(unsigned)blocks, BI_BM_THREADS, smem, st>>>(a);
     BI_LAUNCH_CHECK();
     return BI_OK;
+}
+
+template <int NS, int D>
+static int bi_bm_launch_s(const BiBmArgs& a, int smem, cudaStream_t st) {
+    switch (a.S) {
+        case 1: return bi_bm_launch<NS, D, 1>(a, smem, st);
+        case 2: return bi_bm_launch<NS, D, 2>(a, smem, st);
+        case 3: return bi_bm_launch<NS, D, 3>(a, smem, st);
+        case 4: return bi_bm_launch<NS, D, 4>(a, smem, st);
+        case 5: return bi_bm_launch<NS, D, 5>(a, smem, st);
+        case 6: return bi_bm_launch<NS, D, 6>(a, smem, st);
+        case 7: return bi_bm_launch<NS, D, 7>(a, smem, st);
+        default: return bi_bm_launch<NS, D, 8>(a, smem, st);
+    }
 }
 
 extern "C" int bi_template_bm_supported(int32_t n_space, int32_t method, int32_t n_dims, const int32_t* n_anchors_host,
@@ -329,7 +359,7 @@ extern "C" int bi_template_bm_density(const double* templates_bm_dev, int64_t n_
     BI_LAUNCH_CHECK();
     const int smem = a.stages * ((a.row_bytes + 127) & ~127) + n_space * BI_BM_CHUNK * 8 + 2 * BI_BM_CHUNK * 4 +
                      ((int)n_cells + 2 + 8) * 4 + 8 + 2 * 8;
-#define BI_BM_CASE(NSV, DV) if (n_space == NSV && n_dims == DV) return bi_bm_launch<NSV, DV>(a, smem, st);
+#define BI_BM_CASE(NSV, DV) if (n_space == NSV && n_dims == DV) return bi_bm_launch_s<NSV, DV>(a, smem, st);
     BI_BM_CASE(1, 1) BI_BM_CASE(1, 2) BI_BM_CASE(1, 3) BI_BM_CASE(1, 4)
     BI_BM_CASE(2, 1) BI_BM_CASE(2, 2) BI_BM_CASE(2, 3) BI_BM_CASE(2, 4)
 #undef BI_BM_CASE

@@ -112,4 +112,5 @@ int bi_template_partials_impl(const double* templates_dev, int64_t row_stride, i
                               const int32_t* pair_point_dev, const int64_t* pair_partial_offset_dev,
                               double outlier_likelihood, double* partial_dev,
                               const int32_t* group_order_dev, const int32_t* n_ordered_dev, int32_t sb_max,
-                              const double* pre_dev, void* stream);
+                              const double* pre_dev, const int32_t* pre_corner_dev, const double* pre_weight_dev,
+                              void* stream);
