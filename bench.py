@@ -511,12 +511,25 @@ def other_configs(args, rank, world, device):
                     "evaluations_per_s": info["evaluations"] / fit_s, "converged": int(info["converged"].sum())}
         ll.set_toy_data(toys)
     n_ev = toys.n_events
+    # the sweep against HBM: SURVEY.md 8d counts 20 bytes per event (prepared event: bin + two fractions); the bin-major form
+    # moves 24 (bin-sorted event) + 8 written + 8 read (density) per event.  It is bound by the L1 data pipe (shared-memory
+    # row loads + the scattered per-toy records), see profiles/r2_k5c_toys_ncu.md; DRAM traffic from the committed capture.
+    c4_roofline = {"bound": "hbm", "bytes_alg": 20.0 * n_ev, "achieved": 20.0 * n_ev / t_dev / 1e9, "peak": measured_peaks()[0]["hbm_gbs"],
+                   "unit": "GB/s", "frac": 20.0 * n_ev / t_dev / 1e9 / measured_peaks()[0]["hbm_gbs"],
+                   "traffic": ncu_traffic("c4_bin_major_density") if sched.get("bm") is not None else None,
+                   "limiter": "L1 data pipe (LSU wavefronts 64 % of peak, FP64 pipe 40 %): 24 rows x 32 B of shared-memory "
+                              "operands per event; FP64 floor of the reference's operation order 1.96 ms per 1e8 events",
+                   "note": "whole sweep (K1, records, densities, tree, finalize) against SURVEY.md 8d's 20 B per event"}
     out["config4_toys"] = {
         "workload": "toy-MC: %d toys per GPU x ~1000 events, 3 sources, 3 shape parameters x 5 anchors (125 anchors), "
                     "100x100 templates, one parameter point per toy" % T,
         "api": "ll.batch_toys" if world == 1 else "distributed.ToyShardedLikelihood.batch_toys (toys sharded over the ranks, "
                "results of all ranks gathered over NVLink by one bi_peer_exchange launch inside the evaluation's CUDA graph)",
-        "kernel": "k_template_partials<1,2> (fused template lookup + morph + log-sum, bit-identical to K3 + K2)",
+        "kernel": ("k_bm_density<2,3,3> + k_template_partials<1,2,pre> (densities formed bin-major: the rows of one bin staged in "
+                   "shared memory by one TMA bulk copy, events bucketed by hypercube cell, per-toy records; range test + canonical "
+                   "tree + rare path by K5's own code; bit-identical to K3 + K2)") if sched.get("bm") is not None else
+                  "k_template_partials<1,2> (fused template lookup + morph + log-sum, bit-identical to K3 + K2)",
+        "roofline": c4_roofline,
         "toys_per_gpu": T, "events_per_gpu": int(n_ev), "n_gpus": world, "finite_results": int(np.isfinite(res).sum()),
         "device": {"ms": t_dev * 1e3, "toys_per_s": world * T / t_dev, "point_events_per_s": world * n_ev / t_dev},
         "e2e": {"ms": t_e2e * 1e3, "toys_per_s": world * T / t_e2e, "point_events_per_s": world * n_ev / t_e2e,
@@ -631,17 +644,28 @@ def other_configs(args, rank, world, device):
     for P in (1, P3):
         zs_d, mult_d, _, _, _ = beng._upload_points(zs3[:P], mult3[:P], None, None)
         zs_d, mult_d = zs_d.clone(), mult_d.clone()
+        # device time: the launch sequence of one evaluation (K1, schedule, pass A, total, pass B, total) replayed as a CUDA
+        # graph -- what BinnedEngine.evaluate does from its third call on -- between two events (no host work inside)
+        for _ in range(2):
+            beng.run_device(P, zs_d, mult_d, None, None)
+        torch.cuda.synchronize()
+        g3 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g3, capture_error_mode="thread_local"):
+            beng.run_device(P, zs_d, mult_d, None, None)
         dm = []
         for k in range(8):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            beng.run_device(P, zs_d, mult_d, None, None)
+            g3.replay()
             b.record()
             torch.cuda.synchronize()
             if k > 1:
                 dm.append(a.elapsed_time(b))
+        del g3
+        for _ in range(4):                                         # the third call captures the evaluation's CUDA graph
+            beng.evaluate(zs3[:P], mult3[:P])
         ts = []
-        for _ in range(3):
+        for _ in range(10 if P == 1 else 3):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             beng.evaluate(zs3[:P], mult3[:P])

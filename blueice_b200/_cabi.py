@@ -89,6 +89,7 @@ SIGNATURES = {
                                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_template_bm_supported": (ctypes.c_int, [_i32, _i32, _i32, _c_void_p, _i32, _i64]),
     "bi_template_bm_record_doubles": (_i64, [_i32, _i32]),
+    "bi_template_bm_chunk": (_i32, []),
     "bi_template_bm_density": (ctypes.c_int, [_c_void_p, _i64, _i32, _i32, _c_void_p, _i32, _i64,
                                               _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                               _c_void_p, _c_void_p, _c_void_p, _i64,
@@ -144,7 +145,6 @@ MMA_MAX_TERMS = 128
 PLAN_MAX_CELLS = 16384
 TS_MAX_TERMS = 256
 TS_GROUP_POINTS = 8
-BM_CHUNK = 2048          # events per task of the bin-major toy sweep (BI_BM_CHUNK, bi_template_bm.cu)
 MIX_GROUP_POINTS = 8
 MIX_GROUP_POINTS_WIDE = 16
 POINT_OUT_OF_RANGE = 1

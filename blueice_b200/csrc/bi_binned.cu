@@ -43,11 +43,26 @@ struct BiBinnedArgs {
     const int32_t* groups;         // [n_groups, 4] (first, count, -, -): points of a group share their hypercube cell
     const int32_t* header;         // header[0] = n_groups
     double* tbuf;                  // [P, ld] t_b = A_b * w_b of the Beeston-Barlow pass (written by MODE 1, read by MODE 2)
-    double* blockval;              // [P, n_blocks] tree-reduced sums of 32-bin blocks
+    double* blockval;              // [P, 16 * n_super] tree-reduced sums of 32-bin blocks, block k of a point at bi_bv_index(k)
     int64_t n_blocks, n_tiles, tb_ld;
     int32_t tile;                  // bins per tile: 128 or 256
     int32_t store_terms;           // MODE 1: keep all S terms of lambda_b per (point, bin) in tbuf [P, BI_BIN_STORE_S, tb_ld]
+    int32_t bv_interleaved;        // layout of blockval rows, see bi_bv_index
+    double* pt_const;              // [P, 4] per-point constants of the Beeston-Barlow passes: sum_a, p_cal (k_binned_plan),
+                                   // sum_t, mu_adj (k_canonical_total_blocks after pass A)
 };
+
+// block sums are stored superblock-interleaved -- block k = 16 j + i at i * n_super + j -- so that the thread that adds the
+// 16 blocks of superblock j reads 16 coalesced rows (k_canonical_total_blocks; block-major rows cost one tag lookup per
+// value: 13 us per total at 25 000 blocks)
+// (a handful of points only: at a scan the 8 blocks of a tile would land in 8 different sectors, and the totals of many
+// points run side by side anyway -- there the rows stay block-major)
+__host__ __device__ __forceinline__ int64_t bi_bv_index(int64_t k, int64_t n_blocks, int interleaved) {
+    if (!interleaved) return k;
+    const int64_t n_super = (n_blocks + 15) >> 4;
+    return (k & 15) * n_super + (k >> 4);
+}
+__host__ __device__ __forceinline__ int64_t bi_bv_ld(int64_t n_blocks) { return ((n_blocks + 15) >> 4) << 4; }
 
 __device__ __forceinline__ double bi_morph_value(const double* __restrict__ base, int64_t row_stride, int64_t off,
                                                  const int32_t* __restrict__ corner, const double* __restrict__ w, int C) {
@@ -300,8 +315,7 @@ __host__ __device__ inline int bi_bin_stage_bytes(int C, int S, int n_kinds, int
 }
 
 template <int MODE, int CT, int NB, int NT, int NSTAGE>
-__global__ void __launch_bounds__(NT, 1024 / NT) k_binned_tile(const __grid_constant__ BiBinnedArgs a) {
-    extern __shared__ __align__(128) unsigned char bi_bin_smem[];
+__device__ __forceinline__ void bi_binned_tile_body(const BiBinnedArgs& a, unsigned char* bi_bin_smem) {
     const int S = a.S, C = CT ? CT : a.C, bi = a.bb_source;
     const int n_kinds = MODE == 0 ? S : (MODE == 1 ? S + 1 : S - 1);          // staged row kinds (x C corners each)
     const int n_rows = C * n_kinds;
@@ -349,13 +363,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_binned_tile(const __grid_cons
             const int q = i / S, s2 = i - q * S;
             s_mu[q * S + s2] = a.mus[(int64_t)a.group_points[first + q] * S + s2];
         }
-        if (MODE != 0 && tid < count) {
-            const int64_t p = a.group_points[first + tid];
-            const double sum_a = bi_morph_value(a.nm_sum_anchor, 1, 0, a.corner + p * C, a.weight + p * C, C);
-            const double p_cal = __ddiv_rn(a.mus[p * S + bi], sum_a);                       // likelihood.py:645
-            double sum_t = 0.0, mu_adj = 0.0;
-            if (MODE == 2) { sum_t = a.sum_t[p]; mu_adj = __dmul_rn(sum_t, p_cal); }        // likelihood.py:658
-            s_pt[tid * 4] = sum_a; s_pt[tid * 4 + 1] = p_cal; s_pt[tid * 4 + 2] = sum_t; s_pt[tid * 4 + 3] = mu_adj;
+        if (MODE != 0 && tid < 4 * count) {                   // sum_a, p_cal, sum_t, mu_adj (likelihood.py:645,658)
+            const int64_t p = a.group_points[first + (tid >> 2)];
+            s_pt[tid] = a.pt_const[4 * p + (tid & 3)];
         }
     };
 
@@ -385,7 +395,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_binned_tile(const __grid_cons
         // ---- compute: items = (point q of the group, PAIR of 32-bin blocks kk, kk + half): the two blocks are independent
         // dependency chains the compiler interleaves (the FP64 chains of one block alone leave the pipe idle)
         const int n_blk = (int)min((int64_t)(NB / 32), (a.n_bins - bin0 + 31) / 32);
-        const int half = (n_blk + 1) >> 1;
+        // a handful of points: one block per item, so that every warp of the CTA has work (a single point is 8 blocks)
+        const bool pairs = count * ((n_blk + 1) >> 1) >= NT / 32;
+        const int half = pairs ? (n_blk + 1) >> 1 : n_blk;
         for (int item = warp; item < count * half; item += NT / 32) {
             const int q = item / half, kk = item - q * half;
             const int64_t p = s_pidx[q];
@@ -405,7 +417,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_binned_tile(const __grid_cons
                 const int k = kk + j * half;
                 const int off = k * 32 + lane;
                 const int64_t b = bin0 + off;
-                if (k < n_blk && b < a.n_bins) {
+                if ((j == 0 || pairs) && k < n_blk && b < a.n_bins) {
                     const double d = obs_p[b];
                     const double* r0 = s_rows + off;
                     if (MODE == 1) {
@@ -464,13 +476,20 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_binned_tile(const __grid_cons
                 if (lane == 0 && flag) atomicOr(&a.flags[p], flag);
             }
             if (lane == 0) {
-                a.blockval[p * a.n_blocks + (bin0 >> 5) + kk] = val[0];
-                if (kk + half < n_blk) a.blockval[p * a.n_blocks + (bin0 >> 5) + kk + half] = val[1];
+                a.blockval[p * bi_bv_ld(a.n_blocks) + bi_bv_index((bin0 >> 5) + kk, a.n_blocks, a.bv_interleaved)] = val[0];
+                if (pairs && kk + half < n_blk)
+                    a.blockval[p * bi_bv_ld(a.n_blocks) + bi_bv_index((bin0 >> 5) + kk + half, a.n_blocks, a.bv_interleaved)] = val[1];
             }
         }
         __syncthreads();                       // every warp is done with this stage: it may be refilled
         if (NSTAGE == 2) buf ^= 1;
     }
+}
+
+template <int MODE, int CT, int NB, int NT, int NSTAGE>
+__global__ void __launch_bounds__(NT, 1024 / NT) k_binned_tile(const __grid_constant__ BiBinnedArgs a) {
+    extern __shared__ __align__(128) unsigned char bi_bin_smem_dyn[];
+    bi_binned_tile_body<MODE, CT, NB, NT, NSTAGE>(a, bi_bin_smem_dyn);
 }
 
 // schedule of k_binned_tile for a chunk of <= 1024 points: the evaluable points sorted by hypercube cell (key = anchor
@@ -480,7 +499,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_binned_tile(const __grid_cons
 __global__ void __launch_bounds__(BI_BIN_CHUNK_MAX)
 k_binned_plan(const int32_t* __restrict__ corner, const int32_t* __restrict__ status, int C, int n_points,
               int32_t* __restrict__ group_points, int32_t* __restrict__ groups, int32_t* __restrict__ header,
-              int32_t* __restrict__ flags) {
+              int32_t* __restrict__ flags, const double* __restrict__ nm_sum_anchor, const double* __restrict__ weight,
+              const double* __restrict__ mus, int S, int bb_source, double* __restrict__ pt_const) {
     __shared__ int key[BI_BIN_CHUNK_MAX];
     __shared__ int skey[BI_BIN_CHUNK_MAX];
     __shared__ int gflag[BI_BIN_CHUNK_MAX];
@@ -488,6 +508,14 @@ k_binned_plan(const int32_t* __restrict__ corner, const int32_t* __restrict__ st
     const int none = 0x7fffffff;
     key[t] = (t < n_points && status[t] == 0) ? corner[(int64_t)t * C] : none;
     if (t < n_points) flags[t] = 0;
+    if (t < n_points && bb_source >= 0) {
+        // n_model_events[source_i].sum(): morph of the per-anchor bin sums; p_cal = mu_i / that (likelihood.py:645)
+        const double sum_a = bi_morph_value(nm_sum_anchor, 1, 0, corner + (int64_t)t * C, weight + (int64_t)t * C, C);
+        pt_const[4 * t] = sum_a;
+        pt_const[4 * t + 1] = __ddiv_rn(mus[(int64_t)t * S + bb_source], sum_a);
+        pt_const[4 * t + 2] = 0.0;
+        pt_const[4 * t + 3] = 0.0;
+    }
     __syncthreads();
     const int my = key[t];
     int rank = 0, run_start = 0;
@@ -517,67 +545,109 @@ k_binned_plan(const int32_t* __restrict__ corner, const int32_t* __restrict__ st
 // Beeston-Barlow pass B from the terms pass A stored (few points: the evaluation is HBM-bound and re-reading the anchor
 // rows would cost more than 16 S bytes per (point, bin)): lambda_b = sum over s in source order of the stored terms, the
 // BB source's being (t_b / sum_t) * mu_adj (likelihood.py:657-658,667-670); one warp per (point, 32-bin block)
-__global__ void __launch_bounds__(256) k_binned_passb_stored(const __grid_constant__ BiBinnedArgs a) {
+// the stored terms of the warp's next item travel during the reduction of the current one
+__device__ __forceinline__ void bi_binned_passb_stored_body(const BiBinnedArgs& a, double* blockval) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int S = a.S, C = a.C, bi = a.bb_source;
-    for (int64_t item = warp_global; item < a.n_points * a.n_blocks; item += n_warps) {
+    const int64_t n_items = a.n_points * a.n_blocks;
+    const int S = a.S, bi = a.bb_source;
+    double v[BI_BIN_STORE_S], d = 0.0, lg = 0.0, sum_t = 0.0, mu_adj = 0.0;
+    auto load_item = [&](int64_t item) {
         const int64_t p = item / a.n_blocks, k = item - p * a.n_blocks;
-        if (a.status[p] != 0) continue;
+        const int64_t b = k * 32 + lane;
+        if (item < n_items && b < a.n_bins) {
+#pragma unroll
+            for (int s = 0; s < BI_BIN_STORE_S; ++s)
+                if (s < S) v[s] = a.tbuf[(p * BI_BIN_STORE_S + s) * a.tb_ld + b];
+            d = a.observed[p * a.obs_stride + b];
+            lg = a.lgamma_obs[p * a.obs_stride + b];
+            sum_t = a.pt_const[4 * p + 2];
+            mu_adj = a.pt_const[4 * p + 3];                        // sum_t * p_cal (likelihood.py:658)
+        }
+    };
+    load_item(warp_global);
+    for (int64_t item = warp_global; item < n_items; item += n_warps) {
+        const int64_t p = item / a.n_blocks, k = item - p * a.n_blocks;
         const int64_t b = k * 32 + lane;
         double val = 0.0;
-        if (b < a.n_bins) {
-            const double sum_a = bi_morph_value(a.nm_sum_anchor, 1, 0, a.corner + p * C, a.weight + p * C, C);
-            const double p_cal = __ddiv_rn(a.mus[p * S + bi], sum_a);
-            const double sum_t = a.sum_t[p], mu_adj = __dmul_rn(sum_t, p_cal);
+        const bool live = a.status[p] == 0;
+        if (live && b < a.n_bins) {
             double lam = 0.0;
-            for (int s = 0; s < S; ++s) {
-                const double v = a.tbuf[(p * BI_BIN_STORE_S + s) * a.tb_ld + b];
-                const double term = (s == bi) ? __dmul_rn(__ddiv_rn(v, sum_t), mu_adj) : v;
-                lam = (s == 0) ? term : __dadd_rn(lam, term);
+#pragma unroll
+            for (int s = 0; s < BI_BIN_STORE_S; ++s) {
+                if (s < S) {
+                    const double term = (s == bi) ? __dmul_rn(__ddiv_rn(v[s], sum_t), mu_adj) : v[s];
+                    lam = (s == 0) ? term : __dadd_rn(lam, term);
+                }
             }
-            val = bi_poisson_logpmf(a.observed[p * a.obs_stride + b], a.lgamma_obs[p * a.obs_stride + b], lam);
+            val = bi_poisson_logpmf(d, lg, lam);
         }
+        load_item(item + n_warps);
 #pragma unroll
         for (int x = 1; x < 32; x <<= 1) val = __dadd_rn(val, __shfl_xor_sync(BI_FULL_MASK, val, x));
-        if (lane == 0) a.blockval[p * a.n_blocks + k] = val;
+        if (live && lane == 0) blockval[p * bi_bv_ld(a.n_blocks) + bi_bv_index(k, a.n_blocks, a.bv_interleaved)] = val;
     }
+}
+__global__ void __launch_bounds__(256) k_binned_passb_stored(const __grid_constant__ BiBinnedArgs a) {
+    bi_binned_passb_stored_body(a, a.blockval);
 }
 
 // canonical total from per-block sums: superblock j = ((0 + v_16j) + v_16j+1) + ... (the sequential sum k_binned_pass
 // forms in its loop), then the 256-lane strided total of k_canonical_total
-__global__ void __launch_bounds__(256)
-k_canonical_total_blocks(const double* __restrict__ blockval, int64_t n_blocks, const int32_t* __restrict__ status,
-                         double fill, double* __restrict__ out) {
+// One CTA of 1024 threads per point.  The 16-block superblock sums are formed by all threads at once (16 loads in flight
+// each; a minimiser step has ONE point, and 256 threads walking 1563 superblocks one after the other cost 16 us of load
+// latency per total), kept in shared memory, and added by lanes 0..255 in the canonical strided order.
+#define BI_TOTAL_THREADS 1024
+#define BI_TOTAL_SMEM_SUPERS 4096
+__global__ void __launch_bounds__(BI_TOTAL_THREADS)
+k_canonical_total_blocks(const double* __restrict__ blockval, int64_t n_blocks, int interleaved,
+                         const int32_t* __restrict__ status, double fill, double* __restrict__ out, double* pt_const) {
     __shared__ double warp_tot[8];
+    __shared__ double s_sj[BI_TOTAL_SMEM_SUPERS];
     const int64_t p = blockIdx.x;
     const int t = threadIdx.x;
     if (status[p] != 0) { if (t == 0) out[p] = fill; return; }
-    const double* v = blockval + p * n_blocks;
+    const double* v = blockval + p * bi_bv_ld(n_blocks);
     const int64_t n_super = (n_blocks + 15) / 16;
-    double u = 0.0;
-    for (int64_t j = t; j < n_super; j += 256) {
+    auto super_sum = [&](int64_t j) {                              // ((0 + v_16j) + v_16j+1) + ...; block 16 j + i at i * n_super + j
         const int64_t k0 = j * 16, k1 = min(k0 + 16, n_blocks);
         double sj = 0.0;
         if (k1 - k0 == 16) {                                       // all 16 loads in flight before the sequential adds
             double x[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = v[k0 + k];
+            for (int k = 0; k < 16; ++k) x[k] = interleaved ? v[k * n_super + j] : v[k0 + k];
 #pragma unroll
             for (int k = 0; k < 16; ++k) sj = __dadd_rn(sj, x[k]);
         } else {
-            for (int64_t k = k0; k < k1; ++k) sj = __dadd_rn(sj, v[k]);
+            for (int64_t k = k0; k < k1; ++k) sj = __dadd_rn(sj, interleaved ? v[(k - k0) * n_super + j] : v[k]);
         }
-        u = __dadd_rn(u, sj);
+        return sj;
+    };
+    double u = 0.0;
+    for (int64_t base = 0; base < n_super; base += BI_TOTAL_SMEM_SUPERS) {       // BI_TOTAL_SMEM_SUPERS is a multiple of 256
+        const int64_t n_here = min((int64_t)BI_TOTAL_SMEM_SUPERS, n_super - base);
+        for (int64_t j = t; j < n_here; j += BI_TOTAL_THREADS) s_sj[j] = super_sum(base + j);
+        __syncthreads();
+        if (t < 256)
+            for (int64_t j = t; j < n_here; j += 256) u = __dadd_rn(u, s_sj[j]);
+        __syncthreads();
     }
+    if (t < 256) {
 #pragma unroll
-    for (int x = 1; x < 32; x <<= 1) u = __dadd_rn(u, __shfl_xor_sync(BI_FULL_MASK, u, x));
-    if ((t & 31) == 0) warp_tot[t >> 5] = u;
+        for (int x = 1; x < 32; x <<= 1) u = __dadd_rn(u, __shfl_xor_sync(BI_FULL_MASK, u, x));
+        if ((t & 31) == 0) warp_tot[t >> 5] = u;
+    }
     __syncthreads();
-    if (t == 0)
-        out[p] = __dadd_rn(__dadd_rn(__dadd_rn(warp_tot[0], warp_tot[1]), __dadd_rn(warp_tot[2], warp_tot[3])),
-                           __dadd_rn(__dadd_rn(warp_tot[4], warp_tot[5]), __dadd_rn(warp_tot[6], warp_tot[7])));
+    if (t == 0) {
+        const double total = __dadd_rn(__dadd_rn(__dadd_rn(warp_tot[0], warp_tot[1]), __dadd_rn(warp_tot[2], warp_tot[3])),
+                                       __dadd_rn(__dadd_rn(warp_tot[4], warp_tot[5]), __dadd_rn(warp_tot[6], warp_tot[7])));
+        out[p] = total;
+        if (pt_const) {                                            // after pass A: sum_t and mu_adj = sum_t * p_cal (:658)
+            pt_const[4 * p + 2] = total;
+            pt_const[4 * p + 3] = __dmul_rn(total, pt_const[4 * p + 1]);
+        }
+    }
 }
 
 // canonical total of [P, n_chunks] partials (same order as k_unbinned_finalize); status != 0 -> fill
@@ -666,14 +736,14 @@ static bool bi_bin_store_terms(int64_t n_points, int64_t n_bins) {
     return n_points * BI_BIN_STORE_S * tb_ld <= ((int64_t)1 << lg);
 }
 
-// scratch layout (doubles): sum_t [P] | block sums A [PC, n_blocks] | block sums B [PC, n_blocks] | t_b [PC, tb_ld] (or the
+// scratch layout (doubles): sum_t [P] | point constants [PC, 4] | block sums A [PC, n_blocks] | block sums B [PC, n_blocks] | t_b [PC, tb_ld] (or the
 // stored terms [P, 8, tb_ld]) | schedule (int32: group_points [PC], groups [(PC + 1) * 4], header [8]); PC = points per pass
 extern "C" int64_t bi_binned_scratch_doubles(int64_t n_points, int64_t n_bins) {
     if (n_points <= 0 || n_bins <= 0) return 0;
     const int64_t pc = bi_bin_chunk_points(n_points, n_bins);
     const int64_t n_blocks = (n_bins + 31) / 32, tb_ld = (n_bins + 63) / 64 * 64;
     const int64_t per_bin = bi_bin_store_terms(n_points, n_bins) ? n_points * BI_BIN_STORE_S * tb_ld : pc * tb_ld;
-    return n_points + 2 * pc * n_blocks + per_bin + (5 * pc + 12 + 1) / 2 + 8;
+    return n_points + 4 * pc + 2 * pc * bi_bv_ld(n_blocks) + per_bin + (5 * pc + 12 + 1) / 2 + 8;
 }
 extern "C" int64_t bi_binned_sum_t_offset(int64_t n_points, int64_t n_bins) { (void)n_points; (void)n_bins; return 0; }
 
@@ -764,9 +834,10 @@ extern "C" int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const doubl
     const int64_t n_blocks = (n_bins + 31) / 32, tb_ld = (n_bins + 63) / 64 * 64;
     const bool store_terms = bb_source >= 0 && S <= BI_BIN_STORE_S && bi_bin_store_terms(n_points, n_bins) && pc == n_points;
     double* sum_t_all = scratch_dev;
-    double* bva = scratch_dev + n_points;
-    double* bvb = bva + pc * n_blocks;
-    double* tbuf = bvb + pc * n_blocks;
+    double* pt_const = scratch_dev + n_points;
+    double* bva = pt_const + 4 * pc;
+    double* bvb = bva + pc * bi_bv_ld(n_blocks);
+    double* tbuf = bvb + pc * bi_bv_ld(n_blocks);
     int32_t* plan = reinterpret_cast<int32_t*>(
         tbuf + (bi_bin_store_terms(n_points, n_bins) ? n_points * BI_BIN_STORE_S * tb_ld : pc * tb_ld));
     int32_t* group_points = plan;
@@ -798,7 +869,10 @@ extern "C" int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const doubl
             a.tbuf = tbuf; a.n_blocks = n_blocks; a.tile = tile; a.n_tiles = (n_bins + tile - 1) / tile;
             a.tb_ld = tb_ld;
             a.store_terms = store_terms ? 1 : 0;
-            k_binned_plan<<<1, BI_BIN_CHUNK_MAX, 0, st>>>(a.corner, a.status, C, (int)np, group_points, groups, header, a.flags);
+            a.bv_interleaved = np <= BI_BIN_GROUP_POINTS ? 1 : 0;
+            a.pt_const = pt_const;
+            k_binned_plan<<<1, BI_BIN_CHUNK_MAX, 0, st>>>(a.corner, a.status, C, (int)np, group_points, groups, header, a.flags,
+                                                         a.nm_sum_anchor, a.weight, a.mus, S, bb_source, pt_const);
             auto launch = [&](int mode, double* blockval) -> int {
                 a.blockval = blockval;
                 const int n_kinds = mode == 0 ? S : (mode == 1 ? S + 1 : S - 1);
@@ -813,7 +887,7 @@ extern "C" int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const doubl
                 if ((rc = launch(0, bvb)) != BI_OK) return rc;
             } else {
                 if ((rc = launch(1, bva)) != BI_OK) return rc;
-                k_canonical_total_blocks<<<(unsigned)np, 256, 0, st>>>(bva, n_blocks, a.status, 0.0, sum_t);
+                k_canonical_total_blocks<<<(unsigned)np, BI_TOTAL_THREADS, 0, st>>>(bva, n_blocks, a.bv_interleaved, a.status, 0.0, sum_t, pt_const);
                 a.sum_t = sum_t;
                 if (store_terms) {
                     a.blockval = bvb;
@@ -824,7 +898,7 @@ extern "C" int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const doubl
                     return rc;
                 }
             }
-            k_canonical_total_blocks<<<(unsigned)np, 256, 0, st>>>(bvb, n_blocks, a.status, ninf, logl_dev + p0);
+            k_canonical_total_blocks<<<(unsigned)np, BI_TOTAL_THREADS, 0, st>>>(bvb, n_blocks, a.bv_interleaved, a.status, ninf, logl_dev + p0, nullptr);
         } else {
             const int64_t n_tasks = np * a.n_chunks;
             int64_t blocks = (n_tasks + 7) / 8;

@@ -47,7 +47,7 @@ k_template_prepare(const __grid_constant__ BiSpace sp, const __grid_constant__ B
 // ---------------------------------------------------------------------------------------------
 // the kernel: one warp per unit (pair group, superblock), lane = event
 // ---------------------------------------------------------------------------------------------
-template <int NP, int NS>
+template <int NP, int NS, bool PRE>
 __global__ void __launch_bounds__(BI_TS_THREADS)
 k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bin_stride, const __grid_constant__ BiTsSpace sp,
                     const int32_t* __restrict__ ev_bin, const double* __restrict__ ev_frac, int64_t ld_frac,
@@ -67,7 +67,7 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
     // The rows / weights of the rare path then come from K1's corner / weight outputs [P, C] (pre_corner, pre_weight:
     // row_k = corner[k / S] * S + k % S, wterm_k = weight[k / S]) when a unit first needs them; row / coef / wterm and
     // the prepared events are not read otherwise.
-    const bool use_pre = NP == 1 && pre != nullptr;
+    constexpr bool use_pre = PRE;
     constexpr int NY = NS > 0 ? NS : 1;
     extern __shared__ __align__(16) unsigned char bi_ts_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -136,6 +136,13 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
         for (int q = 0; q < NP; ++q) { M[q] = 1.0; E[q] = 0; Lslow[q] = 0.0; }
         bool any_slow = false;
 
+        // pre mode: the superblock's densities are all in flight before the tree starts (16 coalesced loads per lane)
+        double pp[BI_SUPERBLOCK / BI_EVENT_BLOCK];
+        if (use_pre) {
+#pragma unroll
+            for (int i = 0; i < BI_SUPERBLOCK / BI_EVENT_BLOCK; ++i)
+                pp[i] = (i * BI_EVENT_BLOCK + lane < n_ev) ? pre[ev_begin + i * BI_EVENT_BLOCK + lane] : 1.0;
+        }
 #pragma unroll 1
         for (int e0 = 0; e0 < n_ev; e0 += BI_EVENT_BLOCK) {
             const bool valid = e0 + lane < n_ev;
@@ -158,7 +165,10 @@ k_template_partials(const double* __restrict__ T, int64_t row_stride, int64_t bi
             constexpr int KB = (1 << NS) <= 4 ? BI_TS_BATCH : (BI_TS_BATCH / 2 > 0 ? BI_TS_BATCH / 2 : 1);
             int k = 0;
             if (use_pre) {
-                p[0] = valid ? pre[ev] : 1.0;
+                p[0] = 1.0;
+#pragma unroll
+                for (int i = 0; i < BI_SUPERBLOCK / BI_EVENT_BLOCK; ++i)
+                    if (i * BI_EVENT_BLOCK == e0) p[0] = pp[i];
                 k = K;
             }
 #pragma unroll 1
@@ -1131,7 +1141,7 @@ k_ts_order_groups(const __grid_constant__ BiPlanDims dims, int n_cells, int64_t 
     if (tid == 0) n_ordered[0] = total;
 }
 
-template <int NP, int NS>
+template <int NP, int NS, bool PRE>
 static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride, const BiTsSpace& sp,
                         const int32_t* ev_bin, const double* ev_frac, int64_t ld_frac, const int64_t* dataset_offset,
                         int K, int S, const int32_t* row, const double* coef, const double* wterm,
@@ -1148,16 +1158,16 @@ static int bi_ts_launch(const double* T, int64_t row_stride, int64_t bin_stride,
         BI_CUDA_CHECK(cudaGetDevice(&dev));
         BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         // the cap is per kernel, not per launch: always raise it to what the largest term count needs
-        BI_CUDA_CHECK(cudaFuncSetAttribute(k_template_partials<NP, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        BI_CUDA_CHECK(cudaFuncSetAttribute(k_template_partials<NP, NS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            BI_TS_WARPS * BI_TS_MAX_TERMS * (1 + NP) * 8));
-        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_template_partials<NP, NS>, BI_TS_THREADS, smem));
+        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_template_partials<NP, NS, PRE>, BI_TS_THREADS, smem));
         BI_REQUIRE(per_sm >= 1, "k_template_partials<%d,%d> does not fit on this device", NP, NS);
         per_sm_cached[K] = per_sm;
     }
     int64_t blocks = (int64_t)sms * per_sm_cached[K];
     const int64_t needed = (n_units + BI_TS_WARPS - 1) / BI_TS_WARPS;
     if (blocks > needed) blocks = needed;
-    k_template_partials<NP, NS><<<(unsigned)blocks, BI_TS_THREADS, smem, st>>>(
+    k_template_partials<NP, NS, PRE><<<(unsigned)blocks, BI_TS_THREADS, smem, st>>>(
         T, row_stride, bin_stride, sp, ev_bin, ev_frac, ld_frac, dataset_offset, K, S, row, coef, wterm, term_source, mus,
         status, n_groups, groups, unit_offset, unit_group, n_units, pair_point, pair_partial_offset, outlier, partial,
         group_order, n_ordered, sb_max, pre, pre_corner, pre_weight);
@@ -1217,8 +1227,15 @@ int bi_template_partials_impl(const double* templates_dev, int64_t row_stride, i
     const BiTsGroup* groups = reinterpret_cast<const BiTsGroup*>(groups_dev);
     cudaStream_t st = (cudaStream_t)stream;
 #define BI_TS_CASE(NPV, NSV)                                                                                            \
+    if (group_points == NPV && ns == NSV && (NPV == 1) && pre_dev)                                                      \
+        return bi_ts_launch<1, NSV, true>(templates_dev, row_stride, bin_stride, sp, ev_bin_dev, ev_frac_dev, ld_frac,  \
+                                      dataset_offset_dev, n_terms, n_sources, row_dev, coef_dev, wterm_dev,             \
+                                      term_source_dev, mus_dev, status_dev, n_groups, groups, unit_offset_dev,          \
+                                      unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,                 \
+                                      outlier_likelihood, partial_dev, group_order_dev, n_ordered_dev, sb_max,         \
+                                      pre_dev, pre_corner_dev, pre_weight_dev, st);                                     \
     if (group_points == NPV && ns == NSV)                                                                               \
-        return bi_ts_launch<NPV, NSV>(templates_dev, row_stride, bin_stride, sp, ev_bin_dev, ev_frac_dev, ld_frac,      \
+        return bi_ts_launch<NPV, NSV, false>(templates_dev, row_stride, bin_stride, sp, ev_bin_dev, ev_frac_dev, ld_frac,      \
                                       dataset_offset_dev, n_terms, n_sources, row_dev, coef_dev, wterm_dev,             \
                                       term_source_dev, mus_dev, status_dev, n_groups, groups, unit_offset_dev,          \
                                       unit_group_dev, n_units, pair_point_dev, pair_partial_offset_dev,                 \

@@ -25,8 +25,12 @@
 #include "bi_tma.cuh"
 #include "bi_ts.cuh"
 
+#ifndef BI_BM_THREADS
 #define BI_BM_THREADS 256
+#endif
+#ifndef BI_BM_CHUNK
 #define BI_BM_CHUNK 2048                 /* events per task */
+#endif
 #define BI_BM_PER_THREAD (BI_BM_CHUNK / BI_BM_THREADS)
 #define BI_BM_MAX_SOURCES 8
 #ifndef BI_BM_MIN_CTAS
@@ -105,7 +109,7 @@ static __device__ void bi_bm_scan(int* v, int n, int* carry) {
 }
 
 // shared memory: [stages] row stages (row_bytes each, 128-byte aligned) | event slots: y [NS][CHUNK], toy, src |
-// hist [n_cells + 2] | carry [8] | mbarriers [2]
+// hist [n_cells + 2] | carry [32] | mbarriers [2]
 template <int NS, int D, int S>
 __global__ void __launch_bounds__(BI_BM_THREADS, BI_BM_MIN_CTAS)
 k_bm_density(const __grid_constant__ BiBmArgs a) {
@@ -121,7 +125,7 @@ k_bm_density(const __grid_constant__ BiBmArgs a) {
     int32_t* s_src = s_toy + BI_BM_CHUNK;
     int* s_hist = s_src + BI_BM_CHUNK;                                                             // [n_cells + 2]
     int* s_carry = s_hist + a.n_cells + 2;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_carry + 8) + 7) & ~(uintptr_t)7);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_carry + 32) + 7) & ~(uintptr_t)7);
     const int n_cells = a.n_cells;
 
     if (tid < 2) bi_mbar_init(&s_bar[tid], 1);
@@ -298,6 +302,8 @@ extern "C" int bi_template_bm_supported(int32_t n_space, int32_t method, int32_t
     return 1;
 }
 
+extern "C" int32_t bi_template_bm_chunk(void) { return BI_BM_CHUNK; }
+
 extern "C" int64_t bi_template_bm_record_doubles(int32_t n_dims, int32_t n_sources) {
     return (int64_t)(1 + n_dims + n_sources + 3) / 4 * 4;
 }
@@ -358,7 +364,7 @@ extern "C" int bi_template_bm_density(const double* templates_bm_dev, int64_t n_
                                                                  mus_dev, status_dev, (int)n_cells, record_dev);
     BI_LAUNCH_CHECK();
     const int smem = a.stages * ((a.row_bytes + 127) & ~127) + n_space * BI_BM_CHUNK * 8 + 2 * BI_BM_CHUNK * 4 +
-                     ((int)n_cells + 2 + 8) * 4 + 8 + 2 * 8;
+                     ((int)n_cells + 2 + 32) * 4 + 8 + 2 * 8;
 #define BI_BM_CASE(NSV, DV) if (n_space == NSV && n_dims == DV) return bi_bm_launch_s<NSV, DV>(a, smem, st);
     BI_BM_CASE(1, 1) BI_BM_CASE(1, 2) BI_BM_CASE(1, 3) BI_BM_CASE(1, 4)
     BI_BM_CASE(2, 1) BI_BM_CASE(2, 2) BI_BM_CASE(2, 3) BI_BM_CASE(2, 4)

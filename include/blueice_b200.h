@@ -439,6 +439,7 @@ int bi_template_ll_batch(int32_t n_dims, const int32_t* n_anchors_host, const do
 int bi_template_bm_supported(int32_t n_space, int32_t method, int32_t n_dims, const int32_t* n_anchors_host,
                              int32_t n_sources, int64_t n_rows);
 int64_t bi_template_bm_record_doubles(int32_t n_dims, int32_t n_sources);
+int32_t bi_template_bm_chunk(void);        /* events per task (the caller cuts the bins' event lists into tasks of this size) */
 int bi_template_bm_density(const double* templates_bm_dev, int64_t n_rows, int32_t n_space,
                            int32_t n_dims, const int32_t* n_anchors_host, int32_t n_sources, int64_t n_points,
                            const int32_t* cell_dev, const double* frac_dev, const double* mus_dev,

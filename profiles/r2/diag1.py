@@ -137,7 +137,7 @@ if "k4" in cases:
     beng = BinnedEngine(MorphGrid(axes), mus3.reshape(27, 4), pmf, n_model, 0)
     beng.set_observed(observed)
     res = {}
-    for P in (1, 16, 256):
+    for P in (1, 7, 16, 256):
         zs3, mult3 = wl.scan_points(P, 3, 4, seed=31, z_range=(-1., 1.), mult_range=(0.8, 1.2))
         zs_d, mult_d, _, _, _ = beng._upload_points(zs3, mult3, None, None)
         zs_d, mult_d = zs_d.clone(), mult_d.clone()
