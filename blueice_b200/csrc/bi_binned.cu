@@ -290,6 +290,8 @@ __global__ void __launch_bounds__(256) k_binned_pass(const __grid_constant__ BiB
 #define BI_BIN_TILE 256                 /* largest tile: 8 blocks of 32 bins (the kernel runs 128- or 256-bin tiles) */
 #define BI_BIN_STORE_S 8                /* stored-terms form of the Beeston-Barlow passes: up to 8 sources */
 #define BI_BIN_GROUP_POINTS 32          /* points per group */
+#define BI_BIN_GCACHE 32                /* groups whose cell anchors k_binned_tile keeps in shared memory ... */
+#define BI_BIN_GCACHE_C 16              /* ... when the morph has at most this many corners */
 
 // byte offset of the staged rows inside the dynamic shared memory of k_binned_tile (tables first, rows 128-byte aligned)
 __host__ __device__ inline int bi_bin_rows_offset(int C, int S) {
@@ -324,6 +326,20 @@ __device__ __forceinline__ void bi_binned_tile_body(const BiBinnedArgs& a, unsig
     const int n_groups = a.header[0];
     const int64_t n_tasks = a.n_tiles * n_groups;
     if (tid < NSTAGE) bi_mbar_init(reinterpret_cast<uint64_t*>(bi_bin_smem + tid * stage_bytes), 1);
+    // a few groups (a handful of points): their (first, count) and the anchors of their cell are kept in shared memory --
+    // otherwise every task starts with three dependent global loads (group -> lead point -> corners) before its TMA
+    // copies can be issued, 2 us per 80 kB tile at one point
+    __shared__ int32_t s_ginfo[BI_BIN_GCACHE][2];
+    __shared__ int32_t s_ganchor[BI_BIN_GCACHE][BI_BIN_GCACHE_C];
+    const bool gcache = n_groups <= BI_BIN_GCACHE && C <= BI_BIN_GCACHE_C;
+    if (gcache) {
+        for (int i = tid; i < n_groups * C; i += NT) {
+            const int g = i / C, c = i - g * C;
+            const int first = a.groups[4 * g];
+            if (c == 0) { s_ginfo[g][0] = first; s_ginfo[g][1] = a.groups[4 * g + 1]; }
+            s_ganchor[g][c] = a.corner[(int64_t)a.group_points[first] * C + c];
+        }
+    }
     __syncthreads();
 
     // stage a task: tables by ordinary stores, rows by TMA bulk copies that complete on the stage's mbarrier
@@ -337,14 +353,14 @@ __device__ __forceinline__ void bi_binned_tile_body(const BiBinnedArgs& a, unsig
         double* s_rows = reinterpret_cast<double*>(base + bi_bin_rows_offset(C, S));
         const int64_t tile = task / n_groups;
         const int g = (int)(task - tile * n_groups);
-        const int first = a.groups[4 * g], count = a.groups[4 * g + 1];
+        const int first = gcache ? s_ginfo[g][0] : a.groups[4 * g], count = gcache ? s_ginfo[g][1] : a.groups[4 * g + 1];
         const int64_t bin0 = tile * NB;
         const int tile_bins = (int)min((int64_t)NB, a.ld - bin0);            // even (ld is)
         if (tid == 0) bi_mbar_expect_tx(bar, (unsigned)(n_rows * tile_bins * 8));
-        const int64_t lead = a.group_points[first];                          // the group's cell = its first point's
+        const int64_t lead = gcache ? 0 : a.group_points[first];             // the group's cell = its first point's
         for (int r = tid; r < n_rows; r += NT) {
             const int k = r / C, c = r - k * C;
-            const int64_t anchor = a.corner[lead * C + c];
+            const int64_t anchor = gcache ? s_ganchor[g][c] : a.corner[lead * C + c];
             const double* src;
             if (MODE == 1 && k == S) {
                 src = a.nm_anchor + anchor * a.ld + bin0;
@@ -386,7 +402,7 @@ __device__ __forceinline__ void bi_binned_tile_body(const BiBinnedArgs& a, unsig
         const double* s_rows = reinterpret_cast<const double*>(base + bi_bin_rows_offset(C, S));
         const int64_t tile = task / n_groups;
         const int g = (int)(task - tile * n_groups);
-        const int count = a.groups[4 * g + 1];
+        const int count = gcache ? s_ginfo[g][1] : a.groups[4 * g + 1];
         const int64_t bin0 = tile * NB;
         __syncthreads();                       // this stage's tables (written by other threads) are visible
         bi_mbar_wait(bar, parity[buf]);
@@ -553,8 +569,17 @@ __device__ __forceinline__ void bi_binned_passb_stored_body(const BiBinnedArgs& 
     const int64_t n_items = a.n_points * a.n_blocks;
     const int S = a.S, bi = a.bb_source;
     double v[BI_BIN_STORE_S], d = 0.0, lg = 0.0, sum_t = 0.0, mu_adj = 0.0;
+    // (point, block) of an item: 32-bit division whenever the item count allows (a 64-bit one costs ~100 instructions,
+    // and the kernel is bound by instruction issue)
+    const bool small = n_items < (1LL << 31);
+    const unsigned nb32 = (unsigned)a.n_blocks;
+    auto split = [&](int64_t item, int64_t* p, int64_t* k) {
+        if (small) { const unsigned q = (unsigned)item / nb32; *p = q; *k = (unsigned)item - q * nb32; }
+        else { *p = item / a.n_blocks; *k = item - *p * a.n_blocks; }
+    };
     auto load_item = [&](int64_t item) {
-        const int64_t p = item / a.n_blocks, k = item - p * a.n_blocks;
+        int64_t p, k;
+        split(item < n_items ? item : 0, &p, &k);
         const int64_t b = k * 32 + lane;
         if (item < n_items && b < a.n_bins) {
 #pragma unroll
@@ -568,7 +593,8 @@ __device__ __forceinline__ void bi_binned_passb_stored_body(const BiBinnedArgs& 
     };
     load_item(warp_global);
     for (int64_t item = warp_global; item < n_items; item += n_warps) {
-        const int64_t p = item / a.n_blocks, k = item - p * a.n_blocks;
+        int64_t p, k;
+        split(item, &p, &k);
         const int64_t b = k * 32 + lane;
         double val = 0.0;
         const bool live = a.status[p] == 0;
@@ -800,7 +826,9 @@ static int bi_binned_launch_tile_nb(const BiBinnedArgs& a, int smem, int grid, c
 
 // 512-thread CTAs, two per SM (64 registers), one stage each: while one CTA waits for its tile the other evaluates.
 // Measured on B200 (config 3, 256-point scan / single point): this shape 9.9 ms / 0.20 ms; a two-stage prefetch pipeline in
-// one 1024-thread CTA per SM 11.5 / 0.26; 256-thread CTAs 12.7 / 0.19; 128-bin tiles 10.8 / 0.25.
+// one 1024-thread CTA per SM 11.5 / 0.26; 256-thread CTAs 12.7 / 0.19; 128-bin tiles 10.8 / 0.25.  Round 2, single point
+// with the launch sequence replayed as a graph (0.097 ms): two-stage variants (128 x 128, 256 x 256, 128 x 256 threads)
+// 0.127-0.129 ms; one stage of 128 bins with 128 / 256 threads and up to 8 / 4 CTAs per SM 0.110 / 0.096 ms.
 template <int MODE>
 static int bi_binned_launch_tile(const BiBinnedArgs& a, int smem, int grid, cudaStream_t st) {
     if (a.tile == 128) return bi_binned_launch_tile_nb<MODE, 128, 512, 1>(a, smem, grid, st);
@@ -892,7 +920,7 @@ extern "C" int bi_binned_ll_batch_toys(const double* pmf_anchor_dev, const doubl
                 if (store_terms) {
                     a.blockval = bvb;
                     int64_t blocks = (np * n_blocks + 7) / 8;
-                    if (blocks > 148 * 16) blocks = 148 * 16;
+                    if (blocks > 148 * 8) blocks = 148 * 8;         // one wave of 8 CTAs per SM
                     k_binned_passb_stored<<<(unsigned)blocks, 256, 0, st>>>(a);
                 } else if ((rc = launch(2, bvb)) != BI_OK) {
                     return rc;
