@@ -54,10 +54,10 @@ def test_superblock_count():
     assert lib.bi_num_superblocks(512) == 1
     assert lib.bi_num_superblocks(513) == 2
     assert lib.bi_num_superblocks(100000) == 196
-    # K4 scratch: sum_t [P] + two [PC, n_blocks] block-sum arrays + the per-bin scratch (stored terms [P, 8, tb_ld] for a
-    # few points, t_b [PC, tb_ld] otherwise) + the schedule
+    # K4 scratch: sum_t [P] + point constants [PC, 4] + two [PC, 16 * n_super] block-sum arrays + the per-bin scratch (stored
+    # terms [P, 8, tb_ld] for a few points, t_b [PC, tb_ld] otherwise) + the schedule
     n_blocks, tb_ld = 32, 1024
-    assert lib.bi_binned_scratch_doubles(3, 1000) == 3 + 2 * 3 * n_blocks + 3 * 8 * tb_ld + (5 * 3 + 12 + 1) // 2 + 8
+    assert lib.bi_binned_scratch_doubles(3, 1000) == 3 + 4 * 3 + 2 * 3 * n_blocks + 3 * 8 * tb_ld + (5 * 3 + 12 + 1) // 2 + 8
     assert lib.bi_binned_scratch_doubles(0, 1000) == 0
     assert lib.bi_binned_sum_t_offset(3, 1000) == 0
     assert lib.bi_unbinned_small_ok(1, 1, 1, 1012) == 1 and lib.bi_unbinned_small_ok(2, 2, 4096, 100000) == 0
