@@ -1,0 +1,19 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/c2_pytest.log 2>&1; echo "multi pytest rc=$?"; tail -3 gpurun_out/c2_pytest.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+    bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/c2_bench2.json 2> gpurun_out/c2_bench2.err
+echo "bench2 rc=$?"
+tail -c 800 gpurun_out/c2_bench2.err
+python - <<'PY'
+import json
+try:
+    d = json.loads(open('gpurun_out/c2_bench2.json').read().strip().splitlines()[-1])
+    print(json.dumps({k: d[k] for k in ('value', 'ms_per_step', 'e2e', 'config2_strong_scaling')}, indent=1))
+    oc = d.get('other_configs') or {}
+    print(json.dumps(oc.get('config5_event_sharded'), indent=1)[:2500])
+    print(json.dumps(oc.get('config4_toys'), indent=1)[:2500])
+except Exception as e:
+    print("parse failed", e)
+PY
