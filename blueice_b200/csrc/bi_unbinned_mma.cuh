@@ -264,7 +264,9 @@ __device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, in
         E[mt] += e;
     }
     bad &= active_mask;
-    if (bad) {                                                    // rare: reference-semantics fallback per (t, group)
+    // rare: reference-semantics fallback per (t, group).  The branch is taken by the whole warp (a vote): a lane-divergent
+    // `if (bad)` made every group pay a reconvergence barrier (BSSY / WARPSYNC / BSYNC around the body)
+    if (__any_sync(BI_FULL_MASK, bad != 0)) {
         for (int mt = 0; mt < NMT; ++mt) {
             if ((bad >> mt) & 1u) {
                 const int64_t p = slot_point[mt * 8 + g];
@@ -380,6 +382,13 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
     for (int mt = 0; mt < NMT; ++mt) { M[mt] = 1.0; E[mt] = 0; }
     bool slow_any = false;
     constexpr int TILES_PER_SUPER = BI_SUPERBLOCK / T, GROUPS_PER_TILE = T / BI_GROUP_EVENTS;
+    // the point whose partial this lane stores at a superblock close (lane t of row g: m-tiles t, t + 4), read once per unit
+    int64_t p_store[(NMT + 3) / 4];
+#pragma unroll
+    for (int r = 0; r < (NMT + 3) / 4; ++r) {
+        const int mt_mine = 4 * r + t;
+        p_store[r] = (mt_mine < NMT && ((active_mask >> mt_mine) & 1u)) ? (int64_t)slot_point[mt_mine * 8 + g] : -1;
+    }
 
   while (cur >= 0) {
     const int64_t sb_begin = (int64_t)cur * sb_per;
@@ -438,7 +447,6 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
             for (int q = 0; q < 4; ++q)
                 if (4 * r + q < NMT && t == q) { m = M[4 * r + q]; e = E[4 * r + q]; }
             double L = bi_block_log(m, e);
-            const int mt_mine = 4 * r + t;
             if (any_slow) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -451,10 +459,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
                     }
                 }
             }
-            if (mt_mine < NMT && ((active_mask >> mt_mine) & 1u)) {
-                const int64_t p = slot_point[mt_mine * 8 + g];
-                partial[p * n_super + sb] = L;
-            }
+            if (p_store[r] >= 0) partial[p_store[r] * n_super + sb] = L;
         }
 #pragma unroll
         for (int mt = 0; mt < NMT; ++mt) { M[mt] = 1.0; E[mt] = 0; }
