@@ -657,29 +657,56 @@ static __device__ __noinline__ double bi_mixm_slow(double p00, double p01, doubl
     return __dadd_rn(__dadd_rn(l0, l1), __dadd_rn(l2, l3));
 }
 
-// B fragments of one group: weight of this lane's corner (of every quartet) at event 8n + g, w = ((1 * x_0) * x_1) ...
-// (re-reading the fractions from L1 in fragment layout instead of shuffling them measured slower on B200)
+// B fragments.  The corner weights  w_c = ((1 * x_0) * x_1) ...  (x_d = the event's fraction or fl(1 - fraction) along
+// dimension d) are formed ONCE per event by the lane that loaded it -- NS subtractions and the corner products, all 2^NS
+// corners of the event in one lane -- and staged in shared memory as [group of the chunk][quartet j][event][4 corners];
+// fragment lane (g, t) then reads the weight of corner 4 j + t at event 8 n + g with one conflict-free LDS.64 per octet
+// and quartet.  (Round 1 handed the fractions to the fragment lanes by shuffles and formed the weights there: 16 SHFL +
+// 12 FP64 operations per group and a shuffle -> subtract -> multiply chain in front of every DMMA.)
 template <int NS>
-__device__ __forceinline__ void bi_mixm_weights(const double (&y)[BiMixm<NS>::NY], int g, int t, bool a_zero,
-                                                double (&w)[4][BiMixm<NS>::KS]) {
-    constexpr int KS = BiMixm<NS>::KS;
+struct BiMixmW {
+    static constexpr int GROUP_DOUBLES = BiMixm<NS>::KS * 32 * 4;               // weights of one 32-event group
+    static constexpr int WARP_DOUBLES = BI_MIXM_CHUNK * GROUP_DOUBLES;          // one chunk per warp
+    static constexpr int SMEM_BYTES = BI_TS_WARPS * WARP_DOUBLES * 8;
+};
+template <int NS>
+__device__ __forceinline__ void bi_mixm_store_weights(const BiMixChunk<NS>& ch, double* wbuf, int lane) {
+    constexpr int KS = BiMixm<NS>::KS, CORNERS = BiMixm<NS>::CORNERS, NY = BiMixm<NS>::NY;
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-        double x[BiMixm<NS>::NY];
+    for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
+        double up[NY], dn[NY];
 #pragma unroll
-        for (int dd = 0; dd < NS; ++dd) x[dd] = __shfl_sync(BI_FULL_MASK, y[dd], 8 * n + g);
+        for (int dd = 0; dd < NY; ++dd) {
+            up[dd] = ch.y[dd][i];
+            dn[dd] = __dsub_rn(1.0, up[dd]);
+        }
 #pragma unroll
         for (int j = 0; j < KS; ++j) {
-            const int c = (NS <= 1) ? (t & 1) : 4 * j + t;
-            double v = 1.0;
+            double v4[4];
 #pragma unroll
-            for (int dd = 0; dd < NS; ++dd) {
-                const double f = ((c >> (NS - 1 - dd)) & 1) ? x[dd] : __dsub_rn(1.0, x[dd]);
-                v = dd == 0 ? f : __dmul_rn(v, f);
+            for (int tt = 0; tt < 4; ++tt) {
+                const int c = (NS <= 1) ? (tt & 1) : 4 * j + tt;
+                double v = 1.0;
+#pragma unroll
+                for (int dd = 0; dd < NS; ++dd) {
+                    const double f = ((c >> (NS - 1 - dd)) & 1) ? up[dd] : dn[dd];
+                    v = dd == 0 ? f : __dmul_rn(v, f);
+                }
+                v4[tt] = tt >= CORNERS ? 0.0 : v;                   // fewer than 4 lookup corners: zero padding
             }
-            w[n][j] = a_zero ? 0.0 : v;
+            double2* dst = reinterpret_cast<double2*>(wbuf + ((size_t)(i * KS + j) * 32 + lane) * 4);
+            dst[0] = make_double2(v4[0], v4[1]);
+            dst[1] = make_double2(v4[2], v4[3]);
         }
     }
+}
+// weights of the group at wgrp for this fragment lane: corner 4 j + t at event 8 n + g
+template <int NS>
+__device__ __forceinline__ void bi_mixm_weights(const double* wgrp, int g, int t, double (&w)[4][BiMixm<NS>::KS]) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int j = 0; j < BiMixm<NS>::KS; ++j) w[n][j] = wgrp[((j * 32) + 8 * n + g) * 4 + t];
 }
 
 // densities of this lane's class -> canonical product tree -> (M, E) of the superblock; returns true when a density left
@@ -736,11 +763,11 @@ __device__ __forceinline__ void bi_mixm_load_a(const double* const (&Vq)[MT], bo
 // DEFER = true: branch-free -- bit mt of the result flags an m-tile whose class left the fast range; the caller runs
 // bi_mixm_group_redo for such groups afterwards, in group order (the order in which L accumulates).
 template <int NS, int MT, bool DEFER>
-__device__ __forceinline__ unsigned bi_mixm_group_fast(const double (&a)[MT][4][BiMixm<NS>::KS], const double (&y)[BiMixm<NS>::NY],
+__device__ __forceinline__ unsigned bi_mixm_group_fast(const double (&a)[MT][4][BiMixm<NS>::KS], const double* wgrp,
                                                        int g, int t, bool a_zero, const bool (&live_me)[MT], double outlier,
                                                        double (&M)[MT], int (&E)[MT], double (&L)[MT], bool& any_slow) {
     double w[4][BiMixm<NS>::KS];
-    bi_mixm_weights<NS>(y, g, t, a_zero, w);
+    bi_mixm_weights<NS>(wgrp, g, t, w);
     unsigned flags = 0;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -759,11 +786,11 @@ __device__ __forceinline__ unsigned bi_mixm_group_fast(const double (&a)[MT][4][
 }
 // the densities of a flagged group again (warp-collective), then the log tree in the lanes that flagged it
 template <int NS, int MT>
-__device__ __forceinline__ void bi_mixm_group_redo(const double (&a)[MT][4][BiMixm<NS>::KS], const double (&y)[BiMixm<NS>::NY],
+__device__ __forceinline__ void bi_mixm_group_redo(const double (&a)[MT][4][BiMixm<NS>::KS], const double* wgrp,
                                                    int g, int t, bool a_zero, unsigned flags, double outlier, double (&L)[MT],
                                                    bool& any_slow) {
     double w[4][BiMixm<NS>::KS];
-    bi_mixm_weights<NS>(y, g, t, a_zero, w);
+    bi_mixm_weights<NS>(wgrp, g, t, w);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         double d[4][2];
@@ -780,14 +807,14 @@ __device__ __forceinline__ void bi_mixm_group_redo(const double (&a)[MT][4][BiMi
 // any group: octets that straddle a bin edge take one contraction per event; events >= n_left count as p = 1
 template <int NS, int MT>
 __device__ __forceinline__ void bi_mixm_group_any(const double* const (&Vq)[MT], const BiTsSpace& sp, int bin,
-                                                  const double (&y)[BiMixm<NS>::NY], int n_left, int g, int t, bool a_zero,
+                                                  const double* wgrp, int n_left, int g, int t, bool a_zero,
                                                   const bool (&live_me)[MT], double outlier, double (&M)[MT], int (&E)[MT],
                                                   double (&L)[MT], bool& any_slow) {
     constexpr int KS = BiMixm<NS>::KS, PACK = BiMixm<NS>::PACK;
     const int first = __shfl_sync(BI_FULL_MASK, bin, threadIdx.x & 24);
     const unsigned neq = __ballot_sync(BI_FULL_MASK, bin != first);   // octets whose 8 events do not share one bin
     double w[4][KS];
-    bi_mixm_weights<NS>(y, g, t, a_zero, w);
+    bi_mixm_weights<NS>(wgrp, g, t, w);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         double d[4][2];
@@ -846,11 +873,13 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                        const int32_t* __restrict__ pair_point, const int64_t* __restrict__ pair_partial_offset,
                        double outlier, double* __restrict__ partial) {
     static_assert(NS >= 0 && NS <= 4, "piecewise lookups or linear lookups in 1..4 dimensions");
-    constexpr int NY = BiMixm<NS>::NY, KS = BiMixm<NS>::KS;
+    constexpr int KS = BiMixm<NS>::KS;
+    extern __shared__ __align__(16) double bi_mixm_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int64_t n_warps = (int64_t)gridDim.x * BI_TS_WARPS;
-    const bool a_zero = t >= BiMixm<NS>::CORNERS;                     // fewer than 4 lookup corners: zero padding
+    double* wbuf = bi_mixm_smem + (size_t)warp * BiMixmW<NS>::WARP_DOUBLES;      // corner weights of this warp's chunk
+    const bool a_zero = BiMixm<NS>::CORNERS < 4 && t >= BiMixm<NS>::CORNERS;   // fewer than 4 lookup corners: zero padding
 
     for (int64_t u = (int64_t)blockIdx.x * BI_TS_WARPS + warp; u < n_units; u += n_warps) {
         int64_t gi;
@@ -897,6 +926,9 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
 #pragma unroll 1
             for (int c0 = 0; c0 < n_ev; c0 += 32 * BI_MIXM_CHUNK) {
                 bi_mixm_load<NS>(ev_bin, ev_frac, ld_frac, ev_begin, c0 + 32 * BI_MIXM_CHUNK, n_ev, lane, nxt);
+                __syncwarp();                                         // the previous chunk's fragment reads are done
+                bi_mixm_store_weights<NS>(cur, wbuf, lane);
+                __syncwarp();
                 bool ne = false;
 #pragma unroll
                 for (int i = 0; i < BI_MIXM_CHUNK; ++i)
@@ -920,27 +952,16 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                             }
                         unsigned flags = 0;                                   // bit i * MT + mt: group i, m-tile mt left the fast range
 #pragma unroll
-                        for (int i = 0; i < BI_MIXM_CHUNK; ++i) {             // one branch-free block: the groups interleave
-                            double yy[NY];
-#pragma unroll
-                            for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][i];
-                            flags |= bi_mixm_group_fast<NS, MT, true>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow) << (i * MT);
-                        }
+                        for (int i = 0; i < BI_MIXM_CHUNK; ++i)               // one branch-free block: the groups interleave
+                            flags |= bi_mixm_group_fast<NS, MT, true>(a, wbuf + i * BiMixmW<NS>::GROUP_DOUBLES, g, t, a_zero,
+                                                                      live_me, outlier, M, E, L, any_slow) << (i * MT);
                         if (__any_sync(BI_FULL_MASK, flags != 0)) {           // rare: log trees, in group order
 #pragma unroll 1
                             for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
                                 const unsigned f = (flags >> (i * MT)) & ((1u << MT) - 1u);
                                 if (!__any_sync(BI_FULL_MASK, f != 0)) continue;
-                                double yy[NY];
-#pragma unroll
-                                for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][0];
-#pragma unroll
-                                for (int k = 1; k < BI_MIXM_CHUNK; ++k)
-                                    if (i == k) {
-#pragma unroll
-                                        for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][k];
-                                    }
-                                bi_mixm_group_redo<NS, MT>(a, yy, g, t, a_zero, f, outlier, L, any_slow);
+                                bi_mixm_group_redo<NS, MT>(a, wbuf + i * BiMixmW<NS>::GROUP_DOUBLES, g, t, a_zero, f, outlier, L,
+                                                           any_slow);
                             }
                         }
                     } else {
@@ -948,10 +969,8 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
 #pragma unroll
                         for (int i = 0; i < BI_MIXM_CHUNK; ++i) {
                             if (i + 1 < BI_MIXM_CHUNK) bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, cur.bin[i + 1], an);
-                            double yy[NY];
-#pragma unroll
-                            for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][i];
-                            bi_mixm_group_fast<NS, MT, false>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
+                            bi_mixm_group_fast<NS, MT, false>(a, wbuf + i * BiMixmW<NS>::GROUP_DOUBLES, g, t, a_zero, live_me,
+                                                              outlier, M, E, L, any_slow);
                             if (i + 1 < BI_MIXM_CHUNK) {
 #pragma unroll
                                 for (int mt = 0; mt < MT; ++mt)
@@ -968,31 +987,29 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                         const int e0 = c0 + 32 * i;
                         if (e0 >= n_ev) break;
                         int bin_i = cur.bin[0];
-                        double yy[NY];
 #pragma unroll
-                        for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][0];
-#pragma unroll
-                        for (int k = 1; k < BI_MIXM_CHUNK; ++k) {
-                            if (i == k) {
-                                bin_i = cur.bin[k];
-#pragma unroll
-                                for (int d = 0; d < NY; ++d) yy[d] = cur.y[d][k];
-                            }
-                        }
+                        for (int k = 1; k < BI_MIXM_CHUNK; ++k)
+                            if (i == k) bin_i = cur.bin[k];
+                        const double* wgrp = wbuf + i * BiMixmW<NS>::GROUP_DOUBLES;
                         const bool shared = !__any_sync(BI_FULL_MASK, bin_i != __shfl_sync(BI_FULL_MASK, bin_i, lane & 24));
                         if (shared && n_ev - e0 >= 32) {                  // the group's octets share their bins
                             double a[MT][4][KS];
                             bi_mixm_load_a<NS, MT>(Vq, a_zero, sp, bin_i, a);
-                            bi_mixm_group_fast<NS, MT, false>(a, yy, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
+                            bi_mixm_group_fast<NS, MT, false>(a, wgrp, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
                         } else {
-                            bi_mixm_group_any<NS, MT>(Vq, sp, bin_i, yy, n_ev - e0, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
+                            bi_mixm_group_any<NS, MT>(Vq, sp, bin_i, wgrp, n_ev - e0, g, t, a_zero, live_me, outlier, M, E, L, any_slow);
                         }
                     }
                 }
                 cur = nxt;
             }
             // ---- close the superblock: M = (M_0 * M_1) * (M_2 * M_3), E = sum, L = (L_0 + L_1) + (L_2 + L_3)
+            // (the four lanes of a row hold identical (m, e, l) after the butterflies: lane t evaluates the log of m-tile t,
+            // so a warp runs ONE log stream per superblock whatever MT is)
+            static_assert(MT <= 4, "one class lane per m-tile");
             const bool slow = __any_sync(BI_FULL_MASK, any_slow);
+            double m_mine = 1.0, l_mine = 0.0;
+            int e_mine = 0;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 double m = M[mt];
@@ -1001,15 +1018,19 @@ k_mixture_partials_mma(const double* __restrict__ tmix, int64_t n_bins /* double
                 int e = E[mt];
                 e += __shfl_xor_sync(BI_FULL_MASK, e, 1);
                 e += __shfl_xor_sync(BI_FULL_MASK, e, 2);
-                double r = bi_block_log(m, e);
+                double l = 0.0;
                 if (slow) {
-                    double l = L[mt];
+                    l = L[mt];
                     l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
                     l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 2));
-                    r = __dadd_rn(r, l);
                 }
-                if (t == 0 && live_me[mt]) partial[pair_partial_offset[pair[mt]] + sb] = r;
+                if (MT == 1 || t == mt) { m_mine = m; e_mine = e; l_mine = l; }
             }
+            double r = bi_block_log(m_mine, e_mine);
+            if (slow) r = __dadd_rn(r, l_mine);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                if (t == mt && live_me[mt]) partial[pair_partial_offset[pair[mt]] + sb] = r;
         }
     }
 }
@@ -1360,14 +1381,17 @@ static int bi_mixm_launch(const double* tmix, int64_t n_bins, const BiTsSpace& s
         int dev = 0, sms = 0, per_sm = 0;
         BI_CUDA_CHECK(cudaGetDevice(&dev));
         BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mixture_partials_mma<NS, MT>, BI_TS_THREADS, 0));
+        BI_CUDA_CHECK(cudaFuncSetAttribute(k_mixture_partials_mma<NS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           BiMixmW<NS>::SMEM_BYTES));
+        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mixture_partials_mma<NS, MT>, BI_TS_THREADS,
+                                                                    BiMixmW<NS>::SMEM_BYTES));
         BI_REQUIRE(per_sm >= 1, "k_mixture_partials_mma<%d,%d> does not fit on this device", NS, MT);
         resident = sms * per_sm;
     }
     int64_t blocks = resident;
     const int64_t needed = (n_units + BI_TS_WARPS - 1) / BI_TS_WARPS;
     if (blocks > needed) blocks = needed;
-    k_mixture_partials_mma<NS, MT><<<(unsigned)blocks, BI_TS_THREADS, 0, st>>>(
+    k_mixture_partials_mma<NS, MT><<<(unsigned)blocks, BI_TS_THREADS, BiMixmW<NS>::SMEM_BYTES, st>>>(
         tmix, n_bins, sp, ev_bin, ev_frac, ld_frac, dataset_offset, status, n_groups, groups, unit_offset, unit_group,
         n_units, pair_point, pair_partial_offset, outlier, partial);
     BI_LAUNCH_CHECK();
