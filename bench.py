@@ -294,6 +294,27 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------------------------
 # own arm
+_PAD = {}
+
+
+def _tight_barrier(world):
+    """Barrier in front of a timed e2e call at N > 1: the NCCL barrier, then a signal-pad barrier over NVLink peer memory
+    (torch symmetric memory, the PeerGather plumbing) followed by a stream synchronize.  The ranks leave it within ~2 us of
+    each other; after dist.barrier() alone they leave ~6 us apart with outliers of several hundred us (measured at N = 8,
+    profiles/r2/diag_ngpu.py), and a wall clock started behind it charges that skew to the call."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    dist.barrier()
+    pad = _PAD.get("pad")
+    if pad is None:
+        from blueice_b200.distributed import PeerGather
+        pad = _PAD["pad"] = PeerGather(1)
+    pad.barrier()
+    torch.cuda.synchronize()
+
+
 def _median_max_over_ranks(fn, n_warm, n_rep, world, device):
     """Wall time of fn() (median of n_rep calls after n_warm warm-ups; every call starts behind a barrier), the maximum
     over the ranks, and the same for the device span (CUDA events around the call)."""
@@ -304,8 +325,7 @@ def _median_max_over_ranks(fn, n_warm, n_rep, world, device):
     wall, dev = [], []
     for _ in range(n_rep):
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        _tight_barrier(world)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         a.record()
@@ -485,8 +505,7 @@ def other_configs(args, rank, world, device):
     e2e = []
     for _ in range(5):
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        _tight_barrier(world)
         t0 = time.perf_counter()
         res = toy_call()
         e2e.append(time.perf_counter() - t0)
@@ -892,8 +911,7 @@ def run_own_arm(args):
     for k in range(args.steps):
         flush_l2()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        _tight_barrier(world)
         t0 = time.perf_counter()
         res = e2e_call()
         e2e_s.append(time.perf_counter() - t0)
@@ -915,7 +933,7 @@ def run_own_arm(args):
         for k in range(args.steps):
             flush_l2()
             torch.cuda.synchronize()
-            dist.barrier()
+            _tight_barrier(world)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             a.record()

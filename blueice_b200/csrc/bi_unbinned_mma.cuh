@@ -59,6 +59,9 @@
 #ifndef BI_MMA_STAGES_SMALL
 #define BI_MMA_STAGES_SMALL 2
 #endif
+#ifndef BI_MMA_GROUP_UNROLL
+#define BI_MMA_GROUP_UNROLL 1   /* groups of a full tile per loop iteration */
+#endif
 #ifndef BI_MMA_WARPS_SMALL
 #define BI_MMA_WARPS_SMALL 4
 #endif
@@ -382,6 +385,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
     for (int mt = 0; mt < NMT; ++mt) { M[mt] = 1.0; E[mt] = 0; }
     bool slow_any = false;
     constexpr int TILES_PER_SUPER = BI_SUPERBLOCK / T, GROUPS_PER_TILE = T / BI_GROUP_EVENTS;
+    constexpr int GROUP_UNROLL = K4 <= 2 ? BI_MMA_GROUP_UNROLL : 1;
     // the point whose partial this lane stores at a superblock close (lane t of row g: m-tiles t, t + 4), read once per unit
     int64_t p_store[(NMT + 3) / 4];
 #pragma unroll
@@ -404,7 +408,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
             const double* tile = ring + (size_t)st * Cfg::STAGE_DOUBLES;
             const int n_valid = n_ev - ti * T;                                   // may exceed T
             if (n_valid >= T) {
-#pragma unroll 1
+#pragma unroll GROUP_UNROLL
                 for (int gi = 0; gi < GROUPS_PER_TILE; ++gi)
                     bi_mma_group<K4, NMT, false>(tile, gi * BI_GROUP_EVENTS, T, K, S, active_mask, a, slot_point, term_source,
                                                  wterm, mus, outlier, slow_acc, slow_any, M, E, lane);

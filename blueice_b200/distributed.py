@@ -328,7 +328,9 @@ class ToyShardedLikelihood(object):
             gathered = engine.last_gathered
         finally:
             engine.peer_gather = None
-        device_ll = np.concatenate([gathered[r, :c] for r, c in enumerate(counts)])
+        # (gathered is a fresh copy of the pinned landing buffer: equal shards need no second copy)
+        device_ll = gathered.reshape(-1) if min(counts) == gathered.shape[1] else \
+            np.concatenate([gathered[r, :c] for r, c in enumerate(counts)])
         has_priors = any(p is not None for _, p, _ in self.ll.shape_parameters.values()) or \
             any(p is not None for p in self.ll.rate_parameters.values())
         if not has_priors:

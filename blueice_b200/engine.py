@@ -490,7 +490,11 @@ class UnbinnedEngine(_EngineBase):
             n_x = P if mode == 'sum' else pg.world * pg.n
             x_view = self._pin_x(st, n_x).numpy()
             x_view = x_view[:P] if mode == 'sum' else x_view.reshape(pg.world, -1)
-        h2d, d2h = st["n_in"] * 8, P * 12 + n_x * 8
+        if pg is not None and mode != 'sum' and pg.n == P and pg.fallback is None:
+            logl_v = x_view[pg.rank]                             # the local rows arrive with the gathered block
+            h2d, d2h = st["n_in"] * 8, P * 4 + n_x * 8
+        else:
+            h2d, d2h = st["n_in"] * 8, P * 12 + n_x * 8
 
         def run():
             if self.peer_gather is not pg or self.peer_mode != mode:
@@ -584,6 +588,10 @@ class UnbinnedEngine(_EngineBase):
                 pg.reduce(st["out_f"][P:2 * P], st["out_f"][2 * P:3 * P], st["out_i"], out=self._pin_x(st, P))
             else:
                 pg.gather(st["out_f"][:P], out=self._pin_x(st, pg.world * pg.n))    # point sharding: all ranks' logl rows
+                if n_f == P and pg.n == P and pg.fallback is None:
+                    # this rank's own logl rows are row `rank` of the gathered block: no separate copy node for them
+                    st["pin_i"].copy_(st["out_i"], non_blocking=True)
+                    return
         st["pin_f"][:n_f].copy_(st["out_f"][:n_f], non_blocking=True)
         st["pin_i"].copy_(st["out_i"], non_blocking=True)
 
@@ -664,8 +672,12 @@ class UnbinnedEngine(_EngineBase):
                 self.last_total = x[:P].copy()
             else:
                 self.last_gathered = x.reshape(pg.world, -1).copy()
+                if n_f == P and pg.n == P and pg.fallback is None:
+                    st["pin_f_np"][:P] = self.last_gathered[pg.rank]    # (the sequence skips the copy node of the local rows)
         self.last_h2d_bytes = st["n_in"] * 8            # zero-copy batches: read by the kernel over PCIe, same bytes
         self.last_d2h_bytes = (3 * P * 8 if st["zero_copy"] else n_f * 8) + P * 4 + n_x * 8
+        if pg is not None and self.peer_mode != 'sum' and n_f == P and pg.n == P and pg.fallback is None:
+            self.last_d2h_bytes -= P * 8
         res = st["pin_f_np"]
         if return_parts:
             return res[P:2 * P].copy(), res[2 * P:3 * P].copy(), st["pin_i_np"].copy()
@@ -1712,9 +1724,9 @@ class TemplateUnbinnedEngine(_EngineBase):
             self._graphs[gkey]["last_s"] = _time.perf_counter() - t_start
         self.last_h2d_bytes = nbytes
         self.last_d2h_bytes = n_f * 8 + P * 4 + n_x * 8
-        res = out_pin.numpy().copy()
-        status = st_pin.numpy().copy()
-        ll, ls = res[:P], res[P:2 * P]
+        res = out_pin.numpy()[:n_f].copy()                                  # only what this call delivered
+        status = st_pin.numpy()[:P].copy()
+        ll, ls = res[:P], (res[P:2 * P] if return_parts else None)
         inv = None
         if order is not None:                                               # pair order -> point order
             inv = np.empty(P, dtype=np.int64)
@@ -1724,7 +1736,8 @@ class TemplateUnbinnedEngine(_EngineBase):
         if pg is not None and mode == 'sum':
             total = g_pin.numpy()[:P].copy()                                # rank-ordered sum of the log sums, pair order
             total = total if inv is None else total[inv]
-            self.last_total = np.where(status != 0, -np.inf, -res[2 * P:3 * P] + total)
+            if return_parts:                                                # (the mu sums arrive with the parts only)
+                self.last_total = np.where(status != 0, -np.inf, -res[2 * P:3 * P] + total)
         elif pg is not None:
             gathered = g_pin.numpy().reshape(pg.world, -1).copy()
             self.last_gathered = gathered if inv is None else np.concatenate([gathered[:, :P][:, inv], gathered[:, P:]], axis=1)
