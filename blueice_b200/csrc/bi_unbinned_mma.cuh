@@ -59,8 +59,8 @@
 #ifndef BI_MMA_STAGES_SMALL
 #define BI_MMA_STAGES_SMALL 2
 #endif
-#ifndef BI_MMA_GROUP_UNROLL
-#define BI_MMA_GROUP_UNROLL 1   /* groups of a full tile per loop iteration */
+#ifndef BI_MMA_GROUP_DEFER
+#define BI_MMA_GROUP_DEFER 1    /* K <= 8: the groups of a full tile run as one branch-free block */
 #endif
 #ifndef BI_MMA_WARPS_SMALL
 #define BI_MMA_WARPS_SMALL 4
@@ -213,13 +213,13 @@ __device__ __forceinline__ void bi_mma_tile(const double* __restrict__ bcol, con
 // NMT (compile time) m-tiles in use: the body is ONE branch-free basic block, so ptxas interleaves the DMMAs
 // of the next m-tile with the product-tree epilogue of the previous one.
 // TAIL: the group holds events >= N (they count as p = 1).
+// Returns the m-tiles (bit mt) whose class left the fast range in this group: their (m, e) stay neutral here and the
+// caller runs bi_mma_group_slow for them -- right away, or, for the groups of a full tile, after the last group, so that
+// the whole tile is ONE basic block and the product-tree tail of a group overlaps the loads and DMMAs of the next.
 template <int K4, int NMT, bool TAIL>
-__device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, int e0, int n_valid, int K, int S,
-                                             unsigned active_mask, const double (&a)[NMT][K4],
-                                             const int32_t* __restrict__ slot_point,
-                                             const int32_t* __restrict__ term_source, const double* __restrict__ wterm,
-                                             const double* __restrict__ mus, double outlier, double* slow_acc,
-                                             bool& slow_any, double (&M)[NMT], int (&E)[NMT], int lane) {
+__device__ __forceinline__ unsigned bi_mma_group_fast(const double* __restrict__ tile, int e0, int n_valid,
+                                                      unsigned active_mask, const double (&a)[NMT][K4],
+                                                      double (&M)[NMT], int (&E)[NMT], int lane) {
     using Cfg = BiMmaCfg<K4>;
     const int g = lane >> 2, t = lane & 3;
     // B fragment of octet n, k-step kk: tile[(4 kk + t) * RS + e0 + 8 n + g] (rows >= K are zero)
@@ -266,20 +266,42 @@ __device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, in
         M[mt] = __dmul_rn(M[mt], m);
         E[mt] += e;
     }
-    bad &= active_mask;
-    // rare: reference-semantics fallback per (t, group).  The branch is taken by the whole warp (a vote): a lane-divergent
-    // `if (bad)` made every group pay a reconvergence barrier (BSSY / WARPSYNC / BSYNC around the body)
-    if (__any_sync(BI_FULL_MASK, bad != 0)) {
-        for (int mt = 0; mt < NMT; ++mt) {
-            if ((bad >> mt) & 1u) {
-                const int64_t p = slot_point[mt * 8 + g];
-                const int nv = TAIL ? (n_valid - e0 < BI_GROUP_EVENTS ? n_valid - e0 : BI_GROUP_EVENTS) : BI_GROUP_EVENTS;
-                const double l = bi_slow_group(tile + e0, Cfg::RS, K, S, t, nv, term_source, wterm + p * K, mus + p * S, outlier);
-                double* acc = slow_acc + mt * Cfg::THREADS;
-                *acc = __dadd_rn(*acc, l);
-                slow_any = true;
-            }
+    return bad & active_mask;
+}
+
+// rare: reference-semantics fallback per (t, group) for the m-tiles flagged in `bad`.  Called behind a warp vote (a
+// lane-divergent `if (bad)` around the group made every group pay a reconvergence barrier).
+template <int K4, int NMT>
+__device__ __forceinline__ void bi_mma_group_slow(const double* __restrict__ tile, int e0, int nv, int K, int S, unsigned bad,
+                                                  const int32_t* __restrict__ slot_point,
+                                                  const int32_t* __restrict__ term_source, const double* __restrict__ wterm,
+                                                  const double* __restrict__ mus, double outlier, double* slow_acc,
+                                                  bool& slow_any, int lane) {
+    using Cfg = BiMmaCfg<K4>;
+    const int g = lane >> 2, t = lane & 3;
+    for (int mt = 0; mt < NMT; ++mt) {
+        if ((bad >> mt) & 1u) {
+            const int64_t p = slot_point[mt * 8 + g];
+            const double l = bi_slow_group(tile + e0, Cfg::RS, K, S, t, nv, term_source, wterm + p * K, mus + p * S, outlier);
+            double* acc = slow_acc + mt * Cfg::THREADS;
+            *acc = __dadd_rn(*acc, l);
+            slow_any = true;
         }
+    }
+}
+
+// one group, rare path right behind it
+template <int K4, int NMT, bool TAIL>
+__device__ __forceinline__ void bi_mma_group(const double* __restrict__ tile, int e0, int n_valid, int K, int S,
+                                             unsigned active_mask, const double (&a)[NMT][K4],
+                                             const int32_t* __restrict__ slot_point,
+                                             const int32_t* __restrict__ term_source, const double* __restrict__ wterm,
+                                             const double* __restrict__ mus, double outlier, double* slow_acc,
+                                             bool& slow_any, double (&M)[NMT], int (&E)[NMT], int lane) {
+    const unsigned bad = bi_mma_group_fast<K4, NMT, TAIL>(tile, e0, n_valid, active_mask, a, M, E, lane);
+    if (__any_sync(BI_FULL_MASK, bad != 0)) {
+        const int nv = TAIL ? (n_valid - e0 < BI_GROUP_EVENTS ? n_valid - e0 : BI_GROUP_EVENTS) : BI_GROUP_EVENTS;
+        bi_mma_group_slow<K4, NMT>(tile, e0, nv, K, S, bad, slot_point, term_source, wterm, mus, outlier, slow_acc, slow_any, lane);
     }
 }
 
@@ -385,7 +407,7 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
     for (int mt = 0; mt < NMT; ++mt) { M[mt] = 1.0; E[mt] = 0; }
     bool slow_any = false;
     constexpr int TILES_PER_SUPER = BI_SUPERBLOCK / T, GROUPS_PER_TILE = T / BI_GROUP_EVENTS;
-    constexpr int GROUP_UNROLL = K4 <= 2 ? BI_MMA_GROUP_UNROLL : 1;
+    constexpr bool GROUP_DEFER = K4 <= 2 && BI_MMA_GROUP_DEFER;
     // the point whose partial this lane stores at a superblock close (lane t of row g: m-tiles t, t + 4), read once per unit
     int64_t p_store[(NMT + 3) / 4];
 #pragma unroll
@@ -407,8 +429,24 @@ __device__ __forceinline__ void bi_mma_unit(const double* __restrict__ A, const 
             bi_mbar_wait(&full_bar[st], (consumed / Cfg::STAGES) & 1u);
             const double* tile = ring + (size_t)st * Cfg::STAGE_DOUBLES;
             const int n_valid = n_ev - ti * T;                                   // may exceed T
-            if (n_valid >= T) {
-#pragma unroll GROUP_UNROLL
+            if (n_valid >= T && GROUP_DEFER) {
+                // full tile: its groups run as one branch-free block, the rare path afterwards in group order (the order
+                // in which the L_t accumulate)
+                unsigned bad[GROUPS_PER_TILE], bad_any = 0;
+#pragma unroll
+                for (int gi = 0; gi < GROUPS_PER_TILE; ++gi) {
+                    bad[gi] = bi_mma_group_fast<K4, NMT, false>(tile, gi * BI_GROUP_EVENTS, T, active_mask, a, M, E, lane);
+                    bad_any |= bad[gi];
+                }
+                if (__any_sync(BI_FULL_MASK, bad_any != 0)) {
+#pragma unroll
+                    for (int gi = 0; gi < GROUPS_PER_TILE; ++gi)
+                        if (__any_sync(BI_FULL_MASK, bad[gi] != 0))
+                            bi_mma_group_slow<K4, NMT>(tile, gi * BI_GROUP_EVENTS, BI_GROUP_EVENTS, K, S, bad[gi], slot_point,
+                                                       term_source, wterm, mus, outlier, slow_acc, slow_any, lane);
+                }
+            } else if (n_valid >= T) {
+#pragma unroll 1
                 for (int gi = 0; gi < GROUPS_PER_TILE; ++gi)
                     bi_mma_group<K4, NMT, false>(tile, gi * BI_GROUP_EVENTS, T, K, S, active_mask, a, slot_point, term_source,
                                                  wterm, mus, outlier, slow_acc, slow_any, M, E, lane);
