@@ -204,8 +204,9 @@ def workload_config(n_events, n_points):
             "n_anchors": len(ANCHORS) ** N_SHAPE, "lookup": "linear",
             "l2": "flushed between timed steps (512 MB write, outside the timed intervals)",
             "parallelism": "weak: every GPU evaluates its own 4096 points of the scan on a replicated dataset (point sharding "
-                           "has no data-path collective); device arm: each step stores its results on every rank over NVLink "
-                           "(bi_peer_broadcast), one barrier after the timed loop; e2e arm: PointShardedLikelihood.batch, "
+                           "has no data-path collective); device arm: each step replays the four launches of the evaluation as one CUDA "
+                           "graph and stores its results on every rank over NVLink (bi_peer_broadcast), one barrier after "
+                           "the timed loop; e2e arm: PointShardedLikelihood.batch, "
                            "every call ends with one bi_peer_exchange launch (stores + flags + wait + delivery to pinned "
                            "host memory) inside the call's CUDA graph; e2e also carries the strongly scaled scan, the "
                            "event-sharded config 5 and the toy-sharded config 4 as flat keys"}
@@ -869,25 +870,54 @@ def run_own_arm(args):
             gathered_dev = peer_gather.gather(logl) if args.gather_wait else peer_gather.broadcast(logl)
         return logl
 
+    launches0 = eng.launches
     for _ in range(max(args.warmup, 3)):
         flush_l2()
         device_step()
+    launches_per_step = (eng.launches - launches0) // max(args.warmup, 3) + (1 if world > 1 else 0)   # + bi_peer_broadcast
+    # the four launches of the evaluation replayed as ONE CUDA graph (as the e2e path does): with N processes sharing the
+    # host, eager launches let single steps stall for hundreds of microseconds between kernels (0.54 ms steps next to
+    # 0.32 ms ones at N = 8), which the device-resident figure should not depend on.  The P2P stores stay a launch of
+    # their own (their slot parity is tracked on the host).
+    step_graph, logl_static = None, None
+    if not args.no_step_graph:
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                logl_static = eng.run_device(P, zs_d, mult_d, None, None, plan, plan_dev)
+            step_graph = g
+        except Exception:
+            step_graph = None
+            torch.cuda.synchronize()
+
+    def timed_step():
+        nonlocal gathered_dev
+        if step_graph is None:
+            return device_step()
+        step_graph.replay()
+        if world > 1:
+            gathered_dev = peer_gather.gather(logl_static) if args.gather_wait else peer_gather.broadcast(logl_static)
+        return logl_static
+
+    for _ in range(3):
+        flush_l2()
+        timed_step()
     barrier()
     sampler.start()
-    launches0 = eng.launches
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     for k in range(args.steps):
         flush_l2()
         starts[k].record()
-        logl = device_step()
+        logl = timed_step()
         ends[k].record()
     if world > 1:
         peer_gather.barrier()
     barrier()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(np.sum(step_ms))
-    launches_timed = eng.launches - launches0 + (args.steps if world > 1 else 0)      # + bi_peer_broadcast per step
+    launches_timed = launches_per_step * args.steps
     result_dev = logl.cpu().numpy().copy()
     gathered_host = gathered_dev.cpu().numpy().copy() if world > 1 else None
 
@@ -903,10 +933,13 @@ def run_own_arm(args):
     else:
         def e2e_call():
             return ll.batch(table, names)
-    for _ in range(3):
+    # (a sharded call rotates over pinned landing buffers, each with its own CUDA graph, captured on its second use: the
+    # warm-up holds its results like the timed loop does, so that both buffers of the rotation are captured before it)
+    res = None
+    for _ in range(6 if world > 1 else 3):
         flush_l2()
         torch.cuda.synchronize()
-        e2e_call()
+        res = e2e_call()
     e2e_s = []
     for k in range(args.steps):
         flush_l2()
@@ -926,7 +959,7 @@ def run_own_arm(args):
     strong = None
     if world > 1:
         table_strong = table_all[:P]
-        for _ in range(3):
+        for _ in range(6):
             flush_l2()
             res_s = sharded.batch(table_strong, names)
         ts, ds = [], []
@@ -1180,6 +1213,7 @@ def main():
                     help="force a K2 kernel for the scan (default: the engine's own choice)")
     ap.add_argument("--gather-wait", action="store_true",
                     help="N > 1: wait for all ranks' results inside every step (a barrier per step) instead of once at the end")
+    ap.add_argument("--no-step-graph", action="store_true", help="device arm: eager launches instead of a CUDA graph replay")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-other", action="store_true", help="skip the config-4 / config-5 template-engine runs")
     ap.add_argument("--toys", type=int, default=100000, help="config 4: toys per GPU")

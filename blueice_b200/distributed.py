@@ -253,8 +253,10 @@ class PointShardedLikelihood(object):
             gathered = engine.last_gathered
         finally:
             engine.peer_gather = None
-        # (gathered may be a view of the engine's pinned result buffer: copy out)
-        device_ll = gathered.reshape(-1).copy() if min(counts) == n_rows else \
+        # (gathered is either a landing buffer handed over to this call -- no copy -- or a view of the engine's scratch
+        # buffer, which the next call overwrites)
+        owned = getattr(engine, 'last_gathered_owned', False)
+        device_ll = (gathered.reshape(-1) if owned else gathered.reshape(-1).copy()) if min(counts) == n_rows else \
             np.concatenate([gathered[r, :c] for r, c in enumerate(counts)])
         has_priors = any(p is not None for _, p, _ in self.ll.shape_parameters.values()) or \
             any(p is not None for p in self.ll.rate_parameters.values())

@@ -14,6 +14,7 @@ Per batch of P points (workspace, reused between calls):
 """
 import ctypes
 import os
+import sys
 import time as _time
 
 import numpy as np
@@ -182,6 +183,7 @@ def plan_points(grid, zs, n_sources, n_super, force_kernel=None):
 _MMA_TARGET_UNITS = (int(os.environ.get('BI_MMA_TARGET_UNITS', 148 * 12 * 32))
                      | (int(os.environ.get('BI_MMA_FULL_UNITS', '1')) << 30))
 _EMPTY_I32 = np.zeros(0, dtype=np.int32)
+_X_SLOTS = int(os.environ.get('BI_X_SLOTS', '3'))                # rotating pinned landing buffers of a gathered result
 _E2E_GRAPHS = os.environ.get('BI_E2E_GRAPHS', '1') != '0'     # replay the e2e sequence of a batch size as one CUDA graph
 _DIRECT_IO = os.environ.get('BI_DIRECT_IO', '1') != '0'        # kernels read / write small batches in pinned host memory
 _DIRECT_IO_MAX_BYTES = 1 << 20
@@ -292,6 +294,7 @@ class UnbinnedEngine(_EngineBase):
         self.peer_gather = None       # distributed.PeerGather: the exchange step of a sharded evaluation, issued on the
         self.peer_mode = 'gather'     # device right after finalize ('gather': logl rows of all ranks, point sharding;
         self.last_gathered = None     # 'sum': rank-ordered sum of the shards' log sums, event sharding)
+        self.last_gathered_owned = True   # False: last_gathered is a view of a scratch buffer, copy before the next call
         self.last_total = None
         self.full_grid_layout = os.environ.get('BI_MMA_NO_TENSORMAP') is None   # rows = [G][S][ld] anchor tensor
 
@@ -484,32 +487,51 @@ class UnbinnedEngine(_EngineBase):
         pg, mode = self.peer_gather, self.peer_mode            # a sharded evaluation: the exchange launch rides along
         n_launch = 1 if st["zero_copy"] else (4 if self.n_super > 0 else 2)
         n_x = 0
-        x_view = None
+        x_np = None
+        local_in_block = False
         if pg is not None:
             n_launch += 0 if pg.fallback is not None else 1
             n_x = P if mode == 'sum' else pg.world * pg.n
-            x_view = self._pin_x(st, n_x).numpy()
-            x_view = x_view[:P] if mode == 'sum' else x_view.reshape(pg.world, -1)
-        if pg is not None and mode != 'sum' and pg.n == P and pg.fallback is None:
-            logl_v = x_view[pg.rank]                             # the local rows arrive with the gathered block
-            h2d, d2h = st["n_in"] * 8, P * 4 + n_x * 8
-        else:
-            h2d, d2h = st["n_in"] * 8, P * 12 + n_x * 8
+            # landing buffers of the exchange result in pinned memory.  Slot 0 is scratch (its contents are copied out by
+            # the caller); a gather of all ranks' rows (point / toy sharding) rotates over slots 1.._X_SLOTS and hands the
+            # buffer itself to the caller -- a slot is reused only when no array or view of the previous result is alive
+            # (CPython reference count of the slot's ndarray: every NumPy view chains back to it), so a gathered block of
+            # world * P values costs no host copy.  Every slot has its own CUDA graph (the address is part of the launch).
+            n_slots = 1 + (_X_SLOTS if mode != 'sum' and pg.fallback is None else 0)
+            x_np = [self._pin_x(st, n_x, k).numpy() for k in range(n_slots)]
+            local_in_block = mode != 'sum' and pg.n == P and pg.fallback is None
+        h2d, d2h = st["n_in"] * 8, (P * 4 if local_in_block else P * 12) + n_x * 8
+        getrefcount = sys.getrefcount
+        last_slot = [0]
 
         def run():
             if self.peer_gather is not pg or self.peer_mode != mode:
                 raise RuntimeError("batch_runner: the engine's exchange set-up changed since the runner was built")
-            graph = self._fused_graph(st, P)
+            slot = 0
+            if pg is not None:
+                self.last_gathered = self.last_total = None      # (the views of the previous call are released)
+                for k in range(1, len(x_np)):
+                    cand = 1 + (last_slot[0] + k - 1) % (len(x_np) - 1)
+                    if getrefcount(x_np[cand]) == 2:             # the list and this call: nobody holds the last result
+                        slot = last_slot[0] = cand
+                        break
+            graph = self._fused_graph(st, P, slot)
             if graph is not None:
                 graph.replay()
             else:
-                self._fused_sequence(st, P, stream)
+                self._fused_sequence(st, P, stream, slot)
             sync()
             self.launches += n_launch
             self.last_h2d_bytes, self.last_d2h_bytes = h2d, d2h
-            if pg is not None:                                   # views of the pinned exchange result (no copies)
-                self.last_gathered, self.last_total = (None, x_view) if mode == 'sum' else (x_view, None)
-            return logl_v, status_v
+            if pg is None:
+                return logl_v, status_v
+            self.last_gathered_owned = slot != 0                 # True: the caller may keep the block without copying it
+            if mode == 'sum':
+                self.last_total = x_np[slot][:P]
+                return logl_v, status_v
+            block = x_np[slot].reshape(pg.world, -1)
+            self.last_gathered = block
+            return (block[pg.rank] if local_in_block else logl_v), status_v
         return zs_v, mult_v, scale_v, run
 
     def _fused_state(self, P, has_scale, has_eff):
@@ -565,7 +587,7 @@ class UnbinnedEngine(_EngineBase):
         self._fused_cache[key] = st
         return st
 
-    def _fused_sequence(self, st, n_f, stream):
+    def _fused_sequence(self, st, n_f, stream, slot=0):
         """Everything the device does for one e2e evaluation of a cached state, issued on `stream`: H2D of the staged
         inputs, the fused call (four launches), the exchange step of a sharded evaluation (one launch), D2H."""
         P = st["P"]
@@ -585,9 +607,9 @@ class UnbinnedEngine(_EngineBase):
             # the exchange kernel delivers its result to pinned host memory itself (no copy node)
             if self.peer_mode == 'sum':
                 # event sharding: -musum + (rank-ordered sum of the shards' log sums), -inf where the point is unphysical
-                pg.reduce(st["out_f"][P:2 * P], st["out_f"][2 * P:3 * P], st["out_i"], out=self._pin_x(st, P))
+                pg.reduce(st["out_f"][P:2 * P], st["out_f"][2 * P:3 * P], st["out_i"], out=self._pin_x(st, P, slot))
             else:
-                pg.gather(st["out_f"][:P], out=self._pin_x(st, pg.world * pg.n))    # point sharding: all ranks' logl rows
+                pg.gather(st["out_f"][:P], out=self._pin_x(st, pg.world * pg.n, slot))    # point sharding: all ranks' logl rows
                 if n_f == P and pg.n == P and pg.fallback is None:
                     # this rank's own logl rows are row `rank` of the gathered block: no separate copy node for them
                     st["pin_i"].copy_(st["out_i"], non_blocking=True)
@@ -595,14 +617,14 @@ class UnbinnedEngine(_EngineBase):
         st["pin_f"][:n_f].copy_(st["out_f"][:n_f], non_blocking=True)
         st["pin_i"].copy_(st["out_i"], non_blocking=True)
 
-    def _pin_x(self, st, n):
-        """Pinned landing buffer of the exchange results of a cached state (one per size)."""
-        pin_x = st.get(("pin_x", n))
+    def _pin_x(self, st, n, slot=0):
+        """Pinned landing buffer `slot` of the exchange results of a cached state (per size)."""
+        pin_x = st.get(("pin_x", n, slot))
         if pin_x is None:
-            pin_x = st[("pin_x", n)] = self.torch.empty(n, dtype=self.torch.float64, pin_memory=True)
+            pin_x = st[("pin_x", n, slot)] = self.torch.empty(n, dtype=self.torch.float64, pin_memory=True)
         return pin_x
 
-    def _fused_graph(self, st, n_f):
+    def _fused_graph(self, st, n_f, slot=0):
         """CUDA graph of the e2e sequence of this cached state (None: not built yet, disabled, or capture failed).
         Built on the SECOND call with a state, so that one-off evaluations and the lazily initialised kernel
         attributes of the first call stay outside the capture.  A sharded evaluation captures its exchange launch too
@@ -612,7 +634,7 @@ class UnbinnedEngine(_EngineBase):
         pg = self.peer_gather
         if pg is not None and pg.fallback is not None:
             return None                                             # NCCL fallback: stay eager
-        key = ("graph", n_f, None if pg is None else (id(pg), self.peer_mode))
+        key = ("graph", n_f, None if pg is None else (id(pg), self.peer_mode), slot)
         if key in st:
             return st[key]
         ckey = ("calls",) + key[1:]
@@ -625,7 +647,7 @@ class UnbinnedEngine(_EngineBase):
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
-                self._fused_sequence(st, n_f, torch.cuda.current_stream(self.device))
+                self._fused_sequence(st, n_f, torch.cuda.current_stream(self.device), slot)
             graph = g
         except Exception:                                           # capture not possible here: stay on the eager path
             graph = None
@@ -664,6 +686,7 @@ class UnbinnedEngine(_EngineBase):
             (4 if self.n_super > 0 else 2) + (0 if pg is None or pg.fallback is not None else 1)
         stream.synchronize()
         self.last_gathered = self.last_total = None
+        self.last_gathered_owned = True                 # (copies of the scratch slot)
         n_x = 0
         if pg is not None:
             n_x = P if self.peer_mode == 'sum' else pg.world * pg.n

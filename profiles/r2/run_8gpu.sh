@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/g8_pytest.log 2>&1; echo "multi pytest rc=$?"; tail -3 gpurun_out/g8_pytest.log
+true
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \
     bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/g8_bench8.json 2> gpurun_out/g8_bench8.err
 echo "bench8 rc=$?"

@@ -55,6 +55,24 @@ def main():
     table2[:, 0] *= 1.01
     assert np.array_equal(sharded.batch(table2, names), ll.batch(table2, names))
 
+    # equal shards, no priors: the gathered block is handed over without a host copy (rotating pinned landing buffers);
+    # results that are still referenced must survive later calls, whatever the caller keeps (arrays, rows, slices)
+    ll0, _, names0 = wl.c2_api(2, 2, (-1., 0., 1.), (40, 30), n_events=5000, seed=11)
+    sharded0 = bdist.PointShardedLikelihood(ll0)
+    tabs = [np.ascontiguousarray(table[:32 * world] * (1.0 + 0.001 * k)) for k in range(7)]
+    for t in tabs:
+        t[:, 2:] = table[:32 * world, 2:]                             # keep the shape parameters in range
+    want = [ll0.batch(t, names0) for t in tabs]
+    kept = []
+    for k, t in enumerate(tabs):
+        r = sharded0.batch(t, names0)
+        assert np.array_equal(r, want[k]), ("equal shards differ", k)
+        kept.append(r if k % 3 == 0 else (r[5:9] if k % 3 == 1 else None))   # whole array / a view / nothing
+    for k, r in enumerate(kept):
+        if r is not None:
+            assert np.array_equal(r, want[k] if k % 3 == 0 else want[k][5:9]), ("a kept result was overwritten", k)
+    report["landing_buffer_rotation"] = "ok"
+
     # ---- event sharding, anchor-tensor engine --------------------------------------------------------------------
     bounds = bdist.shard_bounds(len(d), world, align=512)
     pts = table[:23]
