@@ -124,6 +124,8 @@ SIGNATURES = {
     "bi_peer_exchange_words": (_i64, [_i32, _i64]),
     "bi_peer_exchange": (ctypes.c_int, [_c_void_p, _i64, _i64, _c_void_p, _i32, _i32, _i32, _c_void_p, _c_void_p,
                                         _c_void_p, _c_void_p]),
+    "bi_peer_gather_status": (ctypes.c_int, [_c_void_p, _i64, _i64, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p,
+                                             _c_void_p]),
     "bi_peer_broadcast": (ctypes.c_int, [_c_void_p, _i64, _c_void_p, _i32, _i64, _c_void_p]),
     "bi_bench_fp64_fma": (ctypes.c_int, [_i64, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "bi_bench_fp64_mma": (ctypes.c_int, [_i64, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),

@@ -77,7 +77,7 @@ template <int MODE>      // 0: gather -> out[world, n];  1: rank-ordered sum -> 
 __global__ void __launch_bounds__(256)
 k_peer_exchange(const double* __restrict__ src, int64_t n_src, int64_t n, const __grid_constant__ BiPeers peers,
                 int world, int rank, const double* __restrict__ musum, const int32_t* __restrict__ status,
-                double* __restrict__ out) {
+                double* __restrict__ out, int32_t* __restrict__ status_out) {
     double* mine = peers.p[rank];
     unsigned long long* flags = reinterpret_cast<unsigned long long*>(mine + 2 * (int64_t)world * n);
     unsigned long long* local = flags + world;
@@ -94,6 +94,10 @@ k_peer_exchange(const double* __restrict__ src, int64_t n_src, int64_t n, const 
         const double v = src[i];
         for (int r = 0; r < world; ++r) peers.p[(rank + r) % world][slot + (int64_t)rank * n + i] = v;
     }
+    // (gather mode: this rank's point status travels to the caller's buffer -- pinned host memory -- in the same launch,
+    // while the peers' rows are still on their way)
+    if (MODE == 0 && status_out != nullptr)
+        for (int64_t i = tid; i < n_src; i += nthr) status_out[i] = status[i];
     __threadfence_system();
     __syncthreads();
     // 2. the last CTA to arrive publishes: flag[rank] = epoch on every rank
@@ -122,7 +126,15 @@ k_peer_exchange(const double* __restrict__ src, int64_t n_src, int64_t n, const 
     // 4. epilogue on the delivered rows (L1 bypassed: they were written by other devices)
     if (MODE == 0) {
         const int64_t total = (int64_t)world * n;
-        for (int64_t i = tid; i < total; i += nthr) out[i] = __ldcg(mine + slot + i);
+        const double* rows = mine + slot;
+        if ((((uintptr_t)rows | (uintptr_t)out) & 15) == 0) {         // 16-byte stores towards (pinned host) memory
+            const int64_t pairs = total >> 1;
+            for (int64_t i = tid; i < pairs; i += nthr)
+                reinterpret_cast<double2*>(out)[i] = __ldcg(reinterpret_cast<const double2*>(rows) + i);
+            if ((total & 1) && tid == 0) out[total - 1] = __ldcg(rows + total - 1);
+        } else {
+            for (int64_t i = tid; i < total; i += nthr) out[i] = __ldcg(rows + i);
+        }
     } else {
         for (int64_t i = tid; i < n; i += nthr) {
             double acc = __ldcg(mine + slot + i);                        // ((r0 + r1) + r2) + ...: fixed rank order, so
@@ -151,9 +163,9 @@ extern "C" int64_t bi_peer_exchange_words(int32_t world, int64_t n) {
     return 2 * (int64_t)world * (n > 0 ? n : 1) + world + 4;
 }
 
-extern "C" int bi_peer_exchange(const double* src_dev, int64_t n_src, int64_t n, const uint64_t* peer_ptrs_host,
-                                int32_t world, int32_t rank, int32_t mode, const double* musum_dev,
-                                const int32_t* status_dev, double* out_dev, void* stream) {
+static int bi_peer_exchange_impl(const double* src_dev, int64_t n_src, int64_t n, const uint64_t* peer_ptrs_host,
+                                 int32_t world, int32_t rank, int32_t mode, const double* musum_dev,
+                                 const int32_t* status_dev, double* out_dev, int32_t* status_out, void* stream) {
     BI_REQUIRE(world >= 1 && world <= BI_MAX_PEERS, "world=%d outside [1,%d]", world, BI_MAX_PEERS);
     BI_REQUIRE(rank >= 0 && rank < world, "rank=%d outside [0,%d)", rank, world);
     BI_REQUIRE(n >= 1 && n_src >= 0 && n_src <= n, "bi_peer_exchange: need 0 <= n_src <= n, n >= 1");
@@ -166,14 +178,32 @@ extern "C" int bi_peer_exchange(const double* src_dev, int64_t n_src, int64_t n,
         peers.p[r] = reinterpret_cast<double*>(peer_ptrs_host[r]);
     }
     // enough CTAs to keep a few thousand stores in flight; all of them must be able to be resident while they wait
-    int64_t blocks = ((int64_t)world * n + 2047) / 2048;
+    int64_t blocks = ((int64_t)world * n + 1023) / 1024;
     if (blocks < 1) blocks = 1;
-    if (blocks > 64) blocks = 64;
+    if (blocks > 128) blocks = 128;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0)
-        k_peer_exchange<0><<<(unsigned)blocks, 256, 0, st>>>(src_dev, n_src, n, peers, world, rank, musum_dev, status_dev, out_dev);
+        k_peer_exchange<0><<<(unsigned)blocks, 256, 0, st>>>(src_dev, n_src, n, peers, world, rank, musum_dev, status_dev, out_dev,
+                                                             status_out);
     else
-        k_peer_exchange<1><<<(unsigned)blocks, 256, 0, st>>>(src_dev, n_src, n, peers, world, rank, musum_dev, status_dev, out_dev);
+        k_peer_exchange<1><<<(unsigned)blocks, 256, 0, st>>>(src_dev, n_src, n, peers, world, rank, musum_dev, status_dev, out_dev,
+                                                             nullptr);
     BI_LAUNCH_CHECK();
     return BI_OK;
+}
+
+extern "C" int bi_peer_exchange(const double* src_dev, int64_t n_src, int64_t n, const uint64_t* peer_ptrs_host,
+                                int32_t world, int32_t rank, int32_t mode, const double* musum_dev,
+                                const int32_t* status_dev, double* out_dev, void* stream) {
+    return bi_peer_exchange_impl(src_dev, n_src, n, peer_ptrs_host, world, rank, mode, musum_dev, status_dev, out_dev, nullptr,
+                                 stream);
+}
+
+// gather (mode 0) that also delivers this rank's n_src point status words to status_out (e.g. pinned host memory)
+extern "C" int bi_peer_gather_status(const double* src_dev, int64_t n_src, int64_t n, const uint64_t* peer_ptrs_host,
+                                     int32_t world, int32_t rank, const int32_t* status_dev, int32_t* status_out,
+                                     double* out_dev, void* stream) {
+    BI_REQUIRE(status_dev && status_out, "bi_peer_gather_status: NULL status pointer");
+    return bi_peer_exchange_impl(src_dev, n_src, n, peer_ptrs_host, world, rank, 0, nullptr, status_dev, out_dev, status_out,
+                                 stream);
 }

@@ -140,21 +140,31 @@ class PeerGather(object):
         if local.numel() > self.n or (self.fallback is not None and local.numel() != self.n):
             raise ValueError("PeerGather was built for %d values per rank, got %d" % (self.n, local.numel()))
 
-    def gather(self, local, out=None):
+    def gather(self, local, out=None, status=None, status_out=None):
         """local: device tensor of <= n float64 -> tensor [world, n] holding every rank's values (rows of ranks that
         passed fewer than n values keep stale tails).  out: where the kernel writes the rows (default: a device buffer);
-        a pinned host tensor of world * n float64 makes the kernel deliver them to the host itself, without a copy."""
+        a pinned host tensor of world * n float64 makes the kernel deliver them to the host itself, without a copy.
+        status / status_out (int32 tensors of len(local)): the same launch copies this rank's point status words, e.g. to
+        pinned host memory."""
         self._check(local)
         if self.fallback is not None:
             _dist().all_gather_into_tensor(self.out, local.contiguous(), group=self.group)
+            if status_out is not None:
+                status_out.copy_(status, non_blocking=True)
             if out is not None:
                 out.copy_(self.out, non_blocking=True)
                 return out.view(self.world, self.n)
             return self.out.view(self.world, self.n)
         dst = self.out if out is None else out
-        _cabi.check(self.lib.bi_peer_exchange(_cabi.dev_ptr(local), local.numel(), self.n, _cabi.host_ptr(self.peer_ptrs),
-                                              self.world, self.rank, 0, None, None, _cabi.dev_ptr(dst), self._stream()),
-                    "bi_peer_exchange")
+        if status_out is not None:
+            _cabi.check(self.lib.bi_peer_gather_status(_cabi.dev_ptr(local), local.numel(), self.n,
+                                                       _cabi.host_ptr(self.peer_ptrs), self.world, self.rank,
+                                                       _cabi.dev_ptr(status), _cabi.dev_ptr(status_out), _cabi.dev_ptr(dst),
+                                                       self._stream()), "bi_peer_gather_status")
+        else:
+            _cabi.check(self.lib.bi_peer_exchange(_cabi.dev_ptr(local), local.numel(), self.n, _cabi.host_ptr(self.peer_ptrs),
+                                                  self.world, self.rank, 0, None, None, _cabi.dev_ptr(dst), self._stream()),
+                        "bi_peer_exchange")
         self.launches += 1
         return dst.view(self.world, self.n)
 
@@ -216,11 +226,15 @@ class PointShardedLikelihood(object):
         self.ll = ll
         self.group = group
         self._gathers = {}
+        self._splits = {}
+        self._nccl = None
 
     def _device_gather_engine(self, n_rows):
         """The ll's fused unbinned engine with a PeerGather for n_rows rows per rank, or None (binned likelihoods,
         gloo, engines without the fused path): then the results are gathered on the host."""
-        if _dist().get_backend(self.group) != 'nccl':
+        if self._nccl is None:
+            self._nccl = _dist().get_backend(self.group) == 'nccl'
+        if not self._nccl:
             return None
         engine = getattr(self.ll, '_engine', None)
         if engine is None or not hasattr(engine, 'evaluate_fused') or not engine.uses_mma():
@@ -231,14 +245,22 @@ class PointShardedLikelihood(object):
         engine.peer_gather, engine.peer_mode = pg, 'gather'
         return engine
 
+    def _split(self, n_points):
+        """(lo, hi, counts, n_rows) of this rank for a table of n_points rows (cached per table length)."""
+        split = self._splits.get(n_points)
+        if split is None:
+            dist = _dist()
+            rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+            bounds = shard_bounds(n_points, world)
+            counts = [b - a for a, b in bounds]
+            if len(self._splits) > 64:
+                self._splits.clear()
+            split = self._splits[n_points] = (bounds[rank][0], bounds[rank][1], counts, max(counts) if counts else 0)
+        return split
+
     def batch(self, params, names=None, livetime_days=None):
-        dist = _dist()
-        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
         params = np.asarray(params, dtype=np.float64)
-        bounds = shard_bounds(len(params), world)
-        lo, hi = bounds[rank]
-        counts = [b - a for a, b in bounds]
-        n_rows = max(counts) if counts else 0
+        lo, hi, counts, n_rows = self._split(len(params))
         engine = self._device_gather_engine(n_rows) if n_rows else None
         if engine is None:
             local = self.ll.batch(params[lo:hi], names, livetime_days=livetime_days) if hi > lo else np.zeros(0)

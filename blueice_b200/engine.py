@@ -609,11 +609,13 @@ class UnbinnedEngine(_EngineBase):
                 # event sharding: -musum + (rank-ordered sum of the shards' log sums), -inf where the point is unphysical
                 pg.reduce(st["out_f"][P:2 * P], st["out_f"][2 * P:3 * P], st["out_i"], out=self._pin_x(st, P, slot))
             else:
-                pg.gather(st["out_f"][:P], out=self._pin_x(st, pg.world * pg.n, slot))    # point sharding: all ranks' logl rows
                 if n_f == P and pg.n == P and pg.fallback is None:
-                    # this rank's own logl rows are row `rank` of the gathered block: no separate copy node for them
-                    st["pin_i"].copy_(st["out_i"], non_blocking=True)
+                    # point sharding: all ranks' logl rows; this rank's own rows are row `rank` of the gathered block and
+                    # its status words travel in the same launch -- the sequence ends without a copy node
+                    pg.gather(st["out_f"][:P], out=self._pin_x(st, pg.world * pg.n, slot), status=st["out_i"],
+                              status_out=st["pin_i"])
                     return
+                pg.gather(st["out_f"][:P], out=self._pin_x(st, pg.world * pg.n, slot))
         st["pin_f"][:n_f].copy_(st["out_f"][:n_f], non_blocking=True)
         st["pin_i"].copy_(st["out_i"], non_blocking=True)
 

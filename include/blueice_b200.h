@@ -580,12 +580,18 @@ int bi_binned_pmfs(const double* pmf_anchor_dev, const double* n_model_anchor_de
  * to the epoch if a peer did not arrive within 20 s).  It must be ZEROED, followed by one cross-rank barrier, before
  * the first exchange.  Results a caller reads out of out_dev are stream-ordered after the launch.
  *
+ * bi_peer_gather_status: bi_peer_exchange in mode 0 that also copies this rank's n_src point status words
+ * (status_dev -> status_out, e.g. pinned host memory) in the same launch, so that a sharded evaluation ends without a copy.
+ *
  * bi_peer_broadcast: step (1) alone, peer[r][dst_offset + i] = src_dev[i]; the caller provides the barrier.
  */
 int64_t bi_peer_exchange_words(int32_t world, int64_t n);
 int bi_peer_exchange(const double* src_dev, int64_t n_src, int64_t n, const uint64_t* peer_ptrs_host,
                      int32_t world, int32_t rank, int32_t mode, const double* musum_dev,
                      const int32_t* status_dev, double* out_dev, void* stream);
+int bi_peer_gather_status(const double* src_dev, int64_t n_src, int64_t n, const uint64_t* peer_ptrs_host,
+                          int32_t world, int32_t rank, const int32_t* status_dev, int32_t* status_out,
+                          double* out_dev, void* stream);
 int bi_peer_broadcast(const double* src_dev, int64_t n, const uint64_t* peer_ptrs_host, int32_t world,
                       int64_t dst_offset, void* stream);
 
