@@ -1316,6 +1316,8 @@ class TemplateUnbinnedEngine(_EngineBase):
         self.ev_bin = None
         self.peer_gather = None       # distributed.PeerGather (sharded evaluations), see UnbinnedEngine
         self.peer_mode = 'gather'
+        self._x_slots = {}            # n -> [(pinned tensor, its ndarray)]: rotating landing buffers of gathered results
+        self.last_gathered_owned = True
         self.last_gathered = None
         self.last_total = None
         self._graphs = {}             # CUDA graphs of repeated evaluations, per (schedule, batch shape)
@@ -1662,7 +1664,25 @@ class TemplateUnbinnedEngine(_EngineBase):
         st_pin = self.ws.get("d2h_status", P, torch.int32, pinned=True)
         pg, mode = self.peer_gather, self.peer_mode
         n_x = 0 if pg is None else (P if mode == 'sum' else pg.world * pg.n)
-        g_pin = self.ws.get("d2h_gather", n_x, torch.float64, pinned=True) if pg is not None else None
+        g_pin, x_slot = None, 0
+        self.last_gathered = self.last_total = None                      # (releases the views of the previous call)
+        if pg is not None:
+            # landing buffer of the exchange result: a gather rotates over pinned buffers that are handed to the caller
+            # without a host copy (reused only when no array or view of an earlier result is alive, see
+            # UnbinnedEngine.batch_runner); sums, permuted results and the NCCL fallback copy out of a scratch buffer
+            if mode != 'sum' and pg.fallback is None and order is None:
+                pool = self._x_slots.setdefault(n_x, [])
+                for k, (t, a) in enumerate(pool):
+                    if sys.getrefcount(a) == 3:                          # the pool, the loop variable, this call
+                        g_pin, x_slot = t, k + 1
+                        break
+                else:
+                    if len(pool) < _X_SLOTS:
+                        t = torch.empty(max(n_x, 1), dtype=torch.float64, pin_memory=True)
+                        pool.append((t, t.numpy()))
+                        g_pin, x_slot = t, len(pool)
+            if g_pin is None:
+                g_pin = self.ws.get("d2h_gather", n_x, torch.float64, pinned=True)
         state = {}
 
         # small batches: K1 reads the staged points from pinned host memory and (unsharded) the finalize kernel writes
@@ -1708,7 +1728,7 @@ class TemplateUnbinnedEngine(_EngineBase):
         graph = None
         use_graphs = _E2E_GRAPHS and (pg is None or pg.fallback is None)
         if use_graphs:
-            gkey = (id(sched), P, sizes, return_parts, None if pg is None else (id(pg), mode))
+            gkey = (id(sched), P, sizes, return_parts, None if pg is None else (id(pg), mode), x_slot)
             entry = self._graphs.get(gkey)
             if entry is None:
                 if len(self._graphs) >= 8:
@@ -1757,15 +1777,19 @@ class TemplateUnbinnedEngine(_EngineBase):
             inv = np.empty(P, dtype=np.int64)
             inv[order] = np.arange(P)
             ll, ls = ll[inv], ls[inv] if return_parts else ls
-        self.last_gathered = self.last_total = None
+        self.last_gathered_owned = True
         if pg is not None and mode == 'sum':
             total = g_pin.numpy()[:P].copy()                                # rank-ordered sum of the log sums, pair order
             total = total if inv is None else total[inv]
             if return_parts:                                                # (the mu sums arrive with the parts only)
                 self.last_total = np.where(status != 0, -np.inf, -res[2 * P:3 * P] + total)
         elif pg is not None:
-            gathered = g_pin.numpy().reshape(pg.world, -1).copy()
-            self.last_gathered = gathered if inv is None else np.concatenate([gathered[:, :P][:, inv], gathered[:, P:]], axis=1)
+            if x_slot:
+                self.last_gathered = self._x_slots[n_x][x_slot - 1][1][:n_x].reshape(pg.world, -1)      # handed over, no copy
+            else:
+                gathered = g_pin.numpy().reshape(pg.world, -1).copy()
+                self.last_gathered = gathered if inv is None else \
+                    np.concatenate([gathered[:, :P][:, inv], gathered[:, P:]], axis=1)
         if return_parts:
             return ls, res[2 * P:], status
         return (ll, status) if return_status else ll
