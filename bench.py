@@ -11,7 +11,7 @@ hot path over the whole scan.
             the launching stream) = K1 point set-up + K2 fused morph/mixture/log/reduce + finalize.
   e2e       ll.batch(host ndarray) -> host ndarray through the public API: planning, H2D of points and
             schedule from pinned memory, the same kernels, D2H of logL + status, stream sync.
-  roofline  dominant kernel (grouped K2) timed alone; FP64-pipe bound for a shared-dataset scan
+  roofline  dominant kernel (K2) timed alone; FP64-pipe bound for a shared-dataset scan
             (SURVEY.md section 8d), peak = FP64 FMA micro-benchmark measured in this run; the same
             kernel's algorithmic HBM bytes and the streaming (P=1, HBM-bound) regime are reported too.
   cpu_baseline  the oracle pipeline (same SciPy calls as the reference) on a bounded sample, 1 core.
@@ -983,7 +983,7 @@ def run_own_arm(args):
         strong = {"points_total": P, "e2e_ms": float(t[0]) * 1e3 / args.steps, "device_span_ms": float(t[1]) * 1e3 / args.steps,
                   "point_events_per_s_e2e": P * n_events * args.steps / float(t[0])}
 
-    # ---- dominant kernel alone (grouped K2), for the roofline --------------------------------------
+    # ---- dominant kernel alone (K2), for the roofline --------------------------------------
     S, C = eng.n_sources, eng.grid.n_corners
     stream = eng._stream()
 
@@ -999,20 +999,16 @@ def run_own_arm(args):
             e.mma_k2(v)
         return plan_fn, k2_fn, v
 
-    def legacy_k2(e, pl, pl_dev, setup, part):
-        common = (_cabi.dev_ptr(setup["corner"]), _cabi.dev_ptr(setup["weight"]), _cabi.dev_ptr(setup["mus"]),
-                  _cabi.dev_ptr(setup["status"]), e.outlier_likelihood, _cabi.dev_ptr(part), e._stream())
+    def stream_k2(e, pl, pl_dev, setup, part):
         if len(pl.stream_points):
             _cabi.check(e.lib.bi_unbinned_partials_stream(
                 _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(pl_dev[0]),
-                len(pl.stream_points), *common), "bi_unbinned_partials_stream")
-        if len(pl.work):
-            _cabi.check(e.lib.bi_unbinned_partials_grouped(
-                _cabi.dev_ptr(e.ps_anchor), e.ld, e.n_events, S, C, _cabi.dev_ptr(pl_dev[1]),
-                _cabi.dev_ptr(pl_dev[2]), len(pl.work), *common), "bi_unbinned_partials_grouped")
+                len(pl.stream_points), _cabi.dev_ptr(setup["corner"]), _cabi.dev_ptr(setup["weight"]),
+                _cabi.dev_ptr(setup["mus"]), _cabi.dev_ptr(setup["status"]), e.outlier_likelihood,
+                _cabi.dev_ptr(part), e._stream()), "bi_unbinned_partials_stream")
 
     if plan.kernel == 'mma':
-        plan_fn, grouped_only, views = mma_stage_fns(eng, P, zs_d, mult_d)
+        plan_fn, k2_only, views = mma_stage_fns(eng, P, zs_d, mult_d)
     else:
         o = eng._setup(P, zs_d, mult_d, None, None)
         partial = eng.ws.get("partial", P * eng.n_super, torch.float64)
@@ -1020,28 +1016,28 @@ def run_own_arm(args):
         def plan_fn():
             pass
 
-        def grouped_only():
-            legacy_k2(eng, plan, plan_dev, o, partial)
+        def k2_only():
+            stream_k2(eng, plan, plan_dev, o, partial)
 
     k2_ms = []
-    n_grouped = len(plan.group_points) if plan.kernel != 'mma' else P
+    n_in_kernel = len(plan.stream_points) if plan.kernel != 'mma' else P
     sched = None
-    if len(plan.work) or plan.kernel == 'mma':
+    if n_in_kernel:
         for _ in range(3):
             plan_fn()
-            grouped_only()
+            k2_only()
         if plan.kernel == 'mma':
             torch.cuda.synchronize()
             hdr = views["header"][:8].cpu().numpy()
             sched = {"point_groups": int(hdr[0]), "superblock_ranges": int(hdr[1]), "superblocks_per_range": int(hdr[2]),
                      "work_units": int(hdr[3]), "evaluable_points": int(hdr[5])}
-            n_grouped = int(hdr[5])
+            n_in_kernel = int(hdr[5])
         for _ in range(max(args.steps, 10)):
             flush_l2()
             plan_fn()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            grouped_only()
+            k2_only()
             b.record()
             torch.cuda.synchronize()
             k2_ms.append(a.elapsed_time(b))
@@ -1091,7 +1087,7 @@ def run_own_arm(args):
                 pass
 
             def k2_1():
-                legacy_k2(big, plan1, plan1_dev, o1, part1)
+                stream_k2(big, plan1, plan1_dev, o1, part1)
 
         def stream_only():
             k2_1()
@@ -1149,14 +1145,14 @@ def run_own_arm(args):
         roofline = None
         if k2_ms:
             k2 = float(np.mean(k2_ms)) * 1e-3
-            flops_alg = float(n_grouped) * n_events * 2.0 * C * S
+            flops_alg = float(n_in_kernel) * n_events * 2.0 * C * S
             bytes_alg = 8.0 * S * n_events * G
             kname = ("k_unbinned_mma<K4=%d> (DMMA.8x8x4 contraction over K=C*S=%d, per-warp TMA ring)"
                      % ((C * S + 3) // 4, C * S) if plan.kernel == 'mma'
-                     else "k_unbinned_grouped<%d> (threads=points, TMA-staged event tiles)" % C)
+                     else "k_unbinned_stream<%d> (one pass over the anchor tensor per point)" % C)
             roofline = {"kernel": kname, "bound": "tensor", "pipe": "fp64 (DMMA.8x8x4 = the FP64 tensor instruction; it shares one pipe with DFMA)", "achieved": flops_alg / k2 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": flops_alg / k2 / 1e12 / fp64_peak,
-                        "traffic": ncu_traffic("scan" if plan.kernel == 'mma' else "legacy_scan"),
+                        "traffic": ncu_traffic("scan") if plan.kernel == 'mma' else None,
                         "peak_source": "max(bi_bench_fp64_fma, bi_bench_fp64_mma) measured in this run: DFMA and DMMA "
                                        "share one pipe on sm_100a (MEASURED_PEAKS.json holds no FP64 figure)",
                         "flops_alg_per_point_event": 2 * C * S,
@@ -1164,7 +1160,7 @@ def run_own_arm(args):
                                           "one FP64 multiply per point-event (product tree, one log per 512 events) "
                                           "which is NOT counted, so frac <= 2CS/(2CS+2) = %.3f" % (C * S / (C * S + 1.0)), "ms": k2 * 1e3,
                         "share_of_step": k2 * 1e3 / (total_ms / args.steps),
-                        "points_in_kernel": int(n_grouped),
+                        "points_in_kernel": int(n_in_kernel),
                         "hbm": {"bytes_alg": bytes_alg, "achieved_gbs": bytes_alg / k2 / 1e9,
                                 "peak_gbs": peaks["hbm_gbs"], "frac": bytes_alg / k2 / 1e9 / peaks["hbm_gbs"],
                                 "note": "shared-dataset scan: the anchor tensor is read once per launch, "
@@ -1185,8 +1181,7 @@ def run_own_arm(args):
                 "clocks": clocks, "fp64_fma_peak_tflops": fp64_peak,
                 "set_data_s": set_data_s, "model_build_s": build_s,
                 "plan": sched if sched is not None else
-                {"grouped_points": int(n_grouped), "stream_points": int(len(plan.stream_points)),
-                 "work_items": int(len(plan.work))},
+                {"stream_points": int(len(plan.stream_points))},
                 "step_ms_min_max": [float(np.min(step_ms)), float(np.max(step_ms))],
                 "gather_transport": None if world == 1 else ("nvlink p2p stores (symmetric memory)" if peer_gather.fallback
                                                               is None else "nccl all_gather (%s)" % peer_gather.fallback),
@@ -1209,7 +1204,7 @@ def main():
     ap.add_argument("--skip-stream", action="store_true")
     ap.add_argument("--stream-kernel", default=None, choices=[None, "mma", "stream"],
                     help="kernel for the P=1 HBM-bound measurement (default: the engine's own choice)")
-    ap.add_argument("--kernel", default=None, choices=[None, "mma", "grouped", "stream"],
+    ap.add_argument("--kernel", default=None, choices=[None, "mma", "stream"],
                     help="force a K2 kernel for the scan (default: the engine's own choice)")
     ap.add_argument("--gather-wait", action="store_true",
                     help="N > 1: wait for all ranks' results inside every step (a barrier per step) instead of once at the end")

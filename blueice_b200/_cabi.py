@@ -28,9 +28,6 @@ SIGNATURES = {
     "bi_unbinned_partials_stream": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _i64,
                                                    _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
                                                    _c_void_p, _c_void_p]),
-    "bi_unbinned_partials_grouped": (ctypes.c_int, [_c_void_p, _i64, _i64, _i32, _i32, _c_void_p, _c_void_p,
-                                                    _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _f64,
-                                                    _c_void_p, _c_void_p]),
     "bi_plan_max_cells": (_i64, []),
     "bi_unbinned_plan": (ctypes.c_int, [_i32, _c_void_p, _i64, _c_void_p, _c_void_p, _i32, _i64, _i32, _i32,
                                         _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
@@ -139,9 +136,6 @@ MAX_SPACE_DIMS = 4
 MAX_AXIS_POINTS = 256
 EVENT_BLOCK = 32
 SUPERBLOCK = 512
-GROUP_POINTS = 256
-GROUP_MAX_SOURCES = 8
-GROUP_MAX_CORNERS = 16
 STREAM_MAX_CORNERS = 32
 MMA_MAX_TERMS = 128
 PLAN_MAX_CELLS = 16384

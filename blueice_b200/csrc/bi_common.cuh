@@ -1,7 +1,7 @@
 // blueice_b200 -- shared device/host helpers for the sm_100a likelihood kernels.
 //
 // Everything that defines the *canonical arithmetic* of the hot path lives here so that the
-// streaming kernel (lanes = events), the grouped kernel (threads = points) and the finalize kernel
+// streaming kernel (lanes = events), the DMMA kernel (tiles of points x events) and the finalize kernel
 // produce bit-identical numbers for the same parameter point.
 #pragma once
 

@@ -6,13 +6,10 @@
 //     p_i      = nansum_s mu_s * ps[s,i];  p_i <- outlier_likelihood where !(p_i > 0)
 //     partial  = sum_i log p_i                            (per 512-event superblock, canonical order)
 //
-// Two kernels produce BIT-IDENTICAL per-superblock partials for the same point:
-//   k_unbinned_stream  : lanes = events (16-byte loads straight from HBM/L2), one warp per
-//                        (point, superblock).  HBM-bound when few points share the data.
-//   k_unbinned_grouped : threads = points that share one hypercube cell; the cell's C*S slabs of an
-//                        event tile are staged in shared memory by TMA bulk copies
-//                        (cp.async.bulk + mbarrier, multi-stage) and broadcast to all threads.
-//                        FP64-pipe-bound for profile scans / toy batches.
+// k_unbinned_stream: lanes = events (16-byte loads straight from HBM/L2), one warp per (point, superblock).
+// HBM-bound when few points share the data.  It is the general kernel (any number of sources, up to 32 corners);
+// batches within the limits of the DMMA kernel (bi_unbinned_mma.cuh) run there and give BIT-IDENTICAL
+// per-superblock partials for the same point.
 //
 // Canonical arithmetic.  For each block of 32 consecutive events:
 //   quad k (4 events) = fl(fl(p0*p1)*fl(p2*p3)) = m_k * 2^e_k (unbounded-exponent semantics);
@@ -322,55 +319,6 @@ extern "C" int bi_unbinned_partials_stream(const double* ps_anchor_dev, int64_t 
         BI_STREAM_CASE(32)
     }
 #undef BI_STREAM_CASE
-    bi_set_error("unsupported n_corners=%d", n_corners);
-    return BI_ERR_UNSUPPORTED;
-}
-
-// per-C translation units (bi_grouped_c*.cu) instantiate k_unbinned_grouped<C, S> for S = 1..8
-#define BI_DECLARE_GROUPED(CC)                                                                                    \
-    int bi_grouped_launch_c##CC(int S, const double* A, int64_t ld, int64_t N, const int32_t* group_points,       \
-                                const int32_t* work, int64_t n_work, int64_t n_super, const int32_t* corner,      \
-                                const double* weight, const double* mus, double outlier, double* partial,         \
-                                cudaStream_t st);
-BI_DECLARE_GROUPED(1)
-BI_DECLARE_GROUPED(2)
-BI_DECLARE_GROUPED(4)
-BI_DECLARE_GROUPED(8)
-BI_DECLARE_GROUPED(16)
-#undef BI_DECLARE_GROUPED
-
-extern "C" int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
-                                            int32_t n_sources, int32_t n_corners,
-                                            const int32_t* group_points_dev, const int32_t* work_dev, int64_t n_work,
-                                            const int32_t* corner_dev, const double* weight_dev,
-                                            const double* mus_dev, const int32_t* status_dev,
-                                            double outlier_likelihood, double* partial_dev, void* stream) {
-    (void)status_dev;
-    int rc = bi_check_tensor(ps_anchor_dev, ld_events, n_events, n_sources, n_corners);
-    if (rc != BI_OK) return rc;
-    BI_REQUIRE(n_work >= 0, "n_work < 0");
-    const int64_t n_super = bi_num_superblocks(n_events);
-    if (n_work == 0 || n_super == 0) return BI_OK;
-    BI_REQUIRE(n_sources <= BI_GROUP_MAX_SOURCES, "grouped kernel supports at most %d sources (got %d)", BI_GROUP_MAX_SOURCES, n_sources);
-    BI_REQUIRE(n_corners <= 16, "grouped kernel supports at most 16 corners (got %d)", n_corners);
-    BI_REQUIRE(group_points_dev && work_dev && corner_dev && weight_dev && mus_dev && partial_dev,
-               "bi_unbinned_partials_grouped: NULL pointer");
-    BI_REQUIRE(((uintptr_t)work_dev & 15) == 0, "work_dev must be 16-byte aligned");
-    BI_REQUIRE(ld_events % 2 == 0, "ld_events must be even");
-    cudaStream_t st = (cudaStream_t)stream;
-#define BI_GROUP_CASE(CC)                                                                                      \
-    case CC:                                                                                                   \
-        return bi_grouped_launch_c##CC(n_sources, ps_anchor_dev, ld_events, n_events, group_points_dev, work_dev, \
-                                       n_work, n_super, corner_dev, weight_dev, mus_dev, outlier_likelihood,    \
-                                       partial_dev, st);
-    switch (n_corners) {
-        BI_GROUP_CASE(1)
-        BI_GROUP_CASE(2)
-        BI_GROUP_CASE(4)
-        BI_GROUP_CASE(8)
-        BI_GROUP_CASE(16)
-    }
-#undef BI_GROUP_CASE
     bi_set_error("unsupported n_corners=%d", n_corners);
     return BI_ERR_UNSUPPORTED;
 }

@@ -22,8 +22,6 @@ import numpy as np
 from . import _cabi
 
 _LD_ALIGN = 64
-_GROUP_MIN_POINTS = 16          # cells with at least this many points use the grouped kernel
-_GROUP_TARGET_ITEMS = 148 * 8   # aim for a few CTAs per SM
 
 
 def _torch():
@@ -111,71 +109,19 @@ class _Workspace(object):
 class PointPlan(object):
     """Host-side schedule of a batch: which points go to which kernel (results do not depend on it)."""
 
-    def __init__(self, n_points, in_range, stream_points, group_points, work, kernel='vector'):
-        self.kernel = kernel                    # 'mma': work units of the DMMA kernel; 'vector': stream + grouped
-        self.n_points = n_points
-        self.in_range = in_range
+    def __init__(self, n_points, in_range, stream_points, kernel='stream'):
+        self.kernel = kernel                    # 'mma': work units of the DMMA kernel (scheduled on the device);
+        self.n_points = n_points                # 'stream': the per-point streaming kernel (more contraction terms or
+        self.in_range = in_range                # hypercube cells than the DMMA path takes; cross-check in the tests)
         self.stream_points = stream_points      # int32 [n_stream]
-        self.group_points = group_points        # int32 [n_grouped]
-        self.work = work                        # int32 [n_work, 4]
 
 
-def plan_points(grid, zs, n_sources, n_super, force_kernel=None):
-    """Host-side schedule of a batch (pure function; results never depend on it).
-
-    Points whose hypercube cell is shared by at least _GROUP_MIN_POINTS points of the batch go to the
-    grouped kernel in chunks of <= GROUP_POINTS points x ranges of superblocks; all other in-range
-    points go to the streaming kernel; out-of-range points get no work (their result is -inf)."""
+def plan_points(grid, zs):
+    """Host-side schedule of the streaming path (pure function; results never depend on it): every in-range point is
+    one streaming task list entry; out-of-range points get no work (their result is -inf)."""
     P = len(zs)
     in_range = grid.in_range(zs) if grid.n_dims else np.ones(P, dtype=bool)
-    idx = np.nonzero(in_range)[0]
-    can_group = (n_sources <= _cabi.GROUP_MAX_SOURCES and grid.n_corners <= _cabi.GROUP_MAX_CORNERS
-                 and n_super > 0 and force_kernel != 'stream')
-    stream_pts = idx
-    group_pts = np.zeros(0, dtype=np.int64)
-    work = np.zeros((0, 4), dtype=np.int32)
-    min_pts = 1 if force_kernel == 'grouped' else _GROUP_MIN_POINTS
-    if can_group and len(idx) >= min_pts:
-        if grid.n_dims:
-            cells = grid.cell_ids(np.asarray(zs, dtype=np.float64).reshape(P, grid.n_dims)[idx])
-        else:
-            cells = np.zeros(len(idx), dtype=np.int64)
-        order = np.argsort(cells, kind='stable')
-        sorted_cells = cells[order]
-        sorted_idx = idx[order]
-        starts = np.flatnonzero(np.r_[True, sorted_cells[1:] != sorted_cells[:-1]])
-        ends = np.r_[starts[1:], len(sorted_cells)]
-        big = (ends - starts) >= min_pts
-        keep = np.zeros(len(sorted_idx), dtype=bool)
-        chunks = []
-        pos = 0
-        for s0, e0 in zip(starts[big], ends[big]):
-            keep[s0:e0] = True
-            n = e0 - s0
-            for c0 in range(0, n, _cabi.GROUP_POINTS):
-                chunks.append((pos + c0, min(_cabi.GROUP_POINTS, n - c0)))
-            pos += n
-        group_pts = sorted_idx[keep]
-        stream_pts = np.sort(sorted_idx[~keep])
-        if chunks:
-            n_ranges = int(np.clip(_GROUP_TARGET_ITEMS // len(chunks), 1, n_super))
-            sb_per = -(-n_super // n_ranges)
-            sb_begin = np.arange(0, n_super, sb_per, dtype=np.int64)
-            sb_end = np.minimum(sb_begin + sb_per, n_super)
-            ch = np.asarray(chunks, dtype=np.int64)
-            # heaviest chunks first (the block scheduler hands out CTAs in order, so the light ones fill
-            # the tail); within equal weight, event-range-major so co-resident CTAs share tiles in L2
-            weight_class = -np.minimum((ch[:, 1] + 63) // 64, 4)
-            order = np.lexsort((np.tile(np.arange(len(ch)), len(sb_begin)),
-                                np.repeat(np.arange(len(sb_begin)), len(ch)),
-                                np.tile(weight_class, len(sb_begin))))
-            work = np.empty((len(ch) * len(sb_begin), 4), dtype=np.int32)
-            work[:, 0] = np.tile(ch[:, 0], len(sb_begin))
-            work[:, 1] = np.tile(ch[:, 1], len(sb_begin))
-            work[:, 2] = np.repeat(sb_begin, len(ch))
-            work[:, 3] = np.repeat(sb_end, len(ch))
-            work = np.ascontiguousarray(work[order])
-    return PointPlan(P, in_range, stream_pts.astype(np.int32), group_pts.astype(np.int32), work)
+    return PointPlan(P, in_range, np.nonzero(in_range)[0].astype(np.int32))
 
 
 # up to ~32 (group, range) pairs per resident warp and full units + one remainder per cell (measured optimum);
@@ -289,7 +235,7 @@ class UnbinnedEngine(_EngineBase):
         self.n_events = 0
         self.ld = 0
         self.ps_anchor = None
-        self.force_kernel = None      # None (auto) | 'stream' | 'grouped'  (tests / bench)
+        self.force_kernel = None      # None (auto) | 'mma' | 'stream'  (tests / bench)
         self._fused_cache = {}        # batch size -> staging buffers, workspace, prebuilt C arguments
         self.peer_gather = None       # distributed.PeerGather: the exchange step of a sharded evaluation, issued on the
         self.peer_mode = 'gather'     # device right after finalize ('gather': logl rows of all ranks, point sharding;
@@ -351,11 +297,10 @@ class UnbinnedEngine(_EngineBase):
 
     # -- planning (host) ------------------------------------------------------------------------
     def plan(self, zs):
-        """Bucket points by hypercube cell and split the work between the two K2 kernels."""
+        """The batch's schedule: the fused DMMA path plans on the device; the streaming path lists its in-range points."""
         if self.uses_mma():
-            return PointPlan(len(zs), None, _EMPTY_I32, _EMPTY_I32, np.zeros((0, 4), dtype=np.int32), kernel='mma')
-        return plan_points(self.grid, zs, self.n_sources, self.n_super,
-                           None if self.force_kernel == 'mma' else self.force_kernel)
+            return PointPlan(len(zs), None, _EMPTY_I32, kernel='mma')
+        return plan_points(self.grid, zs)
 
     def uses_mma(self):
         """True when the batch runs through the fused device path (K1 -> device schedule -> DMMA K2 -> finalize)."""
@@ -715,23 +660,16 @@ class UnbinnedEngine(_EngineBase):
         torch = self.torch
         if plan.kernel == 'mma':
             return None, None, None, 0
-        n_s, n_g, n_w = len(plan.stream_points), len(plan.group_points), len(plan.work)
-        off_g = round_up(n_s, 4)
-        off_w = off_g + round_up(n_g, 4)
-        total = off_w + 4 * n_w
-        pin = self.ws.get("plan_h", total, torch.int32, pinned=True)
-        pn = pin.numpy()
-        pn[:n_s] = plan.stream_points
-        pn[off_g:off_g + n_g] = plan.group_points
-        pn[off_w:off_w + 4 * n_w] = plan.work.reshape(-1)
-        dev = self.ws.get("plan_d", total, torch.int32)
+        n_s = len(plan.stream_points)
+        pin = self.ws.get("plan_h", n_s, torch.int32, pinned=True)
+        pin.numpy()[:n_s] = plan.stream_points
+        dev = self.ws.get("plan_d", n_s, torch.int32)
         dev.copy_(pin, non_blocking=True)
-        return (dev[:n_s] if n_s else None, dev[off_g:off_g + n_g] if n_g else None,
-                dev[off_w:off_w + 4 * n_w] if n_w else None, total * 4)
+        return (dev[:n_s] if n_s else None), None, None, n_s * 4
 
     # -- evaluation -----------------------------------------------------------------------------
     def run_device(self, P, zs_d, mult_d, scale_d, eff_d, plan, plan_dev, want_setup=False):
-        """Device-only part: K1 -> K2 (stream and/or grouped) -> finalize.  Returns logl (device)."""
+        """Device-only part: K1 -> K2 (the fused DMMA call, or the streaming kernel) -> finalize.  Returns logl (device)."""
         torch = self.torch
         if self.ps_anchor is None:
             raise RuntimeError("set_ps_anchor / allocate_ps_anchor must be called first")
@@ -741,7 +679,7 @@ class UnbinnedEngine(_EngineBase):
         S, C = self.n_sources, self.grid.n_corners
         o = self._setup(P, zs_d, mult_d, scale_d, eff_d)
         partial = self.ws.get("partial", P * max(self.n_super, 1), torch.float64)
-        stream_d, group_d, work_d = plan_dev
+        stream_d = plan_dev[0]
         st = self._stream()
         if self.n_super > 0 and len(plan.stream_points):
             rc = self.lib.bi_unbinned_partials_stream(
@@ -750,14 +688,6 @@ class UnbinnedEngine(_EngineBase):
                 _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]), self.outlier_likelihood,
                 _cabi.dev_ptr(partial), st)
             _cabi.check(rc, "bi_unbinned_partials_stream")
-            self.launches += 1
-        if self.n_super > 0 and len(plan.work):
-            rc = self.lib.bi_unbinned_partials_grouped(
-                _cabi.dev_ptr(self.ps_anchor), self.ld, self.n_events, S, C, _cabi.dev_ptr(group_d),
-                _cabi.dev_ptr(work_d), len(plan.work), _cabi.dev_ptr(o["corner"]), _cabi.dev_ptr(o["weight"]),
-                _cabi.dev_ptr(o["mus"]), _cabi.dev_ptr(o["status"]), self.outlier_likelihood,
-                _cabi.dev_ptr(partial), st)
-            _cabi.check(rc, "bi_unbinned_partials_grouped")
             self.launches += 1
         logl = self.ws.get("logl", P, torch.float64)
         logsum = self.ws.get("logsum", P, torch.float64)

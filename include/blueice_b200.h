@@ -136,29 +136,17 @@ int bi_point_setup_sourcewise(int32_t n_dims, const int32_t* n_anchors_host, con
  *   corner/weight/mus/status: outputs of bi_point_setup
  *   partial_dev     [P, n_super] out: S_j partial log sums (n_super = bi_num_superblocks(n_events))
  *
- * bi_unbinned_partials_stream : lanes = events; any P; HBM-bound when P is small.
- * bi_unbinned_partials_grouped: threads = points that share a hypercube cell, events broadcast from
- *                               shared memory staged by TMA bulk copies; FP64-bound for large P.
- *   group_points_dev [n_grouped] point indices, points of one work item contiguous
- *   work_host        [n_work, 4] int32 (first, count<=BI_GROUP_POINTS, superblock_begin, superblock_end)
- *                    all points of a work item MUST share the same corner list (same cell).
- * Both produce bit-identical partials for the same point.
+ * bi_unbinned_partials_stream: lanes = events; any P, any n_sources, n_corners <= 32; HBM-bound when P is small.
+ *   point_index_dev [n_points] the points to evaluate (NULL: 0..n_points-1)
+ * It is the general path (more than BI_MMA_MAX_TERMS contraction terms or more than BI_PLAN_MAX_CELLS hypercube
+ * cells) and produces partials bit-identical to bi_unbinned_partials_mma for the same point.
  */
-#define BI_GROUP_POINTS 256        /* max points per grouped work item                          */
-#define BI_GROUP_MAX_SOURCES 8     /* grouped kernel keeps mus in registers: n_sources <= 8     */
 int bi_unbinned_partials_stream(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
                                 int32_t n_sources, int32_t n_corners,
                                 const int32_t* point_index_dev, int64_t n_points,
                                 const int32_t* corner_dev, const double* weight_dev,
                                 const double* mus_dev, const int32_t* status_dev,
                                 double outlier_likelihood, double* partial_dev, void* stream);
-
-int bi_unbinned_partials_grouped(const double* ps_anchor_dev, int64_t ld_events, int64_t n_events,
-                                 int32_t n_sources, int32_t n_corners,
-                                 const int32_t* group_points_dev, const int32_t* work_dev, int64_t n_work,
-                                 const int32_t* corner_dev, const double* weight_dev,
-                                 const double* mus_dev, const int32_t* status_dev,
-                                 double outlier_likelihood, double* partial_dev, void* stream);
 
 /*
  * Device-side schedule for bi_unbinned_partials_mma (no host round trip per batch).  Buckets the

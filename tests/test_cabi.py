@@ -41,8 +41,6 @@ def test_header_constants_match_python_mirror():
     assert int(consts["MAX_SOURCES"]) == _cabi.MAX_SOURCES
     assert int(consts["EVENT_BLOCK"]) == _cabi.EVENT_BLOCK
     assert int(consts["SUPERBLOCK"]) == _cabi.SUPERBLOCK
-    assert int(consts["GROUP_POINTS"]) == _cabi.GROUP_POINTS
-    assert int(consts["GROUP_MAX_SOURCES"]) == _cabi.GROUP_MAX_SOURCES
     assert int(consts["MAX_AXIS_POINTS"]) == _cabi.MAX_AXIS_POINTS
     assert int(consts["ABI_VERSION"]) == _cabi.load().bi_abi_version()
 
@@ -85,7 +83,3 @@ def test_argument_validation_reports_errors_without_a_gpu():
     rc = lib.bi_hist_lookup(None, 1, 1, _cabi.host_ptr(_cabi.as_i32([4])), _cabi.host_ptr(_cabi.as_f64(np.arange(5.))),
                             None, 0, 0, 9, None, 0, None, None)
     assert rc == -1 and b"method" in lib.bi_last_error()
-    # grouped kernel limits
-    rc = lib.bi_unbinned_partials_grouped(ctypes.c_void_p(16), 64, 64, 9, 4, None, None, 1, None, None, None, None,
-                                          1e-12, None, None)
-    assert rc == -1 and b"sources" in lib.bi_last_error()

@@ -166,7 +166,7 @@ def test_unbinned_stream_matches_oracle(d, s, n):
 
 @pytest.mark.parametrize("d,s,n", [(0, 1, 1000), (1, 1, 1), (1, 2, 33), (2, 2, 5000), (2, 2, 511), (2, 2, 512),
                                    (2, 2, 513), (3, 3, 2048), (4, 2, 1500), (4, 8, 640), (2, 5, 100000)])
-def test_grouped_is_bitwise_identical_to_stream_and_matches_oracle(d, s, n):
+def test_mma_kernel_against_stream_kernel_and_oracle(d, s, n):
     rng = np.random.default_rng(7 * d + s + n)
     axes, mus_anchor, ps_anchor = make_case(rng, d, s, n)
     eng = build_engine(axes, mus_anchor, ps_anchor)
@@ -178,20 +178,19 @@ def test_grouped_is_bitwise_identical_to_stream_and_matches_oracle(d, s, n):
     mult = rng.uniform(0.5, 2, (p, s))
     mult[3, 0] = -1.0                                 # unphysical
     res = {}
-    for mode in ('stream', 'grouped', None):
+    for mode in ('stream', None):
         eng.force_kernel = mode
         res[mode] = eng.evaluate(zs, mult)
-    assert np.array_equal(res['stream'], res['grouped'], equal_nan=True)
     plan = eng.plan(zs)
     if (2 ** d) * s <= 128:
         assert plan.kernel == 'mma'                   # auto mode really exercised the DMMA kernel
-        assert_logl_close(res[None], res['stream'], n, "mma vs vector kernels")
+        assert_logl_close(res[None], res['stream'], n, "mma vs streaming kernel")
     else:
         assert np.array_equal(res['stream'], res[None], equal_nan=True)
     orc = UnbinnedOracle(axes, mus_anchor).set_ps(ps_anchor)
     check = rng.choice(p, size=12 if n > 20000 else 40, replace=False)
     ref = orc.batch(zs[check], mult[check])
-    assert_logl_close(res[None][check], ref, n, "grouped d=%d s=%d n=%d" % (d, s, n))
+    assert_logl_close(res[None][check], ref, n, "scan d=%d s=%d n=%d" % (d, s, n))
 
 
 def test_results_do_not_depend_on_batch_shape_or_order():
@@ -242,7 +241,7 @@ def test_nan_inf_zero_and_negative_densities(outlier):
     mult = rng.uniform(0.5, 2, (p, 2))
     mult[5, 0] = 0.0                                  # 0 * inf = NaN term, dropped
     mult[6, :] = 0.0                                  # all-zero rates: every event is an outlier
-    for mode in (None, 'stream', 'grouped'):
+    for mode in (None, 'stream'):
         eng.force_kernel = mode
         got = eng.evaluate(zs, mult)
         ref = orc.batch(zs, mult)

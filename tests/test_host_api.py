@@ -191,29 +191,12 @@ def test_plan_points_covers_every_in_range_point_exactly_once():
     grid = engine.MorphGrid([np.array([-2., -1., 0., 1., 2.])] * 2)
     zs = rng.uniform(-2.3, 2.0, (3000, 2))
     zs[7] = np.nan
-    n_super = 37
-    plan = engine.plan_points(grid, zs, 2, n_super)
+    plan = engine.plan_points(grid, zs)
     covered = np.zeros(len(zs), dtype=int)
     covered[plan.stream_points] += 1
-    cells = grid.cell_ids(np.nan_to_num(zs))
-    seen = {}
-    for first, count, sb0, sb1 in plan.work:
-        assert 0 < count <= 256 and 0 <= sb0 < sb1 <= n_super
-        pts = plan.group_points[first:first + count]
-        assert len(set(cells[pts])) == 1                    # one hypercube cell per work item
-        seen.setdefault((first, count), []).append((sb0, sb1))
-    for (first, count), ranges in seen.items():
-        ranges.sort()
-        assert ranges[0][0] == 0 and ranges[-1][1] == n_super
-        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))   # superblock ranges tile [0, n_super)
-        covered[plan.group_points[first:first + count]] += 1
     assert np.array_equal(covered == 1, plan.in_range)
     assert not plan.in_range[7]
-    # forcing a kernel only moves points between the two lists
-    assert len(engine.plan_points(grid, zs, 2, n_super, 'stream').work) == 0
-    assert len(engine.plan_points(grid, zs, 2, n_super, 'grouped').stream_points) == 0
-    # too many sources for the grouped kernel -> everything streams
-    assert len(engine.plan_points(grid, zs, 9, n_super).work) == 0
+    assert np.all(np.diff(plan.stream_points) > 0)          # in batch order
 
 
 def test_group_pairs_invariants():
