@@ -1,5 +1,6 @@
 """Host-side logic of the API mirror that needs no device: parameter bookkeeping and errors, config
 handling of Model/Source, histogram semantics, anchor-grid ordering, batch planning, objectives."""
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -285,3 +286,33 @@ def test_toy_tables_and_means_follow_model_simulate():
     gauss = Model(conf_for_test(n_sources=1))
     with pytest.raises(NotImplementedError):
         toys.source_tables(gauss)
+
+
+def test_install_as_blueice_aliases_the_reference_import_paths():
+    """Code written against the reference imports `blueice.likelihood` etc.; the alias makes those names this package."""
+    import subprocess
+    import sys
+    code = ("import blueice_b200, sys\n"
+            "blueice_b200.install_as_blueice()\n"
+            "import blueice\n"
+            "from blueice.likelihood import UnbinnedLogLikelihood, BinnedLogLikelihood, LogLikelihoodSum\n"
+            "from blueice.source import HistogramPdfSource, DensityEstimatingSource\n"
+            "from blueice.model import Model\n"
+            "from blueice.inference import bestfit_scipy, one_parameter_interval\n"
+            "from blueice.exceptions import InvalidParameter, NotPreparedException\n"
+            "from blueice.pdf_morphers import MORPHERS\n"
+            "import blueice.likelihood, blueice_b200.likelihood\n"
+            "assert blueice.likelihood is blueice_b200.likelihood and blueice is blueice_b200\n"
+            "assert UnbinnedLogLikelihood is blueice_b200.UnbinnedLogLikelihood\n"
+            "try:\n"
+            "    import blueice.parallel\n"
+            "except ImportError:\n"
+            "    pass\n"
+            "else:\n"
+            "    raise SystemExit('blueice.parallel should not resolve')\n"
+            "print('ok')\n")
+    env = dict(os.environ)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env["PYTHONPATH"] = root                       # the reference is NOT on the path: every name must come from the alias
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr
