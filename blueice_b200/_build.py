@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libblueice_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["bi_util.cu", "bi_peer.cu", "bi_setup.cu", "bi_small.cu", "bi_unbinned.cu", "bi_unbinned_mma.cu", "bi_plan.cu", "bi_lookup.cu", "bi_template.cu", "bi_template_bm.cu", "bi_toys.cu", "bi_binned.cu"]
+SOURCES = ["bi_util.cu", "bi_peer.cu", "bi_setup.cu", "bi_small.cu", "bi_unbinned.cu", "bi_unbinned_mma.cu", "bi_unbinned_wide.cu", "bi_plan.cu", "bi_lookup.cu", "bi_template.cu", "bi_template_bm.cu", "bi_toys.cu", "bi_binned.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-fmad=false", "-std=c++17",

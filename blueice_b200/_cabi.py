@@ -137,7 +137,7 @@ MAX_AXIS_POINTS = 256
 EVENT_BLOCK = 32
 SUPERBLOCK = 512
 STREAM_MAX_CORNERS = 32
-MMA_MAX_TERMS = 128
+MMA_MAX_TERMS = 4096
 PLAN_MAX_CELLS = 16384
 TS_MAX_TERMS = 256
 TS_GROUP_POINTS = 8

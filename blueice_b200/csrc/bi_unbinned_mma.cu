@@ -1,7 +1,33 @@
-// blueice_b200 -- C-ABI entry of the DMMA K2 kernel (bi_unbinned_mma.cuh), K = C*S <= 32 contraction terms.
+// blueice_b200 -- C-ABI entry of the DMMA K2 kernels: bi_unbinned_mma.cuh (K = C*S <= 128 contraction terms, per-warp tile
+// rings) and bi_unbinned_wide.cu (longer contractions: K-chunk loop over CTA-shared tiles).
 #include <stdlib.h>
 
 #include "bi_unbinned_mma.cuh"
+
+#define BI_MMA_NARROW_MAX_TERMS 128
+
+// bi_unbinned_wide.cu
+int bi_launch_mma_wide(const double* A, int64_t ld, int64_t N, int K, int S, const int32_t* group_points,
+                       int32_t* groups, int32_t* header, int64_t n_super, const int32_t* row, const double* coef,
+                       const double* wterm, const int32_t* term_source, const double* mus, double outlier,
+                       double* partial, cudaStream_t st);
+int bi_mma_wide_unit_points(void);
+
+#define BI_MMA_WIDE_MIN_TERMS_DEFAULT 49
+
+// Which of the two kernels (they give identical bits): measured on B200 over 4096-point scans of 1e5 events
+// (profiles/r2_wide_kernel.md) the per-warp rings win up to K = 32 (21.3 against 15.2 TFLOP/s), tie at K = 48 and lose
+// beyond (K = 64: 12.7 against 17.4; K = 80..128, one m-tile per warp: 5.7 / 4.7 against 18.4 / 19.3).  The environment
+// variable BI_MMA_WIDE_MIN_TERMS moves the threshold (tests and A/B runs).
+static bool bi_mma_use_wide(int n_terms) {
+    static int min_terms = -1;
+    if (min_terms < 0) {
+        const char* env = getenv("BI_MMA_WIDE_MIN_TERMS");
+        const int v = env ? atoi(env) : 0;
+        min_terms = v >= 1 ? v : BI_MMA_WIDE_MIN_TERMS_DEFAULT;
+    }
+    return n_terms >= min_terms || n_terms > BI_MMA_NARROW_MAX_TERMS;
+}
 
 static int bi_mma_k4(int K) {
     const int k4 = (K + 3) / 4;
@@ -71,6 +97,10 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
     BI_REQUIRE(grid_dims < 0 || (grid_dims <= BI_MAX_DIMS && (grid_dims == 0 || (n_anchors_host && cell_dev))),
                "bi_unbinned_partials_mma: grid_dims needs n_anchors_host and cell_dev");
     cudaStream_t st = (cudaStream_t)stream;
+    if (bi_mma_use_wide(n_terms))
+        return bi_launch_mma_wide(rows_dev, ld_events, n_events, n_terms, n_sources, group_points_dev, groups_dev, header_dev,
+                                  n_super, row_dev, coef_dev, wterm_dev, term_source_dev, mus_dev, outlier_likelihood,
+                                  partial_dev, st);
     const int k4 = bi_mma_k4(n_terms);
     // full-grid layout ([G][S][ld], term k = corner * S + source): one tiled TMA instruction per event tile
     alignas(64) CUtensorMap tmap;
@@ -95,6 +125,7 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
 }
 
 extern "C" int32_t bi_mma_unit_points(int32_t n_terms) {
+    if (bi_mma_use_wide(n_terms)) return bi_mma_wide_unit_points();
     const int k4 = bi_mma_k4(n_terms);
     return 8 * (k4 <= 2 ? BI_MMA_MT_SMALL : (k4 <= 4 ? 4 : (k4 <= 16 ? 2 : 1)));
 }

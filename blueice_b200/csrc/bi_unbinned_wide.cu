@@ -1,0 +1,325 @@
+// blueice_b200 -- K2 for LONG contractions (K = C*S > 128 terms): the DMMA kernel with a K-chunk loop.
+//
+// Same replacement and same canonical arithmetic as bi_unbinned_mma.cuh (blueice/likelihood.py:355-356,678-690 and
+// scipy/interpolate/_rgi.py:520-549):  f(theta_p, x_i) = fma chain over k = 0..K-1 of A[row_k, i] * coef_{p,k},
+// 32-event groups -> pair / quad / oct product tree per class -> (m, e), 16 groups per superblock, ONE log per 512 events;
+// the reference-semantics fallback (nansum, outlier replacement, likelihood.py:686-689) where a density leaves the fast range.
+//
+// What differs is the data movement.  With hundreds of rows per event the per-warp tile ring of k_unbinned_mma has room for
+// one 8-point m-tile per warp and one warp per CTA: every 8 points stream all K rows from L2 again.  Here a CTA owns a unit
+// = (point group of <= 64 points of one hypercube cell, superblock range) and its 4 consumer warps (2 m-tiles = 16 points
+// each) SHARE the event tiles.  A tile = 64 events; its K rows arrive in chunks of 32 rows (one 1-D TMA bulk copy per row,
+// issued by the 32 lanes of a fifth, producer warp) through a CTA-wide ring of 6 stages guarded by full / empty mbarriers.
+// The DMMA accumulators of a tile (2 m-tiles x 8 octets) stay in registers across the chunks, so the chain over k is the
+// same sequential fma chain (DMMA accumulates in k order, profiles/microbench/dmma_probe_b200.log) however K is cut.
+// A fragments (the points' coefficients) cannot stay in registers for arbitrary K: they are read from global memory
+// (L1 / L2 resident: 64 points x K doubles) one chunk ahead of their use.
+//
+// Units are handed out statically (unit u = blockIdx.x + j * gridDim.x of the device schedule, bi_plan.cu), so the
+// producer runs ahead across unit boundaries without talking to the consumers.
+#include "bi_unbinned_mma.cuh"
+
+#define BI_WIDE_WARPS 4                 /* consumer warps per CTA */
+#define BI_WIDE_MT 2                    /* 8-point m-tiles per consumer warp */
+#define BI_WIDE_TE 64                   /* events per tile (2 canonical groups) */
+#define BI_WIDE_RS (BI_WIDE_TE + 4)     /* row stride: B-fragment loads of the four k-lanes hit distinct banks */
+#define BI_WIDE_KC 32                   /* rows per chunk = one bulk copy per producer lane */
+#define BI_WIDE_STAGES 6
+#define BI_WIDE_THREADS ((BI_WIDE_WARPS + 1) * 32)
+#define BI_WIDE_STAGE_DOUBLES (BI_WIDE_KC * BI_WIDE_RS)
+#define BI_WIDE_HEADER_BYTES 128        /* full[STAGES], empty[STAGES] */
+#define BI_WIDE_SMEM_BYTES (BI_WIDE_HEADER_BYTES + BI_WIDE_STAGES * BI_WIDE_STAGE_DOUBLES * 8)
+#define BI_WIDE_OCTETS (BI_WIDE_TE / 8)
+
+__device__ __forceinline__ void bi_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bi_smem_u32(bar)) : "memory");
+}
+
+// density of one event with the reference's semantics (likelihood.py:686-689), rows read from global memory (by the time
+// a group turns out to need it the early chunks of its tile have left shared memory); as bi_slow_density_rows
+static __device__ __noinline__ double bi_wide_slow_density(const double* __restrict__ A, int64_t ld,
+                                                           const int32_t* __restrict__ row_lead, int64_t ev, int K, int S,
+                                                           const int32_t* __restrict__ term_source,
+                                                           const double* __restrict__ wterm,
+                                                           const double* __restrict__ mu, double outlier) {
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        double ps = 0.0;
+        for (int k = 0; k < K; ++k)
+            if (term_source[k] == s) ps = fma(A[(int64_t)row_lead[k] * ld + ev], wterm[k], ps);
+        const double term = __dmul_rn(mu[s], ps);
+        if (term == term) acc = __dadd_rn(acc, term);       // nansum: NaN terms count as 0
+    }
+    return bi_fix_density(acc, outlier);
+}
+
+// (t, group) fallback: the canonical tree over log(p_i) of the class's 8 events (as bi_slow_group); ev0 = first event of
+// the group, n_valid = events of the group that exist (others count as p = 1)
+static __device__ __noinline__ double bi_wide_slow_group(const double* __restrict__ A, int64_t ld,
+                                                         const int32_t* __restrict__ row_lead, int64_t ev0, int K, int S,
+                                                         int t, int n_valid, const int32_t* __restrict__ term_source,
+                                                         const double* __restrict__ wterm,
+                                                         const double* __restrict__ mu, double outlier) {
+    double quad[2];
+    for (int h = 0; h < 2; ++h) {
+        double pr[2];
+        for (int n = 0; n < 2; ++n) {
+            const int e = 8 * (2 * h + n) + 2 * t;
+            const double p0 = (e < n_valid) ? bi_wide_slow_density(A, ld, row_lead, ev0 + e, K, S, term_source, wterm, mu, outlier) : 1.0;
+            const double p1 = (e + 1 < n_valid) ? bi_wide_slow_density(A, ld, row_lead, ev0 + e + 1, K, S, term_source, wterm, mu, outlier) : 1.0;
+            pr[n] = __dadd_rn(log(p0), log(p1));
+        }
+        quad[h] = __dadd_rn(pr[0], pr[1]);
+    }
+    return __dadd_rn(quad[0], quad[1]);
+}
+
+// coefficients of chunk `ch` for this lane: a[mt][kk] = coef[p_mt, ch * KC + 4 kk + t] (0 beyond K)
+__device__ __forceinline__ void bi_wide_load_a(double (&a)[BI_WIDE_MT][BI_WIDE_KC / 4], const double* const (&coef_p)[BI_WIDE_MT],
+                                               int ch, int K, int t) {
+#pragma unroll
+    for (int kk = 0; kk < BI_WIDE_KC / 4; ++kk) {
+        const int k = ch * BI_WIDE_KC + 4 * kk + t;
+#pragma unroll
+        for (int mt = 0; mt < BI_WIDE_MT; ++mt) a[mt][kk] = (k < K) ? coef_p[mt][k] : 0.0;
+    }
+}
+
+// the DMMAs of one chunk: d[mt][n] += sum over the chunk's k-steps of a[mt][kk] x B(tile rows 4 kk + t, octet n)
+// FULL: all 32 rows of the chunk exist; otherwise k-steps beyond K are skipped and rows beyond K (stale shared memory) read as 0
+template <bool FULL>
+__device__ __forceinline__ void bi_wide_chunk(const double* __restrict__ bcol, const double (&a)[BI_WIDE_MT][BI_WIDE_KC / 4],
+                                              double (&d)[BI_WIDE_MT][BI_WIDE_OCTETS][2], int k_left, int t) {
+#pragma unroll
+    for (int kk = 0; kk < BI_WIDE_KC / 4; ++kk) {
+        if (!FULL && 4 * kk >= k_left) break;
+        double b[BI_WIDE_OCTETS];
+#pragma unroll
+        for (int n = 0; n < BI_WIDE_OCTETS; ++n) {
+            b[n] = bcol[4 * kk * BI_WIDE_RS + 8 * n];
+            if (!FULL && 4 * kk + t >= k_left) b[n] = 0.0;
+        }
+#pragma unroll
+        for (int n = 0; n < BI_WIDE_OCTETS; ++n)
+#pragma unroll
+            for (int mt = 0; mt < BI_WIDE_MT; ++mt) bi_dmma(d[mt][n][0], d[mt][n][1], a[mt][kk], b[n]);
+    }
+}
+
+__global__ void __launch_bounds__(BI_WIDE_THREADS, 2)
+k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S,
+                    const int32_t* __restrict__ group_points, const int4* __restrict__ groups,
+                    const int32_t* __restrict__ header, int64_t n_super, const int32_t* __restrict__ row,
+                    const double* __restrict__ coef, const double* __restrict__ wterm,
+                    const int32_t* __restrict__ term_source, const double* __restrict__ mus, double outlier,
+                    double* __restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char bi_wide_smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bi_wide_smem);
+    uint64_t* empty_bar = full_bar + BI_WIDE_STAGES;
+    double* ring = reinterpret_cast<double*>(bi_wide_smem + BI_WIDE_HEADER_BYTES);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_groups = header[0], sb_per = header[2], n_units = header[3];
+    const int n_chunks = (K + BI_WIDE_KC - 1) / BI_WIDE_KC;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BI_WIDE_STAGES; ++i) {
+            bi_mbar_init(&full_bar[i], 1);
+            bi_mbar_init(&empty_bar[i], BI_WIDE_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int st = 0;                 // ring position and its phase bit: the same sequence of (unit, superblock, tile, chunk) on
+    unsigned phase = 0;         // the producer and on every consumer warp
+
+    if (warp == BI_WIDE_WARPS) {
+        // ---------------- producer warp: lane r copies row r of the chunk
+        bool first_lap = true;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int grp = u % n_groups, range = u / n_groups;
+            const int64_t lead = group_points[groups[grp].x];
+            const int32_t* row_lead = row + lead * K;                     // every point of the group has these rows
+            const int64_t sb_begin = (int64_t)range * sb_per;
+            const int64_t sb_end = sb_begin + sb_per < n_super ? sb_begin + sb_per : n_super;
+            for (int64_t sb = sb_begin; sb < sb_end; ++sb) {
+                const int64_t left = N - sb * BI_SUPERBLOCK;
+                const int n_ev = left < BI_SUPERBLOCK ? (int)left : BI_SUPERBLOCK;
+                for (int ti = 0; ti * BI_WIDE_TE < n_ev; ++ti) {
+                    const int64_t ev = sb * BI_SUPERBLOCK + (int64_t)ti * BI_WIDE_TE;
+                    const int64_t cols = ld - ev < BI_WIDE_TE ? ld - ev : BI_WIDE_TE;      // even (ld is)
+                    const unsigned bytes = (unsigned)cols * (unsigned)sizeof(double);
+                    for (int ch = 0; ch < n_chunks; ++ch) {
+                        if (!first_lap) bi_mbar_wait(&empty_bar[st], phase ^ 1u);          // the stage's previous use is consumed
+                        const int n_rows = K - ch * BI_WIDE_KC < BI_WIDE_KC ? K - ch * BI_WIDE_KC : BI_WIDE_KC;
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        if (lane == 0) bi_mbar_expect_tx(&full_bar[st], bytes * (unsigned)n_rows);
+                        __syncwarp();
+                        if (lane < n_rows)
+                            bi_bulk_g2s(ring + (size_t)st * BI_WIDE_STAGE_DOUBLES + (size_t)lane * BI_WIDE_RS,
+                                        A + (int64_t)row_lead[ch * BI_WIDE_KC + lane] * ld + ev, bytes, &full_bar[st]);
+                        if (++st == BI_WIDE_STAGES) { st = 0; phase ^= 1u; first_lap = false; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps
+    const int g = lane >> 2, t = lane & 3;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int grp = u % n_groups, range = u / n_groups;
+        const int4 gp = groups[grp];
+        const int n_pts = gp.y;
+        const int32_t* slot_point = group_points + gp.x;
+        const int64_t lead = slot_point[0];
+        const int32_t* row_lead = row + lead * K;
+        const bool warp_active = warp * BI_WIDE_MT * 8 < n_pts;           // warp-uniform
+        bool live[BI_WIDE_MT];
+        int64_t p_slot[BI_WIDE_MT];
+        const double* coef_p[BI_WIDE_MT];
+#pragma unroll
+        for (int mt = 0; mt < BI_WIDE_MT; ++mt) {
+            const int idx = (warp * BI_WIDE_MT + mt) * 8 + g;
+            live[mt] = idx < n_pts;
+            p_slot[mt] = live[mt] ? (int64_t)slot_point[idx] : lead;      // dead slots replay the group's first point
+            coef_p[mt] = coef + p_slot[mt] * K;
+        }
+        double a_next[BI_WIDE_MT][BI_WIDE_KC / 4];
+        if (warp_active) bi_wide_load_a(a_next, coef_p, 0, K, t);
+
+        const int64_t sb_begin = (int64_t)range * sb_per;
+        const int64_t sb_end = sb_begin + sb_per < n_super ? sb_begin + sb_per : n_super;
+        for (int64_t sb = sb_begin; sb < sb_end; ++sb) {
+            const int64_t left = N - sb * BI_SUPERBLOCK;
+            const int n_ev = left < BI_SUPERBLOCK ? (int)left : BI_SUPERBLOCK;
+            double M[BI_WIDE_MT], L[BI_WIDE_MT];
+            int E[BI_WIDE_MT];
+#pragma unroll
+            for (int mt = 0; mt < BI_WIDE_MT; ++mt) { M[mt] = 1.0; L[mt] = 0.0; E[mt] = 0; }
+
+            for (int ti = 0; ti * BI_WIDE_TE < n_ev; ++ti) {
+                double d[BI_WIDE_MT][BI_WIDE_OCTETS][2];
+#pragma unroll
+                for (int mt = 0; mt < BI_WIDE_MT; ++mt)
+#pragma unroll
+                    for (int n = 0; n < BI_WIDE_OCTETS; ++n) d[mt][n][0] = d[mt][n][1] = 0.0;
+
+#pragma unroll 1
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    double a[BI_WIDE_MT][BI_WIDE_KC / 4];
+                    if (warp_active) {
+#pragma unroll
+                        for (int mt = 0; mt < BI_WIDE_MT; ++mt)
+#pragma unroll
+                            for (int kk = 0; kk < BI_WIDE_KC / 4; ++kk) a[mt][kk] = a_next[mt][kk];
+                        // the coefficients of the chunk after this one (the chunks of every tile cycle 0 .. n_chunks - 1)
+                        bi_wide_load_a(a_next, coef_p, ch + 1 < n_chunks ? ch + 1 : 0, K, t);
+                    }
+                    bi_mbar_wait(&full_bar[st], phase);
+                    if (warp_active) {
+                        const double* bcol = ring + (size_t)st * BI_WIDE_STAGE_DOUBLES + t * BI_WIDE_RS + g;
+                        const int k_left = K - ch * BI_WIDE_KC;
+                        if (k_left >= BI_WIDE_KC) bi_wide_chunk<true>(bcol, a, d, k_left, t);
+                        else bi_wide_chunk<false>(bcol, a, d, k_left, t);
+                    }
+                    __syncwarp();
+                    if (lane == 0) bi_mbar_arrive(&empty_bar[st]);        // this warp is done with the stage
+                    if (++st == BI_WIDE_STAGES) { st = 0; phase ^= 1u; }
+                }
+
+                if (!warp_active) continue;
+                // ---- the tile's two canonical groups: product tree per class, rare path from global memory
+                const int n_valid = n_ev - ti * BI_WIDE_TE;               // may exceed the tile
+#pragma unroll
+                for (int h = 0; h < BI_WIDE_TE / BI_GROUP_EVENTS; ++h) {
+                    if (h * BI_GROUP_EVENTS >= n_valid) break;            // warp-uniform: a group of p = 1 changes nothing
+                    unsigned bad = 0;
+#pragma unroll
+                    for (int mt = 0; mt < BI_WIDE_MT; ++mt) {
+                        double (&dd)[BI_WIDE_OCTETS][2] = d[mt];
+#pragma unroll
+                        for (int n = 4 * h; n < 4 * h + 4; ++n) {         // events >= N count as p = 1
+                            const int e = 8 * n + 2 * t;
+                            if (e >= n_valid) dd[n][0] = 1.0;
+                            if (e + 1 >= n_valid) dd[n][1] = 1.0;
+                        }
+                        unsigned tmax = 0;
+#pragma unroll
+                        for (int n = 4 * h; n < 4 * h + 4; ++n) {
+                            tmax = max(tmax, (unsigned)(__double2hiint(dd[n][0]) - BI_RANGE_LO));
+                            tmax = max(tmax, (unsigned)(__double2hiint(dd[n][1]) - BI_RANGE_LO));
+                        }
+                        const double q0 = __dmul_rn(__dmul_rn(dd[4 * h][0], dd[4 * h][1]), __dmul_rn(dd[4 * h + 1][0], dd[4 * h + 1][1]));
+                        const double q1 = __dmul_rn(__dmul_rn(dd[4 * h + 2][0], dd[4 * h + 2][1]), __dmul_rn(dd[4 * h + 3][0], dd[4 * h + 3][1]));
+                        const double oct = __dmul_rn(q0, q1);
+                        double m;
+                        int e;
+                        bi_split(oct, &m, &e);
+                        if (tmax >= BI_RANGE_SPAN) {
+                            m = 1.0;
+                            e = 0;
+                            if (live[mt]) bad |= 1u << mt;
+                        }
+                        M[mt] = __dmul_rn(M[mt], m);
+                        E[mt] += e;
+                    }
+                    if (__any_sync(BI_FULL_MASK, bad != 0)) {
+                        const int nv = n_valid - h * BI_GROUP_EVENTS < BI_GROUP_EVENTS ? n_valid - h * BI_GROUP_EVENTS : BI_GROUP_EVENTS;
+                        const int64_t ev0 = sb * BI_SUPERBLOCK + (int64_t)ti * BI_WIDE_TE + h * BI_GROUP_EVENTS;
+#pragma unroll
+                        for (int mt = 0; mt < BI_WIDE_MT; ++mt)
+                            if ((bad >> mt) & 1u)
+                                L[mt] = __dadd_rn(L[mt], bi_wide_slow_group(A, ld, row_lead, ev0, K, S, t, nv, term_source,
+                                                                             wterm + p_slot[mt] * K, mus + p_slot[mt] * S, outlier));
+                    }
+                }
+            }
+
+            // ---- close the superblock: combine the four classes, one log per point
+            if (warp_active) {
+#pragma unroll
+                for (int mt = 0; mt < BI_WIDE_MT; ++mt) {
+                    double m = M[mt];
+                    m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 1));
+                    m = __dmul_rn(m, __shfl_xor_sync(BI_FULL_MASK, m, 2));
+                    int e = E[mt];
+                    e += __shfl_xor_sync(BI_FULL_MASK, e, 1);
+                    e += __shfl_xor_sync(BI_FULL_MASK, e, 2);
+                    double l = L[mt];
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 1));
+                    l = __dadd_rn(l, __shfl_xor_sync(BI_FULL_MASK, l, 2));
+                    const double total = __dadd_rn(bi_block_log(m, e), l);
+                    if (live[mt] && t == 0) partial[p_slot[mt] * n_super + sb] = total;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launcher (called by bi_unbinned_partials_mma for n_terms > 128)
+// ---------------------------------------------------------------------------------------------
+int bi_launch_mma_wide(const double* A, int64_t ld, int64_t N, int K, int S, const int32_t* group_points,
+                       int32_t* groups, int32_t* header, int64_t n_super, const int32_t* row, const double* coef,
+                       const double* wterm, const int32_t* term_source, const double* mus, double outlier,
+                       double* partial, cudaStream_t st) {
+    static int blocks = 0;
+    if (!blocks) {
+        int dev = 0, sms = 0, per_sm = 0;
+        BI_CUDA_CHECK(cudaGetDevice(&dev));
+        BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        BI_CUDA_CHECK(cudaFuncSetAttribute(k_unbinned_mma_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, BI_WIDE_SMEM_BYTES));
+        BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unbinned_mma_wide, BI_WIDE_THREADS, BI_WIDE_SMEM_BYTES));
+        BI_REQUIRE(per_sm >= 1, "k_unbinned_mma_wide does not fit on this device");
+        blocks = sms * per_sm;
+    }
+    k_unbinned_mma_wide<<<(unsigned)blocks, BI_WIDE_THREADS, BI_WIDE_SMEM_BYTES, st>>>(
+        A, ld, N, K, S, group_points, reinterpret_cast<const int4*>(groups), header, n_super, row, coef, wterm, term_source,
+        mus, outlier, partial);
+    BI_LAUNCH_CHECK();
+    return BI_OK;
+}
+
+int bi_mma_wide_unit_points(void) { return 8 * BI_WIDE_WARPS * BI_WIDE_MT; }

@@ -184,8 +184,11 @@ int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_po
  * instead of one bulk copy per row.  grid_dims = -1: arbitrary row lists (source-wise interpolation).
  * Densities that leave [2^-126, 2^127) (zero, negative, NaN, inf ...) are re-evaluated with the
  * reference's nansum / outlier semantics from wterm / term_source / mus (likelihood.py:686-689).
+ * Contractions of more than 128 terms run the K-chunk form of the kernel (k_unbinned_mma_wide: a CTA's four warps share
+ * event tiles whose rows arrive in chunks of 32 through a CTA-wide TMA ring, accumulators carried across the chunks:
+ * the same sequential fma chain over k); units are then (group, range) pairs taken in launch order, no counters used.
  */
-#define BI_MMA_MAX_TERMS 128
+#define BI_MMA_MAX_TERMS 4096
 int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t n_events,
                              int32_t n_terms, int32_t n_sources,
                              const int32_t* group_points_dev, int32_t* groups_dev, int32_t* header_dev,

@@ -165,7 +165,9 @@ def test_unbinned_stream_matches_oracle(d, s, n):
 
 
 @pytest.mark.parametrize("d,s,n", [(0, 1, 1000), (1, 1, 1), (1, 2, 33), (2, 2, 5000), (2, 2, 511), (2, 2, 512),
-                                   (2, 2, 513), (3, 3, 2048), (4, 2, 1500), (4, 8, 640), (2, 5, 100000)])
+                                   (2, 2, 513), (3, 3, 2048), (4, 2, 1500), (4, 8, 640), (2, 5, 100000),
+                                   # more than 128 contraction terms: the K-chunk kernel (k_unbinned_mma_wide)
+                                   (5, 5, 3000), (4, 12, 1111), (3, 40, 513), (5, 8, 64), (4, 9, 1), (5, 33, 130)])
 def test_mma_kernel_against_stream_kernel_and_oracle(d, s, n):
     rng = np.random.default_rng(7 * d + s + n)
     axes, mus_anchor, ps_anchor = make_case(rng, d, s, n)
@@ -182,11 +184,8 @@ def test_mma_kernel_against_stream_kernel_and_oracle(d, s, n):
         eng.force_kernel = mode
         res[mode] = eng.evaluate(zs, mult)
     plan = eng.plan(zs)
-    if (2 ** d) * s <= 128:
-        assert plan.kernel == 'mma'                   # auto mode really exercised the DMMA kernel
-        assert_logl_close(res[None], res['stream'], n, "mma vs streaming kernel")
-    else:
-        assert np.array_equal(res['stream'], res[None], equal_nan=True)
+    assert plan.kernel == 'mma'                       # auto mode really exercised the DMMA kernels
+    assert_logl_close(res[None], res['stream'], n, "mma vs streaming kernel")
     orc = UnbinnedOracle(axes, mus_anchor).set_ps(ps_anchor)
     check = rng.choice(p, size=12 if n > 20000 else 40, replace=False)
     ref = orc.batch(zs[check], mult[check])
@@ -209,6 +208,101 @@ def test_results_do_not_depend_on_batch_shape_or_order():
     assert np.array_equal(eng.evaluate(zs[:37], mult[:37]), full[:37])
     assert np.array_equal(eng.evaluate(zs[100:613], mult[100:613]), full[100:613])
     assert eng.evaluate(zs[:0], mult[:0]).shape == (0,)
+
+
+def test_wide_contraction_results_do_not_depend_on_batch_shape_or_order():
+    """160 contraction terms (5 shape parameters x 5 sources): the K-chunk kernel, whose units are CTA-wide groups of 64
+    points -- a point alone, in a permuted batch or in a slice of the batch gives the same bits."""
+    rng = np.random.default_rng(55)
+    axes, mus_anchor, ps_anchor = make_case(rng, 5, 5, 1500)
+    eng = build_engine(axes, mus_anchor, ps_anchor)
+    assert eng.n_terms == 160 and eng.uses_mma()
+    p = 600
+    zs = random_points(rng, axes, p)
+    zs[200:500, 0] = rng.uniform(axes[0][0], axes[0][1], 300)
+    zs[200:500, 1:] = [0.5 * (a[0] + a[1]) for a in axes[1:]]
+    mult = rng.uniform(0.5, 2, (p, 5))
+    full = eng.evaluate(zs, mult)
+    assert np.all(np.isfinite(full))
+    for i in (0, 1, 17, 250, 599):
+        alone = eng.evaluate(zs[i:i + 1], mult[i:i + 1])
+        assert alone[0] == full[i]
+    perm = rng.permutation(p)
+    assert np.array_equal(eng.evaluate(zs[perm], mult[perm]), full[perm])
+    assert np.array_equal(eng.evaluate(zs[190:403], mult[190:403]), full[190:403])
+    orc = UnbinnedOracle(axes, mus_anchor).set_ps(ps_anchor)
+    check = np.r_[0:5, 245:255]
+    assert_logl_close(full[check], orc.batch(zs[check], mult[check]), 1500, "wide contraction vs oracle")
+
+
+@pytest.mark.parametrize("outlier", [1e-12, 0.0])
+def test_wide_contraction_nan_inf_zero_and_negative_densities(outlier):
+    """The rare path of the K-chunk kernel (rows re-read from global memory) against likelihood.py:686-689."""
+    rng = np.random.default_rng(12)
+    axes, mus_anchor, ps_anchor = make_case(rng, 4, 9, 777)                   # 144 terms
+    specials = [0.0, np.nan, np.inf, -1.0, -np.inf, 1e-320, 1e305]
+    for k, v in enumerate(specials):
+        ps_anchor[..., 0, 10 + 3 * k] = v                                     # whole column special in source 0
+        ps_anchor[1, 0, 2, 1, 4, 40 + 3 * k] = v                              # one anchor, one source only
+    ps_anchor[..., 100] = 0.0                                                 # density exactly 0 -> outlier
+    ps_anchor[..., 101] = np.nan                                              # all terms NaN -> nansum 0 -> outlier
+    ps_anchor[..., 776] = 0.0                                                 # in the last, partial group
+    eng = build_engine(axes, mus_anchor, ps_anchor, outlier=outlier)
+    orc = UnbinnedOracle(axes, mus_anchor, outlier_likelihood=outlier).set_ps(ps_anchor)
+    p = 70
+    zs = random_points(rng, axes, p)
+    mult = rng.uniform(0.5, 2, (p, 9))
+    mult[5, 0] = 0.0
+    mult[6, :] = 0.0
+    ref = orc.batch(zs, mult)
+    for mode in (None, 'stream'):
+        eng.force_kernel = mode
+        assert_logl_close(eng.evaluate(zs, mult), ref, 777, "wide special values, outlier=%g, %s" % (outlier, mode))
+
+
+_WIDE_AB_SCRIPT = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+from blueice_b200 import engine
+out = {}
+for d, s, n in %r:
+    rng = np.random.default_rng(1000 + 7 * d + s + n)
+    axes = [np.sort(rng.uniform(-2, 2, 3)) for _ in range(d)]
+    mus_anchor = rng.uniform(5, 500, [3] * d + [s])
+    ps_anchor = np.exp(rng.normal(-4, 2, [3] * d + [s, n]))
+    ps_anchor[..., n // 2] = 0.0
+    grid = engine.MorphGrid(axes)
+    eng = engine.UnbinnedEngine(grid, mus_anchor.reshape(grid.n_anchors, s), 1e-12, None)
+    eng.set_ps_anchor(ps_anchor)
+    zs = np.column_stack([rng.uniform(a[0], a[-1], 333) for a in axes]) if d else np.zeros((333, 0))
+    mult = rng.uniform(0.5, 2, (333, s))
+    out['%%d_%%d_%%d' %% (d, s, n)] = eng.evaluate(zs, mult)
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_k_chunk_kernel_is_bitwise_identical_to_the_per_warp_kernel(tmp_path):
+    """BI_MMA_WIDE_MIN_TERMS=1 sends every contraction to the K-chunk kernel: same fma chain over k, same trees -> same bits
+    as the per-warp-ring kernel (the two runs are separate processes: the threshold is read once)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shapes = [(0, 1, 1000), (2, 2, 5000), (3, 3, 2048), (4, 8, 640), (1, 2, 33), (2, 9, 513)]
+    script = _WIDE_AB_SCRIPT % (root, shapes)
+    res = {}
+    for tag, val in (('narrow', None), ('wide', '1')):
+        env = dict(os.environ)
+        env.pop('BI_MMA_WIDE_MIN_TERMS', None)
+        if val:
+            env['BI_MMA_WIDE_MIN_TERMS'] = val
+        env['BI_SMALL'] = '0'                       # keep the four-launch path for every batch size
+        path = str(tmp_path / (tag + '.npz'))
+        run = subprocess.run([sys.executable, '-c', script, path], env=env, cwd=root, capture_output=True, text=True)
+        assert run.returncode == 0, run.stderr[-2000:]
+        res[tag] = dict(np.load(path))
+    for key in res['narrow']:
+        assert np.array_equal(res['narrow'][key], res['wide'][key], equal_nan=True), key
 
 
 def test_anchor_hit_equals_unmorphed_tensor():
