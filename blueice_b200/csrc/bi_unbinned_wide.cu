@@ -8,25 +8,37 @@
 // What differs is the data movement.  With hundreds of rows per event the per-warp tile ring of k_unbinned_mma has room for
 // one 8-point m-tile per warp and one warp per CTA: every 8 points stream all K rows from L2 again.  Here a CTA owns a unit
 // = (point group of <= 64 points of one hypercube cell, superblock range) and its 4 consumer warps (2 m-tiles = 16 points
-// each) SHARE the event tiles.  A tile = 64 events; its K rows arrive in chunks of 32 rows (one 1-D TMA bulk copy per row,
-// issued by the 32 lanes of a fifth, producer warp) through a CTA-wide ring of 6 stages guarded by full / empty mbarriers.
+// each) SHARE the event tiles.  A tile = 64 events; the contraction is cut into chunks of 32 terms, and three producer
+// warps bring one chunk per ring stage with 1-D TMA bulk copies: the 32 rows x 64 events of the tile (B operand, lane r of
+// the first producer copies row r) AND the 64 points x 32 coefficients of the chunk (A operand, one point per lane of the
+// other two), guarded by full / empty mbarriers.  Both operands are then conflict-free LDS.64 (row pitches = 32 B mod
+// 128 B), nothing the consumers need comes from global memory, and a consumer thread holds little more than its accumulators.
 // The DMMA accumulators of a tile (2 m-tiles x 8 octets) stay in registers across the chunks, so the chain over k is the
 // same sequential fma chain (DMMA accumulates in k order, profiles/microbench/dmma_probe_b200.log) however K is cut.
-// A fragments (the points' coefficients) cannot stay in registers for arbitrary K: they are read from global memory
-// (L1 / L2 resident: 64 points x K doubles) one chunk ahead of their use.
+// (First version, profiles/r2_wide_kernel.md: coefficients prefetched from L2 into registers one chunk ahead -- 168
+// registers, 2 CTAs per SM, the prefetched values spilled behind their loads; DMMA sub-pipe 56 % active.)
 //
 // Units are handed out statically (unit u = blockIdx.x + j * gridDim.x of the device schedule, bi_plan.cu), so the
 // producer runs ahead across unit boundaries without talking to the consumers.
+#include <stdlib.h>
+
 #include "bi_unbinned_mma.cuh"
 
 #define BI_WIDE_WARPS 4                 /* consumer warps per CTA */
 #define BI_WIDE_MT 2                    /* 8-point m-tiles per consumer warp */
+#define BI_WIDE_POINTS (8 * BI_WIDE_WARPS * BI_WIDE_MT)
 #define BI_WIDE_TE 64                   /* events per tile (2 canonical groups) */
-#define BI_WIDE_RS (BI_WIDE_TE + 4)     /* row stride: B-fragment loads of the four k-lanes hit distinct banks */
-#define BI_WIDE_KC 32                   /* rows per chunk = one bulk copy per producer lane */
-#define BI_WIDE_STAGES 6
-#define BI_WIDE_THREADS ((BI_WIDE_WARPS + 1) * 32)
-#define BI_WIDE_STAGE_DOUBLES (BI_WIDE_KC * BI_WIDE_RS)
+#define BI_WIDE_RS (BI_WIDE_TE + 4)     /* B row stride: the four k-lanes of a fragment load hit distinct banks */
+#define BI_WIDE_KC 32                   /* terms per chunk */
+#define BI_WIDE_AS (BI_WIDE_KC + 4)     /* A row stride (one row per point); room for the 16-byte alignment shift */
+#ifndef BI_WIDE_STAGES
+#define BI_WIDE_STAGES 3
+#endif
+#define BI_WIDE_PRODUCERS 3             /* producer warps: term rows, coefficient rows of points 0..31, of points 32..63 */
+#define BI_WIDE_THREADS ((BI_WIDE_WARPS + BI_WIDE_PRODUCERS) * 32)
+#define BI_WIDE_B_DOUBLES (BI_WIDE_KC * BI_WIDE_RS)
+#define BI_WIDE_A_DOUBLES (BI_WIDE_POINTS * BI_WIDE_AS)
+#define BI_WIDE_STAGE_DOUBLES (BI_WIDE_B_DOUBLES + BI_WIDE_A_DOUBLES)
 #define BI_WIDE_HEADER_BYTES 128        /* full[STAGES], empty[STAGES] */
 #define BI_WIDE_SMEM_BYTES (BI_WIDE_HEADER_BYTES + BI_WIDE_STAGES * BI_WIDE_STAGE_DOUBLES * 8)
 #define BI_WIDE_OCTETS (BI_WIDE_TE / 8)
@@ -74,26 +86,21 @@ static __device__ __noinline__ double bi_wide_slow_group(const double* __restric
     return __dadd_rn(quad[0], quad[1]);
 }
 
-// coefficients of chunk `ch` for this lane: a[mt][kk] = coef[p_mt, ch * KC + 4 kk + t] (0 beyond K)
-__device__ __forceinline__ void bi_wide_load_a(double (&a)[BI_WIDE_MT][BI_WIDE_KC / 4], const double* const (&coef_p)[BI_WIDE_MT],
-                                               int ch, int K, int t) {
-#pragma unroll
-    for (int kk = 0; kk < BI_WIDE_KC / 4; ++kk) {
-        const int k = ch * BI_WIDE_KC + 4 * kk + t;
-#pragma unroll
-        for (int mt = 0; mt < BI_WIDE_MT; ++mt) a[mt][kk] = (k < K) ? coef_p[mt][k] : 0.0;
-    }
-}
-
-// the DMMAs of one chunk: d[mt][n] += sum over the chunk's k-steps of a[mt][kk] x B(tile rows 4 kk + t, octet n)
-// FULL: all 32 rows of the chunk exist; otherwise k-steps beyond K are skipped and rows beyond K (stale shared memory) read as 0
+// the DMMAs of one chunk: d[mt][n] += sum over the chunk's k-steps of A(point rows, terms 4 kk + t) x B(term rows 4 kk + t,
+// octet n); acol[mt] / bcol point at this lane's first elements.  FULL: all 32 terms of the chunk exist; otherwise k-steps
+// beyond K are skipped and terms beyond K (stale shared memory) read as 0
 template <bool FULL>
-__device__ __forceinline__ void bi_wide_chunk(const double* __restrict__ bcol, const double (&a)[BI_WIDE_MT][BI_WIDE_KC / 4],
+__device__ __forceinline__ void bi_wide_chunk(const double* __restrict__ bcol, const double* const (&acol)[BI_WIDE_MT],
                                               double (&d)[BI_WIDE_MT][BI_WIDE_OCTETS][2], int k_left, int t) {
 #pragma unroll
     for (int kk = 0; kk < BI_WIDE_KC / 4; ++kk) {
         if (!FULL && 4 * kk >= k_left) break;
-        double b[BI_WIDE_OCTETS];
+        double a[BI_WIDE_MT], b[BI_WIDE_OCTETS];
+#pragma unroll
+        for (int mt = 0; mt < BI_WIDE_MT; ++mt) {
+            a[mt] = acol[mt][4 * kk];
+            if (!FULL && 4 * kk + t >= k_left) a[mt] = 0.0;
+        }
 #pragma unroll
         for (int n = 0; n < BI_WIDE_OCTETS; ++n) {
             b[n] = bcol[4 * kk * BI_WIDE_RS + 8 * n];
@@ -102,11 +109,11 @@ __device__ __forceinline__ void bi_wide_chunk(const double* __restrict__ bcol, c
 #pragma unroll
         for (int n = 0; n < BI_WIDE_OCTETS; ++n)
 #pragma unroll
-            for (int mt = 0; mt < BI_WIDE_MT; ++mt) bi_dmma(d[mt][n][0], d[mt][n][1], a[mt][kk], b[n]);
+            for (int mt = 0; mt < BI_WIDE_MT; ++mt) bi_dmma(d[mt][n][0], d[mt][n][1], a[mt], b[n]);
     }
 }
 
-__global__ void __launch_bounds__(BI_WIDE_THREADS, 2)
+__global__ void __maxnreg__(128)
 k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S,
                     const int32_t* __restrict__ group_points, const int4* __restrict__ groups,
                     const int32_t* __restrict__ header, int64_t n_super, const int32_t* __restrict__ row,
@@ -123,7 +130,7 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < BI_WIDE_STAGES; ++i) {
-            bi_mbar_init(&full_bar[i], 1);
+            bi_mbar_init(&full_bar[i], BI_WIDE_PRODUCERS);
             bi_mbar_init(&empty_bar[i], BI_WIDE_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -133,13 +140,23 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
     int st = 0;                 // ring position and its phase bit: the same sequence of (unit, superblock, tile, chunk) on
     unsigned phase = 0;         // the producer and on every consumer warp
 
-    if (warp == BI_WIDE_WARPS) {
-        // ---------------- producer warp: lane r copies row r of the chunk
+    if (warp >= BI_WIDE_WARPS) {
+        // ---------------- producer warps.  A bulk copy is issued lane by lane (its operands are uniform registers), so one
+        // warp issuing the 96 copies of a chunk is slower than the consumers (first version of this layout: 46 % of the
+        // consumers' samples waited for `full`); three warps issue 32 copies each: warp 0 the term rows (lane r = row r),
+        // warps 1 and 2 the coefficient rows of points 0..31 and 32..63.  Each arrives on `full` with its own byte count.
+        const int pw = warp - BI_WIDE_WARPS;
         bool first_lap = true;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int grp = u % n_groups, range = u / n_groups;
-            const int64_t lead = group_points[groups[grp].x];
+            const int4 gp = groups[grp];
+            const int32_t* slot_point = group_points + gp.x;
+            const int64_t lead = slot_point[0];
             const int32_t* row_lead = row + lead * K;                     // every point of the group has these rows
+            // coefficient row of this lane's point: element offset of (point, term 0) in coef; dead slots replay the
+            // group's first point
+            const int slot = lane + 32 * (pw > 0 ? pw - 1 : 0);
+            const int64_t coef_off = (slot < gp.y ? (int64_t)slot_point[slot] : lead) * K;
             const int64_t sb_begin = (int64_t)range * sb_per;
             const int64_t sb_end = sb_begin + sb_per < n_super ? sb_begin + sb_per : n_super;
             for (int64_t sb = sb_begin; sb < sb_end; ++sb) {
@@ -148,16 +165,33 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
                 for (int ti = 0; ti * BI_WIDE_TE < n_ev; ++ti) {
                     const int64_t ev = sb * BI_SUPERBLOCK + (int64_t)ti * BI_WIDE_TE;
                     const int64_t cols = ld - ev < BI_WIDE_TE ? ld - ev : BI_WIDE_TE;      // even (ld is)
-                    const unsigned bytes = (unsigned)cols * (unsigned)sizeof(double);
                     for (int ch = 0; ch < n_chunks; ++ch) {
                         if (!first_lap) bi_mbar_wait(&empty_bar[st], phase ^ 1u);          // the stage's previous use is consumed
-                        const int n_rows = K - ch * BI_WIDE_KC < BI_WIDE_KC ? K - ch * BI_WIDE_KC : BI_WIDE_KC;
+                        const int n_terms = K - ch * BI_WIDE_KC < BI_WIDE_KC ? K - ch * BI_WIDE_KC : BI_WIDE_KC;
+                        double* stage = ring + (size_t)st * BI_WIDE_STAGE_DOUBLES;
+                        const double* src;
+                        double* dst;
+                        unsigned bytes;
+                        if (pw == 0) {
+                            bytes = lane < n_terms ? (unsigned)cols * (unsigned)sizeof(double) : 0u;
+                            src = A + (int64_t)row_lead[ch * BI_WIDE_KC + (lane < n_terms ? lane : 0)] * ld + ev;
+                            dst = stage + (size_t)lane * BI_WIDE_RS;
+                        } else {
+                            // a coefficient row starts at an arbitrary element of coef: copy the enclosing 16-byte aligned
+                            // span (the consumer skips the leading element where the start is odd)
+                            const int64_t o = coef_off + (int64_t)ch * BI_WIDE_KC, end = o + n_terms;
+                            const int64_t first = o & ~(int64_t)1;
+                            bytes = (unsigned)(((end + 1) & ~(int64_t)1) - first) * (unsigned)sizeof(double);
+                            src = coef + first;
+                            dst = stage + BI_WIDE_B_DOUBLES + (size_t)slot * BI_WIDE_AS;
+                        }
+                        unsigned total = bytes;
+#pragma unroll
+                        for (int x = 16; x > 0; x >>= 1) total += __shfl_xor_sync(BI_FULL_MASK, total, x);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        if (lane == 0) bi_mbar_expect_tx(&full_bar[st], bytes * (unsigned)n_rows);
+                        if (lane == 0) bi_mbar_expect_tx(&full_bar[st], total);
                         __syncwarp();
-                        if (lane < n_rows)
-                            bi_bulk_g2s(ring + (size_t)st * BI_WIDE_STAGE_DOUBLES + (size_t)lane * BI_WIDE_RS,
-                                        A + (int64_t)row_lead[ch * BI_WIDE_KC + lane] * ld + ev, bytes, &full_bar[st]);
+                        if (bytes) bi_bulk_g2s(dst, src, bytes, &full_bar[st]);
                         if (++st == BI_WIDE_STAGES) { st = 0; phase ^= 1u; first_lap = false; }
                     }
                 }
@@ -178,16 +212,15 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
         const bool warp_active = warp * BI_WIDE_MT * 8 < n_pts;           // warp-uniform
         bool live[BI_WIDE_MT];
         int64_t p_slot[BI_WIDE_MT];
-        const double* coef_p[BI_WIDE_MT];
+        int a_off[BI_WIDE_MT];                                            // this lane's first coefficient inside a stage
 #pragma unroll
         for (int mt = 0; mt < BI_WIDE_MT; ++mt) {
             const int idx = (warp * BI_WIDE_MT + mt) * 8 + g;
             live[mt] = idx < n_pts;
             p_slot[mt] = live[mt] ? (int64_t)slot_point[idx] : lead;      // dead slots replay the group's first point
-            coef_p[mt] = coef + p_slot[mt] * K;
+            // the producer copied the row from the even element at or below (point, term 32 ch): skip one where that is odd
+            a_off[mt] = BI_WIDE_B_DOUBLES + idx * BI_WIDE_AS + (int)((p_slot[mt] * K) & 1) + t;
         }
-        double a_next[BI_WIDE_MT][BI_WIDE_KC / 4];
-        if (warp_active) bi_wide_load_a(a_next, coef_p, 0, K, t);
 
         const int64_t sb_begin = (int64_t)range * sb_per;
         const int64_t sb_end = sb_begin + sb_per < n_super ? sb_begin + sb_per : n_super;
@@ -208,21 +241,16 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
 
 #pragma unroll 1
                 for (int ch = 0; ch < n_chunks; ++ch) {
-                    double a[BI_WIDE_MT][BI_WIDE_KC / 4];
-                    if (warp_active) {
-#pragma unroll
-                        for (int mt = 0; mt < BI_WIDE_MT; ++mt)
-#pragma unroll
-                            for (int kk = 0; kk < BI_WIDE_KC / 4; ++kk) a[mt][kk] = a_next[mt][kk];
-                        // the coefficients of the chunk after this one (the chunks of every tile cycle 0 .. n_chunks - 1)
-                        bi_wide_load_a(a_next, coef_p, ch + 1 < n_chunks ? ch + 1 : 0, K, t);
-                    }
                     bi_mbar_wait(&full_bar[st], phase);
                     if (warp_active) {
-                        const double* bcol = ring + (size_t)st * BI_WIDE_STAGE_DOUBLES + t * BI_WIDE_RS + g;
+                        const double* stage = ring + (size_t)st * BI_WIDE_STAGE_DOUBLES;
+                        const double* bcol = stage + t * BI_WIDE_RS + g;
+                        const double* acol[BI_WIDE_MT];
+#pragma unroll
+                        for (int mt = 0; mt < BI_WIDE_MT; ++mt) acol[mt] = stage + a_off[mt];
                         const int k_left = K - ch * BI_WIDE_KC;
-                        if (k_left >= BI_WIDE_KC) bi_wide_chunk<true>(bcol, a, d, k_left, t);
-                        else bi_wide_chunk<false>(bcol, a, d, k_left, t);
+                        if (k_left >= BI_WIDE_KC) bi_wide_chunk<true>(bcol, acol, d, k_left, t);
+                        else bi_wide_chunk<false>(bcol, acol, d, k_left, t);
                     }
                     __syncwarp();
                     if (lane == 0) bi_mbar_arrive(&empty_bar[st]);        // this warp is done with the stage
@@ -311,9 +339,12 @@ int bi_launch_mma_wide(const double* A, int64_t ld, int64_t N, int K, int S, con
         BI_CUDA_CHECK(cudaGetDevice(&dev));
         BI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         BI_CUDA_CHECK(cudaFuncSetAttribute(k_unbinned_mma_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, BI_WIDE_SMEM_BYTES));
+        BI_CUDA_CHECK(cudaFuncSetAttribute(k_unbinned_mma_wide, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
         BI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unbinned_mma_wide, BI_WIDE_THREADS, BI_WIDE_SMEM_BYTES));
         BI_REQUIRE(per_sm >= 1, "k_unbinned_mma_wide does not fit on this device");
         blocks = sms * per_sm;
+        if (getenv("BI_WIDE_VERBOSE")) fprintf(stderr, "k_unbinned_mma_wide: %d CTAs per SM, %d bytes of shared memory\n", per_sm, BI_WIDE_SMEM_BYTES);
     }
     k_unbinned_mma_wide<<<(unsigned)blocks, BI_WIDE_THREADS, BI_WIDE_SMEM_BYTES, st>>>(
         A, ld, N, K, S, group_points, reinterpret_cast<const int4*>(groups), header, n_super, row, coef, wterm, term_source,
@@ -322,4 +353,4 @@ int bi_launch_mma_wide(const double* A, int64_t ld, int64_t N, int K, int S, con
     return BI_OK;
 }
 
-int bi_mma_wide_unit_points(void) { return 8 * BI_WIDE_WARPS * BI_WIDE_MT; }
+int bi_mma_wide_unit_points(void) { return BI_WIDE_POINTS; }

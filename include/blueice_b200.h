@@ -187,6 +187,8 @@ int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_po
  * Contractions of more than 128 terms run the K-chunk form of the kernel (k_unbinned_mma_wide: a CTA's four warps share
  * event tiles whose rows arrive in chunks of 32 through a CTA-wide TMA ring, accumulators carried across the chunks:
  * the same sequential fma chain over k); units are then (group, range) pairs taken in launch order, no counters used.
+ * That kernel copies coefficient rows in 16-byte aligned spans: coef_dev must be readable up to the next 16-byte boundary
+ * behind its last element (any allocation is).
  */
 #define BI_MMA_MAX_TERMS 4096
 int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t n_events,
