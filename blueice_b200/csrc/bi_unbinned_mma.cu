@@ -10,8 +10,9 @@
 int bi_launch_mma_wide(const double* A, int64_t ld, int64_t N, int K, int S, const int32_t* group_points,
                        int32_t* groups, int32_t* header, int64_t n_super, const int32_t* row, const double* coef,
                        const double* wterm, const int32_t* term_source, const double* mus, double outlier,
-                       double* partial, cudaStream_t st);
+                       double* partial, int64_t n_points, double* coef_chunks, cudaStream_t st);
 int bi_mma_wide_unit_points(void);
+int64_t bi_mma_wide_scratch_doubles(int K, int64_t n_points);
 
 #define BI_MMA_WIDE_MIN_TERMS_DEFAULT 49
 
@@ -81,7 +82,7 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
                                         const int32_t* term_source_dev, const double* mus_dev,
                                         double outlier_likelihood, double* partial_dev,
                                         int32_t grid_dims, const int32_t* n_anchors_host, const int32_t* cell_dev,
-                                        void* stream) {
+                                        int64_t n_points, double* coef_chunks_dev, void* stream) {
     BI_REQUIRE(n_events >= 0, "n_events < 0");
     const int64_t n_super = bi_num_superblocks(n_events);
     if (n_super == 0) return BI_OK;
@@ -100,7 +101,7 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
     if (bi_mma_use_wide(n_terms))
         return bi_launch_mma_wide(rows_dev, ld_events, n_events, n_terms, n_sources, group_points_dev, groups_dev, header_dev,
                                   n_super, row_dev, coef_dev, wterm_dev, term_source_dev, mus_dev, outlier_likelihood,
-                                  partial_dev, st);
+                                  partial_dev, n_points, coef_chunks_dev, st);
     const int k4 = bi_mma_k4(n_terms);
     // full-grid layout ([G][S][ld], term k = corner * S + source): one tiled TMA instruction per event tile
     alignas(64) CUtensorMap tmap;
@@ -124,6 +125,11 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
     return BI_ERR_UNSUPPORTED;
 }
 
+extern "C" int64_t bi_mma_coef_chunks_doubles(int32_t n_terms, int64_t n_points) {
+    if (n_terms < 1 || n_points < 0 || !bi_mma_use_wide(n_terms)) return 0;
+    return bi_mma_wide_scratch_doubles(n_terms, n_points);
+}
+
 extern "C" int32_t bi_mma_unit_points(int32_t n_terms) {
     if (bi_mma_use_wide(n_terms)) return bi_mma_wide_unit_points();
     const int k4 = bi_mma_k4(n_terms);
@@ -136,9 +142,10 @@ extern "C" int32_t bi_mma_unit_points(int32_t n_terms) {
 static inline int64_t bi_align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 struct BiUnbinnedWorkspace {
-    int64_t cell, frac, corner, weight, mus, partial, group_points, groups, header, row, coef, wterm, term_source, total;
+    int64_t cell, frac, corner, weight, mus, partial, group_points, groups, header, row, coef, wterm, term_source,
+        coef_chunks, total;
 };
-#define BI_WORKSPACE_REGIONS 14
+#define BI_WORKSPACE_REGIONS 15
 
 static BiUnbinnedWorkspace bi_unbinned_layout(int32_t D, int32_t S, int64_t K, int64_t P, int64_t n_events) {
     const int64_t C = (int64_t)1 << D, Dd = D > 0 ? D : 1, n_super = bi_num_superblocks(n_events);
@@ -157,6 +164,7 @@ static BiUnbinnedWorkspace bi_unbinned_layout(int32_t D, int32_t S, int64_t K, i
     w.coef = o;         o += bi_align256(P * K * 8);
     w.wterm = o;        o += bi_align256(P * K * 8);
     w.term_source = o;  o += bi_align256(K * 4);
+    w.coef_chunks = o;  o += bi_align256(bi_mma_coef_chunks_doubles((int32_t)K, P) * 8);   // K-chunk kernel only
     w.total = o;
     return w;
 }
@@ -167,14 +175,15 @@ extern "C" int64_t bi_unbinned_workspace_bytes(int32_t n_dims, int32_t n_sources
     return bi_unbinned_layout(n_dims, n_sources, n_terms, n_points, n_events).total;
 }
 
-// offsets (bytes) of the workspace regions, in the order of BiUnbinnedWorkspace (14 entries incl. the total)
+// offsets (bytes) of the workspace regions, in the order of BiUnbinnedWorkspace (15 entries incl. the total)
 extern "C" int bi_unbinned_workspace_layout(int32_t n_dims, int32_t n_sources, int32_t n_terms, int64_t n_points,
                                             int64_t n_events, int64_t* offsets_host) {
     BI_REQUIRE(offsets_host && n_dims >= 0 && n_dims <= BI_MAX_DIMS && n_sources >= 1 && n_terms >= 1 && n_points >= 0 &&
                    n_events >= 0, "bi_unbinned_workspace_layout: bad arguments");
     const BiUnbinnedWorkspace w = bi_unbinned_layout(n_dims, n_sources, n_terms, n_points, n_events);
     const int64_t v[BI_WORKSPACE_REGIONS] = {w.cell, w.frac, w.corner, w.weight, w.mus, w.partial, w.group_points,
-                                             w.groups, w.header, w.row, w.coef, w.wterm, w.term_source, w.total};
+                                             w.groups, w.header, w.row, w.coef, w.wterm, w.term_source, w.coef_chunks,
+                                             w.total};
     for (int i = 0; i < BI_WORKSPACE_REGIONS; ++i) offsets_host[i] = v[i];
     return BI_OK;
 }
@@ -198,7 +207,8 @@ static int bi_unbinned_after_setup(int32_t n_dims, const int32_t* n_anchors_host
                                       (int32_t*)(base + w.header), (int32_t*)(base + w.row), (double*)(base + w.coef),
                                       (double*)(base + w.wterm), (int32_t*)(base + w.term_source),
                                       (double*)(base + w.mus), outlier_likelihood, partial,
-                                      full_grid ? n_dims : -1, n_anchors_host, (int32_t*)(base + w.cell), stream);
+                                      full_grid ? n_dims : -1, n_anchors_host, (int32_t*)(base + w.cell), n_points,
+                                      (double*)(base + w.coef_chunks), stream);
         if (rc != BI_OK) return rc;
     }
     return bi_unbinned_finalize(partial, n_super, musum_dev, status_dev, n_points, logl_dev, logsum_dev, stream);

@@ -8,15 +8,18 @@
 // What differs is the data movement.  With hundreds of rows per event the per-warp tile ring of k_unbinned_mma has room for
 // one 8-point m-tile per warp and one warp per CTA: every 8 points stream all K rows from L2 again.  Here a CTA owns a unit
 // = (point group of <= 64 points of one hypercube cell, superblock range) and its 4 consumer warps (2 m-tiles = 16 points
-// each) SHARE the event tiles.  A tile = 64 events; the contraction is cut into chunks of 32 terms, and three producer
-// warps bring one chunk per ring stage with 1-D TMA bulk copies: the 32 rows x 64 events of the tile (B operand, lane r of
-// the first producer copies row r) AND the 64 points x 32 coefficients of the chunk (A operand, one point per lane of the
-// other two), guarded by full / empty mbarriers.  Both operands are then conflict-free LDS.64 (row pitches = 32 B mod
-// 128 B), nothing the consumers need comes from global memory, and a consumer thread holds little more than its accumulators.
+// each) SHARE the event tiles.  A tile = 64 events; the contraction is cut into chunks of 32 terms, and a fifth, producer
+// warp brings one chunk per ring stage with 1-D TMA bulk copies: the 32 rows x 64 events of the tile (B operand, lane r
+// copies row r) and the 64 points x 32 coefficients of the chunk (A operand) -- ONE copy, because k_wide_pack_coef has
+// laid the coefficients out chunk-major in the order of the schedule ([chunk][slot][36], zero beyond K), so the rows of a
+// unit's points are one contiguous block.  Both operands are then conflict-free LDS.64 (row pitches = 32 B mod 128 B),
+// nothing the consumers need comes from global memory, a consumer thread holds little more than its accumulators
+// (128 registers), and with a 2-stage ring three CTAs = 12 consumer warps share an SM.
 // The DMMA accumulators of a tile (2 m-tiles x 8 octets) stay in registers across the chunks, so the chain over k is the
 // same sequential fma chain (DMMA accumulates in k order, profiles/microbench/dmma_probe_b200.log) however K is cut.
-// (First version, profiles/r2_wide_kernel.md: coefficients prefetched from L2 into registers one chunk ahead -- 168
-// registers, 2 CTAs per SM, the prefetched values spilled behind their loads; DMMA sub-pipe 56 % active.)
+// History (profiles/r2_wide_kernel.md): coefficients prefetched from L2 into registers, 2 CTAs / SM: 18 TFLOP/s at
+// K = 160; coefficient rows copied point by point by one producer warp: the producer (a bulk copy is issued lane by lane)
+// could not keep up; by three producer warps, 2 CTAs / SM: 23.5-27 TFLOP/s.
 //
 // Units are handed out statically (unit u = blockIdx.x + j * gridDim.x of the device schedule, bi_plan.cu), so the
 // producer runs ahead across unit boundaries without talking to the consumers.
@@ -30,11 +33,11 @@
 #define BI_WIDE_TE 64                   /* events per tile (2 canonical groups) */
 #define BI_WIDE_RS (BI_WIDE_TE + 4)     /* B row stride: the four k-lanes of a fragment load hit distinct banks */
 #define BI_WIDE_KC 32                   /* terms per chunk */
-#define BI_WIDE_AS (BI_WIDE_KC + 4)     /* A row stride (one row per point); room for the 16-byte alignment shift */
+#define BI_WIDE_AS (BI_WIDE_KC + 4)     /* A row stride (one row per point) */
 #ifndef BI_WIDE_STAGES
-#define BI_WIDE_STAGES 3
+#define BI_WIDE_STAGES 2
 #endif
-#define BI_WIDE_PRODUCERS 3             /* producer warps: term rows, coefficient rows of points 0..31, of points 32..63 */
+#define BI_WIDE_PRODUCERS 1
 #define BI_WIDE_THREADS ((BI_WIDE_WARPS + BI_WIDE_PRODUCERS) * 32)
 #define BI_WIDE_B_DOUBLES (BI_WIDE_KC * BI_WIDE_RS)
 #define BI_WIDE_A_DOUBLES (BI_WIDE_POINTS * BI_WIDE_AS)
@@ -86,6 +89,26 @@ static __device__ __noinline__ double bi_wide_slow_group(const double* __restric
     return __dadd_rn(quad[0], quad[1]);
 }
 
+// coefficients in the order the K-chunk kernel reads them: out[chunk][slot][36] = coef[group_points[slot]][32 chunk + j]
+// for j < 32 and terms below K, 0 otherwise (pad columns, terms beyond K, slots beyond the evaluable points: a unit always
+// copies 64 rows).  One warp per (chunk, slot).
+__global__ void __launch_bounds__(256)
+k_wide_pack_coef(const double* __restrict__ coef, const int32_t* __restrict__ group_points,
+                 const int32_t* __restrict__ header, int K, int64_t n_slots, int n_chunks, double* __restrict__ out) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_slots * n_chunks) return;
+    const int ch = (int)(w / n_slots);
+    const int64_t slot = w - (int64_t)ch * n_slots;
+    const int n_eval = header[5];
+    const int k = ch * BI_WIDE_KC + lane;
+    double v = 0.0;
+    if (slot < n_eval && k < K) v = coef[(int64_t)group_points[slot] * K + k];
+    double* dst = out + w * BI_WIDE_AS;
+    dst[lane] = v;
+    if (lane < BI_WIDE_AS - BI_WIDE_KC) dst[BI_WIDE_KC + lane] = 0.0;
+}
+
 // the DMMAs of one chunk: d[mt][n] += sum over the chunk's k-steps of A(point rows, terms 4 kk + t) x B(term rows 4 kk + t,
 // octet n); acol[mt] / bcol point at this lane's first elements.  FULL: all 32 terms of the chunk exist; otherwise k-steps
 // beyond K are skipped and terms beyond K (stale shared memory) read as 0
@@ -98,8 +121,7 @@ __device__ __forceinline__ void bi_wide_chunk(const double* __restrict__ bcol, c
         double a[BI_WIDE_MT], b[BI_WIDE_OCTETS];
 #pragma unroll
         for (int mt = 0; mt < BI_WIDE_MT; ++mt) {
-            a[mt] = acol[mt][4 * kk];
-            if (!FULL && 4 * kk + t >= k_left) a[mt] = 0.0;
+            a[mt] = acol[mt][4 * kk];                                     // packed with zeros beyond K
         }
 #pragma unroll
         for (int n = 0; n < BI_WIDE_OCTETS; ++n) {
@@ -117,7 +139,7 @@ __global__ void __maxnreg__(128)
 k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, int S,
                     const int32_t* __restrict__ group_points, const int4* __restrict__ groups,
                     const int32_t* __restrict__ header, int64_t n_super, const int32_t* __restrict__ row,
-                    const double* __restrict__ coef, const double* __restrict__ wterm,
+                    const double* __restrict__ coef_chunks, int64_t n_slots, const double* __restrict__ wterm,
                     const int32_t* __restrict__ term_source, const double* __restrict__ mus, double outlier,
                     double* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char bi_wide_smem[];
@@ -141,22 +163,14 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
     unsigned phase = 0;         // the producer and on every consumer warp
 
     if (warp >= BI_WIDE_WARPS) {
-        // ---------------- producer warps.  A bulk copy is issued lane by lane (its operands are uniform registers), so one
-        // warp issuing the 96 copies of a chunk is slower than the consumers (first version of this layout: 46 % of the
-        // consumers' samples waited for `full`); three warps issue 32 copies each: warp 0 the term rows (lane r = row r),
-        // warps 1 and 2 the coefficient rows of points 0..31 and 32..63.  Each arrives on `full` with its own byte count.
-        const int pw = warp - BI_WIDE_WARPS;
+        // ---------------- producer warp: lane r copies term row r of the chunk, lane 0 also the unit's coefficient block
         bool first_lap = true;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int grp = u % n_groups, range = u / n_groups;
             const int4 gp = groups[grp];
-            const int32_t* slot_point = group_points + gp.x;
-            const int64_t lead = slot_point[0];
+            const int64_t lead = group_points[gp.x];
             const int32_t* row_lead = row + lead * K;                     // every point of the group has these rows
-            // coefficient row of this lane's point: element offset of (point, term 0) in coef; dead slots replay the
-            // group's first point
-            const int slot = lane + 32 * (pw > 0 ? pw - 1 : 0);
-            const int64_t coef_off = (slot < gp.y ? (int64_t)slot_point[slot] : lead) * K;
+            const double* a_src = coef_chunks + (int64_t)gp.x * BI_WIDE_AS;   // + chunk * n_slots * AS
             const int64_t sb_begin = (int64_t)range * sb_per;
             const int64_t sb_end = sb_begin + sb_per < n_super ? sb_begin + sb_per : n_super;
             for (int64_t sb = sb_begin; sb < sb_end; ++sb) {
@@ -165,33 +179,21 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
                 for (int ti = 0; ti * BI_WIDE_TE < n_ev; ++ti) {
                     const int64_t ev = sb * BI_SUPERBLOCK + (int64_t)ti * BI_WIDE_TE;
                     const int64_t cols = ld - ev < BI_WIDE_TE ? ld - ev : BI_WIDE_TE;      // even (ld is)
+                    const unsigned b_bytes = (unsigned)cols * (unsigned)sizeof(double);
                     for (int ch = 0; ch < n_chunks; ++ch) {
                         if (!first_lap) bi_mbar_wait(&empty_bar[st], phase ^ 1u);          // the stage's previous use is consumed
                         const int n_terms = K - ch * BI_WIDE_KC < BI_WIDE_KC ? K - ch * BI_WIDE_KC : BI_WIDE_KC;
                         double* stage = ring + (size_t)st * BI_WIDE_STAGE_DOUBLES;
-                        const double* src;
-                        double* dst;
-                        unsigned bytes;
-                        if (pw == 0) {
-                            bytes = lane < n_terms ? (unsigned)cols * (unsigned)sizeof(double) : 0u;
-                            src = A + (int64_t)row_lead[ch * BI_WIDE_KC + (lane < n_terms ? lane : 0)] * ld + ev;
-                            dst = stage + (size_t)lane * BI_WIDE_RS;
-                        } else {
-                            // a coefficient row starts at an arbitrary element of coef: copy the enclosing 16-byte aligned
-                            // span (the consumer skips the leading element where the start is odd)
-                            const int64_t o = coef_off + (int64_t)ch * BI_WIDE_KC, end = o + n_terms;
-                            const int64_t first = o & ~(int64_t)1;
-                            bytes = (unsigned)(((end + 1) & ~(int64_t)1) - first) * (unsigned)sizeof(double);
-                            src = coef + first;
-                            dst = stage + BI_WIDE_B_DOUBLES + (size_t)slot * BI_WIDE_AS;
-                        }
-                        unsigned total = bytes;
-#pragma unroll
-                        for (int x = 16; x > 0; x >>= 1) total += __shfl_xor_sync(BI_FULL_MASK, total, x);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        if (lane == 0) bi_mbar_expect_tx(&full_bar[st], total);
+                        if (lane == 0) {
+                            bi_mbar_expect_tx(&full_bar[st], b_bytes * (unsigned)n_terms + BI_WIDE_A_DOUBLES * 8u);
+                            bi_bulk_g2s(stage + BI_WIDE_B_DOUBLES, a_src + (int64_t)ch * n_slots * BI_WIDE_AS,
+                                        BI_WIDE_A_DOUBLES * 8u, &full_bar[st]);
+                        }
                         __syncwarp();
-                        if (bytes) bi_bulk_g2s(dst, src, bytes, &full_bar[st]);
+                        if (lane < n_terms)
+                            bi_bulk_g2s(stage + (size_t)lane * BI_WIDE_RS,
+                                        A + (int64_t)row_lead[ch * BI_WIDE_KC + lane] * ld + ev, b_bytes, &full_bar[st]);
                         if (++st == BI_WIDE_STAGES) { st = 0; phase ^= 1u; first_lap = false; }
                     }
                 }
@@ -218,8 +220,7 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
             const int idx = (warp * BI_WIDE_MT + mt) * 8 + g;
             live[mt] = idx < n_pts;
             p_slot[mt] = live[mt] ? (int64_t)slot_point[idx] : lead;      // dead slots replay the group's first point
-            // the producer copied the row from the even element at or below (point, term 32 ch): skip one where that is odd
-            a_off[mt] = BI_WIDE_B_DOUBLES + idx * BI_WIDE_AS + (int)((p_slot[mt] * K) & 1) + t;
+            a_off[mt] = BI_WIDE_B_DOUBLES + idx * BI_WIDE_AS + t;
         }
 
         const int64_t sb_begin = (int64_t)range * sb_per;
@@ -327,12 +328,21 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// launcher (called by bi_unbinned_partials_mma for n_terms > 128)
+// launcher (called by bi_unbinned_partials_mma for long contractions)
 // ---------------------------------------------------------------------------------------------
+// doubles of the chunk-major coefficient copy for a batch of n_points points
+int64_t bi_mma_wide_scratch_doubles(int K, int64_t n_points) {
+    const int64_t n_chunks = (K + BI_WIDE_KC - 1) / BI_WIDE_KC;
+    return n_chunks * (n_points + BI_WIDE_POINTS) * BI_WIDE_AS;
+}
+
 int bi_launch_mma_wide(const double* A, int64_t ld, int64_t N, int K, int S, const int32_t* group_points,
                        int32_t* groups, int32_t* header, int64_t n_super, const int32_t* row, const double* coef,
                        const double* wterm, const int32_t* term_source, const double* mus, double outlier,
-                       double* partial, cudaStream_t st) {
+                       double* partial, int64_t n_points, double* coef_chunks, cudaStream_t st) {
+    BI_REQUIRE(coef_chunks && n_points >= 1, "bi_unbinned_partials_mma: contractions of %d terms need n_points and "
+               "coef_chunks_dev (bi_mma_coef_chunks_doubles(n_terms, n_points) doubles)", K);
+    BI_REQUIRE(((uintptr_t)coef_chunks & 15) == 0, "coef_chunks_dev must be 16-byte aligned");
     static int blocks = 0;
     if (!blocks) {
         int dev = 0, sms = 0, per_sm = 0;
@@ -346,9 +356,15 @@ int bi_launch_mma_wide(const double* A, int64_t ld, int64_t N, int K, int S, con
         blocks = sms * per_sm;
         if (getenv("BI_WIDE_VERBOSE")) fprintf(stderr, "k_unbinned_mma_wide: %d CTAs per SM, %d bytes of shared memory\n", per_sm, BI_WIDE_SMEM_BYTES);
     }
+    const int n_chunks = (K + BI_WIDE_KC - 1) / BI_WIDE_KC;
+    const int64_t n_slots = n_points + BI_WIDE_POINTS;
+    const int64_t pack_warps = n_slots * n_chunks;
+    k_wide_pack_coef<<<(unsigned)((pack_warps * 32 + 255) / 256), 256, 0, st>>>(coef, group_points, header, K, n_slots, n_chunks,
+                                                                               coef_chunks);
+    BI_LAUNCH_CHECK();
     k_unbinned_mma_wide<<<(unsigned)blocks, BI_WIDE_THREADS, BI_WIDE_SMEM_BYTES, st>>>(
-        A, ld, N, K, S, group_points, reinterpret_cast<const int4*>(groups), header, n_super, row, coef, wterm, term_source,
-        mus, outlier, partial);
+        A, ld, N, K, S, group_points, reinterpret_cast<const int4*>(groups), header, n_super, row, coef_chunks, n_slots,
+        wterm, term_source, mus, outlier, partial);
     BI_LAUNCH_CHECK();
     return BI_OK;
 }

@@ -317,15 +317,16 @@ class UnbinnedEngine(_EngineBase):
         """(workspace tensor, dict of typed device views) for a P-point batch of the fused path."""
         torch = self.torch
         D, S = self.grid.n_dims, self.n_sources
-        off = np.zeros(14, dtype=np.int64)
+        off = np.zeros(15, dtype=np.int64)
         _cabi.check(self.lib.bi_unbinned_workspace_layout(D, S, self.n_terms, P, self.n_events, _cabi.host_ptr(off)),
                     "bi_unbinned_workspace_layout")
-        ws = self.ws.get("mma_ws", int(off[13]), torch.uint8)
+        ws = self.ws.get("mma_ws", int(off[14]), torch.uint8)
         names = ["cell", "frac", "corner", "weight", "mus", "partial", "group_points", "groups", "header",
-                 "row", "coef", "wterm", "term_source"]
+                 "row", "coef", "wterm", "term_source", "coef_chunks"]
         dtypes = [torch.int32, torch.float64, torch.int32, torch.float64, torch.float64, torch.float64,
-                  torch.int32, torch.int32, torch.int32, torch.int32, torch.float64, torch.float64, torch.int32]
-        views = {}
+                  torch.int32, torch.int32, torch.int32, torch.int32, torch.float64, torch.float64, torch.int32,
+                  torch.float64]
+        views = {"n_points": P}
         for i, (name, dt) in enumerate(zip(names, dtypes)):
             views[name] = ws[int(off[i]):int(off[i + 1])].view(dt)
         return ws, views
@@ -347,7 +348,8 @@ class UnbinnedEngine(_EngineBase):
             _cabi.dev_ptr(views["row"]), _cabi.dev_ptr(views["coef"]), _cabi.dev_ptr(views["wterm"]),
             _cabi.dev_ptr(views["term_source"]), _cabi.dev_ptr(views["mus"]), self.outlier_likelihood,
             _cabi.dev_ptr(views["partial"]), self.grid.n_dims if self.full_grid_layout else -1,
-            _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.dev_ptr(views["cell"]), self._stream()),
+            _cabi.host_ptr(self.grid.n_anchors_i32), _cabi.dev_ptr(views["cell"]), views["n_points"],
+            _cabi.dev_ptr(views["coef_chunks"]), self._stream()),
             "bi_unbinned_partials_mma")
 
     def _small_ok(self, P):
@@ -504,10 +506,10 @@ class UnbinnedEngine(_EngineBase):
             views.append(st["dev_in"][o:o + n] if n else None)
             o += n
         st["n_in"] = n_in
-        off = np.zeros(14, dtype=np.int64)
+        off = np.zeros(15, dtype=np.int64)
         _cabi.check(self.lib.bi_unbinned_workspace_layout(D, S, self.n_terms, P, self.n_events, _cabi.host_ptr(off)),
                     "bi_unbinned_workspace_layout")
-        st["ws"] = torch.empty(int(off[13]), dtype=torch.uint8, device=self.device)
+        st["ws"] = torch.empty(int(off[14]), dtype=torch.uint8, device=self.device)
         st["out_f"] = torch.empty(3 * P, dtype=torch.float64, device=self.device)      # logl | logsum | musum
         st["out_i"] = torch.empty(P, dtype=torch.int32, device=self.device)
         st["pin_f"] = torch.empty(3 * P, dtype=torch.float64, pin_memory=True)

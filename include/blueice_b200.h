@@ -187,8 +187,10 @@ int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_po
  * Contractions of more than 128 terms run the K-chunk form of the kernel (k_unbinned_mma_wide: a CTA's four warps share
  * event tiles whose rows arrive in chunks of 32 through a CTA-wide TMA ring, accumulators carried across the chunks:
  * the same sequential fma chain over k); units are then (group, range) pairs taken in launch order, no counters used.
- * That kernel copies coefficient rows in 16-byte aligned spans: coef_dev must be readable up to the next 16-byte boundary
- * behind its last element (any allocation is).
+ * That kernel reads the coefficients from a chunk-major copy in schedule order which the call writes first
+ * (k_wide_pack_coef): coef_chunks_dev must hold bi_mma_coef_chunks_doubles(n_terms, n_points) doubles (0 for short
+ * contractions: the pointer may then be NULL), 16-byte aligned; n_points = points of the batch (>= every index in
+ * group_points_dev + 1 is not required: it sizes the copy, header_dev[5] <= n_points evaluable points are packed).
  */
 #define BI_MMA_MAX_TERMS 4096
 int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t n_events,
@@ -197,8 +199,10 @@ int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t 
                              const int32_t* row_dev, const double* coef_dev, const double* wterm_dev,
                              const int32_t* term_source_dev, const double* mus_dev,
                              double outlier_likelihood, double* partial_dev,
-                             int32_t grid_dims, const int32_t* n_anchors_host, const int32_t* cell_dev, void* stream);
+                             int32_t grid_dims, const int32_t* n_anchors_host, const int32_t* cell_dev,
+                             int64_t n_points, double* coef_chunks_dev, void* stream);
 int32_t bi_mma_unit_points(int32_t n_terms);
+int64_t bi_mma_coef_chunks_doubles(int32_t n_terms, int64_t n_points);
 
 /*
  * The whole unbinned hot path in ONE call: K1 point set-up -> device-side schedule -> K2 (DMMA) ->
@@ -211,7 +215,7 @@ int32_t bi_mma_unit_points(int32_t n_terms);
 int64_t bi_unbinned_workspace_bytes(int32_t n_dims, int32_t n_sources, int32_t n_terms, int64_t n_points,
                                     int64_t n_events);
 /* byte offsets of the workspace regions: cell, frac, corner, weight, mus, partial, group_points, groups,
- * header, row, coef, wterm, term_source, total (14 int64) -- lets a caller run / inspect the stages separately */
+ * header, row, coef, wterm, term_source, coef_chunks, total (15 int64) -- lets a caller run / inspect the stages separately */
 int bi_unbinned_workspace_layout(int32_t n_dims, int32_t n_sources, int32_t n_terms, int64_t n_points,
                                  int64_t n_events, int64_t* offsets_host);
 int bi_unbinned_ll_batch(int32_t n_dims, const int32_t* n_anchors_host, const double* axes_host,
