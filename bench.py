@@ -441,6 +441,66 @@ def sharded_summary(world, P, n_events, e2e_obj, strong, other):
     return out
 
 
+def long_contraction_scan(device, steps):
+    """Config-2-shaped scan of a model whose contraction is long: 5 shape parameters x 3 anchors (243 anchors, 32 corners
+    per hypercube cell) x 5 sources = 160 terms per point-event, 4096 points over 5e4 events (synthetic per-event pdf
+    tensor, filled on the device).  Such contractions run the K-chunk DMMA kernel (k_unbinned_mma_wide); round 2 started
+    with the streaming kernel here (one pass over the cell's 160 rows per POINT)."""
+    import torch
+    from blueice_b200.engine import MorphGrid, UnbinnedEngine
+    D, S, N, P = 5, 5, 50000, 4096
+    rng = np.random.default_rng(7)
+    axes = [np.sort(rng.uniform(-2, 2, 3)) for _ in range(D)]
+    eng = UnbinnedEngine(MorphGrid(axes), rng.uniform(5, 500, (3 ** D, S)), device=device)
+    eng.allocate_ps_anchor(N)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(7)
+    eng.ps_anchor.copy_(torch.exp(torch.randn(eng.ps_anchor.shape, generator=gen, device=device, dtype=torch.float64) * 2 - 4))
+    zs = np.column_stack([rng.uniform(a[0], a[-1], P) for a in axes])
+    mult = rng.uniform(0.5, 2, (P, S))
+    z_d, m_d, _, _, _ = eng._upload_points(zs, mult, None, None)
+    z_d, m_d = z_d.clone(), m_d.clone()
+    outs = eng.run_fused(P, z_d, m_d, None, None)
+    _, v = eng.mma_workspace(P)
+    torch.cuda.synchronize()
+    finite = bool(torch.isfinite(outs["logl"]).all())
+    n = max(steps, 5)
+    whole, k2 = [], []
+    for _ in range(2 + n):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        eng.run_fused(P, z_d, m_d, None, None)                     # K1 -> schedule -> pack -> K2 -> finalize
+        b.record()
+        eng.mma_plan(P, v, outs["status"])
+        torch.cuda.synchronize()
+        a2 = torch.cuda.Event(enable_timing=True)
+        a2.record()
+        eng.mma_k2(v)                                              # pack + K2 alone
+        c.record()
+        torch.cuda.synchronize()
+        whole.append(a.elapsed_time(b))
+        k2.append(a2.elapsed_time(c))
+    whole, k2 = float(np.mean(whole[2:])), float(np.mean(k2[2:]))
+    K = S << D
+    flops = 2.0 * K * P * N
+    r = eng.evaluate(zs[:64], mult[:64])
+    eng.force_kernel = 'stream'
+    t0 = time.perf_counter()
+    r_s = eng.evaluate(zs[:64], mult[:64])
+    torch.cuda.synchronize()
+    stream_s = time.perf_counter() - t0
+    eng.force_kernel = None
+    return {"workload": "4096-point scan, 5 shape parameters x 3 anchors x 5 sources = %d contraction terms, %d events "
+                        "(synthetic per-event pdf tensor, %.0f MB)" % (K, N, eng.ps_anchor.numel() * 8 / 1e6),
+            "kernel": "k_wide_pack_coef + k_unbinned_mma_wide (K-chunk loop: CTA-shared event tiles, both DMMA operands "
+                      "staged by TMA bulk copies, accumulators carried across the chunks)",
+            "n_terms": K, "n_events": N, "n_points": P, "evaluation_ms": whole, "point_events_per_s": P * N / (whole * 1e-3),
+            "finite": finite, "max_abs_diff_vs_streaming_kernel_64_points": float(np.max(np.abs(r - r_s))),
+            "streaming_kernel_64_points_ms": stream_s * 1e3,
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4)", "ms": k2, "achieved": flops / (k2 * 1e-3) / 1e12,
+                         "unit": "TFLOP/s", "flops_alg_per_point_event": 2 * K, "share_of_evaluation": k2 / whole}}
+
+
 def other_configs(args, rank, world, device):
     """BASELINE configs 4 and 5 through the public API on the template-space engine (K5 / K5b), bounded sizes.
 
@@ -800,6 +860,9 @@ def other_configs(args, rank, world, device):
                   "the FP64 tensor pipe)",
         "bytes_per_event": 4 + 8 * eng.n_space, "n_events": int(N), **res5,
         "generate_s": gen_s, "set_data_s": set_data_s, "model_build_s": build_s}
+    del eng
+    torch.cuda.empty_cache()
+    out["config2_long_contraction"] = long_contraction_scan(device, args.steps)
     return out
 
 
@@ -1129,6 +1192,10 @@ def run_own_arm(args):
         del flush
         torch.cuda.empty_cache()
         other = other_configs(args, rank, world, device)
+        if other and other.get("config2_long_contraction"):
+            rl = other["config2_long_contraction"]["roofline"]
+            rl["peak"] = fp64_peak
+            rl["frac"] = rl["achieved"] / fp64_peak
 
     # ---- reduce over ranks -------------------------------------------------------------------------
     total_ms_max, e2e_total_max = total_ms, e2e_total
