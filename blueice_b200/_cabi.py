@@ -35,7 +35,7 @@ SIGNATURES = {
                                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                                 _f64, _c_void_p, _i32, _c_void_p, _c_void_p, _i64, _c_void_p,
                                                 _c_void_p]),
-    "bi_mma_unit_points": (_i32, [_i32]),
+    "bi_mma_unit_points": (_i32, [_i32, _i64]),
     "bi_mma_coef_chunks_doubles": (_i64, [_i32, _i64]),
     "bi_unbinned_workspace_bytes": (_i64, [_i32, _i32, _i32, _i64, _i64]),
     "bi_unbinned_workspace_layout": (ctypes.c_int, [_i32, _i32, _i32, _i64, _i64, _c_void_p]),

@@ -14,20 +14,34 @@ int bi_launch_mma_wide(const double* A, int64_t ld, int64_t N, int K, int S, con
 int bi_mma_wide_unit_points(void);
 int64_t bi_mma_wide_scratch_doubles(int K, int64_t n_points);
 
-#define BI_MMA_WIDE_MIN_TERMS_DEFAULT 49
+#define BI_MMA_WIDE_MIN_TERMS_DEFAULT 33
+#define BI_MMA_WIDE_MIN_POINTS_DEFAULT 1
 
-// Which of the two kernels (they give identical bits): measured on B200 over 4096-point scans of 1e5 events
-// (profiles/r2_wide_kernel.md) the per-warp rings win up to K = 32 (21.3 against 15.2 TFLOP/s), tie at K = 48 and lose
-// beyond (K = 64: 12.7 against 17.4; K = 80..128, one m-tile per warp: 5.7 / 4.7 against 18.4 / 19.3).  The environment
-// variable BI_MMA_WIDE_MIN_TERMS moves the threshold (tests and A/B runs).
-static bool bi_mma_use_wide(int n_terms) {
-    static int min_terms = -1;
+// Which of the two kernels (they give identical bits) -- K2 alone, measured on B200 (profiles/r2_wide_kernel.md):
+//  * 4096-point scans over 1e5 events: the per-warp rings win at K = 16 (22.2 against 17.0 TFLOP/s), the K-chunk kernel
+//    from K = 24 on (19.8 / 22.8 / 23.5 / 23.2 against 18.9 / 21.2 / 12.8 / 14.2 at K = 24 / 32 / 40 / 48; from K = 80 on the
+//    per-warp rings hold one m-tile per warp and fall to 5-6 TFLOP/s against 25-27);
+//  * P = 1 / 11 / 64 / 256 / 1024 points over datasets larger than L2: at K = 32 the per-warp rings are faster up to 1024
+//    points (0.065 / 0.19 / 0.33 / 0.79 / 2.80 ms against 0.097 / 0.40 / 0.78 / 1.10 / 2.98), at K = 64 and 128 the K-chunk
+//    kernel is faster at every batch size (K = 128: 0.11 / 0.38 / 0.76 / 1.49 / 2.90 ms against 0.21 / 0.79 / 1.75 / 4.25 / 14.1).
+// So the K-chunk kernel takes every contraction of more than 32 terms (the k-step count at which the per-warp rings leave
+// their register-resident B fragments).  Both thresholds -- terms, and points of the batch -- can be set in the
+// environment (tests, A/B runs); BI_MMA_WIDE_MIN_TERMS set in the environment applies to every batch size.
+static bool bi_mma_use_wide(int n_terms, int64_t n_points) {
+    static int min_terms = -1, min_points = -1;
+    static bool terms_forced = false;
     if (min_terms < 0) {
         const char* env = getenv("BI_MMA_WIDE_MIN_TERMS");
         const int v = env ? atoi(env) : 0;
-        min_terms = v >= 1 ? v : BI_MMA_WIDE_MIN_TERMS_DEFAULT;
+        terms_forced = v >= 1;
+        min_terms = terms_forced ? v : BI_MMA_WIDE_MIN_TERMS_DEFAULT;
+        const char* envp = getenv("BI_MMA_WIDE_MIN_POINTS");
+        const int vp = envp ? atoi(envp) : 0;
+        min_points = vp >= 1 ? vp : BI_MMA_WIDE_MIN_POINTS_DEFAULT;
     }
-    return n_terms >= min_terms || n_terms > BI_MMA_NARROW_MAX_TERMS;
+    if (n_terms > BI_MMA_NARROW_MAX_TERMS) return true;
+    if (n_terms < min_terms) return false;
+    return terms_forced || n_points >= min_points;
 }
 
 static int bi_mma_k4(int K) {
@@ -98,7 +112,7 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
     BI_REQUIRE(grid_dims < 0 || (grid_dims <= BI_MAX_DIMS && (grid_dims == 0 || (n_anchors_host && cell_dev))),
                "bi_unbinned_partials_mma: grid_dims needs n_anchors_host and cell_dev");
     cudaStream_t st = (cudaStream_t)stream;
-    if (bi_mma_use_wide(n_terms))
+    if (bi_mma_use_wide(n_terms, n_points))
         return bi_launch_mma_wide(rows_dev, ld_events, n_events, n_terms, n_sources, group_points_dev, groups_dev, header_dev,
                                   n_super, row_dev, coef_dev, wterm_dev, term_source_dev, mus_dev, outlier_likelihood,
                                   partial_dev, n_points, coef_chunks_dev, st);
@@ -126,12 +140,12 @@ extern "C" int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_event
 }
 
 extern "C" int64_t bi_mma_coef_chunks_doubles(int32_t n_terms, int64_t n_points) {
-    if (n_terms < 1 || n_points < 0 || !bi_mma_use_wide(n_terms)) return 0;
+    if (n_terms < 1 || n_points < 0 || !bi_mma_use_wide(n_terms, n_points)) return 0;
     return bi_mma_wide_scratch_doubles(n_terms, n_points);
 }
 
-extern "C" int32_t bi_mma_unit_points(int32_t n_terms) {
-    if (bi_mma_use_wide(n_terms)) return bi_mma_wide_unit_points();
+extern "C" int32_t bi_mma_unit_points(int32_t n_terms, int64_t n_points) {
+    if (bi_mma_use_wide(n_terms, n_points)) return bi_mma_wide_unit_points();
     const int k4 = bi_mma_k4(n_terms);
     return 8 * (k4 <= 2 ? BI_MMA_MT_SMALL : (k4 <= 4 ? 4 : (k4 <= 16 ? 2 : 1)));
 }
@@ -198,7 +212,7 @@ static int bi_unbinned_after_setup(int32_t n_dims, const int32_t* n_anchors_host
     double* partial = (double*)(base + w.partial);
     if (n_super > 0) {
         int rc = bi_unbinned_plan(n_dims, n_anchors_host, n_points, (int32_t*)(base + w.cell), status_dev,
-                                  bi_mma_unit_points(n_terms), n_events, target_units & 0x3fffffff, target_units >> 30,
+                                  bi_mma_unit_points(n_terms, n_points), n_events, target_units & 0x3fffffff, target_units >> 30,
                                   (int32_t*)(base + w.group_points), (int32_t*)(base + w.groups),
                                   (int32_t*)(base + w.header), stream);
         if (rc != BI_OK) return rc;

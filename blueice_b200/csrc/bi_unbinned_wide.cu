@@ -112,17 +112,16 @@ k_wide_pack_coef(const double* __restrict__ coef, const int32_t* __restrict__ gr
 // the DMMAs of one chunk: d[mt][n] += sum over the chunk's k-steps of A(point rows, terms 4 kk + t) x B(term rows 4 kk + t,
 // octet n); acol[mt] / bcol point at this lane's first elements.  FULL: all 32 terms of the chunk exist; otherwise k-steps
 // beyond K are skipped and terms beyond K (stale shared memory) read as 0
-template <bool FULL>
+// NMT: m-tiles of this warp that hold points (a warp with one live m-tile skips the DMMAs of the other: few-point batches)
+template <bool FULL, int NMT>
 __device__ __forceinline__ void bi_wide_chunk(const double* __restrict__ bcol, const double* const (&acol)[BI_WIDE_MT],
                                               double (&d)[BI_WIDE_MT][BI_WIDE_OCTETS][2], int k_left, int t) {
 #pragma unroll
     for (int kk = 0; kk < BI_WIDE_KC / 4; ++kk) {
         if (!FULL && 4 * kk >= k_left) break;
-        double a[BI_WIDE_MT], b[BI_WIDE_OCTETS];
+        double a[NMT], b[BI_WIDE_OCTETS];
 #pragma unroll
-        for (int mt = 0; mt < BI_WIDE_MT; ++mt) {
-            a[mt] = acol[mt][4 * kk];                                     // packed with zeros beyond K
-        }
+        for (int mt = 0; mt < NMT; ++mt) a[mt] = acol[mt][4 * kk];        // packed with zeros beyond K
 #pragma unroll
         for (int n = 0; n < BI_WIDE_OCTETS; ++n) {
             b[n] = bcol[4 * kk * BI_WIDE_RS + 8 * n];
@@ -131,7 +130,7 @@ __device__ __forceinline__ void bi_wide_chunk(const double* __restrict__ bcol, c
 #pragma unroll
         for (int n = 0; n < BI_WIDE_OCTETS; ++n)
 #pragma unroll
-            for (int mt = 0; mt < BI_WIDE_MT; ++mt) bi_dmma(d[mt][n][0], d[mt][n][1], a[mt], b[n]);
+            for (int mt = 0; mt < NMT; ++mt) bi_dmma(d[mt][n][0], d[mt][n][1], a[mt], b[n]);
     }
 }
 
@@ -212,6 +211,7 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
         const int64_t lead = slot_point[0];
         const int32_t* row_lead = row + lead * K;
         const bool warp_active = warp * BI_WIDE_MT * 8 < n_pts;           // warp-uniform
+        const bool two_tiles = (warp * BI_WIDE_MT + 1) * 8 < n_pts;       // warp-uniform: the second m-tile holds points
         bool live[BI_WIDE_MT];
         int64_t p_slot[BI_WIDE_MT];
         int a_off[BI_WIDE_MT];                                            // this lane's first coefficient inside a stage
@@ -250,8 +250,13 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
 #pragma unroll
                         for (int mt = 0; mt < BI_WIDE_MT; ++mt) acol[mt] = stage + a_off[mt];
                         const int k_left = K - ch * BI_WIDE_KC;
-                        if (k_left >= BI_WIDE_KC) bi_wide_chunk<true>(bcol, acol, d, k_left, t);
-                        else bi_wide_chunk<false>(bcol, acol, d, k_left, t);
+                        if (two_tiles) {
+                            if (k_left >= BI_WIDE_KC) bi_wide_chunk<true, 2>(bcol, acol, d, k_left, t);
+                            else bi_wide_chunk<false, 2>(bcol, acol, d, k_left, t);
+                        } else {
+                            if (k_left >= BI_WIDE_KC) bi_wide_chunk<true, 1>(bcol, acol, d, k_left, t);
+                            else bi_wide_chunk<false, 1>(bcol, acol, d, k_left, t);
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) bi_mbar_arrive(&empty_bar[st]);        // this warp is done with the stage

@@ -335,7 +335,7 @@ class UnbinnedEngine(_EngineBase):
         """Stage 2 of the fused path alone (bench / profiling): device-side schedule into the workspace views."""
         _cabi.check(self.lib.bi_unbinned_plan(
             self.grid.n_dims, _cabi.host_ptr(self.grid.n_anchors_i32), P, _cabi.dev_ptr(views["cell"]),
-            _cabi.dev_ptr(status_d), int(self.lib.bi_mma_unit_points(self.n_terms)), self.n_events,
+            _cabi.dev_ptr(status_d), int(self.lib.bi_mma_unit_points(self.n_terms, P)), self.n_events,
             _MMA_TARGET_UNITS & 0x3fffffff, _MMA_TARGET_UNITS >> 30,
             _cabi.dev_ptr(views["group_points"]), _cabi.dev_ptr(views["groups"]), _cabi.dev_ptr(views["header"]),
             self._stream()), "bi_unbinned_plan")

@@ -151,7 +151,7 @@ int bi_unbinned_partials_stream(const double* ps_anchor_dev, int64_t ld_events, 
 /*
  * Device-side schedule for bi_unbinned_partials_mma (no host round trip per batch).  Buckets the
  * evaluable points (status == 0) by hypercube cell and cuts them into point groups of at most
- * `unit_points` = bi_mma_unit_points(n_terms) points.
+ * `unit_points` = bi_mma_unit_points(n_terms, n_points) points.
  *   cell_dev / status_dev   outputs of bi_point_setup ([P, max(D, 1)] and [P])
  *   group_points_dev [P]    out: point indices, cell-major
  *   groups_dev [(P + 1) * 4] out: (first, count, range counter = 0, 0) per point group, 16-byte aligned
@@ -176,7 +176,7 @@ int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_po
  * (bi_point_setup / bi_point_setup_sourcewise write row / coef / wterm / term_source).
  *   rows_dev   [n_rows, ld_events] per-event pdf values, one row per (anchor, source); ld_events even
  *   group_points_dev / groups_dev / header_dev as written by bi_unbinned_plan (or by the caller: all
- *   points of a group MUST share their row list, have status 0, and count <= bi_mma_unit_points(n_terms);
+ *   points of a group MUST share their row list, have status 0, and count <= bi_mma_unit_points(n_terms, n_points);
  *   header_dev[4] and every group's range counter must be 0 on entry).  Requires n_terms <= BI_MMA_MAX_TERMS.
  * grid_dims >= 0 declares the full-grid layout (rows_dev = [G][S][ld] anchor tensor over grid_dims shape
  * parameters with n_anchors_host anchors each, term k = corner * S + source, cell_dev = bi_point_setup's cells):
@@ -184,7 +184,7 @@ int bi_unbinned_plan(int32_t n_dims, const int32_t* n_anchors_host, int64_t n_po
  * instead of one bulk copy per row.  grid_dims = -1: arbitrary row lists (source-wise interpolation).
  * Densities that leave [2^-126, 2^127) (zero, negative, NaN, inf ...) are re-evaluated with the
  * reference's nansum / outlier semantics from wterm / term_source / mus (likelihood.py:686-689).
- * Contractions of more than 128 terms run the K-chunk form of the kernel (k_unbinned_mma_wide: a CTA's four warps share
+ * Contractions of more than 32 terms run the K-chunk form of the kernel (k_unbinned_mma_wide: a CTA's four warps share
  * event tiles whose rows arrive in chunks of 32 through a CTA-wide TMA ring, accumulators carried across the chunks:
  * the same sequential fma chain over k); units are then (group, range) pairs taken in launch order, no counters used.
  * That kernel reads the coefficients from a chunk-major copy in schedule order which the call writes first
@@ -201,7 +201,7 @@ int bi_unbinned_partials_mma(const double* rows_dev, int64_t ld_events, int64_t 
                              double outlier_likelihood, double* partial_dev,
                              int32_t grid_dims, const int32_t* n_anchors_host, const int32_t* cell_dev,
                              int64_t n_points, double* coef_chunks_dev, void* stream);
-int32_t bi_mma_unit_points(int32_t n_terms);
+int32_t bi_mma_unit_points(int32_t n_terms, int64_t n_points);
 int64_t bi_mma_coef_chunks_doubles(int32_t n_terms, int64_t n_points);
 
 /*

@@ -16,7 +16,9 @@ from blueice_b200 import engine  # noqa: E402
 
 
 def main():
-    d, s, n, p = [int(v) for v in sys.argv[1:5]]
+    d, s, n = [int(v) for v in sys.argv[1:4]]
+    p_list = [int(v) for v in sys.argv[4].split(',')]
+    p = max(p_list)
     with_stream = len(sys.argv) > 5
     rng = np.random.default_rng(1)
     axes = [np.sort(rng.uniform(-2, 2, 3)) for _ in range(d)]
@@ -49,10 +51,43 @@ def main():
         out[key + "_points"] = pts
         out[key + "_ms"] = ms
         out[key + "_tflops"] = 2.0 * out["K"] * pts * n / (ms * 1e-3) / 1e12
+    if len(p_list) > 1:                      # a list of batch sizes: K2 alone at every size, one JSON line each
+        for pp in p_list:
+            o2 = dict(D=d, S=s, K=out["K"], N=n, P=pp, wide_min_terms=out["wide_min_terms"],
+                      wide_min_points=os.environ.get("BI_MMA_WIDE_MIN_POINTS"))
+            o2.update(k2_alone(eng, zs[:pp], mult[:pp], n, out["K"]))
+            print(json.dumps(o2))
+        return
+    out.update(k2_alone(eng, zs, mult, n, out["K"]))
     if with_stream:
         k = min(64, len(res['stream']))
         out["max_abs_diff_vs_stream"] = float(np.max(np.abs(res[None][:k] - res['stream'][:k])))
     print(json.dumps(out))
+
+
+def k2_alone(eng, zs, mult, n, K):
+    """K2 alone (coefficient packing included where the K-chunk kernel runs) on the workspace of a fused call."""
+    p = len(zs)
+    out = {}
+    eng.force_kernel = None
+    z_d, m_d, _, _, _ = eng._upload_points(zs, mult, None, None)
+    z_d, m_d = z_d.clone(), m_d.clone()
+    outs = eng.run_fused(p, z_d, m_d, None, None)
+    _, v = eng.mma_workspace(p)
+    ts = []
+    for _ in range(7):
+        eng.mma_plan(p, v, outs["status"])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.mma_k2(v)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    out["k2_ms"] = float(np.mean(ts[2:]))
+    out["k2_tflops"] = 2.0 * K * p * n / (out["k2_ms"] * 1e-3) / 1e12
+    out["k2_hbm_gbs_if_one_pass"] = 8.0 * K * n / (out["k2_ms"] * 1e-3) / 1e9
+    return out
 
 
 if __name__ == "__main__":
