@@ -282,20 +282,24 @@ np.savez(sys.argv[1], **out)
 
 
 def test_k_chunk_kernel_is_bitwise_identical_to_the_per_warp_kernel(tmp_path):
-    """BI_MMA_WIDE_MIN_TERMS=1 sends every contraction to the K-chunk kernel: same fma chain over k, same trees -> same bits
-    as the per-warp-ring kernel (the two runs are separate processes: the threshold is read once)."""
+    """BI_MMA_WIDE_MIN_TERMS=1 sends every contraction to the K-chunk kernel, BI_MMA_WIDE_MIN_POINTS=huge every contraction of
+    up to 128 terms to the per-warp-ring kernel: same fma chain over k, same trees -> same bits (the two runs are separate
+    processes: the thresholds are read once)."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    shapes = [(0, 1, 1000), (2, 2, 5000), (3, 3, 2048), (4, 8, 640), (1, 2, 33), (2, 9, 513)]
+    shapes = [(0, 1, 1000), (2, 2, 5000), (3, 3, 2048), (4, 8, 640), (1, 2, 33), (2, 9, 513), (3, 7, 1200), (4, 5, 700)]
     script = _WIDE_AB_SCRIPT % (root, shapes)
     res = {}
     for tag, val in (('narrow', None), ('wide', '1')):
         env = dict(os.environ)
         env.pop('BI_MMA_WIDE_MIN_TERMS', None)
+        env.pop('BI_MMA_WIDE_MIN_POINTS', None)
         if val:
             env['BI_MMA_WIDE_MIN_TERMS'] = val
+        else:
+            env['BI_MMA_WIDE_MIN_POINTS'] = '1000000000'
         env['BI_SMALL'] = '0'                       # keep the four-launch path for every batch size
         path = str(tmp_path / (tag + '.npz'))
         run = subprocess.run([sys.executable, '-c', script, path], env=env, cwd=root, capture_output=True, text=True)
