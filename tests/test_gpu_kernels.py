@@ -347,7 +347,10 @@ def test_nan_inf_zero_and_negative_densities(outlier):
 
 
 @pytest.mark.parametrize("source_dims,n", [([[0, 1], [1], []], 1000), ([[0], [1], [0, 1, 2], [2]], 777),
-                                           ([[], []], 100), ([[0, 1, 2, 3]], 513), ([[1], [0], [1], [0], [1]], 2049)])
+                                           ([[], []], 100), ([[0, 1, 2, 3]], 513), ([[1], [0], [1], [0], [1]], 2049),
+                                           # 45 and 135 contraction terms (odd counts): the K-chunk kernel on arbitrary row lists
+                                           ([[0, 1, 2]] * 5 + [[1]] * 2 + [[]], 700),
+                                           ([[0, 1, 2, 3]] * 8 + [[0, 2]] + [[3]] + [[]], 300)])
 def test_sourcewise_engine_matches_oracle(source_dims, n):
     """bi_point_setup_sourcewise + K2 against one RegularGridInterpolator per source (likelihood.py:210-240,534-555)."""
     engine = _engine_mod()
