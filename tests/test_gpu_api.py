@@ -764,3 +764,48 @@ def test_lean_paths_equal_the_general_path(monkeypatch):
         assert np.array_equal(a, b)
     assert results["1"][0][5] == -np.inf and results["1"][0][6] == -np.inf
     assert np.array_equal(results["1"][2], results["1"][0][[0, 5, 6, 9]])
+
+
+def test_long_contraction_model_through_the_api():
+    """3 shape parameters (8 corners per hypercube cell) x 5 sources = 40 contraction terms: ll.batch runs the K-chunk form of
+    K2 (more than 32 terms).  Scalar calls == batch rows bit for bit (the scalar path is the same kernel at P = 1), and the
+    batch agrees with the oracle evaluated on the engine's own per-event anchor tensor (likelihood.py:355-356,678-690)."""
+    from blueice_b200 import UnbinnedLogLikelihood
+    from blueice_b200.test_helpers import conf_for_test
+    from oracle.pipeline import UnbinnedOracle
+    lf = UnbinnedLogLikelihood(conf_for_test(n_sources=5, events_per_day=300.))
+    lf.add_shape_parameter('mu', (-0.5, 0., 0.5))
+    lf.add_shape_parameter('sigma', (0.8, 1., 1.3))
+    lf.add_shape_parameter('some_multiplier', (0.5, 1., 2.))
+    for i in range(5):
+        lf.add_rate_parameter('s%d' % i)
+    lf.prepare()
+    d = lf.base_model.simulate()
+    lf.set_data(d)
+    n = len(d)
+    eng = lf._engine
+    assert eng.n_terms == 40 and eng.uses_mma()
+    names = lf.parameter_names()
+    rng = np.random.default_rng(3)
+    P = 300
+    mult = rng.uniform(0.5, 2, (P, 5))
+    zs = np.column_stack([rng.uniform(-0.5, 0.5, P), rng.uniform(0.8, 1.3, P), rng.uniform(0.5, 2., P)])
+    zs[:3] = [[-0.5, 0.8, 0.5], [0., 1., 1.], [0.5, 1.3, 2.]]              # on anchors
+    table = np.column_stack([mult, zs])
+    got = lf.batch(table, names)
+    assert np.all(np.isfinite(got))
+    for i in (0, 1, 2, 17, 299):
+        assert lf(**dict(zip(names, [float(v) for v in table[i]]))) == got[i]
+    assert lf() == lf.batch(np.array([[1.] * 5 + [0., 1., 1.]]), names)[0]
+    axes = [np.asarray(a, dtype=float) for a in eng.grid.axes]
+    shape = [len(a) for a in axes]
+    ps = eng.ps_anchor[:, :, :n].cpu().numpy().reshape(shape + [5, n])
+    orc = UnbinnedOracle(axes, eng.mus_anchor_host.reshape(shape + [5])).set_ps(ps)
+    assert_vector_close(got, orc.batch(zs, mult), n)
+    table[7, 5] = 0.6                                                   # mu beyond its last anchor -> -inf
+    table[8, 0] = -1.0                                                  # unphysical rate -> -inf
+    out = lf.batch(table, names)
+    assert out[7] == -np.inf and out[8] == -np.inf
+    keep = np.ones(P, dtype=bool)
+    keep[[7, 8]] = False
+    assert np.array_equal(out[keep], got[keep])
