@@ -170,6 +170,9 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
             const int64_t lead = group_points[gp.x];
             const int32_t* row_lead = row + lead * K;                     // every point of the group has these rows
             const double* a_src = coef_chunks + (int64_t)gp.x * BI_WIDE_AS;   // + chunk * n_slots * AS
+            // coefficient rows of the m-tiles that hold points (a group of 32 points copies half the block)
+            const unsigned a_bytes = (unsigned)(((gp.y + 7) & ~7) < BI_WIDE_POINTS ? ((gp.y + 7) & ~7) : BI_WIDE_POINTS) *
+                                     (unsigned)(BI_WIDE_AS * sizeof(double));
             const int64_t sb_begin = (int64_t)range * sb_per;
             const int64_t sb_end = sb_begin + sb_per < n_super ? sb_begin + sb_per : n_super;
             for (int64_t sb = sb_begin; sb < sb_end; ++sb) {
@@ -185,9 +188,9 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
                         double* stage = ring + (size_t)st * BI_WIDE_STAGE_DOUBLES;
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         if (lane == 0) {
-                            bi_mbar_expect_tx(&full_bar[st], b_bytes * (unsigned)n_terms + BI_WIDE_A_DOUBLES * 8u);
-                            bi_bulk_g2s(stage + BI_WIDE_B_DOUBLES, a_src + (int64_t)ch * n_slots * BI_WIDE_AS,
-                                        BI_WIDE_A_DOUBLES * 8u, &full_bar[st]);
+                            bi_mbar_expect_tx(&full_bar[st], b_bytes * (unsigned)n_terms + a_bytes);
+                            bi_bulk_g2s(stage + BI_WIDE_B_DOUBLES, a_src + (int64_t)ch * n_slots * BI_WIDE_AS, a_bytes,
+                                        &full_bar[st]);
                         }
                         __syncwarp();
                         if (lane < n_terms)
@@ -210,15 +213,20 @@ k_unbinned_mma_wide(const double* __restrict__ A, int64_t ld, int64_t N, int K, 
         const int32_t* slot_point = group_points + gp.x;
         const int64_t lead = slot_point[0];
         const int32_t* row_lead = row + lead * K;
-        const bool warp_active = warp * BI_WIDE_MT * 8 < n_pts;           // warp-uniform
-        const bool two_tiles = (warp * BI_WIDE_MT + 1) * 8 < n_pts;       // warp-uniform: the second m-tile holds points
+        // m-tiles of this warp: two adjacent ones, or -- a group of at most 8 * WARPS points -- one per warp, so that a
+        // half-filled unit keeps all four warps issuing (a warp alone issues a DMMA every ~32 cycles, the pipe takes one
+        // every 16)
+        const bool spread = n_pts <= 8 * BI_WIDE_WARPS;
+        const int tile0 = spread ? warp : warp * BI_WIDE_MT;
+        const bool warp_active = tile0 * 8 < n_pts;                       // warp-uniform
+        const bool two_tiles = !spread && (tile0 + 1) * 8 < n_pts;        // warp-uniform: the second m-tile holds points
         bool live[BI_WIDE_MT];
         int64_t p_slot[BI_WIDE_MT];
         int a_off[BI_WIDE_MT];                                            // this lane's first coefficient inside a stage
 #pragma unroll
         for (int mt = 0; mt < BI_WIDE_MT; ++mt) {
-            const int idx = (warp * BI_WIDE_MT + mt) * 8 + g;
-            live[mt] = idx < n_pts;
+            const int idx = (tile0 + mt) * 8 + g;
+            live[mt] = idx < n_pts && (mt == 0 || !spread);
             p_slot[mt] = live[mt] ? (int64_t)slot_point[idx] : lead;      // dead slots replay the group's first point
             a_off[mt] = BI_WIDE_B_DOUBLES + idx * BI_WIDE_AS + t;
         }
