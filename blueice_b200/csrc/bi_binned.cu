@@ -358,7 +358,12 @@ __device__ __forceinline__ void bi_binned_tile_body(const BiBinnedArgs& a, unsig
         const int tile_bins = (int)min((int64_t)NB, a.ld - bin0);            // even (ld is)
         if (tid == 0) bi_mbar_expect_tx(bar, (unsigned)(n_rows * tile_bins * 8));
         const int64_t lead = gcache ? 0 : a.group_points[first];             // the group's cell = its first point's
-        for (int r = tid; r < n_rows; r += NT) {
+        // a bulk copy is issued lane by lane (uniform-register operands): row r goes to lane r / n_warps of warp r % n_warps,
+        // so the copies of a tile are spread over all warps instead of serialised in the first one or two
+#ifndef BI_BINNED_SPREAD_COPIES
+#define BI_BINNED_SPREAD_COPIES 1
+#endif
+        for (int r = BI_BINNED_SPREAD_COPIES ? lane * (NT / 32) + warp : tid; r < n_rows; r += NT) {
             const int k = r / C, c = r - k * C;
             const int64_t anchor = gcache ? s_ganchor[g][c] : a.corner[lead * C + c];
             const double* src;
