@@ -708,7 +708,7 @@ def other_configs(args, rank, world, device):
         out["config1_gaussian"]["cpu_port_events"] = int(len(x1))
     del ll1
     # ---- config 3 (binned + Beeston-Barlow; K4) ----
-    from blueice_b200.engine import BinnedEngine, MorphGrid
+    from blueice_b200.engine import BinnedEngine, MorphGrid, capture_graph
     t0 = time.perf_counter()
     axes, edges, mus3, pmf, n_model, observed = wl.c3_arrays((200, 200, 20), 4, 3, (-1., 0., 1.), seed=3)
     beng = BinnedEngine(MorphGrid(axes), mus3.reshape(27, 4), pmf, n_model, 0)
@@ -730,7 +730,7 @@ def other_configs(args, rank, world, device):
             beng.run_device(P, zs_d, mult_d, None, None)
         torch.cuda.synchronize()
         g3 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g3, capture_error_mode="thread_local"):
+        with capture_graph(torch, g3):
             beng.run_device(P, zs_d, mult_d, None, None)
         dm = []
         for k in range(8):
@@ -871,7 +871,7 @@ def run_own_arm(args):
     import torch
     import torch.distributed as dist
     from blueice_b200 import _cabi
-    from blueice_b200.engine import MorphGrid, UnbinnedEngine
+    from blueice_b200.engine import MorphGrid, UnbinnedEngine, capture_graph
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -947,7 +947,7 @@ def run_own_arm(args):
         try:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            with capture_graph(torch, g):
                 logl_static = eng.run_device(P, zs_d, mult_d, None, None, plan, plan_dev)
             step_graph = g
         except Exception:

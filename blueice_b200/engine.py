@@ -12,7 +12,9 @@ Per batch of P points (workspace, reused between calls):
     zs [P, D], mult [P, S], scale [P], eff [P, S] -> cell [P, D], frac [P, D], corner [P, C],
     weight [P, C], mus [P, S], musum [P], status [P], partial [P, n_super], logl [P]
 """
+import contextlib
 import ctypes
+import gc
 import os
 import sys
 import time as _time
@@ -27,6 +29,25 @@ _LD_ALIGN = 64
 def _torch():
     import torch
     return torch
+
+
+@contextlib.contextmanager
+def capture_graph(torch, graph):
+    """torch.cuda.graph(graph) with Python's cyclic collector switched off for the duration of the capture.
+
+    A collection that happens to fire inside a capture destroys whatever garbage is around at that moment -- engines of
+    earlier evaluations with their pinned buffers and CUDA graphs -- and those destructors call CUDA APIs a capturing
+    thread must not call: the error is raised inside a destructor and the process aborts (seen once in eight full runs of
+    the GPU tests, in the capture of BinnedEngine.evaluate's third call).  torch collects before the capture starts; this
+    keeps it from collecting again until the capture has ended."""
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 def require_cuda():
@@ -595,7 +616,7 @@ class UnbinnedEngine(_EngineBase):
         try:
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
+            with capture_graph(torch, g):
                 self._fused_sequence(st, n_f, torch.cuda.current_stream(self.device), slot)
             graph = g
         except Exception:                                           # capture not possible here: stay on the eager path
@@ -1085,7 +1106,7 @@ class BinnedEngine(_EngineBase):
                     torch.cuda.current_stream(self.device).synchronize()
                     launches = self.launches
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    with capture_graph(torch, g):
                         device_sequence()
                     entry["graph"], entry["version"], entry["n_launch"] = g, self.ws.version, self.launches - launches
                     self.launches = launches
@@ -1672,7 +1693,7 @@ class TemplateUnbinnedEngine(_EngineBase):
                 try:                                                # the first calls size the workspace buffers eagerly
                     torch.cuda.current_stream(self.device).synchronize()
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
+                    with capture_graph(torch, g):
                         device_sequence()
                     entry["graph"] = g
                     entry["ptrs"] = self.ws.version

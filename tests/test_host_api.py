@@ -316,3 +316,41 @@ def test_install_as_blueice_aliases_the_reference_import_paths():
     env["PYTHONPATH"] = root                       # the reference is NOT on the path: every name must come from the alias
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr
+
+
+def test_capture_graph_keeps_the_cyclic_collector_off_during_a_capture():
+    """engine.capture_graph: a collection inside a CUDA graph capture runs destructors that call CUDA APIs a capturing thread
+    must not call (the process aborts); the collector is off inside the capture and restored afterwards, also on errors."""
+    import gc
+    seen = []
+
+    class FakeGraphContext(object):
+        def __init__(self, graph, capture_error_mode=None):
+            seen.append(('mode', capture_error_mode))
+
+        def __enter__(self):
+            seen.append(('inside', gc.isenabled()))
+
+        def __exit__(self, *exc):
+            return False
+
+    class FakeTorch(object):
+        class cuda(object):
+            graph = FakeGraphContext
+
+    assert gc.isenabled()
+    with engine.capture_graph(FakeTorch, object()):
+        assert not gc.isenabled()
+    assert gc.isenabled()
+    with pytest.raises(RuntimeError):
+        with engine.capture_graph(FakeTorch, object()):
+            raise RuntimeError("capture failed")
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with engine.capture_graph(FakeTorch, object()):
+            pass
+        assert not gc.isenabled()                    # a caller that runs with the collector off keeps it off
+    finally:
+        gc.enable()
+    assert ('mode', 'thread_local') in seen and ('inside', False) in seen
