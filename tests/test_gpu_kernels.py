@@ -210,6 +210,23 @@ def test_results_do_not_depend_on_batch_shape_or_order():
     assert eng.evaluate(zs[:0], mult[:0]).shape == (0,)
 
 
+def test_six_shape_parameters_against_the_oracle():
+    """6 shape parameters: 64 corners per hypercube cell (x 2 sources = 128 terms, x 3 = 192) -- beyond the streaming kernel's
+    32 corners, so the only cross-check is the oracle (scipy's RegularGridInterpolator over the 6-D anchor grid)."""
+    for s_count, n in ((2, 700), (3, 300)):
+        rng = np.random.default_rng(66 + s_count)
+        axes, mus_anchor, ps_anchor = make_case(rng, 6, s_count, n, anchors_per_dim=2)
+        eng = build_engine(axes, mus_anchor, ps_anchor)
+        assert eng.n_terms == 64 * s_count and eng.uses_mma()
+        p = 90
+        zs = random_points(rng, axes, p)
+        mult = rng.uniform(0.5, 2, (p, s_count))
+        got = eng.evaluate(zs, mult)
+        orc = UnbinnedOracle(axes, mus_anchor).set_ps(ps_anchor)
+        assert_logl_close(got, orc.batch(zs, mult), n, "6 shape parameters, %d sources" % s_count)
+        assert eng.evaluate(zs[5:6], mult[5:6])[0] == got[5]
+
+
 def test_wide_contraction_results_do_not_depend_on_batch_shape_or_order():
     """160 contraction terms (5 shape parameters x 5 sources): the K-chunk kernel, whose units are CTA-wide groups of 64
     points -- a point alone, in a permuted batch or in a slice of the batch gives the same bits."""
