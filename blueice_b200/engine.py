@@ -373,6 +373,11 @@ class UnbinnedEngine(_EngineBase):
             _cabi.dev_ptr(views["coef_chunks"]), self._stream()),
             "bi_unbinned_partials_mma")
 
+    def _k2_sequence_launches(self, P):
+        """Kernels of one fused evaluation: K1, schedule, K2, finalize -- plus the coefficient packing of the K-chunk kernel
+        (contractions of more than 32 terms)."""
+        return 5 if int(self.lib.bi_mma_coef_chunks_doubles(self.n_terms, P)) > 0 else 4
+
     def _small_ok(self, P):
         """True when bi_unbinned_ll_batch evaluates a P-point batch with its single fused launch (tiny batches)."""
         if os.environ.get('BI_SMALL') == '0' or self.n_events <= 0 or not self.uses_mma():
@@ -401,7 +406,7 @@ class UnbinnedEngine(_EngineBase):
                    musum=self.ws.get("musum", P, torch.float64), status=self.ws.get("status", P, torch.int32))
         fn, args = self._fused_args(P, zs_d, mult_d, scale_d, eff_d, ws, out)
         _cabi.check(fn(*args, self._stream()), fn.__name__)
-        self.launches += 1 if self._small_ok(P) else (4 if self.n_super > 0 else 2)
+        self.launches += 1 if self._small_ok(P) else (self._k2_sequence_launches(P) if self.n_super > 0 else 2)
         return out
 
     def scalar_runner(self, has_scale):
@@ -653,7 +658,7 @@ class UnbinnedEngine(_EngineBase):
         else:
             self._fused_sequence(st, n_f, stream)
         self.launches += 1 if st["zero_copy"] else \
-            (4 if self.n_super > 0 else 2) + (0 if pg is None or pg.fallback is not None else 1)
+            (self._k2_sequence_launches(P) if self.n_super > 0 else 2) + (0 if pg is None or pg.fallback is not None else 1)
         stream.synchronize()
         self.last_gathered = self.last_total = None
         self.last_gathered_owned = True                 # (copies of the scratch slot)
