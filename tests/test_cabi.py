@@ -83,3 +83,24 @@ def test_argument_validation_reports_errors_without_a_gpu():
     rc = lib.bi_hist_lookup(None, 1, 1, _cabi.host_ptr(_cabi.as_i32([4])), _cabi.host_ptr(_cabi.as_f64(np.arange(5.))),
                             None, 0, 0, 9, None, 0, None, None)
     assert rc == -1 and b"method" in lib.bi_last_error()
+
+
+def test_kernel_choice_and_workspace_of_long_contractions():
+    """Host-side rules of K2 (no device needed): contractions of more than 32 terms run the K-chunk kernel -- units of 64
+    points, a chunk-major copy of the coefficients ([chunk][slot][36], 64 slots of padding) as the last workspace region."""
+    lib = _cabi.load()
+    for k in (1, 8, 16):
+        assert lib.bi_mma_unit_points(k, 4096) == 32 and lib.bi_mma_coef_chunks_doubles(k, 100) == 0
+    assert lib.bi_mma_unit_points(32, 4096) == 16 and lib.bi_mma_coef_chunks_doubles(32, 100) == 0
+    for k in (33, 48, 128, 129, 160, _cabi.MMA_MAX_TERMS):
+        assert lib.bi_mma_unit_points(k, 4096) == 64 and lib.bi_mma_unit_points(k, 1) == 64
+        chunks = -(-k // 32)
+        assert lib.bi_mma_coef_chunks_doubles(k, 100) == chunks * (100 + 64) * 36
+    off = np.zeros(15, dtype=np.int64)
+    assert lib.bi_unbinned_workspace_layout(5, 5, 160, 4096, 50000, _cabi.host_ptr(off)) == 0
+    assert np.all(np.diff(off) >= 0) and np.all(off % 256 == 0)
+    assert off[14] == lib.bi_unbinned_workspace_bytes(5, 5, 160, 4096, 50000)
+    assert off[14] - off[13] >= 8 * lib.bi_mma_coef_chunks_doubles(160, 4096) > 0
+    off8 = np.zeros(15, dtype=np.int64)
+    assert lib.bi_unbinned_workspace_layout(2, 2, 8, 4096, 99957, _cabi.host_ptr(off8)) == 0
+    assert off8[14] == off8[13]                                      # short contractions: no such region
