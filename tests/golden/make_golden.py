@@ -266,6 +266,36 @@ def golden_reparam():
          shape_parameters=np.array(list(lf.shape_parameters.keys())))
 
 
+# ---------------------------------------------------------------------------------------------
+# G7: a model with a long contraction -- 3 shape parameters (8 corners per hypercube cell) x 5 sources = 40 terms per
+# point-event, the regime of the K-chunk form of K2 (more than 32 terms)
+# ---------------------------------------------------------------------------------------------
+def golden_long_contraction():
+    lf = UnbinnedLogLikelihood(conf_for_test(n_sources=5, events_per_day=300.))
+    lf.add_shape_parameter('mu', (-0.5, 0., 0.5))
+    lf.add_shape_parameter('sigma', (0.8, 1., 1.3))
+    lf.add_shape_parameter('some_multiplier', (0.5, 1., 2.))
+    for i in range(5):
+        lf.add_rate_parameter('s%d' % i)
+    lf.prepare()
+    np.random.seed(7)
+    d = lf.base_model.simulate()
+    lf.set_data(d)
+    names = ['s%d_rate_multiplier' % i for i in range(5)] + ['mu', 'sigma', 'some_multiplier']
+    rng = np.random.default_rng(8)
+    P = 40
+    table = np.column_stack([rng.uniform(0.5, 2., (P, 5)), rng.uniform(-0.5, 0.5, P), rng.uniform(0.8, 1.3, P),
+                             rng.uniform(0.5, 2., P)])
+    table[0] = [1.] * 5 + [0., 1., 1.]                       # the base model
+    table[1, 5:] = [-0.5, 0.8, 0.5]                          # anchors
+    table[2, 5:] = [0.5, 1.3, 2.]
+    table[3, 5] = 0.75                                       # out of range -> -inf
+    table[4, 0] = -1.                                        # unphysical -> -inf
+    table[5, :5] = 0.                                        # every event an outlier
+    logl = np.array([lf(**dict(zip(names, [float(v) for v in row]))) for row in table])
+    save('long_contraction', x=d['x'], params=table, logl=logl, names=np.array(names))
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -279,3 +309,4 @@ if __name__ == '__main__':
     golden_multisource()
     golden_sourcewise()
     golden_reparam()
+    golden_long_contraction()

@@ -155,6 +155,31 @@ def test_golden_multisource():
     assert_vector_close(lf.batch(g['params'], names), g['logl'], len(d))
 
 
+def test_golden_long_contraction():
+    """3 shape parameters x 5 sources = 40 contraction terms (the K-chunk form of K2) against values of the unmodified
+    reference (tests/golden/make_golden.py: golden_long_contraction)."""
+    from blueice_b200 import UnbinnedLogLikelihood
+    from blueice_b200.test_helpers import conf_for_test
+    g = load_golden('long_contraction')
+    lf = UnbinnedLogLikelihood(conf_for_test(n_sources=5, events_per_day=300.))
+    lf.add_shape_parameter('mu', (-0.5, 0., 0.5))
+    lf.add_shape_parameter('sigma', (0.8, 1., 1.3))
+    lf.add_shape_parameter('some_multiplier', (0.5, 1., 2.))
+    for i in range(5):
+        lf.add_rate_parameter('s%d' % i)
+    lf.prepare()
+    d = np.zeros(len(g['x']), dtype=[('x', float), ('source', int)])
+    d['x'] = g['x']
+    lf.set_data(d)
+    assert lf._engine.n_terms == 40
+    names = [str(v) for v in g['names']]
+    got = lf.batch(g['params'], names)
+    assert np.isneginf(g['logl']).sum() == 2
+    assert_vector_close(got, g['logl'], len(d))
+    for i in (0, 1, 5, 17):                                  # scalar calls: the same bits as the batch rows
+        assert lf(**dict(zip(names, [float(v) for v in g['params'][i]]))) == got[i]
+
+
 def test_golden_sourcewise():
     """source_wise_interpolation (likelihood.py:113-145,210-240,534-555): s0 on (mu, sigma), s1 on sigma, s2 on nothing."""
     from blueice_b200 import UnbinnedLogLikelihood
