@@ -104,3 +104,27 @@ def test_kernel_choice_and_workspace_of_long_contractions():
     off8 = np.zeros(15, dtype=np.int64)
     assert lib.bi_unbinned_workspace_layout(2, 2, 8, 4096, 99957, _cabi.host_ptr(off8)) == 0
     assert off8[14] == off8[13]                                      # short contractions: no such region
+
+
+def test_ctypes_signatures_have_the_header_s_parameter_counts_and_kinds():
+    """Every prototype of include/blueice_b200.h against its ctypes mirror: number of parameters, and pointer / integer /
+    floating-point kind of each (a mismatch corrupts the call silently)."""
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = dict(re.findall(r"\b(bi_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S))
+    checked = 0
+    for name, (restype, argtypes) in _cabi.SIGNATURES.items():
+        assert name in protos, name
+        params = [p.strip() for p in protos[name].split(",")] if protos[name].strip() not in ("", "void") else []
+        assert len(params) == len(argtypes), "%s: header has %d parameters, ctypes %d" % (name, len(params), len(argtypes))
+        for p, t in zip(params, argtypes):
+            if "*" in p:
+                assert t in (ctypes.c_void_p, ctypes.c_char_p), (name, p, t)
+            elif re.search(r"\b(double|float)\b", p):
+                assert t is ctypes.c_double, (name, p, t)
+            elif re.search(r"\bint64_t\b|\buint64_t\b", p):
+                assert ctypes.sizeof(t) == 8 and t is not ctypes.c_double and t is not ctypes.c_void_p, (name, p, t)
+            else:
+                assert ctypes.sizeof(t) == 4, (name, p, t)
+        checked += 1
+    assert checked >= 40
