@@ -83,6 +83,13 @@ def test_argument_validation_reports_errors_without_a_gpu():
     rc = lib.bi_hist_lookup(None, 1, 1, _cabi.host_ptr(_cabi.as_i32([4])), _cabi.host_ptr(_cabi.as_f64(np.arange(5.))),
                             None, 0, 0, 9, None, 0, None, None)
     assert rc == -1 and b"method" in lib.bi_last_error()
+    # a long contraction without the chunk-major coefficient buffer, and more terms than any kernel takes
+    p = ctypes.c_void_p(256)
+    rc = lib.bi_unbinned_partials_mma(p, 64, 64, 160, 5, p, p, p, p, p, p, p, p, 1e-12, p, -1, None, None, 10, None, None)
+    assert rc == -1 and b"coef_chunks_dev" in lib.bi_last_error()
+    rc = lib.bi_unbinned_partials_mma(p, 64, 64, _cabi.MMA_MAX_TERMS + 1, 5, p, p, p, p, p, p, p, p, 1e-12, p, -1, None, None,
+                                      10, p, None)
+    assert rc == -1 and b"contraction terms" in lib.bi_last_error()
 
 
 def test_kernel_choice_and_workspace_of_long_contractions():
